@@ -1,0 +1,121 @@
+// bssm_common.cuh -- shared device utilities: Philox4x32-10, noise keying, math wrappers.
+// Self-contained (no host headers) so the same text compiles under nvcc and NVRTC.
+#pragma once
+
+#ifndef __CUDACC_RTC__
+#include <stdint.h>
+#else
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#endif
+
+#define BSSM_DEV __device__ __forceinline__
+#define BSSM_HD __host__ __device__ __forceinline__
+
+namespace bssm {
+
+// ---- noise tags (the oracle restates the same table) ----
+enum : uint32_t {
+  TAG_INIT_Z = 1, TAG_TRANS_Z = 2, TAG_TRANS2_Z = 3, TAG_RESAMP_U = 4, TAG_RESAMP_AUX_U = 5,
+  TAG_MOVE_Z = 6, TAG_MOVE_U = 7, TAG_TRANS_U = 8, TAG_TRANS2_U = 9, TAG_INIT_U = 10,
+  TAG_THETA_Z = 16, TAG_THETA_U = 17
+};
+constexpr uint32_t T_INIT = 0xFFFFFFFFu;
+
+struct uint4x { uint32_t w[4]; };
+
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011).
+BSSM_HD uint4x philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  uint4x o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
+
+struct NoiseKey {
+  uint32_t k0, k1;   // (seed_lo, seed_hi ^ run_id)
+  uint32_t stream;   // filter / chain id
+};
+BSSM_HD NoiseKey make_key(uint64_t seed, uint32_t run_id, uint32_t stream) {
+  NoiseKey k; k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32) ^ run_id; k.stream = stream; return k;
+}
+// words for the quad containing particle `index` (index>>2)
+BSSM_HD uint4x noise_quad(const NoiseKey& k, uint32_t t, uint32_t tag, uint32_t slot, uint32_t quad) {
+  return philox4x32_10(quad, t, k.stream, tag | (slot << 8), k.k0, k.k1);
+}
+BSSM_HD double word_to_unit_f64(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+BSSM_HD float word_to_unit_f32(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// ---- math wrappers templated on the state precision ----
+template <typename Real> struct Math;
+template <> struct Math<double> {
+  static BSSM_DEV double unit(uint32_t w) { return word_to_unit_f64(w); }
+  static BSSM_DEV void box_muller(uint32_t a, uint32_t b, double& n0, double& n1) {
+    double u1 = word_to_unit_f64(a), u2 = word_to_unit_f64(b);
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincos(2.0 * 3.14159265358979323846 * u2, &s, &c);
+    n0 = r * c; n1 = r * s;
+  }
+  static BSSM_DEV double exp_(double x) { return exp(x); }
+  static BSSM_DEV double log_(double x) { return log(x); }
+  static BSSM_DEV double sin_(double x) { return sin(x); }
+  static BSSM_DEV double cos_(double x) { return cos(x); }
+  static BSSM_DEV double ninf() { return -__longlong_as_double(0x7FF0000000000000LL); }
+};
+template <> struct Math<float> {
+  static BSSM_DEV float unit(uint32_t w) { return word_to_unit_f32(w); }
+  static BSSM_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float u1 = word_to_unit_f32(a), u2 = word_to_unit_f32(b);
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);  // argument in [0, 2pi): fast path is accurate here
+    n0 = r * c; n1 = r * s;
+  }
+  static BSSM_DEV float exp_(float x) { return __expf(x); }
+  static BSSM_DEV float log_(float x) { return logf(x); }
+  static BSSM_DEV float sin_(float x) { return sinf(x); }
+  static BSSM_DEV float cos_(float x) { return cosf(x); }
+  static BSSM_DEV float ninf() { return -__int_as_float(0x7F800000); }
+};
+
+// R densities
+template <typename Real> BSSM_DEV Real dnorm_log(Real x, Real mu, Real sigma, Real log_sigma) {
+  Real z = (x - mu) / sigma;
+  return -((Real)0.918938533204672741780329736406 + (Real)0.5 * z * z + log_sigma);
+}
+template <typename Real> BSSM_DEV Real dpois_log(Real y, Real lambda) {
+  if (lambda == (Real)0) return (y == (Real)0) ? (Real)0 : Math<Real>::ninf();
+  return y * Math<Real>::log_(lambda) - lambda - (Real)lgamma((double)y + 1.0);
+}
+// Binomial(n, p) by sequential cdf inversion from one uniform; always double (matches the oracle)
+BSSM_DEV double binom_inversion(double nd, double p, double u) {
+  int n = (int)nd;
+  if (n <= 0 || p <= 0) return 0.0;
+  if (p >= 1) return (double)n;
+  double q = 1.0 - p, r = p / q;
+  double pmf = exp((double)n * log1p(-p));
+  double cdf = pmf;
+  int k = 0;
+  while (u > cdf && k < n) {
+    k++;
+    pmf *= ((double)(n - k + 1) / (double)k) * r;
+    cdf += pmf;
+  }
+  return (double)k;
+}
+
+}  // namespace bssm
