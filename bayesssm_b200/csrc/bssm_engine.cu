@@ -1,0 +1,589 @@
+// bssm_engine.cu -- C ABI of libbayesssm_b200.so: context, resamplers, particle filters.
+// (PMMH lives in bssm_pmmh.cu, the persistent bootstrap-filter kernel in bssm_fast.cu.)
+// No CPU fallback anywhere: every entry point needs a CUDA device.
+#include "bssm_engine.cuh"
+
+#include <stdarg.h>
+
+namespace bssm {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int scratch_get(bssm_ctx* ctx, int slot, size_t bytes, void** out) {
+  Scratch& s = ctx->scratch[slot];
+  if (bytes == 0) bytes = 16;
+  if (s.cap < bytes) {
+    if (s.p) { BSSM_CK(cudaStreamSynchronize(ctx->stream)); BSSM_CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
+    size_t cap = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&s.p, cap);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+      s.p = nullptr;
+      return BSSM_ERR_CUDA;
+    }
+    s.cap = cap;
+  }
+  *out = s.p;
+  return BSSM_OK;
+}
+
+int check_launch(bssm_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed (%s): %s", what, cudaGetErrorString(e));
+    return BSSM_ERR_CUDA;
+  }
+  return BSSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cdf pipeline
+// ---------------------------------------------------------------------------------------------
+__global__ void k_zero_sum_check(const double* total, int nseg, int* status, const int* enable) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg || !seg_on(enable, s)) return;
+  if (status && status[s] == 0 && total[s] == 0.0) status[s] = BSSM_ERR_ZERO_SUM;
+}
+
+template <typename Src, typename MakeNorm>
+int resample_cdf(bssm_ctx* ctx, const Src& src, MakeNorm make_norm, const RsArgs& a) {
+  const int ntiles = (a.n + RS_TILE - 1) / RS_TILE;
+  double* part; TileRec* rec; double* cstart; int* used; double* total;
+  BSSM_TRY(scratch(ctx, SL_RS_PART, (size_t)a.nseg * ntiles, &part));
+  BSSM_TRY(scratch(ctx, SL_RS_REC, (size_t)a.nseg * ntiles, &rec));
+  BSSM_TRY(scratch(ctx, SL_RS_CSTART, (size_t)a.nseg * ntiles, &cstart));
+  BSSM_TRY(scratch(ctx, SL_RS_USED, (size_t)a.nseg * ntiles, &used));
+  if (a.total) total = a.total; else BSSM_TRY(scratch(ctx, SL_RS_TOTAL, (size_t)a.nseg, &total));
+  dim3 grid(ntiles, a.nseg);
+  cudaStream_t st = ctx->stream;
+  k_tile_sums<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.status, a.validate, a.enable);
+  BSSM_LAUNCH(ctx, "k_tile_sums");
+  if (!a.exact) {
+    k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.cdf, a.cdf_stride, rec, 0, a.enable);
+    BSSM_LAUNCH(ctx, "k_tile_scan");
+    return BSSM_OK;
+  }
+  // pass 1: exact sequential total of the raw weights (src/resampling.cpp:20,47)
+  k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable);
+  BSSM_LAUNCH(ctx, "k_tile_scan");
+  k_chain<Src><<<a.nseg, 32, 0, st>>>(src, a.n, a.n_per, ntiles, rec, cstart, used, total, nullptr, 0, nullptr, a.enable);
+  BSSM_LAUNCH(ctx, "k_chain");
+  if (a.status) {
+    k_zero_sum_check<<<(a.nseg + 127) / 128, 128, 0, st>>>(total, a.nseg, a.status, a.enable);
+    BSSM_LAUNCH(ctx, "k_zero_sum_check");
+  }
+  // pass 2: exact sequential cumsum of w / total (src/resampling.cpp:24-25,51-52)
+  auto srcn = make_norm(total);
+  typedef decltype(srcn) SrcN;
+  k_tile_sums<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, part, nullptr, 0, a.enable);
+  BSSM_LAUNCH(ctx, "k_tile_sums");
+  k_tile_scan<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable);
+  BSSM_LAUNCH(ctx, "k_tile_scan");
+  k_chain<SrcN><<<a.nseg, 32, 0, st>>>(srcn, a.n, a.n_per, ntiles, rec, cstart, used, part /* pass-2 total (~1) is not needed; must not overwrite `total` */,
+                                       a.cdf, a.cdf_stride, a.n_serial, a.enable);
+  BSSM_LAUNCH(ctx, "k_chain");
+  k_tile_exact<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, cstart, used, a.cdf, a.cdf_stride, a.enable);
+  BSSM_LAUNCH(ctx, "k_tile_exact");
+  return BSSM_OK;
+}
+
+static int resample_cdf_plain(bssm_ctx* ctx, const double* d_w, size_t w_stride, const RsArgs& a) {
+  SrcPlain src{d_w, w_stride};
+  return resample_cdf(ctx, src, [=](const double* total) { return SrcPlainNorm{d_w, w_stride, total}; }, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle filter orchestration
+// ---------------------------------------------------------------------------------------------
+struct FilterLaunch {
+  int model, precision, resample_fn, exact, hist, T;
+};
+
+template <typename Real>
+static int resample_stage(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int obs, int aux_stage, double* cdf) {
+  RsArgs a;
+  a.nseg = f.C; a.n = f.N; a.n_per = f.n_per; a.enable = f.resample; a.cdf = cdf; a.cdf_stride = (size_t)f.N;
+  a.status = nullptr; a.validate = 0; a.exact = L.exact; a.n_serial = nullptr; a.total = nullptr;
+  const Real* lw = (const Real*)(aux_stage ? f.lw_aux : f.lw);
+  const double *M = f.M, *S = f.S;
+  size_t stride = (size_t)f.N;
+  SrcLogW<Real> src{lw, stride, M, S};
+  BSSM_TRY(resample_cdf(ctx, src, [=](const double* total) { return SrcLogWNorm<Real>{lw, stride, M, S, total}; }, a));
+  USrcFilter us;
+  us.buf = aux_stage ? f.noise.u_resample_aux : f.noise.u_resample;
+  us.N = f.N; us.injected = f.noise.injected; us.seed = f.seed; us.run_id = f.run_id; us.stream = f.stream;
+  us.tag = aux_stage ? TAG_RESAMP_AUX_U : TAG_RESAMP_U; us.obs = obs;
+  dim3 grid(f.nblk, f.C);
+  k_search_gather<Real><<<grid, FT_THREADS, 0, ctx->stream>>>(f, us, L.resample_fn, obs, aux_stage, cdf);
+  BSSM_LAUNCH(ctx, "k_search_gather");
+  k_flip<<<(f.C + 127) / 128, 128, 0, ctx->stream>>>(f);
+  BSSM_LAUNCH(ctx, "k_flip");
+  return BSSM_OK;
+}
+
+template <typename Model, typename Real>
+static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
+  dim3 grid(f.nblk, f.C);
+  cudaStream_t st = ctx->stream;
+  k_init<Model, Real><<<grid, FT_THREADS, 0, st>>>(f);
+  BSSM_LAUNCH(ctx, "k_init");
+  k_finalize<<<f.C, 128, 0, st>>>(f, 0, 0);
+  BSSM_LAUNCH(ctx, "k_finalize");
+  if (L.hist) { k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, 0); BSSM_LAUNCH(ctx, "k_history"); }
+  const bool may_resample = (f.algorithm == BSSM_RMPF) || (f.ralg != BSSM_SIS);
+  for (int obs = 0; obs < L.T; obs++) {
+    if (f.algorithm == BSSM_APF) {
+      if (!Model::HAS_AUX) { set_error("model has no aux_log_likelihood_fn"); return BSSM_ERR_UNSUPPORTED; }
+      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_GAP, 1);
+      BSSM_LAUNCH(ctx, "k_weight");
+      k_finalize<<<f.C, 128, 0, st>>>(f, obs, 2);
+      BSSM_LAUNCH(ctx, "k_finalize");
+      BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 1, cdf));
+      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_SECOND, 2);
+      BSSM_LAUNCH(ctx, "k_weight");
+    } else {
+      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_GAP, 0);
+      BSSM_LAUNCH(ctx, "k_weight");
+    }
+    k_finalize<<<f.C, 128, 0, st>>>(f, obs, 1);
+    BSSM_LAUNCH(ctx, "k_finalize");
+    if (may_resample) {
+      BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 0, cdf));
+      k_post<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs);
+      BSSM_LAUNCH(ctx, "k_post");
+      k_finalize<<<f.C, 128, 0, st>>>(f, obs, 3);
+      BSSM_LAUNCH(ctx, "k_finalize");
+    }
+    if (L.hist) { k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, obs + 1); BSSM_LAUNCH(ctx, "k_history"); }
+  }
+  return BSSM_OK;
+}
+
+template <typename Model>
+static int run_filter_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
+  if (L.precision == BSSM_F64) return run_filter_steps<Model, double>(ctx, f, L, cdf);
+  return run_filter_steps<Model, float>(ctx, f, L, cdf);
+}
+
+int model_dims(int model, int* d, int* ntheta, int* nconst) {
+#define MD(M) { *d = M::D; *ntheta = M::NTHETA; *nconst = M::NCONST; return BSSM_OK; }
+  switch (model) {
+    case BSSM_MODEL_AR_SIN: MD(ModelArSin)
+    case BSSM_MODEL_LG: MD(ModelLG)
+    case BSSM_MODEL_RW_DRIFT: MD(ModelRwDrift)
+    case BSSM_MODEL_SIR_CB: MD(ModelSirCB)
+    case BSSM_MODEL_AR_COS: MD(ModelArCos)
+    case BSSM_MODEL_RW2D: MD(ModelRw2D)
+  }
+#undef MD
+  set_error("unknown model id %d", model);
+  return BSSM_ERR_BAD_ARG;
+}
+
+// enqueue one batched filter run on ctx->stream (no synchronisation)
+int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
+  switch (L.model) {
+    case BSSM_MODEL_AR_SIN: return run_filter_model<ModelArSin>(ctx, f, L, cdf);
+    case BSSM_MODEL_LG: return run_filter_model<ModelLG>(ctx, f, L, cdf);
+    case BSSM_MODEL_RW_DRIFT: return run_filter_model<ModelRwDrift>(ctx, f, L, cdf);
+    case BSSM_MODEL_SIR_CB: return run_filter_model<ModelSirCB>(ctx, f, L, cdf);
+    case BSSM_MODEL_AR_COS: return run_filter_model<ModelArCos>(ctx, f, L, cdf);
+    case BSSM_MODEL_RW2D: return run_filter_model<ModelRw2D>(ctx, f, L, cdf);
+  }
+  set_error("unknown model id %d", L.model);
+  return BSSM_ERR_BAD_ARG;
+}
+
+__global__ void k_fill_ids(unsigned int* stream, unsigned int* run_id, int C, unsigned int stream_base, unsigned int rid) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { stream[c] = stream_base + (unsigned int)c; run_id[c] = rid; }
+}
+__global__ void k_fill_int(int* p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_fill_uniform(double* p, size_t n, unsigned long long seed) {
+  NoiseKey key = make_key(seed, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint4x q = noise_quad(key, (unsigned int)(i >> 34), 0x55u, 0u, (unsigned int)(i >> 2));
+    p[i] = word_to_unit_f64(q.w[i & 3]);
+  }
+}
+
+// allocate the per-batch state of a filter run inside the context's scratch slots
+int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out) {
+  const size_t C = f.C, N = f.N, d = f.d, T = f.T;
+  const size_t rs = L.precision == BSSM_F64 ? 8 : 4;
+  f.nblk = (int)((N + FT_THREADS - 1) / FT_THREADS);
+  if (f.nblk > 1024) f.nblk = 1024;
+  if (f.nblk < 1) f.nblk = 1;
+  BSSM_TRY(scratch_get(ctx, SL_F_XA, C * d * N * rs, &f.xa));
+  BSSM_TRY(scratch_get(ctx, SL_F_XB, C * d * N * rs, &f.xb));
+  BSSM_TRY(scratch_get(ctx, SL_F_LW, C * N * rs, &f.lw));
+  if (need_aux) {
+    BSSM_TRY(scratch_get(ctx, SL_F_LWAUX, C * N * rs, &f.lw_aux));
+    BSSM_TRY(scratch_get(ctx, SL_F_AUXG, C * N * rs, &f.auxg));
+  } else { f.lw_aux = nullptr; f.auxg = nullptr; }
+  BSSM_TRY(scratch(ctx, SL_F_PART, C * f.nblk * PART_W, &f.part));
+  BSSM_TRY(scratch(ctx, SL_F_CDF, C * N, cdf_out));
+  double* sd; int* si;
+  BSSM_TRY(scratch(ctx, SL_F_SCAL_D, C * 4, &sd));
+  BSSM_TRY(scratch(ctx, SL_F_SCAL_I, C * 6, &si));
+  f.M = sd; f.S = sd + C; f.loglike = sd + 2 * C; f.cur_ess = sd + 3 * C;
+  f.alive = si; f.resample = si + C; f.status = si + 2 * C; f.early_exit = si + 3 * C; f.n_resampled = si + 4 * C; f.cur = si + 5 * C;
+  BSSM_TRY(scratch(ctx, SL_F_ESS, C * (T + 1), &f.ess));
+  BSSM_TRY(scratch(ctx, SL_F_SEST, C * (T + 1) * d, &f.state_est));
+  BSSM_TRY(scratch(ctx, SL_F_LLH, C * (T ? T : 1), &f.loglike_history));
+  if (L.hist) {
+    BSSM_TRY(scratch(ctx, SL_F_PH, C * (T + 1) * d * N, &f.particles_history));
+    BSSM_TRY(scratch(ctx, SL_F_WH, C * (T + 1) * N, &f.weights_history));
+  } else { f.particles_history = nullptr; f.weights_history = nullptr; }
+  if (want_anc) {
+    BSSM_TRY(scratch(ctx, SL_F_ANC, C * (T ? T : 1) * N, &f.anc_history));
+    BSSM_CK(cudaMemsetAsync(f.anc_history, 0, C * T * N * sizeof(int), ctx->stream));
+    if (need_aux) {
+      BSSM_TRY(scratch(ctx, SL_F_ANCA, C * (T ? T : 1) * N, &f.anc_aux_history));
+      BSSM_CK(cudaMemsetAsync(f.anc_aux_history, 0, C * T * N * sizeof(int), ctx->stream));
+    } else f.anc_aux_history = nullptr;
+  } else { f.anc_history = nullptr; f.anc_aux_history = nullptr; }
+  return BSSM_OK;
+}
+
+// reset the per-run state (outputs zero-filled as the reference's early-exit return, :189-202)
+int filter_reset(bssm_ctx* ctx, FilterDev& f, const int* d_active) {
+  const size_t C = f.C, T = f.T, d = f.d;
+  cudaStream_t st = ctx->stream;
+  BSSM_CK(cudaMemsetAsync(f.M, 0, C * 4 * sizeof(double), st));
+  BSSM_CK(cudaMemsetAsync(f.alive, 0, C * 6 * sizeof(int), st));
+  if (d_active) BSSM_CK(cudaMemcpyAsync(f.alive, d_active, C * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  else { k_fill_int<<<(int)((C + 255) / 256), 256, 0, st>>>(f.alive, (int)C, 1); BSSM_LAUNCH(ctx, "k_fill_int"); }
+  BSSM_CK(cudaMemsetAsync(f.ess, 0, C * (T + 1) * sizeof(double), st));
+  BSSM_CK(cudaMemsetAsync(f.state_est, 0, C * (T + 1) * d * sizeof(double), st));
+  if (f.loglike_history) BSSM_CK(cudaMemsetAsync(f.loglike_history, 0, C * T * sizeof(double), st));
+  return BSSM_OK;
+}
+
+}  // namespace bssm
+
+using namespace bssm;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int bssm_abi_version(void) { return BSSM_ABI_VERSION; }
+const char* bssm_last_error(void) { return g_err; }
+
+int bssm_create(int device, bssm_ctx** out) {
+  if (!out) { set_error("bssm_create: out is NULL"); return BSSM_ERR_BAD_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    set_error("no CUDA device available (%s); this engine has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return BSSM_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(device));
+  bssm_ctx* ctx = new bssm_ctx();
+  ctx->device = device;
+  BSSM_CK(cudaGetDeviceProperties(&ctx->prop, device));
+  BSSM_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  BSSM_CK(cudaEventCreate(&ctx->ev0));
+  BSSM_CK(cudaEventCreate(&ctx->ev1));
+  *out = ctx;
+  return BSSM_OK;
+}
+
+void bssm_destroy(bssm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < SL_COUNT; i++) if (ctx->scratch[i].p) cudaFree(ctx->scratch[i].p);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int bssm_device_info(bssm_ctx* ctx, char* name, int* sm_count, int* cc_major, int* cc_minor, size_t* global_mem) {
+  if (!ctx) { set_error("null context"); return BSSM_ERR_BAD_ARG; }
+  if (name) { strncpy(name, ctx->prop.name, 255); name[255] = 0; }
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (cc_major) *cc_major = ctx->prop.major;
+  if (cc_minor) *cc_minor = ctx->prop.minor;
+  if (global_mem) *global_mem = ctx->prop.totalGlobalMem;
+  return BSSM_OK;
+}
+int64_t bssm_launch_count(bssm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int bssm_synchronize(bssm_ctx* ctx) {
+  BSSM_CK(cudaSetDevice(ctx->device));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  return BSSM_OK;
+}
+int bssm_timer_start(bssm_ctx* ctx) { BSSM_CK(cudaEventRecord(ctx->ev0, ctx->stream)); return BSSM_OK; }
+int bssm_timer_stop(bssm_ctx* ctx, float* ms_out) {
+  BSSM_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  BSSM_CK(cudaEventSynchronize(ctx->ev1));
+  BSSM_CK(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+  return BSSM_OK;
+}
+
+int bssm_dev_alloc(bssm_ctx* ctx, size_t bytes, void** d_ptr) {
+  BSSM_CK(cudaSetDevice(ctx->device));
+  BSSM_CK(cudaMalloc(d_ptr, bytes ? bytes : 16));
+  return BSSM_OK;
+}
+int bssm_dev_free(bssm_ctx* ctx, void* d_ptr) {
+  BSSM_CK(cudaSetDevice(ctx->device));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  BSSM_CK(cudaFree(d_ptr));
+  return BSSM_OK;
+}
+int bssm_dev_upload(bssm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  BSSM_CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  return BSSM_OK;
+}
+int bssm_dev_download(bssm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  BSSM_CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  return BSSM_OK;
+}
+int bssm_dev_fill_uniform(bssm_ctx* ctx, double* d_ptr, size_t n, uint64_t seed) {
+  k_fill_uniform<<<1184, 256, 0, ctx->stream>>>(d_ptr, n, seed);
+  BSSM_LAUNCH(ctx, "k_fill_uniform");
+  return BSSM_OK;
+}
+
+// ---- resamplers -------------------------------------------------------------------------------
+int bssm_resample_device(bssm_ctx* ctx, int resample_fn, int batch, int n, const double* d_weights, const double* d_u,
+                         int32_t* d_idx_out, int* d_status) {
+  if (!ctx || batch <= 0 || n <= 0 || !d_weights || !d_u || !d_idx_out) { set_error("bssm_resample_device: bad argument"); return BSSM_ERR_BAD_ARG; }
+  if (resample_fn < 0 || resample_fn > 2) { set_error("unknown resample_fn %d", resample_fn); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  double* cdf;
+  BSSM_TRY(scratch(ctx, SL_API_CDF, (size_t)batch * n, &cdf));
+  int* status = d_status;
+  if (!status) BSSM_TRY(scratch(ctx, SL_RS_STATUS, (size_t)batch, &status));
+  BSSM_CK(cudaMemsetAsync(status, 0, sizeof(int) * batch, ctx->stream));
+  RsArgs a;
+  a.nseg = batch; a.n = n; a.n_per = nullptr; a.enable = nullptr; a.cdf = cdf; a.cdf_stride = (size_t)n;
+  a.status = status; a.validate = 1; a.exact = 1; a.n_serial = nullptr; a.total = nullptr;
+  BSSM_TRY(resample_cdf_plain(ctx, d_weights, (size_t)n, a));
+  USrcBuf us{d_u, resample_fn == BSSM_SYSTEMATIC ? (size_t)1 : (size_t)n};
+  int gx = (n + 255) / 256; if (gx > 4096) gx = 4096;
+  k_search<USrcBuf><<<dim3(gx, batch), 256, 0, ctx->stream>>>(us, resample_fn, n, nullptr, cdf, (size_t)n, d_idx_out, (size_t)n, nullptr);
+  BSSM_LAUNCH(ctx, "k_search");
+  return BSSM_OK;
+}
+
+static int resample_host(bssm_ctx* ctx, int fn, int n, const double* w, const double* u, int nu, int32_t* idx_out) {
+  if (!ctx || n <= 0 || !w || !u || !idx_out) { set_error("resample: bad argument (n must be >= 1)"); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  double *dw, *du; int32_t* di; int* dst;
+  BSSM_TRY(scratch(ctx, SL_API_W, (size_t)n, &dw));
+  BSSM_TRY(scratch(ctx, SL_API_U, (size_t)nu, &du));
+  BSSM_TRY(scratch(ctx, SL_API_IDX, (size_t)n, &di));
+  BSSM_TRY(scratch(ctx, SL_RS_STATUS, (size_t)1, &dst));
+  BSSM_CK(cudaMemcpyAsync(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  BSSM_CK(cudaMemcpyAsync(du, u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
+  BSSM_TRY(bssm_resample_device(ctx, fn, 1, n, dw, du, di, dst));
+  int status = 0;
+  BSSM_CK(cudaMemcpyAsync(&status, dst, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BSSM_CK(cudaMemcpyAsync(idx_out, di, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  if (status == BSSM_ERR_NEGATIVE_WEIGHT) { set_error("Weights must be non-negative"); return status; }
+  if (status == BSSM_ERR_ZERO_SUM) { set_error("Sum of weights must be greater than 0"); return status; }
+  if (status == BSSM_ERR_NAN_WEIGHT) { set_error("Weights must not be NaN"); return status; }
+  return BSSM_OK;
+}
+int bssm_resample_stratified(bssm_ctx* ctx, int n, const double* weights, const double* u, int32_t* idx_out) {
+  return resample_host(ctx, BSSM_STRATIFIED, n, weights, u, n, idx_out);
+}
+int bssm_resample_systematic(bssm_ctx* ctx, int n, const double* weights, double u, int32_t* idx_out) {
+  return resample_host(ctx, BSSM_SYSTEMATIC, n, weights, &u, 1, idx_out);
+}
+int bssm_resample_multinomial(bssm_ctx* ctx, int n, const double* weights, const double* u, int32_t* idx_out) {
+  return resample_host(ctx, BSSM_MULTINOMIAL, n, weights, u, n, idx_out);
+}
+
+int bssm_resample_cdf(bssm_ctx* ctx, int n, const double* weights, double* cdf_out, double* total_out, int64_t* n_serial_out) {
+  if (!ctx || n <= 0 || !weights) { set_error("bssm_resample_cdf: bad argument"); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  double *dw, *cdf, *total; int* dst; long long* dser;
+  BSSM_TRY(scratch(ctx, SL_API_W, (size_t)n, &dw));
+  BSSM_TRY(scratch(ctx, SL_API_CDF, (size_t)n, &cdf));
+  BSSM_TRY(scratch(ctx, SL_RS_STATUS, (size_t)1, &dst));
+  BSSM_TRY(scratch(ctx, SL_RS_TOTAL, (size_t)1, &total));
+  BSSM_TRY(scratch(ctx, SL_RS_NSERIAL, (size_t)1, &dser));
+  BSSM_CK(cudaMemcpyAsync(dw, weights, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  BSSM_CK(cudaMemsetAsync(dst, 0, sizeof(int), ctx->stream));
+  RsArgs a;
+  a.nseg = 1; a.n = n; a.n_per = nullptr; a.enable = nullptr; a.cdf = cdf; a.cdf_stride = (size_t)n;
+  a.status = dst; a.validate = 1; a.exact = 1; a.n_serial = dser; a.total = total;
+  BSSM_TRY(resample_cdf_plain(ctx, dw, (size_t)n, a));
+  int status = 0; long long ser = 0;
+  BSSM_CK(cudaMemcpyAsync(&status, dst, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BSSM_CK(cudaMemcpyAsync(&ser, dser, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cdf_out) BSSM_CK(cudaMemcpyAsync(cdf_out, cdf, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (total_out) BSSM_CK(cudaMemcpyAsync(total_out, total, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  if (n_serial_out) *n_serial_out = ser;
+  if (status) { set_error("invalid weights (status %d)", status); return status; }
+  return BSSM_OK;
+}
+
+// ---- particle filters -------------------------------------------------------------------------
+int bssm_model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst) {
+  (void)ctx;
+  int dd, nt, nc;
+  BSSM_TRY(model_dims(model, &dd, &nt, &nc));
+  if (d) *d = dd;
+  if (ntheta) *ntheta = nt;
+  if (nconst) *nconst = nc;
+  return BSSM_OK;
+}
+
+static int upload_opt(bssm_ctx* ctx, int slot, const double* h, size_t count, const double** d_out) {
+  *d_out = nullptr;
+  if (!h || !count) return BSSM_OK;
+  double* d;
+  BSSM_TRY(scratch(ctx, slot, count, &d));
+  BSSM_CK(cudaMemcpyAsync(d, h, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = d;
+  return BSSM_OK;
+}
+
+static int filter_validate(const bssm_filter_config* cfg) {
+  if (cfg->num_particles < 1) { set_error("Assertion on 'num_particles' failed: must be >= 1"); return BSSM_ERR_BAD_ARG; }
+  if (cfg->num_obs < 0 || cfg->dy < 1 || cfg->dy > 4) { set_error("bad y dimensions (T=%d, dy=%d)", cfg->num_obs, cfg->dy); return BSSM_ERR_BAD_ARG; }
+  if (cfg->num_filters < 1) { set_error("num_filters must be >= 1"); return BSSM_ERR_BAD_ARG; }
+  if (cfg->algorithm < 0 || cfg->algorithm > 2 || cfg->resample_algorithm < 0 || cfg->resample_algorithm > 2 ||
+      cfg->resample_fn < 0 || cfg->resample_fn > 2) { set_error("unknown algorithm / resample_algorithm / resample_fn"); return BSSM_ERR_BAD_ARG; }
+  if (cfg->obs_times) {
+    int prev = 0;
+    for (int i = 0; i < cfg->num_obs; i++) {
+      if (cfg->obs_times[i] < prev) { set_error("obs_times must be non-decreasing positive integers"); return BSSM_ERR_BAD_ARG; }
+      prev = cfg->obs_times[i];
+    }
+  }
+  return BSSM_OK;
+}
+
+int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* y, const double* theta, bssm_filter_result* res) {
+  if (!ctx || !cfg || !y || !theta || !res) { set_error("bssm_filter_run: null argument"); return BSSM_ERR_BAD_ARG; }
+  BSSM_TRY(filter_validate(cfg));
+  BSSM_CK(cudaSetDevice(ctx->device));
+  int d, nth, nc;
+  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  const int C = cfg->num_filters, N = cfg->num_particles, T = cfg->num_obs;
+  FilterDev f;
+  memset(&f, 0, sizeof(f));
+  f.C = C; f.N = N; f.T = T; f.dy = cfg->dy; f.d = d; f.n_per = nullptr;
+  f.theta_stride = nth + nc; f.seed = cfg->seed;
+  f.algorithm = cfg->algorithm;
+  f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->resample_algorithm;
+  f.threshold = cfg->threshold;
+  FilterLaunch L;
+  L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
+  L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
+  L.hist = cfg->return_particles; L.T = T;
+  const bool need_aux = cfg->algorithm == BSSM_APF;
+  const bool want_anc = res->ancestors_history != nullptr || res->ancestors_aux_history != nullptr;
+  double* cdf;
+  BSSM_TRY(filter_setup(ctx, f, L, need_aux, want_anc, &cdf));
+  // inputs
+  double* d_theta; double* d_y; int* d_obs = nullptr; unsigned int* ids;
+  BSSM_TRY(scratch(ctx, SL_F_THETA, (size_t)C * f.theta_stride, &d_theta));
+  BSSM_TRY(scratch(ctx, SL_F_Y, (size_t)(T ? T : 1) * cfg->dy, &d_y));
+  BSSM_TRY(scratch(ctx, SL_F_IDS, (size_t)2 * C, &ids));
+  BSSM_CK(cudaMemcpyAsync(d_theta, theta, sizeof(double) * C * f.theta_stride, cudaMemcpyHostToDevice, ctx->stream));
+  if (T) BSSM_CK(cudaMemcpyAsync(d_y, y, sizeof(double) * T * cfg->dy, cudaMemcpyHostToDevice, ctx->stream));
+  if (cfg->obs_times && T) {
+    BSSM_TRY(scratch(ctx, SL_F_OBS, (size_t)T, &d_obs));
+    BSSM_CK(cudaMemcpyAsync(d_obs, cfg->obs_times, sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  f.theta = d_theta; f.y = d_y; f.obs_times = d_obs; f.stream = ids; f.run_id = ids + C;
+  k_fill_ids<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ids, ids + C, C, cfg->stream_base, cfg->run_id);
+  BSSM_LAUNCH(ctx, "k_fill_ids");
+  // injected noise
+  memset(&f.noise, 0, sizeof(f.noise));
+  if (cfg->noise) {
+    const bssm_noise_buffers* nb = cfg->noise;
+    int n_time = T ? (cfg->obs_times ? cfg->obs_times[T - 1] : T) : 0;
+    const size_t NN = (size_t)N;
+    // slot counts come from the model; the caller sized the buffers with bssm_model_noise_dims
+    int nzi, nui, nzt, nut, nzm, num;
+    BSSM_TRY(bssm_model_noise_dims(ctx, cfg->model, &nzi, &nui, &nzt, &nut, &nzm, &num));
+    f.noise.injected = 1;
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 0, nb->z_init, nzi * NN, &f.noise.z_init));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 1, nb->u_init, nui * NN, &f.noise.u_init));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 2, nb->z_trans, (size_t)n_time * nzt * NN, &f.noise.z_trans));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 3, nb->u_trans, (size_t)n_time * nut * NN, &f.noise.u_trans));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 4, nb->z_trans2, (size_t)T * nzt * NN, &f.noise.z_trans2));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 5, nb->u_trans2, (size_t)T * nut * NN, &f.noise.u_trans2));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 6, nb->u_resample, (size_t)T * NN, &f.noise.u_resample));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 7, nb->u_resample_aux, (size_t)T * NN, &f.noise.u_resample_aux));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 8, nb->z_move, (size_t)T * nzm * NN, &f.noise.z_move));
+    BSSM_TRY(upload_opt(ctx, SL_F_NOISE0 + 9, nb->u_move, (size_t)T * num * NN, &f.noise.u_move));
+    bool ok = (nzi == 0 || f.noise.z_init) && (nui == 0 || f.noise.u_init) && (nzt == 0 || f.noise.z_trans) &&
+              (nut == 0 || f.noise.u_trans);
+    if (cfg->algorithm == BSSM_APF) ok = ok && (nzt == 0 || f.noise.z_trans2) && (nut == 0 || f.noise.u_trans2) && f.noise.u_resample_aux;
+    if (cfg->algorithm == BSSM_RMPF) ok = ok && (nzm == 0 || f.noise.z_move) && (num == 0 || f.noise.u_move);
+    if (f.ralg != BSSM_SIS) ok = ok && f.noise.u_resample;
+    if (!ok) { set_error("injected noise: a buffer this model/algorithm consumes is NULL"); return BSSM_ERR_BAD_ARG; }
+  }
+  BSSM_TRY(filter_reset(ctx, f, nullptr));
+  BSSM_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  BSSM_TRY(filter_enqueue(ctx, f, L, cdf));
+  BSSM_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  // outputs
+  cudaStream_t st = ctx->stream;
+  const size_t T1 = (size_t)T + 1;
+#define DL(dst, src, count, type) if (dst) BSSM_CK(cudaMemcpyAsync(dst, src, (count) * sizeof(type), cudaMemcpyDeviceToHost, st))
+  DL(res->loglike, f.loglike, (size_t)C, double);
+  DL(res->loglike_history, f.loglike_history, (size_t)C * T, double);
+  DL(res->ess, f.ess, (size_t)C * T1, double);
+  DL(res->state_est, f.state_est, (size_t)C * T1 * d, double);
+  if (cfg->return_particles) {
+    DL(res->particles_history, f.particles_history, (size_t)C * T1 * d * N, double);
+    DL(res->weights_history, f.weights_history, (size_t)C * T1 * N, double);
+  }
+  DL(res->status, f.status, (size_t)C, int);
+  DL(res->early_exit, f.early_exit, (size_t)C, int);
+  DL(res->n_resampled, f.n_resampled, (size_t)C, int);
+  if (want_anc) {
+    DL(res->ancestors_history, f.anc_history, (size_t)C * T * N, int);
+    if (need_aux) DL(res->ancestors_aux_history, f.anc_aux_history, (size_t)C * T * N, int);
+  }
+#undef DL
+  BSSM_CK(cudaStreamSynchronize(st));
+  BSSM_CK(cudaEventElapsedTime(&res->kernel_ms, ctx->ev0, ctx->ev1));
+  return BSSM_OK;
+}
+
+int bssm_model_noise_dims(bssm_ctx* ctx, int model, int* nz_init, int* nu_init, int* nz_trans, int* nu_trans, int* nz_move, int* nu_move) {
+  (void)ctx;
+#define ND(M) { *nz_init = M::NZ_INIT; *nu_init = M::NU_INIT; *nz_trans = M::NZ_TRANS; *nu_trans = M::NU_TRANS; *nz_move = M::NZ_MOVE; *nu_move = M::NU_MOVE; return BSSM_OK; }
+  switch (model) {
+    case BSSM_MODEL_AR_SIN: ND(ModelArSin)
+    case BSSM_MODEL_LG: ND(ModelLG)
+    case BSSM_MODEL_RW_DRIFT: ND(ModelRwDrift)
+    case BSSM_MODEL_SIR_CB: ND(ModelSirCB)
+    case BSSM_MODEL_AR_COS: ND(ModelArCos)
+    case BSSM_MODEL_RW2D: ND(ModelRw2D)
+  }
+#undef ND
+  set_error("unknown model id %d", model);
+  return BSSM_ERR_BAD_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// bssm_engine.cuh -- host-side context, scratch memory and launch helpers shared by the
+// translation units of libbayesssm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bayesssm_b200.h"
+#include "bssm_filter.cuh"
+#include "bssm_resample.cuh"
+
+namespace bssm {
+
+void set_error(const char* fmt, ...);
+
+#define BSSM_CK(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      bssm::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      return BSSM_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+#define BSSM_TRY(call)            \
+  do {                            \
+    int s__ = (call);             \
+    if (s__ != BSSM_OK) return s__; \
+  } while (0)
+
+// growable device scratch buffers owned by the context
+enum ScratchSlot {
+  SL_RS_PART = 0, SL_RS_REC, SL_RS_CSTART, SL_RS_USED, SL_RS_TOTAL, SL_RS_NSERIAL, SL_RS_STATUS,
+  SL_API_W, SL_API_U, SL_API_IDX, SL_API_CDF,
+  SL_F_XA, SL_F_XB, SL_F_LW, SL_F_LWAUX, SL_F_AUXG, SL_F_PART, SL_F_CDF, SL_F_SCAL_D, SL_F_SCAL_I,
+  SL_F_ESS, SL_F_SEST, SL_F_LLH, SL_F_PH, SL_F_WH, SL_F_ANC, SL_F_ANCA, SL_F_THETA, SL_F_Y, SL_F_OBS,
+  SL_F_IDS, SL_F_NOISE0, /* 10 noise slots */
+  SL_F_NOISE_LAST = SL_F_NOISE0 + 9,
+  SL_P_BASE, /* PMMH slots */
+  SL_P_LAST = SL_P_BASE + 23,
+  SL_FAST_BASE,
+  SL_FAST_LAST = SL_FAST_BASE + 7,
+  SL_COUNT
+};
+
+struct Scratch { void* p = nullptr; size_t cap = 0; };
+
+}  // namespace bssm
+
+struct bssm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaDeviceProp prop;
+  int64_t launches = 0;
+  bssm::Scratch scratch[bssm::SL_COUNT];
+  std::string compile_log;
+  void* nvrtc_state = nullptr;
+};
+
+namespace bssm {
+
+int scratch_get(bssm_ctx* ctx, int slot, size_t bytes, void** out);
+template <typename T> inline int scratch(bssm_ctx* ctx, int slot, size_t count, T** out) {
+  void* p = nullptr;
+  int st = scratch_get(ctx, slot, count * sizeof(T), &p);
+  *out = (T*)p;
+  return st;
+}
+int check_launch(bssm_ctx* ctx, const char* what);
+
+#define BSSM_LAUNCH(ctx, what)                       \
+  do {                                               \
+    (ctx)->launches++;                               \
+    BSSM_TRY(bssm::check_launch((ctx), what));       \
+  } while (0)
+
+// cdf of `nseg` weight vectors (see bssm_resample.cuh).  Src yields the weights, SrcN the
+// weights divided by the exact total (only used when exact != 0).
+struct RsArgs {
+  int nseg, n;             // n = stride / max length
+  const int* n_per;        // [nseg] or nullptr
+  const int* enable;       // [nseg] or nullptr
+  double* cdf; size_t cdf_stride;
+  int* status;             // [nseg] validation result (atomicMax) or nullptr
+  int validate;
+  int exact;
+  long long* n_serial;     // [nseg] or nullptr: elements the chain walked serially (diagnostic)
+  double* total;           // [nseg] out (exact: sequential sum of the raw weights)
+};
+
+}  // namespace bssm

@@ -40,7 +40,8 @@ extern "C" {
 enum { BSSM_BPF = 0, BSSM_APF = 1, BSSM_RMPF = 2 };            /* pf_wrapper identity */
 enum { BSSM_SIS = 0, BSSM_SISR = 1, BSSM_SISAR = 2 };          /* resample_algorithm  */
 enum { BSSM_STRATIFIED = 0, BSSM_SYSTEMATIC = 1, BSSM_MULTINOMIAL = 2 }; /* resample_fn */
-enum { BSSM_F32 = 0, BSSM_F64 = 1 };                           /* state / weight precision (cdf is always f64) */
+enum { BSSM_F32 = 0, BSSM_F64 = 1 };
+enum { BSSM_ENGINE_AUTO = 0, BSSM_ENGINE_GENERAL = 1, BSSM_ENGINE_PERSISTENT = 2 };                           /* state / weight precision (cdf is always f64) */
 enum {
   BSSM_MODEL_AR_SIN = 0,   /* README.md:137-146                       theta = (phi, sigma_x, sigma_y) */
   BSSM_MODEL_LG = 1,       /* tests/testthat/test-pmmh_tuning.R:163   theta = (phi, sigma_x, sigma_y) */
@@ -132,8 +133,9 @@ typedef struct {
   uint32_t stream_base;   /* filter c uses Philox stream stream_base + c */
   const bssm_noise_buffers *noise; /* NULL => Philox */
   int return_particles;   /* fill particles_history / weights_history */
-  int ctas_per_filter;    /* 0 => auto */
-  int block_threads;      /* 0 => auto */
+  int exact_resampling;   /* 1: cdf bit-exact vs the sequential reference cumsum; 0: plain parallel fp64 scan;
+                             -1 => auto (1 for BSSM_F64, 0 for BSSM_F32) */
+  int engine;             /* BSSM_ENGINE_AUTO / GENERAL / PERSISTENT */
 } bssm_filter_config;
 
 typedef struct {
@@ -147,10 +149,15 @@ typedef struct {
   int32_t *status;           /* [C] BSSM_OK / BSSM_ERR_NAN_WEIGHT ... */
   int32_t *early_exit;       /* [C] 1 if all log-weights < -1e8 (R/particle_filter_core.R:189-202) */
   int32_t *n_resampled;      /* [C] steps where (second-stage) resampling fired */
+  int32_t *ancestors_history;     /* [C][T][N] 1-based, 0 where no resampling (test aid; general engine) */
+  int32_t *ancestors_aux_history; /* [C][T][N] APF first stage */
   float kernel_ms;           /* device time of the engine launch (CUDA events) */
 } bssm_filter_result;
 
 int bssm_model_dims(bssm_ctx *ctx, int model, int *d, int *ntheta, int *nconst);
+/* normals / uniforms one particle consumes in init, one transition, one RMPF move (sizes of bssm_noise_buffers) */
+int bssm_model_noise_dims(bssm_ctx *ctx, int model, int *nz_init, int *nu_init, int *nz_trans, int *nu_trans,
+                          int *nz_move, int *nu_move);
 /* theta: [C][ntheta + nconst] host doubles (parameters, then model constants) */
 int bssm_filter_run(bssm_ctx *ctx, const bssm_filter_config *cfg, const double *y, const double *theta,
                     bssm_filter_result *res);
@@ -197,6 +204,7 @@ typedef struct {
   uint64_t seed;
   int skip_pilot;            /* 1 => use init_theta as chain start and proposal_chol_in / fixed_num_particles */
   const double *proposal_chol_in; /* [num_chains][p][p] when skip_pilot */
+  int engine;                /* BSSM_ENGINE_* for the filter runs */
 } bssm_pmmh_config;
 
 typedef struct {

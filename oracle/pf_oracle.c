@@ -279,7 +279,7 @@ static int get_dims(int model, model_dims *m) {
   memset(m, 0, sizeof(*m));
   switch (model) {
     case ORC_MODEL_AR_SIN: case ORC_MODEL_LG: case ORC_MODEL_AR_COS:
-      m->d = 1; m->ntheta = 3; m->nz_init = 1; m->nz_trans = 1; return 0;
+      m->d = 1; m->ntheta = 3; m->nz_init = 1; m->nz_trans = 1; m->nz_move = 1; m->nu_move = 1; return 0;
     case ORC_MODEL_RW_DRIFT:
       m->d = 1; m->ntheta = 2; m->nz_init = 1; m->nz_trans = 1; m->nz_move = 1; m->nu_move = 1; return 0;
     case ORC_MODEL_SIR_CB:

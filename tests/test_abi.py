@@ -1,0 +1,50 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/bayesssm_b200.h declares."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "bayesssm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bssm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bayesssm_b200 import _native
+    from bayesssm_b200.build import build_native
+    build_native()
+    lib = _native.load_library()
+    names = _header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _native.SYMBOLS, f"{n} has no ctypes prototype"
+    assert lib.bssm_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from bayesssm_b200 import _native
+    with pytest.raises(_native.EngineError) as e:
+        _native.Context(0)
+    assert e.value.status == _native.ERR_NO_DEVICE
+
+
+def test_host_side_transforms_match_oracle(orc):
+    from bayesssm_b200 import _native
+    lib = _native.load_library()
+    for tr in (0, 1, 2):
+        for th in (0.2, 0.5, 0.9):
+            assert lib.bssm_transform(th, tr) == orc.transform(th, tr)
+            z = orc.transform(th, tr)
+            assert lib.bssm_back_transform(z, tr) == orc.back_transform(z, tr)
+    for kind, a, b in ((0, 0, 0), (1, 0, 1), (1, 0, 10), (2, 1, 0), (3, 0, 1), (4, 1, 0), (4, 2, 0)):
+        for x in (-0.5, 0.0, 0.3, 1.0, 2.5):
+            u, v = lib.bssm_log_prior(kind, a, b, x), orc.log_prior(kind, a, b, x)
+            assert u == v or abs(u - v) < 1e-15

@@ -1,0 +1,132 @@
+"""GPU parity of the particle filters (general engine, through the C ABI) against the oracle restating
+R/particle_filter_core.R, with identical injected particles and noise: log-likelihood within 1e-6 relative
+(north star; measured ~1e-13), identical ancestors, state estimates / ESS to 1e-9."""
+import numpy as np
+import pytest
+
+import engine_helpers as eh
+from bayesssm_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+AR, LG, RWD, SIR, ARCOS, RW2D = range(6)
+THETA = {AR: [0.8, 1.0, 0.5], LG: [0.8, 1.0, 1.0], RWD: [1.0, 0.3], SIR: [0.5, 0.2, 500.0, 70.0], ARCOS: [0.8, 1.0, 0.5], RW2D: [0.1]}
+
+
+def sim_y(model, T, rng):
+    if model == SIR:
+        return rng.poisson(60, T).astype(float)
+    if model == RWD:
+        return np.cumsum(1.0 + rng.standard_normal(T)) + 0.3 * rng.standard_normal(T)
+    x, ys = rng.standard_normal(), []
+    for _ in range(T):
+        x = 0.8 * x + (np.sin(x) if model in (AR, ARCOS) else 0.0) + rng.standard_normal()
+        ys.append((np.cos(x) if model == ARCOS else x) + 0.5 * rng.standard_normal())
+    return np.array(ys)
+
+
+def compare(orc, engine, model, algorithm, ralg, rfn, N, T, obs_times=None, threshold=-1.0, seed=0, hist=True):
+    rng = np.random.default_rng(1000 + 17 * model + 5 * algorithm + ralg + 3 * rfn + N)
+    y = sim_y(model, T, rng)
+    n_time = int(obs_times[-1]) if obs_times is not None else T
+    noise = orc.make_noise(model, N, T, n_time, rng)
+    th = THETA[model]
+    ref = orc.particle_filter(model, algorithm, ralg, rfn, N, y, th, threshold=threshold, obs_times=obs_times,
+                              noise=noise, return_particles=hist, want_ancestors=True)
+    got = eh.filter_run(engine, model, algorithm, ralg, rfn, N, y, th, threshold=threshold, obs_times=obs_times,
+                        noise=noise, precision=nat.F64, return_particles=hist, want_ancestors=True)
+    assert ref["status"] == 0 and got["status"][0] == 0
+    assert got["early_exit"][0] == ref["early_exit"]
+    assert got["n_resampled"][0] == ref["n_resampled"]
+    # north-star tolerance: 1e-6 relative on the log-likelihood; we hold a far tighter one
+    assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-10 * max(1.0, abs(ref["loglike"]))
+    np.testing.assert_allclose(got["loglike_history"][0], ref["loglike_history"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-9)
+    np.testing.assert_allclose(got["state_est"][0], ref["state_est"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(got["ancestors_history"][0], ref["ancestors_history"])
+    if algorithm == 1:
+        assert np.array_equal(got["ancestors_aux_history"][0], ref["ancestors_aux_history"])
+    if hist:
+        np.testing.assert_allclose(got["particles_history"][0], ref["particles_history"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(got["weights_history"][0], ref["weights_history"], rtol=1e-9, atol=1e-300)
+    return ref, got
+
+
+@pytest.mark.parametrize("rfn", [0, 1, 2])
+@pytest.mark.parametrize("ralg", [0, 1, 2])
+def test_bpf_nonlinear_ar(orc, engine, ralg, rfn):
+    compare(orc, engine, AR, 0, ralg, rfn, N=1000, T=20)      # config C1 shape: README model, T=20, N=1000
+
+
+@pytest.mark.parametrize("model", [LG, RWD, SIR, ARCOS, RW2D])
+def test_bpf_other_models(orc, engine, model):
+    compare(orc, engine, model, 0, 2, 0, N=777, T=15)
+
+
+@pytest.mark.parametrize("model", [AR, RWD, SIR, LG])
+@pytest.mark.parametrize("rfn", [0, 1])
+def test_apf(orc, engine, model, rfn):
+    compare(orc, engine, model, 1, 2, rfn, N=500, T=12)
+
+
+@pytest.mark.parametrize("model", [RWD, SIR, AR])
+def test_rmpf(orc, engine, model):
+    compare(orc, engine, model, 2, 2, 0, N=500, T=12)
+
+
+def test_obs_times_gaps(orc, engine):
+    compare(orc, engine, AR, 0, 2, 0, N=300, T=6, obs_times=[1, 2, 4, 7, 8, 12])
+
+
+def test_explicit_threshold(orc, engine):
+    compare(orc, engine, AR, 0, 2, 1, N=4096, T=10, threshold=0.9 * 4096)
+
+
+def test_large_n_single_step_sizes(orc, engine):
+    compare(orc, engine, AR, 0, 1, 0, N=70001, T=3, hist=False)
+
+
+def test_early_exit(orc, engine):
+    # all log-weights < -1e8 => loglike = -Inf and a truncated, zero-filled result (R/particle_filter_core.R:189-202)
+    y = np.array([0.1, 1e6, 0.2])
+    rng = np.random.default_rng(1)
+    noise = orc.make_noise(AR, 64, 3, 3, rng)
+    th = [0.8, 1.0, 1e-3]
+    ref = orc.particle_filter(AR, 0, 2, 0, 64, y, th, noise=noise)
+    got = eh.filter_run(engine, AR, 0, 2, 0, 64, y, th, noise=noise)
+    assert ref["early_exit"] == 1 and got["early_exit"][0] == 1
+    assert got["loglike"][0] == -np.inf and ref["loglike"] == -np.inf
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-9)
+    np.testing.assert_allclose(got["state_est"][0], ref["state_est"], rtol=1e-9, atol=1e-12)
+
+
+def test_philox_mode_matches_oracle_philox(orc, engine):
+    # same counter-based generator on both sides: no injected buffers at all
+    rng = np.random.default_rng(2)
+    y = sim_y(AR, 25, rng)
+    for stream in (0, 5):
+        ref = orc.particle_filter(AR, 0, 2, 0, 2000, y, THETA[AR], seed=1405, run_id=3, stream=stream)
+        got = eh.filter_run(engine, AR, 0, 2, 0, 2000, y, THETA[AR], seed=1405, run_id=3, stream_base=stream)
+        assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+        np.testing.assert_allclose(got["state_est"][0], ref["state_est"], rtol=1e-6, atol=1e-6)
+
+
+def test_batched_filters_are_independent_streams(orc, engine):
+    rng = np.random.default_rng(3)
+    y = sim_y(LG, 30, rng)
+    got = eh.filter_run(engine, LG, 0, 1, 0, 512, y, THETA[LG], seed=7, num_filters=6)
+    for c in (0, 3, 5):
+        ref = orc.particle_filter(LG, 0, 1, 0, 512, y, THETA[LG], seed=7, stream=c)
+        assert abs(got["loglike"][c] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+
+
+def test_f32_precision_statistically_consistent(orc, engine):
+    # throughput precision (fp32 state / weights, fp64 cdf and accumulators) against the exact Kalman value
+    rng = np.random.default_rng(4)
+    y = sim_y(LG, 100, rng)
+    exact = orc.kalman_loglik(y, 0.8, 1.0, 1.0)
+    got = eh.filter_run(engine, LG, 0, 1, 0, 4096, y, THETA[LG], seed=11, num_filters=32, precision=nat.F32)
+    lls = got["loglike"]
+    est = np.log(np.mean(np.exp(lls - lls.max()))) + lls.max()
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(est - exact) < 3 * se + 0.02, (est, exact, se)
