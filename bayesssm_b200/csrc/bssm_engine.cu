@@ -101,9 +101,6 @@ static int resample_cdf_plain(bssm_ctx* ctx, const double* d_w, size_t w_stride,
 // ---------------------------------------------------------------------------------------------
 // particle filter orchestration
 // ---------------------------------------------------------------------------------------------
-struct FilterLaunch {
-  int model, precision, resample_fn, exact, hist, T;
-};
 
 template <typename Real>
 static int resample_stage(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int obs, int aux_stage, double* cdf) {
@@ -495,7 +492,7 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   FilterLaunch L;
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
   L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
-  L.hist = cfg->return_particles; L.T = T;
+  L.hist = cfg->return_particles; L.T = T; L.engine = cfg->engine;
   const bool need_aux = cfg->algorithm == BSSM_APF;
   const bool want_anc = res->ancestors_history != nullptr || res->ancestors_aux_history != nullptr;
   double* cdf;
@@ -567,6 +564,50 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
 #undef DL
   BSSM_CK(cudaStreamSynchronize(st));
   BSSM_CK(cudaEventElapsedTime(&res->kernel_ms, ctx->ev0, ctx->ev1));
+  return BSSM_OK;
+}
+
+// device-resident variant: y [T][dy] and theta [C][ntheta+nconst] already in HBM, Philox noise, no
+// histories; only the log-likelihoods are written (device).  No host<->device traffic.
+int bssm_filter_run_device(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* d_y, const double* d_theta,
+                           double* d_loglike, float* kernel_ms) {
+  if (!ctx || !cfg || !d_y || !d_theta) { set_error("bssm_filter_run_device: null argument"); return BSSM_ERR_BAD_ARG; }
+  BSSM_TRY(filter_validate(cfg));
+  if (cfg->noise || cfg->return_particles) { set_error("bssm_filter_run_device: injected noise / histories need bssm_filter_run"); return BSSM_ERR_UNSUPPORTED; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  int d, nth, nc;
+  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  const int C = cfg->num_filters, T = cfg->num_obs;
+  FilterDev f;
+  memset(&f, 0, sizeof(f));
+  f.C = C; f.N = cfg->num_particles; f.T = T; f.dy = cfg->dy; f.d = d; f.theta_stride = nth + nc; f.seed = cfg->seed;
+  f.algorithm = cfg->algorithm;
+  f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->resample_algorithm;
+  f.threshold = cfg->threshold;
+  FilterLaunch L;
+  L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
+  L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
+  L.hist = 0; L.T = T; L.engine = cfg->engine;
+  double* cdf;
+  BSSM_TRY(filter_setup(ctx, f, L, cfg->algorithm == BSSM_APF, false, &cdf));
+  unsigned int* ids; int* d_obs = nullptr;
+  BSSM_TRY(scratch(ctx, SL_F_IDS, (size_t)2 * C, &ids));
+  if (cfg->obs_times && T) {
+    BSSM_TRY(scratch(ctx, SL_F_OBS, (size_t)T, &d_obs));
+    BSSM_CK(cudaMemcpyAsync(d_obs, cfg->obs_times, sizeof(int) * T, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  f.theta = d_theta; f.y = d_y; f.obs_times = d_obs; f.stream = ids; f.run_id = ids + C;
+  k_fill_ids<<<(C + 127) / 128, 128, 0, ctx->stream>>>(ids, ids + C, C, cfg->stream_base, cfg->run_id);
+  BSSM_LAUNCH(ctx, "k_fill_ids");
+  BSSM_TRY(filter_reset(ctx, f, nullptr));
+  BSSM_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  BSSM_TRY(filter_enqueue(ctx, f, L, cdf));
+  BSSM_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (d_loglike) BSSM_CK(cudaMemcpyAsync(d_loglike, f.loglike, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (kernel_ms) {
+    BSSM_CK(cudaEventSynchronize(ctx->ev1));
+    BSSM_CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+  }
   return BSSM_OK;
 }
 

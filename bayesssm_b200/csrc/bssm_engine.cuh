@@ -92,4 +92,13 @@ struct RsArgs {
   double* total;           // [nseg] out (exact: sequential sum of the raw weights)
 };
 
+// ---- batched filter runs (bssm_engine.cu), reused by the PMMH driver -----------------------------
+struct FilterLaunch {
+  int model, precision, resample_fn, exact, hist, T, engine;
+};
+int model_dims(int model, int* d, int* ntheta, int* nconst);
+int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out);
+int filter_reset(bssm_ctx* ctx, FilterDev& f, const int* d_active);
+int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf);
+
 }  // namespace bssm

@@ -1,20 +1,468 @@
-// bssm_pmmh.cu -- placeholder until the device-resident PMMH lands (next commit).
+// bssm_pmmh.cu -- device-resident Particle Marginal Metropolis-Hastings.
+// Replaces the per-chain closure chain_result (R/pmmh.R:345-505), the pilot chain
+// .run_pilot_chain (R/pmmh_tuning.R:111-317), .pilot_run (R/pmmh_tuning.R:29-64), the parameter
+// transforms (R/utils.R:102-152) and the chain fan-out (R/pmmh.R:511-535).
+// All chains of this call advance together: one thread per chain proposes / accepts, the
+// batched filter ([chains x particles]) runs in between, and nothing returns to the host until
+// a phase is over.  Quirks A10-A16 of SURVEY.md Appendix A are reproduced on purpose.
 #include "bssm_engine.cuh"
+
 #include <math.h>
+
 using namespace bssm;
+
+namespace bssm {
+
+enum { PH_PILOT = 1, PH_PILOT_RUN = 2, PH_MAIN = 3 };
+constexpr int PMAX = 8;
+
+struct PmmhDev {
+  int C, p, nconst, theta_stride;
+  unsigned long long seed;
+  unsigned int chain_id_base;
+  int prior_kind[PMAX]; double prior_a[PMAX], prior_b[PMAX];
+  int transform[PMAX]; double pilot_sd[PMAX];
+  double consts[8];
+  // per chain
+  double *cur, *prop;        // [C][p]
+  double *cur_ll;            // [C]
+  double *lp_prop;           // [C] sum of log priors at the proposal
+  double *theta_full;        // [C][theta_stride]  filter input (theta, consts)
+  int *valid;                // [C] proposal has finite priors (main chain) / chain alive
+  int *alive;                // [C]
+  int *status;               // [C]
+  int *n_accept;             // [C]
+  unsigned int *stream, *run_id;  // [C] filter Philox ids
+  // filter outputs
+  const double* f_loglike; const int* f_status;
+};
+
+// R densities as in SURVEY.md Appendix F
+__device__ inline double dev_log_prior(int kind, double a, double b, double x) {
+  const double LSP = 0.918938533204672741780329736406;
+  const double INF = __longlong_as_double(0x7FF0000000000000LL);
+  switch (kind) {
+    case BSSM_PRIOR_FLAT: return 0.0;
+    case BSSM_PRIOR_NORMAL: { double z = (x - a) / b; return -(LSP + 0.5 * z * z + log(b)); }
+    case BSSM_PRIOR_EXP: return x < 0 ? -INF : log(a) - a * x;
+    case BSSM_PRIOR_UNIF: return (a <= x && x <= b) ? -log(b - a) : -INF;
+    case BSSM_PRIOR_HALFNORMAL: { if (x < 0) return -INF; double z = (x - 0.0) / a; return log(2.0) + (-(LSP + 0.5 * z * z + log(a))); }
+  }
+  return __longlong_as_double(0x7FF8000000000000LL);
+}
+__device__ inline double dev_transform(double th, int tr) {  // R/utils.R:102-112
+  return tr == BSSM_TR_LOG ? log(th) : (tr == BSSM_TR_LOGIT ? log(th / (1.0 - th)) : th);
+}
+__device__ inline double dev_back_transform(double z, int tr) {  // R/utils.R:122-132
+  return tr == BSSM_TR_LOG ? exp(z) : (tr == BSSM_TR_LOGIT ? 1.0 / (1.0 + exp(-z)) : z);
+}
+__device__ inline double dev_log_jacobian(const double* th, const int* tr, int p) {  // R/utils.R:142-152 (sic, A14)
+  double s = 0.0;
+  for (int j = 0; j < p; j++) {
+    if (tr[j] == BSSM_TR_LOG) s += log(th[j]);
+    else if (tr[j] == BSSM_TR_LOGIT) s += log(1.0 / (th[j] * (1.0 - th[j])));
+  }
+  return s;
+}
+__device__ inline bool dev_priors_finite(const PmmhDev& P, const double* th, double* sum_out) {
+  double s = 0.0; bool ok = true;
+  for (int j = 0; j < P.p; j++) {
+    double lp = dev_log_prior(P.prior_kind[j], P.prior_a[j], P.prior_b[j], th[j]);
+    if (!isfinite(lp)) ok = false;
+    s += lp;
+  }
+  *sum_out = s;
+  return ok;
+}
+__device__ inline double theta_normal(const PmmhDev& P, int phase, unsigned int chain, unsigned int it, unsigned int attempt, int j) {
+  NoiseKey key = make_key(P.seed, (unsigned int)phase << 28, chain);
+  uint4x q = noise_quad(key, it, TAG_THETA_Z, attempt, (unsigned int)j >> 2);
+  int pr = (j & 3) >> 1;
+  double n0, n1;
+  Math<double>::box_muller(q.w[2 * pr], q.w[2 * pr + 1], n0, n1);
+  return (j & 1) ? n1 : n0;
+}
+__device__ inline double theta_uniform(const PmmhDev& P, int phase, unsigned int chain, unsigned int it) {
+  NoiseKey key = make_key(P.seed, (unsigned int)phase << 28, chain);
+  uint4x q = noise_quad(key, it, TAG_THETA_U, 0u, 0u);
+  return word_to_unit_f64(q.w[0]);
+}
+__device__ inline void set_filter_theta(const PmmhDev& P, int c, const double* th) {
+  double* tf = P.theta_full + (size_t)c * P.theta_stride;
+  for (int j = 0; j < P.p; j++) tf[j] = th[j];
+  for (int j = 0; j < P.nconst; j++) tf[P.p + j] = P.consts[j];
+}
+
+// start of a phase: current point = start[c], valid iff priors finite (R/pmmh_tuning.R:135-143)
+__global__ void k_pm_start(PmmhDev P, const double* start, int phase, int check_prior, int init_state) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  double th[PMAX];
+  for (int j = 0; j < P.p; j++) th[j] = start[(size_t)c * P.p + j];
+  double s;
+  bool ok = dev_priors_finite(P, th, &s);
+  if (init_state) { P.alive[c] = 1; P.status[c] = 0; P.n_accept[c] = 0; }
+  if (check_prior && !ok && P.alive[c]) { P.alive[c] = 0; P.status[c] = BSSM_ERR_PRIOR_INIT; }
+  for (int j = 0; j < P.p; j++) { P.cur[(size_t)c * P.p + j] = th[j]; P.prop[(size_t)c * P.p + j] = th[j]; }
+  set_filter_theta(P, c, th);
+  P.valid[c] = P.alive[c];
+  P.stream[c] = P.chain_id_base + (unsigned int)c;
+  P.run_id[c] = ((unsigned int)phase << 28) | 0u;
+}
+// after the first filter of a phase: record its log-likelihood and draw 0
+__global__ void k_pm_first(PmmhDev P, double* chain, double* ll_chain, int m) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  if (P.alive[c] && P.f_status[c]) { P.alive[c] = 0; P.status[c] = P.f_status[c]; }
+  P.cur_ll[c] = P.f_loglike[c];
+  for (int j = 0; j < P.p; j++) chain[((size_t)c * m) * P.p + j] = P.cur[(size_t)c * P.p + j];
+  ll_chain[(size_t)c * m] = P.cur_ll[c];
+}
+
+// proposal.  pilot (R/pmmh_tuning.R:193-208): z* = z + N(0, diag(sd^2)), re-drawn until every prior is finite.
+// main (R/pmmh.R:424-442): z* ~ N(z, L L'); a non-finite prior rejects WITHOUT running the filter.
+__global__ void k_pm_propose(PmmhDev P, int phase, int it, const double* chol /* [C][p][p] */) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  P.run_id[c] = ((unsigned int)phase << 28) | (unsigned int)it;
+  if (!P.alive[c]) { P.valid[c] = 0; return; }
+  unsigned int chain = P.chain_id_base + (unsigned int)c;
+  const int p = P.p;
+  double cur[PMAX], prop[PMAX], zc[PMAX];
+  for (int j = 0; j < p; j++) { cur[j] = P.cur[(size_t)c * p + j]; zc[j] = dev_transform(cur[j], P.transform[j]); }
+  double lp = 0.0;
+  bool ok = false;
+  if (phase == PH_PILOT) {
+    for (unsigned int attempt = 0; attempt <= 0xFFFFu; attempt++) {
+      for (int j = 0; j < p; j++) {
+        double zp = zc[j] + (0.0 + P.pilot_sd[j] * theta_normal(P, phase, chain, (unsigned int)it, attempt, j));
+        prop[j] = dev_back_transform(zp, P.transform[j]);
+      }
+      if (dev_priors_finite(P, prop, &lp)) { ok = true; break; }
+    }
+    if (!ok) { P.alive[c] = 0; P.status[c] = BSSM_ERR_BAD_ARG; }
+  } else {
+    double xi[PMAX];
+    for (int j = 0; j < p; j++) xi[j] = theta_normal(P, phase, chain, (unsigned int)it, 0u, j);
+    const double* L = chol + (size_t)c * p * p;
+    for (int a = 0; a < p; a++) {
+      double s = zc[a];
+      for (int b = 0; b <= a; b++) s += L[a * p + b] * xi[b];
+      prop[a] = dev_back_transform(s, P.transform[a]);
+    }
+    ok = dev_priors_finite(P, prop, &lp);
+  }
+  for (int j = 0; j < p; j++) P.prop[(size_t)c * p + j] = prop[j];
+  P.lp_prop[c] = lp;
+  P.valid[c] = ok ? 1 : 0;
+  if (ok) set_filter_theta(P, c, prop);
+}
+
+// accept / reject (R/pmmh_tuning.R:233-253, R/pmmh.R:461-496) and draw storage
+__global__ void k_pm_accept(PmmhDev P, int phase, int it, double* chain, double* ll_chain, int m) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  const int p = P.p;
+  double cur[PMAX];
+  for (int j = 0; j < p; j++) cur[j] = P.cur[(size_t)c * p + j];
+  if (P.alive[c] && P.valid[c]) {
+    if (P.f_status[c]) { P.alive[c] = 0; P.status[c] = P.f_status[c]; }
+    else {
+      double prop[PMAX];
+      for (int j = 0; j < p; j++) prop[j] = P.prop[(size_t)c * p + j];
+      double prop_ll = P.f_loglike[c], cur_ll = P.cur_ll[c];
+      double lp_cur;
+      dev_priors_finite(P, cur, &lp_cur);
+      double jp = dev_log_jacobian(prop, P.transform, p), jc = dev_log_jacobian(cur, P.transform, p);
+      double num, den;
+      if (phase == PH_PILOT) { num = P.lp_prop[c] + prop_ll + jp; den = lp_cur + cur_ll + jc; }
+      else { num = prop_ll + P.lp_prop[c] + jp; den = cur_ll + lp_cur + jc; }
+      double ratio = num - den;
+      if (ratio != ratio) ratio = -__longlong_as_double(0x7FF0000000000000LL);
+      double u = theta_uniform(P, phase, P.chain_id_base + (unsigned int)c, (unsigned int)it);
+      if (log(u) < ratio) {
+        for (int j = 0; j < p; j++) { cur[j] = prop[j]; P.cur[(size_t)c * p + j] = prop[j]; }
+        P.cur_ll[c] = prop_ll;
+        if (phase == PH_MAIN) P.n_accept[c] += 1;
+      }
+    }
+  }
+  for (int j = 0; j < p; j++) chain[((size_t)c * m + it) * p + j] = cur[j];
+  ll_chain[(size_t)c * m + it] = P.cur_ll[c];
+}
+
+// pilot posterior mean / covariance of the second half on the original scale (R/pmmh_tuning.R:260-267)
+__global__ void k_pm_pilot_stats(PmmhDev P, const double* chain, int pilot_m, double* mean, double* cov) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  const int p = P.p;
+  int b0 = pilot_m / 2, nn = pilot_m - b0;
+  const double* ch = chain + (size_t)c * pilot_m * p;
+  double mu[PMAX];
+  for (int j = 0; j < p; j++) {
+    double s = 0.0;
+    for (int it = b0; it < pilot_m; it++) s += ch[(size_t)it * p + j];
+    mu[j] = s / (double)nn;
+    mean[(size_t)c * p + j] = mu[j];
+  }
+  for (int a = 0; a < p; a++)
+    for (int b = 0; b < p; b++) {
+      double s = 0.0;
+      for (int it = b0; it < pilot_m; it++) s += (ch[(size_t)it * p + a] - mu[a]) * (ch[(size_t)it * p + b] - mu[b]);
+      cov[((size_t)c * p + a) * p + b] = s / (double)(nn - 1);
+    }
+}
+
+// replicate filters of .pilot_run: filter r of chain c is batch entry c*reps + r
+__global__ void k_pm_reps_setup(PmmhDev P, const double* mean, int reps, double* theta_rep, unsigned int* stream_rep,
+                                unsigned int* run_rep, int* active_rep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.C * reps) return;
+  int c = i / reps, r = i % reps;
+  double* tf = theta_rep + (size_t)i * P.theta_stride;
+  for (int j = 0; j < P.p; j++) tf[j] = mean[(size_t)c * P.p + j];
+  for (int j = 0; j < P.nconst; j++) tf[P.p + j] = P.consts[j];
+  stream_rep[i] = P.chain_id_base + (unsigned int)c;
+  run_rep[i] = ((unsigned int)PH_PILOT_RUN << 28) | (unsigned int)r;
+  active_rep[i] = P.alive[c];
+}
+
+// target_n (R/pmmh_tuning.R:54-57) and the proposal factor: lower Cholesky of D Sigma D (R/pmmh.R:378-389)
+__global__ void k_pm_tune(PmmhDev P, const double* rep_ll, const int* rep_status, int reps, int pilot_n, int fixed_n,
+                          const double* mean, const double* cov, double* pilot_ll_out, int* target_n, double* chol) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  const int p = P.p;
+  double mu = 0.0;
+  for (int r = 0; r < reps; r++) {
+    double v = rep_ll[(size_t)c * reps + r];
+    if (pilot_ll_out) pilot_ll_out[(size_t)c * reps + r] = v;
+    if (P.alive[c] && rep_status[(size_t)c * reps + r]) { P.alive[c] = 0; P.status[c] = rep_status[(size_t)c * reps + r]; }
+    mu += v;
+  }
+  mu /= (double)reps;
+  double v = 0.0;
+  for (int r = 0; r < reps; r++) { double dlt = rep_ll[(size_t)c * reps + r] - mu; v += dlt * dlt; }
+  v /= (double)(reps - 1);
+  double tn = ceil((double)pilot_n * v);
+  if (!(tn >= 50)) tn = 50;
+  if (tn > 1000) tn = 1000;
+  target_n[c] = fixed_n > 0 ? fixed_n : (int)tn;
+  double sc[PMAX], S[PMAX * PMAX];
+  for (int j = 0; j < p; j++) {
+    double th = mean[(size_t)c * p + j];
+    sc[j] = P.transform[j] == BSSM_TR_LOG ? 1.0 / th : (P.transform[j] == BSSM_TR_LOGIT ? 1.0 / (th * (1.0 - th)) : 1.0);
+  }
+  for (int a = 0; a < p; a++) for (int b = 0; b < p; b++) S[a * p + b] = sc[a] * cov[((size_t)c * p + a) * p + b] * sc[b];
+  double* L = chol + (size_t)c * p * p;
+  for (int i = 0; i < p * p; i++) L[i] = 0.0;
+  for (int j = 0; j < p; j++) {
+    double dsum = S[j * p + j];
+    for (int k = 0; k < j; k++) dsum -= L[j * p + k] * L[j * p + k];
+    if (!(dsum > 0)) continue;
+    double dj = sqrt(dsum);
+    L[j * p + j] = dj;
+    for (int i = j + 1; i < p; i++) {
+      double s = S[i * p + j];
+      for (int k = 0; k < j; k++) s -= L[i * p + k] * L[j * p + k];
+      L[i * p + j] = s / dj;
+    }
+  }
+}
+
+struct PmmhBuffers {
+  double *cur, *prop, *cur_ll, *lp_prop, *theta_full, *pilot_chain, *pilot_ll, *mean, *cov, *chol, *chain, *ll_chain,
+      *theta_rep, *y;
+  int *valid, *alive, *status, *n_accept, *target_n, *active_rep, *obs;
+  unsigned int *ids, *ids_rep;
+};
+
+// one batched filter pass for the chains (theta from P.theta_full, activity from P.valid)
+static int run_chain_filters(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf, const int* d_active) {
+  BSSM_TRY(filter_reset(ctx, f, d_active));
+  return filter_enqueue(ctx, f, L, cdf);
+}
+
+}  // namespace bssm
+
 extern "C" {
-int bssm_pmmh_run(bssm_ctx*, const bssm_pmmh_config*, const double*, const double*, bssm_pmmh_result*) {
-  set_error("bssm_pmmh_run: not built yet"); return BSSM_ERR_UNSUPPORTED;
+
+int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, const double* init_theta,
+                  bssm_pmmh_result* res) {
+  if (!ctx || !cfg || !y || !init_theta || !res) { set_error("bssm_pmmh_run: null argument"); return BSSM_ERR_BAD_ARG; }
+  int d, nth, nc;
+  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  const int C = cfg->num_chains, p = cfg->p, T = cfg->num_obs;
+  if (p != nth || p < 1 || p > PMAX) { set_error("pmmh: p=%d does not match the model's %d parameters", p, nth); return BSSM_ERR_BAD_ARG; }
+  if (cfg->nconst != nc) { set_error("pmmh: model needs %d constants, got %d", nc, cfg->nconst); return BSSM_ERR_BAD_ARG; }
+  if (C < 1 || cfg->m < 1 || T < 1) { set_error("pmmh: num_chains, m and num_obs must be >= 1"); return BSSM_ERR_BAD_ARG; }
+  if (!cfg->skip_pilot && (cfg->pilot_m < 4 || cfg->pilot_n < 1 || cfg->pilot_reps < 2)) { set_error("pmmh: pilot_m >= 4, pilot_n >= 1, pilot_reps >= 2 required"); return BSSM_ERR_BAD_ARG; }
+  if (cfg->skip_pilot && (!cfg->proposal_chol_in || cfg->fixed_num_particles < 1)) { set_error("pmmh: skip_pilot needs proposal_chol_in and fixed_num_particles"); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int m = cfg->m, pm = cfg->skip_pilot ? 1 : cfg->pilot_m, reps = cfg->skip_pilot ? 1 : cfg->pilot_reps;
+  const int ts = nth + nc;
+
+  // ---- device state ----
+  PmmhBuffers B;
+  int slot = SL_P_BASE;
+  auto dalloc = [&](double** ptr, size_t n) { return scratch(ctx, slot++, n, ptr); };
+  BSSM_TRY(dalloc(&B.cur, (size_t)C * p)); BSSM_TRY(dalloc(&B.prop, (size_t)C * p));
+  BSSM_TRY(dalloc(&B.cur_ll, (size_t)C)); BSSM_TRY(dalloc(&B.lp_prop, (size_t)C));
+  BSSM_TRY(dalloc(&B.theta_full, (size_t)C * ts));
+  BSSM_TRY(dalloc(&B.pilot_chain, (size_t)C * pm * p)); BSSM_TRY(dalloc(&B.pilot_ll, (size_t)C * pm));
+  BSSM_TRY(dalloc(&B.mean, (size_t)C * p)); BSSM_TRY(dalloc(&B.cov, (size_t)C * p * p)); BSSM_TRY(dalloc(&B.chol, (size_t)C * p * p));
+  BSSM_TRY(dalloc(&B.chain, (size_t)C * m * p)); BSSM_TRY(dalloc(&B.ll_chain, (size_t)C * m));
+  BSSM_TRY(dalloc(&B.theta_rep, (size_t)C * reps * ts));
+  BSSM_TRY(dalloc(&B.y, (size_t)T * cfg->dy));
+  int* ibuf;
+  BSSM_TRY(scratch(ctx, slot++, (size_t)C * 5 + (size_t)C * reps + T, &ibuf));
+  B.valid = ibuf; B.alive = ibuf + C; B.status = ibuf + 2 * C; B.n_accept = ibuf + 3 * C; B.target_n = ibuf + 4 * C;
+  B.active_rep = ibuf + 5 * C; B.obs = B.active_rep + (size_t)C * reps;
+  BSSM_TRY(scratch(ctx, slot++, (size_t)2 * C, &B.ids));
+  BSSM_TRY(scratch(ctx, slot++, (size_t)2 * C * reps, &B.ids_rep));
+  double* d_init;
+  BSSM_TRY(scratch(ctx, slot++, (size_t)C * p, &d_init));
+  BSSM_CK(cudaMemcpyAsync(B.y, y, sizeof(double) * T * cfg->dy, cudaMemcpyHostToDevice, st));
+  BSSM_CK(cudaMemcpyAsync(d_init, init_theta, sizeof(double) * C * p, cudaMemcpyHostToDevice, st));
+  if (cfg->obs_times) BSSM_CK(cudaMemcpyAsync(B.obs, cfg->obs_times, sizeof(int) * T, cudaMemcpyHostToDevice, st));
+  BSSM_CK(cudaMemsetAsync(B.alive, 0, sizeof(int) * C * 5, st));
+
+  PmmhDev P;
+  memset(&P, 0, sizeof(P));
+  P.C = C; P.p = p; P.nconst = nc; P.theta_stride = ts; P.seed = cfg->seed; P.chain_id_base = cfg->chain_id_base;
+  for (int j = 0; j < p; j++) {
+    P.prior_kind[j] = cfg->prior_kind[j]; P.prior_a[j] = cfg->prior_a[j]; P.prior_b[j] = cfg->prior_b[j];
+    P.transform[j] = cfg->transform ? cfg->transform[j] : BSSM_TR_IDENTITY;
+    P.pilot_sd[j] = cfg->pilot_proposal_sd ? cfg->pilot_proposal_sd[j] : 0.1;
+  }
+  for (int j = 0; j < nc; j++) P.consts[j] = cfg->consts[j];
+  P.cur = B.cur; P.prop = B.prop; P.cur_ll = B.cur_ll; P.lp_prop = B.lp_prop; P.theta_full = B.theta_full;
+  P.valid = B.valid; P.alive = B.alive; P.status = B.status; P.n_accept = B.n_accept;
+  P.stream = B.ids; P.run_id = B.ids + C;
+
+  // ---- filter batch for the chains ----
+  FilterDev f;
+  memset(&f, 0, sizeof(f));
+  f.C = C; f.T = T; f.dy = cfg->dy; f.d = d; f.theta = B.theta_full; f.theta_stride = ts; f.y = B.y;
+  f.obs_times = cfg->obs_times ? B.obs : nullptr; f.stream = P.stream; f.run_id = P.run_id; f.seed = cfg->seed;
+  f.algorithm = cfg->algorithm; f.threshold = -1.0;
+  FilterLaunch L;
+  L.model = cfg->model; L.precision = cfg->precision; L.exact = (cfg->precision == BSSM_F64); L.hist = 0; L.T = T;
+  L.engine = cfg->engine;
+  const bool need_aux = cfg->algorithm == BSSM_APF;
+  const int gb = (C + 127) / 128;
+  double* cdf = nullptr;
+  float pilot_ms = 0.f, main_ms = 0.f;
+  std::vector<int> h_target(C, cfg->fixed_num_particles);
+
+  BSSM_CK(cudaEventRecord(ctx->ev0, st));
+  if (!cfg->skip_pilot) {
+    // ---- pilot chain (R/pmmh_tuning.R:111-317) ----
+    f.N = cfg->pilot_n; f.n_per = nullptr;
+    f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->pilot_resample_algorithm;
+    L.resample_fn = cfg->pilot_resample_fn;
+    BSSM_TRY(filter_setup(ctx, f, L, need_aux, false, &cdf));
+    P.f_loglike = f.loglike; P.f_status = f.status;
+    k_pm_start<<<gb, 128, 0, st>>>(P, d_init, PH_PILOT, 1, 1);
+    BSSM_LAUNCH(ctx, "k_pm_start");
+    BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
+    k_pm_first<<<gb, 128, 0, st>>>(P, B.pilot_chain, B.pilot_ll, pm);
+    BSSM_LAUNCH(ctx, "k_pm_first");
+    for (int it = 1; it < pm; it++) {
+      k_pm_propose<<<gb, 128, 0, st>>>(P, PH_PILOT, it, nullptr);
+      BSSM_LAUNCH(ctx, "k_pm_propose");
+      BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
+      k_pm_accept<<<gb, 128, 0, st>>>(P, PH_PILOT, it, B.pilot_chain, B.pilot_ll, pm);
+      BSSM_LAUNCH(ctx, "k_pm_accept");
+    }
+    k_pm_pilot_stats<<<gb, 128, 0, st>>>(P, B.pilot_chain, pm, B.mean, B.cov);
+    BSSM_LAUNCH(ctx, "k_pm_pilot_stats");
+    // ---- .pilot_run: reps replicate filters per chain at the pilot mean, wrapper defaults SISAR + stratified ----
+    {
+      FilterDev fr = f;
+      fr.C = C * reps; fr.theta = B.theta_rep; fr.stream = B.ids_rep; fr.run_id = B.ids_rep + (size_t)C * reps;
+      fr.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : BSSM_SISAR;
+      FilterLaunch Lr = L;
+      Lr.resample_fn = BSSM_STRATIFIED;
+      BSSM_TRY(filter_setup(ctx, fr, Lr, need_aux, false, &cdf));
+      k_pm_reps_setup<<<(C * reps + 127) / 128, 128, 0, st>>>(P, B.mean, reps, B.theta_rep, B.ids_rep, B.ids_rep + (size_t)C * reps, B.active_rep);
+      BSSM_LAUNCH(ctx, "k_pm_reps_setup");
+      BSSM_TRY(run_chain_filters(ctx, fr, Lr, cdf, B.active_rep));
+      double* d_rep_ll;  // keep the replicate log-likelihoods in their own buffer for the result
+      BSSM_TRY(scratch(ctx, slot++, (size_t)C * reps, &d_rep_ll));
+      k_pm_tune<<<gb, 128, 0, st>>>(P, fr.loglike, fr.status, reps, cfg->pilot_n, cfg->fixed_num_particles, B.mean, B.cov,
+                                    d_rep_ll, B.target_n, B.chol);
+      BSSM_LAUNCH(ctx, "k_pm_tune");
+      if (res->pilot_loglikes) BSSM_CK(cudaMemcpyAsync(res->pilot_loglikes, d_rep_ll, sizeof(double) * C * reps, cudaMemcpyDeviceToHost, st));
+    }
+    BSSM_CK(cudaMemcpyAsync(h_target.data(), B.target_n, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
+    BSSM_CK(cudaEventRecord(ctx->ev1, st));
+    BSSM_CK(cudaStreamSynchronize(st));  // once per phase: target_n sizes the main-phase buffers
+    BSSM_CK(cudaEventElapsedTime(&pilot_ms, ctx->ev0, ctx->ev1));
+  } else {
+    BSSM_CK(cudaMemcpyAsync(B.chol, cfg->proposal_chol_in, sizeof(double) * C * p * p, cudaMemcpyHostToDevice, st));
+    BSSM_CK(cudaMemcpyAsync(B.mean, d_init, sizeof(double) * C * p, cudaMemcpyDeviceToDevice, st));
+    BSSM_CK(cudaMemcpyAsync(B.target_n, h_target.data(), sizeof(int) * C, cudaMemcpyHostToDevice, st));
+    BSSM_CK(cudaStreamSynchronize(st));
+  }
+
+  // ---- main chain (R/pmmh.R:395-500); filter defaults SISAR + stratified (quirk A10) ----
+  int nmax = 1;
+  for (int c = 0; c < C; c++) nmax = h_target[c] > nmax ? h_target[c] : nmax;
+  bool ragged = false;
+  for (int c = 0; c < C; c++) ragged = ragged || h_target[c] != nmax;
+  f.C = C; f.N = nmax; f.n_per = ragged ? B.target_n : nullptr; f.theta = B.theta_full; f.stream = P.stream; f.run_id = P.run_id;
+  f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : BSSM_SISAR;
+  L.resample_fn = BSSM_STRATIFIED;
+  BSSM_TRY(filter_setup(ctx, f, L, need_aux, false, &cdf));
+  P.f_loglike = f.loglike; P.f_status = f.status;
+  BSSM_CK(cudaEventRecord(ctx->ev0, st));
+  k_pm_start<<<gb, 128, 0, st>>>(P, B.mean, PH_MAIN, cfg->skip_pilot ? 1 : 0, cfg->skip_pilot ? 1 : 0);
+  BSSM_LAUNCH(ctx, "k_pm_start");
+  BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
+  k_pm_first<<<gb, 128, 0, st>>>(P, B.chain, B.ll_chain, m);
+  BSSM_LAUNCH(ctx, "k_pm_first");
+  for (int it = 1; it < m; it++) {
+    k_pm_propose<<<gb, 128, 0, st>>>(P, PH_MAIN, it, B.chol);
+    BSSM_LAUNCH(ctx, "k_pm_propose");
+    BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
+    k_pm_accept<<<gb, 128, 0, st>>>(P, PH_MAIN, it, B.chain, B.ll_chain, m);
+    BSSM_LAUNCH(ctx, "k_pm_accept");
+  }
+  BSSM_CK(cudaEventRecord(ctx->ev1, st));
+
+  // ---- results ----
+#define DL(dst, src, count, type) if (dst) BSSM_CK(cudaMemcpyAsync(dst, src, (count) * sizeof(type), cudaMemcpyDeviceToHost, st))
+  if (!cfg->skip_pilot) {
+    DL(res->pilot_theta_chain, B.pilot_chain, (size_t)C * pm * p, double);
+    DL(res->pilot_loglike_chain, B.pilot_ll, (size_t)C * pm, double);
+    DL(res->pilot_theta_cov, B.cov, (size_t)C * p * p, double);
+  }
+  DL(res->pilot_theta_mean, B.mean, (size_t)C * p, double);
+  DL(res->target_n, B.target_n, (size_t)C, int);
+  DL(res->proposal_chol, B.chol, (size_t)C * p * p, double);
+  DL(res->theta_chain, B.chain, (size_t)C * m * p, double);
+  DL(res->loglike_chain, B.ll_chain, (size_t)C * m, double);
+  DL(res->n_accept, B.n_accept, (size_t)C, int);
+  DL(res->status, B.status, (size_t)C, int);
+#undef DL
+  BSSM_CK(cudaStreamSynchronize(st));
+  BSSM_CK(cudaEventElapsedTime(&main_ms, ctx->ev0, ctx->ev1));
+  res->pilot_ms = pilot_ms;
+  res->main_ms = main_ms;
+  return BSSM_OK;
 }
-int bssm_filter_run_device(bssm_ctx*, const bssm_filter_config*, const double*, const double*, double*, float*) {
-  set_error("bssm_filter_run_device: not built yet"); return BSSM_ERR_UNSUPPORTED;
-}
-int bssm_model_compile(bssm_ctx*, const char*, int*) { set_error("bssm_model_compile: not built yet"); return BSSM_ERR_UNSUPPORTED; }
-const char* bssm_model_compile_log(bssm_ctx* ctx) { return ctx ? ctx->compile_log.c_str() : ""; }
+
 double bssm_transform(double th, int tr) { return tr == BSSM_TR_LOG ? log(th) : (tr == BSSM_TR_LOGIT ? log(th / (1.0 - th)) : th); }
 double bssm_back_transform(double z, int tr) { return tr == BSSM_TR_LOG ? exp(z) : (tr == BSSM_TR_LOGIT ? 1.0 / (1.0 + exp(-z)) : z); }
 double bssm_log_jacobian(const double* th, const int* tr, int p) {
-  double s = 0; for (int j = 0; j < p; j++) { if (tr[j] == BSSM_TR_LOG) s += log(th[j]); else if (tr[j] == BSSM_TR_LOGIT) s += log(1.0 / (th[j] * (1.0 - th[j]))); } return s;
+  double s = 0;
+  for (int j = 0; j < p; j++) {
+    if (tr[j] == BSSM_TR_LOG) s += log(th[j]);
+    else if (tr[j] == BSSM_TR_LOGIT) s += log(1.0 / (th[j] * (1.0 - th[j])));
+  }
+  return s;
 }
 double bssm_log_prior(int kind, double a, double b, double x) {
   const double LSP = 0.918938533204672741780329736406;
@@ -27,4 +475,5 @@ double bssm_log_prior(int kind, double a, double b, double x) {
   }
   return NAN;
 }
-}
+
+}  // extern "C"

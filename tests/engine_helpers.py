@@ -99,3 +99,58 @@ def filter_run(ctx, model, algorithm, resample_algorithm, resample_fn, N, y, the
     nat.check(ctx.lib.bssm_filter_run(ctx.handle, C.byref(cfg), _p(y), _p(theta), C.byref(res)))
     out["kernel_ms"] = res.kernel_ms
     return out
+
+
+def pmmh_run(ctx, model, algorithm, y, init_theta, prior_kind, prior_a, prior_b, transform, pilot_proposal_sd,
+             pilot_n, pilot_m, pilot_reps, m, seed, chain_id_base=0, pilot_resample_algorithm=2, pilot_resample_fn=0,
+             fixed_num_particles=0, consts=None, obs_times=None, precision=nat.F64, skip_pilot=False,
+             proposal_chol=None, engine=nat.ENGINE_AUTO):
+    y = _d(y)
+    if y.ndim == 1:
+        y = y[:, None]
+    T, dy = y.shape
+    init_theta = _d(init_theta)
+    if init_theta.ndim == 1:
+        init_theta = init_theta[None, :]
+    Cn, p = init_theta.shape
+    cfg = nat.PmmhConfig()
+    pk = np.ascontiguousarray(prior_kind, dtype=np.int32)
+    pa, pb = _d(prior_a), _d(prior_b)
+    tr = np.ascontiguousarray(transform, dtype=np.int32)
+    sd = _d(pilot_proposal_sd)
+    cfg.model, cfg.algorithm, cfg.p = model, algorithm, p
+    cfg.prior_kind, cfg.prior_a, cfg.prior_b = pk.ctypes.data_as(nat.c_int_p), _p(pa), _p(pb)
+    cfg.transform, cfg.pilot_proposal_sd = tr.ctypes.data_as(nat.c_int_p), _p(sd)
+    cfg.pilot_n, cfg.pilot_m, cfg.pilot_reps = pilot_n, pilot_m, pilot_reps
+    cfg.pilot_resample_algorithm, cfg.pilot_resample_fn = pilot_resample_algorithm, pilot_resample_fn
+    cfg.m, cfg.num_chains, cfg.chain_id_base = m, Cn, chain_id_base
+    cfg.fixed_num_particles = fixed_num_particles
+    cfg.num_obs, cfg.dy = T, dy
+    ot = None
+    if obs_times is not None:
+        ot = np.ascontiguousarray(obs_times, dtype=np.int32)
+        cfg.obs_times = ot.ctypes.data_as(nat.c_int_p)
+    cs = _d(consts) if consts is not None else np.zeros(1)
+    cfg.consts, cfg.nconst = _p(cs), (len(consts) if consts is not None else 0)
+    cfg.precision, cfg.seed = precision, seed
+    cfg.skip_pilot = int(skip_pilot)
+    chol_in = None
+    if proposal_chol is not None:
+        chol_in = _d(proposal_chol)
+        cfg.proposal_chol_in = _p(chol_in)
+    cfg.engine = engine
+    pm = 1 if skip_pilot else pilot_m
+    reps = 1 if skip_pilot else pilot_reps
+    out = {"pilot_theta_chain": np.zeros((Cn, pm, p)), "pilot_loglike_chain": np.zeros((Cn, pm)),
+           "pilot_theta_mean": np.zeros((Cn, p)), "pilot_theta_cov": np.zeros((Cn, p, p)),
+           "pilot_loglikes": np.zeros((Cn, reps)), "proposal_chol": np.zeros((Cn, p, p)),
+           "theta_chain": np.zeros((Cn, m, p)), "loglike_chain": np.zeros((Cn, m))}
+    res = nat.PmmhResult()
+    for k, v in out.items():
+        setattr(res, k, _p(v))
+    for k in ("target_n", "n_accept", "status"):
+        out[k] = np.zeros(Cn, dtype=np.int32)
+        setattr(res, k, out[k].ctypes.data_as(i32p))
+    nat.check(ctx.lib.bssm_pmmh_run(ctx.handle, C.byref(cfg), _p(y), _p(init_theta), C.byref(res)))
+    out["pilot_ms"], out["main_ms"] = res.pilot_ms, res.main_ms
+    return out
