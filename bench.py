@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-filter hot path (BASELINE.json metric: particle-timesteps/sec).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA engine
+  python bench.py --impl reference --gpus N ...            the reference algorithm on the host cores (oracle port)
+
+A "step" is one full pass of the hot path over one batch: one bootstrap filter of the README
+nonlinear-AR model, T=1000 observations, N=2^20 particles, SISAR (threshold 0.5 N) + stratified
+resampling -- BASELINE.json configs[1].  With N GPUs every rank runs its own independent filter
+(independent units, no data-path collective; weak scaling); `--workload pmmh` instead times
+chain-sharded PMMH iterations (configs[4]) with the final NCCL gather of draws.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+THETA = (0.8, 1.0, 0.5)  # README.md:97-114
+MODEL_AR = 0
+
+
+def simulate_y(T, seed=1405):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal()
+    ys = np.empty(T)
+    for t in range(T):
+        x = THETA[0] * x + np.sin(x) + THETA[1] * rng.standard_normal()
+        ys[t] = x + THETA[2] * rng.standard_normal()
+    return ys
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def algorithmic_bytes(N, T, n_resampled, sx=4, sw=4, sc=8, d=1):
+    """B_P = 2 d s_x + s_w every step, B_R = s_w + 2 s_c + 2 d s_x on resampled steps."""
+    return N * (T * (2 * d * sx + sw) + n_resampled * (sw + 2 * sc + 2 * d * sx))
+
+
+def cpu_sample(N, T, seed=1405):
+    import oracle
+    y = simulate_y(T)
+    secs, ll, nres = oracle.bench_bootstrap_filter(MODEL_AR, N, y, THETA, resample_algorithm=2, resample_fn=0,
+                                                   threshold=0.5 * N, seed=seed)
+    return secs, ll, nres
+
+
+def run_reference(args, rank, world):
+    """The reference algorithm (oracle port; R itself is not installable here) on all host cores: one
+    independent filter per core, the package's only parallelism (one chain per worker, R/pmmh.R:512-535)."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.lib()
+    cores = os.cpu_count() or 1
+    N, T = 1 << 17, 25
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        return cpu_sample(N, T, seed=1405 + i)[0]
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(cores)))
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = cores * N * T * args.steps / total
+    line = {"impl": "reference", "metric": "particle-timesteps/sec", "value": value, "unit": "particle-timesteps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "particle-timesteps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} independent bootstrap filters (one per core), N=2^17, T=25, SISAR+stratified, "
+                                       "C oracle restating R/particle_filter_core.R + src/resampling.cpp with R's "
+                                       "Mersenne-Twister/inversion RNG; R itself is not installable in this image"},
+            "e2e": {"value": value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "bootstrap_filter nonlinear-AR (README model) T=%d N=%d SISAR threshold=0.5N %s resampling, "
+                        "one filter per GPU" % (args.T, args.N, args.resample_fn),
+            "T": args.T, "N": args.N, "resample_fn": args.resample_fn, "precision": args.precision,
+            "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=1 << 20)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--resample-fn", dest="resample_fn", default="stratified", choices=["stratified", "systematic", "multinomial"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "general", "persistent"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from bayesssm_b200 import _native as nat
+    from bayesssm_b200 import bootstrap_filter, models
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = nat.Context(local_rank)
+    lib = ctx.lib
+    N, T = args.N, args.T
+    y = simulate_y(T)
+    fn = nat.RESAMPLE_FNS[args.resample_fn]
+    prec = nat.F32 if args.precision == "f32" else nat.F64
+    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT}[args.engine]
+
+    # device-resident inputs (torch owns the memory; the engine gets raw pointers)
+    d_y = torch.tensor(y, dtype=torch.float64, device="cuda")
+    d_theta = torch.tensor([THETA], dtype=torch.float64, device="cuda")
+    d_ll = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    cfg = nat.FilterConfig()
+    cfg.model, cfg.algorithm, cfg.resample_algorithm, cfg.resample_fn = MODEL_AR, nat.BPF, nat.SISAR, fn
+    cfg.threshold = 0.5 * N
+    cfg.num_particles, cfg.num_obs, cfg.dy = N, T, 1
+    cfg.num_filters, cfg.precision = 1, prec
+    cfg.seed, cfg.run_id, cfg.stream_base = 1405, 0, rank
+    cfg.return_particles, cfg.exact_resampling, cfg.engine = 0, -1, engine
+
+    def device_step(i):
+        cfg.run_id = i
+        ms = C.c_float()
+        nat.check(lib.bssm_filter_run_device(ctx.handle, C.byref(cfg), d_y.data_ptr(), d_theta.data_ptr(),
+                                             d_ll.data_ptr(), C.byref(ms)))
+        return ms.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    with ClockSampler(local_rank) as clocks:
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the timed region)
+            torch.cuda.synchronize()
+            step_ms.append(device_step(args.warmup + i))  # CUDA events on the engine's stream around the whole filter
+        barrier()
+    launches = ctx.launch_count() - launches0
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * N * T * args.steps / (total_ms * 1e-3)
+
+    # number of resampled steps of the timed configuration (for the algorithmic bytes): one host-API run
+    m = models.nonlinear_ar()
+    api = lambda seed: bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn,
+                                        resample_algorithm="SISAR", resample_fn=args.resample_fn, threshold=0.5 * N,
+                                        return_particles=False, precision=args.precision, seed=seed, ctx=ctx, engine=engine,
+                                        phi=THETA[0], sigma_x=THETA[1], sigma_y=THETA[2])
+    r0 = api(1405)
+    n_res = r0["n_resampled"]
+
+    # e2e: the user-facing call with HOST buffers (y up, state_est / ess / loglike_history / loglike back)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        api(2000 + i)
+        e2e_ms.append(1e3 * (time.perf_counter() - t1))
+    e2e_total = float(sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = world * N * T * args.steps / (e2e_total * 1e-3)
+    h2d = 8 * T + 8 * 3
+    d2h = 8 * ((T + 1) * 2 + T + 1) + 4 * 3
+
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = algorithmic_bytes(N, T, n_res, sx=4 if prec == nat.F32 else 8, sw=4 if prec == nat.F32 else 8)
+    ms_per_launch = total_ms / args.steps
+    achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
+    line = {
+        "metric": "particle-timesteps/sec", "value": value, "unit": "particle-timesteps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "whole filter pass (all launches of one step)" if launches / max(args.steps, 1) > 4 else "persistent filter kernel",
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "resampled_steps": int(n_res), "T": T},
+        "loglike": r0["loglike"],
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        Ns, Ts = 1 << 20, 12
+        secs, _, _ = cpu_sample(Ns, Ts)
+        line["cpu_baseline"] = {"value": Ns * Ts / secs, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
+                                "sample": f"same model/config, N=2^20, first {Ts} of the {T} observations, 1 thread (the R "
+                                          "interpreter is single-threaded), C oracle with R's RNG cost model"}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
