@@ -185,6 +185,13 @@ int model_dims(int model, int* d, int* ntheta, int* nconst) {
 
 // enqueue one batched filter run on ctx->stream (no synchronisation)
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
+  // engine choice: the persistent kernel serves the throughput precision of the bootstrap filter;
+  // everything else (and BSSM_F64 parity runs unless forced) goes through the general kernels
+  if (L.engine == BSSM_ENGINE_PERSISTENT) {
+    if (!fast_supported(f, L)) { set_error("BSSM_ENGINE_PERSISTENT: configuration not supported by the persistent kernel (BPF, 1-D built-in model, stratified/systematic, no histories / injected noise)"); return BSSM_ERR_UNSUPPORTED; }
+    return fast_filter_enqueue(ctx, f, L);
+  }
+  if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && fast_supported(f, L)) return fast_filter_enqueue(ctx, f, L);
   switch (L.model) {
     case BSSM_MODEL_AR_SIN: return run_filter_model<ModelArSin>(ctx, f, L, cdf);
     case BSSM_MODEL_LG: return run_filter_model<ModelLG>(ctx, f, L, cdf);

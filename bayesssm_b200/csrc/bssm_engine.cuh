@@ -100,5 +100,8 @@ int model_dims(int model, int* d, int* ntheta, int* nconst);
 int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out);
 int filter_reset(bssm_ctx* ctx, FilterDev& f, const int* d_active);
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf);
+// persistent bootstrap-filter kernel (bssm_fast.cu)
+bool fast_supported(const FilterDev& f, const FilterLaunch& L);
+int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L);
 
 }  // namespace bssm

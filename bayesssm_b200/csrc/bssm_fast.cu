@@ -1,0 +1,72 @@
+// bssm_fast.cu -- host side of the persistent bootstrap-filter kernel (bssm_fast.cuh).
+#include "bssm_engine.cuh"
+#include "bssm_fast.cuh"
+
+namespace bssm {
+
+bool fast_supported(const FilterDev& f, const FilterLaunch& L) {
+  if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history) return false;
+  if (L.resample_fn == BSSM_MULTINOMIAL) return false;
+  if (!(L.model == BSSM_MODEL_AR_SIN || L.model == BSSM_MODEL_LG || L.model == BSSM_MODEL_AR_COS || L.model == BSSM_MODEL_RW_DRIFT)) return false;
+  if ((long long)f.N > (long long)FAST_MAX_G * FAST_MAX_NB) return false;
+  return true;
+}
+
+template <typename Model, typename Real>
+static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
+  const int nsm = ctx->prop.multiProcessorCount;
+  // group size: as few CTAs as hold the particles, widened to fill the chip when there are few filters
+  int G = (f.N + FAST_MAX_NB - 1) / FAST_MAX_NB;
+  if (f.C * G < nsm) {
+    int wide = nsm / f.C;
+    int cap = (f.N + 1023) / 1024;   // keep >= ~1024 particles per CTA
+    if (wide > cap) wide = cap;
+    if (wide > G) G = wide;
+  }
+  if (G > FAST_MAX_G) G = FAST_MAX_G;
+  if (G < 1) G = 1;
+  int nb_max = (f.N + G - 1) / G;
+  nb_max = (nb_max + FAST_PPT - 1) / FAST_PPT * FAST_PPT;
+  if (nb_max > FAST_MAX_NB) { set_error("persistent kernel: %d particles per CTA exceed %d", nb_max, FAST_MAX_NB); return BSSM_ERR_UNSUPPORTED; }
+  int threads = (nb_max / FAST_PPT + 31) / 32 * 32;
+  if (threads < 32) threads = 32;
+  size_t smem = (size_t)nb_max * sizeof(double) + (size_t)4 * G * sizeof(double) + (4 * 32 + 16) * sizeof(double) + (size_t)nb_max * sizeof(Real);
+  auto kern = k_fast_bpf<Model, Real>;
+  BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  BSSM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  long long resident = (long long)per_sm * nsm;
+  if (resident < G) { set_error("persistent kernel: group of %d CTAs does not fit (%lld resident)", G, resident); return BSSM_ERR_UNSUPPORTED; }
+  int ngroups = (int)(resident / G);
+  if (ngroups > f.C) ngroups = f.C;
+  FastParams P;
+  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = nb_max;
+  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, (size_t)ngroups * 2 * G, &P.rec));
+  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 1, (size_t)ngroups * G, &P.rec2));
+  BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, (size_t)ngroups * G * nb_max * sizeof(Real), &P.xnew));
+  BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(FastRec) * (size_t)ngroups * 2 * G, ctx->stream));
+  BSSM_CK(cudaMemsetAsync(P.rec2, 0, sizeof(FastRec2) * (size_t)ngroups * G, ctx->stream));
+  void* args[] = {&P};
+  BSSM_CK(cudaLaunchCooperativeKernel((void*)kern, dim3(ngroups * G), dim3(threads), args, smem, ctx->stream));
+  BSSM_LAUNCH(ctx, "k_fast_bpf");
+  return BSSM_OK;
+}
+
+template <typename Model>
+static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
+  if (L.precision == BSSM_F64) return fast_launch<Model, double>(ctx, f, L);
+  return fast_launch<Model, float>(ctx, f, L);
+}
+
+int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
+  switch (L.model) {
+    case BSSM_MODEL_AR_SIN: return fast_model<ModelArSin>(ctx, f, L);
+    case BSSM_MODEL_LG: return fast_model<ModelLG>(ctx, f, L);
+    case BSSM_MODEL_AR_COS: return fast_model<ModelArCos>(ctx, f, L);
+    case BSSM_MODEL_RW_DRIFT: return fast_model<ModelRwDrift>(ctx, f, L);
+  }
+  set_error("persistent kernel: model %d not supported", L.model);
+  return BSSM_ERR_UNSUPPORTED;
+}
+
+}  // namespace bssm
