@@ -74,6 +74,7 @@ template <> struct Math<double> {
   static BSSM_DEV double log_(double x) { return log(x); }
   static BSSM_DEV double sin_(double x) { return sin(x); }
   static BSSM_DEV double cos_(double x) { return cos(x); }
+  static BSSM_DEV double div_(double a, double b) { return a / b; }
   static BSSM_DEV double ninf() { return -__longlong_as_double(0x7FF0000000000000LL); }
 };
 template <> struct Math<float> {
@@ -87,14 +88,21 @@ template <> struct Math<float> {
   }
   static BSSM_DEV float exp_(float x) { return __expf(x); }
   static BSSM_DEV float log_(float x) { return logf(x); }
-  static BSSM_DEV float sin_(float x) { return sinf(x); }
-  static BSSM_DEV float cos_(float x) { return cosf(x); }
+  // throughput precision: reduce to [-pi, pi] with a two-term 2*pi, then the SFU (abs. error < 1e-6)
+  static BSSM_DEV float reduce_2pi(float x) {
+    float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);
+    return fmaf(k, 1.7484556e-7f, r);
+  }
+  static BSSM_DEV float sin_(float x) { return __sinf(reduce_2pi(x)); }
+  static BSSM_DEV float cos_(float x) { return __cosf(reduce_2pi(x)); }
+  static BSSM_DEV float div_(float a, float b) { return __fdividef(a, b); }
   static BSSM_DEV float ninf() { return -__int_as_float(0x7F800000); }
 };
 
 // R densities
 template <typename Real> BSSM_DEV Real dnorm_log(Real x, Real mu, Real sigma, Real log_sigma) {
-  Real z = (x - mu) / sigma;
+  Real z = Math<Real>::div_(x - mu, sigma);
   return -((Real)0.918938533204672741780329736406 + (Real)0.5 * z * z + log_sigma);
 }
 template <typename Real> BSSM_DEV Real dpois_log(Real y, Real lambda) {

@@ -30,7 +30,8 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   if (nb_max > FAST_MAX_NB) { set_error("persistent kernel: %d particles per CTA exceed %d", nb_max, FAST_MAX_NB); return BSSM_ERR_UNSUPPORTED; }
   int threads = (nb_max / FAST_PPT + 31) / 32 * 32;
   if (threads < 32) threads = 32;
-  size_t smem = (size_t)nb_max * sizeof(double) + (size_t)4 * G * sizeof(double) + (4 * 32 + 16) * sizeof(double) + (size_t)nb_max * sizeof(Real);
+  const int cap = nb_max + FAST_SLACK;
+  size_t smem = (size_t)4 * G * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
   auto kern = k_fast_bpf<Model, Real>;
   BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -40,7 +41,7 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   int ngroups = (int)(resident / G);
   if (ngroups > f.C) ngroups = f.C;
   FastParams P;
-  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = nb_max;
+  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = nb_max; P.cap = cap;
   BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, (size_t)ngroups * 2 * G, &P.rec));
   BSSM_TRY(scratch(ctx, SL_FAST_BASE + 1, (size_t)ngroups * G, &P.rec2));
   BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, (size_t)ngroups * G * nb_max * sizeof(Real), &P.xnew));

@@ -4,18 +4,22 @@
 // A filter is run by a GROUP of G co-resident CTAs (cooperative launch); CTA b owns the
 // contiguous slice [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps
 // (PPT particles per thread).  Per observation:
-//   P1  propagate (Philox normals, one Philox call per 4 particles) + log-weight, block max,
-//       block sums of e = exp(lw - max_b), e^2, e*x                         [registers + shuffles]
-//   B1  each CTA publishes (max_b, sums) as an epoch-stamped record in L2; every CTA polls the G
-//       records (release/acquire, no atomics) and derives, redundantly but identically, the global
-//       max / sum / ESS / resampling decision and its own cdf offset          [1 L2 round trip]
-//   P3  local fp64 cdf of the normalised weights into shared memory (block scan)
-//   P4  each CTA serves the contiguous run of OUTPUT slots whose positions (i + U_i)/N fall inside
-//       its cdf interval: lower_bound in shared memory, coalesced store of the chosen x to x_new
+//   P1  propagate (normals pre-generated while waiting at the previous sync point; one Philox call
+//       per 4 particles) + log-weight; block max; e = exp(lw - max_b); block sums of e, e^2, e*x
+//       and the block-local fp64 inclusive scan of e                         [registers + shuffles]
+//   B1  every CTA publishes (max_b, sums) as an epoch-stamped record in L2 and polls the G records
+//       (release/acquire, no atomics); all CTAs then derive, redundantly but bit-identically, the
+//       global max / sum / ESS / resampling decision and their own cdf interval  [1 L2 round trip]
+//   P3  INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form -- the
+//       number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
+//       slots [F(c_{j-1}), F(c_j)).  No search.  The stratified uniforms of the CTA's output range
+//       are staged once in shared memory (one Philox call per 4 slots).
+//   P4  the chosen x are scattered into a shared-memory staging buffer and copied out to x_new
+//       with coalesced 16-byte stores
 //   B2  epoch-stamped "done" records; every CTA reloads its slice of x_new     [1 L2 round trip]
-// Nothing but x_new (4 B write + 4 B read per particle, L2 resident) and the tiny records leaves
-// the SM.  Same Philox keying and tie rule as the general engine, so results are independent of
-// G and of the launch geometry up to floating-point summation order.
+// Only x_new (one write + one read per particle, L2 resident) and the tiny records leave the SM.
+// Same Philox keying and tie rule (first j with cdf[j] >= pos, clamp) as the general engine, so
+// results do not depend on G or the launch geometry beyond floating-point summation order.
 #pragma once
 #include "bssm_common.cuh"
 #include "bssm_filter.cuh"
@@ -27,6 +31,9 @@ constexpr int FAST_PPT = 8;          // particles per thread (registers)
 constexpr int FAST_THREADS = 896;    // max threads per CTA (<= 72 registers each)
 constexpr int FAST_MAX_NB = FAST_THREADS * FAST_PPT;  // 7168 particles per CTA
 constexpr int FAST_MAX_G = 256;      // CTAs per group
+constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
+constexpr int FAST_HEAVY = 48;       // offspring count above which a source is expanded cooperatively
+constexpr int FAST_HEAVY_CAP = 64;
 
 struct __align__(64) FastRec {   // published once per observation by each CTA
   double m, s, q, sx;
@@ -47,6 +54,7 @@ struct FastParams {
   FastRec2* rec2;   // [ngroups][G]
   void* xnew;       // [ngroups][G * nb_max] Real
   int nb_max;       // slice stride (multiple of FAST_PPT)
+  int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
 };
 
 __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
@@ -71,45 +79,34 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
 
-// number of output slots i in [0, n) whose position is <= c, i.e. #{ i : pos_i <= c }.
-// pos_i = (i + U_i) / n (stratified, U_i = Philox word of slot i) or (i + U) / n (systematic).
-// Positions are non-decreasing in i, so this is the first i with pos_i > c.
-struct PosGen {
-  NoiseKey key; unsigned int obs; int fn; int n; bool pow2; double inv_n; double u_sys;
+// Output-slot bookkeeping of one resampling step.  Position of slot i: (i + U_i) / n (stratified,
+// U_i = Philox word of slot i) or (i + U) / n (systematic).  count_le(c) = #{ i : pos_i <= c }
+// = first slot whose position exceeds c.  With t = c*n and i = floor(t): slots below i have
+// i' + U < i' + 1 <= t, slots above have i' >= i + 1 > t, so only slot i needs a look.
+struct SlotCounter {
+  NoiseKey key; unsigned int obs; int fn; int n; double u_sys;
+  const unsigned int* s_u; int u_base, u_cap;   // staged Philox words for slots [u_base, u_base + u_cap)
   __device__ __forceinline__ double u_of(int i) const {
     if (fn == 1) return u_sys;
-    uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);
+    int k = i - u_base;
+    if (k >= 0 && k < u_cap) return word_to_unit_f64(s_u[k]);
+    uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);   // outside the staged window (rare)
     return word_to_unit_f64(q.w[i & 3]);
   }
-  __device__ __forceinline__ double pos(int i, double u) const {
-    double s = (double)i + u;
-    return pow2 ? s * inv_n : s / (double)n;
-  }
   __device__ __forceinline__ int count_le(double c) const {
-    if (!(c > 0.0)) return 0;
     double t = c * (double)n;
-    int i = (t >= (double)n) ? n - 1 : (int)t;   // candidate: stratum containing c
-    // move down while slot i is above c, up while the next slot is still <= c
-    while (i >= 0 && pos(i, u_of(i)) > c) i--;
-    while (i + 1 < n && pos(i + 1, u_of(i + 1)) <= c) i++;
-    return i + 1;
+    if (!(t > 0.0)) return 0;
+    if (t >= (double)n) return n;
+    int i = (int)t;
+    return i + (((double)i + u_of(i)) <= t ? 1 : 0);
   }
 };
-
-// first j in [lo, n_loc-1] with cdf[j] >= p (clamped to n_loc-1); cdf in shared memory
-__device__ __forceinline__ int smem_lower_bound(const double* cdf, int lo, int n_loc, double p) {
-  int hi = n_loc - 1;
-  if (lo >= hi || cdf[lo] >= p) return lo < hi ? lo : hi;
-  lo++;
-  if (lo >= hi || cdf[lo] >= p) return lo < hi ? lo : hi;
-  lo++;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (cdf[mid] < p) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 template <typename Model, typename Real>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
@@ -121,18 +118,24 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
   const int group = blockIdx.x / G, b = blockIdx.x % G;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   // shared memory carve-up
-  double* s_cdf = (double*)smem_raw;                               // [nb_max]
-  double* s_tab = s_cdf + P.nb_max;                                // [4][G]: m, s, q, sx of every CTA
-  double* s_red = s_tab + 4 * G;                                   // [4][32] reduction scratch
-  Real* s_x = (Real*)(s_red + 4 * 32 + 16);                        // [nb_max]
-  __shared__ int s_flag[4];
-  __shared__ double s_misc[8];
+  double* s_tab = (double*)smem_raw;                 // [4][G]: m, s, q, sx of every CTA
+  double* s_red = s_tab + 4 * G;                     // [5][32] per-warp partials
+  Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
+  unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
+  __shared__ int s_flag[2];
+  __shared__ int s_wf[32];
+  __shared__ int s_heavy_n;
+  __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
+  __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
+  // scalars of the current step, written by thread 0 in P2
+  __shared__ double s_lo, s_hi, s_wscale, s_ll;
+  __shared__ int s_resample, s_dead;
 
   FastRec* rec = P.rec + (size_t)group * 2 * G;
   FastRec2* rec2 = P.rec2 + (size_t)group * G;
   Real* xnew = (Real*)P.xnew + (size_t)group * G * P.nb_max;
   unsigned int ep1 = 0, ep2 = 0;   // record epochs (B1 / B2): identical sequences in every CTA of the group
-  if (tid < 4) s_flag[tid] = 0;
+  if (tid < 2) s_flag[tid] = 0;
   __syncthreads();
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
 
@@ -144,11 +147,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
     const int base = b * nb;                                  // first global particle of this CTA
     const int n_loc = max(0, min(n - base, nb));              // particles owned by this CTA
     const int ibase = base + tid * FAST_PPT;                  // first global particle of this thread
-    const bool pow2 = (n & (n - 1)) == 0;
+    const int n_own = max(0, min(FAST_PPT, min(n - ibase, nb - tid * FAST_PPT)));  // owned particles of this thread
     Real par[Model::NPAR];
     Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
     const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
     const int T1 = f.T + 1;
+    int ralg = f.ralg;
+    double thr = f.threshold;
+    if (thr < 0) thr = (ralg == 0) ? __longlong_as_double(0x7FF0000000000000LL) : (ralg == 1 ? (double)n : (double)n / 2.0);
 
     // ---- init (R/particle_filter_core.R:76-116) ----
     Real x[FAST_PPT];
@@ -156,23 +162,21 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
 #pragma unroll
     for (int h = 0; h < FAST_PPT / 4; h++) {
       uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
-      Real z0, z1, z2, z3;
-      Math<Real>::box_muller(qd.w[0], qd.w[1], z0, z1);
-      Math<Real>::box_muller(qd.w[2], qd.w[3], z2, z3);
-      Real zz[4] = {z0, z1, z2, z3};
+      Real zz[4];
+      Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
+      Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         Real xi[1]; Real zi[1] = {zz[k]};
         Model::template init<Real>(xi, par, zi, nullptr);
         x[4 * h + k] = xi[0];
-        if (ibase + 4 * h + k < n && tid * FAST_PPT + 4 * h + k < nb) sum0 += (double)xi[0];
+        if (4 * h + k < n_own) sum0 += (double)xi[0];
       }
     }
-    // t = 0 outputs need the global mean: publish through the same record path
     double loglike = 0.0;
     int n_resampled = 0;
-    bool dead = false;
-    // block sum of sum0 -> record; CTA 0 gathers the t = 0 state estimate
+    if (tid == 0) { s_ll = 0.0; s_heavy_n = 0; }
+    // t = 0 state estimate: block sum -> record; CTA 0 gathers
     {
       double v = warp_sum_d(sum0);
       if (lane == 0) s_red[wid] = v;
@@ -209,6 +213,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       __syncthreads();
     }
 
+    // normals of the next transition, generated ahead of time (they do not depend on x)
+    Real zpre[FAST_PPT];
+    int zpre_t = -1;   // absolute time index (tnow - 1) the pre-generated normals belong to
+    auto gen_normals = [&](int tz, Real* z) {
+#pragma unroll
+      for (int h = 0; h < FAST_PPT / 4; h++) {
+        uint4x qd = noise_quad(key, (unsigned int)tz, TAG_TRANS_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
+        Math<Real>::box_muller(qd.w[0], qd.w[1], z[4 * h + 0], z[4 * h + 1]);
+        Math<Real>::box_muller(qd.w[2], qd.w[3], z[4 * h + 2], z[4 * h + 3]);
+      }
+    };
+
     for (int obs = 0; obs < f.T; obs++) {
       const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
       const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
@@ -216,80 +232,85 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
 
       // ---- P1: propagate + log-weight ----
-      Real lw[FAST_PPT];
       for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
+        if (zpre_t != tnow - 1) gen_normals(tnow - 1, zpre);
 #pragma unroll
-        for (int h = 0; h < FAST_PPT / 4; h++) {
-          uint4x qd = noise_quad(key, (unsigned int)(tnow - 1), TAG_TRANS_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
-          Real z0, z1, z2, z3;
-          Math<Real>::box_muller(qd.w[0], qd.w[1], z0, z1);
-          Math<Real>::box_muller(qd.w[2], qd.w[3], z2, z3);
-          Real zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            Real zi[1] = {zz[k]};
-            Model::template transition<Real>(&x[4 * h + k], par, tnow, zi, nullptr);
-          }
+        for (int k = 0; k < FAST_PPT; k++) {
+          Real zi[1] = {zpre[k]};
+          Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
         }
       }
+      Real e[FAST_PPT];   // first the log-weights, then exp(lw - block max)
       Real mloc = Math<Real>::ninf();
       int nanf = 0;
 #pragma unroll
       for (int k = 0; k < FAST_PPT; k++) {
-        const bool own = (ibase + k < n) && (tid * FAST_PPT + k < nb);
+        const bool own = k < n_own;
         if (!own) x[k] = (Real)0;   // padding lanes never hold garbage (x_new beyond n is not written)
         Real l = Model::template loglik<Real>(yv, &x[k], par, ot);
         if (!own) l = Math<Real>::ninf();
         if (l != l) nanf = 1;
-        lw[k] = l;
+        e[k] = l;
         mloc = l > mloc ? l : mloc;
       }
-      // block max
+      // block max: per-warp partials, then every warp reduces the partials redundantly (one barrier)
       {
         Real v = mloc;
 #pragma unroll
         for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
         nanf = __any_sync(0xffffffffu, nanf);
         if (lane == 0) { s_red[wid] = (double)v; s_red[32 + wid] = (double)nanf; }
-        __syncthreads();
-        if (wid == 0) {
-          double t = lane < nw ? s_red[lane] : NINF;
-          double nf = lane < nw ? s_red[32 + lane] : 0.0;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) { double u = __shfl_xor_sync(0xffffffffu, t, o); t = u > t ? u : t; nf += __shfl_xor_sync(0xffffffffu, nf, o); }
-          if (lane == 0) { s_misc[0] = t; s_misc[1] = nf; }
-        }
-        __syncthreads();
       }
-      const double mb = s_misc[0];
-      const int nan_b = s_misc[1] != 0.0;
-      // e = exp(lw - mb); block sums
-      Real e[FAST_PPT];
-      double ts = 0.0, tq = 0.0, tx = 0.0;
+      __syncthreads();
+      double mb, nan_b;
       {
-        Real fs = 0, fq = 0, fx = 0;
+        double t = lane < nw ? s_red[lane] : NINF;
+        double nf = lane < nw ? s_red[32 + lane] : 0.0;
+        mb = warp_max_d(t);
+        nan_b = warp_max_d(nf);
+      }
+      // e = exp(lw - mb); thread sums; block-local inclusive scan of e (fp64)
+      double run = 0.0;      // this thread's sum of e
+      double exu;            // block-local exclusive prefix of this thread (unnormalised)
+      {
+        Real fq = 0, fx = 0;
+        const Real mbr = (Real)mb;
 #pragma unroll
         for (int k = 0; k < FAST_PPT; k++) {
-          Real ek = (lw[k] == Math<Real>::ninf() || mb == NINF) ? (Real)0 : FastMath<Real>::exp_(lw[k] - (Real)mb);
+          Real ek = (e[k] == Math<Real>::ninf() || mb == NINF) ? (Real)0 : FastMath<Real>::exp_(e[k] - mbr);
           e[k] = ek;
-          fs += ek; fq += ek * ek; fx += ek * x[k];
+          run += (double)ek; fq += ek * ek; fx += ek * x[k];
         }
-        ts = warp_sum_d((double)fs); tq = warp_sum_d((double)fq); tx = warp_sum_d((double)fx);
-        if (lane == 0) { s_red[wid] = ts; s_red[32 + wid] = tq; s_red[64 + wid] = tx; }
+        double inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        double tq = warp_sum_d((double)fq), tx = warp_sum_d((double)fx);
+        __syncthreads();   // s_red partials of the max have been consumed by every warp
+        if (lane == 31) s_red[wid] = inc;            // warp totals of e
+        if (lane == 0) { s_red[32 + wid] = tq; s_red[64 + wid] = tx; }
+        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        exu = lane == 0 ? 0.0 : prev;                // exclusive within the warp
         __syncthreads();
+        // every warp scans the warp totals redundantly
+        double wt = lane < nw ? s_red[lane] : 0.0;
+        double winc = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        double woff = __shfl_sync(0xffffffffu, winc - wt, wid);   // exclusive prefix of this warp
+        exu += woff;
         if (wid == 0) {
-          double a0 = lane < nw ? s_red[lane] : 0.0, a1 = lane < nw ? s_red[32 + lane] : 0.0, a2 = lane < nw ? s_red[64 + lane] : 0.0;
-          a0 = warp_sum_d(a0); a1 = warp_sum_d(a1); a2 = warp_sum_d(a2);
+          double a0 = __shfl_sync(0xffffffffu, winc, 31);
+          double a1 = warp_sum_d(lane < nw ? s_red[32 + lane] : 0.0), a2 = warp_sum_d(lane < nw ? s_red[64 + lane] : 0.0);
           if (lane == 0) {
             FastRec* r = &rec[((ep1 + 1) & 1) * G + b];
-            r->m = mb; r->s = a0; r->q = a1; r->sx = a2; r->nan = nan_b;
+            r->m = mb; r->s = a0; r->q = a1; r->sx = a2; r->nan = nan_b != 0.0;
             __threadfence();
             st_release_u32(&r->epoch, ep1 + 1);
           }
         }
       }
       ep1++;
-      // ---- B1: poll the G records, build the scaled table ----
+      // ---- B1: poll the G records ----
       for (int j = tid; j < G; j += blockDim.x) {
         const FastRec* r = &rec[(ep1 & 1) * G + j];
         while (ld_acquire_u32(&r->epoch) != ep1) {}
@@ -300,21 +321,19 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         if (__ldcg(&r->nan)) s_flag[0] = 1;
       }
       __syncthreads();
-      // ---- P2: global max / sums / offsets: warp 0, fixed order => identical in every CTA ----
+      // ---- P2: global max / sums / this CTA's cdf interval; warp 0, fixed order => identical in every CTA ----
       if (wid == 0) {
         double M = NINF;
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { double u = __shfl_xor_sync(0xffffffffu, M, o); M = u > M ? u : M; }
-        double S = 0.0, Q = 0.0, SX = 0.0, carry = 0.0, mine_lo = 0.0, mine_hi = 0.0;
+        M = warp_max_d(M);
+        double Q = 0.0, SX = 0.0, carry = 0.0, mine_lo = 0.0, mine_hi = 0.0;
         for (int j0 = 0; j0 < G; j0 += 32) {
           int j = j0 + lane;
-          double sc = 0.0, sj = 0.0, qj = 0.0, xj = 0.0;
+          double sj = 0.0, qj = 0.0, xj = 0.0;
           if (j < G) {
-            sc = (s_tab[j] == NINF || M == NINF) ? 0.0 : exp(s_tab[j] - M);
+            double sc = (s_tab[j] == NINF || M == NINF) ? 0.0 : exp(s_tab[j] - M);
             sj = s_tab[G + j] * sc; qj = s_tab[2 * G + j] * sc * sc; xj = s_tab[3 * G + j] * sc;
           }
-          // inclusive scan of sj over the warp (fixed order)
           double inc = sj;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -325,105 +344,150 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
           carry = __shfl_sync(0xffffffffu, incl, 31);
           Q += qj; SX += xj;
         }
-        S = carry;
+        const double S = carry;
         Q = warp_sum_d(Q); SX = warp_sum_d(SX);
         mine_lo = warp_sum_d(mine_lo); mine_hi = warp_sum_d(mine_hi);  // only one lane is non-zero
-        if (lane == 0) { s_misc[2] = M; s_misc[3] = S; s_misc[4] = Q; s_misc[5] = SX; s_misc[6] = mine_lo; s_misc[7] = mine_hi; }
+        if (lane == 0) {
+          int dead = 0, resample = 0;
+          if (s_flag[0]) {              // NaN weight somewhere: R's `if (NA)` error
+            if (b == 0) f.status[c] = 3;
+            dead = 1; s_flag[0] = 0;
+          } else if (M < -1e8) {        // all(lw < -1e8): R/particle_filter_core.R:189-202
+            loglike = NINF;
+            if (b == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
+            dead = 1;
+          } else {
+            loglike += (M + log(S) - log((double)n));
+            const double ess = (S * S) / Q;
+            resample = (ralg == 0) ? 0 : (ralg == 1 ? 1 : (ess < thr));
+            if (b == 0) {
+              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+              f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
+              if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+            }
+            s_lo = mine_lo / S;
+            s_hi = (b == G - 1) ? 2.0 : mine_hi / S;
+            s_wscale = ((mb == NINF) ? 0.0 : exp(mb - M)) / S;
+          }
+          s_dead = dead; s_resample = resample; s_ll = loglike; s_heavy_n = 0;
+        }
       }
       __syncthreads();
-      const double M = s_misc[2], S = s_misc[3], Q = s_misc[4], SX = s_misc[5];
-      if (s_flag[0]) {  // NaN weight somewhere: R's `if (NA)` error
-        if (b == 0 && tid == 0) { f.status[c] = 3; }
-        dead = true;
-      } else if (M < -1e8) {  // all(lw < -1e8): R/particle_filter_core.R:189-202
-        loglike = NINF;
-        if (b == 0 && tid == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
-        dead = true;
-      }
-      if (dead) { __syncthreads(); if (tid == 0) s_flag[0] = 0; __syncthreads(); break; }
-      loglike += (M + log(S) - log((double)n));
-      const double ess = (S * S) / Q;
-      int ralg = f.ralg;
-      double thr = f.threshold;
-      if (thr < 0) thr = (ralg == 0) ? __longlong_as_double(0x7FF0000000000000LL) : (ralg == 1 ? (double)n : (double)n / 2.0);
-      const bool resample = (ralg == 0) ? false : (ralg == 1 ? true : (ess < thr));
-      if (b == 0 && tid == 0) {
-        if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-        f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
-        if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-      }
-      if (!resample) continue;
+      if (s_dead) break;
+      if (!s_resample) continue;
       n_resampled++;
 
-      // ---- P3: local cdf (normalised weights, fp64) and x into shared memory ----
-      const double lo_cdf = s_misc[6] / S, hi_cdf = (b == G - 1) ? 2.0 : s_misc[7] / S;   // this CTA's cdf interval (lo, hi]
-      const double wscale = ((mb == NINF) ? 0.0 : exp(mb - M)) / S;
+      // ---- P3: closed-form offspring ranges ----
+      const double lo_cdf = s_lo, hi_cdf = s_hi, wscale = s_wscale;
+      SlotCounter sc;
+      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.u_sys = 0.0;
+      sc.s_u = s_u; sc.u_cap = P.cap;
       {
-        double loc[FAST_PPT];
-        double run = 0.0;
-#pragma unroll
-        for (int k = 0; k < FAST_PPT; k++) { run += (double)e[k] * wscale; loc[k] = run; }
-        double inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_red[wid] = inc;
+        double t0 = lo_cdf * (double)n;
+        int i0 = t0 >= (double)n ? n : (int)t0;
+        sc.u_base = max(0, (i0 & ~3) - 4);
+      }
+      if (P.resample_fn == 1) {
+        uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
+        sc.u_sys = word_to_unit_f64(q0.w[0]);
+      } else {
+        // stage the Philox words of the slots this CTA is expected to serve: one call per 4 slots
+        const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
+        for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += blockDim.x) {
+          uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+          *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+        }
         __syncthreads();
-        double woff = 0.0;
-        for (int w = 0; w < wid; w++) woff += s_red[w];
-        const double ex = lo_cdf + (woff + (inc - run));
+      }
+      const int o_lo = sc.count_le(lo_cdf);
+      const int o_hi = (b == G - 1) ? n : sc.count_le(hi_cdf);
+      // F of this thread's sources (monotone by a running max; clamped into [o_lo, o_hi])
+      int F[FAST_PPT];
+      {
+        double acc = exu;
+        int fmax = o_lo;
 #pragma unroll
         for (int k = 0; k < FAST_PPT; k++) {
-          int li = tid * FAST_PPT + k;
-          if (li < nb) { s_cdf[li] = ex + loc[k]; s_x[li] = x[k]; }
+          acc += (double)e[k];
+          int v = o_lo;
+          if (k < n_own) {
+            double cj = lo_cdf + acc * wscale;
+            v = sc.count_le(cj);
+            if (tid * FAST_PPT + k == n_loc - 1) v = o_hi;     // clamp: the last particle takes what is left
+            v = min(max(v, o_lo), o_hi);
+          }
+          fmax = max(fmax, v);
+          F[k] = fmax;
         }
-      }
-      // output range served by this CTA: positions in (lo_cdf, hi_cdf]
-      PosGen pg;
-      pg.key = key; pg.obs = (unsigned int)obs; pg.fn = P.resample_fn; pg.n = n; pg.pow2 = pow2; pg.inv_n = 1.0 / (double)n;
-      pg.u_sys = 0.0;
-      if (P.resample_fn == 1) { uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u); pg.u_sys = word_to_unit_f64(q0.w[0]); }
-      if (tid == 0) s_flag[2] = pg.count_le(lo_cdf);
-      if (tid == 32 % blockDim.x) s_flag[3] = (b == G - 1) ? n : pg.count_le(hi_cdf);
-      __syncthreads();
-      const int o_lo = s_flag[2], o_hi = s_flag[3];
-      // ---- P4: search + scatter (outputs are handled in aligned quads: one Philox call per 4) ----
-      double sumx = 0.0;
-      if (n_loc > 0 && o_hi > o_lo) {
-        Real fsum = 0;
-        for (int qd = (o_lo >> 2) + tid; qd <= ((o_hi - 1) >> 2); qd += blockDim.x) {
-          uint4x uq;
-          if (P.resample_fn == 0) uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-          int j = 0;
-          Real v[4];
+        // exclusive prefix-max of the per-thread last F over the block
+        int inc = F[FAST_PPT - 1];
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            int i = 4 * qd + k;
-            v[k] = 0;
-            if (i >= o_lo && i < o_hi) {
-              double u = (P.resample_fn == 0) ? word_to_unit_f64(uq.w[k]) : pg.u_sys;
-              double p = pg.pos(i, u);
-              j = smem_lower_bound(s_cdf, j, n_loc, p);
-              v[k] = s_x[j];
-              fsum += v[k];
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+        if (lane == 31) s_wf[wid] = inc;
+        int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) prev = o_lo;
+        __syncthreads();
+        int wv = lane < nw ? s_wf[lane] : o_lo;
+        int winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc = max(winc, t); }
+        int wprev = __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);
+        if (wid == 0) wprev = o_lo;
+        prev = max(prev, wprev);
+        // fold the predecessor's value into this thread's F
+#pragma unroll
+        for (int k = 0; k < FAST_PPT; k++) F[k] = max(F[k], prev);
+        // ---- P4: scatter into the staging buffer (chunks of `cap` slots), copy out coalesced ----
+        const int o_base = o_lo & ~3;
+        double sumx = 0.0;
+        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
+          const int c1 = min(o_hi, c0 + P.cap);
+          int lo_k = prev;
+#pragma unroll
+          for (int k = 0; k < FAST_PPT; k++) {
+            const int hi_k = F[k];
+            if (k < n_own && hi_k > lo_k) {
+              if (c0 == o_base) sumx += (double)(hi_k - lo_k) * (double)x[k];
+              const int a = max(lo_k, c0), z = min(hi_k, c1);
+              if (z - a > FAST_HEAVY) {
+                int slot = atomicAdd(&s_heavy_n, 1);
+                if (slot < FAST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = z; s_heavy_x[slot] = x[k]; }
+                else for (int o = a; o < z; o++) s_out[o - c0] = x[k];
+              } else {
+                for (int o = a; o < z; o++) s_out[o - c0] = x[k];
+              }
+            }
+            lo_k = max(lo_k, hi_k);
+          }
+          __syncthreads();
+          const int nh = min(s_heavy_n, FAST_HEAVY_CAP);
+          for (int h = 0; h < nh; h++) {
+            const int a = s_heavy_lo[h], z = s_heavy_hi[h];
+            const Real xv = s_heavy_x[h];
+            for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
+          }
+          if (nh) __syncthreads();
+          // copy out: aligned 16-byte stores in the middle, scalars at the ragged ends
+          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
+          for (int o = c0 + 4 * tid; o < last; o += 4 * blockDim.x) {
+            if (o >= first && o + 3 < last) {
+              if (sizeof(Real) == 4) __stcg((float4*)((float*)xnew + o), *(const float4*)((const float*)s_out + (o - c0)));
+              else {
+                __stcg((double2*)((double*)xnew + o), *(const double2*)((const double*)s_out + (o - c0)));
+                __stcg((double2*)((double*)xnew + o + 2), *(const double2*)((const double*)s_out + (o - c0) + 2));
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; k++) if (o + k >= first && o + k < last) __stcg(&xnew[o + k], s_out[o + k - c0]);
             }
           }
-          int i0 = 4 * qd;
-          if (i0 >= o_lo && i0 + 3 < o_hi) {
-            if (sizeof(Real) == 4) __stcg((float4*)((float*)xnew + i0), make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]));
-            else { __stcg((double2*)((double*)xnew + i0), make_double2((double)v[0], (double)v[1])); __stcg((double2*)((double*)xnew + i0 + 2), make_double2((double)v[2], (double)v[3])); }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (i0 + k >= o_lo && i0 + k < o_hi) __stcg(&xnew[i0 + k], v[k]);
-          }
+          if (tid == 0) s_heavy_n = 0;
+          __syncthreads();
         }
-        sumx = (double)fsum;
-      }
-      // block sum of sumx, publish "done"
-      {
+        // block sum of sumx, publish "done"
         double v = warp_sum_d(sumx);
-        __syncthreads();   // all scatter stores issued before the release below (and s_red reuse)
         if (lane == 0) s_red[wid] = v;
-        __syncthreads();
+        __syncthreads();   // (also orders every scatter store of this CTA before the release below)
         if (wid == 0) {
           double t = lane < nw ? s_red[lane] : 0.0;
           t = warp_sum_d(t);
@@ -436,6 +500,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         }
       }
       ep2++;
+      // overlap the L2 round trip with the next transition's normals
+      if (obs + 1 < f.T) { zpre_t = ot; gen_normals(ot, zpre); }
       // ---- B2: wait for every CTA's scatter, reload this CTA's slice ----
       double tot = 0.0;
       for (int j = tid; j < G; j += blockDim.x) {
@@ -466,7 +532,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         }
       }
     }  // obs
-    if (b == 0 && tid == 0) { f.loglike[c] = loglike; f.n_resampled[c] = n_resampled; }
+    if (b == 0 && tid == 0) { f.loglike[c] = s_ll; f.n_resampled[c] = n_resampled; }
     __syncthreads();
   }    // filters
 }
