@@ -78,19 +78,22 @@ template <> struct Math<double> {
   static BSSM_DEV double ninf() { return -__longlong_as_double(0x7FF0000000000000LL); }
 };
 template <> struct Math<float> {
-  static BSSM_DEV float unit(uint32_t w) { return word_to_unit_f32(w); }
+  // Throughput precision.  Uniforms come from the top 23 bits of a Philox word by bit assembly
+  // (no int->float conversion on the XU pipe), logarithm / square root / sine / cosine / exp on the SFU.
+  static BSSM_DEV float unit(uint32_t w) { return (__uint_as_float(0x3F800000u | (w >> 9)) - 1.0f) + 5.9604645e-8f; }  // (0, 1)
+  static BSSM_DEV float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
   static BSSM_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    float u1 = word_to_unit_f32(a), u2 = word_to_unit_f32(b);
-    float r = sqrtf(-2.0f * __logf(u1));
+    float u1 = unit(a), u2 = unit(b);
+    float r = sqrt_approx(-2.0f * __logf(u1));
     float s, c;
-    __sincosf(6.283185307179586f * u2, &s, &c);  // argument in [0, 2pi): fast path is accurate here
+    __sincosf(6.283185307179586f * u2, &s, &c);  // argument in (0, 2pi): the SFU path is accurate to ~1e-6 here
     n0 = r * c; n1 = r * s;
   }
   static BSSM_DEV float exp_(float x) { return __expf(x); }
   static BSSM_DEV float log_(float x) { return logf(x); }
-  // throughput precision: reduce to [-pi, pi] with a two-term 2*pi, then the SFU (abs. error < 1e-6)
+  // reduce to [-pi, pi] with a two-term 2*pi (round-to-nearest by the 1.5*2^23 trick), then the SFU (abs. error < 1e-6)
   static BSSM_DEV float reduce_2pi(float x) {
-    float k = rintf(x * 0.15915494309189535f);
+    float k = (x * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
     float r = fmaf(k, -6.2831854820251465f, x);
     return fmaf(k, 1.7484556e-7f, r);
   }

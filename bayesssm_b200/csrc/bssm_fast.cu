@@ -2,6 +2,8 @@
 #include "bssm_engine.cuh"
 #include "bssm_fast.cuh"
 
+#include <stdlib.h>
+
 namespace bssm {
 
 bool fast_supported(const FilterDev& f, const FilterLaunch& L) {
@@ -12,27 +14,24 @@ bool fast_supported(const FilterDev& f, const FilterLaunch& L) {
   return true;
 }
 
-template <typename Model, typename Real>
-static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
+static int fast_ppt_choice(int nb_max) {
+  const char* e = getenv("BSSM_FAST_PPT");
+  if (e && atoi(e) == 8) return 8;
+  if (e && atoi(e) == 16) return 16;
+  return nb_max >= 2048 ? 16 : 8;
+}
+
+template <typename Model, typename Real, int PPT>
+static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G) {
   const int nsm = ctx->prop.multiProcessorCount;
-  // group size: as few CTAs as hold the particles, widened to fill the chip when there are few filters
-  int G = (f.N + FAST_MAX_NB - 1) / FAST_MAX_NB;
-  if (f.C * G < nsm) {
-    int wide = nsm / f.C;
-    int cap = (f.N + 1023) / 1024;   // keep >= ~1024 particles per CTA
-    if (wide > cap) wide = cap;
-    if (wide > G) G = wide;
-  }
-  if (G > FAST_MAX_G) G = FAST_MAX_G;
-  if (G < 1) G = 1;
   int nb_max = (f.N + G - 1) / G;
-  nb_max = (nb_max + FAST_PPT - 1) / FAST_PPT * FAST_PPT;
+  nb_max = (nb_max + PPT - 1) / PPT * PPT;
   if (nb_max > FAST_MAX_NB) { set_error("persistent kernel: %d particles per CTA exceed %d", nb_max, FAST_MAX_NB); return BSSM_ERR_UNSUPPORTED; }
-  int threads = (nb_max / FAST_PPT + 31) / 32 * 32;
+  int threads = (nb_max / PPT + 31) / 32 * 32;
   if (threads < 32) threads = 32;
   const int cap = nb_max + FAST_SLACK;
   size_t smem = (size_t)4 * G * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
-  auto kern = k_fast_bpf<Model, Real>;
+  auto kern = k_fast_bpf<Model, Real, PPT>;
   BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   BSSM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -55,8 +54,21 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
 
 template <typename Model>
 static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
-  if (L.precision == BSSM_F64) return fast_launch<Model, double>(ctx, f, L);
-  return fast_launch<Model, float>(ctx, f, L);
+  const int nsm = ctx->prop.multiProcessorCount;
+  // group size: as few CTAs as hold the particles, widened to fill the chip when there are few filters
+  int G = (f.N + FAST_MAX_NB - 1) / FAST_MAX_NB;
+  if (f.C * G < nsm) {
+    int wide = nsm / f.C;
+    int cap = (f.N + 1023) / 1024;   // keep >= ~1024 particles per CTA
+    if (wide > cap) wide = cap;
+    if (wide > G) G = wide;
+  }
+  if (G > FAST_MAX_G) G = FAST_MAX_G;
+  if (G < 1) G = 1;
+  const int nb = (f.N + G - 1) / G;
+  if (L.precision == BSSM_F64) return fast_launch<Model, double, 8>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16>(ctx, f, L, G);
+  return fast_launch<Model, float, 8>(ctx, f, L, G);
 }
 
 int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {

@@ -6,10 +6,11 @@
 // (PPT particles per thread).  Per observation:
 //   P1  propagate (normals pre-generated while waiting at the previous sync point; one Philox call
 //       per 4 particles) + log-weight; block max; e = exp(lw - max_b); block sums of e, e^2, e*x
-//       and the block-local fp64 inclusive scan of e                         [registers + shuffles]
-//   B1  every CTA publishes (max_b, sums) as an epoch-stamped record in L2 and polls the G records
-//       (release/acquire, no atomics); all CTAs then derive, redundantly but bit-identically, the
-//       global max / sum / ESS / resampling decision and their own cdf interval  [1 L2 round trip]
+//       and the block-local inclusive scan of e                              [registers + shuffles]
+//   B1  every CTA publishes (max_b, sums) as an epoch-stamped record in L2, generates the NEXT
+//       step's normals while the record travels, then polls the G records (release/acquire, no
+//       atomics); all CTAs derive, redundantly but bit-identically, the global max / sum / ESS /
+//       resampling decision and the cdf interval of every CTA                  [1 L2 round trip]
 //   P3  INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form -- the
 //       number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
 //       slots [F(c_{j-1}), F(c_j)).  No search.  The stratified uniforms of the CTA's output range
@@ -20,6 +21,8 @@
 // Only x_new (one write + one read per particle, L2 resident) and the tiny records leave the SM.
 // Same Philox keying and tie rule (first j with cdf[j] >= pos, clamp) as the general engine, so
 // results do not depend on G or the launch geometry beyond floating-point summation order.
+// In the throughput precision (Real = float) the within-thread part of the cdf and the slot
+// arithmetic run in fp32 relative to an fp64 per-thread origin.
 #pragma once
 #include "bssm_common.cuh"
 #include "bssm_filter.cuh"
@@ -27,12 +30,10 @@
 
 namespace bssm {
 
-constexpr int FAST_PPT = 8;          // particles per thread (registers)
-constexpr int FAST_THREADS = 896;    // max threads per CTA (<= 72 registers each)
-constexpr int FAST_MAX_NB = FAST_THREADS * FAST_PPT;  // 7168 particles per CTA
+constexpr int FAST_MAX_NB = 7168;    // particles per CTA
 constexpr int FAST_MAX_G = 256;      // CTAs per group
 constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
-constexpr int FAST_HEAVY = 48;       // offspring count above which a source is expanded cooperatively
+constexpr int FAST_HEAVY = 64;       // offspring count above which a source is expanded cooperatively
 constexpr int FAST_HEAVY_CAP = 64;
 
 struct __align__(64) FastRec {   // published once per observation by each CTA
@@ -53,7 +54,7 @@ struct FastParams {
   FastRec* rec;     // [ngroups][2][G]
   FastRec2* rec2;   // [ngroups][G]
   void* xnew;       // [ngroups][G * nb_max] Real
-  int nb_max;       // slice stride (multiple of FAST_PPT)
+  int nb_max;       // slice stride (multiple of PPT)
   int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
 };
 
@@ -65,14 +66,9 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-template <typename Real> struct FastMath;
-template <> struct FastMath<float> {
-  static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
-};
-template <> struct FastMath<double> {
-  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
-};
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -84,50 +80,57 @@ __device__ __forceinline__ double warp_max_d(double v) {
   for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
   return v;
 }
+__device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
 
 // Output-slot bookkeeping of one resampling step.  Position of slot i: (i + U_i) / n (stratified,
 // U_i = Philox word of slot i) or (i + U) / n (systematic).  count_le(c) = #{ i : pos_i <= c }
 // = first slot whose position exceeds c.  With t = c*n and i = floor(t): slots below i have
 // i' + U < i' + 1 <= t, slots above have i' >= i + 1 > t, so only slot i needs a look.
 struct SlotCounter {
-  NoiseKey key; unsigned int obs; int fn; int n; double u_sys;
+  NoiseKey key; unsigned int obs; int fn; int n; unsigned int w_sys;
   const unsigned int* s_u; int u_base, u_cap;   // staged Philox words for slots [u_base, u_base + u_cap)
-  __device__ __forceinline__ double u_of(int i) const {
-    if (fn == 1) return u_sys;
-    int k = i - u_base;
-    if (k >= 0 && k < u_cap) return word_to_unit_f64(s_u[k]);
+  __device__ __forceinline__ unsigned int word_of(int i) const {
+    if (fn == 1) return w_sys;
+    unsigned int k = (unsigned int)(i - u_base);
+    if (k < (unsigned int)u_cap) return s_u[k];
     uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);   // outside the staged window (rare)
-    return word_to_unit_f64(q.w[i & 3]);
+    return q.w[i & 3];
   }
-  __device__ __forceinline__ int count_le(double c) const {
+  __device__ __forceinline__ int count_le(double c) const {   // exact rule (fp64)
     double t = c * (double)n;
     if (!(t > 0.0)) return 0;
     if (t >= (double)n) return n;
     int i = (int)t;
-    return i + (((double)i + u_of(i)) <= t ? 1 : 0);
+    return i + (((double)i + word_to_unit_f64(word_of(i))) <= t ? 1 : 0);
   }
 };
 
-template <typename Model, typename Real>
-__global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
+template <typename Model, typename Real, int PPT>
+__global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P) {
   static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
                 "persistent kernel: 1-D models with one normal per transition");
+  static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
+  constexpr bool F32 = sizeof(Real) == 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FilterDev& f = P.f;
   const int G = P.G;
   const int group = blockIdx.x / G, b = blockIdx.x % G;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   // shared memory carve-up
-  double* s_tab = (double*)smem_raw;                 // [4][G]: m, s, q, sx of every CTA
+  double* s_tab = (double*)smem_raw;                 // [4][G]: m, s -> inclusive cdf numerator A, q, sx of every CTA
   double* s_red = s_tab + 4 * G;                     // [5][32] per-warp partials
   Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
   unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
-  __shared__ int s_flag[2];
   __shared__ int s_wf[32];
   __shared__ int s_heavy_n;
   __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
   __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
-  // scalars of the current step, written by thread 0 in P2
+  __shared__ double s_p2[3][8];                      // P2 cross-warp partials: s totals, q, sx
+  // scalars of the current step, written in P2
   __shared__ double s_lo, s_hi, s_wscale, s_ll;
   __shared__ int s_resample, s_dead;
 
@@ -135,32 +138,34 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
   FastRec2* rec2 = P.rec2 + (size_t)group * G;
   Real* xnew = (Real*)P.xnew + (size_t)group * G * P.nb_max;
   unsigned int ep1 = 0, ep2 = 0;   // record epochs (B1 / B2): identical sequences in every CTA of the group
-  if (tid < 2) s_flag[tid] = 0;
-  __syncthreads();
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  // P2 geometry: PW warps share the G records, R consecutive records per thread
+  const int PW = min(nw, (G + 31) >> 5);
+  const int R = (G + PW * 32 - 1) / (PW * 32);
 
   for (int c = group; c < f.C; c += P.ngroups) {
     if (!f.alive[c]) continue;
     const int n = filt_n(f, c);
     int nb = (n + G - 1) / G;
-    nb = (nb + FAST_PPT - 1) / FAST_PPT * FAST_PPT;
+    nb = (nb + PPT - 1) / PPT * PPT;
     const int base = b * nb;                                  // first global particle of this CTA
     const int n_loc = max(0, min(n - base, nb));              // particles owned by this CTA
-    const int ibase = base + tid * FAST_PPT;                  // first global particle of this thread
-    const int n_own = max(0, min(FAST_PPT, min(n - ibase, nb - tid * FAST_PPT)));  // owned particles of this thread
+    const int ibase = base + tid * PPT;                       // first global particle of this thread
+    const int n_own = max(0, min(PPT, min(n - ibase, nb - tid * PPT)));  // owned particles of this thread
     Real par[Model::NPAR];
     Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
     const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
     const int T1 = f.T + 1;
-    int ralg = f.ralg;
+    const int ralg = f.ralg;
     double thr = f.threshold;
     if (thr < 0) thr = (ralg == 0) ? __longlong_as_double(0x7FF0000000000000LL) : (ralg == 1 ? (double)n : (double)n / 2.0);
+    const double log_n = log((double)n);
 
     // ---- init (R/particle_filter_core.R:76-116) ----
-    Real x[FAST_PPT];
+    Real x[PPT];
     double sum0 = 0.0;
 #pragma unroll
-    for (int h = 0; h < FAST_PPT / 4; h++) {
+    for (int h = 0; h < PPT / 4; h++) {
       uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
       Real zz[4];
       Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
@@ -169,8 +174,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       for (int k = 0; k < 4; k++) {
         Real xi[1]; Real zi[1] = {zz[k]};
         Model::template init<Real>(xi, par, zi, nullptr);
-        x[4 * h + k] = xi[0];
-        if (4 * h + k < n_own) sum0 += (double)xi[0];
+        x[4 * h + k] = (4 * h + k < n_own) ? xi[0] : (Real)0;   // padding lanes stay finite
+        sum0 += (double)x[4 * h + k];
       }
     }
     double loglike = 0.0;
@@ -214,15 +219,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
     }
 
     // normals of the next transition, generated ahead of time (they do not depend on x)
-    Real zpre[FAST_PPT];
+    Real zpre[PPT];
     int zpre_t = -1;   // absolute time index (tnow - 1) the pre-generated normals belong to
-    auto gen_normals = [&](int tz, Real* z) {
+    auto gen_normals = [&](int tz) {
 #pragma unroll
-      for (int h = 0; h < FAST_PPT / 4; h++) {
+      for (int h = 0; h < PPT / 4; h++) {
         uint4x qd = noise_quad(key, (unsigned int)tz, TAG_TRANS_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
-        Math<Real>::box_muller(qd.w[0], qd.w[1], z[4 * h + 0], z[4 * h + 1]);
-        Math<Real>::box_muller(qd.w[2], qd.w[3], z[4 * h + 2], z[4 * h + 3]);
+        Math<Real>::box_muller(qd.w[0], qd.w[1], zpre[4 * h + 0], zpre[4 * h + 1]);
+        Math<Real>::box_muller(qd.w[2], qd.w[3], zpre[4 * h + 2], zpre[4 * h + 3]);
       }
+      zpre_t = tz;
     };
 
     for (int obs = 0; obs < f.T; obs++) {
@@ -233,57 +239,43 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
 
       // ---- P1: propagate + log-weight ----
       for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
-        if (zpre_t != tnow - 1) gen_normals(tnow - 1, zpre);
+        if (zpre_t != tnow - 1) gen_normals(tnow - 1);
 #pragma unroll
-        for (int k = 0; k < FAST_PPT; k++) {
+        for (int k = 0; k < PPT; k++) {
           Real zi[1] = {zpre[k]};
           Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
         }
       }
-      Real e[FAST_PPT];   // first the log-weights, then exp(lw - block max)
+      Real e[PPT];   // first the log-weights, then exp(lw - block max)
       Real mloc = Math<Real>::ninf();
-      int nanf = 0;
 #pragma unroll
-      for (int k = 0; k < FAST_PPT; k++) {
-        const bool own = k < n_own;
-        if (!own) x[k] = (Real)0;   // padding lanes never hold garbage (x_new beyond n is not written)
-        Real l = Model::template loglik<Real>(yv, &x[k], par, ot);
-        if (!own) l = Math<Real>::ninf();
-        if (l != l) nanf = 1;
-        e[k] = l;
-        mloc = l > mloc ? l : mloc;
+      for (int k = 0; k < PPT; k++) {
+        e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
+        if (k >= n_own) e[k] = Math<Real>::ninf();
+        mloc = e[k] > mloc ? e[k] : mloc;
       }
       // block max: per-warp partials, then every warp reduces the partials redundantly (one barrier)
       {
         Real v = mloc;
 #pragma unroll
         for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-        nanf = __any_sync(0xffffffffu, nanf);
-        if (lane == 0) { s_red[wid] = (double)v; s_red[32 + wid] = (double)nanf; }
+        if (lane == 0) s_red[wid] = (double)v;
       }
       __syncthreads();
-      double mb, nan_b;
-      {
-        double t = lane < nw ? s_red[lane] : NINF;
-        double nf = lane < nw ? s_red[32 + lane] : 0.0;
-        mb = warp_max_d(t);
-        nan_b = warp_max_d(nf);
-      }
-      // e = exp(lw - mb); thread sums; block-local inclusive scan of e (fp64)
-      double run = 0.0;      // this thread's sum of e
+      const double mb = warp_max_d(lane < nw ? s_red[lane] : NINF);
+      // e = exp(lw - mb); thread sums; block-local inclusive scan of e
       double exu;            // block-local exclusive prefix of this thread (unnormalised)
       {
-        Real fq = 0, fx = 0;
-        const Real mbr = (Real)mb;
+        Real fs = 0, fq = 0, fx = 0;
+        const Real mbr = (mb == NINF) ? (Real)0 : (Real)mb;   // exp(-inf - 0) = 0: no per-particle guard
 #pragma unroll
-        for (int k = 0; k < FAST_PPT; k++) {
-          Real ek = (e[k] == Math<Real>::ninf() || mb == NINF) ? (Real)0 : FastMath<Real>::exp_(e[k] - mbr);
+        for (int k = 0; k < PPT; k++) {
+          Real ek = Math<Real>::exp_(e[k] - mbr);
           e[k] = ek;
-          run += (double)ek; fq += ek * ek; fx += ek * x[k];
+          fs += ek; fq += ek * ek; fx += ek * x[k];
         }
-        double inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const double run = (double)fs;
+        double inc = warp_incl_scan_d(run, lane);
         double tq = warp_sum_d((double)fq), tx = warp_sum_d((double)fx);
         __syncthreads();   // s_red partials of the max have been consumed by every warp
         if (lane == 31) s_red[wid] = inc;            // warp totals of e
@@ -293,23 +285,22 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         __syncthreads();
         // every warp scans the warp totals redundantly
         double wt = lane < nw ? s_red[lane] : 0.0;
-        double winc = wt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-        double woff = __shfl_sync(0xffffffffu, winc - wt, wid);   // exclusive prefix of this warp
-        exu += woff;
+        double winc = warp_incl_scan_d(wt, lane);
+        exu += __shfl_sync(0xffffffffu, winc - wt, wid);   // + exclusive prefix of this warp
         if (wid == 0) {
           double a0 = __shfl_sync(0xffffffffu, winc, 31);
           double a1 = warp_sum_d(lane < nw ? s_red[32 + lane] : 0.0), a2 = warp_sum_d(lane < nw ? s_red[64 + lane] : 0.0);
           if (lane == 0) {
             FastRec* r = &rec[((ep1 + 1) & 1) * G + b];
-            r->m = mb; r->s = a0; r->q = a1; r->sx = a2; r->nan = nan_b != 0.0;
+            r->m = mb; r->s = a0; r->q = a1; r->sx = a2; r->nan = (a0 != a0) || (a2 != a2) || (mb != mb);
             __threadfence();
             st_release_u32(&r->epoch, ep1 + 1);
           }
         }
       }
       ep1++;
+      // overlap the L2 round trip with the next observation's normals
+      if (obs + 1 < f.T) gen_normals(ot);
       // ---- B1: poll the G records ----
       for (int j = tid; j < G; j += blockDim.x) {
         const FastRec* r = &rec[(ep1 & 1) * G + j];
@@ -318,46 +309,49 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         s_tab[G + j] = __ldcg(&r->s);
         s_tab[2 * G + j] = __ldcg(&r->q);
         s_tab[3 * G + j] = __ldcg(&r->sx);
-        if (__ldcg(&r->nan)) s_flag[0] = 1;
       }
       __syncthreads();
-      // ---- P2: global max / sums / this CTA's cdf interval; warp 0, fixed order => identical in every CTA ----
-      if (wid == 0) {
+      // ---- P2: global max / sums / cdf interval of every CTA.  PW warps, R records per thread, fixed
+      //      order: every CTA evaluates the same expressions on the same data => bit-identical tables ----
+      if (wid < PW) {
         double M = NINF;
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
         M = warp_max_d(M);
-        double Q = 0.0, SX = 0.0, carry = 0.0, mine_lo = 0.0, mine_hi = 0.0;
-        for (int j0 = 0; j0 < G; j0 += 32) {
-          int j = j0 + lane;
-          double sj = 0.0, qj = 0.0, xj = 0.0;
+        const int j0 = tid * R;
+        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0;
+        for (int r = 0; r < R; r++) {
+          const int j = j0 + r;
           if (j < G) {
-            double sc = (s_tab[j] == NINF || M == NINF) ? 0.0 : exp(s_tab[j] - M);
-            sj = s_tab[G + j] * sc; qj = s_tab[2 * G + j] * sc * sc; xj = s_tab[3 * G + j] * sc;
+            const double mj = s_tab[j];
+            const double sc = (mj == NINF || M == NINF) ? 0.0 : exp(mj - M);
+            loc_s += s_tab[G + j] * sc;
+            s_tab[G + j] = loc_s;                     // thread-local inclusive
+            loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc;
           }
-          double inc = sj;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-          double incl = carry + inc;
-          double prev = __shfl_up_sync(0xffffffffu, incl, 1);   // neighbour's inclusive value, bit-identical
-          if (lane == 0) prev = carry;
-          if (j == b) { mine_lo = prev; mine_hi = incl; }
-          carry = __shfl_sync(0xffffffffu, incl, 31);
-          Q += qj; SX += xj;
         }
-        const double S = carry;
-        Q = warp_sum_d(Q); SX = warp_sum_d(SX);
-        mine_lo = warp_sum_d(mine_lo); mine_hi = warp_sum_d(mine_hi);  // only one lane is non-zero
-        if (lane == 0) {
+        const double inc = warp_incl_scan_d(loc_s, lane);
+        const double tq = warp_sum_d(loc_q), tx = warp_sum_d(loc_x);
+        if (lane == 31) s_p2[0][wid] = inc;
+        if (lane == 0) { s_p2[1][wid] = tq; s_p2[2][wid] = tx; }
+        named_barrier(1, PW * 32);
+        double carry = 0.0;
+        for (int w = 0; w < wid; w++) carry += s_p2[0][w];
+        const double off = carry + (inc - loc_s);     // sum of everything before this thread's first record
+        for (int r = 0; r < R; r++) { const int j = j0 + r; if (j < G) s_tab[G + j] = off + s_tab[G + j]; }  // A_j
+        named_barrier(1, PW * 32);
+        if (tid == 0) {
+          double S = s_tab[G + G - 1], Q = 0.0, SX = 0.0, nanv = 0.0;
+          for (int w = 0; w < PW; w++) { Q += s_p2[1][w]; SX += s_p2[2][w]; }
           int dead = 0, resample = 0;
-          if (s_flag[0]) {              // NaN weight somewhere: R's `if (NA)` error
+          if (S != S || SX != SX || M != M) {   // NaN weight somewhere: R's `if (NA)` error
             if (b == 0) f.status[c] = 3;
-            dead = 1; s_flag[0] = 0;
-          } else if (M < -1e8) {        // all(lw < -1e8): R/particle_filter_core.R:189-202
+            dead = 1;
+          } else if (M < -1e8) {               // all(lw < -1e8): R/particle_filter_core.R:189-202
             loglike = NINF;
             if (b == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
             dead = 1;
           } else {
-            loglike += (M + log(S) - log((double)n));
+            loglike += (M + log(S) - log_n);
             const double ess = (S * S) / Q;
             resample = (ralg == 0) ? 0 : (ralg == 1 ? 1 : (ess < thr));
             if (b == 0) {
@@ -365,11 +359,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
               f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
               if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
             }
-            s_lo = mine_lo / S;
-            s_hi = (b == G - 1) ? 2.0 : mine_hi / S;
-            s_wscale = ((mb == NINF) ? 0.0 : exp(mb - M)) / S;
+            if (resample) {
+              s_lo = (b == 0 ? 0.0 : s_tab[G + b - 1]) / S;
+              s_hi = (b == G - 1) ? 2.0 : s_tab[G + b] / S;
+              s_wscale = ((mb == NINF) ? 0.0 : exp(mb - M)) / S;
+            }
           }
-          s_dead = dead; s_resample = resample; s_ll = loglike; s_heavy_n = 0;
+          (void)nanv;
+          s_dead = dead; s_resample = resample; s_ll = loglike;
         }
       }
       __syncthreads();
@@ -380,7 +377,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       // ---- P3: closed-form offspring ranges ----
       const double lo_cdf = s_lo, hi_cdf = s_hi, wscale = s_wscale;
       SlotCounter sc;
-      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.u_sys = 0.0;
+      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
       sc.s_u = s_u; sc.u_cap = P.cap;
       {
         double t0 = lo_cdf * (double)n;
@@ -389,7 +386,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       }
       if (P.resample_fn == 1) {
         uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
-        sc.u_sys = word_to_unit_f64(q0.w[0]);
+        sc.w_sys = q0.w[0];
       } else {
         // stage the Philox words of the slots this CTA is expected to serve: one call per 4 slots
         const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
@@ -402,30 +399,62 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
       const int o_lo = sc.count_le(lo_cdf);
       const int o_hi = (b == G - 1) ? n : sc.count_le(hi_cdf);
       // F of this thread's sources (monotone by a running max; clamped into [o_lo, o_hi])
-      int F[FAST_PPT];
+      int F[PPT];
       {
-        double acc = exu;
         int fmax = o_lo;
+        if (F32) {
+          // fp64 origin per thread, fp32 increments: t_k = T0 + (sum of e up to k) * wscale * n
+          const double T0 = (lo_cdf + exu * wscale) * (double)n;
+          const double T0c = T0 < (double)n ? T0 : (double)n;
+          const int I0 = (int)T0c;
+          const float f0 = (float)(T0c - (double)I0);
+          const float wsn = (float)(wscale * (double)n);
+          float accf = 0.f;
 #pragma unroll
-        for (int k = 0; k < FAST_PPT; k++) {
-          acc += (double)e[k];
-          int v = o_lo;
-          if (k < n_own) {
-            double cj = lo_cdf + acc * wscale;
-            v = sc.count_le(cj);
-            if (tid * FAST_PPT + k == n_loc - 1) v = o_hi;     // clamp: the last particle takes what is left
+          for (int k = 0; k < PPT; k++) {
+            accf += (float)e[k];
+            const float tf = fmaf(accf, wsn, f0);
+            // floor and fraction without conversion instructions (1.5 * 2^23 trick)
+            const float r = (tf - 0.5f) + 12582912.0f;
+            const int ii = __float_as_int(r) - 0x4B400000;
+            const float frac = tf - (r - 12582912.0f);                    // in [0, 1]
+            const float g = frac + 1.0f;                                   // [1, 2]
+            const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;   // frac * 2^32, 23 bits
+            const int i = I0 + ii;
+            int v;
+            if (i >= n) v = n;
+            else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);   // (i + U_i) <= t  <=>  U_i <= frac
+            if (tid * PPT + k == n_loc - 1) v = o_hi;     // clamp: the last particle takes what is left
             v = min(max(v, o_lo), o_hi);
+            if (k >= n_own) v = o_lo;
+            fmax = max(fmax, v);
+            F[k] = fmax;
           }
-          fmax = max(fmax, v);
-          F[k] = fmax;
+        } else {
+          double acc = exu;
+#pragma unroll
+          for (int k = 0; k < PPT; k++) {
+            acc += (double)e[k];
+            int v = o_lo;
+            if (k < n_own) {
+              v = sc.count_le(lo_cdf + acc * wscale);
+              if (tid * PPT + k == n_loc - 1) v = o_hi;
+              v = min(max(v, o_lo), o_hi);
+            }
+            fmax = max(fmax, v);
+            F[k] = fmax;
+          }
         }
-        // exclusive prefix-max of the per-thread last F over the block
-        int inc = F[FAST_PPT - 1];
+      }
+      // exclusive prefix-max of the per-thread last F over the block
+      int prevF;
+      {
+        int inc = F[PPT - 1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
         if (lane == 31) s_wf[wid] = inc;
-        int prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) prev = o_lo;
+        prevF = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) prevF = o_lo;
         __syncthreads();
         int wv = lane < nw ? s_wf[lane] : o_lo;
         int winc = wv;
@@ -433,30 +462,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc = max(winc, t); }
         int wprev = __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);
         if (wid == 0) wprev = o_lo;
-        prev = max(prev, wprev);
-        // fold the predecessor's value into this thread's F
+        prevF = max(prevF, wprev);
 #pragma unroll
-        for (int k = 0; k < FAST_PPT; k++) F[k] = max(F[k], prev);
-        // ---- P4: scatter into the staging buffer (chunks of `cap` slots), copy out coalesced ----
+        for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
+      }
+      // ---- P4: scatter into the staging buffer (chunks of `cap` slots), copy out coalesced ----
+      {
         const int o_base = o_lo & ~3;
-        double sumx = 0.0;
+        Real sumx = 0;
         for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
           const int c1 = min(o_hi, c0 + P.cap);
-          int lo_k = prev;
+          int lo_k = prevF;
 #pragma unroll
-          for (int k = 0; k < FAST_PPT; k++) {
+          for (int k = 0; k < PPT; k++) {
             const int hi_k = F[k];
-            if (k < n_own && hi_k > lo_k) {
-              if (c0 == o_base) sumx += (double)(hi_k - lo_k) * (double)x[k];
-              const int a = max(lo_k, c0), z = min(hi_k, c1);
-              if (z - a > FAST_HEAVY) {
-                int slot = atomicAdd(&s_heavy_n, 1);
-                if (slot < FAST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = z; s_heavy_x[slot] = x[k]; }
-                else for (int o = a; o < z; o++) s_out[o - c0] = x[k];
-              } else {
-                for (int o = a; o < z; o++) s_out[o - c0] = x[k];
-              }
+            const int a = max(lo_k, c0);
+            int cnt = min(hi_k, c1) - a;
+            if (c0 == o_base && hi_k > lo_k) {
+              // count as a float without a conversion instruction (exact below 2^23)
+              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
+              sumx += (Real)cf * x[k];
             }
+            if (cnt > FAST_HEAVY) {
+              int slot = atomicAdd(&s_heavy_n, 1);
+              if (slot < FAST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = a + cnt; s_heavy_x[slot] = x[k]; cnt = 0; }
+            }
+            // warp-uniform trip count: no divergent loop bookkeeping
+            const int mx = __reduce_max_sync(0xffffffffu, cnt);
+            Real* dst = s_out + (a - c0);
+            for (int r = 0; r < mx; r++) if (r < cnt) dst[r] = x[k];
             lo_k = max(lo_k, hi_k);
           }
           __syncthreads();
@@ -471,7 +505,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
           const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
           for (int o = c0 + 4 * tid; o < last; o += 4 * blockDim.x) {
             if (o >= first && o + 3 < last) {
-              if (sizeof(Real) == 4) __stcg((float4*)((float*)xnew + o), *(const float4*)((const float*)s_out + (o - c0)));
+              if (F32) __stcg((float4*)((float*)xnew + o), *(const float4*)((const float*)s_out + (o - c0)));
               else {
                 __stcg((double2*)((double*)xnew + o), *(const double2*)((const double*)s_out + (o - c0)));
                 __stcg((double2*)((double*)xnew + o + 2), *(const double2*)((const double*)s_out + (o - c0) + 2));
@@ -485,7 +519,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
           __syncthreads();
         }
         // block sum of sumx, publish "done"
-        double v = warp_sum_d(sumx);
+        double v = warp_sum_d((double)sumx);
         if (lane == 0) s_red[wid] = v;
         __syncthreads();   // (also orders every scatter store of this CTA before the release below)
         if (wid == 0) {
@@ -500,8 +534,6 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
         }
       }
       ep2++;
-      // overlap the L2 round trip with the next transition's normals
-      if (obs + 1 < f.T) { zpre_t = ot; gen_normals(ot, zpre); }
       // ---- B2: wait for every CTA's scatter, reload this CTA's slice ----
       double tot = 0.0;
       for (int j = tid; j < G; j += blockDim.x) {
@@ -520,15 +552,21 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_fast_bpf(FastParams P) {
           f.state_est[(size_t)c * T1 + obs + 1] = t / (double)n;
         }
       }
-      if (tid * FAST_PPT < nb) {
+      if (n_own > 0) {
         const Real* src = xnew + ibase;
-        if (sizeof(Real) == 4) {
-          float4 a = __ldcg((const float4*)src), bb = __ldcg((const float4*)src + 1);
-          x[0] = (Real)a.x; x[1] = (Real)a.y; x[2] = (Real)a.z; x[3] = (Real)a.w;
-          x[4] = (Real)bb.x; x[5] = (Real)bb.y; x[6] = (Real)bb.z; x[7] = (Real)bb.w;
+        if (F32) {
+#pragma unroll
+          for (int h = 0; h < PPT / 4; h++) {
+            float4 a = __ldcg((const float4*)src + h);
+            x[4 * h] = (Real)a.x; x[4 * h + 1] = (Real)a.y; x[4 * h + 2] = (Real)a.z; x[4 * h + 3] = (Real)a.w;
+          }
         } else {
 #pragma unroll
-          for (int k = 0; k < FAST_PPT; k += 2) { double2 a = __ldcg((const double2*)((const double*)src + k)); x[k] = (Real)a.x; x[k + 1] = (Real)a.y; }
+          for (int k = 0; k < PPT; k += 2) { double2 a = __ldcg((const double2*)((const double*)src + k)); x[k] = (Real)a.x; x[k + 1] = (Real)a.y; }
+        }
+        if (n_own < PPT) {
+#pragma unroll
+          for (int k = 0; k < PPT; k++) if (k >= n_own) x[k] = (Real)0;   // x_new beyond n is never written
         }
       }
     }  // obs
