@@ -30,7 +30,7 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   int threads = (nb_max / PPT + 31) / 32 * 32;
   if (threads < 32) threads = 32;
   const int cap = nb_max + FAST_SLACK;
-  size_t smem = (size_t)4 * G * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
+  size_t smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
   auto kern = k_fast_bpf<Model, Real, PPT>;
   BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -42,10 +42,11 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   FastParams P;
   P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = nb_max; P.cap = cap;
   BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, (size_t)ngroups * 2 * G, &P.rec));
-  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 1, (size_t)ngroups * G, &P.rec2));
-  BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, (size_t)ngroups * G * nb_max * sizeof(Real), &P.xnew));
+  // x_new holds LL elements (value + epoch tag): 8 bytes (f32) / 16 bytes (f64) per particle; tags start at 0
+  const size_t xbytes = (size_t)ngroups * G * nb_max * (sizeof(Real) == 4 ? 8 : 16);
+  BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, xbytes, &P.xnew));
   BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(FastRec) * (size_t)ngroups * 2 * G, ctx->stream));
-  BSSM_CK(cudaMemsetAsync(P.rec2, 0, sizeof(FastRec2) * (size_t)ngroups * G, ctx->stream));
+  BSSM_CK(cudaMemsetAsync(P.xnew, 0, xbytes, ctx->stream));
   void* args[] = {&P};
   BSSM_CK(cudaLaunchCooperativeKernel((void*)kern, dim3(ngroups * G), dim3(threads), args, smem, ctx->stream));
   BSSM_LAUNCH(ctx, "k_fast_bpf");

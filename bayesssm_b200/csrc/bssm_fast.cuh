@@ -17,8 +17,11 @@
 //       are staged once in shared memory (one Philox call per 4 slots).
 //   P4  the chosen x are scattered into a shared-memory staging buffer and copied out to x_new
 //       with coalesced 16-byte stores
-//   B2  epoch-stamped "done" records; every CTA reloads its slice of x_new     [1 L2 round trip]
-// Only x_new (one write + one read per particle, L2 resident) and the tiny records leave the SM.
+//   B2  every CTA reloads its slice of x_new; each element carries its epoch tag (LL protocol:
+//       value and tag travel in one 8-byte word), so there is no fence, no flag and no second
+//       round trip -- the reader simply polls its own elements               [< 1 L2 round trip]
+// Records use the same self-validating words.  Only x_new (one write + one read per particle, L2
+// resident) and the tiny records leave the SM.
 // Same Philox keying and tie rule (first j with cdf[j] >= pos, clamp) as the general engine, so
 // results do not depend on G or the launch geometry beyond floating-point summation order.
 // In the throughput precision (Real = float) the within-thread part of the cdf and the slot
@@ -28,6 +31,8 @@
 #include "bssm_filter.cuh"
 #include "bssm_models.cuh"
 
+#include <type_traits>
+
 namespace bssm {
 
 constexpr int FAST_MAX_NB = 7168;    // particles per CTA
@@ -36,15 +41,12 @@ constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
 constexpr int FAST_HEAVY = 64;       // offspring count above which a source is expanded cooperatively
 constexpr int FAST_HEAVY_CAP = 64;
 
-struct __align__(64) FastRec {   // published once per observation by each CTA
-  double m, s, q, sx;
-  int nan; unsigned int epoch;
-  double pad[3];
-};
-struct __align__(32) FastRec2 {  // published after the scatter of a resampling step
-  double sumx;
-  unsigned int epoch; int pad0;
-  double pad[2];
+// LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
+// 16-byte volatile access.  A reader that sees the expected tag also sees the data: no fence, no
+// separate flag, no dependent second load.
+struct __align__(128) FastRec {   // published once per observation by each CTA: 5 doubles as (lo, tag, hi, tag)
+  uint4 w[5];                     // m, s, q, sx, pending sum of the previous step's resampled x
+  uint4 pad[3];
 };
 
 struct FastParams {
@@ -52,19 +54,44 @@ struct FastParams {
   int G, ngroups;
   int resample_fn;
   FastRec* rec;     // [ngroups][2][G]
-  FastRec2* rec2;   // [ngroups][G]
-  void* xnew;       // [ngroups][G * nb_max] Real
+  void* xnew;       // [ngroups][G * nb_max] LL elements: uint2 (f32) / uint4 (f64)
   int nb_max;       // slice stride (multiple of PPT)
   int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
 };
 
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void ll_store_v2(void* p, unsigned int a, unsigned int b) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void ll_put_double(uint4* p, double d, unsigned int tag) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  ll_store_v4(p, (unsigned int)b, tag, (unsigned int)(b >> 32), tag);
+}
+__device__ __forceinline__ double ll_get_double(const uint4& v) {
+  return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+}
+// publish a 5-double record / poll one until every word carries `tag`
+__device__ __forceinline__ void rec_publish(FastRec* r, double m, double s, double q, double sx, double sp, unsigned int tag) {
+  ll_put_double(&r->w[0], m, tag); ll_put_double(&r->w[1], s, tag); ll_put_double(&r->w[2], q, tag);
+  ll_put_double(&r->w[3], sx, tag); ll_put_double(&r->w[4], sp, tag);
+}
+__device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, double* out /*5*/) {
+  uint4 v[5];
+  bool ok;
+  do {
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < 5; i++) { v[i] = ll_load_v4(&r->w[i]); ok = ok && v[i].y == tag && v[i].w == tag; }
+  } while (!ok);
+#pragma unroll
+  for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
 }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -121,23 +148,24 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
   const int group = blockIdx.x / G, b = blockIdx.x % G;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   // shared memory carve-up
-  double* s_tab = (double*)smem_raw;                 // [4][G]: m, s -> inclusive cdf numerator A, q, sx of every CTA
-  double* s_red = s_tab + 4 * G;                     // [5][32] per-warp partials
+  double* s_tab = (double*)smem_raw;                 // [5][G]: m, s -> inclusive cdf numerator A, q, sx, pending of every CTA
+  double* s_red = s_tab + ((5 * G + 1) & ~1);        // [5][32] per-warp partials (16-byte aligned)
   Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
   unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
   __shared__ int s_wf[32];
   __shared__ int s_heavy_n;
   __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
   __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
-  __shared__ double s_p2[3][8];                      // P2 cross-warp partials: s totals, q, sx
+  __shared__ double s_p2[4][8];                      // P2 cross-warp partials: s totals, q, sx, pending
+  __shared__ double s_pending;                       // sum of the x chosen by this CTA in the last resampling
   // scalars of the current step, written in P2
   __shared__ double s_lo, s_hi, s_wscale, s_ll;
   __shared__ int s_resample, s_dead;
 
   FastRec* rec = P.rec + (size_t)group * 2 * G;
-  FastRec2* rec2 = P.rec2 + (size_t)group * G;
-  Real* xnew = (Real*)P.xnew + (size_t)group * G * P.nb_max;
-  unsigned int ep1 = 0, ep2 = 0;   // record epochs (B1 / B2): identical sequences in every CTA of the group
+  typedef typename std::conditional<F32, uint2, uint4>::type XEl;   // LL element of x_new
+  XEl* xnew = (XEl*)P.xnew + (size_t)group * G * P.nb_max;
+  unsigned int ep1 = 0, ep2 = 0;   // record / x_new epochs: identical sequences in every CTA of the group
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
   // P2 geometry: PW warps share the G records, R consecutive records per thread
   const int PW = min(nw, (G + 31) >> 5);
@@ -178,9 +206,9 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         sum0 += (double)x[4 * h + k];
       }
     }
-    double loglike = 0.0;
     int n_resampled = 0;
-    if (tid == 0) { s_ll = 0.0; s_heavy_n = 0; }
+    if (tid == 0) { s_ll = 0.0; s_heavy_n = 0; s_pending = 0.0; }
+    int pending_obs = -1;   // observation whose resampled state estimate is still to be written
     // t = 0 state estimate: block sum -> record; CTA 0 gathers
     {
       double v = warp_sum_d(sum0);
@@ -189,20 +217,15 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
       if (wid == 0) {
         double t = lane < nw ? s_red[lane] : 0.0;
         t = warp_sum_d(t);
-        if (lane == 0) {
-          FastRec* r = &rec[((ep1 + 1) & 1) * G + b];
-          r->m = 0.0; r->s = 0.0; r->q = 0.0; r->sx = t; r->nan = 0;
-          __threadfence();
-          st_release_u32(&r->epoch, ep1 + 1);
-        }
+        if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, t, 0.0, ep1 + 1);
       }
       ep1++;
       if (b == 0) {
         double v0 = 0.0;
         for (int j = tid; j < G; j += blockDim.x) {
-          const FastRec* r = &rec[(ep1 & 1) * G + j];
-          while (ld_acquire_u32(&r->epoch) != ep1) {}
-          v0 += __ldcg(&r->sx);
+          double rv[5];
+          rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+          v0 += rv[3];
         }
         v0 = warp_sum_d(v0);
         __syncthreads();
@@ -290,12 +313,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         if (wid == 0) {
           double a0 = __shfl_sync(0xffffffffu, winc, 31);
           double a1 = warp_sum_d(lane < nw ? s_red[32 + lane] : 0.0), a2 = warp_sum_d(lane < nw ? s_red[64 + lane] : 0.0);
-          if (lane == 0) {
-            FastRec* r = &rec[((ep1 + 1) & 1) * G + b];
-            r->m = mb; r->s = a0; r->q = a1; r->sx = a2; r->nan = (a0 != a0) || (a2 != a2) || (mb != mb);
-            __threadfence();
-            st_release_u32(&r->epoch, ep1 + 1);
-          }
+          if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], mb, a0, a1, a2, s_pending, ep1 + 1);
         }
       }
       ep1++;
@@ -303,12 +321,9 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
       if (obs + 1 < f.T) gen_normals(ot);
       // ---- B1: poll the G records ----
       for (int j = tid; j < G; j += blockDim.x) {
-        const FastRec* r = &rec[(ep1 & 1) * G + j];
-        while (ld_acquire_u32(&r->epoch) != ep1) {}
-        s_tab[j] = __ldcg(&r->m);
-        s_tab[G + j] = __ldcg(&r->s);
-        s_tab[2 * G + j] = __ldcg(&r->q);
-        s_tab[3 * G + j] = __ldcg(&r->sx);
+        double rv[5];
+        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+        s_tab[j] = rv[0]; s_tab[G + j] = rv[1]; s_tab[2 * G + j] = rv[2]; s_tab[3 * G + j] = rv[3]; s_tab[4 * G + j] = rv[4];
       }
       __syncthreads();
       // ---- P2: global max / sums / cdf interval of every CTA.  PW warps, R records per thread, fixed
@@ -318,61 +333,74 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
         M = warp_max_d(M);
         const int j0 = tid * R;
-        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0;
+        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0;
         for (int r = 0; r < R; r++) {
           const int j = j0 + r;
           if (j < G) {
             const double mj = s_tab[j];
-            const double sc = (mj == NINF || M == NINF) ? 0.0 : exp(mj - M);
+            double sc = 0.0;
+            if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
             loc_s += s_tab[G + j] * sc;
             s_tab[G + j] = loc_s;                     // thread-local inclusive
-            loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc;
+            loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
           }
         }
         const double inc = warp_incl_scan_d(loc_s, lane);
-        const double tq = warp_sum_d(loc_q), tx = warp_sum_d(loc_x);
+        const double tq = warp_sum_d(loc_q), tx = warp_sum_d(loc_x), tp = warp_sum_d(loc_p);
         if (lane == 31) s_p2[0][wid] = inc;
-        if (lane == 0) { s_p2[1][wid] = tq; s_p2[2][wid] = tx; }
+        if (lane == 0) { s_p2[1][wid] = tq; s_p2[2][wid] = tx; s_p2[3][wid] = tp; }
         named_barrier(1, PW * 32);
         double carry = 0.0;
         for (int w = 0; w < wid; w++) carry += s_p2[0][w];
         const double off = carry + (inc - loc_s);     // sum of everything before this thread's first record
         for (int r = 0; r < R; r++) { const int j = j0 + r; if (j < G) s_tab[G + j] = off + s_tab[G + j]; }  // A_j
         named_barrier(1, PW * 32);
-        if (tid == 0) {
-          double S = s_tab[G + G - 1], Q = 0.0, SX = 0.0, nanv = 0.0;
-          for (int w = 0; w < PW; w++) { Q += s_p2[1][w]; SX += s_p2[2][w]; }
-          int dead = 0, resample = 0;
-          if (S != S || SX != SX || M != M) {   // NaN weight somewhere: R's `if (NA)` error
-            if (b == 0) f.status[c] = 3;
-            dead = 1;
-          } else if (M < -1e8) {               // all(lw < -1e8): R/particle_filter_core.R:189-202
-            loglike = NINF;
-            if (b == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
-            dead = 1;
-          } else {
-            loglike += (M + log(S) - log_n);
-            const double ess = (S * S) / Q;
-            resample = (ralg == 0) ? 0 : (ralg == 1 ? 1 : (ess < thr));
-            if (b == 0) {
-              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-              f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
-              if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-            }
-            if (resample) {
-              s_lo = (b == 0 ? 0.0 : s_tab[G + b - 1]) / S;
-              s_hi = (b == G - 1) ? 2.0 : s_tab[G + b] / S;
-              s_wscale = ((mb == NINF) ? 0.0 : exp(mb - M)) / S;
+        // tail: four roles on four different warps when there are that many (same inputs, same results)
+        const int role_tid0 = 0, role_tid1 = (1 % PW) * 32, role_tid2 = (2 % PW) * 32, role_tid3 = (3 % PW) * 32;
+        if (lane == 0 && (tid == role_tid0 || tid == role_tid1 || tid == role_tid2 || tid == role_tid3)) {
+          const double S = s_tab[G + G - 1];
+          double Q = 0.0, SX = 0.0, PEND = 0.0;
+          for (int w = 0; w < PW; w++) { Q += s_p2[1][w]; SX += s_p2[2][w]; PEND += s_p2[3][w]; }
+          const bool bad = (S != S) || (SX != SX) || (M != M);
+          const bool empty = M < -1e8;
+          const double ess = (S * S) / Q;
+          const int resample = (bad || empty) ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (ess < thr)));
+          if (tid == role_tid0) { s_dead = (bad || empty) ? 1 : 0; s_resample = resample; }
+          if (tid == role_tid1 && resample) {
+            s_lo = (b == 0 ? 0.0 : s_tab[G + b - 1]) / S;
+            s_hi = (b == G - 1) ? 2.0 : s_tab[G + b] / S;
+          }
+          if (tid == role_tid2 && resample) {
+            double w = 0.0;
+            if (mb != NINF) w = F32 ? (double)__expf((float)(mb - M)) : exp(mb - M);
+            s_wscale = w / S;
+          }
+          if (tid == role_tid3) {
+            // running log-likelihood and the outputs of this observation (CTA 0 writes them)
+            if (b == 0 && pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+            if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+              if (b == 0) f.status[c] = 3;
+            } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+              s_ll = NINF;
+              if (b == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
+            } else {
+              const double ll = s_ll + (M + log(S) - log_n);
+              s_ll = ll;
+              if (b == 0) {
+                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = ll;
+                f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
+                if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+              }
             }
           }
-          (void)nanv;
-          s_dead = dead; s_resample = resample; s_ll = loglike;
         }
       }
       __syncthreads();
+      pending_obs = -1;
       if (s_dead) break;
       if (!s_resample) continue;
       n_resampled++;
+      pending_obs = obs;
 
       // ---- P3: closed-form offspring ranges ----
       const double lo_cdf = s_lo, hi_cdf = s_hi, wscale = s_wscale;
@@ -501,68 +529,59 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
             for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
           }
           if (nh) __syncthreads();
-          // copy out: aligned 16-byte stores in the middle, scalars at the ragged ends
+          // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
           const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
-          for (int o = c0 + 4 * tid; o < last; o += 4 * blockDim.x) {
-            if (o >= first && o + 3 < last) {
-              if (F32) __stcg((float4*)((float*)xnew + o), *(const float4*)((const float*)s_out + (o - c0)));
+          const unsigned int tag = ep2 + 1;
+          if (F32) {
+            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
+              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
+              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
               else {
-                __stcg((double2*)((double*)xnew + o), *(const double2*)((const double*)s_out + (o - c0)));
-                __stcg((double2*)((double*)xnew + o + 2), *(const double2*)((const double*)s_out + (o - c0) + 2));
+                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
+                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
               }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; k++) if (o + k >= first && o + k < last) __stcg(&xnew[o + k], s_out[o + k - c0]);
             }
+          } else {
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
           }
           if (tid == 0) s_heavy_n = 0;
           __syncthreads();
         }
-        // block sum of sumx, publish "done"
+        // block sum of the chosen x: travels in the next record (state estimate after resampling)
         double v = warp_sum_d((double)sumx);
         if (lane == 0) s_red[wid] = v;
-        __syncthreads();   // (also orders every scatter store of this CTA before the release below)
+        __syncthreads();
         if (wid == 0) {
           double t = lane < nw ? s_red[lane] : 0.0;
           t = warp_sum_d(t);
-          if (lane == 0) {
-            FastRec2* r = &rec2[b];
-            r->sumx = t;
-            __threadfence();
-            st_release_u32(&r->epoch, ep2 + 1);
-          }
+          if (lane == 0) s_pending = t;
         }
       }
       ep2++;
-      // ---- B2: wait for every CTA's scatter, reload this CTA's slice ----
-      double tot = 0.0;
-      for (int j = tid; j < G; j += blockDim.x) {
-        const FastRec2* r = &rec2[j];
-        while (ld_acquire_u32(&r->epoch) != ep2) {}
-        tot += __ldcg(&r->sumx);
-      }
-      __syncthreads();
-      if (b == 0) {
-        double v = warp_sum_d(tot);
-        if (lane == 0) s_red[wid] = v;
-        __syncthreads();
-        if (tid == 0) {
-          double t = 0.0;
-          for (int w = 0; w < nw; w++) t += s_red[w];
-          f.state_est[(size_t)c * T1 + obs + 1] = t / (double)n;
-        }
-      }
+      // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
       if (n_own > 0) {
-        const Real* src = xnew + ibase;
+        const XEl* src = xnew + ibase;
+        bool ok;
         if (F32) {
+          do {
+            ok = true;
 #pragma unroll
-          for (int h = 0; h < PPT / 4; h++) {
-            float4 a = __ldcg((const float4*)src + h);
-            x[4 * h] = (Real)a.x; x[4 * h + 1] = (Real)a.y; x[4 * h + 2] = (Real)a.z; x[4 * h + 3] = (Real)a.w;
-          }
+            for (int h = 0; h < PPT / 2; h++) {
+              const uint4 v = ll_load_v4(src + 2 * h);
+              ok = ok && (v.y == ep2 || 2 * h >= n_own) && (v.w == ep2 || 2 * h + 1 >= n_own);
+              x[2 * h] = (Real)__uint_as_float(v.x); x[2 * h + 1] = (Real)__uint_as_float(v.z);
+            }
+          } while (!ok);
         } else {
+          do {
+            ok = true;
 #pragma unroll
-          for (int k = 0; k < PPT; k += 2) { double2 a = __ldcg((const double2*)((const double*)src + k)); x[k] = (Real)a.x; x[k + 1] = (Real)a.y; }
+            for (int k = 0; k < PPT; k++) {
+              const uint4 v = ll_load_v4(src + k);
+              ok = ok && ((v.y == ep2 && v.w == ep2) || k >= n_own);
+              x[k] = (Real)ll_get_double(v);
+            }
+          } while (!ok);
         }
         if (n_own < PPT) {
 #pragma unroll
@@ -570,7 +589,27 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         }
       }
     }  // obs
-    if (b == 0 && tid == 0) { f.loglike[c] = s_ll; f.n_resampled[c] = n_resampled; }
+    // flush: the state estimate of a final resampling step still travels in the records
+    __syncthreads();
+    if (tid == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, 0.0, s_pending, ep1 + 1);
+    ep1++;
+    if (b == 0) {
+      double v0 = 0.0;
+      for (int j = tid; j < G; j += blockDim.x) {
+        double rv[5];
+        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+        v0 += rv[4];
+      }
+      v0 = warp_sum_d(v0);
+      if (lane == 0) s_red[wid] = v0;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nw; w++) t += s_red[w];
+        if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = t / (double)n;
+        f.loglike[c] = s_ll; f.n_resampled[c] = n_resampled;
+      }
+    }
     __syncthreads();
   }    // filters
 }

@@ -77,8 +77,8 @@ def test_f32_persistent_close_to_general_f32(engine):
     y = sim_y(AR, 50, rng)
     a = eh.filter_run(engine, AR, 0, 2, 0, 1 << 16, y, THETA[AR], seed=21, precision=nat.F32, engine=nat.ENGINE_PERSISTENT)
     b = eh.filter_run(engine, AR, 0, 2, 0, 1 << 16, y, THETA[AR], seed=21, precision=nat.F32, engine=nat.ENGINE_GENERAL)
-    assert abs(a["loglike"][0] - b["loglike"][0]) < 0.05
-    np.testing.assert_allclose(a["state_est"][0], b["state_est"][0], atol=0.02)
+    assert abs(a["loglike"][0] - b["loglike"][0]) < 0.25   # Monte-Carlo error at N = 2^16 over 50 steps
+    np.testing.assert_allclose(a["state_est"][0], b["state_est"][0], atol=0.05)
     assert abs(int(a["n_resampled"][0]) - int(b["n_resampled"][0])) <= 1
 
 
@@ -89,8 +89,15 @@ def test_full_size_n_2pow20_runs_and_is_consistent(engine):
     a = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=nat.ENGINE_PERSISTENT)
     b = eh.filter_run(engine, AR, 0, 2, 1, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=nat.ENGINE_PERSISTENT)
     g = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=nat.ENGINE_GENERAL)
-    assert abs(a["loglike"][0] - g["loglike"][0]) < 0.02 and abs(b["loglike"][0] - g["loglike"][0]) < 0.02
-    np.testing.assert_allclose(a["state_est"][0], g["state_est"][0], atol=0.01)
+    # f32 runs are perturbed copies of one another (different rounding => a few different ancestors), so they
+    # agree to Monte-Carlo error, which one low-ESS observation dominates (scripts/diag_precision.py): ~2e-2 here
+    assert abs(a["loglike"][0] - g["loglike"][0]) < 0.1 and abs(b["loglike"][0] - g["loglike"][0]) < 0.1
+    np.testing.assert_allclose(a["state_est"][0], g["state_est"][0], atol=0.02)
+    # in f64 the persistent kernel and the general engine agree to rounding even at this size
+    p64 = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F64, engine=nat.ENGINE_PERSISTENT)
+    g64 = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F64, engine=nat.ENGINE_GENERAL)
+    assert abs(p64["loglike"][0] - g64["loglike"][0]) <= 1e-9 * abs(g64["loglike"][0])
+    np.testing.assert_allclose(p64["ess"][0], g64["ess"][0], rtol=1e-9)
 
 
 def test_pmmh_on_persistent_engine_matches_oracle(orc, engine):
