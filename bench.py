@@ -147,6 +147,75 @@ def workload_config(args):
             "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)"}
 
 
+def run_pmmh_workload(args, ctx, rank, local_rank, world):
+    """BASELINE configs[4]: PMMH on the nonlinear AR model, `--chains` chains x N = 65536 x T = 1000, chains split
+    across the ranks by global id (strong scaling), pilot skipped (fixed proposal factor and particle count), one
+    final NCCL gather of the draws.  A step is one PMMH iteration of ALL chains."""
+    import torch
+    import torch.distributed as dist
+
+    from bayesssm_b200 import distributed as D
+    from bayesssm_b200 import models, priors
+    from bayesssm_b200 import _native as nat
+    from bayesssm_b200.pmmh import default_tune_control, run_chains
+    T, N, Ctot = args.T, args.pmmh_N, args.chains
+    y = simulate_y(T)
+    base, count = D.shard_chains(Ctot, rank, world)
+    m = models.nonlinear_ar()
+    pri = [priors.uniform(0, 1), priors.exponential(1), priors.exponential(1)]
+    init = np.tile(np.array(THETA), (count, 1))
+    chol = np.tile(np.diag([0.05, 0.05, 0.05]), (count, 1, 1))
+    prec = nat.F32 if args.precision == "f32" else nat.F64
+    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT}[args.engine]
+
+    def run(iters, seed):
+        return run_chains(ctx, m, nat.BPF, y, init, pri, [nat.TR_LOGIT, nat.TR_LOG, nat.TR_LOG], default_tune_control(),
+                          iters + 1, seed, chain_id_base=base, fixed_num_particles=N, precision=prec, skip_pilot=True,
+                          proposal_chol=chol, engine=engine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    run(max(args.warmup, 1), 1)
+    barrier()
+    l0 = ctx.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        out = run(args.steps, 2)
+        main_ms = out["main_ms"] * args.steps / (args.steps + 1)   # the first filter of the phase is not an iteration
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = ctx.launch_count() - l0
+    gathered = D.gather_chain_arrays({"theta_chain": out["theta_chain"], "n_accept": out["n_accept"]}, Ctot, rank, world,
+                                     device=torch.device("cuda", local_rank) if world > 1 else None)
+    if world > 1:
+        t = torch.tensor([main_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        main_ms, wall_ms = float(t[0]), float(t[1])
+    iters_per_s = args.steps / (main_ms * 1e-3)
+    pts = Ctot * N * T * iters_per_s
+    peak, peak_src = measured_peak_gbs()
+    line = {"metric": "pmmh-iterations/sec", "value": iters_per_s, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"pmmh nonlinear-AR {Ctot} chains x N={N} x T={T}, chain-sharded, pilot skipped, final NCCL gather of draws",
+                       "chains": Ctot, "N": N, "T": T, "engine": args.engine, "l2": "working set 8 B/particle of resident groups; inputs far larger than L2 over the run"},
+            "particle_timesteps_per_s": pts,
+            "e2e": {"value": args.steps / (wall_ms * 1e-3), "unit": "iter/s", "h2d_bytes_per_step": int(8 * T / args.steps),
+                    "d2h_bytes_per_step": int(out["theta_chain"].nbytes / args.steps)},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": pts * 30.0 / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": pts * 30.0 / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
+                         "kernel": "persistent filter kernel", "algorithmic_bytes_per_particle_timestep": 30.0},
+            "acceptance_rate": float(gathered["n_accept"].mean() / max(args.steps, 1)),
+            "draws_gathered_shape": list(gathered["theta_chain"].shape)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +228,10 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "general", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="filter", choices=["filter", "pmmh"],
+                    help="filter: BASELINE configs[1] (default); pmmh: configs[4], 1024 chains x N=65536 x T=1000 chain-sharded")
+    ap.add_argument("--chains", type=int, default=1024)
+    ap.add_argument("--pmmh-N", dest="pmmh_N", type=int, default=65536)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -182,6 +255,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = nat.Context(local_rank)
     lib = ctx.lib
+    if args.workload == "pmmh":
+        run_pmmh_workload(args, ctx, rank, local_rank, world)
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     N, T = args.N, args.T
     y = simulate_y(T)
     fn = nat.RESAMPLE_FNS[args.resample_fn]
