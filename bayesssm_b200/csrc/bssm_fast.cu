@@ -57,7 +57,11 @@ template <typename Model>
 static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   const int nsm = ctx->prop.multiProcessorCount;
   // group size: as few CTAs as hold the particles, widened to fill the chip when there are few filters
-  int G = (f.N + FAST_MAX_NB - 1) / FAST_MAX_NB;
+  // many filters: half-size slices put two groups on every SM, so one group's waits overlap the other's work
+  // (measured +9 % on 128 chains x 65536); a single big filter keeps one CTA per SM
+  int nb_cap = ((long long)f.C * ((f.N + FAST_MAX_NB - 1) / FAST_MAX_NB) >= nsm) ? FAST_MAX_NB / 2 : FAST_MAX_NB;
+  if (const char* e = getenv("BSSM_FAST_NB")) { int v = atoi(e); if (v >= 256 && v <= FAST_MAX_NB) nb_cap = v; }
+  int G = (f.N + nb_cap - 1) / nb_cap;
   if (f.C * G < nsm) {
     int wide = nsm / f.C;
     int cap = (f.N + 1023) / 1024;   // keep >= ~1024 particles per CTA

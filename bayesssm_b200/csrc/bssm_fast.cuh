@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, t, 0.0, ep1 + 1);
       }
       ep1++;
-      if (b == 0) {
+      // every CTA polls every record (not only CTA 0): a record buffer may only be reused once all CTAs
+      // have passed the poll of the epoch before, which is what orders the two-deep record buffers
+      {
         double v0 = 0.0;
         for (int j = tid; j < G; j += blockDim.x) {
           double rv[5];
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         __syncthreads();
         if (lane == 0) s_red[wid] = v0;
         __syncthreads();
-        if (tid == 0) {
+        if (b == 0 && tid == 0) {
           double t = 0.0;
           for (int w = 0; w < nw; w++) t += s_red[w];
           f.ess[(size_t)c * T1] = (double)n;
@@ -593,9 +595,9 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
     __syncthreads();
     if (tid == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, 0.0, s_pending, ep1 + 1);
     ep1++;
-    if (b == 0) {
+    {
       double v0 = 0.0;
-      for (int j = tid; j < G; j += blockDim.x) {
+      for (int j = tid; j < G; j += blockDim.x) {   // all CTAs poll: see the note at the t = 0 exchange
         double rv[5];
         rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
         v0 += rv[4];
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
       v0 = warp_sum_d(v0);
       if (lane == 0) s_red[wid] = v0;
       __syncthreads();
-      if (tid == 0) {
+      if (b == 0 && tid == 0) {
         double t = 0.0;
         for (int w = 0; w < nw; w++) t += s_red[w];
         if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = t / (double)n;

@@ -114,3 +114,21 @@ def test_pmmh_on_persistent_engine_matches_oracle(orc, engine):
         np.testing.assert_allclose(got["pilot_theta_chain"][c], ref["pilot_theta_chain"], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(got["theta_chain"][c], ref["theta_chain"], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(got["loglike_chain"][c], ref["loglike_chain"], rtol=1e-6)
+
+
+def test_many_filters_per_group_and_several_groups_per_sm(orc, engine):
+    # more filters than resident groups: every group runs several filters back to back (record buffers and x_new
+    # are reused across filters); small slices put several groups on one SM
+    rng = np.random.default_rng(12)
+    y = sim_y(AR, 8, rng)
+    C = 700
+    got = eh.filter_run(engine, AR, 0, 2, 0, 2048, y, THETA[AR], seed=31, num_filters=C, precision=nat.F64,
+                        engine=nat.ENGINE_PERSISTENT)
+    assert (got["status"] == 0).all() and np.isfinite(got["loglike"]).all()
+    for c in (0, 1, 147, 148, 333, 699):
+        ref = orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], seed=31, stream=c)
+        assert abs(got["loglike"][c] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+        np.testing.assert_allclose(got["state_est"][c][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+    big = eh.filter_run(engine, AR, 0, 1, 1, 30000, y, THETA[AR], seed=32, num_filters=40, precision=nat.F32,
+                        engine=nat.ENGINE_PERSISTENT)
+    assert (big["status"] == 0).all() and np.isfinite(big["loglike"]).all() and (big["n_resampled"] == 8).all()
