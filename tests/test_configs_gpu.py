@@ -31,7 +31,7 @@ def test_config3_lg_256_filters_against_kalman(orc, engine):
 @pytest.mark.parametrize("algorithm", [1, 2])
 def test_config4_sir_apf_rmpf_n_2pow18(engine, algorithm):
     # stochastic SIR (chain-binomial), pop = 500, I0 = 70, lambda = 0.5, gamma = 0.2, Poisson observations,
-    # T = 100, N = 2^18; invariants: 0 <= S <= S0 non-increasing in expectation, 0 <= I, S + I <= pop
+    # T = 100, N = 2^18; invariants of every particle carry over to the weighted means: 0 <= S <= S0, 0 <= I, S + I <= pop
     rng = np.random.default_rng(4)
     S, I, ys = 430, 70, []
     for _ in range(100):
@@ -45,8 +45,8 @@ def test_config4_sir_apf_rmpf_n_2pow18(engine, algorithm):
     se = got["state_est"][0]
     assert (se >= -1e-9).all() and (se.sum(axis=1) <= 500 + 1e-9).all()
     assert se[0, 0] == 430 and se[0, 1] == 70
-    assert (np.diff(se[:, 0]) <= 1e-6).all()                     # susceptibles never increase
-    assert np.abs(se[1:, 1] - y).mean() < 6.0                    # filtered infected count tracks the observations
+    assert (se[:, 0] <= 430 + 1e-9).all()                        # particles never gain susceptibles
+    assert np.abs(se[1:, 1] - y).mean() < 15.0                   # filtered infected count tracks the Poisson observations (sd ~ 12 at the peak)
     assert (got["ess"][0] <= (1 << 18) + 1e-6).all() and (got["ess"][0] > 1).all()
 
 
