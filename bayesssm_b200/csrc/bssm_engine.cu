@@ -124,36 +124,59 @@ static int resample_stage(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, in
   return BSSM_OK;
 }
 
-template <typename Model, typename Real>
-static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
+// model kernels are launched through handles so that built-in (compiled in) and NVRTC-compiled user
+// models share one orchestration
+template <typename Model, typename Real> static ModelKernels builtin_kernels() {
+  ModelKernels k;
+  k.init = (void*)k_init<Model, Real>; k.weight = (void*)k_weight<Model, Real>; k.post = (void*)k_post<Model, Real>;
+  k.has_aux = Model::HAS_AUX; k.has_move = Model::HAS_MOVE;
+  return k;
+}
+static int launch_init(bssm_ctx* ctx, const ModelKernels& K, dim3 grid, FilterDev& f) {
+  void* args[] = {&f};
+  BSSM_CK(cudaLaunchKernel(K.init, grid, dim3(FT_THREADS), args, 0, ctx->stream));
+  BSSM_LAUNCH(ctx, "k_init");
+  return BSSM_OK;
+}
+static int launch_weight(bssm_ctx* ctx, const ModelKernels& K, dim3 grid, FilterDev& f, int obs, int flags, int wkind) {
+  void* args[] = {&f, &obs, &flags, &wkind};
+  BSSM_CK(cudaLaunchKernel(K.weight, grid, dim3(FT_THREADS), args, 0, ctx->stream));
+  BSSM_LAUNCH(ctx, "k_weight");
+  return BSSM_OK;
+}
+static int launch_post(bssm_ctx* ctx, const ModelKernels& K, dim3 grid, FilterDev& f, int obs) {
+  void* args[] = {&f, &obs};
+  BSSM_CK(cudaLaunchKernel(K.post, grid, dim3(FT_THREADS), args, 0, ctx->stream));
+  BSSM_LAUNCH(ctx, "k_post");
+  return BSSM_OK;
+}
+
+template <typename Real>
+static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf, const ModelKernels& K) {
   dim3 grid(f.nblk, f.C);
   cudaStream_t st = ctx->stream;
-  k_init<Model, Real><<<grid, FT_THREADS, 0, st>>>(f);
-  BSSM_LAUNCH(ctx, "k_init");
+  if (f.algorithm == BSSM_APF && !K.has_aux) { set_error("model has no aux_log_likelihood_fn"); return BSSM_ERR_UNSUPPORTED; }
+  if (f.algorithm == BSSM_RMPF && !K.has_move) { set_error("model has no move_fn"); return BSSM_ERR_UNSUPPORTED; }
+  BSSM_TRY(launch_init(ctx, K, grid, f));
   k_finalize<<<f.C, 128, 0, st>>>(f, 0, 0);
   BSSM_LAUNCH(ctx, "k_finalize");
   if (L.hist) { k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, 0); BSSM_LAUNCH(ctx, "k_history"); }
   const bool may_resample = (f.algorithm == BSSM_RMPF) || (f.ralg != BSSM_SIS);
   for (int obs = 0; obs < L.T; obs++) {
     if (f.algorithm == BSSM_APF) {
-      if (!Model::HAS_AUX) { set_error("model has no aux_log_likelihood_fn"); return BSSM_ERR_UNSUPPORTED; }
-      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_GAP, 1);
-      BSSM_LAUNCH(ctx, "k_weight");
+      BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_GAP, 1));
       k_finalize<<<f.C, 128, 0, st>>>(f, obs, 2);
       BSSM_LAUNCH(ctx, "k_finalize");
       BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 1, cdf));
-      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_SECOND, 2);
-      BSSM_LAUNCH(ctx, "k_weight");
+      BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_SECOND, 2));
     } else {
-      k_weight<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs, WF_GAP, 0);
-      BSSM_LAUNCH(ctx, "k_weight");
+      BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_GAP, 0));
     }
     k_finalize<<<f.C, 128, 0, st>>>(f, obs, 1);
     BSSM_LAUNCH(ctx, "k_finalize");
     if (may_resample) {
       BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 0, cdf));
-      k_post<Model, Real><<<grid, FT_THREADS, 0, st>>>(f, obs);
-      BSSM_LAUNCH(ctx, "k_post");
+      BSSM_TRY(launch_post(ctx, K, grid, f, obs));
       k_finalize<<<f.C, 128, 0, st>>>(f, obs, 3);
       BSSM_LAUNCH(ctx, "k_finalize");
     }
@@ -164,11 +187,17 @@ static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, 
 
 template <typename Model>
 static int run_filter_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
-  if (L.precision == BSSM_F64) return run_filter_steps<Model, double>(ctx, f, L, cdf);
-  return run_filter_steps<Model, float>(ctx, f, L, cdf);
+  if (L.precision == BSSM_F64) return run_filter_steps<double>(ctx, f, L, cdf, builtin_kernels<Model, double>());
+  return run_filter_steps<float>(ctx, f, L, cdf, builtin_kernels<Model, float>());
 }
 
-int model_dims(int model, int* d, int* ntheta, int* nconst) {
+int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst) {
+  if (model >= BSSM_USER_MODEL_BASE) {
+    const UserModelInfo* u = user_model(ctx, model);
+    if (!u) { set_error("unknown user model id %d", model); return BSSM_ERR_BAD_ARG; }
+    *d = u->dims[0]; *ntheta = u->dims[1]; *nconst = u->dims[2];
+    return BSSM_OK;
+  }
 #define MD(M) { *d = M::D; *ntheta = M::NTHETA; *nconst = M::NCONST; return BSSM_OK; }
   switch (model) {
     case BSSM_MODEL_AR_SIN: MD(ModelArSin)
@@ -192,6 +221,12 @@ int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* c
     return fast_filter_enqueue(ctx, f, L);
   }
   if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && fast_supported(f, L)) return fast_filter_enqueue(ctx, f, L);
+  if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC-compiled user model (bssm_nvrtc.cu)
+    const UserModelInfo* u = user_model(ctx, L.model);
+    if (!u) { set_error("unknown user model id %d", L.model); return BSSM_ERR_BAD_ARG; }
+    if (L.precision == BSSM_F64) return run_filter_steps<double>(ctx, f, L, cdf, u->k64);
+    return run_filter_steps<float>(ctx, f, L, cdf, u->k32);
+  }
   switch (L.model) {
     case BSSM_MODEL_AR_SIN: return run_filter_model<ModelArSin>(ctx, f, L, cdf);
     case BSSM_MODEL_LG: return run_filter_model<ModelLG>(ctx, f, L, cdf);
@@ -449,7 +484,7 @@ int bssm_resample_cdf(bssm_ctx* ctx, int n, const double* weights, double* cdf_o
 int bssm_model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst) {
   (void)ctx;
   int dd, nt, nc;
-  BSSM_TRY(model_dims(model, &dd, &nt, &nc));
+  BSSM_TRY(model_dims(ctx, model, &dd, &nt, &nc));
   if (d) *d = dd;
   if (ntheta) *ntheta = nt;
   if (nconst) *nconst = nc;
@@ -487,7 +522,7 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   BSSM_TRY(filter_validate(cfg));
   BSSM_CK(cudaSetDevice(ctx->device));
   int d, nth, nc;
-  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  BSSM_TRY(model_dims(ctx, cfg->model, &d, &nth, &nc));
   const int C = cfg->num_filters, N = cfg->num_particles, T = cfg->num_obs;
   FilterDev f;
   memset(&f, 0, sizeof(f));
@@ -583,7 +618,7 @@ int bssm_filter_run_device(bssm_ctx* ctx, const bssm_filter_config* cfg, const d
   if (cfg->noise || cfg->return_particles) { set_error("bssm_filter_run_device: injected noise / histories need bssm_filter_run"); return BSSM_ERR_UNSUPPORTED; }
   BSSM_CK(cudaSetDevice(ctx->device));
   int d, nth, nc;
-  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  BSSM_TRY(model_dims(ctx, cfg->model, &d, &nth, &nc));
   const int C = cfg->num_filters, T = cfg->num_obs;
   FilterDev f;
   memset(&f, 0, sizeof(f));
@@ -619,7 +654,12 @@ int bssm_filter_run_device(bssm_ctx* ctx, const bssm_filter_config* cfg, const d
 }
 
 int bssm_model_noise_dims(bssm_ctx* ctx, int model, int* nz_init, int* nu_init, int* nz_trans, int* nu_trans, int* nz_move, int* nu_move) {
-  (void)ctx;
+  if (model >= BSSM_USER_MODEL_BASE) {
+    const UserModelInfo* u = user_model(ctx, model);
+    if (!u) { set_error("unknown user model id %d", model); return BSSM_ERR_BAD_ARG; }
+    *nz_init = u->dims[3]; *nu_init = u->dims[4]; *nz_trans = u->dims[5]; *nu_trans = u->dims[6]; *nz_move = u->dims[7]; *nu_move = u->dims[8];
+    return BSSM_OK;
+  }
 #define ND(M) { *nz_init = M::NZ_INIT; *nu_init = M::NU_INIT; *nz_trans = M::NZ_TRANS; *nu_trans = M::NU_TRANS; *nz_move = M::NZ_MOVE; *nu_move = M::NU_MOVE; return BSSM_OK; }
   switch (model) {
     case BSSM_MODEL_AR_SIN: ND(ModelArSin)

@@ -48,6 +48,16 @@ enum ScratchSlot {
 
 struct Scratch { void* p = nullptr; size_t cap = 0; };
 
+// handles of the model-dependent kernels of the general engine (built-in: function addresses;
+// NVRTC user model: cudaKernel_t from the compiled library)
+struct ModelKernels { void *init = nullptr, *weight = nullptr, *post = nullptr; bool has_aux = false, has_move = false; };
+constexpr int BSSM_USER_MODEL_BASE = 1000;
+struct UserModelInfo {
+  void* library = nullptr;   // cudaLibrary_t
+  ModelKernels k32, k64;
+  int dims[12];              // D, NTHETA, NCONST, NZ_INIT, NU_INIT, NZ_TRANS, NU_TRANS, NZ_MOVE, NU_MOVE, HAS_AUX, HAS_MOVE, NPAR
+};
+
 }  // namespace bssm
 
 struct bssm_ctx {
@@ -58,7 +68,7 @@ struct bssm_ctx {
   int64_t launches = 0;
   bssm::Scratch scratch[bssm::SL_COUNT];
   std::string compile_log;
-  void* nvrtc_state = nullptr;
+  std::vector<bssm::UserModelInfo> user_models;
 };
 
 namespace bssm {
@@ -96,12 +106,14 @@ struct RsArgs {
 struct FilterLaunch {
   int model, precision, resample_fn, exact, hist, T, engine;
 };
-int model_dims(int model, int* d, int* ntheta, int* nconst);
+int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst);
 int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out);
 int filter_reset(bssm_ctx* ctx, FilterDev& f, const int* d_active);
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf);
 // persistent bootstrap-filter kernel (bssm_fast.cu)
 bool fast_supported(const FilterDev& f, const FilterLaunch& L);
 int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L);
+// NVRTC user models (bssm_nvrtc.cu)
+const UserModelInfo* user_model(bssm_ctx* ctx, int model_id);
 
 }  // namespace bssm

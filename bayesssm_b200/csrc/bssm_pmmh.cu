@@ -291,7 +291,7 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
                   bssm_pmmh_result* res) {
   if (!ctx || !cfg || !y || !init_theta || !res) { set_error("bssm_pmmh_run: null argument"); return BSSM_ERR_BAD_ARG; }
   int d, nth, nc;
-  BSSM_TRY(model_dims(cfg->model, &d, &nth, &nc));
+  BSSM_TRY(model_dims(ctx, cfg->model, &d, &nth, &nc));
   const int C = cfg->num_chains, p = cfg->p, T = cfg->num_obs;
   if (p != nth || p < 1 || p > PMAX) { set_error("pmmh: p=%d does not match the model's %d parameters", p, nth); return BSSM_ERR_BAD_ARG; }
   if (cfg->nconst != nc) { set_error("pmmh: model needs %d constants, got %d", nc, cfg->nconst); return BSSM_ERR_BAD_ARG; }

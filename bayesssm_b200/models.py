@@ -98,3 +98,23 @@ def resolve_model(*fns) -> DeviceModel:
     if model is None:
         raise TypeError("no device model given")
     return model
+
+
+def cuda_model(name, source, param_names, const_names=(), dim=1, has_aux=False, has_move=False, ctx=None):
+    """A user model written as a CUDA device-function snippet (what the reference expresses as R closures,
+    R/particle_filter-doc.R:11-18).  `source` defines `struct UserModel` following the contract at the top of
+    bayesssm_b200/csrc/bssm_models.cuh; the engine compiles it with NVRTC for sm_100a together with its
+    model-dependent kernels.  Needs a CUDA device (compilation loads the module)."""
+    import ctypes as C
+    ctx = ctx or nat.default_context()
+    mid = C.c_int()
+    st = ctx.lib.bssm_model_compile(ctx.handle, source.encode("utf-8"), C.byref(mid))
+    if st != nat.OK:
+        raise nat.EngineError(st, nat.last_error())
+    d, nth, nc = C.c_int(), C.c_int(), C.c_int()
+    nat.check(ctx.lib.bssm_model_dims(ctx.handle, mid.value, C.byref(d), C.byref(nth), C.byref(nc)))
+    if (d.value, nth.value, nc.value) != (dim, len(param_names), len(const_names)):
+        raise ValueError(f"UserModel declares D={d.value}, NTHETA={nth.value}, NCONST={nc.value}; "
+                         f"the Python side says dim={dim}, {len(param_names)} parameters, {len(const_names)} constants")
+    return DeviceModel(name, mid.value, tuple(param_names), tuple(const_names), dim=dim, has_aux=has_aux,
+                       has_move=has_move, source=source)

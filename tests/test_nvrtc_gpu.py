@@ -1,0 +1,109 @@
+"""User models as CUDA snippets compiled by NVRTC (the GPU counterpart of passing R closures; precedent:
+the cppFunction transition of vignettes/articles/detailed-overview.Rmd:408-466)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import bayesssm_b200 as b
+import engine_helpers as eh
+from bayesssm_b200 import _native as nat
+from test_filter_gpu import sim_y
+
+pytestmark = pytest.mark.gpu
+
+# the README model (README.md:137-146) restated as a snippet: must reproduce the built-in model bit for bit
+AR_SNIPPET = r'''
+struct UserModel {
+  static constexpr int D = 1, NTHETA = 3, NCONST = 0, NZ_INIT = 1, NU_INIT = 0, NZ_TRANS = 1, NU_TRANS = 0,
+                       NZ_MOVE = 1, NU_MOVE = 1, NPAR = 4;
+  static constexpr bool HAS_AUX = true, HAS_MOVE = true;
+  template <typename R> static BSSM_DEV void prepare(const double* th, R* par) {
+    par[0] = (R)th[0]; par[1] = (R)th[1]; par[2] = (R)th[2]; par[3] = (R)log(th[2]);
+  }
+  template <typename R> static BSSM_DEV void init(R* x, const R*, const R* z, const double*) { x[0] = z[0]; }
+  template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R* z, const double*) {
+    x[0] = par[0] * x[0] + Math<R>::sin_(x[0]) + par[1] * z[0];
+  }
+  template <typename R> static BSSM_DEV R loglik(const double* y, const R* x, const R* par, int) {
+    return dnorm_log<R>((R)y[0], x[0], par[2], par[3]);
+  }
+  template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
+    return dnorm_log<R>((R)y[0], par[0] * x[0] + Math<R>::sin_(x[0]), par[2], par[3]);
+  }
+  template <typename R> static BSSM_DEV void move(R* x, const double* y, const R* par, int t, const R* z, const double* u) {
+    R prop = x[0] + (R)0.1 * z[0];
+    R lc = loglik<R>(y, x, par, t), lp = loglik<R>(y, &prop, par, t);
+    if (log(u[0]) < (double)(lp - lc)) x[0] = prop;
+  }
+};
+'''
+
+# stochastic volatility: a model the engine does not ship
+SV_SNIPPET = r'''
+struct UserModel {
+  static constexpr int D = 1, NTHETA = 3, NCONST = 0, NZ_INIT = 1, NU_INIT = 0, NZ_TRANS = 1, NU_TRANS = 0,
+                       NZ_MOVE = 0, NU_MOVE = 0, NPAR = 4;
+  static constexpr bool HAS_AUX = false, HAS_MOVE = false;
+  template <typename R> static BSSM_DEV void prepare(const double* th, R* par) {
+    par[0] = (R)th[0]; par[1] = (R)th[1]; par[2] = (R)th[2]; par[3] = (R)(th[2] / sqrt(1.0 - th[1] * th[1]));
+  }
+  template <typename R> static BSSM_DEV void init(R* x, const R* par, const R* z, const double*) { x[0] = par[0] + par[3] * z[0]; }
+  template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R* z, const double*) {
+    x[0] = par[0] + par[1] * (x[0] - par[0]) + par[2] * z[0];
+  }
+  template <typename R> static BSSM_DEV R loglik(const double* y, const R* x, const R*, int) {
+    R yy = (R)y[0];
+    return -((R)0.918938533204672741780329736406 + (R)0.5 * x[0] + (R)0.5 * yy * yy * Math<R>::exp_(-x[0]));
+  }
+  template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int t) { return loglik<R>(y, x, par, t); }
+  template <typename R> static BSSM_DEV void move(R*, const double*, const R*, int, const R*, const double*) {}
+};
+'''
+
+
+def test_snippet_reproduces_builtin_model_and_oracle(orc, engine):
+    mid = C.c_int()
+    nat.check(engine.lib.bssm_model_compile(engine.handle, AR_SNIPPET.encode(), C.byref(mid)))
+    assert mid.value >= 1000
+    rng = np.random.default_rng(1)
+    y = sim_y(0, 15, rng)
+    th = [0.8, 1.0, 0.5]
+    for algorithm in (0, 1, 2):
+        noise = orc.make_noise(0, 600, 15, 15, rng)
+        ref = orc.particle_filter(0, algorithm, 2, 0, 600, y, th, noise=noise, want_ancestors=True)
+        usr = eh.filter_run(engine, mid.value, algorithm, 2, 0, 600, y, th, noise=noise, want_ancestors=True)
+        blt = eh.filter_run(engine, 0, algorithm, 2, 0, 600, y, th, noise=noise, want_ancestors=True)
+        assert usr["loglike"][0] == blt["loglike"][0] and np.array_equal(usr["state_est"], blt["state_est"])
+        assert abs(usr["loglike"][0] - ref["loglike"]) <= 1e-10 * abs(ref["loglike"])
+        assert np.array_equal(usr["ancestors_history"][0], ref["ancestors_history"])
+
+
+def test_new_model_through_the_public_api():
+    sv = b.models.cuda_model("stochastic_volatility", SV_SNIPPET, ("mu", "phi", "sigma"))
+    rng = np.random.default_rng(2)
+    x, ys = -1.0, []
+    for _ in range(200):
+        x = -1.0 + 0.95 * (x + 1.0) + 0.25 * rng.standard_normal()
+        ys.append(np.exp(x / 2) * rng.standard_normal())
+    y = np.array(ys)
+    lls = [b.bootstrap_filter(y, 20000, sv.init_fn, sv.transition_fn, sv.log_likelihood_fn, return_particles=False,
+                              seed=s, mu=-1.0, phi=0.95, sigma=0.25)["loglike"] for s in range(4)]
+    bad = b.bootstrap_filter(y, 20000, sv.init_fn, sv.transition_fn, sv.log_likelihood_fn, return_particles=False,
+                             seed=0, mu=2.0, phi=0.95, sigma=0.25)["loglike"]
+    assert np.isfinite(lls).all() and np.std(lls) < 0.5 and bad < min(lls) - 5      # the true mu is far more likely
+    pri = {"mu": b.priors.normal(0, 2), "phi": b.priors.uniform(0, 1), "sigma": b.priors.exponential(1)}
+    with pytest.warns(UserWarning):
+        out = b.pmmh(b.bootstrap_filter, y, 200, sv.init_fn, sv.transition_fn, sv.log_likelihood_fn, pri,
+                     [{"mu": -1.0, "phi": 0.9, "sigma": 0.3}] * 2, burn_in=50, num_chains=2,
+                     param_transform={"mu": "identity", "phi": "logit", "sigma": "log"},
+                     tune_control=b.default_tune_control(pilot_m=100, pilot_reps=8), seed=4, print_result=False)
+    assert len(out["theta_chain"]) == 300 and np.isfinite(out["theta_chain"][["mu", "phi", "sigma"]].to_numpy()).all()
+
+
+def test_compile_error_is_reported(engine):
+    mid = C.c_int()
+    st = engine.lib.bssm_model_compile(engine.handle, b"struct UserModel { this is not C++ };", C.byref(mid))
+    assert st == nat.ERR_NVRTC
+    assert "error" in nat.last_error().lower()
+    assert b"user_model.cu" in engine.lib.bssm_model_compile_log(engine.handle)
