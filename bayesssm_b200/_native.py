@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbayesssm_b200.so")
+LIB_PATH = os.environ.get("BSSM_LIB_PATH") or os.path.join(_HERE, "libbayesssm_b200.so")   # override: A/B experiments only
 
 # status codes / enums (include/bayesssm_b200.h)
 OK, ERR_NEGATIVE_WEIGHT, ERR_ZERO_SUM, ERR_NAN_WEIGHT, ERR_BAD_ARG, ERR_PRIOR_INIT, ERR_CUDA, ERR_NVRTC, \

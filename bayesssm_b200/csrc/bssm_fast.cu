@@ -29,7 +29,7 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   if (nb_max > FAST_MAX_NB) { set_error("persistent kernel: %d particles per CTA exceed %d", nb_max, FAST_MAX_NB); return BSSM_ERR_UNSUPPORTED; }
   int threads = (nb_max / PPT + 31) / 32 * 32;
   if (threads < 32) threads = 32;
-  const int cap = nb_max + FAST_SLACK;
+  const int cap = (nb_max + FAST_SLACK + 31) / 32 * 32;   // multiple of 32: the bank swizzle permutes within 32-word blocks
   size_t smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
   auto kern = k_fast_bpf<Model, Real, PPT>;
   BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -47,9 +47,27 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, xbytes, &P.xnew));
   BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(FastRec) * (size_t)ngroups * 2 * G, ctx->stream));
   BSSM_CK(cudaMemsetAsync(P.xnew, 0, xbytes, ctx->stream));
+  P.timing = nullptr;
+  const bool timing = getenv("BSSM_FAST_TIMING") != nullptr;
+  if (timing) {
+    BSSM_TRY(scratch(ctx, SL_FAST_BASE + 3, (size_t)ngroups * G * 16, &P.timing));
+    BSSM_CK(cudaMemsetAsync(P.timing, 0, sizeof(long long) * (size_t)ngroups * G * 16, ctx->stream));
+  }
   void* args[] = {&P};
   BSSM_CK(cudaLaunchCooperativeKernel((void*)kern, dim3(ngroups * G), dim3(threads), args, smem, ctx->stream));
   BSSM_LAUNCH(ctx, "k_fast_bpf");
+  if (timing) {   // diagnostics only: per-phase cycles of thread 0, averaged over the CTAs
+    std::vector<long long> h((size_t)ngroups * G * 16);
+    BSSM_CK(cudaMemcpyAsync(h.data(), P.timing, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    BSSM_CK(cudaStreamSynchronize(ctx->stream));
+    const char* names[9] = {"loop head", "P1 propagate/weights/reduce", "next-step normals", "B1 poll", "P2", "stage uniforms",
+                            "offspring ranges", "scatter+copy-out", "B2 reload"};
+    double tot = 0;
+    double avg[9];
+    for (int i = 0; i < 9; i++) { double a = 0; for (int c = 0; c < ngroups * G; c++) a += (double)h[(size_t)c * 16 + i]; avg[i] = a / (ngroups * G); tot += avg[i]; }
+    fprintf(stderr, "[bssm fast timing] G=%d groups=%d threads=%d T=%d: cycles per observation (thread 0, mean over CTAs)\n", G, ngroups, threads, f.T);
+    for (int i = 0; i < 9; i++) fprintf(stderr, "  %-28s %9.0f  (%4.1f%%)\n", names[i], avg[i] / (f.T > 0 ? f.T : 1), 100.0 * avg[i] / tot);
+  }
   return BSSM_OK;
 }
 

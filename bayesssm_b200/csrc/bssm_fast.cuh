@@ -57,6 +57,7 @@ struct FastParams {
   void* xnew;       // [ngroups][G * nb_max] LL elements: uint2 (f32) / uint4 (f64)
   int nb_max;       // slice stride (multiple of PPT)
   int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
+  long long* timing;  // optional [gridDim][16] phase cycle counters (BSSM_FAST_TIMING=1, diagnostics)
 };
 
 __device__ __forceinline__ void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
@@ -93,6 +94,9 @@ __device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, dou
 #pragma unroll
   for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
 }
+// bank swizzle of the staging buffers: lanes of a warp touch them at a stride of ~PPT words (blocked particle
+// ownership), which without it is a PPT-way bank conflict; XOR with the 32-word block index spreads the lanes
+__device__ __forceinline__ int sw32(int i) { return i ^ ((i >> 5) & 31); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -123,7 +127,7 @@ struct SlotCounter {
   __device__ __forceinline__ unsigned int word_of(int i) const {
     if (fn == 1) return w_sys;
     unsigned int k = (unsigned int)(i - u_base);
-    if (k < (unsigned int)u_cap) return s_u[k];
+    if (k < (unsigned int)u_cap) return s_u[sw32((int)k)];
     uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);   // outside the staged window (rare)
     return q.w[i & 3];
   }
@@ -156,20 +160,23 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
   __shared__ int s_heavy_n;
   __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
   __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
-  __shared__ double s_p2[4][8];                      // P2 cross-warp partials: s totals, q, sx, pending
   __shared__ double s_pending;                       // sum of the x chosen by this CTA in the last resampling
-  // scalars of the current step, written in P2
-  __shared__ double s_lo, s_hi, s_wscale, s_ll;
-  __shared__ int s_resample, s_dead;
 
   FastRec* rec = P.rec + (size_t)group * 2 * G;
   typedef typename std::conditional<F32, uint2, uint4>::type XEl;   // LL element of x_new
   XEl* xnew = (XEl*)P.xnew + (size_t)group * G * P.nb_max;
   unsigned int ep1 = 0, ep2 = 0;   // record / x_new epochs: identical sequences in every CTA of the group
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
-  // P2 geometry: PW warps share the G records, R consecutive records per thread
-  const int PW = min(nw, (G + 31) >> 5);
-  const int R = (G + PW * 32 - 1) / (PW * 32);
+  // optional phase timing (diagnostics): compiled in only with -DBSSM_FAST_TIMING_BUILD, because the counters
+  // would otherwise hold ~26 registers for the whole kernel
+#ifdef BSSM_FAST_TIMING_BUILD
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define FAST_TICK(ph) do { if (P.timing && tid == 0) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define FAST_TICK(ph) do { } while (0)
+#endif
+  const int R = (G + 31) >> 5;   // records per lane in P2
 
   for (int c = group; c < f.C; c += P.ngroups) {
     if (!f.alive[c]) continue;
@@ -207,7 +214,8 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
       }
     }
     int n_resampled = 0;
-    if (tid == 0) { s_ll = 0.0; s_heavy_n = 0; s_pending = 0.0; }
+    double loglike = 0.0;   // meaningful in thread 0 of CTA 0
+    if (tid == 0) { s_heavy_n = 0; s_pending = 0.0; }
     int pending_obs = -1;   // observation whose resampled state estimate is still to be written
     // t = 0 state estimate: block sum -> record; CTA 0 gathers
     {
@@ -256,12 +264,15 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
       zpre_t = tz;
     };
 
+    double ynext[4] = {0, 0, 0, 0};
+    if (f.T > 0) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[k];
     for (int obs = 0; obs < f.T; obs++) {
       const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
       const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
-      double yv[4] = {0, 0, 0, 0};
-      for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
+      double yv[4] = {ynext[0], ynext[1], ynext[2], ynext[3]};
+      if (obs + 1 < f.T) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[(size_t)(obs + 1) * f.dy + k];   // prefetch
 
+      FAST_TICK(0);
       // ---- P1: propagate + log-weight ----
       for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
         if (zpre_t != tnow - 1) gen_normals(tnow - 1);
@@ -319,8 +330,10 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         }
       }
       ep1++;
+      FAST_TICK(1);   // P1 (propagate, weights, block reductions, publish)
       // overlap the L2 round trip with the next observation's normals
       if (obs + 1 < f.T) gen_normals(ot);
+      FAST_TICK(2);   // next-step normals
       // ---- B1: poll the G records ----
       for (int j = tid; j < G; j += blockDim.x) {
         double rv[5];
@@ -328,14 +341,18 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         s_tab[j] = rv[0]; s_tab[G + j] = rv[1]; s_tab[2 * G + j] = rv[2]; s_tab[3 * G + j] = rv[3]; s_tab[4 * G + j] = rv[4];
       }
       __syncthreads();
-      // ---- P2: global max / sums / cdf interval of every CTA.  PW warps, R records per thread, fixed
-      //      order: every CTA evaluates the same expressions on the same data => bit-identical tables ----
-      if (wid < PW) {
+      FAST_TICK(3);   // B1 poll + barrier
+      // ---- P2: global max / sums / this CTA's cdf interval.  EVERY warp evaluates the same expressions on the
+      //      same table (R consecutive records per lane, one warp scan), so the results are warp-uniform
+      //      registers, bit-identical in every warp of every CTA: no roles, no broadcast, no barrier ----
+      int dead = 0, resample = 0;
+      double lo_cdf = 0.0, hi_cdf = 0.0, wscale = 0.0;
+      {
         double M = NINF;
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
         M = warp_max_d(M);
-        const int j0 = tid * R;
-        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0;
+        const int j0 = lane * R;
+        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0, my_lo = 0.0, my_hi = 0.0;
         for (int r = 0; r < R; r++) {
           const int j = j0 + r;
           if (j < G) {
@@ -343,69 +360,55 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
             double sc = 0.0;
             if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
             loc_s += s_tab[G + j] * sc;
-            s_tab[G + j] = loc_s;                     // thread-local inclusive
+            if (j == b - 1) my_lo = loc_s;            // thread-local inclusive values of records b-1 and b
+            if (j == b) my_hi = loc_s;
             loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
           }
         }
         const double inc = warp_incl_scan_d(loc_s, lane);
-        const double tq = warp_sum_d(loc_q), tx = warp_sum_d(loc_x), tp = warp_sum_d(loc_p);
-        if (lane == 31) s_p2[0][wid] = inc;
-        if (lane == 0) { s_p2[1][wid] = tq; s_p2[2][wid] = tx; s_p2[3][wid] = tp; }
-        named_barrier(1, PW * 32);
-        double carry = 0.0;
-        for (int w = 0; w < wid; w++) carry += s_p2[0][w];
-        const double off = carry + (inc - loc_s);     // sum of everything before this thread's first record
-        for (int r = 0; r < R; r++) { const int j = j0 + r; if (j < G) s_tab[G + j] = off + s_tab[G + j]; }  // A_j
-        named_barrier(1, PW * 32);
-        // tail: four roles on four different warps when there are that many (same inputs, same results)
-        const int role_tid0 = 0, role_tid1 = (1 % PW) * 32, role_tid2 = (2 % PW) * 32, role_tid3 = (3 % PW) * 32;
-        if (lane == 0 && (tid == role_tid0 || tid == role_tid1 || tid == role_tid2 || tid == role_tid3)) {
-          const double S = s_tab[G + G - 1];
-          double Q = 0.0, SX = 0.0, PEND = 0.0;
-          for (int w = 0; w < PW; w++) { Q += s_p2[1][w]; SX += s_p2[2][w]; PEND += s_p2[3][w]; }
-          const bool bad = (S != S) || (SX != SX) || (M != M);
-          const bool empty = M < -1e8;
-          const double ess = (S * S) / Q;
-          const int resample = (bad || empty) ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (ess < thr)));
-          if (tid == role_tid0) { s_dead = (bad || empty) ? 1 : 0; s_resample = resample; }
-          if (tid == role_tid1 && resample) {
-            s_lo = (b == 0 ? 0.0 : s_tab[G + b - 1]) / S;
-            s_hi = (b == G - 1) ? 2.0 : s_tab[G + b] / S;
-          }
-          if (tid == role_tid2 && resample) {
-            double w = 0.0;
-            if (mb != NINF) w = F32 ? (double)__expf((float)(mb - M)) : exp(mb - M);
-            s_wscale = w / S;
-          }
-          if (tid == role_tid3) {
-            // running log-likelihood and the outputs of this observation (CTA 0 writes them)
-            if (b == 0 && pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
-            if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
-              if (b == 0) f.status[c] = 3;
-            } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
-              s_ll = NINF;
-              if (b == 0) { if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF; f.early_exit[c] = 1; }
-            } else {
-              const double ll = s_ll + (M + log(S) - log_n);
-              s_ll = ll;
-              if (b == 0) {
-                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = ll;
-                f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : ess;
-                if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-              }
-            }
+        const double off = inc - loc_s;               // everything before this lane's first record
+        const double S = __shfl_sync(0xffffffffu, inc, 31);
+        const double Q = warp_sum_d(loc_q), SX = warp_sum_d(loc_x), PEND = warp_sum_d(loc_p);
+        const double A_hi = __shfl_sync(0xffffffffu, off + my_hi, b / R);
+        const double A_lo = b == 0 ? 0.0 : __shfl_sync(0xffffffffu, off + my_lo, (b - 1) / R);
+        const bool bad = (S != S) || (SX != SX) || (M != M);
+        const bool empty = M < -1e8;
+        dead = (bad || empty) ? 1 : 0;
+        // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
+        resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
+        if (resample) {
+          const double invS = 1.0 / S;
+          lo_cdf = A_lo * invS;
+          hi_cdf = (b == G - 1) ? 2.0 : A_hi * invS;
+          double w = 0.0;
+          if (mb != NINF) w = F32 ? (double)__expf((float)(mb - M)) : exp(mb - M);
+          wscale = w * invS;
+        }
+        if (b == 0 && tid == 0) {
+          // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
+          if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+          if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+            f.status[c] = 3;
+          } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+            loglike = NINF;
+            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
+            f.early_exit[c] = 1;
+          } else {
+            loglike += (M + log(S) - log_n);
+            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+            f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+            if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
           }
         }
       }
-      __syncthreads();
+      FAST_TICK(4);   // P2
       pending_obs = -1;
-      if (s_dead) break;
-      if (!s_resample) continue;
+      if (dead) break;
+      if (!resample) continue;
       n_resampled++;
       pending_obs = obs;
 
       // ---- P3: closed-form offspring ranges ----
-      const double lo_cdf = s_lo, hi_cdf = s_hi, wscale = s_wscale;
       SlotCounter sc;
       sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
       sc.s_u = s_u; sc.u_cap = P.cap;
@@ -422,10 +425,17 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
         for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += blockDim.x) {
           uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-          *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+          // swizzled store of the quad: the XOR constant is the same for its 4 words, so the quad stays a quad
+          // (moved to quad k ^ (c & ~3)) with its components permuted by c & 3
+          const int k = 4 * qd - sc.u_base, cx = (k >> 5) & 31;
+          unsigned int w0 = uq.w[0], w1 = uq.w[1], w2 = uq.w[2], w3 = uq.w[3], t;
+          if (cx & 1) { t = w0; w0 = w1; w1 = t; t = w2; w2 = w3; w3 = t; }
+          if (cx & 2) { t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
+          *(uint4*)&s_u[k ^ (cx & ~3)] = make_uint4(w0, w1, w2, w3);
         }
         __syncthreads();
       }
+      FAST_TICK(5);   // stage uniforms
       const int o_lo = sc.count_le(lo_cdf);
       const int o_hi = (b == G - 1) ? n : sc.count_le(hi_cdf);
       // F of this thread's sources (monotone by a running max; clamped into [o_lo, o_hi])
@@ -496,6 +506,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
 #pragma unroll
         for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
       }
+      FAST_TICK(6);   // offspring ranges + prefix max
       // ---- P4: scatter into the staging buffer (chunks of `cap` slots), copy out coalesced ----
       {
         const int o_base = o_lo & ~3;
@@ -519,8 +530,8 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
             }
             // warp-uniform trip count: no divergent loop bookkeeping
             const int mx = __reduce_max_sync(0xffffffffu, cnt);
-            Real* dst = s_out + (a - c0);
-            for (int r = 0; r < mx; r++) if (r < cnt) dst[r] = x[k];
+            const int d0 = a - c0;
+            for (int r = 0; r < mx; r++) if (r < cnt) s_out[sw32(d0 + r)] = x[k];
             lo_k = max(lo_k, hi_k);
           }
           __syncthreads();
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           for (int h = 0; h < nh; h++) {
             const int a = s_heavy_lo[h], z = s_heavy_hi[h];
             const Real xv = s_heavy_x[h];
-            for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
+            for (int o = a + tid; o < z; o += blockDim.x) s_out[sw32(o - c0)] = xv;
           }
           if (nh) __syncthreads();
           // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
@@ -536,7 +547,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           const unsigned int tag = ep2 + 1;
           if (F32) {
             for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
-              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
+              const float v0 = (float)s_out[sw32(o - c0)], v1 = (float)s_out[sw32(o + 1 - c0)];
               if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
               else {
                 if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
               }
             }
           } else {
-            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[sw32(o - c0)], tag);
           }
           if (tid == 0) s_heavy_n = 0;
           __syncthreads();
@@ -560,6 +571,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         }
       }
       ep2++;
+      FAST_TICK(7);   // scatter + copy-out + block sum
       // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
       if (n_own > 0) {
         const XEl* src = xnew + ibase;
@@ -590,6 +602,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           for (int k = 0; k < PPT; k++) if (k >= n_own) x[k] = (Real)0;   // x_new beyond n is never written
         }
       }
+      FAST_TICK(8);   // B2 poll (reload) -- no barrier here: warps whose elements arrived start the next step
     }  // obs
     // flush: the state estimate of a final resampling step still travels in the records
     __syncthreads();
@@ -609,11 +622,15 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         double t = 0.0;
         for (int w = 0; w < nw; w++) t += s_red[w];
         if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = t / (double)n;
-        f.loglike[c] = s_ll; f.n_resampled[c] = n_resampled;
+        f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
       }
     }
     __syncthreads();
   }    // filters
+#ifdef BSSM_FAST_TIMING_BUILD
+  if (P.timing && tid == 0) for (int i = 0; i < 12; i++) P.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
+#endif
+#undef FAST_TICK
 }
 
 }  // namespace bssm
