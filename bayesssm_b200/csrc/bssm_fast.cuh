@@ -94,9 +94,6 @@ __device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, dou
 #pragma unroll
   for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
 }
-// bank swizzle of the staging buffers: lanes of a warp touch them at a stride of ~PPT words (blocked particle
-// ownership), which without it is a PPT-way bank conflict; XOR with the 32-word block index spreads the lanes
-__device__ __forceinline__ int sw32(int i) { return i ^ ((i >> 5) & 31); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -121,15 +118,19 @@ __device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
 // U_i = Philox word of slot i) or (i + U) / n (systematic).  count_le(c) = #{ i : pos_i <= c }
 // = first slot whose position exceeds c.  With t = c*n and i = floor(t): slots below i have
 // i' + U < i' + 1 <= t, slots above have i' >= i + 1 > t, so only slot i needs a look.
+// rare path (slot outside the staged window): kept out of line so the hot loop stays small (+3 %, A/B)
+__device__ __noinline__ unsigned int philox_word_slow(NoiseKey key, unsigned int obs, int i) {
+  uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);
+  return q.w[i & 3];
+}
 struct SlotCounter {
   NoiseKey key; unsigned int obs; int fn; int n; unsigned int w_sys;
   const unsigned int* s_u; int u_base, u_cap;   // staged Philox words for slots [u_base, u_base + u_cap)
   __device__ __forceinline__ unsigned int word_of(int i) const {
     if (fn == 1) return w_sys;
     unsigned int k = (unsigned int)(i - u_base);
-    if (k < (unsigned int)u_cap) return s_u[sw32((int)k)];
-    uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);   // outside the staged window (rare)
-    return q.w[i & 3];
+    if (k < (unsigned int)u_cap) return s_u[k];
+    return philox_word_slow(key, obs, i);
   }
   __device__ __forceinline__ int count_le(double c) const {   // exact rule (fp64)
     double t = c * (double)n;
@@ -425,13 +426,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
         for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += blockDim.x) {
           uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-          // swizzled store of the quad: the XOR constant is the same for its 4 words, so the quad stays a quad
-          // (moved to quad k ^ (c & ~3)) with its components permuted by c & 3
-          const int k = 4 * qd - sc.u_base, cx = (k >> 5) & 31;
-          unsigned int w0 = uq.w[0], w1 = uq.w[1], w2 = uq.w[2], w3 = uq.w[3], t;
-          if (cx & 1) { t = w0; w0 = w1; w1 = t; t = w2; w2 = w3; w3 = t; }
-          if (cx & 2) { t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
-          *(uint4*)&s_u[k ^ (cx & ~3)] = make_uint4(w0, w1, w2, w3);
+          *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
         }
         __syncthreads();
       }
@@ -530,8 +525,8 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
             }
             // warp-uniform trip count: no divergent loop bookkeeping
             const int mx = __reduce_max_sync(0xffffffffu, cnt);
-            const int d0 = a - c0;
-            for (int r = 0; r < mx; r++) if (r < cnt) s_out[sw32(d0 + r)] = x[k];
+            Real* dst = s_out + (a - c0);
+            for (int r = 0; r < mx; r++) if (r < cnt) dst[r] = x[k];
             lo_k = max(lo_k, hi_k);
           }
           __syncthreads();
@@ -539,7 +534,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           for (int h = 0; h < nh; h++) {
             const int a = s_heavy_lo[h], z = s_heavy_hi[h];
             const Real xv = s_heavy_x[h];
-            for (int o = a + tid; o < z; o += blockDim.x) s_out[sw32(o - c0)] = xv;
+            for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
           }
           if (nh) __syncthreads();
           // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
@@ -547,7 +542,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           const unsigned int tag = ep2 + 1;
           if (F32) {
             for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
-              const float v0 = (float)s_out[sw32(o - c0)], v1 = (float)s_out[sw32(o + 1 - c0)];
+              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
               if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
               else {
                 if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
@@ -555,7 +550,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
               }
             }
           } else {
-            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[sw32(o - c0)], tag);
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
           }
           if (tid == 0) s_heavy_n = 0;
           __syncthreads();
