@@ -342,6 +342,13 @@ def main():
     d2h = 8 * ((T + 1) * 2 + T + 1) + 4 * 3
 
     peak, peak_src = measured_peak_gbs()
+    traffic = None   # DRAM bytes per launch of the persistent kernel from the committed ncu capture (same configuration only)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "persistent_traffic.json")))
+        if (N, T, args.resample_fn, args.precision) == (1 << 20, 1000, "stratified", "f32") and launches / max(args.steps, 1) <= 4:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     bytes_per_launch = algorithmic_bytes(N, T, n_res, sx=4 if prec == nat.F32 else 8, sw=4 if prec == nat.F32 else 8)
     ms_per_launch = total_ms / args.steps
     achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
@@ -354,7 +361,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "kernel": "whole filter pass (all launches of one step)" if launches / max(args.steps, 1) > 4 else "persistent filter kernel",
                      "algorithmic_bytes_per_launch": bytes_per_launch, "resampled_steps": int(n_res), "T": T},
         "loglike": r0["loglike"],
