@@ -60,7 +60,7 @@ int resample_cdf(bssm_ctx* ctx, const Src& src, MakeNorm make_norm, const RsArgs
   BSSM_TRY(scratch(ctx, SL_RS_CSTART, (size_t)a.nseg * ntiles, &cstart));
   BSSM_TRY(scratch(ctx, SL_RS_USED, (size_t)a.nseg * ntiles, &used));
   if (a.total) total = a.total; else BSSM_TRY(scratch(ctx, SL_RS_TOTAL, (size_t)a.nseg, &total));
-  dim3 grid(ntiles, a.nseg);
+  dim3 grid(a.nseg, ntiles);
   cudaStream_t st = ctx->stream;
   k_tile_sums<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.status, a.validate, a.enable);
   BSSM_LAUNCH(ctx, "k_tile_sums");
@@ -116,7 +116,7 @@ static int resample_stage(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, in
   us.buf = aux_stage ? f.noise.u_resample_aux : f.noise.u_resample;
   us.N = f.N; us.injected = f.noise.injected; us.seed = f.seed; us.run_id = f.run_id; us.stream = f.stream;
   us.tag = aux_stage ? TAG_RESAMP_AUX_U : TAG_RESAMP_U; us.obs = obs;
-  dim3 grid(f.nblk, f.C);
+  dim3 grid(f.C, f.nblk);
   k_search_gather<Real><<<grid, FT_THREADS, 0, ctx->stream>>>(f, us, L.resample_fn, obs, aux_stage, cdf);
   BSSM_LAUNCH(ctx, "k_search_gather");
   k_flip<<<(f.C + 127) / 128, 128, 0, ctx->stream>>>(f);
@@ -153,7 +153,7 @@ static int launch_post(bssm_ctx* ctx, const ModelKernels& K, dim3 grid, FilterDe
 
 template <typename Real>
 static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf, const ModelKernels& K) {
-  dim3 grid(f.nblk, f.C);
+  dim3 grid(f.C, f.nblk);
   cudaStream_t st = ctx->stream;
   if (f.algorithm == BSSM_APF && !K.has_aux) { set_error("model has no aux_log_likelihood_fn"); return BSSM_ERR_UNSUPPORTED; }
   if (f.algorithm == BSSM_RMPF && !K.has_move) { set_error("model has no move_fn"); return BSSM_ERR_UNSUPPORTED; }
@@ -419,7 +419,7 @@ int bssm_resample_device(bssm_ctx* ctx, int resample_fn, int batch, int n, const
   BSSM_TRY(resample_cdf_plain(ctx, d_weights, (size_t)n, a));
   USrcBuf us{d_u, resample_fn == BSSM_SYSTEMATIC ? (size_t)1 : (size_t)n};
   int gx = (n + 255) / 256; if (gx > 4096) gx = 4096;
-  k_search<USrcBuf><<<dim3(gx, batch), 256, 0, ctx->stream>>>(us, resample_fn, n, nullptr, cdf, (size_t)n, d_idx_out, (size_t)n, nullptr);
+  k_search<USrcBuf><<<dim3(batch, gx), 256, 0, ctx->stream>>>(us, resample_fn, n, nullptr, cdf, (size_t)n, d_idx_out, (size_t)n, nullptr);
   BSSM_LAUNCH(ctx, "k_search");
   return BSSM_OK;
 }

@@ -1,5 +1,5 @@
 // bssm_filter.cuh -- general particle-filter kernels, batched over
-// C independent filters (grid.y = filter).  Replaces the per-observation loop of
+// C independent filters (grid.x = filter, grid.y = block within the filter).  Replaces the per-observation loop of
 // .particle_filter_core (R/particle_filter_core.R:76-246) for BPF / APF / RMPF, every built-in
 // or NVRTC model, both precisions, injected or Philox noise, optional histories.
 // The throughput configurations of the bootstrap filter use the persistent kernel in
@@ -149,7 +149,7 @@ template <typename Real> __device__ __forceinline__ Real* x_other(const FilterDe
 template <typename Model, typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_init(FilterDev f) {
   __shared__ Acc sm[32];
-  int c = blockIdx.y;
+  int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c]) return;
   int n = filt_n(f, c);
   Real par[Model::NPAR];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_init(FilterDev f) {
   NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
   Real* x = (Real*)f.xa + (size_t)c * f.d * f.N;
   Acc a; acc_init(a); a.m = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     Real z[Model::NZ_INIT > 0 ? Model::NZ_INIT : 1];
     double u[Model::NU_INIT > 0 ? Model::NU_INIT : 1];
     for (int s = 0; s < Model::NZ_INIT; s++) z[s] = noise_normal<Real>(f, key, f.noise.z_init, Model::NZ_INIT, TAG_INIT_Z, T_INIT, 0, s, i);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_init(FilterDev f) {
     a.s += 1.0;
   }
   acc_block_reduce(a, Model::D, sm);
-  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.x) * PART_W);
+  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 
 // ---- K2: propagate + log-weight + block partials ---------------------------------------------
@@ -180,7 +180,7 @@ enum { WF_GAP = 1, WF_SECOND = 2 };
 template <typename Model, typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_weight(FilterDev f, int obs, int flags, int wkind) {
   __shared__ Acc sm[32];
-  int c = blockIdx.y;
+  int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c]) return;
   int n = filt_n(f, c);
   Real par[Model::NPAR];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_weight(FilterDev f, int obs, int
   double yv[4];
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   Acc a; acc_init(a);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     Real xi[Model::D];
     for (int k = 0; k < Model::D; k++) xi[k] = x[(size_t)k * f.N + i];
     Real z[Model::NZ_TRANS > 0 ? Model::NZ_TRANS : 1];
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_weight(FilterDev f, int obs, int
     acc_add<Real>(a, l, xi, Model::D);
   }
   acc_block_reduce(a, Model::D, sm);
-  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.x) * PART_W);
+  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 
 // ---- K3: per-filter finalise -------------------------------------------------------------------
@@ -295,7 +295,7 @@ struct USrcFilter {  // resampling uniforms of observation `obs`: injected [T][N
 template <typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_search_gather(FilterDev f, USrcFilter us, int fn, int obs, int aux_stage,
                                                              const double* __restrict__ cdf) {
-  int c = blockIdx.y;
+  int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c] || !f.resample[c]) return;
   int n = filt_n(f, c);
   const double* cd = cdf + (size_t)c * f.N;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_search_gather(FilterDev f, USrcF
   const Real* lwa = (const Real*)f.lw_aux + (size_t)c * f.N;
   Real* ag = (Real*)f.auxg + (size_t)c * f.N;
   int* hist = aux_stage ? f.anc_aux_history : f.anc_history;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     double pos;
     if (fn == 1) pos = ((double)i + us(c, 0)) / (double)n;
     else { double u = us(c, i); pos = (fn == 0) ? ((double)i + u) / (double)n : u; }
@@ -325,7 +325,7 @@ static __global__ void k_flip(FilterDev f) {
 template <typename Model, typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_post(FilterDev f, int obs) {
   __shared__ Acc sm[32];
-  int c = blockIdx.y;
+  int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c] || !f.resample[c]) return;
   int n = filt_n(f, c);
   Real par[Model::NPAR];
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_post(FilterDev f, int obs) {
   double yv[4];
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   Acc a; acc_init(a); a.m = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     Real xi[Model::D];
     for (int k = 0; k < Model::D; k++) xi[k] = x[(size_t)k * f.N + i];
     if (f.algorithm == 2 && Model::HAS_MOVE) {
@@ -350,20 +350,20 @@ __global__ void __launch_bounds__(FT_THREADS) k_post(FilterDev f, int obs) {
     for (int k = 0; k < Model::D; k++) a.sx[k] += (double)xi[k];
   }
   acc_block_reduce(a, Model::D, sm);
-  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.x) * PART_W);
+  if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 
 // ---- histories (R/particle_filter_core.R:100-116,242-245) ---------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_history(FilterDev f, int row /* 0..T */) {
-  int c = blockIdx.y;
+  int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c]) return;
   int n = filt_n(f, c);
   const Real* x = x_cur<Real>(f, c);
   const Real* lw = (const Real*)f.lw + (size_t)c * f.N;
   bool uniform = (row == 0) || f.resample[c];
   double M = f.M[c], S = f.S[c];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     if (f.particles_history)
       for (int k = 0; k < f.d; k++)
         f.particles_history[(((size_t)c * (f.T + 1) + row) * f.d + k) * f.N + i] = (double)x[(size_t)k * f.N + i];

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_sums(Src src, int n, const 
                                                          int* __restrict__ status, int validate,
                                                          const int* __restrict__ enable) {
   __shared__ double sm[34];
-  int seg = blockIdx.y, tile = blockIdx.x;
+  int seg = blockIdx.x, tile = blockIdx.y;   // segment in grid.x (no 65535 limit)
   if (!seg_on(enable, seg)) return;
   int nn = n_per_seg ? n_per_seg[seg] : n;
   int base = tile * RS_TILE + threadIdx.x * RS_IPT;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_scan(Src src, int n, const 
   __shared__ double wsum[RS_THREADS / 32];
   __shared__ int s_irreg;
   __shared__ i64 fsm[4][RS_THREADS / 32];
-  int seg = blockIdx.y, tile = blockIdx.x;
+  int seg = blockIdx.x, tile = blockIdx.y;   // segment in grid.x (no 65535 limit)
   if (!seg_on(enable, seg)) return;
   int nn = n_per_seg ? n_per_seg[seg] : n;
   if (tile * RS_TILE >= nn) return;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_exact(Src src, int n, const
                                                           double* __restrict__ cdf, size_t cdf_stride,
                                                           const int* __restrict__ enable) {
   __shared__ i64 fsm[2][RS_THREADS / 32];
-  int seg = blockIdx.y, tile = blockIdx.x;
+  int seg = blockIdx.x, tile = blockIdx.y;   // segment in grid.x (no 65535 limit)
   if (!seg_on(enable, seg)) return;
   int nn = n_per_seg ? n_per_seg[seg] : n;
   if (tile * RS_TILE >= nn) return;
@@ -371,11 +371,11 @@ __global__ void __launch_bounds__(256) k_search(USrc us, int fn, int n, const in
                                                const double* __restrict__ cdf, size_t cdf_stride,
                                                int* __restrict__ idx1, size_t idx_stride,
                                                const int* __restrict__ enable) {
-  int seg = blockIdx.y;
+  int seg = blockIdx.x;
   if (!seg_on(enable, seg)) return;
   int nn = n_per_seg ? n_per_seg[seg] : n;
   const double* c = cdf + (size_t)seg * cdf_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < nn; i += gridDim.y * blockDim.x) {
     double pos = resample_pos(us, fn, seg, i, nn);
     idx1[(size_t)seg * idx_stride + i] = lower_bound_clamped(c, nn, pos) + 1;
   }

@@ -130,3 +130,13 @@ def test_f32_precision_statistically_consistent(orc, engine):
     est = np.log(np.mean(np.exp(lls - lls.max()))) + lls.max()
     se = lls.std(ddof=1) / np.sqrt(len(lls))
     assert abs(est - exact) < 3 * se + 0.02, (est, exact, se)
+
+
+def test_more_than_65535_filters_in_one_batch(engine):
+    # .pilot_run of 1024 chains x 100 replicates is one batch of 102 400 filters: the filter index lives in grid.x
+    rng = np.random.default_rng(13)
+    y = sim_y(LG, 4, rng)
+    got = eh.filter_run(engine, LG, 0, 2, 0, 64, y, THETA[LG], seed=3, num_filters=70000, precision=nat.F64,
+                        engine=nat.ENGINE_GENERAL)
+    assert (got["status"] == 0).all() and np.isfinite(got["loglike"]).all()
+    assert len(np.unique(got["loglike"])) > 69000
