@@ -14,12 +14,12 @@ LIB_PATH = os.environ.get("BSSM_LIB_PATH") or os.path.join(_HERE, "libbayesssm_b
 
 # status codes / enums (include/bayesssm_b200.h)
 OK, ERR_NEGATIVE_WEIGHT, ERR_ZERO_SUM, ERR_NAN_WEIGHT, ERR_BAD_ARG, ERR_PRIOR_INIT, ERR_CUDA, ERR_NVRTC, \
-    ERR_UNSUPPORTED, ERR_NO_DEVICE = range(10)
+    ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CAPACITY, ERR_NCCL = range(12)
 BPF, APF, RMPF = 0, 1, 2
 SIS, SISR, SISAR = 0, 1, 2
 STRATIFIED, SYSTEMATIC, MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
-ENGINE_AUTO, ENGINE_GENERAL, ENGINE_PERSISTENT = 0, 1, 2
+ENGINE_AUTO, ENGINE_GENERAL, ENGINE_PERSISTENT, ENGINE_STREAM = 0, 1, 2, 3
 MODEL_AR_SIN, MODEL_LG, MODEL_RW_DRIFT, MODEL_SIR_CB, MODEL_AR_COS, MODEL_RW2D = range(6)
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_EXP, PRIOR_UNIF, PRIOR_HALFNORMAL = range(5)
 TR_IDENTITY, TR_LOG, TR_LOGIT = range(3)
@@ -116,6 +116,12 @@ SYMBOLS = {
     "bssm_model_noise_dims": (C.c_int, [_vp, C.c_int] + [c_int_p] * 6),
     "bssm_filter_run": (C.c_int, [_vp, C.POINTER(FilterConfig), c_double_p, c_double_p, C.POINTER(FilterResult)]),
     "bssm_filter_run_device": (C.c_int, [_vp, C.POINTER(FilterConfig), _vp, _vp, _vp, C.POINTER(C.c_float)]),
+    "bssm_shard_unique_id": (C.c_int, [C.c_char_p, _vp]),
+    "bssm_shard_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, _vp]),
+    "bssm_shard_finalize": (C.c_int, [_vp]),
+    "bssm_shard_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), c_int_p]),
+    "bssm_filter_run_sharded": (C.c_int, [_vp, C.POINTER(FilterConfig), c_double_p, c_double_p, C.c_double,
+                                          C.POINTER(FilterResult), c_int_p]),
     "bssm_model_compile": (C.c_int, [_vp, C.c_char_p, c_int_p]),
     "bssm_model_compile_log": (C.c_char_p, [_vp]),
     "bssm_pmmh_run": (C.c_int, [_vp, C.POINTER(PmmhConfig), c_double_p, c_double_p, C.POINTER(PmmhResult)]),

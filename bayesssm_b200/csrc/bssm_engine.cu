@@ -220,7 +220,12 @@ int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* c
     if (!fast_supported(f, L)) { set_error("BSSM_ENGINE_PERSISTENT: configuration not supported by the persistent kernel (BPF, 1-D built-in model, stratified/systematic, no histories / injected noise)"); return BSSM_ERR_UNSUPPORTED; }
     return fast_filter_enqueue(ctx, f, L);
   }
+  if (L.engine == BSSM_ENGINE_STREAM) {
+    if (!stream_supported(f, L)) { set_error("BSSM_ENGINE_STREAM: configuration not supported by the streaming engine (BPF, 1-D built-in model, stratified/systematic, no histories / injected noise)"); return BSSM_ERR_UNSUPPORTED; }
+    return stream_filter_enqueue(ctx, f, L, nullptr);
+  }
   if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && fast_supported(f, L)) return fast_filter_enqueue(ctx, f, L);
+  if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && stream_supported(f, L)) return stream_filter_enqueue(ctx, f, L, nullptr);
   if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC-compiled user model (bssm_nvrtc.cu)
     const UserModelInfo* u = user_model(ctx, L.model);
     if (!u) { set_error("unknown user model id %d", L.model); return BSSM_ERR_BAD_ARG; }

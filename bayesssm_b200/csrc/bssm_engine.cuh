@@ -43,6 +43,8 @@ enum ScratchSlot {
   SL_P_LAST = SL_P_BASE + 23,
   SL_FAST_BASE,
   SL_FAST_LAST = SL_FAST_BASE + 7,
+  SL_ST_BASE,   /* streaming engine */
+  SL_ST_LAST = SL_ST_BASE + 11,
   SL_COUNT
 };
 
@@ -69,6 +71,8 @@ struct bssm_ctx {
   bssm::Scratch scratch[bssm::SL_COUNT];
   std::string compile_log;
   std::vector<bssm::UserModelInfo> user_models;
+  void* nccl_comm = nullptr;   // ncclComm_t of the shard group (bssm_shard.cu)
+  int shard_rank = 0, shard_world = 1;
 };
 
 namespace bssm {
@@ -113,6 +117,17 @@ int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* c
 // persistent bootstrap-filter kernel (bssm_fast.cu)
 bool fast_supported(const FilterDev& f, const FilterLaunch& L);
 int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L);
+// streaming engine (bssm_stream.cu) and its particle-sharded form (bssm_shard.cu)
+struct ShardRun {
+  int rank, world;
+  int n_glob;        // particles of the whole filter
+  long long goff0;   // this rank's initial slice [goff0, goff0 + nloc0)
+  int nloc0;
+  int cap;           // storage capacity of this rank (particles)
+};
+bool stream_supported(const FilterDev& f, const FilterLaunch& L);
+int stream_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh);
+int shard_allgather(bssm_ctx* ctx, const ShardRun* sh, const void* d_send, void* d_recv, size_t bytes_per_rank);
 // NVRTC user models (bssm_nvrtc.cu)
 const UserModelInfo* user_model(bssm_ctx* ctx, int model_id);
 

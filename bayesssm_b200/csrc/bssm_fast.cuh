@@ -119,7 +119,7 @@ __device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
 // = first slot whose position exceeds c.  With t = c*n and i = floor(t): slots below i have
 // i' + U < i' + 1 <= t, slots above have i' >= i + 1 > t, so only slot i needs a look.
 // rare path (slot outside the staged window): kept out of line so the hot loop stays small (+3 %, A/B)
-__device__ __noinline__ unsigned int philox_word_slow(NoiseKey key, unsigned int obs, int i) {
+static __device__ __noinline__ unsigned int philox_word_slow(NoiseKey key, unsigned int obs, int i) {
   uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i >> 2);
   return q.w[i & 3];
 }

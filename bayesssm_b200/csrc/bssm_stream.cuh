@@ -1,0 +1,789 @@
+// bssm_stream.cuh -- streaming bootstrap-filter engine: particles resident in HBM, TWO kernels per
+// observation.  Serves what does not fit the persistent kernel's registers (bssm_fast.cuh): single
+// filters beyond ~10^6 particles, large batches [chains x particles], and the particle-sharded
+// multi-GPU filter (bssm_shard.cu), where one small record exchange sits between the two kernels.
+// Replaces the per-observation loop of .particle_filter_core (R/particle_filter_core.R:123-246)
+// for algorithm "BPF" and the resamplers of src/resampling.cpp:16-66 (stratified / systematic).
+//
+//   k_st_step      read x, propagate (one Philox call per 4 particles), log-weight, tile partials
+//                  (max, sum e, sum e^2, sum e*x), write x.  The LAST tile of a filter to finish
+//                  (ticket counter) merges the partials in fixed order: global max / sum / ESS /
+//                  log-likelihood / resampling decision, and the exclusive prefix of the tile sums
+//                  -- the scan offsets of the next kernel.  No separate finalise launch, no atomics
+//                  on floating-point data, deterministic.                        [8 B / particle]
+//   k_st_resample  (steps where resampling fires) read x, recompute the weight, tile-local scan;
+//                  INPUT-centric closed-form offspring ranges: a source with cdf value c owns the
+//                  output slots [F(c_prev), F(c)), F(c) = #{ i : (i + U_i)/n <= c } -- no search,
+//                  no cdf array in memory; chosen states are staged in shared memory and leave
+//                  the SM as coalesced vector stores.                            [8 B / particle]
+// Log-weights and the cdf never touch HBM (the weight is recomputed from x and y: a few flops
+// against 8 bytes), so the traffic is 16 B per resampled particle-timestep against the 40 B of the
+// algorithmic model.
+//
+// Tile boundaries in the output are derived by neighbouring tiles from the same prefix values with
+// the same expressions, so every output slot is written exactly once.  Same Philox keying and tie
+// rule (first j with cdf[j] >= pos, clamp) as the other engines.
+//
+// Storage: row c of x0 / x1 holds the filter's local particles at storage index
+// (global index - (goff & ~3)), so Philox quads stay aligned with 16-byte vectors for any shard
+// offset goff (goff = 0 when the filter is not sharded).
+#pragma once
+#include "bssm_common.cuh"
+#include "bssm_fast.cuh"
+#include "bssm_filter.cuh"
+#include "bssm_models.cuh"
+
+namespace bssm {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_NW = ST_THREADS / 32;
+constexpr int ST_SLACK = 512;       // staging capacity beyond the tile size
+constexpr int ST_HEAVY = 64;        // offspring count above which a source is expanded cooperatively
+constexpr int ST_HEAVY_CAP = 32;
+constexpr int ST_ERR_CAPACITY = 10; // status: a shard outgrew its storage (BSSM_ERR_CAPACITY)
+
+
+// layout / cdf descriptor of one filter on this rank, written once per observation
+struct StSeg {
+  long long goff, ngoff;   // global index of the first local particle: now / after this step's resampling
+  int nloc, nnloc;         // local particle count: now / after this step's resampling
+  int last, pad;           // 1: this rank holds the tail of the filter
+  double abase, aend;      // cdf numerator (relative to the global max) before / after this rank's particles
+  double gscale;           // exp(local max - global max)
+};
+
+struct StRec { double m, s, q, sx, pend, nan, pad0, pad1; };   // per-rank record (sharded runs)
+
+struct StreamParams {
+  FilterDev f;
+  int resample_fn;
+  int nt;                  // tiles per filter row (capacity)
+  size_t xstride;          // elements per filter row of x0 / x1 (= nt * tile size)
+  void *x0, *x1;           // x0: resampled (or initial) particles; x1: propagated particles
+  double *part_m, *part_s, *part_q, *part_x;   // [C][nt] tile partials (max; sum e, sum e^2, sum e*x relative to it)
+  double* pref;            // [C][nt + 1] exclusive prefix of the tile sums, relative to the local max
+  double* bsum;            // [C][nt] sum of the states written by a tile (state estimate after resampling)
+  unsigned int* counter;   // [C] tickets
+  int* res;                // [2][C] resampling decision of an observation, by parity
+  StSeg* seg;              // [2][C] by parity
+  int n_glob;              // sharded: global particle count; 0: filt_n
+  int sharded, rank, world;
+  StRec* rec_local;        // [C] this rank's record
+  StRec* rec_all;          // [world][C] gathered records
+  int cap;                 // storage capacity (particles) of a row
+  int bpc, bpc_r;          // blocks per filter of k_st_step / k_st_resample
+  double log_n;            // log(particle count) when every filter has the same count (else NaN: computed on the device)
+  long long* dbg;          // optional [8] clock64 stamps of the merging block (BSSM_ST_TIMING, diagnostics)
+};
+
+// explicitly rounded a + p * g: the same boundary value in every tile / rank that evaluates it
+__device__ __forceinline__ double st_bound(double a, double p, double g) { return __dadd_rn(a, __dmul_rn(p, g)); }
+
+template <typename Real, int PPT> struct StVec {
+  static __device__ __forceinline__ void load(Real* x, const Real* p) {
+    if constexpr (sizeof(Real) == 4) {
+#pragma unroll
+      for (int h = 0; h < PPT / 4; h++) { float4 v = *(const float4*)(p + 4 * h); x[4 * h] = v.x; x[4 * h + 1] = v.y; x[4 * h + 2] = v.z; x[4 * h + 3] = v.w; }
+    } else {
+#pragma unroll
+      for (int h = 0; h < PPT / 2; h++) { double2 v = *(const double2*)(p + 2 * h); x[2 * h] = v.x; x[2 * h + 1] = v.y; }
+    }
+  }
+  static __device__ __forceinline__ void store(Real* p, const Real* x) {
+    if constexpr (sizeof(Real) == 4) {
+#pragma unroll
+      for (int h = 0; h < PPT / 4; h++) *(float4*)(p + 4 * h) = make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < PPT / 2; h++) *(double2*)(p + 2 * h) = make_double2(x[2 * h], x[2 * h + 1]);
+    }
+  }
+};
+
+// layout an observation's kernels work on: the previous observation's descriptor, after its resampling if it fired
+struct StLayout { long long goff; int nloc, lead, ntc; };
+template <int TS>
+__device__ __forceinline__ StLayout st_layout_in(const StreamParams& P, int c, int obs) {
+  const int pp = (obs + 1) & 1;
+  const StSeg& sp = P.seg[pp * P.f.C + c];
+  const int rprev = P.res[pp * P.f.C + c];
+  StLayout L;
+  L.goff = rprev ? sp.ngoff : sp.goff;
+  L.nloc = rprev ? sp.nnloc : sp.nloc;
+  L.lead = (int)(L.goff & 3);
+  L.ntc = max(1, (L.nloc + L.lead + TS - 1) / TS);
+  return L;
+}
+
+// ---- global part of the per-observation bookkeeping (R/particle_filter_core.R:189-224) ----
+// recs: `world` records in rank order.  Every rank evaluates the same expressions on the same records.
+// The work is split into three independent roles so that the merging block of k_st_step can run them on
+// three different warps at once (each is a chain of dependent fp64 operations executed by a single thread,
+// and fp64 latency is what the tail of the kernel is made of): ST_DECIDE publishes what the resampling
+// kernel needs, ST_LOGLIKE the running log-likelihood, ST_ESTIMATES the ESS / state-estimate outputs.
+enum { ST_DECIDE = 1, ST_LOGLIKE = 2, ST_ESTIMATES = 4, ST_ALL_ROLES = 7 };
+static __device__ __noinline__ void st_global(const StreamParams& P, int c, int obs, const StRec* recs, int rstride, int world, int rank,
+                                              long long goff, int nloc, int roles) {
+  const FilterDev& f = P.f;
+  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  const int C = f.C, pc = obs & 1, pp = (obs + 1) & 1;
+  const int n = P.n_glob ? P.n_glob : filt_n(f, c);
+  const int T1 = f.T + 1;
+  const int rprev = P.res[pp * C + c];
+  double M = NINF;
+  int nan = 0;
+  for (int g = 0; g < world; g++) { const StRec& r = recs[(size_t)g * rstride]; M = r.m > M ? r.m : M; nan |= (r.nan != 0.0) || (r.m != r.m); }
+  double S = 0.0, Q = 0.0, SX = 0.0, PEND = 0.0, abase = 0.0, aend = 0.0, gscale = 0.0;
+  for (int g = 0; g < world; g++) {
+    const StRec& r = recs[(size_t)g * rstride];
+    double sc = 0.0;
+    if (r.m == M) sc = (M == NINF) ? 0.0 : 1.0;
+    else if (r.m != NINF) sc = exp(r.m - M);
+    if (g == rank) { abase = S; gscale = sc; }
+    S = st_bound(S, r.s, sc);
+    if (g == rank) aend = S;
+    Q += r.q * sc * sc; SX += r.sx * sc; PEND += r.pend;
+  }
+  const bool bad = nan || (S != S) || (SX != SX) || (M != M);
+  const bool empty = M < -1e8;
+  const int ralg = f.ralg;
+  double thr = f.threshold;
+  if (thr < 0) thr = (ralg == 0) ? -NINF : (ralg == 1 ? (double)n : 0.5 * (double)n);
+  // ess < thr  <=>  S^2 < thr * Q  (no division on the path the next kernel waits for)
+  int resample = (bad || empty) ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
+
+  if (roles & ST_DECIDE) {
+    StSeg sg;
+    sg.goff = goff; sg.nloc = nloc; sg.ngoff = goff; sg.nnloc = nloc; sg.last = (rank == world - 1); sg.pad = 0;
+    sg.abase = abase; sg.aend = aend; sg.gscale = gscale;
+    if (bad) { f.status[c] = 3; f.alive[c] = 0; }                  // NaN weight somewhere: R's `if (NA)` error
+    else if (empty) { f.early_exit[c] = 1; f.alive[c] = 0; }       // all(lw < -1e8): R/particle_filter_core.R:189-202
+    else if (resample) {
+      f.n_resampled[c] += 1;
+      if (world > 1) {               // rank g's share of the output slots: [F(A_g / S), F(A_{g+1} / S))
+        SlotCounter sc;
+        sc.key = make_key(f.seed, f.run_id[c], f.stream[c]); sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n;
+        sc.s_u = nullptr; sc.u_base = 0; sc.u_cap = 0; sc.w_sys = 0u;
+        if (P.resample_fn == 1) { uint4x q0 = noise_quad(sc.key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u); sc.w_sys = q0.w[0]; }
+        // every rank checks every rank's share, so a capacity overflow stops the whole group consistently
+        double run = 0.0;
+        int o_prev = 0, overflow = 0;
+        for (int g = 0; g < world; g++) {
+          const StRec& r = recs[(size_t)g * rstride];
+          double scg = 0.0;
+          if (r.m == M) scg = 1.0;
+          else if (r.m != NINF) scg = exp(r.m - M);
+          run = st_bound(run, r.s, scg);
+          const int o_next = (g == world - 1) ? n : sc.count_le(run / S);
+          if (o_next - o_prev + 4 > P.cap) overflow = 1;
+          if (g == rank) { sg.ngoff = o_prev; sg.nnloc = o_next - o_prev; }
+          o_prev = o_next;
+        }
+        if (overflow) { f.status[c] = ST_ERR_CAPACITY; f.alive[c] = 0; resample = 0; }
+      }
+    }
+    f.M[c] = M; f.S[c] = S;
+    P.seg[pc * C + c] = sg;
+    P.res[pc * C + c] = resample;
+  }
+  if (roles & ST_LOGLIKE) {
+    if (!bad) {
+      const double ll = empty ? NINF : f.loglike[c] + (M + log(S) - ((P.log_n == P.log_n) ? P.log_n : log((double)n)));
+      f.loglike[c] = ll;
+      if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = ll;
+    }
+  }
+  if (roles & ST_ESTIMATES) {
+    if (obs == 0) f.ess[(size_t)c * T1] = (double)n;
+    if (rprev) f.state_est[(size_t)c * T1 + obs] = PEND / (double)n;   // initial particles (obs = 0) or the previous resampling
+    if (!bad && !empty) {
+      f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+      if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+    }
+  }
+}
+
+// ---- local merge of the tile partials by the last block of a filter (all threads of the block) ----
+// Produces this rank's record and the exclusive prefix of the tile sums (relative to the local max).
+// One SM does this while the others idle, so it is built for that SM's memory pipeline: the partials
+// are SoA arrays, warp w owns the contiguous tiles [w * seg, (w + 1) * seg) and walks them 32 at a time
+// (lane = tile: fully coalesced 256-byte requests), rounds are independent apart from a one-add carry.
+// Plain loads: the partials were published with fence + ticket and are read after ticket + fence, and no
+// line of them was in this SM's L1 before (strong .cg loads would serialise behind the prefix stores).
+// Fixed structure => deterministic.
+template <typename Real>
+static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int c, int ntc, bool with_pending, double* s_red /*[4][ST_NW]*/, StRec& out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  const size_t row = (size_t)c * P.nt;
+  const double* __restrict__ pm = P.part_m + row;
+  const double* __restrict__ ps = P.part_s + row;
+  const double* __restrict__ pq = P.part_q + row;
+  const double* __restrict__ px = P.part_x + row;
+  const double* __restrict__ bsum = P.bsum + row;
+  double* __restrict__ pref = P.pref + (size_t)c * (P.nt + 1);
+  const int seg = ((ntc + ST_NW - 1) / ST_NW + 31) & ~31;      // tiles per warp, multiple of 32
+  const int j0 = min(ntc, wid * seg), j1 = min(ntc, j0 + seg);
+  if (P.dbg && tid == 0) P.dbg[4] = clock64();
+  double m = NINF;
+#pragma unroll 4
+  for (int j = j0 + lane; j < j1; j += 32) { const double mj = pm[j]; m = mj > m ? mj : m; }   // NaN maxima are caught through s
+  m = warp_max_d(m);
+  if (lane == 0) s_red[wid] = m;
+  __syncthreads();
+  m = warp_max_d(lane < ST_NW ? s_red[lane] : NINF);
+  __syncthreads();
+  if (P.dbg && tid == 0) P.dbg[5] = clock64();
+  double lq = 0.0, lx = 0.0, lp = 0.0, carry = 0.0;
+#pragma unroll 2
+  for (int jb = j0; jb < j1; jb += 32) {
+    const int j = jb + lane;
+    const bool on = j < j1;
+    const double mj = on ? pm[j] : NINF, sj = on ? ps[j] : 0.0;
+    const double qj = on ? pq[j] : 0.0, xj = on ? px[j] : 0.0;
+    const double bj = (on && with_pending) ? bsum[j] : 0.0;
+    double sc = 0.0;
+    if (!(mj == NINF || m == NINF)) sc = (double)Math<Real>::exp_((Real)(mj - m));   // throughput precision: SFU exp, not an fp64 chain
+    const double v = sj * sc;
+    lq += qj * sc * sc; lx += xj * sc; lp += bj;
+    const double inc = warp_incl_scan_d(v, lane);
+    if (on) pref[j] = carry + (inc - v);            // exclusive prefix relative to this warp's segment
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (P.dbg && tid == 0) P.dbg[6] = clock64();
+  const double tq = warp_sum_d(lq), tx = warp_sum_d(lx), tp = warp_sum_d(lp);
+  if (lane == 0) { s_red[wid] = carry; s_red[ST_NW + wid] = tq; s_red[2 * ST_NW + wid] = tx; s_red[3 * ST_NW + wid] = tp; }
+  __syncthreads();
+  double woff = 0.0, S = 0.0, Q = 0.0, SX = 0.0, PD = 0.0;
+#pragma unroll
+  for (int w = 0; w < ST_NW; w++) {                 // fixed order
+    if (w == wid) woff = S;
+    S += s_red[w]; Q += s_red[ST_NW + w]; SX += s_red[2 * ST_NW + w]; PD += s_red[3 * ST_NW + w];
+  }
+  if (P.dbg && tid == 0) P.dbg[7] = clock64();
+  if (wid > 0) {
+#pragma unroll 4
+    for (int j = j0 + lane; j < j1; j += 32) pref[j] += woff;     // own values: the same thread wrote them
+  }
+  if (tid == 0) pref[ntc] = S;
+  out.m = m; out.s = S; out.q = Q; out.sx = SX; out.pend = PD; out.nan = (S != S) ? 1.0 : 0.0; out.pad0 = 0; out.pad1 = 0;
+  __syncthreads();
+}
+
+// ---- setup: descriptors of "observation -1" (so that observation 0 reads the initial particles from x0) ----
+static __global__ void k_st_setup(StreamParams P, long long goff0, int nloc0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.f.C) return;
+  const int n = P.n_glob ? P.n_glob : filt_n(P.f, c);
+  StSeg sg;
+  sg.goff = sg.ngoff = P.sharded ? goff0 : 0;
+  sg.nloc = sg.nnloc = P.sharded ? nloc0 : n;
+  sg.last = P.rank == P.world - 1; sg.pad = 0; sg.abase = 0; sg.aend = 0; sg.gscale = 1;
+  P.seg[1 * P.f.C + c] = sg; P.seg[c] = sg;
+  P.res[1 * P.f.C + c] = 1; P.res[c] = 0;
+  P.counter[c] = 0u;
+}
+
+// ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, tile sums for the t = 0 state estimate ----
+template <typename Model, typename Real, int PPT>
+__global__ void __launch_bounds__(ST_THREADS) k_st_init(StreamParams P) {
+  constexpr int TS = ST_THREADS * PPT;
+  __shared__ double s_red[ST_NW];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x / P.nt, tile = blockIdx.x % P.nt, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!f.alive[c]) return;
+  const StLayout L = st_layout_in<TS>(P, c, 0);
+  if (tile >= L.ntc) return;
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int sbase = tile * TS + tid * PPT;
+  const long long g0 = L.goff - L.lead + sbase;
+  Real x[PPT];
+  double sum0 = 0.0;
+#pragma unroll
+  for (int h = 0; h < PPT / 4; h++) {
+    uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
+    Real zz[4];
+    Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
+    Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      Real xi[1]; Real zi[1] = {zz[k]};
+      Model::template init<Real>(xi, par, zi, nullptr);
+      const long long g = g0 + 4 * h + k;
+      const bool valid = g >= L.goff && g < L.goff + L.nloc;
+      x[4 * h + k] = valid ? xi[0] : (Real)0;
+      sum0 += (double)x[4 * h + k];
+    }
+  }
+  StVec<Real, PPT>::store((Real*)P.x0 + (size_t)c * P.xstride + sbase, x);
+  double v = warp_sum_d(sum0);
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = warp_sum_d(lane < ST_NW ? s_red[lane] : 0.0);
+    if (lane == 0) P.bsum[(size_t)c * P.nt + tile] = t;
+  }
+}
+
+// per-thread asynchronous prefetch of the next tile's 32 bytes (cp.async, no registers held while in flight).
+// Layout [2 halves][ST_THREADS] x 16 B: conflict-free 128-bit shared loads.
+__device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <typename Real, int PPT>
+__device__ __forceinline__ void st_prefetch(uint4* buf /*[2][ST_THREADS]*/, const Real* g) {
+  static_assert(PPT * sizeof(Real) == 32, "32 bytes per thread and tile");
+  st_cp_async16(&buf[threadIdx.x], g);
+  st_cp_async16(&buf[ST_THREADS + threadIdx.x], (const char*)g + 16);
+  st_cp_async_commit();
+}
+template <typename Real, int PPT>
+__device__ __forceinline__ void st_take(Real* x, const uint4* buf) {
+  st_cp_async_wait();
+  const uint4 a = buf[threadIdx.x], b = buf[ST_THREADS + threadIdx.x];
+  if constexpr (sizeof(Real) == 4) {
+    x[0] = __uint_as_float(a.x); x[1] = __uint_as_float(a.y); x[2] = __uint_as_float(a.z); x[3] = __uint_as_float(a.w);
+    x[4] = __uint_as_float(b.x); x[5] = __uint_as_float(b.y); x[6] = __uint_as_float(b.z); x[7] = __uint_as_float(b.w);
+  } else {
+    x[0] = __longlong_as_double(((long long)a.y << 32) | a.x); x[1] = __longlong_as_double(((long long)a.w << 32) | a.z);
+    x[2] = __longlong_as_double(((long long)b.y << 32) | b.x); x[3] = __longlong_as_double(((long long)b.w << 32) | b.z);
+  }
+}
+template <typename Real> __device__ __forceinline__ Real st_warp_sum(Real v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename Real> __device__ __forceinline__ Real st_warp_max(Real v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+// ---- K_A: propagate + log-weight + tile partials; the last block of a filter merges ----
+// Block (c, j) of `bpc` blocks per filter walks the tiles j, j + bpc, ... of filter c; the next tile's
+// particles are in flight (cp.async) while the current tile is computed, and the block pays the
+// descriptor loads, the parameter set-up and the fence + ticket once, not once per tile.
+template <typename Model, typename Real, int PPT>
+__global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int obs) {
+  static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
+                "streaming engine: 1-D models with one normal per transition");
+  static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
+  constexpr int TS = ST_THREADS * PPT;
+  __shared__ uint4 s_pf[2][2 * ST_THREADS];
+  __shared__ Real s_w[2][4][ST_NW];     // per-warp partials by tile parity
+  __shared__ double s_red[4 * ST_NW];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long t_start = P.dbg ? clock64() : 0;
+  if (!f.alive[c]) return;
+  const StLayout L = st_layout_in<TS>(P, c, obs);
+  if (j >= L.ntc) return;
+  const int rprev = P.res[((obs + 1) & 1) * f.C + c];
+  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  const Real* xin = (const Real*)(rprev ? P.x0 : P.x1) + (size_t)c * P.xstride + tid * PPT;
+  Real* xout = (Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
+  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)j * TS);
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
+  const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
+  double yv[4] = {0, 0, 0, 0};
+  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
+  const size_t prow = (size_t)c * P.nt;
+
+  int it = 0;
+  for (int tile = j; tile < L.ntc; tile += P.bpc, it++) {
+    const int pb = it & 1;
+    Real x[PPT];
+    st_take<Real, PPT>(x, s_pf[pb]);
+    if (tile + P.bpc < L.ntc) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + P.bpc) * TS);
+    const int sbase = tile * TS + tid * PPT;
+    const long long g0 = L.goff - L.lead + sbase;
+    const int k_lo = (int)max(0LL, min((long long)PPT, L.goff - g0));
+    const int k_hi = (int)max(0LL, min((long long)PPT, L.goff + L.nloc - g0));
+    const bool ragged = k_lo > 0 || k_hi < PPT;   // only the first / last threads of a shard hold padding lanes
+    if (ragged) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) x[k] = (Real)0;   // padding lanes stay finite
+    }
+    for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
+#pragma unroll
+      for (int h = 0; h < PPT / 4; h++) {
+        uint4x qd = noise_quad(key, (unsigned int)(tnow - 1), TAG_TRANS_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
+        Real zz[4];
+        Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
+        Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          Real zi[1] = {zz[k]};
+          Model::template transition<Real>(&x[4 * h + k], par, tnow, zi, nullptr);
+        }
+      }
+    }
+    StVec<Real, PPT>::store(xout + (size_t)tile * TS, x);
+    Real e[PPT];
+    Real mloc = Math<Real>::ninf();
+    int nanf = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+      e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
+      nanf |= (e[k] != e[k]);
+    }
+    if (ragged) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) e[k] = Math<Real>::ninf();
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; k++) mloc = e[k] > mloc ? e[k] : mloc;
+    // warp-level reference (no block barrier on the weight path): e relative to the warp max
+    const Real mw = st_warp_max<Real>(mloc);
+    Real fs = 0, fq = 0, fx = 0;
+    {
+      const Real mwr = (mw == Math<Real>::ninf()) ? (Real)0 : mw;
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const Real ek = Math<Real>::exp_(e[k] - mwr);
+        fs += ek; fq += ek * ek; fx += ek * x[k];
+      }
+    }
+    if (nanf) fs = fs + (Real)__int_as_float(0x7FC00000);   // a NaN log-weight poisons the sum (R: `if (NA)` error)
+    fs = st_warp_sum<Real>(fs); fq = st_warp_sum<Real>(fq); fx = st_warp_sum<Real>(fx);
+    if (lane == 0) { s_w[pb][0][wid] = mw; s_w[pb][1][wid] = fs; s_w[pb][2][wid] = fq; s_w[pb][3][wid] = fx; }
+    __syncthreads();
+    if (wid == 0) {
+      // tile partial from the ST_NW warp partials (fixed tree over lanes 0..7, state precision, no fp64 chain)
+      const int l8 = lane & (ST_NW - 1);
+      const Real m = s_w[pb][0][l8];
+      Real mt = m;
+#pragma unroll
+      for (int o = ST_NW / 2; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, mt, o); mt = t > mt ? t : mt; }
+      Real sc = 0;
+      if (!(m == Math<Real>::ninf() || mt == Math<Real>::ninf())) sc = Math<Real>::exp_(m - mt);
+      Real a0 = s_w[pb][1][l8] * sc, a1 = s_w[pb][2][l8] * sc * sc, a2 = s_w[pb][3][l8] * sc;
+#pragma unroll
+      for (int o = ST_NW / 2; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane == 0) { P.part_m[prow + tile] = (double)mt; P.part_s[prow + tile] = (double)a0; P.part_q[prow + tile] = (double)a1; P.part_x[prow + tile] = (double)a2; }
+    }
+  }
+  // one ticket per block; the last block of the filter merges.  The barrier-reduction makes the outcome a
+  // block-uniform value the compiler can see, so the merge below runs as convergent code (plain shuffles)
+  int mine = 0;
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&P.counter[c], 1u);
+    mine = (ticket == (unsigned int)(min(P.bpc, L.ntc) - 1));
+  }
+  if (!__syncthreads_or(mine)) return;
+  __threadfence();
+  const long long t_tick = P.dbg ? clock64() : 0;
+  if (P.dbg && tid == 0) P.dbg[3] = t_tick;
+  StRec r;
+  st_local_merge<Real>(P, c, L.ntc, rprev != 0, s_red, r);
+  const long long t_merge = P.dbg ? clock64() : 0;
+  if (tid == 0) P.counter[c] = 0u;
+  if (P.sharded) { if (tid == 0) P.rec_local[c] = r; }
+  else if (lane == 0 && wid < 3) st_global(P, c, obs, &r, 0, 1, 0, L.goff, L.nloc, 1 << wid);   // three roles on three warps
+  if (P.dbg && tid == 0) { P.dbg[0] = t_tick - t_start; P.dbg[1] = t_merge - t_tick; P.dbg[2] = clock64() - t_merge; P.dbg[7] = t_merge - P.dbg[7]; P.dbg[6] = P.dbg[6] - P.dbg[5]; P.dbg[5] = P.dbg[5] - P.dbg[4]; P.dbg[4] = P.dbg[4] - t_tick; }
+}
+
+// sharded runs: global bookkeeping from the gathered records (one thread per filter)
+static __global__ void k_st_merge(StreamParams P, int obs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.f.C || !P.f.alive[c]) return;
+  const StLayout L = st_layout_in<1>(P, c, obs);
+  st_global(P, c, obs, P.rec_all + c, P.f.C, P.world, P.rank, L.goff, L.nloc, ST_ALL_ROLES);
+}
+
+// ---- K_B: resampling (scan + closed-form offspring ranges + staged scatter) ----
+// Same block-to-tile assignment and prefetch as k_st_step.
+template <typename Model, typename Real, int PPT>
+__global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, int obs) {
+  constexpr bool F32 = sizeof(Real) == 4;
+  constexpr int TS = ST_THREADS * PPT;
+  constexpr int CAP = TS + ST_SLACK;
+  __shared__ __align__(16) Real s_out[CAP];
+  __shared__ __align__(16) unsigned int s_u[CAP];
+  __shared__ uint4 s_pf[2][2 * ST_THREADS];
+  __shared__ double s_red[ST_NW], s_bs[ST_NW], s_cdf[2];
+  __shared__ int s_wf[ST_NW];
+  __shared__ int s_heavy_n;
+  __shared__ int s_heavy_lo[ST_HEAVY_CAP], s_heavy_hi[ST_HEAVY_CAP];
+  __shared__ Real s_heavy_x[ST_HEAVY_CAP];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x / P.bpc_r, j = blockIdx.x % P.bpc_r, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!f.alive[c]) return;
+  const int pc = obs & 1;
+  if (!P.res[pc * f.C + c]) return;
+  const StSeg sg = P.seg[pc * f.C + c];
+  const int lead = (int)(sg.goff & 3);
+  const int ntc = max(1, (sg.nloc + lead + TS - 1) / TS);
+  if (j >= ntc) return;
+  const Real* xin = (const Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
+  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)j * TS);
+  const int n = P.n_glob ? P.n_glob : filt_n(f, c);
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
+  double yv[4] = {0, 0, 0, 0};
+  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
+  const double M = f.M[c], S = f.S[c];
+  const double wscale = 1.0 / S;
+  const double* pref = P.pref + (size_t)c * (P.nt + 1);
+  Real* xo = (Real*)P.x0 + (size_t)c * P.xstride - (sg.ngoff & ~3LL);   // xo[slot] = storage of global slot
+  if (tid == 0) s_heavy_n = 0;
+  double p_lo = pref[j], p_hi = pref[j + 1];
+
+  int it = 0;
+  for (int tile = j; tile < ntc; tile += P.bpc_r, it++) {
+  const int pb = it & 1;
+  const int sbase = tile * TS + tid * PPT;
+  const long long g0 = sg.goff - lead + sbase;
+  const int k_lo = (int)max(0LL, min((long long)PPT, sg.goff - g0));
+  const int k_hi = (int)max(0LL, min((long long)PPT, sg.goff + sg.nloc - g0));
+  const int last_s = min(TS, sg.nloc + lead - tile * TS) - 1;   // in-tile storage index of the last valid particle
+  const bool ragged = k_lo > 0 || k_hi < PPT;
+  // this tile's cdf interval, from the prefix array (bit-identical in the neighbouring tiles)
+  const double A_lo = tile == 0 ? sg.abase : st_bound(sg.abase, p_lo, sg.gscale);
+  const double A_hi = tile == ntc - 1 ? sg.aend : st_bound(sg.abase, p_hi, sg.gscale);
+  Real x[PPT], e[PPT];
+  st_take<Real, PPT>(x, s_pf[pb]);
+  if (tile + P.bpc_r < ntc) {
+    st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + P.bpc_r) * TS);
+    p_lo = pref[tile + P.bpc_r]; p_hi = pref[tile + P.bpc_r + 1];
+  }
+  Real fs = 0;
+  {
+    const Real Mr = (Real)M;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+      const Real lw = Model::template loglik<Real>(yv, &x[k], par, ot);
+      e[k] = Math<Real>::exp_(lw - Mr);
+    }
+    if (ragged) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) e[k] = (Real)0;
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; k++) fs += e[k];
+  }
+  // tile-local exclusive prefix of the thread sums: fp64 across warps; inside a warp fp32 in the throughput
+  // precision (256 particles: error ~1e-4 output slots), fp64 in the parity precision
+  double exu;
+  {
+    Real inc = fs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { Real t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_red[wid] = (double)inc;
+    if (tid == 0) {   // one pair of boundary values per tile, not per thread
+      if (F32) { s_cdf[0] = A_lo * wscale; s_cdf[1] = A_hi * wscale; }      // reciprocal: no fp64 division chain before the barrier
+      else { s_cdf[0] = A_lo / S; s_cdf[1] = A_hi / S; }
+    }
+    __syncthreads();
+    double wbase = 0.0;
+#pragma unroll
+    for (int w = 0; w < ST_NW - 1; w++) wbase += (w < wid) ? s_red[w] : 0.0;   // fixed order
+    exu = wbase + (double)(inc - fs);
+  }
+  const bool tail = sg.last && tile == ntc - 1;
+  const double lo_cdf = s_cdf[0];
+  const double hi_cdf = tail ? 2.0 : s_cdf[1];
+
+  SlotCounter sc;
+  sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
+  sc.s_u = s_u; sc.u_cap = CAP;
+  {
+    const double t0 = lo_cdf * (double)n;
+    const int i0 = t0 >= (double)n ? n : (int)t0;
+    sc.u_base = max(0, (i0 & ~3) - 4);
+  }
+  if (P.resample_fn == 1) {
+    uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
+    sc.w_sys = q0.w[0];
+  } else {
+    const int q_end = min((n + 3) >> 2, (sc.u_base + CAP) >> 2);
+    for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += ST_THREADS) {
+      uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+      *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+    }
+  }
+  __syncthreads();
+  const int o_lo = sc.count_le(lo_cdf);
+  const int o_hi = tail ? n : sc.count_le(hi_cdf);
+  int F[PPT];
+  {
+    int fmax = o_lo;
+    if (F32) {
+      const double T0 = (lo_cdf + exu * wscale) * (double)n;
+      const double T0c = T0 < (double)n ? T0 : (double)n;
+      const int I0 = (int)T0c;
+      const float f0 = (float)(T0c - (double)I0);
+      const float wsn = (float)(wscale * (double)n);
+      float accf = 0.f;
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        accf += (float)e[k];
+        const float tf = fmaf(accf, wsn, f0);
+        const float r = (tf - 0.5f) + 12582912.0f;
+        const int ii = __float_as_int(r) - 0x4B400000;
+        const float frac = tf - (r - 12582912.0f);
+        const float g = frac + 1.0f;
+        const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;
+        const int i = I0 + ii;
+        int v;
+        if (tf >= 4194304.0f) v = sc.count_le(lo_cdf + (exu + (double)accf) * wscale);   // beyond the fp32 floor trick (degenerate weights)
+        else if (i >= n) v = n;
+        else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);
+        if (tid * PPT + k == last_s) v = o_hi;
+        v = min(max(v, o_lo), o_hi);
+        if (ragged && (k < k_lo || k >= k_hi)) v = o_lo;
+        fmax = max(fmax, v);
+        F[k] = fmax;
+      }
+    } else {
+      double acc = exu;
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        acc += (double)e[k];
+        int v = o_lo;
+        if (k >= k_lo && k < k_hi) {
+          v = sc.count_le(lo_cdf + acc * wscale);
+          if (tid * PPT + k == last_s) v = o_hi;
+          v = min(max(v, o_lo), o_hi);
+        }
+        fmax = max(fmax, v);
+        F[k] = fmax;
+      }
+    }
+  }
+  int prevF;
+  {
+    int inc = F[PPT - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+    if (lane == 31) s_wf[wid] = inc;
+    prevF = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prevF = o_lo;
+    __syncthreads();
+    int wv = lane < ST_NW ? s_wf[lane] : o_lo;
+    int winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc = max(winc, t); }
+    int wprev = __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);
+    if (wid == 0) wprev = o_lo;
+    prevF = max(prevF, wprev);
+#pragma unroll
+    for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
+  }
+  // scatter into the staging buffer (chunks of CAP slots), copy out coalesced
+  Real sumx = 0;
+  const int o_base = o_lo & ~3;
+  for (int c0 = o_base; c0 < o_hi; c0 += CAP) {
+    const int c1 = min(o_hi, c0 + CAP);
+    int lo_k = prevF;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+      const int hi_k = F[k];
+      const int a = max(lo_k, c0);
+      int cnt = min(hi_k, c1) - a;
+      if (c0 == o_base && hi_k > lo_k) sumx += (Real)(hi_k - lo_k) * x[k];
+      if (cnt > ST_HEAVY) {
+        int slot = atomicAdd(&s_heavy_n, 1);
+        if (slot < ST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = a + cnt; s_heavy_x[slot] = x[k]; cnt = 0; }
+      }
+      Real* dst = s_out + (a - c0);
+      if (cnt > 0) dst[0] = x[k];
+      if (cnt > 1) dst[1] = x[k];
+      if (__any_sync(0xffffffffu, cnt > 2)) {       // warp-uniform: most sources have 0, 1 or 2 offspring
+        const int mx = __reduce_max_sync(0xffffffffu, cnt);
+        for (int r = 2; r < mx; r++) if (r < cnt) dst[r] = x[k];
+      }
+      lo_k = max(lo_k, hi_k);
+    }
+    __syncthreads();
+    const int nh = min(s_heavy_n, ST_HEAVY_CAP);
+    for (int h = 0; h < nh; h++) {
+      const int a = s_heavy_lo[h], z = s_heavy_hi[h];
+      const Real xv = s_heavy_x[h];
+      for (int o = a + tid; o < z; o += ST_THREADS) s_out[o - c0] = xv;
+    }
+    if (nh) __syncthreads();
+    const int first = max(c0, o_lo), last = c1;
+    if (F32) {
+      for (int o = c0 + 4 * tid; o < last; o += 4 * ST_THREADS) {
+        const float4 v = *(const float4*)&s_out[o - c0];
+        if (o >= first && o + 3 < last) *(float4*)&xo[o] = v;
+        else {
+          if (o >= first && o < last) xo[o] = v.x;
+          if (o + 1 >= first && o + 1 < last) xo[o + 1] = v.y;
+          if (o + 2 >= first && o + 2 < last) xo[o + 2] = v.z;
+          if (o + 3 >= first && o + 3 < last) xo[o + 3] = v.w;
+        }
+      }
+    } else {
+      for (int o = first + tid; o < last; o += ST_THREADS) xo[o] = s_out[o - c0];
+    }
+    if (tid == 0) s_heavy_n = 0;
+    __syncthreads();
+  }
+  // tile sum of the chosen states (state estimate after resampling, merged by the next observation's k_st_step)
+  double v = warp_sum_d((double)sumx);
+  if (lane == 0) s_bs[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = warp_sum_d(lane < ST_NW ? s_bs[lane] : 0.0);
+    if (lane == 0) P.bsum[(size_t)c * P.nt + tile] = t;
+  }
+  }  // tiles
+}
+
+// ---- flush: the state estimate of a final resampling (or of the initial particles when T = 0) ----
+static __global__ void __launch_bounds__(ST_THREADS) k_st_flush(StreamParams P, int obs /* = T */, int TS) {
+  __shared__ double s_red[ST_NW];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!f.alive[c]) return;
+  const int pp = (obs + 1) & 1;
+  const int rprev = P.res[pp * f.C + c];
+  const StSeg& sp = P.seg[pp * f.C + c];
+  const int nloc = rprev ? sp.nnloc : sp.nloc;
+  const int lead = (int)((rprev ? sp.ngoff : sp.goff) & 3);
+  const int ntc = max(1, (nloc + lead + TS - 1) / TS);
+  const int chunk = (ntc + ST_THREADS - 1) / ST_THREADS;
+  double lp = 0.0;
+  if (rprev) for (int j = tid * chunk; j < min(ntc, (tid + 1) * chunk); j++) lp += P.bsum[(size_t)c * P.nt + j];
+  lp = warp_sum_d(lp);
+  if (lane == 0) s_red[wid] = lp;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < ST_NW; w++) t += s_red[w];
+    const int n = P.n_glob ? P.n_glob : filt_n(f, c);
+    if (P.sharded) { StRec r; r.m = 0; r.s = 0; r.q = 0; r.sx = 0; r.pend = t; r.nan = rprev ? 1.0 : 0.0; r.pad0 = r.pad1 = 0; P.rec_local[c] = r; }
+    else if (rprev) {
+      if (obs == 0) f.ess[(size_t)c * (f.T + 1)] = (double)n;
+      f.state_est[(size_t)c * (f.T + 1) + obs] = t / (double)n;
+    }
+  }
+}
+static __global__ void k_st_flush_merge(StreamParams P, int obs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const FilterDev& f = P.f;
+  if (c >= f.C || !f.alive[c]) return;
+  if (!P.res[((obs + 1) & 1) * f.C + c]) return;
+  double t = 0.0;
+  for (int g = 0; g < P.world; g++) t += P.rec_all[(size_t)g * f.C + c].pend;
+  if (obs == 0) f.ess[(size_t)c * (f.T + 1)] = (double)P.n_glob;
+  f.state_est[(size_t)c * (f.T + 1) + obs] = t / (double)P.n_glob;
+}
+
+}  // namespace bssm

@@ -166,7 +166,7 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world):
     init = np.tile(np.array(THETA), (count, 1))
     chol = np.tile(np.diag([0.05, 0.05, 0.05]), (count, 1, 1))
     prec = nat.F32 if args.precision == "f32" else nat.F64
-    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT}[args.engine]
+    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT, "stream": nat.ENGINE_STREAM}[args.engine]
 
     def run(iters, seed):
         return run_chains(ctx, m, nat.BPF, y, init, pri, [nat.TR_LOGIT, nat.TR_LOG, nat.TR_LOG], default_tune_control(),
@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--resample-fn", dest="resample_fn", default="stratified", choices=["stratified", "systematic", "multinomial"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "general", "persistent"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "general", "persistent", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="filter", choices=["filter", "pmmh"],
                     help="filter: BASELINE configs[1] (default); pmmh: configs[4], 1024 chains x N=65536 x T=1000 chain-sharded")
@@ -265,7 +265,7 @@ def main():
     y = simulate_y(T)
     fn = nat.RESAMPLE_FNS[args.resample_fn]
     prec = nat.F32 if args.precision == "f32" else nat.F64
-    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT}[args.engine]
+    engine = {"auto": nat.ENGINE_AUTO, "general": nat.ENGINE_GENERAL, "persistent": nat.ENGINE_PERSISTENT, "stream": nat.ENGINE_STREAM}[args.engine]
 
     # device-resident inputs (torch owns the memory; the engine gets raw pointers)
     d_y = torch.tensor(y, dtype=torch.float64, device="cuda")

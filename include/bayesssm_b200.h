@@ -35,13 +35,15 @@ extern "C" {
 #define BSSM_ERR_NVRTC 7
 #define BSSM_ERR_UNSUPPORTED 8
 #define BSSM_ERR_NO_DEVICE 9
+#define BSSM_ERR_CAPACITY 10       /* particle-sharded filter: one rank's share of the offspring outgrew its storage */
+#define BSSM_ERR_NCCL 11
 
 /* ---- enums (R match.arg strings -> ints) ---- */
 enum { BSSM_BPF = 0, BSSM_APF = 1, BSSM_RMPF = 2 };            /* pf_wrapper identity */
 enum { BSSM_SIS = 0, BSSM_SISR = 1, BSSM_SISAR = 2 };          /* resample_algorithm  */
 enum { BSSM_STRATIFIED = 0, BSSM_SYSTEMATIC = 1, BSSM_MULTINOMIAL = 2 }; /* resample_fn */
-enum { BSSM_F32 = 0, BSSM_F64 = 1 };
-enum { BSSM_ENGINE_AUTO = 0, BSSM_ENGINE_GENERAL = 1, BSSM_ENGINE_PERSISTENT = 2 };                           /* state / weight precision (cdf is always f64) */
+enum { BSSM_F32 = 0, BSSM_F64 = 1 };                          /* state / weight precision (cdf is always f64) */
+enum { BSSM_ENGINE_AUTO = 0, BSSM_ENGINE_GENERAL = 1, BSSM_ENGINE_PERSISTENT = 2, BSSM_ENGINE_STREAM = 3 };
 enum {
   BSSM_MODEL_AR_SIN = 0,   /* README.md:137-146                       theta = (phi, sigma_x, sigma_y) */
   BSSM_MODEL_LG = 1,       /* tests/testthat/test-pmmh_tuning.R:163   theta = (phi, sigma_x, sigma_y) */
@@ -135,7 +137,7 @@ typedef struct {
   int return_particles;   /* fill particles_history / weights_history */
   int exact_resampling;   /* 1: cdf bit-exact vs the sequential reference cumsum; 0: plain parallel fp64 scan;
                              -1 => auto (1 for BSSM_F64, 0 for BSSM_F32) */
-  int engine;             /* BSSM_ENGINE_AUTO / GENERAL / PERSISTENT */
+  int engine;             /* BSSM_ENGINE_AUTO / GENERAL / PERSISTENT / STREAM */
 } bssm_filter_config;
 
 typedef struct {
@@ -166,6 +168,33 @@ int bssm_filter_run(bssm_ctx *ctx, const bssm_filter_config *cfg, const double *
  * and by the PMMH driver. */
 int bssm_filter_run_device(bssm_ctx *ctx, const bssm_filter_config *cfg, const double *d_y,
                            const double *d_theta, double *d_loglike, float *kernel_ms);
+
+/* ------------------------------------------------------------------------- *
+ * Particle-sharded single filter (one filter too large for one GPU, N >= 2^28):
+ * the counterpart of running .particle_filter_core (R/particle_filter_core.R:19-267)
+ * on one huge particle set.  One process per GPU; rank g keeps a contiguous block
+ * of the particles.  Per observation the ranks all-gather one 64-byte record
+ * (ncclAllGather over NVLink); the log-normaliser, ESS and resampling decision are
+ * derived identically on every rank, the exclusive prefix of the per-rank weight
+ * totals gives each rank its cdf offset, and each rank resamples the offspring of
+ * its own particles -- no particle crosses NVLink.  Philox streams are keyed by the
+ * global particle index: the result equals the one-GPU result up to the summation
+ * order of the normaliser.
+ *   bssm_shard_unique_id   rank 0: a 128-byte NCCL unique id, to be sent to the other ranks
+ *   bssm_shard_init        every rank: join the group (world == 1 needs no id and no NCCL)
+ *   bssm_filter_run_sharded  collective; cfg->num_particles is the GLOBAL count, cfg->num_filters
+ *                          must be 1, BPF + stratified / systematic, built-in 1-D models.
+ *                          capacity_factor (>= 1, default 1.5): storage per rank as a multiple of
+ *                          N / world; BSSM_ERR_CAPACITY in status if a rank's share outgrows it.
+ * nccl_lib_path: path of libnccl.so.2 (NULL: $BSSM_NCCL_LIB, then the loader's search path).
+ * ------------------------------------------------------------------------- */
+int bssm_shard_unique_id(const char *nccl_lib_path, void *id_out_128);
+int bssm_shard_init(bssm_ctx *ctx, const char *nccl_lib_path, int rank, int world, const void *id_128);
+int bssm_shard_finalize(bssm_ctx *ctx);
+/* initial block partition (boundaries at multiples of 4): rank's slice [goff, goff + nloc) */
+int bssm_shard_partition(int n, int world, int rank, int64_t *goff_out, int *nloc_out);
+int bssm_filter_run_sharded(bssm_ctx *ctx, const bssm_filter_config *cfg, const double *y, const double *theta,
+                            double capacity_factor, bssm_filter_result *res, int *n_local_final);
 
 /* ------------------------------------------------------------------------- *
  * NVRTC models: CUDA device-function snippets instead of R closures

@@ -1,0 +1,153 @@
+"""The streaming bootstrap-filter engine (bssm_stream.cuh: particles in HBM, two kernels per observation)
+against the oracle and the other engines.  Same Philox streams on every side, so in f64 it reproduces the
+oracle's Philox-mode filter up to summation order; in f32 (throughput precision) it is checked
+statistically (Kalman) and against the general engine."""
+import numpy as np
+import pytest
+
+import engine_helpers as eh
+from bayesssm_b200 import _native as nat
+from test_filter_gpu import THETA, sim_y
+
+pytestmark = pytest.mark.gpu
+AR, LG, RWD, ARCOS = 0, 1, 2, 4
+ST = nat.ENGINE_STREAM
+
+
+# sizes around the tile boundaries (f64 tile = 1024 particles): one partial tile, exact tiles, ragged tails
+@pytest.mark.parametrize("N,T", [(1, 5), (3, 6), (1000, 30), (1024, 10), (1025, 10), (4096, 40), (70001, 12), (1 << 17, 6)])
+@pytest.mark.parametrize("rfn", [0, 1])
+def test_f64_matches_oracle_philox(orc, engine, N, T, rfn):
+    rng = np.random.default_rng(N + rfn)
+    y = sim_y(AR, T, rng)
+    ref = orc.particle_filter(AR, 0, 2, rfn, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    got = eh.filter_run(engine, AR, 0, 2, rfn, N, y, THETA[AR], seed=1405, run_id=2, stream_base=3,
+                        precision=nat.F64, engine=ST)
+    assert got["status"][0] == 0
+    assert got["n_resampled"][0] == ref["n_resampled"]
+    # north-star tolerance 1e-6 relative
+    assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+    np.testing.assert_allclose(got["loglike_history"][0], ref["loglike_history"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-6)
+    np.testing.assert_allclose(got["state_est"][0][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("ralg", [0, 1, 2])
+def test_resample_algorithms_and_models(orc, engine, ralg):
+    rng = np.random.default_rng(5)
+    for model in (LG, RWD, ARCOS):
+        y = sim_y(AR if model == ARCOS else model, 20, rng)
+        th = THETA[AR] if model == ARCOS else THETA[model]
+        ref = orc.particle_filter(model, 0, ralg, 0, 3000, y, th, seed=9, stream=1)
+        got = eh.filter_run(engine, model, 0, ralg, 0, 3000, y, th, seed=9, stream_base=1, precision=nat.F64, engine=ST)
+        assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+        np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-6)
+        np.testing.assert_allclose(got["state_est"][0][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+
+
+def test_threshold_obs_times_and_early_exit(orc, engine):
+    rng = np.random.default_rng(6)
+    y = sim_y(AR, 6, rng)
+    ot = [1, 2, 4, 7, 8, 12]
+    ref = orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3, threshold=1500.0)
+    got = eh.filter_run(engine, AR, 0, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3, threshold=1500.0,
+                        precision=nat.F64, engine=ST)
+    assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+    assert got["n_resampled"][0] == ref["n_resampled"]
+    y2 = np.array([0.1, 1e6, 0.2])
+    th = [0.8, 1.0, 1e-3]
+    ref = orc.particle_filter(AR, 0, 2, 0, 512, y2, th, seed=3)
+    got = eh.filter_run(engine, AR, 0, 2, 0, 512, y2, th, seed=3, precision=nat.F64, engine=ST)
+    assert ref["early_exit"] == 1 and got["early_exit"][0] == 1 and got["loglike"][0] == -np.inf
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-6)
+    # T = 0: only the initial state estimate
+    got = eh.filter_run(engine, AR, 0, 2, 0, 777, np.zeros((0, 1)), THETA[AR], seed=3, precision=nat.F64, engine=ST)
+    ref = orc.particle_filter(AR, 0, 2, 0, 777, np.zeros(0), THETA[AR], seed=3)
+    assert got["ess"][0][0] == 777 and abs(got["state_est"][0][0, 0] - ref["state_est"][0, 0]) < 1e-12
+
+
+def test_degenerate_weights_one_particle_takes_everything(orc, engine):
+    # a very sharp likelihood: a handful of particles own all offspring (heavy-source path, many output chunks
+    # from one tile, empty tiles elsewhere)
+    rng = np.random.default_rng(11)
+    y = sim_y(AR, 5, rng)
+    th = [0.8, 1.0, 2e-4]
+    for prec, tol in ((nat.F64, 1e-6), (nat.F32, None)):
+        ref = orc.particle_filter(AR, 0, 1, 0, 50000, y, th, seed=13)
+        got = eh.filter_run(engine, AR, 0, 1, 0, 50000, y, th, seed=13, precision=prec, engine=ST)
+        assert got["status"][0] == 0 and got["early_exit"][0] == ref["early_exit"]
+        if tol:
+            assert abs(got["loglike"][0] - ref["loglike"]) <= tol * abs(ref["loglike"])
+            np.testing.assert_allclose(got["state_est"][0][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+        else:
+            assert abs(got["loglike"][0] - ref["loglike"]) <= 0.1   # f32 at sigma_y = 2e-4: weights themselves carry ~1e-3 errors
+            np.testing.assert_allclose(got["state_est"][0][:, 0], ref["state_est"][:, 0], atol=2e-3)
+
+
+def test_batched_f32_against_kalman(orc, engine):
+    # config C3 shape (reduced): linear-Gaussian, replicate filters, SISR; estimate within 3 MC standard errors
+    rng = np.random.default_rng(7)
+    y = sim_y(LG, 200, rng)
+    exact = orc.kalman_loglik(y, 0.8, 1.0, 1.0)
+    got = eh.filter_run(engine, LG, 0, 1, 0, 1 << 14, y, THETA[LG], seed=11, num_filters=64, precision=nat.F32, engine=ST)
+    assert (got["status"] == 0).all()
+    lls = got["loglike"]
+    est = np.log(np.mean(np.exp(lls - lls.max()))) + lls.max()
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(est - exact) < 3 * se + 0.01, (est, exact, se)
+    assert len(np.unique(lls)) == 64
+
+
+def test_batched_filters_match_oracle_per_stream(orc, engine):
+    rng = np.random.default_rng(12)
+    y = sim_y(AR, 8, rng)
+    C = 300
+    got = eh.filter_run(engine, AR, 0, 2, 0, 2500, y, THETA[AR], seed=31, num_filters=C, precision=nat.F64, engine=ST)
+    assert (got["status"] == 0).all() and np.isfinite(got["loglike"]).all()
+    for c in (0, 1, 147, 299):
+        ref = orc.particle_filter(AR, 0, 2, 0, 2500, y, THETA[AR], seed=31, stream=c)
+        assert abs(got["loglike"][c] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+        np.testing.assert_allclose(got["state_est"][c][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+
+
+def test_f32_close_to_general_and_f64_identical_at_2pow20(engine):
+    # BASELINE config C2 geometry, short T
+    rng = np.random.default_rng(9)
+    y = sim_y(AR, 20, rng)
+    a = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=ST)
+    b = eh.filter_run(engine, AR, 0, 2, 1, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=ST)
+    g = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=nat.ENGINE_GENERAL)
+    assert abs(a["loglike"][0] - g["loglike"][0]) < 0.1 and abs(b["loglike"][0] - g["loglike"][0]) < 0.1
+    np.testing.assert_allclose(a["state_est"][0], g["state_est"][0], atol=0.02)
+    s64 = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F64, engine=ST)
+    g64 = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F64, engine=nat.ENGINE_GENERAL)
+    assert abs(s64["loglike"][0] - g64["loglike"][0]) <= 1e-9 * abs(g64["loglike"][0])
+    np.testing.assert_allclose(s64["ess"][0], g64["ess"][0], rtol=1e-9)
+    np.testing.assert_allclose(s64["state_est"][0], g64["state_est"][0], rtol=1e-9, atol=1e-9)
+
+
+def test_larger_than_the_persistent_kernel_holds(engine):
+    # N = 2^23 exceeds the register-resident kernel (<= 256 x 7168); AUTO must pick the streaming engine
+    rng = np.random.default_rng(10)
+    y = sim_y(AR, 6, rng)
+    n0 = engine.launch_count()
+    a = eh.filter_run(engine, AR, 0, 2, 0, 1 << 23, y, THETA[AR], seed=5, precision=nat.F32, engine=nat.ENGINE_AUTO)
+    assert engine.launch_count() - n0 < 40          # 2 kernels per observation, not the general engine's ~10
+    s = eh.filter_run(engine, AR, 0, 2, 0, 1 << 20, y, THETA[AR], seed=5, precision=nat.F32, engine=ST)
+    assert a["status"][0] == 0 and abs(a["loglike"][0] - s["loglike"][0]) < 0.05
+
+
+def test_pmmh_on_streaming_engine_matches_oracle(orc, engine):
+    from test_pmmh_gpu import PRIOR, readme_data
+    rng = np.random.default_rng(1405)
+    y = readme_data(12, rng)
+    inits = np.array([[0.8, 1.0, 0.5], [0.5, 0.7, 1.2]])
+    kw = dict(transform=[2, 1, 1], pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=30, pilot_reps=6, m=40, seed=99)
+    got = eh.pmmh_run(engine, 0, 0, y, inits, chain_id_base=4, engine=ST, **PRIOR, **kw)
+    assert (got["status"] == 0).all()
+    for c in range(2):
+        ref = orc.pmmh_chain(0, 0, y, inits[c], chain_id=4 + c, **PRIOR, **kw)
+        assert got["target_n"][c] == ref["target_n"]
+        np.testing.assert_allclose(got["pilot_theta_chain"][c], ref["pilot_theta_chain"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["theta_chain"][c], ref["theta_chain"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got["loglike_chain"][c], ref["loglike_chain"], rtol=1e-6)
