@@ -35,12 +35,37 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   P.nt = (cap + 4 + TS - 1) / TS;
   P.xstride = (size_t)P.nt * TS;
   const size_t rs = sizeof(Real);
+  // blocks per filter: the resident block slots of the chip split over the filters, each block walking a
+  // contiguous range of tiles; among a few candidates take the one with the fewest rounds (waves x tiles
+  // per block).  The three kernels share the block -> tile ranges, so the scarcer kernel sets the slots.
+  {
+    int ps = 1, pr = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)k_st_step<Model, Real, PPT>, ST_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr, (const void*)k_st_resample<Model, Real, PPT>, ST_THREADS, 0);
+    int per_sm = ps < pr ? ps : pr;
+    if (per_sm < 1) per_sm = 1;
+    const long long slots = (long long)per_sm * ctx->prop.multiProcessorCount;
+    long long b0 = (slots + C - 1) / C;
+    const long long bmin = (P.nt + ST_MAX_TPB - 1) / ST_MAX_TPB;   // at most ST_MAX_TPB tiles per block
+    if (b0 < bmin) b0 = bmin;
+    if (b0 > P.nt) b0 = P.nt;
+    long long best = b0, best_cost = -1;
+    for (long long b = b0; b <= P.nt && b <= 4 * b0 + 3; b++) {
+      const long long waves = ((long long)C * b + slots - 1) / slots;
+      const long long cost = waves * ((P.nt + b - 1) / b) * 16 + waves;   // + a little per wave for the block prologue
+      if (best_cost < 0 || cost < best_cost) { best = b; best_cost = cost; }
+    }
+    if (const char* e = getenv("BSSM_ST_BPC")) { int v = atoi(e); if (v >= bmin && v <= P.nt) best = v; }
+    P.bpc = (int)best;
+  }
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 0, (size_t)C * P.xstride * rs, &P.x0));
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 1, (size_t)C * P.xstride * rs, &P.x1));
-  BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.nt * 4, &P.part_m));
-  P.part_s = P.part_m + (size_t)C * P.nt; P.part_q = P.part_s + (size_t)C * P.nt; P.part_x = P.part_q + (size_t)C * P.nt;
-  BSSM_TRY(scratch(ctx, SL_ST_BASE + 3, (size_t)C * (P.nt + 1), &P.pref));
-  BSSM_TRY(scratch(ctx, SL_ST_BASE + 4, (size_t)C * P.nt, &P.bsum));
+  BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.nt * 2, &P.tile_m));
+  P.tile_s = P.tile_m + (size_t)C * P.nt;
+  BSSM_TRY(scratch(ctx, SL_ST_BASE + 3, (size_t)C * (P.bpc + 1), &P.pref));
+  BSSM_TRY(scratch(ctx, SL_ST_BASE + 4, (size_t)C * P.bpc, &P.bsum));
+  BSSM_TRY(scratch(ctx, SL_ST_BASE + 10, (size_t)C * P.bpc * 4, &P.blk_m));
+  P.blk_s = P.blk_m + (size_t)C * P.bpc; P.blk_q = P.blk_s + (size_t)C * P.bpc; P.blk_x = P.blk_q + (size_t)C * P.bpc;
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 5, (size_t)C, &P.counter));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 6, (size_t)2 * C, &P.res));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 7, (size_t)2 * C, &P.seg));
@@ -53,32 +78,11 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 11, (size_t)8, &P.dbg));
     BSSM_CK(cudaMemsetAsync(P.dbg, 0, 8 * sizeof(long long), st));
   }
-  if ((long long)P.nt * C > 2147483647LL) { set_error("streaming engine: too many tiles (%d filters x %d)", C, P.nt); return BSSM_ERR_UNSUPPORTED; }
+  if ((long long)P.bpc * C > 2147483647LL) { set_error("streaming engine: too many blocks (%d filters x %d)", C, P.bpc); return BSSM_ERR_UNSUPPORTED; }
   k_st_setup<<<(C + 127) / 128, 128, 0, st>>>(P, goff0, nloc0);
   BSSM_LAUNCH(ctx, "k_st_setup");
-  // blocks per filter: the resident block slots of the chip split over the filters, each block walking
-  // several tiles; among a few candidates take the one with the fewest rounds (waves x tiles per block)
-  auto pick_bpc = [&](const void* kern, const char* env) -> int {
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ST_THREADS, 0);
-    if (per_sm < 1) per_sm = 1;
-    long long slots = (long long)per_sm * ctx->prop.multiProcessorCount;
-    if (const char* e = getenv(env)) { int v = atoi(e); if (v >= 1) return v > P.nt ? P.nt : v; }
-    long long b0 = (slots + C - 1) / C;
-    if (b0 > P.nt) b0 = P.nt;
-    long long best = b0, best_cost = -1;
-    for (long long b = b0; b <= P.nt && b <= 4 * b0 + 3; b++) {
-      const long long waves = ((long long)C * b + slots - 1) / slots;
-      const long long cost = waves * ((P.nt + b - 1) / b) * 16 + waves;   // + a little per wave for the block prologue
-      if (best_cost < 0 || cost < best_cost) { best = b; best_cost = cost; }
-    }
-    return (int)best;
-  };
-  P.bpc = pick_bpc((const void*)k_st_step<Model, Real, PPT>, "BSSM_ST_BPC");
-  P.bpc_r = pick_bpc((const void*)k_st_resample<Model, Real, PPT>, "BSSM_ST_BPC_R");
-  const dim3 grid_init((unsigned int)((size_t)P.nt * C));   // tile index fastest
-  const dim3 grid((unsigned int)((size_t)P.bpc * C)), grid_r((unsigned int)((size_t)P.bpc_r * C));
-  k_st_init<Model, Real, PPT><<<grid_init, ST_THREADS, 0, st>>>(P);
+  const dim3 grid((unsigned int)((size_t)P.bpc * C));   // block index within the filter fastest
+  k_st_init<Model, Real, PPT><<<grid, ST_THREADS, 0, st>>>(P);
   BSSM_LAUNCH(ctx, "k_st_init");
   const bool may_resample = f.ralg != BSSM_SIS;
   for (int obs = 0; obs < L.T; obs++) {
@@ -90,7 +94,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      k_st_resample<Model, Real, PPT><<<grid_r, ST_THREADS, 0, st>>>(P, obs);
+      k_st_resample<Model, Real, PPT><<<grid, ST_THREADS, 0, st>>>(P, obs);
       BSSM_LAUNCH(ctx, "k_st_resample");
     }
   }
@@ -99,9 +103,9 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_CK(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     BSSM_CK(cudaStreamSynchronize(st));
     fprintf(stderr, "[bssm stream timing] last k_st_step, merging block: %lld cycles until its ticket, merge %lld (max pass %lld, block max %lld, sum pass %lld, prefix pass + rest %lld), global bookkeeping %lld; bpc=%d bpc_r=%d nt=%d\n",
-            h[0], h[1], h[4], h[5], h[6], h[7], h[2], P.bpc, P.bpc_r, P.nt);
+            h[0], h[1], h[4], h[5], h[6], h[7], h[2], P.bpc, P.bpc, P.nt);
   }
-  k_st_flush<<<C, ST_THREADS, 0, st>>>(P, L.T, TS);
+  k_st_flush<TS><<<C, ST_THREADS, 0, st>>>(P, L.T);
   BSSM_LAUNCH(ctx, "k_st_flush");
   if (sh) {
     BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));

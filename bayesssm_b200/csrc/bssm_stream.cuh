@@ -5,12 +5,13 @@
 // Replaces the per-observation loop of .particle_filter_core (R/particle_filter_core.R:123-246)
 // for algorithm "BPF" and the resamplers of src/resampling.cpp:16-66 (stratified / systematic).
 //
-//   k_st_step      read x, propagate (one Philox call per 4 particles), log-weight, tile partials
-//                  (max, sum e, sum e^2, sum e*x), write x.  The LAST tile of a filter to finish
-//                  (ticket counter) merges the partials in fixed order: global max / sum / ESS /
-//                  log-likelihood / resampling decision, and the exclusive prefix of the tile sums
-//                  -- the scan offsets of the next kernel.  No separate finalise launch, no atomics
-//                  on floating-point data, deterministic.                        [8 B / particle]
+//   k_st_step      read x, propagate (one Philox call per 4 particles), log-weight, write x.  A block
+//                  walks a contiguous range of tiles and keeps (max, sum e, sum e^2, sum e*x) per
+//                  tile and per block.  The LAST block of a filter to finish (ticket counter) merges
+//                  the BLOCK records in fixed order: global max / sum / ESS / log-likelihood /
+//                  resampling decision, and the exclusive prefix of the block sums -- the scan
+//                  offsets of the next kernel.  No separate finalise launch, no atomics on
+//                  floating-point data, deterministic.                           [8 B / particle]
 //   k_st_resample  (steps where resampling fires) read x, recompute the weight, tile-local scan;
 //                  INPUT-centric closed-form offspring ranges: a source with cdf value c owns the
 //                  output slots [F(c_prev), F(c)), F(c) = #{ i : (i + U_i)/n <= c } -- no search,
@@ -41,6 +42,7 @@ constexpr int ST_SLACK = 512;       // staging capacity beyond the tile size
 constexpr int ST_HEAVY = 64;        // offspring count above which a source is expanded cooperatively
 constexpr int ST_HEAVY_CAP = 32;
 constexpr int ST_ERR_CAPACITY = 10; // status: a shard outgrew its storage (BSSM_ERR_CAPACITY)
+constexpr int ST_MAX_TPB = 256;     // tiles per block (k_st_resample keeps their prefix in shared memory)
 
 
 // layout / cdf descriptor of one filter on this rank, written once per observation
@@ -50,6 +52,7 @@ struct StSeg {
   int last, pad;           // 1: this rank holds the tail of the filter
   double abase, aend;      // cdf numerator (relative to the global max) before / after this rank's particles
   double gscale;           // exp(local max - global max)
+  double mloc;             // local max (reference of the block prefixes of this rank)
 };
 
 struct StRec { double m, s, q, sx, pend, nan, pad0, pad1; };   // per-rank record (sharded runs)
@@ -60,9 +63,10 @@ struct StreamParams {
   int nt;                  // tiles per filter row (capacity)
   size_t xstride;          // elements per filter row of x0 / x1 (= nt * tile size)
   void *x0, *x1;           // x0: resampled (or initial) particles; x1: propagated particles
-  double *part_m, *part_s, *part_q, *part_x;   // [C][nt] tile partials (max; sum e, sum e^2, sum e*x relative to it)
-  double* pref;            // [C][nt + 1] exclusive prefix of the tile sums, relative to the local max
-  double* bsum;            // [C][nt] sum of the states written by a tile (state estimate after resampling)
+  double *tile_m, *tile_s; // [C][nt] tile max and sum e relative to it (within-block prefixes of k_st_resample)
+  double *blk_m, *blk_s, *blk_q, *blk_x;   // [C][bpc] block records (max; sum e, sum e^2, sum e*x relative to it)
+  double* pref;            // [C][bpc + 1] exclusive prefix of the block sums, relative to the local max
+  double* bsum;            // [C][bpc] sum of the states written by a block (state estimate after resampling)
   unsigned int* counter;   // [C] tickets
   int* res;                // [2][C] resampling decision of an observation, by parity
   StSeg* seg;              // [2][C] by parity
@@ -71,7 +75,7 @@ struct StreamParams {
   StRec* rec_local;        // [C] this rank's record
   StRec* rec_all;          // [world][C] gathered records
   int cap;                 // storage capacity (particles) of a row
-  int bpc, bpc_r;          // blocks per filter of k_st_step / k_st_resample
+  int bpc;                 // blocks per filter (k_st_init, k_st_step and k_st_resample share the block -> tile ranges)
   double log_n;            // log(particle count) when every filter has the same count (else NaN: computed on the device)
   long long* dbg;          // optional [8] clock64 stamps of the merging block (BSSM_ST_TIMING, diagnostics)
 };
@@ -100,19 +104,26 @@ template <typename Real, int PPT> struct StVec {
   }
 };
 
-// layout an observation's kernels work on: the previous observation's descriptor, after its resampling if it fired
-struct StLayout { long long goff; int nloc, lead, ntc; };
+// layout an observation's kernels work on, and the split of its tiles over the blocks of a filter:
+// block j owns the contiguous tiles [j * tpb, min(ntc, (j + 1) * tpb)), nb blocks are active
+struct StLayout { long long goff; int nloc, lead, ntc, tpb, nb; };
+template <int TS>
+__device__ __forceinline__ StLayout st_make_layout(long long goff, int nloc, int bpc) {
+  StLayout L;
+  L.goff = goff; L.nloc = nloc;
+  L.lead = (int)(goff & 3);
+  L.ntc = max(1, (nloc + L.lead + TS - 1) / TS);
+  L.tpb = (L.ntc + bpc - 1) / bpc;
+  L.nb = (L.ntc + L.tpb - 1) / L.tpb;
+  return L;
+}
+// the previous observation's descriptor, after its resampling if it fired
 template <int TS>
 __device__ __forceinline__ StLayout st_layout_in(const StreamParams& P, int c, int obs) {
   const int pp = (obs + 1) & 1;
   const StSeg& sp = P.seg[pp * P.f.C + c];
   const int rprev = P.res[pp * P.f.C + c];
-  StLayout L;
-  L.goff = rprev ? sp.ngoff : sp.goff;
-  L.nloc = rprev ? sp.nnloc : sp.nloc;
-  L.lead = (int)(L.goff & 3);
-  L.ntc = max(1, (L.nloc + L.lead + TS - 1) / TS);
-  return L;
+  return st_make_layout<TS>(rprev ? sp.ngoff : sp.goff, rprev ? sp.nnloc : sp.nloc, P.bpc);
 }
 
 // ---- global part of the per-observation bookkeeping (R/particle_filter_core.R:189-224) ----
@@ -155,7 +166,7 @@ static __device__ __noinline__ void st_global(const StreamParams& P, int c, int 
   if (roles & ST_DECIDE) {
     StSeg sg;
     sg.goff = goff; sg.nloc = nloc; sg.ngoff = goff; sg.nnloc = nloc; sg.last = (rank == world - 1); sg.pad = 0;
-    sg.abase = abase; sg.aend = aend; sg.gscale = gscale;
+    sg.abase = abase; sg.aend = aend; sg.gscale = gscale; sg.mloc = recs[(size_t)rank * rstride].m;
     if (bad) { f.status[c] = 3; f.alive[c] = 0; }                  // NaN weight somewhere: R's `if (NA)` error
     else if (empty) { f.early_exit[c] = 1; f.alive[c] = 0; }       // all(lw < -1e8): R/particle_filter_core.R:189-202
     else if (resample) {
@@ -203,28 +214,30 @@ static __device__ __noinline__ void st_global(const StreamParams& P, int c, int 
   }
 }
 
-// ---- local merge of the tile partials by the last block of a filter (all threads of the block) ----
-// Produces this rank's record and the exclusive prefix of the tile sums (relative to the local max).
-// One SM does this while the others idle, so it is built for that SM's memory pipeline: the partials
-// are SoA arrays, warp w owns the contiguous tiles [w * seg, (w + 1) * seg) and walks them 32 at a time
-// (lane = tile: fully coalesced 256-byte requests), rounds are independent apart from a one-add carry.
-// Plain loads: the partials were published with fence + ticket and are read after ticket + fence, and no
-// line of them was in this SM's L1 before (strong .cg loads would serialise behind the prefix stores).
-// Fixed structure => deterministic.
+// ---- local merge of the block records by the last block of a filter (all threads of the block) ----
+// Produces this rank's record and the exclusive prefix of the block sums (relative to the local max).
+// One SM does this while the others idle, so there is little of it (one record per BLOCK, not per tile:
+// at most a few rounds) and it is laid out for that SM's memory pipeline: SoA arrays, lane = record
+// (coalesced), every load of a round issued before the first use.  Fixed structure => deterministic.
+// Plain loads: the records were published with fence + ticket and are read after ticket + fence, and no
+// line of them was in this SM's L1 before.
 template <typename Real>
-static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int c, int ntc, bool with_pending, double* s_red /*[4][ST_NW]*/, StRec& out) {
+static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int c, int nb, int nb_pending, double* s_red /*[4][ST_NW]*/, StRec& out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
-  const size_t row = (size_t)c * P.nt;
-  const double* __restrict__ pm = P.part_m + row;
-  const double* __restrict__ ps = P.part_s + row;
-  const double* __restrict__ pq = P.part_q + row;
-  const double* __restrict__ px = P.part_x + row;
+  const size_t row = (size_t)c * P.bpc;
+  const double* __restrict__ pm = P.blk_m + row;
+  const double* __restrict__ ps = P.blk_s + row;
+  const double* __restrict__ pq = P.blk_q + row;
+  const double* __restrict__ px = P.blk_x + row;
   const double* __restrict__ bsum = P.bsum + row;
-  double* __restrict__ pref = P.pref + (size_t)c * (P.nt + 1);
-  const int seg = ((ntc + ST_NW - 1) / ST_NW + 31) & ~31;      // tiles per warp, multiple of 32
-  const int j0 = min(ntc, wid * seg), j1 = min(ntc, j0 + seg);
+  double* __restrict__ pref = P.pref + (size_t)c * (P.bpc + 1);
+  const int seg = ((nb + ST_NW - 1) / ST_NW + 31) & ~31;      // records per warp, multiple of 32
+  const int j0 = min(nb, wid * seg), j1 = min(nb, j0 + seg);
   if (P.dbg && tid == 0) P.dbg[4] = clock64();
+  // pending state sum of the previous resampling (or of the initial particles): its own record count
+  double lp = 0.0;
+  for (int j = tid; j < nb_pending; j += ST_THREADS) lp += bsum[j];
   double m = NINF;
 #pragma unroll 4
   for (int j = j0 + lane; j < j1; j += 32) { const double mj = pm[j]; m = mj > m ? mj : m; }   // NaN maxima are caught through s
@@ -234,18 +247,17 @@ static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int
   m = warp_max_d(lane < ST_NW ? s_red[lane] : NINF);
   __syncthreads();
   if (P.dbg && tid == 0) P.dbg[5] = clock64();
-  double lq = 0.0, lx = 0.0, lp = 0.0, carry = 0.0;
+  double lq = 0.0, lx = 0.0, carry = 0.0;
 #pragma unroll 2
   for (int jb = j0; jb < j1; jb += 32) {
     const int j = jb + lane;
     const bool on = j < j1;
     const double mj = on ? pm[j] : NINF, sj = on ? ps[j] : 0.0;
     const double qj = on ? pq[j] : 0.0, xj = on ? px[j] : 0.0;
-    const double bj = (on && with_pending) ? bsum[j] : 0.0;
     double sc = 0.0;
-    if (!(mj == NINF || m == NINF)) sc = (double)Math<Real>::exp_((Real)(mj - m));   // throughput precision: SFU exp, not an fp64 chain
+    if (!(mj == NINF || m == NINF)) sc = (double)Math<Real>::exp_((Real)(mj - m));   // throughput precision: SFU exp
     const double v = sj * sc;
-    lq += qj * sc * sc; lx += xj * sc; lp += bj;
+    lq += qj * sc * sc; lx += xj * sc;
     const double inc = warp_incl_scan_d(v, lane);
     if (on) pref[j] = carry + (inc - v);            // exclusive prefix relative to this warp's segment
     carry += __shfl_sync(0xffffffffu, inc, 31);
@@ -265,7 +277,7 @@ static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int
 #pragma unroll 4
     for (int j = j0 + lane; j < j1; j += 32) pref[j] += woff;     // own values: the same thread wrote them
   }
-  if (tid == 0) pref[ntc] = S;
+  if (tid == 0) pref[nb] = S;
   out.m = m; out.s = S; out.q = Q; out.sx = SX; out.pend = PD; out.nan = (S != S) ? 1.0 : 0.0; out.pad0 = 0; out.pad1 = 0;
   __syncthreads();
 }
@@ -278,52 +290,54 @@ static __global__ void k_st_setup(StreamParams P, long long goff0, int nloc0) {
   StSeg sg;
   sg.goff = sg.ngoff = P.sharded ? goff0 : 0;
   sg.nloc = sg.nnloc = P.sharded ? nloc0 : n;
-  sg.last = P.rank == P.world - 1; sg.pad = 0; sg.abase = 0; sg.aend = 0; sg.gscale = 1;
+  sg.last = P.rank == P.world - 1; sg.pad = 0; sg.abase = 0; sg.aend = 0; sg.gscale = 1; sg.mloc = 0;
   P.seg[1 * P.f.C + c] = sg; P.seg[c] = sg;
   P.res[1 * P.f.C + c] = 1; P.res[c] = 0;
   P.counter[c] = 0u;
 }
 
-// ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, tile sums for the t = 0 state estimate ----
+// ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, block sums for the t = 0 state estimate ----
 template <typename Model, typename Real, int PPT>
 __global__ void __launch_bounds__(ST_THREADS) k_st_init(StreamParams P) {
   constexpr int TS = ST_THREADS * PPT;
   __shared__ double s_red[ST_NW];
   const FilterDev& f = P.f;
-  const int c = blockIdx.x / P.nt, tile = blockIdx.x % P.nt, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (!f.alive[c]) return;
   const StLayout L = st_layout_in<TS>(P, c, 0);
-  if (tile >= L.ntc) return;
+  if (j >= L.nb) return;
   Real par[Model::NPAR];
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
-  const int sbase = tile * TS + tid * PPT;
-  const long long g0 = L.goff - L.lead + sbase;
-  Real x[PPT];
   double sum0 = 0.0;
+  for (int tile = j * L.tpb; tile < min(L.ntc, (j + 1) * L.tpb); tile++) {
+    const int sbase = tile * TS + tid * PPT;
+    const long long g0 = L.goff - L.lead + sbase;
+    Real x[PPT];
 #pragma unroll
-  for (int h = 0; h < PPT / 4; h++) {
-    uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
-    Real zz[4];
-    Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
-    Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+    for (int h = 0; h < PPT / 4; h++) {
+      uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
+      Real zz[4];
+      Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
+      Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      Real xi[1]; Real zi[1] = {zz[k]};
-      Model::template init<Real>(xi, par, zi, nullptr);
-      const long long g = g0 + 4 * h + k;
-      const bool valid = g >= L.goff && g < L.goff + L.nloc;
-      x[4 * h + k] = valid ? xi[0] : (Real)0;
-      sum0 += (double)x[4 * h + k];
+      for (int k = 0; k < 4; k++) {
+        Real xi[1]; Real zi[1] = {zz[k]};
+        Model::template init<Real>(xi, par, zi, nullptr);
+        const long long g = g0 + 4 * h + k;
+        const bool valid = g >= L.goff && g < L.goff + L.nloc;
+        x[4 * h + k] = valid ? xi[0] : (Real)0;
+        sum0 += (double)x[4 * h + k];
+      }
     }
+    StVec<Real, PPT>::store((Real*)P.x0 + (size_t)c * P.xstride + sbase, x);
   }
-  StVec<Real, PPT>::store((Real*)P.x0 + (size_t)c * P.xstride + sbase, x);
   double v = warp_sum_d(sum0);
   if (lane == 0) s_red[wid] = v;
   __syncthreads();
   if (wid == 0) {
     double t = warp_sum_d(lane < ST_NW ? s_red[lane] : 0.0);
-    if (lane == 0) P.bsum[(size_t)c * P.nt + tile] = t;
+    if (lane == 0) P.bsum[(size_t)c * P.bpc + j] = t;
   }
 }
 
@@ -365,10 +379,10 @@ template <typename Real> __device__ __forceinline__ Real st_warp_max(Real v) {
   return v;
 }
 
-// ---- K_A: propagate + log-weight + tile partials; the last block of a filter merges ----
-// Block (c, j) of `bpc` blocks per filter walks the tiles j, j + bpc, ... of filter c; the next tile's
-// particles are in flight (cp.async) while the current tile is computed, and the block pays the
-// descriptor loads, the parameter set-up and the fence + ticket once, not once per tile.
+// ---- K_A: propagate + log-weight + tile / block partials; the last block of a filter merges ----
+// Block (c, j) walks the contiguous tiles [j * tpb, (j + 1) * tpb) of filter c; the next tile's particles
+// are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
+// the parameter set-up and the fence + ticket once, not once per tile.
 template <typename Model, typename Real, int PPT>
 __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int obs) {
   static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
@@ -383,12 +397,13 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
   const long long t_start = P.dbg ? clock64() : 0;
   if (!f.alive[c]) return;
   const StLayout L = st_layout_in<TS>(P, c, obs);
-  if (j >= L.ntc) return;
-  const int rprev = P.res[((obs + 1) & 1) * f.C + c];
-  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  if (j >= L.nb) return;
+  const int pp = (obs + 1) & 1;
+  const int rprev = P.res[pp * f.C + c];
+  const int t0 = j * L.tpb, t1 = min(L.ntc, t0 + L.tpb);
   const Real* xin = (const Real*)(rprev ? P.x0 : P.x1) + (size_t)c * P.xstride + tid * PPT;
   Real* xout = (Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
-  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)j * TS);
+  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)t0 * TS);
   Real par[Model::NPAR];
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
@@ -396,14 +411,15 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
   const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
-  const size_t prow = (size_t)c * P.nt;
+  const size_t trow = (size_t)c * P.nt;
+  // block record (warp 0, identical in its lanes): online max / rescaled sums over the block's tiles
+  Real mB = Math<Real>::ninf(), sB = 0, qB = 0, xB = 0;
 
-  int it = 0;
-  for (int tile = j; tile < L.ntc; tile += P.bpc, it++) {
-    const int pb = it & 1;
+  for (int tile = t0; tile < t1; tile++) {
+    const int pb = (tile - t0) & 1;
     Real x[PPT];
     st_take<Real, PPT>(x, s_pf[pb]);
-    if (tile + P.bpc < L.ntc) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + P.bpc) * TS);
+    if (tile + 1 < t1) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
     const int sbase = tile * TS + tid * PPT;
     const long long g0 = L.goff - L.lead + sbase;
     const int k_lo = (int)max(0LL, min((long long)PPT, L.goff - g0));
@@ -471,23 +487,40 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
       for (int o = ST_NW / 2; o; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
-      if (lane == 0) { P.part_m[prow + tile] = (double)mt; P.part_s[prow + tile] = (double)a0; P.part_q[prow + tile] = (double)a1; P.part_x[prow + tile] = (double)a2; }
+      if (lane == 0) { P.tile_m[trow + tile] = (double)mt; P.tile_s[trow + tile] = (double)a0; }
+      // fold the tile into the block record (tiles in order)
+      if (mt > mB) {
+        const Real r = (mB == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mB - mt);
+        sB = sB * r + a0; qB = qB * r * r + a1; xB = xB * r + a2; mB = mt;
+      } else if (mt != Math<Real>::ninf()) {
+        const Real r = Math<Real>::exp_(mt - mB);
+        sB += a0 * r; qB += a1 * r * r; xB += a2 * r;
+      } else {
+        sB += a0; qB += a1; xB += a2;   // empty tile: zeros, or the NaN marker of a poisoned sum
+      }
     }
   }
   // one ticket per block; the last block of the filter merges.  The barrier-reduction makes the outcome a
-  // block-uniform value the compiler can see, so the merge below runs as convergent code (plain shuffles)
+  // block-uniform value the compiler can see
   int mine = 0;
   if (tid == 0) {
+    const size_t brow = (size_t)c * P.bpc + j;
+    P.blk_m[brow] = (double)mB; P.blk_s[brow] = (double)sB; P.blk_q[brow] = (double)qB; P.blk_x[brow] = (double)xB;
     __threadfence();
     const unsigned int ticket = atomicAdd(&P.counter[c], 1u);
-    mine = (ticket == (unsigned int)(min(P.bpc, L.ntc) - 1));
+    mine = (ticket == (unsigned int)(L.nb - 1));
   }
   if (!__syncthreads_or(mine)) return;
   __threadfence();
   const long long t_tick = P.dbg ? clock64() : 0;
-  if (P.dbg && tid == 0) P.dbg[3] = t_tick;
+  // records of the pending state sum: the blocks of the layout the previous resampling (or the init) ran on
+  int nb_pending = 0;
+  if (rprev) {
+    const StSeg& sp = P.seg[pp * f.C + c];
+    nb_pending = obs == 0 ? L.nb : st_make_layout<TS>(sp.goff, sp.nloc, P.bpc).nb;
+  }
   StRec r;
-  st_local_merge<Real>(P, c, L.ntc, rprev != 0, s_red, r);
+  st_local_merge<Real>(P, c, L.nb, nb_pending, s_red, r);
   const long long t_merge = P.dbg ? clock64() : 0;
   if (tid == 0) P.counter[c] = 0u;
   if (P.sharded) { if (tid == 0) P.rec_local[c] = r; }
@@ -504,31 +537,39 @@ static __global__ void k_st_merge(StreamParams P, int obs) {
 }
 
 // ---- K_B: resampling (scan + closed-form offspring ranges + staged scatter) ----
-// Same block-to-tile assignment and prefetch as k_st_step.
+// Same block -> tile ranges and prefetch as k_st_step.  A block's cdf interval comes from the block prefix
+// array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
+// running sums of the tile partials.
 template <typename Model, typename Real, int PPT>
-__global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, int obs) {
+__global__ void __launch_bounds__(ST_THREADS, 4) k_st_resample(StreamParams P, int obs) {
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;
   constexpr int CAP = TS + ST_SLACK;
-  __shared__ __align__(16) Real s_out[CAP];
-  __shared__ __align__(16) unsigned int s_u[CAP];
+  constexpr int SPT = CAP / ST_THREADS;      // output slots per thread in the expansion
+  static_assert(CAP % ST_THREADS == 0 && SPT % 2 == 0, "staging capacity: whole, even number of slots per thread");
+  // one buffer, two lives: the staged stratified uniforms (raw Philox words) of the tile while the offspring
+  // ranges are computed, then the staged outputs of a chunk
+  __shared__ __align__(16) unsigned char s_uo[CAP * (sizeof(Real) > 4 ? sizeof(Real) : 4)];
+  unsigned int* const s_u = (unsigned int*)s_uo;
+  Real* const s_out = (Real*)s_uo;
+  __shared__ __align__(16) unsigned int s_head[CAP];       // expansion: (source index << 16 | address of its x) at the first slot of a source
   __shared__ uint4 s_pf[2][2 * ST_THREADS];
+  __shared__ double s_pl[ST_MAX_TPB + 1];   // exclusive prefix of the tile sums inside this block (local-max scale)
   __shared__ double s_red[ST_NW], s_bs[ST_NW], s_cdf[2];
   __shared__ int s_wf[ST_NW];
-  __shared__ int s_heavy_n;
-  __shared__ int s_heavy_lo[ST_HEAVY_CAP], s_heavy_hi[ST_HEAVY_CAP];
-  __shared__ Real s_heavy_x[ST_HEAVY_CAP];
+  __shared__ unsigned int s_wh[ST_NW];
   const FilterDev& f = P.f;
-  const int c = blockIdx.x / P.bpc_r, j = blockIdx.x % P.bpc_r, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (!f.alive[c]) return;
   const int pc = obs & 1;
   if (!P.res[pc * f.C + c]) return;
   const StSeg sg = P.seg[pc * f.C + c];
-  const int lead = (int)(sg.goff & 3);
-  const int ntc = max(1, (sg.nloc + lead + TS - 1) / TS);
-  if (j >= ntc) return;
+  const StLayout L = st_make_layout<TS>(sg.goff, sg.nloc, P.bpc);
+  if (j >= L.nb) return;
+  const int lead = L.lead, ntc = L.ntc;
+  const int t0 = j * L.tpb, t1 = min(ntc, t0 + L.tpb);
   const Real* xin = (const Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
-  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)j * TS);
+  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)t0 * TS);
   const int n = P.n_glob ? P.n_glob : filt_n(f, c);
   Real par[Model::NPAR];
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
@@ -538,29 +579,44 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   const double M = f.M[c], S = f.S[c];
   const double wscale = 1.0 / S;
-  const double* pref = P.pref + (size_t)c * (P.nt + 1);
+  const double* pref = P.pref + (size_t)c * (P.bpc + 1);
+  const double b_lo = pref[j], b_hi = pref[j + 1];
   Real* xo = (Real*)P.x0 + (size_t)c * P.xstride - (sg.ngoff & ~3LL);   // xo[slot] = storage of global slot
-  if (tid == 0) s_heavy_n = 0;
-  double p_lo = pref[j], p_hi = pref[j + 1];
+#pragma unroll
+  for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;     // every thread keeps its own slots of the head array clear
+  if (wid == 0) {
+    // within-block exclusive prefix of the tile sums on the local-max scale (tiles in order, 32 per round)
+    const double* tm = P.tile_m + (size_t)c * P.nt;
+    const double* tsum = P.tile_s + (size_t)c * P.nt;
+    const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+    double carry = 0.0;
+    for (int tb = t0; tb < t1; tb += 32) {
+      const int t = tb + lane;
+      double v = 0.0;
+      if (t < t1) {
+        const double mt = tm[t];
+        if (!(mt == NINF || sg.mloc == NINF)) v = tsum[t] * (double)Math<Real>::exp_((Real)(mt - sg.mloc));
+      }
+      const double inc = warp_incl_scan_d(v, lane);
+      if (t < t1) s_pl[t - t0] = carry + (inc - v);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+  }
+  double bacc = 0.0;   // sum of the states written by this block (meaningful in thread 0)
 
-  int it = 0;
-  for (int tile = j; tile < ntc; tile += P.bpc_r, it++) {
-  const int pb = it & 1;
+  for (int tile = t0; tile < t1; tile++) {
+  const int pb = (tile - t0) & 1;
   const int sbase = tile * TS + tid * PPT;
   const long long g0 = sg.goff - lead + sbase;
   const int k_lo = (int)max(0LL, min((long long)PPT, sg.goff - g0));
   const int k_hi = (int)max(0LL, min((long long)PPT, sg.goff + sg.nloc - g0));
   const int last_s = min(TS, sg.nloc + lead - tile * TS) - 1;   // in-tile storage index of the last valid particle
   const bool ragged = k_lo > 0 || k_hi < PPT;
-  // this tile's cdf interval, from the prefix array (bit-identical in the neighbouring tiles)
-  const double A_lo = tile == 0 ? sg.abase : st_bound(sg.abase, p_lo, sg.gscale);
-  const double A_hi = tile == ntc - 1 ? sg.aend : st_bound(sg.abase, p_hi, sg.gscale);
+  const bool special = ragged || (last_s >= tid * PPT && last_s < (tid + 1) * PPT);
   Real x[PPT], e[PPT];
   st_take<Real, PPT>(x, s_pf[pb]);
-  if (tile + P.bpc_r < ntc) {
-    st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + P.bpc_r) * TS);
-    p_lo = pref[tile + P.bpc_r]; p_hi = pref[tile + P.bpc_r + 1];
-  }
+  if (tile + 1 < t1) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
   Real fs = 0;
   {
     const Real Mr = (Real)M;
@@ -585,6 +641,13 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
     for (int o = 1; o < 32; o <<= 1) { Real t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) s_red[wid] = (double)inc;
     if (tid == 0) {   // one pair of boundary values per tile, not per thread
+      // block edges from the prefix array (the neighbouring block reads the same value), rank edges from the
+      // descriptor, tile edges inside the block from this block's own prefix
+      double A_lo, A_hi;
+      if (tile == 0) A_lo = sg.abase;
+      else A_lo = st_bound(sg.abase, tile == t0 ? b_lo : b_lo + s_pl[tile - t0], sg.gscale);
+      if (tile == ntc - 1) A_hi = sg.aend;
+      else A_hi = st_bound(sg.abase, tile == t1 - 1 ? b_hi : b_lo + s_pl[tile + 1 - t0], sg.gscale);
       if (F32) { s_cdf[0] = A_lo * wscale; s_cdf[1] = A_hi * wscale; }      // reciprocal: no fp64 division chain before the barrier
       else { s_cdf[0] = A_lo / S; s_cdf[1] = A_hi / S; }
     }
@@ -643,11 +706,20 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
         if (tf >= 4194304.0f) v = sc.count_le(lo_cdf + (exu + (double)accf) * wscale);   // beyond the fp32 floor trick (degenerate weights)
         else if (i >= n) v = n;
         else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);
-        if (tid * PPT + k == last_s) v = o_hi;
         v = min(max(v, o_lo), o_hi);
-        if (ragged && (k < k_lo || k >= k_hi)) v = o_lo;
         fmax = max(fmax, v);
         F[k] = fmax;
+      }
+      if (special) {   // the thread with padding lanes and / or the last valid particle of the tile (which takes what is left)
+        fmax = o_lo;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+          int v = F[k];
+          if (tid * PPT + k == last_s) v = o_hi;
+          if (k < k_lo || k >= k_hi) v = o_lo;
+          fmax = max(fmax, v);
+          F[k] = fmax;
+        }
       }
     } else {
       double acc = exu;
@@ -684,9 +756,15 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
 #pragma unroll
     for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
   }
-  // scatter into the staging buffer (chunks of CAP slots), copy out coalesced
+  // Expansion, output-centric (chunks of CAP slots): every source with offspring in the chunk marks the first of
+  // its slots with (source index, address of its x in the prefetch buffer); a running maximum over the slots --
+  // source indices grow with the slot -- tells every slot its source.  O(1) per source and per slot, no loop
+  // over the offspring of a source, no special case for heavy sources.  The chosen x are staged and leave the
+  // SM as coalesced vector stores.
   Real sumx = 0;
   const int o_base = o_lo & ~3;
+  constexpr int EPH = 16 / (int)sizeof(Real);                          // elements per 16-byte half of the prefetch layout
+  const Real* s_x = (const Real*)s_pf[pb];
   for (int c0 = o_base; c0 < o_hi; c0 += CAP) {
     const int c1 = min(o_hi, c0 + CAP);
     int lo_k = prevF;
@@ -694,29 +772,39 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
     for (int k = 0; k < PPT; k++) {
       const int hi_k = F[k];
       const int a = max(lo_k, c0);
-      int cnt = min(hi_k, c1) - a;
+      if (min(hi_k, c1) > a) s_head[a - c0] = ((unsigned int)(tid * PPT + k) << 16) | (unsigned int)(((k / EPH) * ST_THREADS + tid) * EPH + (k % EPH));
       if (c0 == o_base && hi_k > lo_k) sumx += (Real)(hi_k - lo_k) * x[k];
-      if (cnt > ST_HEAVY) {
-        int slot = atomicAdd(&s_heavy_n, 1);
-        if (slot < ST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = a + cnt; s_heavy_x[slot] = x[k]; cnt = 0; }
-      }
-      Real* dst = s_out + (a - c0);
-      if (cnt > 0) dst[0] = x[k];
-      if (cnt > 1) dst[1] = x[k];
-      if (__any_sync(0xffffffffu, cnt > 2)) {       // warp-uniform: most sources have 0, 1 or 2 offspring
-        const int mx = __reduce_max_sync(0xffffffffu, cnt);
-        for (int r = 2; r < mx; r++) if (r < cnt) dst[r] = x[k];
-      }
       lo_k = max(lo_k, hi_k);
     }
     __syncthreads();
-    const int nh = min(s_heavy_n, ST_HEAVY_CAP);
-    for (int h = 0; h < nh; h++) {
-      const int a = s_heavy_lo[h], z = s_heavy_hi[h];
-      const Real xv = s_heavy_x[h];
-      for (int o = a + tid; o < z; o += ST_THREADS) s_out[o - c0] = xv;
+    // running maximum over the slots: thread-local, then across the warp, then across the warps
+    unsigned int h[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; i += 2) { const uint2 v2 = *(const uint2*)&s_head[tid * SPT + i]; h[i] = v2.x; h[i + 1] = v2.y; }
+#pragma unroll
+    for (int i = 0; i < SPT; i += 2) *(uint2*)&s_head[tid * SPT + i] = make_uint2(0u, 0u);   // clear for the next chunk / tile
+#pragma unroll
+    for (int i = 1; i < SPT; i++) h[i] = max(h[i], h[i - 1]);
+    unsigned int inc = h[SPT - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+    if (lane == 31) s_wh[wid] = inc;
+    unsigned int carry = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) carry = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < ST_NW - 1; w++) carry = max(carry, (w < wid) ? s_wh[w] : 0u);
+    Real val[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; i++) val[i] = s_x[max(h[i], carry) & 0xFFFFu];
+    if constexpr (F32) {
+#pragma unroll
+      for (int i = 0; i < SPT; i += 2) *(float2*)&s_out[tid * SPT + i] = make_float2(val[i], val[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < SPT; i++) s_out[tid * SPT + i] = val[i];
     }
-    if (nh) __syncthreads();
+    __syncthreads();
     const int first = max(c0, o_lo), last = c1;
     if (F32) {
       for (int o = c0 + 4 * tid; o < last; o += 4 * ST_THREADS) {
@@ -732,22 +820,22 @@ __global__ void __launch_bounds__(ST_THREADS, 3) k_st_resample(StreamParams P, i
     } else {
       for (int o = first + tid; o < last; o += ST_THREADS) xo[o] = s_out[o - c0];
     }
-    if (tid == 0) s_heavy_n = 0;
     __syncthreads();
   }
-  // tile sum of the chosen states (state estimate after resampling, merged by the next observation's k_st_step)
+  // sum of the chosen states (state estimate after resampling, merged by the next observation's k_st_step)
   double v = warp_sum_d((double)sumx);
   if (lane == 0) s_bs[wid] = v;
   __syncthreads();
-  if (wid == 0) {
-    double t = warp_sum_d(lane < ST_NW ? s_bs[lane] : 0.0);
-    if (lane == 0) P.bsum[(size_t)c * P.nt + tile] = t;
+  if (tid == 0) {
+    for (int w = 0; w < ST_NW; w++) bacc += s_bs[w];
   }
   }  // tiles
+  if (tid == 0) P.bsum[(size_t)c * P.bpc + j] = bacc;
 }
 
 // ---- flush: the state estimate of a final resampling (or of the initial particles when T = 0) ----
-static __global__ void __launch_bounds__(ST_THREADS) k_st_flush(StreamParams P, int obs /* = T */, int TS) {
+template <int TS>
+static __global__ void __launch_bounds__(ST_THREADS) k_st_flush(StreamParams P, int obs /* = T */) {
   __shared__ double s_red[ST_NW];
   const FilterDev& f = P.f;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -755,12 +843,10 @@ static __global__ void __launch_bounds__(ST_THREADS) k_st_flush(StreamParams P, 
   const int pp = (obs + 1) & 1;
   const int rprev = P.res[pp * f.C + c];
   const StSeg& sp = P.seg[pp * f.C + c];
-  const int nloc = rprev ? sp.nnloc : sp.nloc;
-  const int lead = (int)((rprev ? sp.ngoff : sp.goff) & 3);
-  const int ntc = max(1, (nloc + lead + TS - 1) / TS);
-  const int chunk = (ntc + ST_THREADS - 1) / ST_THREADS;
+  // the blocks of the layout the last resampling (or the init) ran on
+  const int nbp = st_make_layout<TS>(sp.goff, sp.nloc, P.bpc).nb;
   double lp = 0.0;
-  if (rprev) for (int j = tid * chunk; j < min(ntc, (tid + 1) * chunk); j++) lp += P.bsum[(size_t)c * P.nt + j];
+  if (rprev) for (int j = tid; j < nbp; j += ST_THREADS) lp += P.bsum[(size_t)c * P.bpc + j];
   lp = warp_sum_d(lp);
   if (lane == 0) s_red[wid] = lp;
   __syncthreads();
