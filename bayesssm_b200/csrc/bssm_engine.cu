@@ -2,6 +2,7 @@
 // (PMMH lives in bssm_pmmh.cu, the persistent bootstrap-filter kernel in bssm_fast.cu.)
 // No CPU fallback anywhere: every entry point needs a CUDA device.
 #include "bssm_engine.cuh"
+#include "bssm_fast.cuh"
 
 #include <stdarg.h>
 
@@ -212,20 +213,45 @@ int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst) {
   return BSSM_ERR_BAD_ARG;
 }
 
+// Which engine serves a run.  The general kernels serve everything; the two bootstrap-filter engines serve the
+// throughput precision (and BSSM_F64 when asked for by name):
+//   persistent kernel  particles in registers, one launch per filter: single filters up to ~2 M particles and
+//                      small batches -- latency-bound sizes
+//   streaming engine   particles in HBM, two launches per observation: large batches [chains x particles] and
+//                      single filters beyond the persistent kernel's capacity (measured: 1024 x 65536 runs
+//                      1.3x faster here, N = 2^26 is only possible here)
+// Returns -1 when an engine requested by name cannot serve the configuration.
+int resolve_engine(bssm_ctx* ctx, const FilterDev& f_in, const FilterLaunch& L, bool injected, bool want_anc) {
+  FilterDev f = f_in;
+  f.noise.injected = injected ? 1 : 0;
+  f.anc_history = want_anc ? (int*)1 : nullptr;
+  if (L.engine == BSSM_ENGINE_GENERAL) return BSSM_ENGINE_GENERAL;
+  if (L.engine == BSSM_ENGINE_PERSISTENT) return fast_supported(f, L) ? BSSM_ENGINE_PERSISTENT : -1;
+  if (L.engine == BSSM_ENGINE_STREAM) return stream_supported(f, L) ? BSSM_ENGINE_STREAM : -1;
+  if (L.precision != BSSM_F32) return BSSM_ENGINE_GENERAL;
+  // the persistent kernel needs the CTAs of a filter co-resident: at most one full slice per SM
+  const bool fast_ok = fast_supported(f, L) && (long long)f.N <= (long long)ctx->prop.multiProcessorCount * FAST_MAX_NB;
+  const bool stream_ok = stream_supported(f, L);
+  const long long total = (long long)f.C * f.N;
+  // measured on B200 (scripts/bench_engines.py): 1024 x 65536 streaming +30 %, 4 x 2^20 +29 %; 256 x 65536 a tie;
+  // smaller batches and slices belong to the persistent kernel
+  const bool stream_wins = (f.N >= (1 << 19) && f.C >= 4) || (f.N >= 32768 && total >= (1LL << 25));
+  if (stream_ok && (!fast_ok || stream_wins)) return BSSM_ENGINE_STREAM;
+  if (fast_ok) return BSSM_ENGINE_PERSISTENT;
+  return BSSM_ENGINE_GENERAL;
+}
+
 // enqueue one batched filter run on ctx->stream (no synchronisation)
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
-  // engine choice: the persistent kernel serves the throughput precision of the bootstrap filter;
-  // everything else (and BSSM_F64 parity runs unless forced) goes through the general kernels
-  if (L.engine == BSSM_ENGINE_PERSISTENT) {
-    if (!fast_supported(f, L)) { set_error("BSSM_ENGINE_PERSISTENT: configuration not supported by the persistent kernel (BPF, 1-D built-in model, stratified/systematic, no histories / injected noise)"); return BSSM_ERR_UNSUPPORTED; }
-    return fast_filter_enqueue(ctx, f, L);
+  const int eng = resolve_engine(ctx, f, L, f.noise.injected != 0, f.anc_history != nullptr);
+  if (eng < 0) {
+    set_error("%s: configuration not supported by that engine (bootstrap filter of a 1-D built-in model, stratified / systematic resampling, no histories / injected noise)",
+              L.engine == BSSM_ENGINE_PERSISTENT ? "BSSM_ENGINE_PERSISTENT" : "BSSM_ENGINE_STREAM");
+    return BSSM_ERR_UNSUPPORTED;
   }
-  if (L.engine == BSSM_ENGINE_STREAM) {
-    if (!stream_supported(f, L)) { set_error("BSSM_ENGINE_STREAM: configuration not supported by the streaming engine (BPF, 1-D built-in model, stratified/systematic, no histories / injected noise)"); return BSSM_ERR_UNSUPPORTED; }
-    return stream_filter_enqueue(ctx, f, L, nullptr);
-  }
-  if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && fast_supported(f, L)) return fast_filter_enqueue(ctx, f, L);
-  if (L.engine == BSSM_ENGINE_AUTO && L.precision == BSSM_F32 && stream_supported(f, L)) return stream_filter_enqueue(ctx, f, L, nullptr);
+  if (eng == BSSM_ENGINE_PERSISTENT) return fast_filter_enqueue(ctx, f, L);
+  if (eng == BSSM_ENGINE_STREAM) return stream_filter_enqueue(ctx, f, L, nullptr);
+  if (!f.xa) { set_error("internal: general engine selected but its particle arrays were not set up"); return BSSM_ERR_BAD_ARG; }
   if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC-compiled user model (bssm_nvrtc.cu)
     const UserModelInfo* u = user_model(ctx, L.model);
     if (!u) { set_error("unknown user model id %d", L.model); return BSSM_ERR_BAD_ARG; }
@@ -261,21 +287,27 @@ __global__ void k_fill_uniform(double* p, size_t n, unsigned long long seed) {
 }
 
 // allocate the per-batch state of a filter run inside the context's scratch slots
-int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out) {
+int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out, bool injected) {
   const size_t C = f.C, N = f.N, d = f.d, T = f.T;
   const size_t rs = L.precision == BSSM_F64 ? 8 : 4;
   f.nblk = (int)((N + FT_THREADS - 1) / FT_THREADS);
   if (f.nblk > 1024) f.nblk = 1024;
   if (f.nblk < 1) f.nblk = 1;
-  BSSM_TRY(scratch_get(ctx, SL_F_XA, C * d * N * rs, &f.xa));
-  BSSM_TRY(scratch_get(ctx, SL_F_XB, C * d * N * rs, &f.xb));
-  BSSM_TRY(scratch_get(ctx, SL_F_LW, C * N * rs, &f.lw));
-  if (need_aux) {
-    BSSM_TRY(scratch_get(ctx, SL_F_LWAUX, C * N * rs, &f.lw_aux));
-    BSSM_TRY(scratch_get(ctx, SL_F_AUXG, C * N * rs, &f.auxg));
-  } else { f.lw_aux = nullptr; f.auxg = nullptr; }
-  BSSM_TRY(scratch(ctx, SL_F_PART, C * f.nblk * PART_W, &f.part));
-  BSSM_TRY(scratch(ctx, SL_F_CDF, C * N, cdf_out));
+  // the particle / weight / cdf arrays belong to the general kernels; the persistent and streaming engines keep their own state
+  const int eng = resolve_engine(ctx, f, L, injected, want_anc);
+  const bool general = eng == BSSM_ENGINE_GENERAL || eng < 0;
+  f.xa = f.xb = f.lw = f.lw_aux = f.auxg = nullptr; f.part = nullptr; *cdf_out = nullptr;
+  if (general) {
+    BSSM_TRY(scratch_get(ctx, SL_F_XA, C * d * N * rs, &f.xa));
+    BSSM_TRY(scratch_get(ctx, SL_F_XB, C * d * N * rs, &f.xb));
+    BSSM_TRY(scratch_get(ctx, SL_F_LW, C * N * rs, &f.lw));
+    if (need_aux) {
+      BSSM_TRY(scratch_get(ctx, SL_F_LWAUX, C * N * rs, &f.lw_aux));
+      BSSM_TRY(scratch_get(ctx, SL_F_AUXG, C * N * rs, &f.auxg));
+    }
+    BSSM_TRY(scratch(ctx, SL_F_PART, C * f.nblk * PART_W, &f.part));
+    BSSM_TRY(scratch(ctx, SL_F_CDF, C * N, cdf_out));
+  }
   double* sd; int* si;
   BSSM_TRY(scratch(ctx, SL_F_SCAL_D, C * 4, &sd));
   BSSM_TRY(scratch(ctx, SL_F_SCAL_I, C * 6, &si));
@@ -543,7 +575,7 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   const bool need_aux = cfg->algorithm == BSSM_APF;
   const bool want_anc = res->ancestors_history != nullptr || res->ancestors_aux_history != nullptr;
   double* cdf;
-  BSSM_TRY(filter_setup(ctx, f, L, need_aux, want_anc, &cdf));
+  BSSM_TRY(filter_setup(ctx, f, L, need_aux, want_anc, &cdf, cfg->noise != nullptr));
   // inputs
   double* d_theta; double* d_y; int* d_obs = nullptr; unsigned int* ids;
   BSSM_TRY(scratch(ctx, SL_F_THETA, (size_t)C * f.theta_stride, &d_theta));

@@ -111,7 +111,8 @@ struct FilterLaunch {
   int model, precision, resample_fn, exact, hist, T, engine;
 };
 int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst);
-int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out);
+int resolve_engine(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L, bool injected, bool want_anc);
+int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, bool want_anc, double** cdf_out, bool injected = false);
 int filter_reset(bssm_ctx* ctx, FilterDev& f, const int* d_active);
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf);
 // persistent bootstrap-filter kernel (bssm_fast.cu)

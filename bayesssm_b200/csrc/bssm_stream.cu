@@ -49,10 +49,13 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     const long long bmin = (P.nt + ST_MAX_TPB - 1) / ST_MAX_TPB;   // at most ST_MAX_TPB tiles per block
     if (b0 < bmin) b0 = bmin;
     if (b0 > P.nt) b0 = P.nt;
-    long long best = b0, best_cost = -1;
-    for (long long b = b0; b <= P.nt && b <= 4 * b0 + 3; b++) {
-      const long long waves = ((long long)C * b + slots - 1) / slots;
-      const long long cost = waves * ((P.nt + b - 1) / b) * 16 + waves;   // + a little per wave for the block prologue
+    // cost in tile-times: the blocks' work spread over the resident slots plus one block's length as the tail;
+    // a block pays ~2 tile-times of prologue / ticket on top of its tiles
+    long long best = b0; double best_cost = -1.0;
+    for (long long b = b0; b <= P.nt && b <= 8 * b0 + 8; b++) {
+      const double len = (double)((P.nt + b - 1) / b) + 2.0;
+      const double blocks = (double)C * (double)b;
+      const double cost = (blocks <= (double)slots ? len : blocks * len / (double)slots + len);
       if (best_cost < 0 || cost < best_cost) { best = b; best_cost = cost; }
     }
     if (const char* e = getenv("BSSM_ST_BPC")) { int v = atoi(e); if (v >= bmin && v <= P.nt) best = v; }

@@ -202,18 +202,85 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": main_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"pmmh nonlinear-AR {Ctot} chains x N={N} x T={T}, chain-sharded, pilot skipped, final NCCL gather of draws",
-                       "chains": Ctot, "N": N, "T": T, "engine": args.engine, "l2": "working set 8 B/particle of resident groups; inputs far larger than L2 over the run"},
+                       "chains": Ctot, "N": N, "T": T, "engine": args.engine, "l2": "working set 2 x 256 MiB of particles per GPU at 1024 chains: larger than L2"},
             "particle_timesteps_per_s": pts,
             "e2e": {"value": args.steps / (wall_ms * 1e-3), "unit": "iter/s", "h2d_bytes_per_step": int(8 * T / args.steps),
                     "d2h_bytes_per_step": int(out["theta_chain"].nbytes / args.steps)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": pts * 30.0 / 1e9, "peak": peak * world, "unit": "GB/s",
                          "frac": pts * 30.0 / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
-                         "kernel": "persistent filter kernel", "algorithmic_bytes_per_particle_timestep": 30.0},
+                         "kernel": "batched filter kernels of one iteration (AUTO: streaming engine k_st_step + k_st_resample at this size)",
+                         "algorithmic_bytes_per_particle_timestep": 30.0, "note": "12 B + 28 B x resampled fraction (0.63 on this model)"},
             "acceptance_rate": float(gathered["n_accept"].mean() / max(args.steps, 1)),
             "draws_gathered_shape": list(gathered["theta_chain"].shape)}
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+def run_sharded_workload(args, ctx, rank, local_rank, world):
+    """One bootstrap filter of `--shard-N` particles (default 2^28) sharded over the ranks (third row):
+    per observation ONE ncclAllGather of a 64-byte record; no particle crosses NVLink.  Strong scaling: the
+    filter is fixed, the ranks split its particles.  A step is one whole filter of `--shard-T` observations."""
+    import torch
+    import torch.distributed as dist
+
+    from bayesssm_b200 import models, sharding as S
+    N, T = args.shard_N, args.shard_T
+    y = simulate_y(T)
+    grp = S.ShardGroup(ctx, rank=rank, world=world, device=torch.device("cuda", local_rank) if world > 1 else None)
+    m = models.nonlinear_ar()
+
+    def run(seed):
+        return S.sharded_bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp,
+                                          resample_algorithm="SISAR", resample_fn=args.resample_fn, threshold=0.5 * N,
+                                          precision=args.precision, seed=seed, capacity_factor=args.capacity_factor,
+                                          phi=THETA[0], sigma_x=THETA[1], sigma_y=THETA[2])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for i in range(args.warmup):
+        run(i)
+    barrier()
+    l0 = ctx.launch_count()
+    ms, e2e = [], []
+    with ClockSampler(local_rank) as clocks:
+        for i in range(args.steps):
+            barrier()
+            t1 = time.perf_counter()
+            r = run(100 + i)
+            e2e.append(1e3 * (time.perf_counter() - t1))
+            ms.append(r["kernel_ms"])
+        barrier()
+    launches = ctx.launch_count() - l0
+    tot, tot_e2e = float(sum(ms)), float(sum(e2e))
+    if world > 1:
+        t = torch.tensor([tot, tot_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot, tot_e2e = float(t[0]), float(t[1])
+    value = N * T * args.steps / (tot * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    nbytes = algorithmic_bytes(N, T, r["n_resampled"])
+    achieved = nbytes / (tot / args.steps * 1e-3) / 1e9
+    line = {"metric": "particle-timesteps/sec", "value": value, "unit": "particle-timesteps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"ONE bootstrap filter nonlinear-AR N={N} T={T} SISAR threshold=0.5N {args.resample_fn}, particles "
+                                   f"sharded over {world} GPU(s), one ncclAllGather of a 64-byte record per observation",
+                       "N": N, "T": T, "engine": "stream (sharded)", "capacity_factor": args.capacity_factor,
+                       "l2": "working set (8 B/particle x 2 buffers per rank) far larger than L2"},
+            "e2e": {"value": N * T * args.steps / (tot_e2e * 1e-3), "unit": "particle-timesteps/s",
+                    "h2d_bytes_per_step": 8 * T + 24, "d2h_bytes_per_step": 8 * (3 * T + 3) + 12},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_st_step + k_st_resample (all launches of one filter)",
+                         "algorithmic_bytes_per_launch": nbytes, "resampled_steps": int(r["n_resampled"]), "T": T},
+            "loglike": r["loglike"], "n_local_final": r["n_local_final"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    grp.close()
 
 
 def main():
@@ -228,8 +295,12 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "general", "persistent", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="filter", choices=["filter", "pmmh"],
-                    help="filter: BASELINE configs[1] (default); pmmh: configs[4], 1024 chains x N=65536 x T=1000 chain-sharded")
+    ap.add_argument("--workload", default="filter", choices=["filter", "pmmh", "sharded"],
+                    help="filter: BASELINE configs[1] (default); pmmh: configs[4], 1024 chains x N=65536 x T=1000 chain-sharded; "
+                         "sharded: one filter of --shard-N particles sharded over the ranks")
+    ap.add_argument("--shard-N", dest="shard_N", type=int, default=1 << 28)
+    ap.add_argument("--shard-T", dest="shard_T", type=int, default=50)
+    ap.add_argument("--capacity-factor", dest="capacity_factor", type=float, default=1.5)
     ap.add_argument("--chains", type=int, default=1024)
     ap.add_argument("--pmmh-N", dest="pmmh_N", type=int, default=65536)
     args = ap.parse_args()
@@ -255,8 +326,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = nat.Context(local_rank)
     lib = ctx.lib
-    if args.workload == "pmmh":
-        run_pmmh_workload(args, ctx, rank, local_rank, world)
+    if args.workload in ("pmmh", "sharded"):
+        (run_pmmh_workload if args.workload == "pmmh" else run_sharded_workload)(args, ctx, rank, local_rank, world)
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
@@ -362,7 +433,9 @@ def main():
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "whole filter pass (all launches of one step)" if launches / max(args.steps, 1) > 4 else "persistent filter kernel",
+                     "kernel": "persistent filter kernel" if launches / max(args.steps, 1) <= 4 else
+                               ("k_st_step + k_st_resample (streaming engine, all launches of one filter)" if launches / max(args.steps, 1) <= 2 * T + 8
+                                else "whole filter pass (general engine, all launches of one step)"),
                      "algorithmic_bytes_per_launch": bytes_per_launch, "resampled_steps": int(n_res), "T": T},
         "loglike": r0["loglike"],
     }
