@@ -75,7 +75,7 @@ class PmmhConfig(C.Structure):
         ("consts", c_double_p), ("nconst", C.c_int),
         ("precision", C.c_int), ("seed", C.c_uint64),
         ("skip_pilot", C.c_int), ("proposal_chol_in", c_double_p),
-        ("engine", C.c_int),
+        ("engine", C.c_int), ("return_latent_state_est", C.c_int),
     ]
 
 
@@ -87,6 +87,7 @@ class PmmhResult(C.Structure):
         ("theta_chain", c_double_p), ("loglike_chain", c_double_p),
         ("n_accept", c_int32_p), ("status", c_int32_p),
         ("pilot_ms", C.c_float), ("main_ms", C.c_float),
+        ("latent_state_chain", c_double_p),
     ]
 
 

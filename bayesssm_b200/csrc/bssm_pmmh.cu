@@ -32,6 +32,7 @@ struct PmmhDev {
   int *alive;                // [C]
   int *status;               // [C]
   int *n_accept;             // [C]
+  int *moved;                // [C] 1 if the chain took a new state in this iteration (latent state bookkeeping)
   unsigned int *stream, *run_id;  // [C] filter Philox ids
   // filter outputs
   const double* f_loglike; const int* f_status;
@@ -115,6 +116,7 @@ __global__ void k_pm_first(PmmhDev P, double* chain, double* ll_chain, int m) {
   if (c >= P.C) return;
   if (P.alive[c] && P.f_status[c]) { P.alive[c] = 0; P.status[c] = P.f_status[c]; }
   P.cur_ll[c] = P.f_loglike[c];
+  P.moved[c] = 1;
   for (int j = 0; j < P.p; j++) chain[((size_t)c * m) * P.p + j] = P.cur[(size_t)c * P.p + j];
   ll_chain[(size_t)c * m] = P.cur_ll[c];
 }
@@ -165,6 +167,7 @@ __global__ void k_pm_accept(PmmhDev P, int phase, int it, double* chain, double*
   const int p = P.p;
   double cur[PMAX];
   for (int j = 0; j < p; j++) cur[j] = P.cur[(size_t)c * p + j];
+  P.moved[c] = 0;
   if (P.alive[c] && P.valid[c]) {
     if (P.f_status[c]) { P.alive[c] = 0; P.status[c] = P.f_status[c]; }
     else {
@@ -183,12 +186,25 @@ __global__ void k_pm_accept(PmmhDev P, int phase, int it, double* chain, double*
       if (log(u) < ratio) {
         for (int j = 0; j < p; j++) { cur[j] = prop[j]; P.cur[(size_t)c * p + j] = prop[j]; }
         P.cur_ll[c] = prop_ll;
+        P.moved[c] = 1;
         if (phase == PH_MAIN) P.n_accept[c] += 1;
       }
     }
   }
   for (int j = 0; j < p; j++) chain[((size_t)c * m + it) * p + j] = cur[j];
   ll_chain[(size_t)c * m + it] = P.cur_ll[c];
+}
+
+// latent state estimates of the chain (R/pmmh.R:420,494-499): the state_est of the filter run that produced the
+// current state is carried along and stored for every iteration
+__global__ void k_pm_latent(PmmhDev P, const double* f_state_est, int len /* (T+1) d */, double* cur_se, double* se_chain, int it, int m) {
+  const int c = blockIdx.y;
+  const int moved = P.moved[c];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+    double v = moved ? f_state_est[(size_t)c * len + k] : cur_se[(size_t)c * len + k];
+    if (moved) cur_se[(size_t)c * len + k] = v;
+    se_chain[((size_t)c * m + it) * len + k] = v;
+  }
 }
 
 // pilot posterior mean / covariance of the second half on the original scale (R/pmmh_tuning.R:260-267)
@@ -323,6 +339,16 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   BSSM_TRY(scratch(ctx, slot++, (size_t)2 * C * reps, &B.ids_rep));
   double* d_init;
   BSSM_TRY(scratch(ctx, slot++, (size_t)C * p, &d_init));
+  int* d_moved;
+  BSSM_TRY(scratch(ctx, slot++, (size_t)C, &d_moved));
+  // latent state estimates (R/pmmh.R: return_latent_state_est): current + per-iteration copies, only when asked for
+  const bool latent = cfg->return_latent_state_est != 0 && res->latent_state_chain != nullptr;
+  const int se_len = (T + 1) * d;
+  double *d_cur_se = nullptr, *d_se_chain = nullptr;
+  if (latent) {
+    BSSM_TRY(scratch(ctx, slot++, (size_t)C * se_len, &d_cur_se));
+    BSSM_TRY(scratch(ctx, slot++, (size_t)C * m * se_len, &d_se_chain));
+  }
   BSSM_CK(cudaMemcpyAsync(B.y, y, sizeof(double) * T * cfg->dy, cudaMemcpyHostToDevice, st));
   BSSM_CK(cudaMemcpyAsync(d_init, init_theta, sizeof(double) * C * p, cudaMemcpyHostToDevice, st));
   if (cfg->obs_times) BSSM_CK(cudaMemcpyAsync(B.obs, cfg->obs_times, sizeof(int) * T, cudaMemcpyHostToDevice, st));
@@ -338,7 +364,7 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   }
   for (int j = 0; j < nc; j++) P.consts[j] = cfg->consts[j];
   P.cur = B.cur; P.prop = B.prop; P.cur_ll = B.cur_ll; P.lp_prop = B.lp_prop; P.theta_full = B.theta_full;
-  P.valid = B.valid; P.alive = B.alive; P.status = B.status; P.n_accept = B.n_accept;
+  P.valid = B.valid; P.alive = B.alive; P.status = B.status; P.n_accept = B.n_accept; P.moved = d_moved;
   P.stream = B.ids; P.run_id = B.ids + C;
 
   // ---- filter batch for the chains ----
@@ -423,12 +449,15 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
   k_pm_first<<<gb, 128, 0, st>>>(P, B.chain, B.ll_chain, m);
   BSSM_LAUNCH(ctx, "k_pm_first");
+  const dim3 grid_se((se_len + 255) / 256 > 64 ? 64 : (se_len + 255) / 256, C);
+  if (latent) { k_pm_latent<<<grid_se, 256, 0, st>>>(P, f.state_est, se_len, d_cur_se, d_se_chain, 0, m); BSSM_LAUNCH(ctx, "k_pm_latent"); }
   for (int it = 1; it < m; it++) {
     k_pm_propose<<<gb, 128, 0, st>>>(P, PH_MAIN, it, B.chol);
     BSSM_LAUNCH(ctx, "k_pm_propose");
     BSSM_TRY(run_chain_filters(ctx, f, L, cdf, P.valid));
     k_pm_accept<<<gb, 128, 0, st>>>(P, PH_MAIN, it, B.chain, B.ll_chain, m);
     BSSM_LAUNCH(ctx, "k_pm_accept");
+    if (latent) { k_pm_latent<<<grid_se, 256, 0, st>>>(P, f.state_est, se_len, d_cur_se, d_se_chain, it, m); BSSM_LAUNCH(ctx, "k_pm_latent"); }
   }
   BSSM_CK(cudaEventRecord(ctx->ev1, st));
 
@@ -445,6 +474,7 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   DL(res->theta_chain, B.chain, (size_t)C * m * p, double);
   DL(res->loglike_chain, B.ll_chain, (size_t)C * m, double);
   DL(res->n_accept, B.n_accept, (size_t)C, int);
+  if (latent) DL(res->latent_state_chain, d_se_chain, (size_t)C * m * se_len, double);
   DL(res->status, B.status, (size_t)C, int);
 #undef DL
   BSSM_CK(cudaStreamSynchronize(st));

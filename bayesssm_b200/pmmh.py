@@ -69,7 +69,7 @@ class PmmhOutput(dict):
 
 def run_chains(ctx, model, algorithm, y, init_theta, prior_specs, transforms, tune_control, m, seed,
                chain_id_base=0, fixed_num_particles=0, consts=(), obs_times=None, precision=nat.F64,
-               skip_pilot=False, proposal_chol=None, engine=nat.ENGINE_AUTO):
+               skip_pilot=False, proposal_chol=None, engine=nat.ENGINE_AUTO, return_latent_state_est=False):
     """Raw engine call for this process's shard of chains (used by pmmh() and by the multi-GPU bench)."""
     y = np.ascontiguousarray(y, dtype=np.float64)
     if y.ndim == 1:
@@ -117,6 +117,10 @@ def run_chains(ctx, model, algorithm, y, init_theta, prior_specs, transforms, tu
     for k in ("target_n", "n_accept", "status"):
         out[k] = np.zeros(Cn, dtype=np.int32)
         setattr(res, k, out[k].ctypes.data_as(nat.c_int32_p))
+    if return_latent_state_est:
+        cfg.return_latent_state_est = 1
+        out["latent_state_chain"] = np.zeros((Cn, int(m), T + 1, model.dim))
+        res.latent_state_chain = out["latent_state_chain"].ctypes.data_as(nat.c_double_p)
     nat.check(ctx.lib.bssm_pmmh_run(ctx.handle, C.byref(cfg), y.ctypes.data_as(nat.c_double_p),
                                     init_theta.ctypes.data_as(nat.c_double_p), C.byref(res)))
     out["pilot_ms"], out["main_ms"] = res.pilot_ms, res.main_ms
@@ -196,7 +200,8 @@ def pmmh(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, log_priors
     prec = _filters._precision(precision)
     try:
         out = run_chains(ctx, model, algorithm, y_arr, init_theta, prior_specs, transforms, tune_control, m, seed,
-                         fixed_num_particles=int(num_particles or 0), consts=consts, obs_times=obs_times, precision=prec)
+                         fixed_num_particles=int(num_particles or 0), consts=consts, obs_times=obs_times, precision=prec,
+                         return_latent_state_est=bool(return_latent_state_est))
     except nat.EngineError as e:
         raise RuntimeError(str(e)) from e
     if (out["status"] == nat.ERR_PRIOR_INIT).any():
@@ -235,8 +240,12 @@ def pmmh(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, log_priors
     result["target_n"] = out["target_n"].copy()
     result["timing_ms"] = {"pilot": out["pilot_ms"], "main": out["main_ms"]}
     if return_latent_state_est:
-        raise NotImplementedError("return_latent_state_est: per-iteration state estimates are not stored "
-                                  "(SURVEY.md 8f rank 3)")
+        # R/pmmh.R:547-552,604-606: per chain a list of the post-burn-in state estimates (vectors of T+1, or
+        # (T+1) x d matrices for multi-dimensional states)
+        lat = out["latent_state_chain"][:, burn_in:]
+        d = lat.shape[-1]
+        result["latent_state_chain"] = [[(lat[c, i, :, 0].copy() if d == 1 else lat[c, i].copy()) for i in range(lat.shape[1])]
+                                        for c in range(num_chains)]
     if print_result:
         print(result)
     if any(np.isfinite(v) and v < 400 for v in param_ess.values()):

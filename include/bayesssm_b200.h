@@ -234,6 +234,7 @@ typedef struct {
   int skip_pilot;            /* 1 => use init_theta as chain start and proposal_chol_in / fixed_num_particles */
   const double *proposal_chol_in; /* [num_chains][p][p] when skip_pilot */
   int engine;                /* BSSM_ENGINE_* for the filter runs */
+  int return_latent_state_est; /* R/pmmh.R return_latent_state_est: fill latent_state_chain */
 } bssm_pmmh_config;
 
 typedef struct {
@@ -249,6 +250,7 @@ typedef struct {
   int32_t *n_accept;           /* [chains] */
   int32_t *status;             /* [chains] */
   float pilot_ms, main_ms;     /* device time of the two phases */
+  double *latent_state_chain;  /* [chains][m][T+1][d] state_est of the filter run behind every draw (R/pmmh.R:420,494-499), or NULL */
 } bssm_pmmh_result;
 
 /* init_theta: [num_chains][p] (pilot_init_params) */

@@ -87,6 +87,7 @@ SEXP _bayesSSM_b200_filter(SEXP cfg_, SEXP y_, SEXP theta_) {
   cfg.seed = (uint64_t)opt_real(cfg_, "seed", 1.0);
   cfg.return_particles = opt_int(cfg_, "return_particles", 1);
   cfg.exact_resampling = -1;
+  cfg.engine = opt_int(cfg_, "engine", BSSM_ENGINE_AUTO);
   SEXP ot = list_get(cfg_, "obs_times");
   if (ot != R_NilValue) cfg.obs_times = INTEGER(ot);
   int d = 1, nth = 0, nc = 0;
@@ -164,6 +165,7 @@ SEXP _bayesSSM_b200_pmmh(SEXP cfg_, SEXP y_, SEXP init_) {
   if (cs != R_NilValue) { cfg.consts = REAL(cs); cfg.nconst = (int)XLENGTH(cs); }
   cfg.precision = opt_int(cfg_, "precision", BSSM_F64);
   cfg.seed = (uint64_t)opt_real(cfg_, "seed", 1.0);
+  cfg.engine = opt_int(cfg_, "engine", BSSM_ENGINE_AUTO);
   const int T = cfg.num_obs, m = cfg.m;
   double *y = (double *)R_alloc((size_t)T * cfg.dy, sizeof(double));
   for (int t = 0; t < T; t++) for (int k = 0; k < cfg.dy; k++) y[(size_t)t * cfg.dy + k] = REAL(y_)[(size_t)k * T + t];
@@ -198,6 +200,66 @@ SEXP _bayesSSM_b200_pmmh(SEXP cfg_, SEXP y_, SEXP init_) {
   return out;
 }
 
+/* ---- particle-sharded single filter: one R process per GPU (e.g. under mpirun / callr workers) ----
+ * .Call("_bayesSSM_b200_shard_unique_id")                  rank 0: raw(128), to be sent to the other ranks
+ * .Call("_bayesSSM_b200_shard_init", rank, world, id)      every rank (device = rank of the process on the node)
+ * .Call("_bayesSSM_b200_shard_filter", cfg, y, theta)      collective; cfg$num_particles is the GLOBAL count */
+SEXP _bayesSSM_b200_shard_unique_id(void) {
+  SEXP id = PROTECT(Rf_allocVector(RAWSXP, 128));
+  int st = bssm_shard_unique_id(NULL, RAW(id));
+  UNPROTECT(1);
+  if (st != BSSM_OK) Rf_error("%s", bssm_last_error());
+  return id;
+}
+SEXP _bayesSSM_b200_shard_init(SEXP rank_, SEXP world_, SEXP id_) {
+  const int rank = Rf_asInteger(rank_), world = Rf_asInteger(world_);
+  if (!g_ctx) { if (bssm_create(rank, &g_ctx) != BSSM_OK) Rf_error("bayesSSM (B200 engine): %s", bssm_last_error()); }
+  if (world > 1 && (TYPEOF(id_) != RAWSXP || XLENGTH(id_) != 128)) Rf_error("id must be the raw(128) of shard_unique_id");
+  if (bssm_shard_init(g_ctx, NULL, rank, world, world > 1 ? RAW(id_) : NULL) != BSSM_OK) Rf_error("%s", bssm_last_error());
+  return R_NilValue;
+}
+SEXP _bayesSSM_b200_shard_filter(SEXP cfg_, SEXP y_, SEXP theta_) {
+  bssm_ctx *ctx = ctx_get();
+  bssm_filter_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.model = opt_int(cfg_, "model", 0);
+  cfg.algorithm = BSSM_BPF;
+  cfg.resample_algorithm = opt_int(cfg_, "resample_algorithm", BSSM_SISAR);
+  cfg.resample_fn = opt_int(cfg_, "resample_fn", BSSM_STRATIFIED);
+  cfg.threshold = opt_real(cfg_, "threshold", -1.0);
+  cfg.num_particles = opt_int(cfg_, "num_particles", 0);
+  cfg.num_obs = Rf_isMatrix(y_) ? Rf_nrows(y_) : (int)XLENGTH(y_);
+  cfg.dy = Rf_isMatrix(y_) ? Rf_ncols(y_) : 1;
+  cfg.num_filters = 1;
+  cfg.precision = opt_int(cfg_, "precision", BSSM_F32);
+  cfg.seed = (uint64_t)opt_real(cfg_, "seed", 1.0);
+  cfg.engine = BSSM_ENGINE_STREAM;
+  const int T = cfg.num_obs;
+  double *y = (double *)R_alloc((size_t)T * cfg.dy, sizeof(double));
+  for (int t = 0; t < T; t++) for (int k = 0; k < cfg.dy; k++) y[(size_t)t * cfg.dy + k] = REAL(y_)[(size_t)k * T + t];
+  SEXP state_est = PROTECT(Rf_allocVector(REALSXP, T + 1)), ess = PROTECT(Rf_allocVector(REALSXP, T + 1));
+  SEXP llh = PROTECT(Rf_allocVector(REALSXP, T));
+  double loglike = 0.0;
+  int32_t status = 0, early = 0, nres = 0;
+  int nloc = 0;
+  bssm_filter_result res;
+  memset(&res, 0, sizeof(res));
+  res.loglike = &loglike; res.loglike_history = REAL(llh); res.ess = REAL(ess); res.state_est = REAL(state_est);
+  res.status = &status; res.early_exit = &early; res.n_resampled = &nres;
+  int st = bssm_filter_run_sharded(ctx, &cfg, y, REAL(theta_), opt_real(cfg_, "capacity_factor", 1.5), &res, &nloc);
+  if (st != BSSM_OK) { UNPROTECT(3); Rf_error("%s", bssm_last_error()); }
+  if (status == BSSM_ERR_CAPACITY) { UNPROTECT(3); Rf_error("a rank's share of the offspring outgrew its storage; raise capacity_factor"); }
+  if (status == BSSM_ERR_NAN_WEIGHT) { UNPROTECT(3); Rf_error("missing value where TRUE/FALSE needed"); }
+  const char *names[] = {"state_est", "ess", "loglike", "loglike_history", "early_exit", "n_resampled", "n_local", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(out, 0, state_est); SET_VECTOR_ELT(out, 1, ess);
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(loglike)); SET_VECTOR_ELT(out, 3, llh);
+  SET_VECTOR_ELT(out, 4, Rf_ScalarLogical(early)); SET_VECTOR_ELT(out, 5, Rf_ScalarInteger(nres));
+  SET_VECTOR_ELT(out, 6, Rf_ScalarInteger(nloc));
+  UNPROTECT(4);
+  return out;
+}
+
 SEXP _bayesSSM_b200_device_info(void) {
   char name[256];
   int sm = 0, maj = 0, mnr = 0;
@@ -213,6 +275,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bayesSSM_b200_filter", (DL_FUNC)&_bayesSSM_b200_filter, 3},
     {"_bayesSSM_b200_pmmh", (DL_FUNC)&_bayesSSM_b200_pmmh, 3},
     {"_bayesSSM_b200_device_info", (DL_FUNC)&_bayesSSM_b200_device_info, 0},
+    {"_bayesSSM_b200_shard_unique_id", (DL_FUNC)&_bayesSSM_b200_shard_unique_id, 0},
+    {"_bayesSSM_b200_shard_init", (DL_FUNC)&_bayesSSM_b200_shard_init, 3},
+    {"_bayesSSM_b200_shard_filter", (DL_FUNC)&_bayesSSM_b200_shard_filter, 3},
     {NULL, NULL, 0}};
 
 void R_init_bayesSSM(DllInfo *dll) { /* replaces src/RcppExports.cpp:57-60 */
@@ -221,5 +286,5 @@ void R_init_bayesSSM(DllInfo *dll) { /* replaces src/RcppExports.cpp:57-60 */
 }
 void R_unload_bayesSSM(DllInfo *dll) {
   (void)dll;
-  if (g_ctx) { bssm_destroy(g_ctx); g_ctx = NULL; }
+  if (g_ctx) { bssm_shard_finalize(g_ctx); bssm_destroy(g_ctx); g_ctx = NULL; }
 }

@@ -1,0 +1,4 @@
+#include <stddef.h>
+#include <stdint.h>
+void *R_alloc(size_t, int); double unif_rand(void); void GetRNGstate(void); void PutRNGstate(void);
+void Rf_error(const char*, ...);

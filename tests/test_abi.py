@@ -48,3 +48,21 @@ def test_host_side_transforms_match_oracle(orc):
         for x in (-0.5, 0.0, 0.3, 1.0, 2.5):
             u, v = lib.bssm_log_prior(kind, a, b, x), orc.log_prior(kind, a, b, x)
             assert u == v or abs(u - v) < 1e-15
+
+
+def test_r_shim_compiles_against_stub_r_headers():
+    """R is not installed here: the .Call shim is at least type-checked against the ABI header and a minimal
+    restatement of the R C API declarations it uses."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "r_stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r_shim", "src", "bssm_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every routine the shim registers exists in the file, and every bssm_* it calls is declared in the header
+    src = open(os.path.join(ROOT, "r_shim", "src", "bssm_shim.c")).read()
+    called = set(re.findall(r"\b(bssm_[a-z_0-9]+)\s*\(", src))
+    assert called <= set(_header_symbols()), called - set(_header_symbols())

@@ -128,3 +128,47 @@ def test_pmmh_posterior_recovers_parameters():
     # the total innovation scale
     tot = np.sqrt(tc["sigma_x"] ** 2 + tc["sigma_y"] ** 2).mean()
     assert abs(tc["phi"].mean() - 0.8) < 0.4 and abs(tc["sigma_x"].mean() - 1.0) < 0.5 and abs(tot - np.sqrt(2.0)) < 0.5
+
+
+def test_pmmh_return_latent_state_est(orc, engine):
+    """R/pmmh.R:420,494-499,604-606: the state estimate of the filter run behind every draw travels with the chain.
+    Checked against oracle filter runs at the accepted draws (same Philox ids: run_id = main phase << 28 | iteration,
+    stream = global chain id), and carried over unchanged on rejections."""
+    import bayesssm_b200 as b
+    from bayesssm_b200.pmmh import default_tune_control, run_chains
+    from bayesssm_b200 import _native as nat
+    rng = np.random.default_rng(1405)
+    x, ys = rng.standard_normal(), []
+    for _ in range(10):
+        x = 0.8 * x + np.sin(x) + rng.standard_normal()
+        ys.append(x + 0.5 * rng.standard_normal())
+    y = np.array(ys)
+    mdl = b.models.nonlinear_ar()
+    pri = [b.priors.uniform(0, 1), b.priors.exponential(1), b.priors.exponential(1)]
+    init = np.array([[0.8, 1.0, 0.5], [0.6, 0.8, 0.7]])
+    chol = np.tile(np.diag([0.3, 0.2, 0.2]), (2, 1, 1))
+    m, N, seed = 25, 300, 11
+    out = run_chains(engine, mdl, nat.BPF, y, init, pri, [nat.TR_LOGIT, nat.TR_LOG, nat.TR_LOG], default_tune_control(), m,
+                     seed, chain_id_base=7, fixed_num_particles=N, precision=nat.F64, skip_pilot=True, proposal_chol=chol,
+                     return_latent_state_est=True)
+    lat, th = out["latent_state_chain"], out["theta_chain"]
+    assert lat.shape == (2, m, len(y) + 1, 1)
+    moved = 0
+    for c in range(2):
+        for i in range(m):
+            if i > 0 and np.array_equal(th[c, i], th[c, i - 1]):
+                np.testing.assert_array_equal(lat[c, i], lat[c, i - 1])       # rejected: carried over
+                continue
+            ref = orc.particle_filter(0, 0, 2, 0, N, y, th[c, i], seed=seed, run_id=(3 << 28) | i, stream=7 + c)
+            np.testing.assert_allclose(lat[c, i, :, 0], ref["state_est"][:, 0], rtol=1e-9, atol=1e-12)
+            moved += 1
+    assert moved > 4
+    # user-facing form: a list per chain of post-burn-in vectors
+    res = b.pmmh(b.bootstrap_filter, y, m=12, init_fn=mdl.init_fn, transition_fn=mdl.transition_fn,
+                 log_likelihood_fn=mdl.log_likelihood_fn,
+                 log_priors={"phi": pri[0], "sigma_x": pri[1], "sigma_y": pri[2]},
+                 pilot_init_params=[{"phi": .8, "sigma_x": 1., "sigma_y": .5}] * 2, burn_in=2, num_chains=2,
+                 tune_control=dict(default_tune_control(), pilot_m=20, pilot_n=50, pilot_reps=4),
+                 return_latent_state_est=True, seed=5, ctx=engine, print_result=False)
+    assert len(res["latent_state_chain"]) == 2 and len(res["latent_state_chain"][0]) == 10
+    assert res["latent_state_chain"][0][0].shape == (len(y) + 1,)
