@@ -21,7 +21,7 @@ static int fast_ppt_choice(int nb_max) {
   return nb_max >= 2048 ? 16 : 8;
 }
 
-template <typename Model, typename Real, int PPT>
+template <typename Model, typename Real, int PPT, bool HEADS>
 static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G) {
   const int nsm = ctx->prop.multiProcessorCount;
   int nb_max = (f.N + G - 1) / G;
@@ -29,9 +29,12 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   if (nb_max > FAST_MAX_NB) { set_error("persistent kernel: %d particles per CTA exceed %d", nb_max, FAST_MAX_NB); return BSSM_ERR_UNSUPPORTED; }
   int threads = (nb_max / PPT + 31) / 32 * 32;
   if (threads < 32) threads = 32;
-  const int cap = (nb_max + FAST_SLACK + 31) / 32 * 32;   // multiple of 32: the bank swizzle permutes within 32-word blocks
+  // staging capacity of one expansion pass: PPT * 5/4 output slots per thread (25 % beyond the slice; more offspring
+  // than that take further passes)
+  const int cap = HEADS ? threads * fast_spt(PPT) : (nb_max + FAST_SLACK + 31) / 32 * 32;
   size_t smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
-  auto kern = k_fast_bpf<Model, Real, PPT>;
+  if (HEADS) smem += (size_t)cap * sizeof(unsigned int) + (size_t)threads * PPT * sizeof(Real);   // head array + the CTA's particles
+  auto kern = k_fast_bpf<Model, Real, PPT, HEADS>;
   BSSM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   BSSM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -89,9 +92,11 @@ static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   if (G > FAST_MAX_G) G = FAST_MAX_G;
   if (G < 1) G = 1;
   const int nb = (f.N + G - 1) / G;
-  if (L.precision == BSSM_F64) return fast_launch<Model, double, 8>(ctx, f, L, G);
-  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16>(ctx, f, L, G);
-  return fast_launch<Model, float, 8>(ctx, f, L, G);
+  // expansion of the offspring: head flags + running maximum on small slices (8 particles per thread), per-source
+  // scatter loops on big ones (profiles/r1_ab_experiments.md)
+  if (L.precision == BSSM_F64) return nb <= 2048 ? fast_launch<Model, double, 8, true>(ctx, f, L, G) : fast_launch<Model, double, 8, false>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, false>(ctx, f, L, G);
+  return fast_launch<Model, float, 8, true>(ctx, f, L, G);
 }
 
 int fast_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {

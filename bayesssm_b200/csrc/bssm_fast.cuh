@@ -40,6 +40,8 @@ constexpr int FAST_MAX_G = 256;      // CTAs per group
 constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
 constexpr int FAST_HEAVY = 64;       // offspring count above which a source is expanded cooperatively
 constexpr int FAST_HEAVY_CAP = 64;
+// output slots per thread of one expansion pass: 25 % beyond the slice, rounded up to whole 16-byte accesses
+__host__ __device__ constexpr int fast_spt(int ppt) { return (ppt * 5 / 4 + 3) & ~3; }
 
 // LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
 // 16-byte volatile access.  A reader that sees the expected tag also sees the data: no fence, no
@@ -141,7 +143,7 @@ struct SlotCounter {
   }
 };
 
-template <typename Model, typename Real, int PPT>
+template <typename Model, typename Real, int PPT, bool HEADS>
 __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P) {
   static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
                 "persistent kernel: 1-D models with one normal per transition");
@@ -157,7 +159,12 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
   double* s_red = s_tab + ((5 * G + 1) & ~1);        // [5][32] per-warp partials (16-byte aligned)
   Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
   unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
+  unsigned int* s_head = s_u + P.cap;                // [cap] (HEADS only) expansion: (source index << 16 | index of its x in s_x) at the first slot of a source
+  Real* s_x = (Real*)(s_head + P.cap);               // [blockDim.x * PPT] this CTA's particles, [PPT/4][threads] x 16 B (conflict-free)
+  constexpr int SPT = fast_spt(PPT);                 // output slots per thread in the expansion: cap = blockDim.x * SPT
+  static_assert(SPT % 4 == 0, "16-byte accesses to the head / staging arrays");
   __shared__ int s_wf[32];
+  __shared__ unsigned int s_wh[32];
   __shared__ int s_heavy_n;
   __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
   __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
@@ -217,6 +224,10 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
     int n_resampled = 0;
     double loglike = 0.0;   // meaningful in thread 0 of CTA 0
     if (tid == 0) { s_heavy_n = 0; s_pending = 0.0; }
+    if constexpr (HEADS) {
+#pragma unroll
+      for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;   // every thread keeps its own slots of the head array clear
+    }
     int pending_obs = -1;   // observation whose resampled state estimate is still to be written
     // t = 0 state estimate: block sum -> record; CTA 0 gathers
     {
@@ -502,10 +513,89 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
       }
       FAST_TICK(6);   // offspring ranges + prefix max
-      // ---- P4: scatter into the staging buffer (chunks of `cap` slots), copy out coalesced ----
+      // ---- P4: expansion, output-centric (chunks of `cap` slots).  Every source with offspring in the chunk marks the
+      //      first of its slots with (source index, index of its x in s_x); a running maximum over the slots -- source
+      //      indices grow with the slot -- tells every slot its source: O(1) per source and per slot, no loop over
+      //      the offspring of a source, no special case for heavy sources.  The chosen x are staged and leave the
+      //      SM as coalesced 16-byte stores ----
+      //      HEADS = false (big slices, 16 particles per thread): per-source scatter loops into the staging buffer --
+      //      measured 2 % faster there (the expansion pays two more barriers), 20 % slower on small slices ----
       {
-        const int o_base = o_lo & ~3;
         Real sumx = 0;
+        if constexpr (HEADS) {
+        const int o_base = o_lo & ~3;
+        const int nthr = blockDim.x;
+        // this CTA's particles into shared memory (the registers are reloaded from x_new below)
+#pragma unroll
+        for (int h4 = 0; h4 < PPT / 4; h4++) {
+          if (F32) *(float4*)&s_x[(h4 * nthr + tid) * 4] = make_float4((float)x[4 * h4], (float)x[4 * h4 + 1], (float)x[4 * h4 + 2], (float)x[4 * h4 + 3]);
+          else { s_x[(h4 * nthr + tid) * 4] = x[4 * h4]; s_x[(h4 * nthr + tid) * 4 + 1] = x[4 * h4 + 1]; s_x[(h4 * nthr + tid) * 4 + 2] = x[4 * h4 + 2]; s_x[(h4 * nthr + tid) * 4 + 3] = x[4 * h4 + 3]; }
+        }
+        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
+          const int c1 = min(o_hi, c0 + P.cap);
+          int lo_k = prevF;
+#pragma unroll
+          for (int k = 0; k < PPT; k++) {
+            const int hi_k = F[k];
+            const int a = max(lo_k, c0);
+            if (min(hi_k, c1) > a) s_head[a - c0] = ((unsigned int)(tid * PPT + k) << 16) | (unsigned int)(((k >> 2) * nthr + tid) * 4 + (k & 3));
+            if (c0 == o_base && hi_k > lo_k) {
+              // count as a float without a conversion instruction (exact below 2^23)
+              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
+              sumx += (Real)cf * x[k];
+            }
+            lo_k = max(lo_k, hi_k);
+          }
+          __syncthreads();
+          unsigned int hd[SPT];
+#pragma unroll
+          for (int i = 0; i < SPT; i += 4) { const uint4 v4 = *(const uint4*)&s_head[tid * SPT + i]; hd[i] = v4.x; hd[i + 1] = v4.y; hd[i + 2] = v4.z; hd[i + 3] = v4.w; }
+#pragma unroll
+          for (int i = 0; i < SPT; i += 4) *(uint4*)&s_head[tid * SPT + i] = make_uint4(0u, 0u, 0u, 0u);   // clear for the next chunk / step
+#pragma unroll
+          for (int i = 1; i < SPT; i++) hd[i] = max(hd[i], hd[i - 1]);
+          unsigned int inc = hd[SPT - 1];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+          if (lane == 31) s_wh[wid] = inc;
+          unsigned int carry = __shfl_up_sync(0xffffffffu, inc, 1);
+          if (lane == 0) carry = 0u;
+          __syncthreads();
+          {
+            unsigned int wv = lane < nw ? s_wh[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, wv, o); if (lane >= o) wv = max(wv, t); }
+            const unsigned int wprev = __shfl_sync(0xffffffffu, wv, (wid + 31) & 31);
+            if (wid > 0) carry = max(carry, wprev);
+          }
+          Real val[SPT];
+#pragma unroll
+          for (int i = 0; i < SPT; i++) val[i] = s_x[max(hd[i], carry) & 0xFFFFu];
+#pragma unroll
+          for (int i = 0; i < SPT; i += 4) {
+            if (F32) *(float4*)&s_out[tid * SPT + i] = make_float4((float)val[i], (float)val[i + 1], (float)val[i + 2], (float)val[i + 3]);
+            else { s_out[tid * SPT + i] = val[i]; s_out[tid * SPT + i + 1] = val[i + 1]; s_out[tid * SPT + i + 2] = val[i + 2]; s_out[tid * SPT + i + 3] = val[i + 3]; }
+          }
+          __syncthreads();
+          // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
+          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
+          const unsigned int tag = ep2 + 1;
+          if (F32) {
+            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
+              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
+              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+              else {
+                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
+                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
+              }
+            }
+          } else {
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
+          }
+          __syncthreads();
+        }
+        } else {
+        const int o_base = o_lo & ~3;
         for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
           const int c1 = min(o_hi, c0 + P.cap);
           int lo_k = prevF;
@@ -554,6 +644,7 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
           }
           if (tid == 0) s_heavy_n = 0;
           __syncthreads();
+        }
         }
         // block sum of the chosen x: travels in the next record (state estimate after resampling)
         double v = warp_sum_d((double)sumx);
