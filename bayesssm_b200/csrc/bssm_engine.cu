@@ -227,11 +227,11 @@ int resolve_engine(bssm_ctx* ctx, const FilterDev& f_in, const FilterLaunch& L, 
   f.anc_history = want_anc ? (int*)1 : nullptr;
   if (L.engine == BSSM_ENGINE_GENERAL) return BSSM_ENGINE_GENERAL;
   if (L.engine == BSSM_ENGINE_PERSISTENT) return fast_supported(f, L) ? BSSM_ENGINE_PERSISTENT : -1;
-  if (L.engine == BSSM_ENGINE_STREAM) return stream_supported(f, L) ? BSSM_ENGINE_STREAM : -1;
+  if (L.engine == BSSM_ENGINE_STREAM) return stream_supported(ctx, f, L) ? BSSM_ENGINE_STREAM : -1;
   if (L.precision != BSSM_F32) return BSSM_ENGINE_GENERAL;
   // the persistent kernel needs the CTAs of a filter co-resident: at most one full slice per SM
   const bool fast_ok = fast_supported(f, L) && (long long)f.N <= (long long)ctx->prop.multiProcessorCount * FAST_MAX_NB;
-  const bool stream_ok = stream_supported(f, L);
+  const bool stream_ok = stream_supported(ctx, f, L);
   const long long total = (long long)f.C * f.N;
   // measured on B200 (scripts/bench_engines.py): 1024 x 65536 streaming +30 %, 4 x 2^20 +29 %; 256 x 65536 a tie;
   // smaller batches and slices belong to the persistent kernel

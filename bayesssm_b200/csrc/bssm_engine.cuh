@@ -53,10 +53,14 @@ struct Scratch { void* p = nullptr; size_t cap = 0; };
 // handles of the model-dependent kernels of the general engine (built-in: function addresses;
 // NVRTC user model: cudaKernel_t from the compiled library)
 struct ModelKernels { void *init = nullptr, *weight = nullptr, *post = nullptr; bool has_aux = false, has_move = false; };
+// handles of the streaming engine's kernels (bssm_stream.cuh): k_st_init, k_st_step, k_st_resample, k_st_flush
+struct StreamKernels { void *init = nullptr, *step = nullptr, *resample = nullptr, *flush = nullptr; };
 constexpr int BSSM_USER_MODEL_BASE = 1000;
 struct UserModelInfo {
   void* library = nullptr;   // cudaLibrary_t
   ModelKernels k32, k64;
+  StreamKernels s32, s64;    // streaming engine (valid when stream_ok)
+  bool stream_ok = false;    // 1-D state, one normal per init / transition, no uniforms
   int dims[12];              // D, NTHETA, NCONST, NZ_INIT, NU_INIT, NZ_TRANS, NU_TRANS, NZ_MOVE, NU_MOVE, HAS_AUX, HAS_MOVE, NPAR
 };
 
@@ -126,7 +130,7 @@ struct ShardRun {
   int nloc0;
   int cap;           // storage capacity of this rank (particles)
 };
-bool stream_supported(const FilterDev& f, const FilterLaunch& L);
+bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L);
 int stream_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh);
 int shard_allgather(bssm_ctx* ctx, const ShardRun* sh, const void* d_send, void* d_recv, size_t bytes_per_rank);
 // NVRTC user models (bssm_nvrtc.cu)

@@ -162,7 +162,7 @@ int bssm_filter_run_sharded(bssm_ctx* ctx, const bssm_filter_config* cfg, const 
   FilterLaunch L;
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn; L.exact = 0; L.hist = 0; L.T = T;
   L.engine = BSSM_ENGINE_STREAM;
-  if (!stream_supported(f, L)) { set_error("sharded filter: bootstrap filter of a 1-D built-in model with stratified / systematic resampling only"); return BSSM_ERR_UNSUPPORTED; }
+  if (!stream_supported(ctx, f, L)) { set_error("sharded filter: bootstrap filter of a 1-D built-in model with stratified / systematic resampling only"); return BSSM_ERR_UNSUPPORTED; }
   // per-filter scalars and outputs (the particle arrays belong to the streaming engine)
   double* sd; int* si;
   BSSM_TRY(scratch(ctx, SL_F_SCAL_D, (size_t)C * 4, &sd));

@@ -10,15 +10,28 @@
 
 namespace bssm {
 
-bool stream_supported(const FilterDev& f, const FilterLaunch& L) {
+bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L) {
   if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history) return false;
   if (L.resample_fn == BSSM_MULTINOMIAL) return false;
+  if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC user model: its shape decides (bssm_nvrtc.cu)
+    const UserModelInfo* u = user_model(ctx, L.model);
+    return u && u->stream_ok;
+  }
   if (!(L.model == BSSM_MODEL_AR_SIN || L.model == BSSM_MODEL_LG || L.model == BSSM_MODEL_AR_COS || L.model == BSSM_MODEL_RW_DRIFT)) return false;
   return true;
 }
 
-template <typename Model, typename Real, int PPT>
-static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh) {
+// kernels are launched through handles, so that built-in models (function addresses) and NVRTC-compiled user
+// models (cudaKernel_t of the compiled library) share one orchestration
+static int st_launch(bssm_ctx* ctx, void* kern, dim3 grid, StreamParams& P, int* obs, const char* what) {
+  void* args[] = {&P, obs};
+  BSSM_CK(cudaLaunchKernel(kern, grid, dim3(ST_THREADS), args, 0, ctx->stream));
+  BSSM_LAUNCH(ctx, what);
+  return BSSM_OK;
+}
+
+template <typename Real, int PPT>
+static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh, const StreamKernels& K) {
   constexpr int TS = ST_THREADS * PPT;
   cudaStream_t st = ctx->stream;
   StreamParams P;
@@ -39,11 +52,11 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   // contiguous range of tiles; among a few candidates take the one with the fewest rounds (waves x tiles
   // per block).  The three kernels share the block -> tile ranges, so the scarcer kernel sets the slots.
   {
-    int ps = 1, pr = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)k_st_step<Model, Real, PPT>, ST_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr, (const void*)k_st_resample<Model, Real, PPT>, ST_THREADS, 0);
+    int ps = 0, pr = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)K.step, ST_THREADS, 0) != cudaSuccess) { ps = 0; cudaGetLastError(); }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr, (const void*)K.resample, ST_THREADS, 0) != cudaSuccess) { pr = 0; cudaGetLastError(); }
     int per_sm = ps < pr ? ps : pr;
-    if (per_sm < 1) per_sm = 1;
+    if (per_sm < 1) per_sm = 4;   // the kernels are built for 4 blocks per SM (__launch_bounds__)
     const long long slots = (long long)per_sm * ctx->prop.multiProcessorCount;
     long long b0 = (slots + C - 1) / C;
     const long long bmin = (P.nt + ST_MAX_TPB - 1) / ST_MAX_TPB;   // at most ST_MAX_TPB tiles per block
@@ -85,20 +98,21 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   k_st_setup<<<(C + 127) / 128, 128, 0, st>>>(P, goff0, nloc0);
   BSSM_LAUNCH(ctx, "k_st_setup");
   const dim3 grid((unsigned int)((size_t)P.bpc * C));   // block index within the filter fastest
-  k_st_init<Model, Real, PPT><<<grid, ST_THREADS, 0, st>>>(P);
-  BSSM_LAUNCH(ctx, "k_st_init");
+  {
+    void* args[] = {&P};
+    BSSM_CK(cudaLaunchKernel(K.init, grid, dim3(ST_THREADS), args, 0, st));
+    BSSM_LAUNCH(ctx, "k_st_init");
+  }
   const bool may_resample = f.ralg != BSSM_SIS;
   for (int obs = 0; obs < L.T; obs++) {
-    k_st_step<Model, Real, PPT><<<grid, ST_THREADS, 0, st>>>(P, obs);
-    BSSM_LAUNCH(ctx, "k_st_step");
+    BSSM_TRY(st_launch(ctx, K.step, grid, P, &obs, "k_st_step"));
     if (sh) {
       BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
       k_st_merge<<<(C + 127) / 128, 128, 0, st>>>(P, obs);
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      k_st_resample<Model, Real, PPT><<<grid, ST_THREADS, 0, st>>>(P, obs);
-      BSSM_LAUNCH(ctx, "k_st_resample");
+      BSSM_TRY(st_launch(ctx, K.resample, grid, P, &obs, "k_st_resample"));
     }
   }
   if (P.dbg) {
@@ -118,13 +132,24 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   return BSSM_OK;
 }
 
+template <typename Model, typename Real, int PPT> static StreamKernels builtin_stream_kernels() {
+  StreamKernels K;
+  K.init = (void*)k_st_init<Model, Real, PPT>; K.step = (void*)k_st_step<Model, Real, PPT>; K.resample = (void*)k_st_resample<Model, Real, PPT>;
+  return K;
+}
 template <typename Model>
 static int stream_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh) {
-  if (L.precision == BSSM_F64) return stream_launch<Model, double, 4>(ctx, f, L, sh);
-  return stream_launch<Model, float, 8>(ctx, f, L, sh);
+  if (L.precision == BSSM_F64) return stream_launch<double, 4>(ctx, f, L, sh, builtin_stream_kernels<Model, double, 4>());
+  return stream_launch<float, 8>(ctx, f, L, sh, builtin_stream_kernels<Model, float, 8>());
 }
 
 int stream_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh) {
+  if (L.model >= BSSM_USER_MODEL_BASE) {
+    const UserModelInfo* u = user_model(ctx, L.model);
+    if (!u || !u->stream_ok) { set_error("streaming engine: user model %d not supported (1-D state, one normal per init / transition)", L.model); return BSSM_ERR_UNSUPPORTED; }
+    if (L.precision == BSSM_F64) return stream_launch<double, 4>(ctx, f, L, sh, u->s64);
+    return stream_launch<float, 8>(ctx, f, L, sh, u->s32);
+  }
   switch (L.model) {
     case BSSM_MODEL_AR_SIN: return stream_model<ModelArSin>(ctx, f, L, sh);
     case BSSM_MODEL_LG: return stream_model<ModelLG>(ctx, f, L, sh);

@@ -30,9 +30,9 @@
 // offset goff (goff = 0 when the filter is not sharded).
 #pragma once
 #include "bssm_common.cuh"
-#include "bssm_fast.cuh"
 #include "bssm_filter.cuh"
 #include "bssm_models.cuh"
+#include "bssm_slots.cuh"
 
 namespace bssm {
 
@@ -385,8 +385,8 @@ template <typename Real> __device__ __forceinline__ Real st_warp_max(Real v) {
 // the parameter set-up and the fence + ticket once, not once per tile.
 template <typename Model, typename Real, int PPT>
 __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int obs) {
-  static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
-                "streaming engine: 1-D models with one normal per transition");
+  // serves 1-D models with one normal per init / transition and no uniforms; checked on the host (stream_supported),
+  // because NVRTC instantiates these kernels for every user model whatever its shape
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr int TS = ST_THREADS * PPT;
   __shared__ uint4 s_pf[2][2 * ST_THREADS];

@@ -107,3 +107,41 @@ def test_compile_error_is_reported(engine):
     assert st == nat.ERR_NVRTC
     assert "error" in nat.last_error().lower()
     assert b"user_model.cu" in engine.lib.bssm_model_compile_log(engine.handle)
+
+
+def test_snippets_run_on_the_streaming_engine(orc, engine):
+    """The streaming engine's kernels are compiled by NVRTC together with the snippet: the README model as a snippet
+    reproduces the built-in model bit for bit on that engine too, a new model agrees with the general kernels, and
+    AUTO sends f32 bootstrap filters of an eligible snippet there (2 launches per observation, not ~10)."""
+    ST = nat.ENGINE_STREAM
+    mid, sv = C.c_int(), C.c_int()
+    nat.check(engine.lib.bssm_model_compile(engine.handle, AR_SNIPPET.encode(), C.byref(mid)))
+    nat.check(engine.lib.bssm_model_compile(engine.handle, SV_SNIPPET.encode(), C.byref(sv)))
+    rng = np.random.default_rng(3)
+    y = sim_y(0, 25, rng)
+    th = [0.8, 1.0, 0.5]
+    for prec in (nat.F64, nat.F32):
+        for N in (3000, 70001):
+            usr = eh.filter_run(engine, mid.value, 0, 2, 0, N, y, th, seed=5, stream_base=2, precision=prec, engine=ST)
+            blt = eh.filter_run(engine, 0, 0, 2, 0, N, y, th, seed=5, stream_base=2, precision=prec, engine=ST)
+            assert usr["status"][0] == 0
+            assert usr["loglike"][0] == blt["loglike"][0] and np.array_equal(usr["state_est"], blt["state_est"])
+            assert np.array_equal(usr["ess"], blt["ess"])
+    ref = orc.particle_filter(0, 0, 2, 0, 3000, y, th, seed=5, stream=2)
+    usr = eh.filter_run(engine, mid.value, 0, 2, 0, 3000, y, th, seed=5, stream_base=2, precision=nat.F64, engine=ST)
+    assert abs(usr["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])
+    # stochastic volatility: streaming engine against the general kernels, same Philox streams
+    ysv = 0.6 * rng.standard_normal(40)
+    thv = [-1.0, 0.95, 0.25]
+    a = eh.filter_run(engine, sv.value, 0, 2, 1, 50000, ysv, thv, seed=8, precision=nat.F64, engine=ST)
+    g = eh.filter_run(engine, sv.value, 0, 2, 1, 50000, ysv, thv, seed=8, precision=nat.F64, engine=nat.ENGINE_GENERAL)
+    assert a["n_resampled"][0] == g["n_resampled"][0]
+    assert abs(a["loglike"][0] - g["loglike"][0]) <= 1e-9 * abs(g["loglike"][0])
+    np.testing.assert_allclose(a["state_est"][0], g["state_est"][0], rtol=1e-8, atol=1e-9)
+    n0 = engine.launch_count()
+    f = eh.filter_run(engine, sv.value, 0, 2, 0, 1 << 18, ysv, thv, seed=8, precision=nat.F32)   # AUTO
+    assert engine.launch_count() - n0 < 2 * 40 + 12
+    assert abs(f["loglike"][0] - g["loglike"][0]) < 0.3
+    # APF / injected noise / 2-D models stay on the general kernels; asking for the streaming engine there is an error
+    with pytest.raises(nat.EngineError):
+        eh.filter_run(engine, sv.value, 1, 2, 0, 1000, ysv, thv, seed=8, precision=nat.F32, engine=ST)
