@@ -233,9 +233,9 @@ int resolve_engine(bssm_ctx* ctx, const FilterDev& f_in, const FilterLaunch& L, 
   const bool fast_ok = fast_supported(f, L) && (long long)f.N <= (long long)ctx->prop.multiProcessorCount * FAST_MAX_NB;
   const bool stream_ok = stream_supported(ctx, f, L);
   const long long total = (long long)f.C * f.N;
-  // measured on B200 (scripts/bench_engines.py): 1024 x 65536 streaming +30 %, 4 x 2^20 +29 %; 256 x 65536 a tie;
+  // measured on B200 (scripts/bench_engines.py): 1024 x 65536 streaming +41 %, 256 x 65536 +10 %, 4 x 2^20 +29 %;
   // smaller batches and slices belong to the persistent kernel
-  const bool stream_wins = (f.N >= (1 << 19) && f.C >= 4) || (f.N >= 32768 && total >= (1LL << 25));
+  const bool stream_wins = (f.N >= (1 << 19) && f.C >= 4) || (f.N >= 32768 && total >= (1LL << 24));
   if (stream_ok && (!fast_ok || stream_wins)) return BSSM_ENGINE_STREAM;
   if (fast_ok) return BSSM_ENGINE_PERSISTENT;
   return BSSM_ENGINE_GENERAL;

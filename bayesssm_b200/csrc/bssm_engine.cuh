@@ -59,7 +59,7 @@ constexpr int BSSM_USER_MODEL_BASE = 1000;
 struct UserModelInfo {
   void* library = nullptr;   // cudaLibrary_t
   ModelKernels k32, k64;
-  StreamKernels s32, s64;    // streaming engine (valid when stream_ok)
+  StreamKernels s32[2], s64[2];   // streaming engine, [0] 256 / [1] 128 threads per block (valid when stream_ok)
   bool stream_ok = false;    // 1-D state, one normal per init / transition, no uniforms
   int dims[12];              // D, NTHETA, NCONST, NZ_INIT, NU_INIT, NZ_TRANS, NU_TRANS, NZ_MOVE, NU_MOVE, HAS_AUX, HAS_MOVE, NPAR
 };

@@ -23,15 +23,16 @@ bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L) 
 
 // kernels are launched through handles, so that built-in models (function addresses) and NVRTC-compiled user
 // models (cudaKernel_t of the compiled library) share one orchestration
-static int st_launch(bssm_ctx* ctx, void* kern, dim3 grid, StreamParams& P, int* obs, const char* what) {
+static int st_launch(bssm_ctx* ctx, void* kern, dim3 grid, int threads, StreamParams& P, int* obs, const char* what) {
   void* args[] = {&P, obs};
-  BSSM_CK(cudaLaunchKernel(kern, grid, dim3(ST_THREADS), args, 0, ctx->stream));
+  BSSM_CK(cudaLaunchKernel(kern, grid, dim3(threads), args, 0, ctx->stream));
   BSSM_LAUNCH(ctx, what);
   return BSSM_OK;
 }
 
-template <typename Real, int PPT>
+template <typename Real, int PPT, int THREADS>
 static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh, const StreamKernels& K) {
+  constexpr int ST_THREADS = THREADS;
   constexpr int TS = ST_THREADS * PPT;
   cudaStream_t st = ctx->stream;
   StreamParams P;
@@ -56,7 +57,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)K.step, ST_THREADS, 0) != cudaSuccess) { ps = 0; cudaGetLastError(); }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr, (const void*)K.resample, ST_THREADS, 0) != cudaSuccess) { pr = 0; cudaGetLastError(); }
     int per_sm = ps < pr ? ps : pr;
-    if (per_sm < 1) per_sm = 4;   // the kernels are built for 4 blocks per SM (__launch_bounds__)
+    if (per_sm < 1) per_sm = 1024 / ST_THREADS;   // the kernels are built for 1024 threads per SM (__launch_bounds__)
     const long long slots = (long long)per_sm * ctx->prop.multiProcessorCount;
     long long b0 = (slots + C - 1) / C;
     const long long bmin = (P.nt + ST_MAX_TPB - 1) / ST_MAX_TPB;   // at most ST_MAX_TPB tiles per block
@@ -105,14 +106,14 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   const bool may_resample = f.ralg != BSSM_SIS;
   for (int obs = 0; obs < L.T; obs++) {
-    BSSM_TRY(st_launch(ctx, K.step, grid, P, &obs, "k_st_step"));
+    BSSM_TRY(st_launch(ctx, K.step, grid, ST_THREADS, P, &obs, "k_st_step"));
     if (sh) {
       BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
       k_st_merge<<<(C + 127) / 128, 128, 0, st>>>(P, obs);
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      BSSM_TRY(st_launch(ctx, K.resample, grid, P, &obs, "k_st_resample"));
+      BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample"));
     }
   }
   if (P.dbg) {
@@ -122,7 +123,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     fprintf(stderr, "[bssm stream timing] last k_st_step, merging block: %lld cycles until its ticket, merge %lld (max pass %lld, block max %lld, sum pass %lld, prefix pass + rest %lld), global bookkeeping %lld; bpc=%d bpc_r=%d nt=%d\n",
             h[0], h[1], h[4], h[5], h[6], h[7], h[2], P.bpc, P.bpc, P.nt);
   }
-  k_st_flush<TS><<<C, ST_THREADS, 0, st>>>(P, L.T);
+  k_st_flush<TS><<<C, 256, 0, st>>>(P, L.T);
   BSSM_LAUNCH(ctx, "k_st_flush");
   if (sh) {
     BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
@@ -132,23 +133,34 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   return BSSM_OK;
 }
 
-template <typename Model, typename Real, int PPT> static StreamKernels builtin_stream_kernels() {
+template <typename Model, typename Real, int PPT, int THREADS> static StreamKernels builtin_stream_kernels() {
   StreamKernels K;
-  K.init = (void*)k_st_init<Model, Real, PPT>; K.step = (void*)k_st_step<Model, Real, PPT>; K.resample = (void*)k_st_resample<Model, Real, PPT>;
+  K.init = (void*)k_st_init<Model, Real, PPT, THREADS>; K.step = (void*)k_st_step<Model, Real, PPT, THREADS>;
+  K.resample = (void*)k_st_resample<Model, Real, PPT, THREADS>;
   return K;
+}
+// 128 threads per block for batches, 256 for a few big filters (see the note in bssm_stream.cuh)
+static bool stream_small_blocks(const FilterDev& f) {
+  if (const char* e = getenv("BSSM_ST_THREADS")) return atoi(e) == 128;
+  return f.C >= 16;
 }
 template <typename Model>
 static int stream_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh) {
-  if (L.precision == BSSM_F64) return stream_launch<double, 4>(ctx, f, L, sh, builtin_stream_kernels<Model, double, 4>());
-  return stream_launch<float, 8>(ctx, f, L, sh, builtin_stream_kernels<Model, float, 8>());
+  const bool small = stream_small_blocks(f);
+  if (L.precision == BSSM_F64)
+    return small ? stream_launch<double, 4, 128>(ctx, f, L, sh, builtin_stream_kernels<Model, double, 4, 128>())
+                 : stream_launch<double, 4, 256>(ctx, f, L, sh, builtin_stream_kernels<Model, double, 4, 256>());
+  return small ? stream_launch<float, 8, 128>(ctx, f, L, sh, builtin_stream_kernels<Model, float, 8, 128>())
+               : stream_launch<float, 8, 256>(ctx, f, L, sh, builtin_stream_kernels<Model, float, 8, 256>());
 }
 
 int stream_filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, const ShardRun* sh) {
   if (L.model >= BSSM_USER_MODEL_BASE) {
     const UserModelInfo* u = user_model(ctx, L.model);
     if (!u || !u->stream_ok) { set_error("streaming engine: user model %d not supported (1-D state, one normal per init / transition)", L.model); return BSSM_ERR_UNSUPPORTED; }
-    if (L.precision == BSSM_F64) return stream_launch<double, 4>(ctx, f, L, sh, u->s64);
-    return stream_launch<float, 8>(ctx, f, L, sh, u->s32);
+    const int v = stream_small_blocks(f) ? 1 : 0;
+    if (L.precision == BSSM_F64) return v ? stream_launch<double, 4, 128>(ctx, f, L, sh, u->s64[1]) : stream_launch<double, 4, 256>(ctx, f, L, sh, u->s64[0]);
+    return v ? stream_launch<float, 8, 128>(ctx, f, L, sh, u->s32[1]) : stream_launch<float, 8, 256>(ctx, f, L, sh, u->s32[0]);
   }
   switch (L.model) {
     case BSSM_MODEL_AR_SIN: return stream_model<ModelArSin>(ctx, f, L, sh);

@@ -36,8 +36,8 @@
 
 namespace bssm {
 
-constexpr int ST_THREADS = 256;
-constexpr int ST_NW = ST_THREADS / 32;
+// threads per block are a template parameter of the kernels (THREADS): 256 for single big filters (fewer block
+// records to merge), 128 for batches (smaller barrier domains: +6-8 % there, -3 % on single filters)
 constexpr int ST_SLACK = 512;       // staging capacity beyond the tile size
 constexpr int ST_HEAVY = 64;        // offspring count above which a source is expanded cooperatively
 constexpr int ST_HEAVY_CAP = 32;
@@ -221,8 +221,9 @@ static __device__ __noinline__ void st_global(const StreamParams& P, int c, int 
 // (coalesced), every load of a round issued before the first use.  Fixed structure => deterministic.
 // Plain loads: the records were published with fence + ticket and are read after ticket + fence, and no
 // line of them was in this SM's L1 before.
-template <typename Real>
+template <typename Real, int ST_THREADS>
 static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int c, int nb, int nb_pending, double* s_red /*[4][ST_NW]*/, StRec& out) {
+  constexpr int ST_NW = ST_THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
   const size_t row = (size_t)c * P.bpc;
@@ -297,8 +298,9 @@ static __global__ void k_st_setup(StreamParams P, long long goff0, int nloc0) {
 }
 
 // ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, block sums for the t = 0 state estimate ----
-template <typename Model, typename Real, int PPT>
-__global__ void __launch_bounds__(ST_THREADS) k_st_init(StreamParams P) {
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_st_init(StreamParams P) {
+  constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr int TS = ST_THREADS * PPT;
   __shared__ double s_red[ST_NW];
   const FilterDev& f = P.f;
@@ -349,14 +351,14 @@ __device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <typename Real, int PPT>
+template <typename Real, int PPT, int ST_THREADS>
 __device__ __forceinline__ void st_prefetch(uint4* buf /*[2][ST_THREADS]*/, const Real* g) {
   static_assert(PPT * sizeof(Real) == 32, "32 bytes per thread and tile");
   st_cp_async16(&buf[threadIdx.x], g);
   st_cp_async16(&buf[ST_THREADS + threadIdx.x], (const char*)g + 16);
   st_cp_async_commit();
 }
-template <typename Real, int PPT>
+template <typename Real, int PPT, int ST_THREADS>
 __device__ __forceinline__ void st_take(Real* x, const uint4* buf) {
   st_cp_async_wait();
   const uint4 a = buf[threadIdx.x], b = buf[ST_THREADS + threadIdx.x];
@@ -383,8 +385,9 @@ template <typename Real> __device__ __forceinline__ Real st_warp_max(Real v) {
 // Block (c, j) walks the contiguous tiles [j * tpb, (j + 1) * tpb) of filter c; the next tile's particles
 // are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
 // the parameter set-up and the fence + ticket once, not once per tile.
-template <typename Model, typename Real, int PPT>
-__global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int obs) {
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParams P, int obs) {
+  constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   // serves 1-D models with one normal per init / transition and no uniforms; checked on the host (stream_supported),
   // because NVRTC instantiates these kernels for every user model whatever its shape
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
   const int t0 = j * L.tpb, t1 = min(L.ntc, t0 + L.tpb);
   const Real* xin = (const Real*)(rprev ? P.x0 : P.x1) + (size_t)c * P.xstride + tid * PPT;
   Real* xout = (Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
-  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)t0 * TS);
+  st_prefetch<Real, PPT, ST_THREADS>(s_pf[0], xin + (size_t)t0 * TS);
   Real par[Model::NPAR];
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
@@ -418,8 +421,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
   for (int tile = t0; tile < t1; tile++) {
     const int pb = (tile - t0) & 1;
     Real x[PPT];
-    st_take<Real, PPT>(x, s_pf[pb]);
-    if (tile + 1 < t1) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
+    st_take<Real, PPT, ST_THREADS>(x, s_pf[pb]);
+    if (tile + 1 < t1) st_prefetch<Real, PPT, ST_THREADS>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
     const int sbase = tile * TS + tid * PPT;
     const long long g0 = L.goff - L.lead + sbase;
     const int k_lo = (int)max(0LL, min((long long)PPT, L.goff - g0));
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_step(StreamParams P, int o
     nb_pending = obs == 0 ? L.nb : st_make_layout<TS>(sp.goff, sp.nloc, P.bpc).nb;
   }
   StRec r;
-  st_local_merge<Real>(P, c, L.nb, nb_pending, s_red, r);
+  st_local_merge<Real, ST_THREADS>(P, c, L.nb, nb_pending, s_red, r);
   const long long t_merge = P.dbg ? clock64() : 0;
   if (tid == 0) P.counter[c] = 0u;
   if (P.sharded) { if (tid == 0) P.rec_local[c] = r; }
@@ -540,8 +543,9 @@ static __global__ void k_st_merge(StreamParams P, int obs) {
 // Same block -> tile ranges and prefetch as k_st_step.  A block's cdf interval comes from the block prefix
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
 // running sums of the tile partials.
-template <typename Model, typename Real, int PPT>
-__global__ void __launch_bounds__(ST_THREADS, 4) k_st_resample(StreamParams P, int obs) {
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamParams P, int obs) {
+  constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;
   constexpr int CAP = TS + ST_SLACK;
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_resample(StreamParams P, i
   const int lead = L.lead, ntc = L.ntc;
   const int t0 = j * L.tpb, t1 = min(ntc, t0 + L.tpb);
   const Real* xin = (const Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
-  st_prefetch<Real, PPT>(s_pf[0], xin + (size_t)t0 * TS);
+  st_prefetch<Real, PPT, ST_THREADS>(s_pf[0], xin + (size_t)t0 * TS);
   const int n = P.n_glob ? P.n_glob : filt_n(f, c);
   Real par[Model::NPAR];
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
@@ -615,8 +619,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_resample(StreamParams P, i
   const bool ragged = k_lo > 0 || k_hi < PPT;
   const bool special = ragged || (last_s >= tid * PPT && last_s < (tid + 1) * PPT);
   Real x[PPT], e[PPT];
-  st_take<Real, PPT>(x, s_pf[pb]);
-  if (tile + 1 < t1) st_prefetch<Real, PPT>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
+  st_take<Real, PPT, ST_THREADS>(x, s_pf[pb]);
+  if (tile + 1 < t1) st_prefetch<Real, PPT, ST_THREADS>(s_pf[pb ^ 1], xin + (size_t)(tile + 1) * TS);
   Real fs = 0;
   {
     const Real Mr = (Real)M;
@@ -835,7 +839,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_st_resample(StreamParams P, i
 
 // ---- flush: the state estimate of a final resampling (or of the initial particles when T = 0) ----
 template <int TS>
-static __global__ void __launch_bounds__(ST_THREADS) k_st_flush(StreamParams P, int obs /* = T */) {
+static __global__ void __launch_bounds__(256) k_st_flush(StreamParams P, int obs /* = T */) {
+  constexpr int ST_THREADS = 256, ST_NW = 8;
   __shared__ double s_red[ST_NW];
   const FilterDev& f = P.f;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
