@@ -77,8 +77,8 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 0, (size_t)C * P.xstride * rs, &P.x0));
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 1, (size_t)C * P.xstride * rs, &P.x1));
-  BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.nt * 2, &P.tile_m));
-  P.tile_s = P.tile_m + (size_t)C * P.nt;
+  BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.nt * (ST_THREADS / 32) * 2, &P.tile_m));
+  P.tile_s = P.tile_m + (size_t)C * P.nt * (ST_THREADS / 32);
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 3, (size_t)C * (P.bpc + 1), &P.pref));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 4, (size_t)C * P.bpc, &P.bsum));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 10, (size_t)C * P.bpc * 4, &P.blk_m));

@@ -38,9 +38,6 @@ namespace bssm {
 
 // threads per block are a template parameter of the kernels (THREADS): 256 for single big filters (fewer block
 // records to merge), 128 for batches (smaller barrier domains: +6-8 % there, -3 % on single filters)
-constexpr int ST_SLACK = 512;       // staging capacity beyond the tile size
-constexpr int ST_HEAVY = 64;        // offspring count above which a source is expanded cooperatively
-constexpr int ST_HEAVY_CAP = 32;
 constexpr int ST_ERR_CAPACITY = 10; // status: a shard outgrew its storage (BSSM_ERR_CAPACITY)
 constexpr int ST_MAX_TPB = 256;     // tiles per block (k_st_resample keeps their prefix in shared memory)
 
@@ -63,7 +60,7 @@ struct StreamParams {
   int nt;                  // tiles per filter row (capacity)
   size_t xstride;          // elements per filter row of x0 / x1 (= nt * tile size)
   void *x0, *x1;           // x0: resampled (or initial) particles; x1: propagated particles
-  double *tile_m, *tile_s; // [C][nt] tile max and sum e relative to it (within-block prefixes of k_st_resample)
+  double *tile_m, *tile_s; // [C][nt][warps per block] sub-tile max and sum e relative to it (one per warp of k_st_step; within-block prefixes of k_st_resample)
   double *blk_m, *blk_s, *blk_q, *blk_x;   // [C][bpc] block records (max; sum e, sum e^2, sum e*x relative to it)
   double* pref;            // [C][bpc + 1] exclusive prefix of the block sums, relative to the local max
   double* bsum;            // [C][bpc] sum of the states written by a block (state estimate after resampling)
@@ -393,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr int TS = ST_THREADS * PPT;
   __shared__ uint4 s_pf[2][2 * ST_THREADS];
-  __shared__ Real s_w[2][4][ST_NW];     // per-warp partials by tile parity
+  __shared__ Real s_w[4][ST_NW];        // per-warp records at the end of the block
   __shared__ double s_red[4 * ST_NW];
   const FilterDev& f = P.f;
   const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -415,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   const size_t trow = (size_t)c * P.nt;
-  // block record (warp 0, identical in its lanes): online max / rescaled sums over the block's tiles
+  // this warp's record (identical in its lanes): online max / rescaled sums over its sub-tiles
   Real mB = Math<Real>::ninf(), sB = 0, qB = 0, xB = 0;
 
   for (int tile = t0; tile < t1; tile++) {
@@ -474,34 +471,36 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
     }
     if (nanf) fs = fs + (Real)__int_as_float(0x7FC00000);   // a NaN log-weight poisons the sum (R: `if (NA)` error)
     fs = st_warp_sum<Real>(fs); fq = st_warp_sum<Real>(fq); fx = st_warp_sum<Real>(fx);
-    if (lane == 0) { s_w[pb][0][wid] = mw; s_w[pb][1][wid] = fs; s_w[pb][2][wid] = fq; s_w[pb][3][wid] = fx; }
-    __syncthreads();
-    if (wid == 0) {
-      // tile partial from the ST_NW warp partials (fixed tree over lanes 0..7, state precision, no fp64 chain)
-      const int l8 = lane & (ST_NW - 1);
-      const Real m = s_w[pb][0][l8];
-      Real mt = m;
-#pragma unroll
-      for (int o = ST_NW / 2; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, mt, o); mt = t > mt ? t : mt; }
-      Real sc = 0;
-      if (!(m == Math<Real>::ninf() || mt == Math<Real>::ninf())) sc = Math<Real>::exp_(m - mt);
-      Real a0 = s_w[pb][1][l8] * sc, a1 = s_w[pb][2][l8] * sc * sc, a2 = s_w[pb][3][l8] * sc;
-#pragma unroll
-      for (int o = ST_NW / 2; o; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-      }
-      if (lane == 0) { P.tile_m[trow + tile] = (double)mt; P.tile_s[trow + tile] = (double)a0; }
-      // fold the tile into the block record (tiles in order)
-      if (mt > mB) {
-        const Real r = (mB == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mB - mt);
-        sB = sB * r + a0; qB = qB * r * r + a1; xB = xB * r + a2; mB = mt;
-      } else if (mt != Math<Real>::ninf()) {
-        const Real r = Math<Real>::exp_(mt - mB);
-        sB += a0 * r; qB += a1 * r * r; xB += a2 * r;
-      } else {
-        sB += a0; qB += a1; xB += a2;   // empty tile: zeros, or the NaN marker of a poisoned sum
-      }
+    // no block barrier in this loop: every warp publishes the partial of its own 32 * PPT particles (the "sub-tile")
+    // and folds it into its own running record; k_st_resample sums the sub-tiles of a tile when it needs tile sums
+    if (lane == 0) { P.tile_m[(trow + tile) * ST_NW + wid] = (double)mw; P.tile_s[(trow + tile) * ST_NW + wid] = (double)fs; }
+    if (mw > mB) {
+      const Real r = (mB == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mB - mw);
+      sB = sB * r + fs; qB = qB * r * r + fq; xB = xB * r + fx; mB = mw;
+    } else if (mw != Math<Real>::ninf()) {
+      const Real r = Math<Real>::exp_(mw - mB);
+      sB += fs * r; qB += fq * r * r; xB += fx * r;
+    } else {
+      sB += fs; qB += fq; xB += fx;   // empty sub-tile: zeros, or the NaN marker of a poisoned sum
     }
+  }
+  // block record from the warp records (fixed order)
+  if (lane == 0) { s_w[0][wid] = mB; s_w[1][wid] = sB; s_w[2][wid] = qB; s_w[3][wid] = xB; }
+  __syncthreads();
+  if (tid == 0) {
+    Real mt = Math<Real>::ninf();
+#pragma unroll
+    for (int w = 0; w < ST_NW; w++) mt = s_w[0][w] > mt ? s_w[0][w] : mt;
+    Real a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int w = 0; w < ST_NW; w++) {
+      const Real m = s_w[0][w];
+      Real sc = 0;
+      if (m == Math<Real>::ninf()) sc = (Real)1;   // empty warp record: zeros or the NaN marker
+      else sc = Math<Real>::exp_(m - mt);
+      a0 += s_w[1][w] * sc; a1 += s_w[2][w] * sc * sc; a2 += s_w[3][w] * sc;
+    }
+    mB = mt; sB = a0; qB = a1; xB = a2;
   }
   // one ticket per block; the last block of the filter merges.  The barrier-reduction makes the outcome a
   // block-uniform value the compiler can see
@@ -548,7 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;
-  constexpr int CAP = TS + ST_SLACK;
+  constexpr int CAP = ST_THREADS * ((PPT * 5 / 4 + 1) & ~1);   // staging capacity: a quarter beyond the tile (more offspring take further chunks)
   constexpr int SPT = CAP / ST_THREADS;      // output slots per thread in the expansion
   static_assert(CAP % ST_THREADS == 0 && SPT % 2 == 0, "staging capacity: whole, even number of slots per thread");
   // one buffer, two lives: the staged stratified uniforms (raw Philox words) of the tile while the offspring
@@ -589,17 +588,22 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
 #pragma unroll
   for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;     // every thread keeps its own slots of the head array clear
   if (wid == 0) {
-    // within-block exclusive prefix of the tile sums on the local-max scale (tiles in order, 32 per round)
-    const double* tm = P.tile_m + (size_t)c * P.nt;
-    const double* tsum = P.tile_s + (size_t)c * P.nt;
+    // within-block exclusive prefix of the tile sums on the local-max scale (tiles in order, 32 per round); a tile sum
+    // is the sum of its ST_NW sub-tile partials (one per warp of k_st_step)
+    const double* tm = P.tile_m + (size_t)c * P.nt * ST_NW;
+    const double* tsum = P.tile_s + (size_t)c * P.nt * ST_NW;
     const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
     double carry = 0.0;
     for (int tb = t0; tb < t1; tb += 32) {
       const int t = tb + lane;
       double v = 0.0;
       if (t < t1) {
-        const double mt = tm[t];
-        if (!(mt == NINF || sg.mloc == NINF)) v = tsum[t] * (double)Math<Real>::exp_((Real)(mt - sg.mloc));
+#pragma unroll
+        for (int w = 0; w < ST_NW; w++) {
+          const double mt = tm[(size_t)t * ST_NW + w];
+          if (!(mt == NINF || sg.mloc == NINF)) v += tsum[(size_t)t * ST_NW + w] * (double)Math<Real>::exp_((Real)(mt - sg.mloc));
+          else if (mt == NINF) v += tsum[(size_t)t * ST_NW + w];   // zero, or the NaN marker
+        }
       }
       const double inc = warp_incl_scan_d(v, lane);
       if (t < t1) s_pl[t - t0] = carry + (inc - v);

@@ -51,3 +51,22 @@ def pmmh_sharded(run_local, num_chains: int, rank: int, world: int, device=None,
     if local is None:
         raise ValueError("more ranks than chains")
     return gather_chain_arrays({k: local[k] for k in keys if k in local}, num_chains, rank, world, device)
+
+
+def replicate_filters_sharded(y, num_particles, model, num_filters: int, rank: int, world: int, device=None, ctx=None,
+                              keys=("loglike", "n_resampled", "status"), **kwargs):
+    """`num_filters` replicate bootstrap filters of one model (config C3) split across the ranks by GLOBAL filter id
+    (Philox stream = filter id, so a filter's estimate does not depend on where it runs); one all_gather of the
+    per-filter results at the end.  kwargs go to filters.batched_bootstrap_filter (resample_algorithm, precision,
+    seed, engine, model parameters ...)."""
+    from .filters import _particle_filter_core
+
+    def run_local(base, count):
+        params = {k: v for k, v in kwargs.items() if k not in ("resample_algorithm", "resample_fn", "threshold", "precision", "seed", "engine")}
+        from . import _native as nat
+        out = _particle_filter_core(y, num_particles, model, "BPF", kwargs.get("resample_algorithm", "SISAR"),
+                                    kwargs.get("resample_fn", "stratified"), kwargs.get("threshold"), False, None, params,
+                                    kwargs.get("precision", "f32"), kwargs.get("seed", 0), ctx, num_filters=count,
+                                    engine=kwargs.get("engine", nat.ENGINE_AUTO), stream_base=base)
+        return out
+    return pmmh_sharded(run_local, num_filters, rank, world, device, keys=keys)

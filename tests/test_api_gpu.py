@@ -172,3 +172,20 @@ def test_pmmh_return_latent_state_est(orc, engine):
                  return_latent_state_est=True, seed=5, ctx=engine, print_result=False)
     assert len(res["latent_state_chain"]) == 2 and len(res["latent_state_chain"][0]) == 10
     assert res["latent_state_chain"][0][0].shape == (len(y) + 1,)
+
+
+def test_replicate_filters_sharded_is_placement_independent(engine):
+    """Config C3 across GPUs: filters are split by global filter id (= Philox stream); the shard [base, base+count)
+    run alone reproduces the same rows of the full batch (world = 1 here; the gather is exercised on CPU with gloo)."""
+    from bayesssm_b200 import distributed as D
+    mdl = b.models.linear_gaussian()
+    rng = np.random.default_rng(2)
+    y = rng.standard_normal(30)
+    kw = dict(resample_algorithm="SISR", precision="f64", seed=9, phi=0.8, sigma_x=1.0, sigma_y=1.0)
+    full = D.replicate_filters_sharded(y, 2000, mdl, 12, 0, 1, ctx=engine, **kw)
+    assert full["loglike"].shape == (12,) and len(np.unique(full["loglike"])) == 12
+    from bayesssm_b200.filters import _particle_filter_core
+    base, count = D.shard_chains(12, 1, 3)
+    part = _particle_filter_core(y, 2000, mdl, "BPF", "SISR", "stratified", None, False, None,
+                                 dict(phi=0.8, sigma_x=1.0, sigma_y=1.0), "f64", 9, engine, num_filters=count, stream_base=base)
+    np.testing.assert_array_equal(part["loglike"], full["loglike"][base:base + count])
