@@ -700,23 +700,47 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
       const float f0 = (float)(T0c - (double)I0);
       const float wsn = (float)(wscale * (double)n);
       float accf = 0.f;
+      // One test per thread instead of three per particle: the positions grow with k, so if the LAST one is inside
+      // the staged window of uniforms, below n and within the range of the fp32 floor trick, all of them are.
+      const float tf_last = fmaf((float)fs, wsn, f0);
+      const int rel0 = I0 - sc.u_base;
+      const bool fast = P.resample_fn != 1 && tf_last < 4194304.0f && rel0 >= 0 && rel0 + (int)tf_last + 1 < CAP &&
+                        I0 + (int)tf_last + 1 < n;
+      if (fast) {
+        const unsigned int* su = s_u + rel0;
 #pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        accf += (float)e[k];
-        const float tf = fmaf(accf, wsn, f0);
-        const float r = (tf - 0.5f) + 12582912.0f;
-        const int ii = __float_as_int(r) - 0x4B400000;
-        const float frac = tf - (r - 12582912.0f);
-        const float g = frac + 1.0f;
-        const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;
-        const int i = I0 + ii;
-        int v;
-        if (tf >= 4194304.0f) v = sc.count_le(lo_cdf + (exu + (double)accf) * wscale);   // beyond the fp32 floor trick (degenerate weights)
-        else if (i >= n) v = n;
-        else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);
-        v = min(max(v, o_lo), o_hi);
-        fmax = max(fmax, v);
-        F[k] = fmax;
+        for (int k = 0; k < PPT; k++) {
+          accf += (float)e[k];
+          const float tf = fmaf(accf, wsn, f0);
+          const float r = (tf - 0.5f) + 12582912.0f;                       // floor and fraction without conversion instructions
+          const int ii = __float_as_int(r) - 0x4B400000;
+          const float frac = tf - (r - 12582912.0f);
+          const float g = frac + 1.0f;
+          const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;
+          int v = I0 + ii + ((su[ii] < fbits || g >= 2.0f) ? 1 : 0);       // (i + U_i) <= t  <=>  U_i <= frac
+          v = min(max(v, o_lo), o_hi);
+          fmax = max(fmax, v);
+          F[k] = fmax;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+          accf += (float)e[k];
+          const float tf = fmaf(accf, wsn, f0);
+          const float r = (tf - 0.5f) + 12582912.0f;
+          const int ii = __float_as_int(r) - 0x4B400000;
+          const float frac = tf - (r - 12582912.0f);
+          const float g = frac + 1.0f;
+          const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;
+          const int i = I0 + ii;
+          int v;
+          if (tf >= 4194304.0f) v = sc.count_le(lo_cdf + (exu + (double)accf) * wscale);   // beyond the fp32 floor trick (degenerate weights)
+          else if (i >= n) v = n;
+          else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);
+          v = min(max(v, o_lo), o_hi);
+          fmax = max(fmax, v);
+          F[k] = fmax;
+        }
       }
       if (special) {   // the thread with padding lanes and / or the last valid particle of the tile (which takes what is left)
         fmax = o_lo;
@@ -776,13 +800,27 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   for (int c0 = o_base; c0 < o_hi; c0 += CAP) {
     const int c1 = min(o_hi, c0 + CAP);
     int lo_k = prevF;
+    const unsigned int key0 = ((unsigned int)(tid * PPT) << 16) | (unsigned int)(tid * EPH);   // key of source k = key0 + a constant
+    if (o_hi - o_base <= CAP) {          // the usual case: all the offspring of the tile in one chunk (block-uniform)
 #pragma unroll
-    for (int k = 0; k < PPT; k++) {
-      const int hi_k = F[k];
-      const int a = max(lo_k, c0);
-      if (min(hi_k, c1) > a) s_head[a - c0] = ((unsigned int)(tid * PPT + k) << 16) | (unsigned int)(((k / EPH) * ST_THREADS + tid) * EPH + (k % EPH));
-      if (c0 == o_base && hi_k > lo_k) sumx += (Real)(hi_k - lo_k) * x[k];
-      lo_k = max(lo_k, hi_k);
+      for (int k = 0; k < PPT; k++) {
+        const int hi_k = F[k];           // F is non-decreasing and starts at prevF
+        if (hi_k > lo_k) {
+          s_head[lo_k - o_base] = key0 + (((unsigned int)k << 16) | (unsigned int)((k / EPH) * ST_THREADS * EPH + (k % EPH)));
+          if constexpr (F32) sumx += (__int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f) * x[k];   // count as a float, exact below 2^23
+          else sumx += (Real)(hi_k - lo_k) * x[k];
+        }
+        lo_k = hi_k;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const int hi_k = F[k];
+        const int a = max(lo_k, c0);
+        if (min(hi_k, c1) > a) s_head[a - c0] = key0 + (((unsigned int)k << 16) | (unsigned int)((k / EPH) * ST_THREADS * EPH + (k % EPH)));
+        if (c0 == o_base && hi_k > lo_k) sumx += (Real)(hi_k - lo_k) * x[k];
+        lo_k = max(lo_k, hi_k);
+      }
     }
     __syncthreads();
     // running maximum over the slots: thread-local, then across the warp, then across the warps
