@@ -60,7 +60,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     if (per_sm < 1) per_sm = 1024 / ST_THREADS;   // the kernels are built for 1024 threads per SM (__launch_bounds__)
     const long long slots = (long long)per_sm * ctx->prop.multiProcessorCount;
     long long b0 = (slots + C - 1) / C;
-    const long long bmin = (P.nt + ST_MAX_TPB - 1) / ST_MAX_TPB;   // at most ST_MAX_TPB tiles per block
+    const long long bmin = 1;
     if (b0 < bmin) b0 = bmin;
     if (b0 > P.nt) b0 = P.nt;
     // cost in tile-times: the blocks' work spread over the resident slots plus one block's length as the tail;
@@ -77,8 +77,6 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 0, (size_t)C * P.xstride * rs, &P.x0));
   BSSM_TRY(scratch_get(ctx, SL_ST_BASE + 1, (size_t)C * P.xstride * rs, &P.x1));
-  BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.nt * (ST_THREADS / 32) * 2, &P.tile_m));
-  P.tile_s = P.tile_m + (size_t)C * P.nt * (ST_THREADS / 32);
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 3, (size_t)C * (P.bpc + 1), &P.pref));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 4, (size_t)C * P.bpc, &P.bsum));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 10, (size_t)C * P.bpc * 4, &P.blk_m));

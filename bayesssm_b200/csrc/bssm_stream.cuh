@@ -39,7 +39,6 @@ namespace bssm {
 // threads per block are a template parameter of the kernels (THREADS): 256 for single big filters (fewer block
 // records to merge), 128 for batches (smaller barrier domains: +6-8 % there, -3 % on single filters)
 constexpr int ST_ERR_CAPACITY = 10; // status: a shard outgrew its storage (BSSM_ERR_CAPACITY)
-constexpr int ST_MAX_TPB = 256;     // tiles per block (k_st_resample keeps their prefix in shared memory)
 
 
 // layout / cdf descriptor of one filter on this rank, written once per observation
@@ -60,7 +59,6 @@ struct StreamParams {
   int nt;                  // tiles per filter row (capacity)
   size_t xstride;          // elements per filter row of x0 / x1 (= nt * tile size)
   void *x0, *x1;           // x0: resampled (or initial) particles; x1: propagated particles
-  double *tile_m, *tile_s; // [C][nt][warps per block] sub-tile max and sum e relative to it (one per warp of k_st_step; within-block prefixes of k_st_resample)
   double *blk_m, *blk_s, *blk_q, *blk_x;   // [C][bpc] block records (max; sum e, sum e^2, sum e*x relative to it)
   double* pref;            // [C][bpc + 1] exclusive prefix of the block sums, relative to the local max
   double* bsum;            // [C][bpc] sum of the states written by a block (state estimate after resampling)
@@ -411,9 +409,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
-  const size_t trow = (size_t)c * P.nt;
-  // this warp's record (identical in its lanes): online max / rescaled sums over its sub-tiles
-  Real mB = Math<Real>::ninf(), sB = 0, qB = 0, xB = 0;
+  // this thread's record: running max and sums (relative to it) over its particles of all the block's tiles
+  Real mT = Math<Real>::ninf(), sT = 0, qT = 0, xT = 0;
+  int nanf = 0;
 
   for (int tile = t0; tile < t1; tile++) {
     const int pb = (tile - t0) & 1;
@@ -446,7 +444,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
     StVec<Real, PPT>::store(xout + (size_t)tile * TS, x);
     Real e[PPT];
     Real mloc = Math<Real>::ninf();
-    int nanf = 0;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
       e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
@@ -458,49 +455,41 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
     }
 #pragma unroll
     for (int k = 0; k < PPT; k++) mloc = e[k] > mloc ? e[k] : mloc;
-    // warp-level reference (no block barrier on the weight path): e relative to the warp max
-    const Real mw = st_warp_max<Real>(mloc);
-    Real fs = 0, fq = 0, fx = 0;
+    // Thread-local online accumulation: e relative to this THREAD's running max (rescaled on the rare tiles that
+    // raise it).  No shuffle, no barrier, no store of partials in this loop: the sums meet once, at the block's end.
+    if (mloc > mT) {
+      const Real r = (mT == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mT - mloc);
+      sT *= r; qT *= r * r; xT *= r; mT = mloc;
+    }
     {
-      const Real mwr = (mw == Math<Real>::ninf()) ? (Real)0 : mw;
+      const Real mref = (mT == Math<Real>::ninf()) ? (Real)0 : mT;
 #pragma unroll
       for (int k = 0; k < PPT; k++) {
-        const Real ek = Math<Real>::exp_(e[k] - mwr);
-        fs += ek; fq += ek * ek; fx += ek * x[k];
+        const Real ek = Math<Real>::exp_(e[k] - mref);
+        sT += ek; qT += ek * ek; xT += ek * x[k];
       }
     }
-    if (nanf) fs = fs + (Real)__int_as_float(0x7FC00000);   // a NaN log-weight poisons the sum (R: `if (NA)` error)
-    fs = st_warp_sum<Real>(fs); fq = st_warp_sum<Real>(fq); fx = st_warp_sum<Real>(fx);
-    // no block barrier in this loop: every warp publishes the partial of its own 32 * PPT particles (the "sub-tile")
-    // and folds it into its own running record; k_st_resample sums the sub-tiles of a tile when it needs tile sums
-    if (lane == 0) { P.tile_m[(trow + tile) * ST_NW + wid] = (double)mw; P.tile_s[(trow + tile) * ST_NW + wid] = (double)fs; }
-    if (mw > mB) {
-      const Real r = (mB == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mB - mw);
-      sB = sB * r + fs; qB = qB * r * r + fq; xB = xB * r + fx; mB = mw;
-    } else if (mw != Math<Real>::ninf()) {
-      const Real r = Math<Real>::exp_(mw - mB);
-      sB += fs * r; qB += fq * r * r; xB += fx * r;
-    } else {
-      sB += fs; qB += fq; xB += fx;   // empty sub-tile: zeros, or the NaN marker of a poisoned sum
-    }
   }
-  // block record from the warp records (fixed order)
-  if (lane == 0) { s_w[0][wid] = mB; s_w[1][wid] = sB; s_w[2][wid] = qB; s_w[3][wid] = xB; }
+  // block record: thread records -> warp records (shuffles) -> block record (fixed order)
+  {
+    if (nanf) sT = sT + (Real)__int_as_float(0x7FC00000);   // a NaN log-weight poisons the sum (R: `if (NA)` error)
+    const Real mw = st_warp_max<Real>(mT);
+    Real sc = (Real)1;                                       // empty thread record: zeros or the NaN marker pass through
+    if (mT != Math<Real>::ninf()) sc = Math<Real>::exp_(mT - mw);
+    const Real fs = st_warp_sum<Real>(sT * sc), fq = st_warp_sum<Real>(qT * sc * sc), fx = st_warp_sum<Real>(xT * sc);
+    if (lane == 0) { s_w[0][wid] = mw; s_w[1][wid] = fs; s_w[2][wid] = fq; s_w[3][wid] = fx; }
+  }
   __syncthreads();
+  Real mB = Math<Real>::ninf(), sB = 0, qB = 0, xB = 0;
   if (tid == 0) {
-    Real mt = Math<Real>::ninf();
 #pragma unroll
-    for (int w = 0; w < ST_NW; w++) mt = s_w[0][w] > mt ? s_w[0][w] : mt;
-    Real a0 = 0, a1 = 0, a2 = 0;
+    for (int w = 0; w < ST_NW; w++) mB = s_w[0][w] > mB ? s_w[0][w] : mB;
 #pragma unroll
     for (int w = 0; w < ST_NW; w++) {
       const Real m = s_w[0][w];
-      Real sc = 0;
-      if (m == Math<Real>::ninf()) sc = (Real)1;   // empty warp record: zeros or the NaN marker
-      else sc = Math<Real>::exp_(m - mt);
-      a0 += s_w[1][w] * sc; a1 += s_w[2][w] * sc * sc; a2 += s_w[3][w] * sc;
+      const Real sc = (m == Math<Real>::ninf()) ? (Real)1 : Math<Real>::exp_(m - mB);
+      sB += s_w[1][w] * sc; qB += s_w[2][w] * sc * sc; xB += s_w[3][w] * sc;
     }
-    mB = mt; sB = a0; qB = a1; xB = a2;
   }
   // one ticket per block; the last block of the filter merges.  The barrier-reduction makes the outcome a
   // block-uniform value the compiler can see
@@ -557,8 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   Real* const s_out = (Real*)s_uo;
   __shared__ __align__(16) unsigned int s_head[CAP];       // expansion: (source index << 16 | address of its x) at the first slot of a source
   __shared__ uint4 s_pf[2][2 * ST_THREADS];
-  __shared__ double s_pl[ST_MAX_TPB + 1];   // exclusive prefix of the tile sums inside this block (local-max scale)
-  __shared__ double s_red[ST_NW], s_bs[ST_NW], s_cdf[2];
+  __shared__ double s_red[ST_NW], s_bs[ST_NW];
   __shared__ int s_wf[ST_NW];
   __shared__ unsigned int s_wh[ST_NW];
   const FilterDev& f = P.f;
@@ -587,30 +575,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   Real* xo = (Real*)P.x0 + (size_t)c * P.xstride - (sg.ngoff & ~3LL);   // xo[slot] = storage of global slot
 #pragma unroll
   for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;     // every thread keeps its own slots of the head array clear
-  if (wid == 0) {
-    // within-block exclusive prefix of the tile sums on the local-max scale (tiles in order, 32 per round); a tile sum
-    // is the sum of its ST_NW sub-tile partials (one per warp of k_st_step)
-    const double* tm = P.tile_m + (size_t)c * P.nt * ST_NW;
-    const double* tsum = P.tile_s + (size_t)c * P.nt * ST_NW;
-    const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
-    double carry = 0.0;
-    for (int tb = t0; tb < t1; tb += 32) {
-      const int t = tb + lane;
-      double v = 0.0;
-      if (t < t1) {
-#pragma unroll
-        for (int w = 0; w < ST_NW; w++) {
-          const double mt = tm[(size_t)t * ST_NW + w];
-          if (!(mt == NINF || sg.mloc == NINF)) v += tsum[(size_t)t * ST_NW + w] * (double)Math<Real>::exp_((Real)(mt - sg.mloc));
-          else if (mt == NINF) v += tsum[(size_t)t * ST_NW + w];   // zero, or the NaN marker
-        }
-      }
-      const double inc = warp_incl_scan_d(v, lane);
-      if (t < t1) s_pl[t - t0] = carry + (inc - v);
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-  }
+  // cdf numerator interval of this block on the global scale (block edges: the neighbouring block evaluates the same
+  // expression on the same prefix value); inside the block the tile edges are running sums of this kernel's own tile totals
+  const double blk_lo = st_bound(sg.abase, b_lo, sg.gscale), blk_hi = st_bound(sg.abase, b_hi, sg.gscale);
+  double run = 0.0;    // sum of the tile totals of this block so far (identical in every thread)
   double bacc = 0.0;   // sum of the states written by this block (meaningful in thread 0)
 
   for (int tile = t0; tile < t1; tile++) {
@@ -642,32 +610,30 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   }
   // tile-local exclusive prefix of the thread sums: fp64 across warps; inside a warp fp32 in the throughput
   // precision (256 particles: error ~1e-4 output slots), fp64 in the parity precision
-  double exu;
+  double exu, lo_cdf, hi_cdf;
   {
     Real inc = fs;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { Real t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) s_red[wid] = (double)inc;
-    if (tid == 0) {   // one pair of boundary values per tile, not per thread
-      // block edges from the prefix array (the neighbouring block reads the same value), rank edges from the
-      // descriptor, tile edges inside the block from this block's own prefix
-      double A_lo, A_hi;
-      if (tile == 0) A_lo = sg.abase;
-      else A_lo = st_bound(sg.abase, tile == t0 ? b_lo : b_lo + s_pl[tile - t0], sg.gscale);
-      if (tile == ntc - 1) A_hi = sg.aend;
-      else A_hi = st_bound(sg.abase, tile == t1 - 1 ? b_hi : b_lo + s_pl[tile + 1 - t0], sg.gscale);
-      if (F32) { s_cdf[0] = A_lo * wscale; s_cdf[1] = A_hi * wscale; }      // reciprocal: no fp64 division chain before the barrier
-      else { s_cdf[0] = A_lo / S; s_cdf[1] = A_hi / S; }
-    }
     __syncthreads();
-    double wbase = 0.0;
+    double wbase = 0.0, total = 0.0;
 #pragma unroll
-    for (int w = 0; w < ST_NW - 1; w++) wbase += (w < wid) ? s_red[w] : 0.0;   // fixed order
+    for (int w = 0; w < ST_NW; w++) { if (w == wid) wbase = total; total += s_red[w]; }   // fixed order, identical in every thread
     exu = wbase + (double)(inc - fs);
+    // tile edges: rank edges from the descriptor, block edges from the prefix array, edges inside the block from the
+    // running sum -- clamped into the block's interval, so that rounding can never reach into a neighbour's slots
+    double A_lo, A_hi;
+    if (tile == 0) A_lo = sg.abase;
+    else A_lo = tile == t0 ? blk_lo : fmin(blk_lo + run, blk_hi);
+    run += total;
+    if (tile == ntc - 1) A_hi = sg.aend;
+    else A_hi = tile == t1 - 1 ? blk_hi : fmin(blk_lo + run, blk_hi);
+    if (F32) { lo_cdf = A_lo * wscale; hi_cdf = A_hi * wscale; }      // reciprocal: no fp64 division chain
+    else { lo_cdf = A_lo / S; hi_cdf = A_hi / S; }
   }
   const bool tail = sg.last && tile == ntc - 1;
-  const double lo_cdf = s_cdf[0];
-  const double hi_cdf = tail ? 2.0 : s_cdf[1];
+  if (tail) hi_cdf = 2.0;
 
   SlotCounter sc;
   sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
