@@ -410,8 +410,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   // this thread's record: running max and sums (relative to it) over its particles of all the block's tiles
+  // (a NaN log-weight never raises the max and turns exp(NaN - ref) into NaN: it poisons the sum by itself --
+  // R's `if (NA)` error, reported as BSSM_ERR_NAN_WEIGHT)
   Real mT = Math<Real>::ninf(), sT = 0, qT = 0, xT = 0;
-  int nanf = 0;
 
   for (int tile = t0; tile < t1; tile++) {
     const int pb = (tile - t0) & 1;
@@ -445,10 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
     Real e[PPT];
     Real mloc = Math<Real>::ninf();
 #pragma unroll
-    for (int k = 0; k < PPT; k++) {
-      e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
-      nanf |= (e[k] != e[k]);
-    }
+    for (int k = 0; k < PPT; k++) e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
     if (ragged) {
 #pragma unroll
       for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) e[k] = Math<Real>::ninf();
@@ -472,7 +470,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   }
   // block record: thread records -> warp records (shuffles) -> block record (fixed order)
   {
-    if (nanf) sT = sT + (Real)__int_as_float(0x7FC00000);   // a NaN log-weight poisons the sum (R: `if (NA)` error)
     const Real mw = st_warp_max<Real>(mT);
     Real sc = (Real)1;                                       // empty thread record: zeros or the NaN marker pass through
     if (mT != Math<Real>::ninf()) sc = Math<Real>::exp_(mT - mw);

@@ -151,3 +151,18 @@ def test_pmmh_on_streaming_engine_matches_oracle(orc, engine):
         np.testing.assert_allclose(got["pilot_theta_chain"][c], ref["pilot_theta_chain"], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(got["theta_chain"][c], ref["theta_chain"], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(got["loglike_chain"][c], ref["loglike_chain"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("eng", [nat.ENGINE_GENERAL, nat.ENGINE_PERSISTENT, nat.ENGINE_STREAM])
+def test_nan_weights_are_reported_by_every_engine(engine, eng):
+    # R's `if (all(lw < -1e8))` raises "missing value where TRUE/FALSE needed" on NaN weights (R/particle_filter_core.R:189):
+    # status BSSM_ERR_NAN_WEIGHT, whichever engine runs -- also when a single particle of a batch member is affected
+    rng = np.random.default_rng(3)
+    y = sim_y(AR, 5, rng)
+    got = eh.filter_run(engine, AR, 0, 2, 0, 5000, y, [0.8, 1.0, float("nan")], seed=1, precision=nat.F32, engine=eng)
+    assert got["status"][0] == nat.ERR_NAN_WEIGHT
+    th = np.tile(np.array([0.8, 1.0, 0.5]), (3, 1))
+    th[1, 0] = float("nan")                  # NaN dynamics: the states, hence the weights, of filter 1 only
+    got = eh.filter_run(engine, AR, 0, 2, 0, 5000, y, th, seed=1, num_filters=3, precision=nat.F32, engine=eng)
+    assert got["status"].tolist() == [0, nat.ERR_NAN_WEIGHT, 0]
+    assert np.isfinite(got["loglike"][[0, 2]]).all()
