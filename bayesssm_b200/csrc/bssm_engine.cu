@@ -233,9 +233,10 @@ int resolve_engine(bssm_ctx* ctx, const FilterDev& f_in, const FilterLaunch& L, 
   const bool fast_ok = fast_supported(f, L) && (long long)f.N <= (long long)ctx->prop.multiProcessorCount * FAST_MAX_NB;
   const bool stream_ok = stream_supported(ctx, f, L);
   const long long total = (long long)f.C * f.N;
-  // measured on B200 (scripts/bench_engines.py): 1024 x 65536 streaming +41 %, 256 x 65536 +10 %, 4 x 2^20 +29 %;
-  // smaller batches and slices belong to the persistent kernel
-  const bool stream_wins = (f.N >= (1 << 19) && f.C >= 4) || (f.N >= 32768 && total >= (1LL << 24));
+  // measured on B200 (scripts/bench_engines.py, G particle-timesteps/s streaming vs persistent): 1024 x 65536 141 vs 86,
+  // 256 x 65536 103 vs 84, 128 x 65536 89 vs 82, 32 x 2^18 89 vs 75, 3 x 2^20 56 vs 48; but 64 x 65536 67 vs 77,
+  // 8 x 2^19 64 vs 67, 2 x 2^20 47 vs 50, 1024 x 1000 27 vs 67: smaller batches and slices belong to the persistent kernel
+  const bool stream_wins = (f.N >= (1 << 20) && f.C >= 3) || (f.N >= 32768 && total >= (1LL << 23));
   if (stream_ok && (!fast_ok || stream_wins)) return BSSM_ENGINE_STREAM;
   if (fast_ok) return BSSM_ENGINE_PERSISTENT;
   return BSSM_ENGINE_GENERAL;
