@@ -166,3 +166,17 @@ def test_nan_weights_are_reported_by_every_engine(engine, eng):
     got = eh.filter_run(engine, AR, 0, 2, 0, 5000, y, th, seed=1, num_filters=3, precision=nat.F32, engine=eng)
     assert got["status"].tolist() == [0, nat.ERR_NAN_WEIGHT, 0]
     assert np.isfinite(got["loglike"][[0, 2]]).all()
+
+
+def test_runs_are_bit_reproducible(engine):
+    # no atomics on floating-point data, fixed merge order, every output slot written exactly once: repeated runs are
+    # bit-identical (a race between tiles / blocks would show up here), for one big filter and for a batch
+    rng = np.random.default_rng(4)
+    y = sim_y(AR, 30, rng)
+    for kw in (dict(N=1 << 21, num_filters=1), dict(N=40000, num_filters=37)):
+        runs = [eh.filter_run(engine, AR, 0, 2, 0, kw["N"], y, THETA[AR], seed=17, num_filters=kw["num_filters"], precision=nat.F32,
+                              engine=ST) for _ in range(3)]
+        for r in runs[1:]:
+            assert np.array_equal(r["loglike"], runs[0]["loglike"])
+            assert np.array_equal(r["state_est"], runs[0]["state_est"]) and np.array_equal(r["ess"], runs[0]["ess"])
+        assert (runs[0]["status"] == 0).all() and (runs[0]["n_resampled"] > 0).all()
