@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   // expression on the same prefix value); inside the block the tile edges are running sums of this kernel's own tile totals
   const double blk_lo = st_bound(sg.abase, b_lo, sg.gscale), blk_hi = st_bound(sg.abase, b_hi, sg.gscale);
   double run = 0.0;    // sum of the tile totals of this block so far (identical in every thread)
-  double bacc = 0.0;   // sum of the states written by this block (meaningful in thread 0)
+  double bacc = 0.0;   // this thread's share of the sum of the states written by this block
 
   for (int tile = t0; tile < t1; tile++) {
   const int pb = (tile - t0) & 1;
@@ -831,14 +831,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
     }
     __syncthreads();
   }
-  // sum of the chosen states (state estimate after resampling, merged by the next observation's k_st_step)
-  double v = warp_sum_d((double)sumx);
-  if (lane == 0) s_bs[wid] = v;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 0; w < ST_NW; w++) bacc += s_bs[w];
-  }
+  bacc += (double)sumx;   // this thread's share of the sum of the chosen states; reduced once, after the last tile
   }  // tiles
+  // sum of the states written by this block (state estimate after resampling, merged by the next observation's k_st_step)
+  {
+    const double v = warp_sum_d(bacc);
+    if (lane == 0) s_bs[wid] = v;
+    __syncthreads();
+    bacc = 0.0;
+    if (tid == 0) {
+      for (int w = 0; w < ST_NW; w++) bacc += s_bs[w];
+    }
+  }
   if (tid == 0) P.bsum[(size_t)c * P.bpc + j] = bacc;
 }
 
