@@ -180,6 +180,11 @@ SEXP _bayesSSM_b200_pmmh(SEXP cfg_, SEXP y_, SEXP init_) {
   double *ll_rm = (double *)R_alloc((size_t)C * m, sizeof(double)), *pm_rm = (double *)R_alloc((size_t)C * p, sizeof(double));
   res.loglike_chain = ll_rm; res.target_n = INTEGER(tn); res.n_accept = INTEGER(na); res.status = INTEGER(stv);
   res.pilot_theta_mean = pm_rm;
+  int dstate = 1, nth_ = 0, nc_ = 0;
+  if (bssm_model_dims(ctx, cfg.model, &dstate, &nth_, &nc_) != BSSM_OK) { UNPROTECT(5); Rf_error("%s", bssm_last_error()); }
+  cfg.return_latent_state_est = opt_int(cfg_, "return_latent_state_est", 0);
+  const size_t se_len = (size_t)(T + 1) * dstate;
+  if (cfg.return_latent_state_est) res.latent_state_chain = (double *)R_alloc((size_t)C * m * se_len, sizeof(double));
   int st = bssm_pmmh_run(ctx, &cfg, y, init, &res);
   if (st != BSSM_OK) { UNPROTECT(5); Rf_error("%s", bssm_last_error()); }
   SEXP dims = PROTECT(Rf_allocVector(INTSXP, 3));
@@ -192,11 +197,24 @@ SEXP _bayesSSM_b200_pmmh(SEXP cfg_, SEXP y_, SEXP init_) {
     for (int i = 0; i < m; i++) REAL(ll)[(size_t)c * m + i] = ll_rm[(size_t)c * m + i];
     for (int j = 0; j < p; j++) REAL(pmean)[(size_t)j * C + c] = pm_rm[(size_t)c * p + j];
   }
-  const char *names[] = {"theta_chain", "loglike_chain", "target_n", "n_accept", "status", "pilot_theta_mean", ""};
+  /* latent_state_chain: array [T+1, d, m, chain] (R/pmmh.R:420,494-499), or NULL */
+  SEXP lat = R_NilValue;
+  int nprot = 8;
+  if (cfg.return_latent_state_est) {
+    lat = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)((size_t)C * m * se_len)));
+    nprot++;
+    for (int c = 0; c < C; c++) for (int i = 0; i < m; i++) for (int t = 0; t <= T; t++) for (int k = 0; k < dstate; k++)
+      REAL(lat)[(((size_t)c * m + i) * dstate + k) * (T + 1) + t] = res.latent_state_chain[(((size_t)c * m + i) * (T + 1) + t) * dstate + k];
+    SEXP ld = PROTECT(Rf_allocVector(INTSXP, 4));
+    nprot++;
+    INTEGER(ld)[0] = T + 1; INTEGER(ld)[1] = dstate; INTEGER(ld)[2] = m; INTEGER(ld)[3] = C;
+    Rf_setAttrib(lat, R_DimSymbol, ld);
+  }
+  const char *names[] = {"theta_chain", "loglike_chain", "target_n", "n_accept", "status", "pilot_theta_mean", "latent_state_chain", ""};
   SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
   SET_VECTOR_ELT(out, 0, th); SET_VECTOR_ELT(out, 1, ll); SET_VECTOR_ELT(out, 2, tn);
-  SET_VECTOR_ELT(out, 3, na); SET_VECTOR_ELT(out, 4, stv); SET_VECTOR_ELT(out, 5, pmean);
-  UNPROTECT(8);
+  SET_VECTOR_ELT(out, 3, na); SET_VECTOR_ELT(out, 4, stv); SET_VECTOR_ELT(out, 5, pmean); SET_VECTOR_ELT(out, 6, lat);
+  UNPROTECT(nprot);
   return out;
 }
 
@@ -260,6 +278,23 @@ SEXP _bayesSSM_b200_shard_filter(SEXP cfg_, SEXP y_, SEXP theta_) {
   return out;
 }
 
+/* .Call("_bayesSSM_b200_model_compile", source) -> list(model, d, ntheta, nconst): a CUDA snippet defining
+ * `struct UserModel` (contract: bayesssm_b200/csrc/bssm_models.cuh) compiled by NVRTC for sm_100a; stands where the
+ * reference takes R closures (R/particle_filter-doc.R:11-18). */
+SEXP _bayesSSM_b200_model_compile(SEXP src_) {
+  if (TYPEOF(src_) != STRSXP || XLENGTH(src_) != 1) Rf_error("source must be a character(1) CUDA snippet");
+  bssm_ctx *ctx = ctx_get();
+  int id = 0, d = 0, nth = 0, nc = 0;
+  if (bssm_model_compile(ctx, CHAR(STRING_ELT(src_, 0)), &id) != BSSM_OK) Rf_error("%s", bssm_last_error());
+  if (bssm_model_dims(ctx, id, &d, &nth, &nc) != BSSM_OK) Rf_error("%s", bssm_last_error());
+  const char *names[] = {"model", "d", "ntheta", "nconst", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(id)); SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(d));
+  SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(nth)); SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(nc));
+  UNPROTECT(1);
+  return out;
+}
+
 SEXP _bayesSSM_b200_device_info(void) {
   char name[256];
   int sm = 0, maj = 0, mnr = 0;
@@ -275,6 +310,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bayesSSM_b200_filter", (DL_FUNC)&_bayesSSM_b200_filter, 3},
     {"_bayesSSM_b200_pmmh", (DL_FUNC)&_bayesSSM_b200_pmmh, 3},
     {"_bayesSSM_b200_device_info", (DL_FUNC)&_bayesSSM_b200_device_info, 0},
+    {"_bayesSSM_b200_model_compile", (DL_FUNC)&_bayesSSM_b200_model_compile, 1},
     {"_bayesSSM_b200_shard_unique_id", (DL_FUNC)&_bayesSSM_b200_shard_unique_id, 0},
     {"_bayesSSM_b200_shard_init", (DL_FUNC)&_bayesSSM_b200_shard_init, 3},
     {"_bayesSSM_b200_shard_filter", (DL_FUNC)&_bayesSSM_b200_shard_filter, 3},

@@ -6,6 +6,7 @@ extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 #define INTSXP 13
 #define VECSXP 19
 #define RAWSXP 24
+#define STRSXP 16
 int TYPEOF(SEXP); R_xlen_t XLENGTH(SEXP); double *REAL(SEXP); int *INTEGER(SEXP); Rbyte *RAW(SEXP);
 SEXP Rf_allocVector(int, R_xlen_t); SEXP Rf_allocMatrix(int,int,int); SEXP PROTECT(SEXP); void UNPROTECT(int);
 int Rf_asInteger(SEXP); double Rf_asReal(SEXP); SEXP Rf_getAttrib(SEXP,SEXP); SEXP Rf_setAttrib(SEXP,SEXP,SEXP);
