@@ -180,3 +180,17 @@ def test_runs_are_bit_reproducible(engine):
             assert np.array_equal(r["loglike"], runs[0]["loglike"])
             assert np.array_equal(r["state_est"], runs[0]["state_est"]) and np.array_equal(r["ess"], runs[0]["ess"])
         assert (runs[0]["status"] == 0).all() and (runs[0]["n_resampled"] > 0).all()
+
+
+def test_big_single_filters_f32_against_kalman(orc, engine):
+    # one filter of 2^22 particles (256-thread variant, the size class of the particle-sharded runs), throughput
+    # precision, SISR (under SISAR the reference drops the weights of non-resampled steps -- quirk A1 -- and the
+    # estimate is biased by construction): the estimates of a few independent runs agree with the exact Kalman value
+    rng = np.random.default_rng(21)
+    y = sim_y(LG, 100, rng)
+    exact = orc.kalman_loglik(y, 0.8, 1.0, 1.0)
+    lls = np.array([eh.filter_run(engine, LG, 0, 1, 0, 1 << 22, y, THETA[LG], seed=100 + s, precision=nat.F32, engine=ST)["loglike"][0]
+                    for s in range(6)])
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(lls.mean() - exact) < 3 * se + 5e-3, (lls, exact)
+    assert lls.std(ddof=1) < 0.05
