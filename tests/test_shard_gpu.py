@@ -74,6 +74,17 @@ for name, N, T, rfn, prec in (("small_f64", 6000, 15, "stratified", "f64"), ("sy
         assert abs(got["loglike"] - one["loglike"][0]) < 0.05, (name, got["loglike"], one["loglike"][0])
         np.testing.assert_allclose(got["state_est"], one["state_est"][0][:, 0], atol=0.02)
     out[name] = got["loglike"]
+# Kalman gate on the sharded path: linear-Gaussian model, SISR, throughput precision, a few seeds
+lg = models.linear_gaussian()
+rng2 = np.random.default_rng(21)
+ylg = sim_y(1, 60, rng2)
+exact = oracle.kalman_loglik(ylg, 0.8, 1.0, 1.0)
+lls = np.array([S.sharded_bootstrap_filter(ylg, 1 << 21, lg.init_fn, lg.transition_fn, lg.log_likelihood_fn, grp,
+                                           resample_algorithm="SISR", precision="f32", seed=200 + s, phi=0.8, sigma_x=1.0,
+                                           sigma_y=1.0)["loglike"] for s in range(5)])
+se = lls.std(ddof=1) / np.sqrt(len(lls))
+assert abs(lls.mean() - exact) < 3 * se + 5e-3, (lls, exact)
+out["kalman_diff"] = float(lls.mean() - exact)
 # capacity overflow is reported, not a crash: a very sharp likelihood piles the offspring on one rank
 y = np.array([0.3, 0.1]); 
 try:
