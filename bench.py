@@ -204,7 +204,8 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world):
             "config": {"workload": f"pmmh nonlinear-AR {Ctot} chains x N={N} x T={T}, chain-sharded, pilot skipped, final NCCL gather of draws",
                        "chains": Ctot, "N": N, "T": T, "engine": args.engine, "l2": "working set 2 x 256 MiB of particles per GPU at 1024 chains: larger than L2"},
             "particle_timesteps_per_s": pts,
-            "e2e": {"value": args.steps / (wall_ms * 1e-3), "unit": "iter/s", "h2d_bytes_per_step": int(8 * T / args.steps),
+            "e2e": {"value": (args.steps + 1) / (wall_ms * 1e-3), "unit": "iter/s",   # the call runs steps + 1 filter passes: draw 1 is the filter at the start value (R/pmmh.R:402-423)
+                    "h2d_bytes_per_step": int(8 * T / args.steps),
                     "d2h_bytes_per_step": int(out["theta_chain"].nbytes / args.steps)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": pts * 30.0 / 1e9, "peak": peak * world, "unit": "GB/s",
