@@ -45,8 +45,9 @@ constexpr int FAST_HEAVY_CAP = 64;
 __host__ __device__ constexpr int fast_spt(int ppt) { return (ppt * 5 / 4 + 3) & ~3; }
 
 // LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
-// 16-byte volatile access.  A reader that sees the expected tag also sees the data: no fence, no
-// separate flag, no dependent second load.
+// 16-byte access.  A reader that sees the expected tag also sees the data: no fence, no separate
+// flag, no dependent second load.  The accesses are relaxed at GPU scope (all that an exchange between
+// CTAs of one GPU needs): +4 % over `volatile`, which is system scope (profiles/r1_ab_experiments.md).
 struct __align__(128) FastRec {   // published once per observation by each CTA: 5 doubles as (lo, tag, hi, tag)
   uint4 w[5];                     // m, s, q, sx, pending sum of the previous step's resampled x
   uint4 pad[3];
@@ -64,14 +65,14 @@ struct FastParams {
 };
 
 __device__ __forceinline__ void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void ll_store_v2(void* p, unsigned int a, unsigned int b) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint4 ll_load_v4(const void* p) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void ll_put_double(uint4* p, double d, unsigned int tag) {
