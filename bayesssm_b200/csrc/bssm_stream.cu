@@ -118,8 +118,8 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     long long h[8];
     BSSM_CK(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     BSSM_CK(cudaStreamSynchronize(st));
-    fprintf(stderr, "[bssm stream timing] last k_st_step, merging block: %lld cycles until its ticket, merge %lld (max pass %lld, block max %lld, sum pass %lld, prefix pass + rest %lld), global bookkeeping %lld; bpc=%d bpc_r=%d nt=%d\n",
-            h[0], h[1], h[4], h[5], h[6], h[7], h[2], P.bpc, P.bpc, P.nt);
+    fprintf(stderr, "[bssm stream timing] last k_st_step, merging block: %lld cycles until its ticket, merge %lld (max pass %lld, block max %lld, sum pass %lld, prefix pass + rest %lld), global bookkeeping %lld; bpc=%d nt=%d\n",
+            h[0], h[1], h[4], h[5], h[6], h[7], h[2], P.bpc, P.nt);
   }
   k_st_flush<TS><<<C, 256, 0, st>>>(P, L.T);
   BSSM_LAUNCH(ctx, "k_st_flush");

@@ -6,12 +6,13 @@
 // for algorithm "BPF" and the resamplers of src/resampling.cpp:16-66 (stratified / systematic).
 //
 //   k_st_step      read x, propagate (one Philox call per 4 particles), log-weight, write x.  A block
-//                  walks a contiguous range of tiles and keeps (max, sum e, sum e^2, sum e*x) per
-//                  tile and per block.  The LAST block of a filter to finish (ticket counter) merges
-//                  the BLOCK records in fixed order: global max / sum / ESS / log-likelihood /
-//                  resampling decision, and the exclusive prefix of the block sums -- the scan
-//                  offsets of the next kernel.  No separate finalise launch, no atomics on
-//                  floating-point data, deterministic.                           [8 B / particle]
+//                  walks a contiguous range of tiles; every thread keeps an online (max, sum e,
+//                  sum e^2, sum e*x) record of its own particles -- no shuffle, barrier or store in
+//                  the tile loop -- and the records meet once, at the block's end.  The LAST block
+//                  of a filter to finish (ticket counter) merges the BLOCK records in fixed order:
+//                  global max / sum / ESS / log-likelihood / resampling decision, and the exclusive
+//                  prefix of the block sums -- the scan offsets of the next kernel.  No separate
+//                  finalise launch, no atomics on floating-point data, deterministic.  [8 B / particle]
 //   k_st_resample  (steps where resampling fires) read x, recompute the weight, tile-local scan;
 //                  INPUT-centric closed-form offspring ranges: a source with cdf value c owns the
 //                  output slots [F(c_prev), F(c)), F(c) = #{ i : (i + U_i)/n <= c } -- no search,
@@ -21,8 +22,9 @@
 // against 8 bytes), so the traffic is 16 B per resampled particle-timestep against the 40 B of the
 // algorithmic model.
 //
-// Tile boundaries in the output are derived by neighbouring tiles from the same prefix values with
-// the same expressions, so every output slot is written exactly once.  Same Philox keying and tie
+// Block boundaries in the output are derived by neighbouring blocks from the same prefix values with
+// the same expressions, tile boundaries inside a block are that block's own running sums (clamped into
+// the block's interval), so every output slot is written exactly once.  Same Philox keying and tie
 // rule (first j with cdf[j] >= pos, clamp) as the other engines.
 //
 // Storage: row c of x0 / x1 holds the filter's local particles at storage index
@@ -527,7 +529,7 @@ static __global__ void k_st_merge(StreamParams P, int obs) {
 // ---- K_B: resampling (scan + closed-form offspring ranges + staged scatter) ----
 // Same block -> tile ranges and prefetch as k_st_step.  A block's cdf interval comes from the block prefix
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
-// running sums of the tile partials.
+// running sums of the tile totals it computes itself (clamped into the block's interval).
 template <typename Model, typename Real, int PPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamParams P, int obs) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
