@@ -441,7 +441,7 @@ def main():
         "loglike": r0["loglike"],
     }
     if rank == 0 and not args.no_cpu_baseline:
-        Ns, Ts = 1 << 20, 12
+        Ns, Ts = 1 << 20, 200   # ~25 s of one host core: a bounded sample of the same workload (resampling steps included)
         secs, _, _ = cpu_sample(Ns, Ts)
         line["cpu_baseline"] = {"value": Ns * Ts / secs, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
                                 "sample": f"same model/config, N=2^20, first {Ts} of the {T} observations, 1 thread (the R "
