@@ -1,5 +1,6 @@
-"""Compile a user-model snippet with NVRTC exactly as bssm_model_compile does (no GPU needed): catches
-constructs NVRTC rejects before any GPU time is spent."""
+"""Compile a user-model snippet with NVRTC exactly as bssm_model_compile does -- the general engine's model kernels
+and the streaming engine's kernels, for sm_100a -- without a GPU: catches constructs NVRTC rejects (host headers in
+the embedded text, for instance) before any GPU time is spent.  tests/test_abi.py runs it."""
 import ctypes as C
 import os
 import sys
@@ -27,8 +28,20 @@ struct UserModel {
   template <typename R> static BSSM_DEV void move(R*, const double*, const R*, int, const R*, const double*) {}
 };
 '''
-prog = '#include "bssm_filter.cuh"\nnamespace bssm {\n#line 1 "user_model.cu"\n' + USER + "\n}\n" + '''
+prog = '#include "bssm_filter.cuh"\n#include "bssm_stream.cuh"\nnamespace bssm {\n#line 1 "user_model.cu"\n' + USER + "\n}\n" + '''
 namespace bssm {
+template __global__ void k_st_init<UserModel, float, 8, 256>(StreamParams);
+template __global__ void k_st_init<UserModel, double, 4, 256>(StreamParams);
+template __global__ void k_st_step<UserModel, float, 8, 256>(StreamParams, int);
+template __global__ void k_st_step<UserModel, double, 4, 256>(StreamParams, int);
+template __global__ void k_st_resample<UserModel, float, 8, 256>(StreamParams, int);
+template __global__ void k_st_resample<UserModel, double, 4, 256>(StreamParams, int);
+template __global__ void k_st_init<UserModel, float, 8, 128>(StreamParams);
+template __global__ void k_st_init<UserModel, double, 4, 128>(StreamParams);
+template __global__ void k_st_step<UserModel, float, 8, 128>(StreamParams, int);
+template __global__ void k_st_step<UserModel, double, 4, 128>(StreamParams, int);
+template __global__ void k_st_resample<UserModel, float, 8, 128>(StreamParams, int);
+template __global__ void k_st_resample<UserModel, double, 4, 128>(StreamParams, int);
 template __global__ void k_init<UserModel, float>(FilterDev);
 template __global__ void k_init<UserModel, double>(FilterDev);
 template __global__ void k_weight<UserModel, float>(FilterDev, int, int, int);
@@ -39,11 +52,11 @@ template __global__ void k_post<UserModel, double>(FilterDev, int);
 extern "C" __global__ void bssm_user_dims(int* o) { o[0] = bssm::UserModel::D; }
 '''
 nv = C.CDLL("libnvrtc.so.12")
-names = [b"bssm_common.cuh", b"bssm_models.cuh", b"bssm_filter.cuh"]
+names = [b"bssm_common.cuh", b"bssm_models.cuh", b"bssm_filter.cuh", b"bssm_slots.cuh", b"bssm_stream.cuh"]
 srcs = [open(os.path.join(CSRC, n.decode())).read().encode() for n in names]
 p = C.c_void_p()
-arr = (C.c_char_p * 3)
-assert nv.nvrtcCreateProgram(C.byref(p), prog.encode(), b"u.cu", 3, arr(*srcs), arr(*names)) == 0
+arr = (C.c_char_p * len(names))
+assert nv.nvrtcCreateProgram(C.byref(p), prog.encode(), b"u.cu", len(names), arr(*srcs), arr(*names)) == 0
 opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo"]
 rc = nv.nvrtcCompileProgram(p, len(opts), (C.c_char_p * len(opts))(*opts))
 n = C.c_size_t()

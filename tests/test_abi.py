@@ -66,3 +66,15 @@ def test_r_shim_compiles_against_stub_r_headers():
     src = open(os.path.join(ROOT, "r_shim", "src", "bssm_shim.c")).read()
     called = set(re.findall(r"\b(bssm_[a-z_0-9]+)\s*\(", src))
     assert called <= set(_header_symbols()), called - set(_header_symbols())
+
+
+def test_nvrtc_compiles_a_snippet_with_all_model_kernels_without_a_gpu():
+    """NVRTC needs no GPU to compile: the embedded header text (general kernels + streaming kernels) must stay free of
+    host headers and compile for sm_100a together with a user snippet -- exactly what bssm_model_compile does."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "nvrtc_check.py")], capture_output=True, text=True, timeout=300)
+    if "libnvrtc" in (r.stderr or "") and "cannot open shared object" in r.stderr:
+        pytest.skip("libnvrtc not installed")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "cubin bytes" in r.stdout
