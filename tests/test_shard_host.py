@@ -82,3 +82,31 @@ print("ok", rank)
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_closed_form_offspring_counts_equal_the_reference_resampler(orc):
+    """The persistent kernel and the streaming engine never search: source j owns the output slots
+    [F(c_{j-1}), F(c_j)) with F(c) = #{ i : (i + u_i) / n <= c } in closed form.  On the reference's own cdf
+    (sequential cumsum of w / sum(w), src/resampling.cpp:20-25) the offspring counts F(c_j) - F(c_{j-1}) must equal
+    the histogram of the reference's ancestors (first j with cdf[j] >= pos, clamp), slot for slot."""
+    from bayesssm_b200 import sharding as S
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 7, 1000, 4097):
+        for fam in ("lognormal", "few_heavy", "uniform"):
+            w = {"lognormal": np.exp(2.0 * rng.standard_normal(n)), "uniform": np.ones(n),
+                 "few_heavy": np.where(rng.random(n) < 0.02, 1.0, 1e-9) + 1e-300}[fam]
+            for fn in ("stratified", "systematic"):
+                u = rng.random(n) if fn == "stratified" else float(rng.random())
+                anc = orc.resample(fn, w, np.atleast_1d(u)) - 1
+                total = 0.0
+                for v in w:                      # Rcpp sugar sum: plain sequential double loop
+                    total += v
+                cdf = np.cumsum(w / total)       # sequential cumsum of the normalised weights
+                F = np.array([S.count_le(float(c), n, u) for c in cdf])
+                F[-1] = n                        # clamp: the last source takes what is left (src/resampling.cpp:33,60)
+                F = np.maximum.accumulate(F)
+                counts = np.diff(np.concatenate([[0], F]))
+                assert counts.sum() == n
+                assert np.array_equal(counts, np.bincount(anc, minlength=n)), (n, fam, fn)
+                # the slots of source j are contiguous and in order: expanding the counts reproduces the ancestor vector
+                assert np.array_equal(np.repeat(np.arange(n), counts), anc)
