@@ -657,8 +657,8 @@ double orc_log_prior(int kind, double a, double b, double x) {
 /* ------------------------------------------------------------------------- */
 enum { PH_PILOT = 1, PH_PILOT_RUN = 2, PH_MAIN = 3 };
 
-static int run_filter(const orc_pmmh_config *c, const double *y, const double *theta, int N, int ralg,
-                      int rfn, uint32_t run_id, uint32_t chain_id, double *loglike) {
+static int run_filter_se(const orc_pmmh_config *c, const double *y, const double *theta, int N, int ralg,
+                         int rfn, uint32_t run_id, uint32_t chain_id, double *loglike, double *state_est_out /* [(T+1) d] or NULL */) {
   model_dims md;
   get_dims(c->model, &md);
   orc_filter_config fc;
@@ -676,8 +676,13 @@ static int run_filter(const orc_pmmh_config *c, const double *y, const double *t
   r.ess = (double *)malloc(sizeof(double) * (size_t)(c->num_obs + 1));
   int st = orc_particle_filter(&fc, y, th, &r);
   *loglike = r.loglike;
+  if (state_est_out) memcpy(state_est_out, r.state_est, sizeof(double) * (size_t)(c->num_obs + 1) * md.d);
   free(r.state_est); free(r.ess);
   return st;
+}
+static int run_filter(const orc_pmmh_config *c, const double *y, const double *theta, int N, int ralg,
+                      int rfn, uint32_t run_id, uint32_t chain_id, double *loglike) {
+  return run_filter_se(c, y, theta, N, ralg, rfn, run_id, chain_id, loglike, NULL);
 }
 static int priors_finite(const orc_pmmh_config *c, const double *th, double *sum_out) {
   double s = 0.0; int ok = 1;
@@ -792,10 +797,20 @@ int orc_pmmh_chain(const orc_pmmh_config *c, const double *y, const double *init
   }
   /* main chain R/pmmh.R:395-500 */
   memcpy(cur, res->pilot_theta_mean, sizeof(double) * (size_t)p);
-  st = run_filter(c, y, cur, res->target_n, ORC_SISAR, ORC_STRATIFIED, ((uint32_t)PH_MAIN << 28) | 0u, chain_id, &cur_ll);
-  if (st) return st;
+  /* latent state estimates (R/pmmh.R:400,420,494-499): current_state_est travels with the chain */
+  model_dims md_se;
+  get_dims(c->model, &md_se);
+  const size_t se_len = (size_t)(c->num_obs + 1) * md_se.d;
+  double *cur_se = NULL, *prop_se = NULL;
+  if (res->latent_state_chain) {
+    cur_se = (double *)malloc(sizeof(double) * se_len);
+    prop_se = (double *)malloc(sizeof(double) * se_len);
+  }
+  st = run_filter_se(c, y, cur, res->target_n, ORC_SISAR, ORC_STRATIFIED, ((uint32_t)PH_MAIN << 28) | 0u, chain_id, &cur_ll, cur_se);
+  if (st) { free(cur_se); free(prop_se); return st; }
   memcpy(res->theta_chain, cur, sizeof(double) * (size_t)p);
   res->loglike_chain[0] = cur_ll;
+  if (cur_se) memcpy(res->latent_state_chain, cur_se, sizeof(double) * se_len);
   res->n_accept = 0;
   for (int it = 1; it < c->m; it++) {
     double xi[8];
@@ -813,21 +828,27 @@ int orc_pmmh_chain(const orc_pmmh_config *c, const double *y, const double *init
     if (!priors_finite(c, prop, &lp_prop_sum)) { /* :435-442 reject without running the filter */
       memcpy(res->theta_chain + (size_t)it * p, cur, sizeof(double) * (size_t)p);
       res->loglike_chain[it] = cur_ll;
+      if (cur_se) memcpy(res->latent_state_chain + (size_t)it * se_len, cur_se, sizeof(double) * se_len);
       continue;
     }
     double prop_ll;
-    st = run_filter(c, y, prop, res->target_n, ORC_SISAR, ORC_STRATIFIED, ((uint32_t)PH_MAIN << 28) | (uint32_t)it, chain_id, &prop_ll);
-    if (st) return st;
+    st = run_filter_se(c, y, prop, res->target_n, ORC_SISAR, ORC_STRATIFIED, ((uint32_t)PH_MAIN << 28) | (uint32_t)it, chain_id, &prop_ll, prop_se);
+    if (st) { free(cur_se); free(prop_se); return st; }
     priors_finite(c, cur, &lp_cur_sum);
     double num = prop_ll + lp_prop_sum + orc_log_jacobian(prop, c->transform, p); /* :474-483 */
     double den = cur_ll + lp_cur_sum + orc_log_jacobian(cur, c->transform, p);
     double ratio = num - den;
     if (isnan(ratio)) ratio = -INFINITY;
     double u = orc_noise_uniform(seed, (uint32_t)PH_MAIN << 28, chain_id, (uint32_t)it, TAG_THETA_U, 0, 0);
-    if (log(u) < ratio) { memcpy(cur, prop, sizeof(double) * (size_t)p); cur_ll = prop_ll; res->n_accept++; }
+    if (log(u) < ratio) {
+      memcpy(cur, prop, sizeof(double) * (size_t)p); cur_ll = prop_ll; res->n_accept++;
+      if (cur_se) memcpy(cur_se, prop_se, sizeof(double) * se_len);
+    }
     memcpy(res->theta_chain + (size_t)it * p, cur, sizeof(double) * (size_t)p);
     res->loglike_chain[it] = cur_ll;
+    if (cur_se) memcpy(res->latent_state_chain + (size_t)it * se_len, cur_se, sizeof(double) * se_len);
   }
+  free(cur_se); free(prop_se);
   return ORC_OK;
 }
 

@@ -150,6 +150,7 @@ typedef struct {
   double *theta_chain;       /* [m][p] (burn-in NOT removed) */
   double *loglike_chain;     /* [m] */
   int n_accept;
+  double *latent_state_chain; /* [m][T+1][d] or NULL: state_est of the filter run behind every draw (R/pmmh.R:420,494-499) */
 } orc_pmmh_chain_result;
 
 /* one chain of R/pmmh.R:345-505 (pilot R/pmmh_tuning.R:111-317, pilot run :29-64) */

@@ -104,7 +104,7 @@ def filter_run(ctx, model, algorithm, resample_algorithm, resample_fn, N, y, the
 def pmmh_run(ctx, model, algorithm, y, init_theta, prior_kind, prior_a, prior_b, transform, pilot_proposal_sd,
              pilot_n, pilot_m, pilot_reps, m, seed, chain_id_base=0, pilot_resample_algorithm=2, pilot_resample_fn=0,
              fixed_num_particles=0, consts=None, obs_times=None, precision=nat.F64, skip_pilot=False,
-             proposal_chol=None, engine=nat.ENGINE_AUTO):
+             proposal_chol=None, engine=nat.ENGINE_AUTO, return_latent_state_est=False, state_dim=1):
     y = _d(y)
     if y.ndim == 1:
         y = y[:, None]
@@ -151,6 +151,10 @@ def pmmh_run(ctx, model, algorithm, y, init_theta, prior_kind, prior_a, prior_b,
     for k in ("target_n", "n_accept", "status"):
         out[k] = np.zeros(Cn, dtype=np.int32)
         setattr(res, k, out[k].ctypes.data_as(i32p))
+    if return_latent_state_est:
+        cfg.return_latent_state_est = 1
+        out["latent_state_chain"] = np.zeros((Cn, m, T + 1, state_dim))
+        res.latent_state_chain = _p(out["latent_state_chain"])
     nat.check(ctx.lib.bssm_pmmh_run(ctx.handle, C.byref(cfg), _p(y), _p(init_theta), C.byref(res)))
     out["pilot_ms"], out["main_ms"] = res.pilot_ms, res.main_ms
     return out

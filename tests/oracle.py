@@ -57,7 +57,7 @@ class PmmhConfig(C.Structure):
 class PmmhChainResult(C.Structure):
     _fields_ = [("pilot_theta_chain", dp), ("pilot_loglike_chain", dp), ("pilot_theta_mean", dp),
                 ("pilot_theta_cov", dp), ("pilot_loglikes", dp), ("target_n", C.c_int), ("proposal_chol", dp),
-                ("theta_chain", dp), ("loglike_chain", dp), ("n_accept", C.c_int)]
+                ("theta_chain", dp), ("loglike_chain", dp), ("n_accept", C.c_int), ("latent_state_chain", dp)]
 
 
 _lib = None
@@ -221,7 +221,7 @@ def kalman_loglik(y, phi, sigma_x, sigma_y):
 
 def pmmh_chain(model, algorithm, y, init_theta, prior_kind, prior_a, prior_b, transform, pilot_proposal_sd,
                pilot_n, pilot_m, pilot_reps, m, chain_id, seed, pilot_resample_algorithm=2, pilot_resample_fn=0,
-               fixed_num_particles=0, consts=None, obs_times=None):
+               fixed_num_particles=0, consts=None, obs_times=None, return_latent_state_est=False):
     y = _d(y)
     if y.ndim == 1:
         y = y[:, None]
@@ -252,6 +252,9 @@ def pmmh_chain(model, algorithm, y, init_theta, prior_kind, prior_a, prior_b, tr
     res = PmmhChainResult()
     for k, v in out.items():
         setattr(res, k, _p(v))
+    if return_latent_state_est:
+        out["latent_state_chain"] = np.zeros((m, T + 1, model_dims(model)["d"]))
+        res.latent_state_chain = _p(out["latent_state_chain"])
     it = _d(init_theta)
     st = lib().orc_pmmh_chain(C.byref(cfg), _p(y), _p(it), chain_id, C.byref(res))
     out["status"] = st

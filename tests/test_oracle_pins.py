@@ -147,3 +147,33 @@ def test_default_tune_control_clamp(orc):
                        pilot_n=30, pilot_m=40, pilot_reps=5, m=20, chain_id=0, seed=1)
     assert r["status"] == 0 and 50 <= r["target_n"] <= 1000
     assert np.isfinite(r["theta_chain"]).all()
+
+
+def test_pmmh_latent_state_chain_travels_with_the_draws(orc):
+    # R/pmmh.R:400,420,494-499: current_state_est is replaced on acceptance only; draw i carries the state estimate of
+    # the filter run (run id = main phase << 28 | iteration of the accepting proposal, stream = chain id) behind it
+    rng = np.random.default_rng(1405)
+    x, ys = rng.standard_normal(), []
+    for _ in range(10):
+        x = 0.8 * x + np.sin(x) + rng.standard_normal()
+        ys.append(x + 0.5 * rng.standard_normal())
+    y = np.array(ys)
+    kw = dict(prior_kind=[3, 2, 2], prior_a=[0., 1., 1.], prior_b=[1., 0., 0.], transform=[2, 1, 1],
+              pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=20, pilot_reps=5, m=30, seed=7)
+    r = orc.pmmh_chain(0, 0, y, [0.8, 1.0, 0.5], chain_id=3, return_latent_state_est=True, **kw)
+    plain = orc.pmmh_chain(0, 0, y, [0.8, 1.0, 0.5], chain_id=3, **kw)
+    np.testing.assert_array_equal(r["theta_chain"], plain["theta_chain"])     # asking for it changes nothing else
+    np.testing.assert_array_equal(r["loglike_chain"], plain["loglike_chain"])
+    lat, th = r["latent_state_chain"], r["theta_chain"]
+    assert lat.shape == (30, len(y) + 1, 1)
+    moved = stayed = 0
+    for i in range(30):
+        if i > 0 and np.array_equal(th[i], th[i - 1]):
+            np.testing.assert_array_equal(lat[i], lat[i - 1])
+            stayed += 1
+            continue
+        ref = orc.particle_filter(0, 0, 2, 0, r["target_n"], y, th[i], seed=7, run_id=(3 << 28) | i, stream=3)
+        np.testing.assert_array_equal(lat[i, :, 0], ref["state_est"][:, 0])
+        assert ref["loglike"] == r["loglike_chain"][i]
+        moved += 1
+    assert moved == r["n_accept"] + 1 and stayed > 0

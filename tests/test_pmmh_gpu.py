@@ -26,10 +26,10 @@ def test_chains_match_oracle(orc, engine, transform):
     y = readme_data(12, rng)
     inits = np.array([[0.8, 1.0, 0.5], [0.5, 0.7, 1.2], [0.3, 1.5, 0.8]])
     kw = dict(transform=transform, pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=30, pilot_reps=6, m=40, seed=99)
-    got = eh.pmmh_run(engine, 0, 0, y, inits, chain_id_base=4, **PRIOR, **kw)
+    got = eh.pmmh_run(engine, 0, 0, y, inits, chain_id_base=4, return_latent_state_est=True, **PRIOR, **kw)
     assert (got["status"] == 0).all()
     for c in range(3):
-        ref = orc.pmmh_chain(0, 0, y, inits[c], chain_id=4 + c, **PRIOR, **kw)
+        ref = orc.pmmh_chain(0, 0, y, inits[c], chain_id=4 + c, return_latent_state_est=True, **PRIOR, **kw)
         assert ref["status"] == 0
         np.testing.assert_allclose(got["pilot_theta_chain"][c], ref["pilot_theta_chain"], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(got["pilot_loglike_chain"][c], ref["pilot_loglike_chain"], rtol=1e-9)
@@ -41,6 +41,8 @@ def test_chains_match_oracle(orc, engine, transform):
         np.testing.assert_allclose(got["theta_chain"][c], ref["theta_chain"], rtol=1e-8, atol=1e-12)
         np.testing.assert_allclose(got["loglike_chain"][c], ref["loglike_chain"], rtol=1e-8)
         assert got["n_accept"][c] == ref["n_accept"]
+        # R/pmmh.R:420,494-499: the state estimate behind every draw, carried over on rejections
+        np.testing.assert_allclose(got["latent_state_chain"][c], ref["latent_state_chain"], rtol=1e-8, atol=1e-10)
 
 
 def test_invalid_initial_parameters(engine):
