@@ -126,6 +126,8 @@ SYMBOLS = {
     "bssm_model_compile": (C.c_int, [_vp, C.c_char_p, c_int_p]),
     "bssm_model_compile_log": (C.c_char_p, [_vp]),
     "bssm_pmmh_run": (C.c_int, [_vp, C.POINTER(PmmhConfig), c_double_p, c_double_p, C.POINTER(PmmhResult)]),
+    "bssm_mcmc_diagnostics": (C.c_int, [_vp, c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
+                                        c_int32_p, C.POINTER(C.c_float)]),
     "bssm_transform": (C.c_double, [C.c_double, C.c_int]),
     "bssm_back_transform": (C.c_double, [C.c_double, C.c_int]),
     "bssm_log_jacobian": (C.c_double, [c_double_p, c_int_p, C.c_int]),

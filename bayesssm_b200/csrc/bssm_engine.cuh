@@ -45,6 +45,8 @@ enum ScratchSlot {
   SL_FAST_LAST = SL_FAST_BASE + 7,
   SL_ST_BASE,   /* streaming engine */
   SL_ST_LAST = SL_ST_BASE + 11,
+  SL_DG_BASE,   /* MCMC diagnostics (bssm_diag.cu) */
+  SL_DG_LAST = SL_DG_BASE + 5,
   SL_COUNT
 };
 

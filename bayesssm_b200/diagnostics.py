@@ -1,77 +1,73 @@
-"""MCMC diagnostics called on every pmmh() return (R/ESS.R:30-104, R/rhat.R:27-67); host numpy
-(post-hoc, not on the device hot path)."""
+"""MCMC diagnostics called on every pmmh() return: ess() (R/ESS.R:30-145) and rhat() (R/rhat.R:27-108), computed on
+the device for all parameters at once through bssm_mcmc_diagnostics (csrc/bssm_diag.cuh).  This module only
+checks the input the way the reference does and maps NA / warnings; nothing is computed on the CPU."""
 from __future__ import annotations
 
+import ctypes as C
 import warnings
 
 import numpy as np
 
+from . import _native as nat
 
-def _as_matrix(chains):
-    if hasattr(chains, "to_numpy"):
-        chains = chains.to_numpy()
-    if not isinstance(chains, np.ndarray) or chains.ndim != 2:
-        raise TypeError("Input 'chains' must be a matrix or a data frame.")
-    return np.asarray(chains, dtype=np.float64)
+_ZERO_VAR = "One or more chains have zero variance."
 
 
-def _acf(x):
-    """stats::acf(x, lag.max = m - 1)$acf: biased autocovariance normalised by lag 0 (FFT)."""
-    m = len(x)
-    xc = x - x.mean()
-    nfft = 1 << int(np.ceil(np.log2(2 * m)))
-    f = np.fft.rfft(xc, nfft)
-    ac = np.fft.irfft(f * np.conj(f), nfft)[:m] / m
-    return ac / ac[0]
+def device_diagnostics(draws, burn_in=0, want_ess=True, want_rhat=True, ctx=None):
+    """draws [k][m][p] (chains, iterations, parameters) -> dict(ess [p], rhat [p], flags [p], device_ms)."""
+    ctx = ctx or nat.default_context()
+    draws = np.ascontiguousarray(draws, dtype=np.float64)
+    k, m, p = draws.shape
+    out_ess, out_rhat = np.full(p, np.nan), np.full(p, np.nan)
+    flags = np.zeros(p, dtype=np.int32)
+    ms = C.c_float(0.0)
+    st = ctx.lib.bssm_mcmc_diagnostics(ctx.handle, draws.ctypes.data_as(nat.c_double_p), k, m, p, int(burn_in),
+                                       out_ess.ctypes.data_as(nat.c_double_p) if want_ess else None,
+                                       out_rhat.ctypes.data_as(nat.c_double_p) if want_rhat else None,
+                                       flags.ctypes.data_as(nat.c_int32_p), C.byref(ms))
+    if st == nat.ERR_BAD_ARG:
+        raise ValueError(nat.last_error())   # "Number of iterations / chains must be at least 2."
+    nat.check(st)
+    return {"ess": out_ess, "rhat": out_rhat, "flags": flags, "device_ms": ms.value}
 
 
-def ess(chains):
-    """Multi-chain effective sample size, Geyer initial monotone sequence (R/ESS.R:30-104)."""
-    mat = _as_matrix(chains)
-    m, k = mat.shape
+def _frame_to_draws(df):
+    """Data frame with a 'chain' column -> (parameter names, draws [k][m][p]) (R/ESS.R:114-141, R/rhat.R:77-104)."""
+    if "chain" not in df.columns:
+        raise ValueError("Data frame must contain a 'chain' column.")
+    params = [c for c in df.columns if c != "chain"]
+    ids = list(dict.fromkeys(df["chain"].tolist()))
+    per_chain = [df.loc[df["chain"] == i, params].to_numpy(dtype=np.float64) for i in ids]
+    if len({a.shape[0] for a in per_chain}) != 1:
+        raise ValueError("Not all chains have the same number of iterations.")
+    return params, np.stack(per_chain, axis=0)
+
+
+def _run(chains, which, ctx):
+    if hasattr(chains, "columns") and hasattr(chains, "loc"):
+        params, draws = _frame_to_draws(chains)
+    elif isinstance(chains, np.ndarray) and chains.ndim == 2:
+        params, draws = None, np.asarray(chains, dtype=np.float64).T[:, :, None]   # m x k matrix -> [k][m][1]
+    else:
+        raise TypeError("Input must be a matrix or a data frame with a 'chain' column.")
+    k, m, _ = draws.shape
     if m < 2:
         raise ValueError("Number of iterations must be at least 2.")
-    if k < 2:
+    if which == "ess" and k < 2:
         raise ValueError("Number of chains must be at least 2.")
-    chain_means = mat.mean(axis=0)
-    b = m / (k - 1) * np.sum((chain_means - chain_means.mean()) ** 2)
-    chain_vars = mat.var(axis=0, ddof=1)
-    if np.any(chain_vars == 0):
-        warnings.warn("One or more chains have zero variance.")
-        return float("nan")
-    w = chain_vars.mean()
-    var_hat = ((m - 1) / m) * w + b / m
-    acf_matrix = np.stack([_acf(mat[:, i]) for i in range(k)], axis=1)  # [m][k]
-    hat_rho = 1.0 - (w - (acf_matrix * chain_vars).sum(axis=1) / k) / var_hat
-    max_pairs = (m - 1) // 2
-    pairs = hat_rho[1:2 * max_pairs:2] + hat_rho[2:2 * max_pairs + 1:2]
-    pairs = np.minimum.accumulate(pairs) if len(pairs) >= 2 else pairs
-    neg = np.flatnonzero(pairs < 0)
-    stop = neg[0] if len(neg) else len(pairs)
-    tau = 1.0 + 2.0 * pairs[:stop].sum()
-    return float(k * m / tau)
+    r = device_diagnostics(draws, 0, want_ess=which == "ess", want_rhat=which == "rhat", ctx=ctx)
+    if np.any(r["flags"] & (1 if which == "ess" else 2)):
+        warnings.warn(_ZERO_VAR)
+    vals = r[which]
+    return float(vals[0]) if params is None else {name: float(v) for name, v in zip(params, vals)}
 
 
-def rhat(chains):
-    """Split-R-hat with the reference's [0.99, 1] -> 1 clamp (R/rhat.R:27-67)."""
-    mat = _as_matrix(chains)
-    m, k = mat.shape
-    if m < 2:
-        raise ValueError("Number of iterations must be at least 2.")
-    if m % 2 == 1:
-        mat = mat[:-1]
-        m -= 1
-    h = m // 2
-    split = np.empty((h, 2 * k))
-    split[:, 0::2] = mat[:h]
-    split[:, 1::2] = mat[h:]
-    chain_means = split.mean(axis=0)
-    b = m / (2 * k - 1) * np.sum((chain_means - chain_means.mean()) ** 2)
-    chain_vars = split.var(axis=0, ddof=1)
-    if np.any(chain_vars == 0):
-        warnings.warn("One or more chains have zero variance.")
-        return float("nan")
-    w = chain_vars.mean()
-    var_hat = ((m - 1) / m) * w + b / m
-    r = float(np.sqrt(var_hat / w))
-    return 1.0 if 0.99 <= r <= 1.0 else r
+def ess(chains, ctx=None):
+    """Multi-chain effective sample size, Geyer's initial monotone sequence (R/ESS.R:30-145).  `chains`: an m x k
+    matrix (iterations x chains) -> float, or a data frame with a 'chain' column -> dict per parameter."""
+    return _run(chains, "ess", ctx)
+
+
+def rhat(chains, ctx=None):
+    """Split R-hat; values in [0.99, 1] are reported as 1 (R/rhat.R:27-108).  Input as for ess()."""
+    return _run(chains, "rhat", ctx)

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native as nat
 from . import filters as _filters
-from .diagnostics import ess, rhat
+from .diagnostics import _ZERO_VAR, device_diagnostics
 from .models import resolve_model
 
 
@@ -221,18 +221,16 @@ def pmmh(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, log_priors
         df.insert(0, "chain", str(c + 1))                      # bind_rows(.id = "chain"): character ids
         frames.append(df)
     theta_chain = pd.concat(frames, ignore_index=True)
-    param_ess, param_rhat = {}, {}
-    for j, name in enumerate(order):                           # R/pmmh.R:570-594
-        mat = post[:, :, j].T
-        if num_chains > 1:
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                param_ess[name] = ess(mat) if mat.shape[0] >= 2 else float("nan")
-        else:
-            param_ess[name] = float("nan")
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            param_rhat[name] = rhat(mat) if mat.shape[0] >= 2 else float("nan")
+    # R/pmmh.R:570-594: ess() (two or more chains) and rhat() of every parameter -- one device call over the
+    # draws as they came back, burn-in skipped there
+    param_ess = {name: float("nan") for name in order}
+    param_rhat = dict(param_ess)
+    if m - burn_in >= 2:
+        dg = device_diagnostics(out["theta_chain"], burn_in, want_ess=num_chains > 1, ctx=ctx)
+        for j, name in enumerate(order):
+            param_ess[name], param_rhat[name] = float(dg["ess"][j]), float(dg["rhat"][j])
+        if np.any(dg["flags"] & (3 if num_chains > 1 else 2)):
+            warnings.warn(_ZERO_VAR)
     if num_chains == 1:
         print("ESS cannot be computed with only one chain Run at least 2 chains.")
     result = PmmhOutput(theta_chain=theta_chain, diagnostics={"ess": param_ess, "rhat": param_rhat})

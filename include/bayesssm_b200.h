@@ -257,6 +257,18 @@ typedef struct {
 int bssm_pmmh_run(bssm_ctx *ctx, const bssm_pmmh_config *cfg, const double *y, const double *init_theta,
                   bssm_pmmh_result *res);
 
+/* MCMC diagnostics of the draws, for all parameters at once: replaces ess() (R/ESS.R:30-104: between/within chain
+ * variances, stats::acf of every chain, Geyer's initial monotone sequence) and rhat() (R/rhat.R:27-67: split R-hat, values in
+ * [0.99, 1] reported as 1), which the reference calls per parameter on every pmmh() return (R/pmmh.R:570-594).
+ * draws: [k][m_total][p] host, chain-major -- the layout of bssm_pmmh_result.theta_chain; with p = 1 it is R's m x k matrix in
+ * column-major order.  Iterations [burn_in, m_total) are used (R/pmmh.R:540-545).  ess, rhat: [p] host outputs, either may be
+ * NULL; ess needs k >= 2 ("Number of chains must be at least 2."), both need m_total - burn_in >= 2 ("Number of iterations must
+ * be at least 2.").  flags: [p] or NULL; bit 0 = a chain has zero variance (ess is NaN: R returns NA with the warning "One or
+ * more chains have zero variance."), bit 1 = a half chain has (rhat is NaN, same warning).  device_ms: time of the kernels, or
+ * NULL. */
+int bssm_mcmc_diagnostics(bssm_ctx *ctx, const double *draws, int k, int m_total, int p, int burn_in, double *ess, double *rhat,
+                          int32_t *flags, float *device_ms);
+
 /* transforms, exported so the R side and the tests use one definition (R/utils.R:102-152) */
 double bssm_transform(double theta, int tr);
 double bssm_back_transform(double z, int tr);

@@ -69,29 +69,6 @@ def test_pmmh_argument_validation():
         b.pmmh(**{**base, "pf_wrapper": print})
 
 
-def test_ess_and_rhat_match_reference_behaviour():
-    # tests/testthat/test-ESS.R, test-rhat.R
-    rng = np.random.default_rng(1405)
-    iid = rng.standard_normal((2000, 4))
-    assert abs(b.ess(iid) - 8000) < 0.05 * 8000 * 2
-    assert b.rhat(iid) < 1.01
-    ar = np.zeros((2000, 4))
-    for t in range(1, 2000):
-        ar[t] = 0.9 * ar[t - 1] + rng.standard_normal(4)
-    assert b.ess(ar) < 0.3 * 8000
-    shifted = iid + np.array([0, 0, 5, 5])
-    assert b.rhat(shifted) > 2
-    assert b.rhat(iid[:1999]) < 1.01                      # odd length: last iteration dropped
-    with pytest.raises(ValueError, match="at least 2"):
-        b.ess(iid[:, :1])
-    with pytest.raises(TypeError, match="matrix or a data frame"):
-        b.ess([1, 2, 3])
-    with pytest.warns(UserWarning, match="zero variance"):
-        assert np.isnan(b.rhat(np.ones((10, 2))))
-    near = np.tile(np.array([0.0, 1.0] * 50)[:, None], (1, 2))
-    assert b.rhat(near) == 1.0                             # [0.99, 1] -> 1 clamp (R/rhat.R:63-65)
-
-
 def test_shard_chains_partition():
     for n, w in ((1024, 8), (10, 4), (7, 2), (3, 3)):
         parts = [D.shard_chains(n, r, w) for r in range(w)]
