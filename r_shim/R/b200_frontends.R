@@ -155,11 +155,12 @@ pmmh <- function(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, lo
   })
   theta_chain <- dplyr::bind_rows(chains, .id = "chain")
   param_ess <- list(); param_rhat <- list()
-  for (j in seq_along(model$params)) {                            # R/pmmh.R:570-594
-    mat <- sapply(chains, function(df) df[[j]])
+  for (j in seq_along(model$params)) {                            # R/pmmh.R:570-594; ess() / rhat() below run on the device
+    mat <- matrix(r$theta_chain[keep, j, ], ncol = num_chains)
     param_ess[[model$params[j]]] <- if (num_chains > 1) ess(mat) else NA
     param_rhat[[model$params[j]]] <- rhat(mat)
   }
+  if (num_chains == 1) message("ESS cannot be computed with only one chain Run at least 2 chains.")
   result <- list(theta_chain = theta_chain, diagnostics = list(ess = param_ess, rhat = param_rhat))
   if (return_latent_state_est)                                     # array [T+1, d, m, chain] -> list of lists as R/pmmh.R:547-552
     result$latent_state_chain <- lapply(seq_len(num_chains), function(c) lapply(keep, function(i) drop(r$latent_state_chain[, , i, c])))
@@ -171,6 +172,35 @@ pmmh <- function(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, lo
     warning("Some Rhat values are above 1.01, indicating that the chains have not converged.")
   result
 }
+
+# ---- ess() / rhat() (R/ESS.R:30-145, R/rhat.R:27-108): same inputs, messages and NA + warning behaviour; the
+# variances, the autocorrelations of every chain and Geyer's truncation are computed by bssm_mcmc_diagnostics ----
+.b200_diag <- function(chains, which) {
+  one <- function(mat) {
+    if (nrow(mat) < 2) stop("Number of iterations must be at least 2.")
+    if (which == "ess" && ncol(mat) < 2) stop("Number of chains must be at least 2.")
+    storage.mode(mat) <- "double"
+    r <- .Call("_bayesSSM_b200_mcmc_diagnostics", mat, as.integer(which == "ess"))
+    if (bitwAnd(r$flags, if (which == "ess") 1L else 2L) != 0L) {
+      warning("One or more chains have zero variance.")
+      return(NA)
+    }
+    r[[which]]
+  }
+  if (!is.matrix(chains) && !is.data.frame(chains))
+    stop("Input must be a matrix or a data frame with a 'chain' column.")
+  if (is.matrix(chains)) return(one(chains))
+  if (!"chain" %in% names(chains)) stop("Data frame must contain a 'chain' column.")
+  param_cols <- setdiff(names(chains), "chain")
+  chain_ids <- unique(chains$chain)
+  sapply(param_cols, function(param) {
+    param_data <- lapply(chain_ids, function(chain) chains[[param]][chains$chain == chain])
+    if (length(unique(sapply(param_data, length))) != 1) stop("Not all chains have the same number of iterations.")
+    one(do.call(cbind, param_data))
+  })
+}
+ess <- function(chains) .b200_diag(chains, "ess")
+rhat <- function(chains) .b200_diag(chains, "rhat")
 
 # ---- one filter larger than one GPU: particle-sharded over the GPUs of a box, one R process per GPU ----
 # rank 0: id <- b200_shard_unique_id(); send it to the other ranks (Rmpi::mpi.bcast, a file, a socket);

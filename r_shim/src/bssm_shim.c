@@ -303,6 +303,25 @@ SEXP _bayesSSM_b200_device_info(void) {
   return Rf_mkString(name);
 }
 
+/* ess() / rhat() of one parameter (R/ESS.R:30-104, R/rhat.R:27-67): `mat` is the reference's m x k REAL matrix
+ * (iterations x chains); column-major storage is exactly draws[k][m][1] of bssm_mcmc_diagnostics.  Returns
+ * list(ess, rhat, flags); the R wrapper turns flags into NA + warning("One or more chains have zero variance."). */
+SEXP _bayesSSM_b200_mcmc_diagnostics(SEXP mat, SEXP want_ess_) {
+  if (!Rf_isMatrix(mat)) Rf_error("Input must be a matrix or a data frame with a 'chain' column.");
+  const int m = Rf_nrows(mat), k = Rf_ncols(mat), want_ess = Rf_asInteger(want_ess_);
+  double ess = NA_REAL, rhat = NA_REAL;
+  int32_t flags = 0;
+  if (bssm_mcmc_diagnostics(ctx_get(), REAL(mat), k, m, 1, 0, want_ess ? &ess : NULL, &rhat, &flags, NULL) != BSSM_OK)
+    Rf_error("%s", bssm_last_error()); /* "Number of iterations / chains must be at least 2." */
+  const char *names[] = {"ess", "rhat", "flags", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarReal((flags & 1) || !want_ess ? NA_REAL : ess));
+  SET_VECTOR_ELT(out, 1, Rf_ScalarReal((flags & 2) ? NA_REAL : rhat));
+  SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(flags));
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_bayesSSM_resample_multinomial_cpp", (DL_FUNC)&_bayesSSM_resample_multinomial_cpp, 2},
     {"_bayesSSM_resample_stratified_cpp", (DL_FUNC)&_bayesSSM_resample_stratified_cpp, 2},
@@ -311,6 +330,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bayesSSM_b200_pmmh", (DL_FUNC)&_bayesSSM_b200_pmmh, 3},
     {"_bayesSSM_b200_device_info", (DL_FUNC)&_bayesSSM_b200_device_info, 0},
     {"_bayesSSM_b200_model_compile", (DL_FUNC)&_bayesSSM_b200_model_compile, 1},
+    {"_bayesSSM_b200_mcmc_diagnostics", (DL_FUNC)&_bayesSSM_b200_mcmc_diagnostics, 2},
     {"_bayesSSM_b200_shard_unique_id", (DL_FUNC)&_bayesSSM_b200_shard_unique_id, 0},
     {"_bayesSSM_b200_shard_init", (DL_FUNC)&_bayesSSM_b200_shard_init, 3},
     {"_bayesSSM_b200_shard_filter", (DL_FUNC)&_bayesSSM_b200_shard_filter, 3},
