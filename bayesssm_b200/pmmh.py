@@ -55,16 +55,37 @@ _TRANSFORMS = {"identity": nat.TR_IDENTITY, "log": nat.TR_LOG, "logit": nat.TR_L
 
 class PmmhOutput(dict):
     """`pmmh_output` (R/pmmh.R:599-608): theta_chain (DataFrame with a leading character `chain` column),
-    diagnostics = {ess, rhat}, optional latent_state_chain."""
+    diagnostics = {ess, rhat}, optional latent_state_chain.  str() is print.pmmh_output (R/print.R:30-66),
+    summary() is summary.pmmh_output (R/summary.R:28-54)."""
 
-    def __str__(self):  # R/print.R:30-66 in spirit
+    def _param_names(self):
+        return [c for c in self["theta_chain"].columns if c != "chain"]
+
+    def summary(self):
+        """Data frame indexed by parameter: mean, sd, median, 2.5%, 97.5% (stats::quantile's default type 7 = numpy's
+        linear interpolation), ESS, Rhat -- unrounded (R/summary.R:33-53)."""
+        import pandas as pd
         tc = self["theta_chain"]
-        lines = ["PMMH Results Summary:"]
-        for name in [c for c in tc.columns if c != "chain"]:
-            col = tc[name].to_numpy()
-            lines.append(f" {name:>10s}  mean {col.mean():8.4f}  sd {col.std(ddof=1):8.4f}  "
-                         f"ESS {self['diagnostics']['ess'][name]:8.1f}  Rhat {self['diagnostics']['rhat'][name]:6.3f}")
-        return "\n".join(lines)
+        rows = {}
+        for name in self._param_names():
+            x = tc[name].to_numpy(dtype=np.float64)
+            lo, hi = np.quantile(x, [0.025, 0.975])
+            rows[name] = {"mean": x.mean(), "sd": x.std(ddof=1), "median": np.median(x), "2.5%": lo, "97.5%": hi,
+                          "ESS": self["diagnostics"]["ess"][name], "Rhat": self["diagnostics"]["rhat"][name]}
+        return pd.DataFrame.from_dict(rows, orient="index")
+
+    def __str__(self):
+        """"PMMH Results Summary:" and one row per parameter; statistics rounded to 2 digits, ESS floored, Rhat
+        rounded to 3 (R/print.R:34-63)."""
+        import pandas as pd
+        sm = self.summary()
+        tab = pd.DataFrame({"Parameter": sm.index, "Mean": sm["mean"].round(2).to_numpy(), "SD": sm["sd"].round(2).to_numpy(),
+                            "Median": sm["median"].round(2).to_numpy(), "2.5%": sm["2.5%"].round(2).to_numpy(),
+                            "97.5%": sm["97.5%"].round(2).to_numpy(), "ESS": np.floor(sm["ESS"].to_numpy(dtype=np.float64)),
+                            "Rhat": sm["Rhat"].round(3).to_numpy()})
+        if np.isfinite(tab["ESS"]).all():
+            tab["ESS"] = tab["ESS"].astype(np.int64)
+        return "PMMH Results Summary:\n" + tab.to_string(index=False)
 
 
 def run_chains(ctx, model, algorithm, y, init_theta, prior_specs, transforms, tune_control, m, seed,

@@ -107,3 +107,31 @@ print("ok", rank)
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_pmmh_output_summary_and_print():
+    """tests/testthat/test-summary.R:1-27 (summary.pmmh_output, R/summary.R:28-54) and print.pmmh_output
+    (R/print.R:30-66): dummy chains, `chain` as the LAST column as in the reference's test."""
+    import pandas as pd
+    from bayesssm_b200.pmmh import PmmhOutput
+    rng = np.random.default_rng(1)
+    chains = pd.concat([pd.DataFrame({"param1": rng.standard_normal(100), "param2": rng.standard_normal(100), "chain": c})
+                        for c in (1, 2)], ignore_index=True)
+    out = PmmhOutput(theta_chain=chains, diagnostics={"ess": {"param1": 200.9, "param2": 190.0},
+                                                      "rhat": {"param1": 1.0104, "param2": 1.0}})
+    sm = out.summary()
+    assert list(sm.columns) == ["mean", "sd", "median", "2.5%", "97.5%", "ESS", "Rhat"]
+    assert list(sm.index) == ["param1", "param2"]
+    assert sm.loc["param1", "ESS"] == 200.9 and sm.loc["param1", "Rhat"] == 1.0104
+    x = chains["param2"].to_numpy()
+    np.testing.assert_allclose(sm.loc["param2", ["mean", "sd", "median"]].to_numpy(dtype=float),
+                               [x.mean(), x.std(ddof=1), np.median(x)])
+    xs = np.sort(x)                                        # quantile type 7: h = (n - 1) q, linear between order statistics
+    h = (len(xs) - 1) * 0.025
+    np.testing.assert_allclose(sm.loc["param2", "2.5%"], xs[int(h)] + (h - int(h)) * (xs[int(h) + 1] - xs[int(h)]))
+    text = str(out).splitlines()
+    assert text[0] == "PMMH Results Summary:"
+    assert text[1].split() == ["Parameter", "Mean", "SD", "Median", "2.5%", "97.5%", "ESS", "Rhat"]
+    row = text[2].split()
+    assert row[0] == "param1" and row[6] == "200" and float(row[7]) == 1.01      # ESS floored, Rhat to 3 digits
+    assert float(row[1]) == round(chains["param1"].mean(), 2)
