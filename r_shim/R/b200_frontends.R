@@ -173,6 +173,9 @@ pmmh <- function(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, lo
   result
 }
 
+# name of the CUDA device the engine runs on (errors if there is none: the engine has no CPU fallback)
+b200_device_info <- function() .Call("_bayesSSM_b200_device_info")
+
 # ---- ess() / rhat() (R/ESS.R:30-145, R/rhat.R:27-108): same inputs, messages and NA + warning behaviour; the
 # variances, the autocorrelations of every chain and Geyer's truncation are computed by bssm_mcmc_diagnostics ----
 .b200_diag <- function(chains, which) {

@@ -78,3 +78,64 @@ def test_nvrtc_compiles_a_snippet_with_all_model_kernels_without_a_gpu():
         pytest.skip("libnvrtc not installed")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "cubin bytes" in r.stdout
+
+
+def _strip_r(src):
+    """R source with comments and string contents blanked (strings keep their quotes)."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        c = src[i]
+        if c == "#":
+            while i < n and src[i] != "\n":
+                i += 1
+            continue
+        if c in "\"'":
+            q = c
+            out.append(q)
+            i += 1
+            while i < n and src[i] != q:
+                i += 2 if src[i] == "\\" else 1
+            out.append(q)
+            i += 1
+            continue
+        out.append(c)
+        i += 1
+    return "".join(out)
+
+
+def test_r_frontends_are_well_formed_and_bind_registered_routines():
+    """R is not installed here, so the R front-ends (r_shim/R/b200_frontends.R) get the checks that need no
+    interpreter: brackets balance outside strings and comments, every .Call() target is a routine the shim registers
+    (r_shim/src/bssm_shim.c CallEntries, the replacement of src/RcppExports.cpp:50-60) with the arity used, and every
+    registered routine is reachable from R or is one of the reference's three resampler symbols (R/RcppExports.R:4-14)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = open(os.path.join(root, "r_shim", "R", "b200_frontends.R")).read()
+    src = _strip_r(raw)
+    stack, pairs = [], {")": "(", "]": "[", "}": "{"}
+    for ch in src:
+        if ch in "([{":
+            stack.append(ch)
+        elif ch in ")]}":
+            assert stack and stack.pop() == pairs[ch]
+    assert not stack
+    shim = open(os.path.join(root, "r_shim", "src", "bssm_shim.c")).read()
+    registered = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(_bayesSSM_\w+)",\s*\(DL_FUNC\)&\1,\s*(\d+)\}', shim)}
+    assert len(registered) >= 10
+    used = {}
+    for m in re.finditer(r'\.Call\("(_bayesSSM_\w+)"', raw):
+        # count the top-level commas of this call's argument list
+        i, depth, commas = m.end(), 1, 0
+        while depth:
+            ch = raw[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            commas += ch == "," and depth == 1
+            i += 1
+        used[m.group(1)] = commas
+    for name, nargs in used.items():
+        assert name in registered, name
+        assert registered[name] == nargs, (name, registered[name], nargs)
+    resamplers = {f"_bayesSSM_resample_{k}_cpp" for k in ("multinomial", "stratified", "systematic")}
+    assert resamplers <= set(registered)
+    assert set(registered) - set(used) <= resamplers
