@@ -139,3 +139,59 @@ def test_r_frontends_are_well_formed_and_bind_registered_routines():
     resamplers = {f"_bayesSSM_resample_{k}_cpp" for k in ("multinomial", "stratified", "systematic")}
     assert resamplers <= set(registered)
     assert set(registered) - set(used) <= resamplers
+
+
+def test_r_config_lists_carry_the_names_the_shim_reads():
+    """Each .Call passes a named list `cfg`; a name the shim looks up but R never sets would come back as NULL.
+    Required names (read with list_get) must all be set by the matching front-end; optional ones (opt_int /
+    opt_real, which have defaults) may be absent; R must not set a name nobody reads."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "r_shim", "src", "bssm_shim.c")).read()
+    raw = open(os.path.join(root, "r_shim", "R", "b200_frontends.R")).read()
+    parts = re.split(r"\nSEXP (_bayesSSM_\w+)\(", shim)
+    reads = {}
+    for i in range(1, len(parts), 2):
+        body = parts[i + 1]
+        req = set(re.findall(r'list_get\(\s*cfg_?\s*,\s*"(\w+)"', body))
+        opt = set(re.findall(r'opt_(?:int|real)\(\s*cfg_?\s*,\s*"(\w+)"', body))
+        if req or opt:
+            reads[parts[i]] = (req, opt)
+    checked = 0
+    for m in re.finditer(r"cfg <- list\(", raw):
+        i, depth = m.end(), 1
+        while depth:
+            depth += raw[i] in "([{"
+            depth -= raw[i] in ")]}"
+            i += 1
+        body = raw[m.end():i - 1]
+        keys = set()
+        for seg in re.finditer(r"(\w+)\s*=(?!=)", body):
+            before = body[:seg.start()]
+            if sum(ch in "([{" for ch in before) == sum(ch in ")]}" for ch in before):
+                keys.add(seg.group(1))
+        call = re.search(r'\.Call\("(_bayesSSM_\w+)",\s*cfg\b', raw[i:])
+        req, opt = reads[call.group(1)]
+        nullable = {"obs_times", "consts"}                     # the shim tests these for R_NilValue
+        assert req - nullable <= keys, (call.group(1), req - keys)
+        assert keys <= req | opt, (call.group(1), keys - req - opt)
+        checked += 1
+    assert checked == 3
+
+
+def test_r_frontends_only_read_result_fields_the_shim_returns():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "r_shim", "src", "bssm_shim.c")).read()
+    raw = open(os.path.join(root, "r_shim", "R", "b200_frontends.R")).read()
+    parts = re.split(r"\nSEXP (_bayesSSM_\w+)\(", shim)
+    returned = {parts[i]: {x for lst in re.findall(r"names\w*\[\]\s*=\s*\{([^}]*)\}", parts[i + 1]) for x in re.findall(r'"(\w+)"', lst)}
+                for i in range(1, len(parts), 2)}
+    seen = 0
+    for m in re.finditer(r'r <- \.Call\("(_bayesSSM_\w+)"', raw):
+        nxt = re.search(r"\n[A-Za-z_.][\w.]* <- function", raw[m.end():])
+        chunk = raw[m.end(): m.end() + (nxt.start() if nxt else len(raw))]
+        used = set(re.findall(r"\br\$(\w+)", chunk))
+        assert used and used <= returned[m.group(1)], (m.group(1), used - returned[m.group(1)])
+        seen += 1
+    assert seen >= 5
