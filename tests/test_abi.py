@@ -195,3 +195,82 @@ def test_r_frontends_only_read_result_fields_the_shim_returns():
         assert used and used <= returned[m.group(1)], (m.group(1), used - returned[m.group(1)])
         seen += 1
     assert seen >= 5
+
+
+def _layout_from_c(tmp_path, header, structs, tag):
+    """offsetof / sizeof of every field the ctypes mirror names, as the C compiler lays the header's struct out."""
+    import subprocess
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{header}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} * %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu %zu\\n", offsetof({cname}, {fname}), sizeof((({cname} *)0)->{fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / f"layout_{tag}.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / f"layout_{tag}"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    return [ln.split() for ln in out.strip().splitlines()]
+
+
+def _check_layout(rows, structs):
+    import ctypes as C
+    n = 0
+    for row in rows:
+        cls = structs[row[0]]
+        if row[1] == "*":
+            assert C.sizeof(cls) == int(row[2]), row
+        else:
+            f = getattr(cls, row[1])
+            assert (f.offset, f.size) == (int(row[2]), int(row[3])), row
+            n += 1
+    assert n == sum(len(c._fields_) for c in structs.values())
+    for cname, cls in structs.items():                         # and no field of the C struct is missing from the mirror
+        last = max(getattr(cls, f).offset + getattr(cls, f).size for f, _ in cls._fields_)
+        assert C.sizeof(cls) - last < 8, cname
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_c_structs(tmp_path):
+    """The Python side passes structs by pointer: every field of the ctypes mirrors (bayesssm_b200/_native.py for
+    include/bayesssm_b200.h, tests/oracle.py for oracle/pf_oracle.h) must sit at the offset the C compiler gives it."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from bayesssm_b200 import _native as nat
+    structs = {"bssm_noise_buffers": nat.NoiseBuffers, "bssm_filter_config": nat.FilterConfig,
+               "bssm_filter_result": nat.FilterResult, "bssm_pmmh_config": nat.PmmhConfig, "bssm_pmmh_result": nat.PmmhResult}
+    _check_layout(_layout_from_c(tmp_path, os.path.join(root, "include", "bayesssm_b200.h"), structs, "abi"), structs)
+    import oracle
+    ostructs = {"orc_noise_buffers": oracle.NoiseBuffers, "orc_filter_config": oracle.FilterConfig,
+                "orc_filter_result": oracle.FilterResult, "orc_pmmh_config": oracle.PmmhConfig,
+                "orc_pmmh_chain_result": oracle.PmmhChainResult}
+    _check_layout(_layout_from_c(tmp_path, os.path.join(root, "oracle", "pf_oracle.h"), ostructs, "oracle"), ostructs)
+
+
+def test_ctypes_prototypes_have_the_arity_and_scalar_kinds_of_the_header():
+    """Every prototype in include/bayesssm_b200.h against bayesssm_b200/_native.py SYMBOLS: same number of
+    parameters; pointers bound as pointers, integers as integers, doubles as doubles."""
+    import ctypes as C
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from bayesssm_b200 import _native as nat
+    text = re.sub(r"/\*.*?\*/", " ", open(os.path.join(root, "include", "bayesssm_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b[\w\s\*]+?\b(bssm_\w+)\s*\(([^;{}]*?)\)\s*;", text)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        assert name in nat.SYMBOLS, name
+        argtypes = nat.SYMBOLS[name][1]
+        assert len(argtypes) == len(params), (name, params, argtypes)
+        for p, a in zip(params, argtypes):
+            is_ptr = "*" in p
+            py_ptr = a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or getattr(a, "_type_", None) == "P"
+            assert is_ptr == bool(py_ptr), (name, p, a)
+            if not is_ptr:
+                kind = p.split()[-2] if len(p.split()) > 1 else p
+                if kind in ("double",):
+                    assert a is C.c_double, (name, p, a)
+                elif kind in ("float",):
+                    assert a is C.c_float, (name, p, a)
+                else:
+                    assert a in (C.c_int, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64, C.c_size_t), (name, p, a)
+                    assert C.sizeof(a) == {"int": 4, "int32_t": 4, "uint32_t": 4, "int64_t": 8, "uint64_t": 8, "size_t": 8}[kind], (name, p, a)
