@@ -81,7 +81,11 @@ template <> struct Math<float> {
   // Throughput precision.  Uniforms come from the top 23 bits of a Philox word by bit assembly
   // (no int->float conversion on the XU pipe), logarithm / square root / sine / cosine / exp on the SFU.
   static BSSM_DEV float unit(uint32_t w) { return (__uint_as_float(0x3F800000u | (w >> 9)) - 1.0f) + 5.9604645e-8f; }  // (0, 1)
+#ifndef BSSM_EMU
   static BSSM_DEV float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else   // CPU logic test (tests/simt_emu.h)
+  static BSSM_DEV float sqrt_approx(float x) { return sqrtf(x); }
+#endif
   static BSSM_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     float u1 = unit(a), u2 = unit(b);
     float r = sqrt_approx(-2.0f * __logf(u1));

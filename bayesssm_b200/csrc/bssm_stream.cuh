@@ -342,12 +342,18 @@ __global__ void __launch_bounds__(THREADS) k_st_init(StreamParams P) {
 
 // per-thread asynchronous prefetch of the next tile's 32 bytes (cp.async, no registers held while in flight).
 // Layout [2 halves][ST_THREADS] x 16 B: conflict-free 128-bit shared loads.
+#ifndef BSSM_EMU
 __device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
   const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else   // CPU logic test (tests/simt_emu.h): the copy completes at once
+inline void st_cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+inline void st_cp_async_commit() {}
+inline void st_cp_async_wait() {}
+#endif
 template <typename Real, int PPT, int ST_THREADS>
 __device__ __forceinline__ void st_prefetch(uint4* buf /*[2][ST_THREADS]*/, const Real* g) {
   static_assert(PPT * sizeof(Real) == 32, "32 bytes per thread and tile");

@@ -1,0 +1,128 @@
+"""The streaming bootstrap-filter engine without a GPU: the kernel text of bayesssm_b200/csrc/bssm_stream.cuh is
+compiled by g++ over a small SIMT emulation (tests/simt_emu.h: the threads of a block are fibers, barriers and warp
+shuffles are real rendezvous, shared memory is per block, blocks run in a chosen order) and driven like
+stream_launch() drives it (tests/host_stream.cpp) -- also in its particle-sharded form, with 2 - 4 emulated ranks
+and the per-observation all-gather of the records as a memcpy.  Results are compared with the oracle's Philox-mode
+filter (R/particle_filter_core.R:76-266 + src/resampling.cpp:16-66 restated in oracle/pf_oracle.c).
+
+In the parity precision (f64) everything but the summation order and the device's FMA contraction is reproduced, so
+the tolerance is 1e-9 where the GPU tests allow 1e-6.  The throughput precision (f32) runs with libm in place of the
+SFU approximations and is held to the statistical tolerance of its GPU tests."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_filter_gpu import THETA, sim_y
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AR, LG, RWD, ARCOS = 0, 1, 2, 4
+
+
+@pytest.fixture(scope="module")
+def host_stream(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("hs") / "host_stream"
+    subprocess.run(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
+
+    def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
+            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        th = np.zeros((len(thetas), 3))
+        for c, t in enumerate(thetas):
+            th[c, :len(t)] = t
+        args = [model, precision, threads, N, len(y), len(thetas), bpc, resample_fn, resample_algorithm, threshold, seed, run_id,
+                stream_base, world, capacity_factor, block_order]
+        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        lines, recs = r.stdout.decode().strip().splitlines(), []
+        for i in range(0, len(lines), 4):
+            h = lines[i].split()
+            recs.append({"rank": int(h[1]), "filter": int(h[3]), "loglike": float(h[5]), "n_resampled": int(h[7]),
+                         "status": int(h[9]), "early_exit": int(h[11]),
+                         "ess": np.array(lines[i + 1].split()[1:], float), "state_est": np.array(lines[i + 2].split()[1:], float),
+                         "loglike_history": np.array(lines[i + 3].split()[1:], float)})
+        return recs
+    return run
+
+
+def check(rec, ref, tol=1e-9):
+    assert rec["status"] == 0 and rec["early_exit"] == ref["early_exit"]
+    assert rec["n_resampled"] == ref["n_resampled"]
+    assert abs(rec["loglike"] - ref["loglike"]) <= tol * abs(ref["loglike"])
+    np.testing.assert_allclose(rec["loglike_history"], ref["loglike_history"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(rec["ess"], ref["ess"], rtol=tol)
+    np.testing.assert_allclose(rec["state_est"], ref["state_est"][:, 0], rtol=tol, atol=tol)
+
+
+# sizes around the tile boundaries (f64 tile = 1024 / 512 particles), both block sizes, both resamplers, all block orders
+@pytest.mark.parametrize("N,T,threads,bpc,rfn,order", [(1, 5, 128, 1, 0, 0), (3, 6, 256, 1, 1, 0), (1024, 6, 256, 1, 0, 0),
+                                                       (1025, 6, 128, 3, 1, 1), (3000, 8, 256, 2, 0, 2), (70001, 4, 256, 5, 0, 2)])
+def test_f64_kernel_text_matches_oracle(orc, host_stream, N, T, threads, bpc, rfn, order):
+    y = sim_y(AR, T, np.random.default_rng(N))
+    ref = orc.particle_filter(AR, 0, 2, rfn, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    rec, = host_stream(AR, N, y, [THETA[AR]], threads=threads, bpc=bpc, resample_fn=rfn, block_order=order)
+    check(rec, ref)
+
+
+@pytest.mark.parametrize("model,ralg", [(LG, 2), (RWD, 0), (ARCOS, 1)])
+def test_models_resample_algorithms_and_batches(orc, host_stream, model, ralg):
+    y = sim_y(AR if model == ARCOS else model, 6, np.random.default_rng(5))
+    base = np.array(THETA[AR] if model == ARCOS else THETA[model])
+    thetas = [list(base * (1 + 0.05 * c)) for c in range(3)]
+    recs = host_stream(model, 2000, y, thetas, threads=128, bpc=4, resample_algorithm=ralg, seed=9, run_id=0, stream_base=1)
+    assert [r["filter"] for r in recs] == [0, 1, 2]
+    for c, rec in enumerate(recs):     # filter c: its own theta, Philox stream stream_base + c
+        check(rec, orc.particle_filter(model, 0, ralg, 0, 2000, y, thetas[c], seed=9, stream=1 + c))
+
+
+def test_threshold_early_exit_and_no_observations(orc, host_stream):
+    y = sim_y(AR, 6, np.random.default_rng(6))
+    rec, = host_stream(AR, 2048, y, [THETA[AR]], threshold=1500.0, seed=3, run_id=0, stream_base=0)
+    check(rec, orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], seed=3, threshold=1500.0))
+    y2, th = np.array([0.1, 1e6, 0.2]), [0.8, 1.0, 1e-3]               # R/particle_filter_core.R:189-202
+    rec, = host_stream(AR, 512, y2, [th], bpc=1, seed=3, run_id=0, stream_base=0)
+    ref = orc.particle_filter(AR, 0, 2, 0, 512, y2, th, seed=3)
+    assert ref["early_exit"] == 1 and rec["early_exit"] == 1 and rec["loglike"] == -np.inf and rec["status"] == 0
+    np.testing.assert_allclose(rec["ess"], ref["ess"], rtol=1e-9)
+    rec, = host_stream(AR, 777, np.zeros(0), [THETA[AR]], bpc=1, seed=3, run_id=0, stream_base=0)
+    ref = orc.particle_filter(AR, 0, 2, 0, 777, np.zeros(0), THETA[AR], seed=3)
+    assert rec["ess"][0] == 777 and abs(rec["state_est"][0] - ref["state_est"][0, 0]) < 1e-12
+
+
+def test_degenerate_weights_a_few_particles_take_everything(orc, host_stream):
+    # a very sharp likelihood: heavy sources spanning many output chunks, empty tiles elsewhere
+    y, th = sim_y(AR, 5, np.random.default_rng(11)), [0.8, 1.0, 2e-4]
+    rec, = host_stream(AR, 50000, y, [th], bpc=4, resample_algorithm=1, seed=13, run_id=0, stream_base=0, block_order=2)
+    check(rec, orc.particle_filter(AR, 0, 1, 0, 50000, y, th, seed=13))
+
+
+@pytest.mark.parametrize("N,world,threads,rfn,ralg", [(4100, 2, 256, 0, 2), (3001, 3, 128, 1, 1), (40000, 4, 128, 0, 2)])
+def test_particle_sharded_ranks_reproduce_the_one_gpu_filter(orc, host_stream, N, world, threads, rfn, ralg):
+    """bssm_shard.cu's per-observation sequence (k_st_step, all-gather of the 64-byte records, k_st_merge,
+    k_st_resample on each rank's own offspring) with emulated ranks: every rank reports the same numbers, and they
+    are the unsharded filter's."""
+    y = sim_y(AR, 5, np.random.default_rng(N))
+    ref = orc.particle_filter(AR, 0, ralg, rfn, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    recs = host_stream(AR, N, y, [THETA[AR]], threads=threads, resample_fn=rfn, resample_algorithm=ralg, world=world, block_order=2)
+    assert [r["rank"] for r in recs] == list(range(world))
+    for rec in recs:
+        check(rec, ref)
+        assert rec["loglike"] == recs[0]["loglike"] and np.array_equal(rec["state_est"], recs[0]["state_est"])
+
+
+def test_capacity_overflow_is_reported_by_every_rank(host_stream):
+    y, th = sim_y(AR, 5, np.random.default_rng(11)), [0.8, 1.0, 2e-4]   # nearly all offspring belong to one rank
+    recs = host_stream(AR, 20000, y, [th], threads=128, bpc=4, resample_algorithm=1, seed=13, world=4, capacity_factor=1.0)
+    assert [r["status"] for r in recs] == [10, 10, 10, 10]               # BSSM_ERR_CAPACITY
+
+
+def test_f32_kernel_text_is_close_and_rank_independent(orc, host_stream):
+    y = sim_y(AR, 5, np.random.default_rng(6000))
+    ref = orc.particle_filter(AR, 0, 2, 0, 6000, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    rec, = host_stream(AR, 6000, y, [THETA[AR]], precision=32)
+    assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
+    assert abs(rec["loglike"] - ref["loglike"]) < 5e-3 and np.abs(rec["state_est"] - ref["state_est"][:, 0]).max() < 5e-3
+    two = host_stream(AR, 6000, y, [THETA[AR]], precision=32, world=2, threads=128, block_order=1)
+    assert two[0]["loglike"] == two[1]["loglike"] and abs(two[0]["loglike"] - ref["loglike"]) < 5e-2
