@@ -64,6 +64,7 @@ struct FastParams {
   long long* timing;  // optional [gridDim][16] phase cycle counters (BSSM_FAST_TIMING=1, diagnostics)
 };
 
+#ifndef BSSM_EMU
 __device__ __forceinline__ void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -75,6 +76,18 @@ __device__ __forceinline__ uint4 ll_load_v4(const void* p) {
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+#else   // CPU logic test (tests/simt_emu.h): each 8-byte (value, tag) unit is one atomic access; a poll lets the others run
+inline void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
+  __atomic_store_n((unsigned long long*)p, ((unsigned long long)b << 32) | a, __ATOMIC_RELEASE);
+  __atomic_store_n((unsigned long long*)p + 1, ((unsigned long long)d << 32) | c, __ATOMIC_RELEASE);
+}
+inline void ll_store_v2(void* p, unsigned int a, unsigned int b) { __atomic_store_n((unsigned long long*)p, ((unsigned long long)b << 32) | a, __ATOMIC_RELEASE); }
+inline uint4 ll_load_v4(const void* p) {
+  emu_poll_yield();
+  const unsigned long long lo = __atomic_load_n((const unsigned long long*)p, __ATOMIC_ACQUIRE), hi = __atomic_load_n((const unsigned long long*)p + 1, __ATOMIC_ACQUIRE);
+  return make_uint4((unsigned int)lo, (unsigned int)(lo >> 32), (unsigned int)hi, (unsigned int)(hi >> 32));
+}
+#endif
 __device__ __forceinline__ void ll_put_double(uint4* p, double d, unsigned int tag) {
   unsigned long long b = (unsigned long long)__double_as_longlong(d);
   ll_store_v4(p, (unsigned int)b, tag, (unsigned int)(b >> 32), tag);
@@ -98,9 +111,11 @@ __device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, dou
 #pragma unroll
   for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
 }
+#ifndef BSSM_EMU
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+#endif
 
 template <typename Model, typename Real, int PPT, bool HEADS>
 __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P) {
@@ -108,7 +123,11 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
                 "persistent kernel: 1-D models with one normal per transition");
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr bool F32 = sizeof(Real) == 4;
+#ifndef BSSM_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#else
+  unsigned char* const smem_raw = emu_dynamic_smem();
+#endif
   const FilterDev& f = P.f;
   const int G = P.G;
   const int group = blockIdx.x / G, b = blockIdx.x % G;

@@ -24,6 +24,7 @@
 #include <memory>
 #include <random>
 #include <functional>
+#include <thread>
 #include <ucontext.h>
 #include <vector>
 
@@ -34,12 +35,12 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 
 struct emu_dim3 { unsigned int x = 1, y = 1, z = 1; };
-static emu_dim3 threadIdx, blockIdx;
+static thread_local emu_dim3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;
 
 struct alignas(16) float4 { float x, y, z, w; };
@@ -62,14 +63,18 @@ struct EmuBlock {
   std::vector<uint64_t> xch;
   int orv = 0;
 };
-static EmuBlock* emu_block = nullptr;
-static std::vector<EmuFiber> emu_fibers;
-static ucontext_t emu_sched_ctx;
-static int emu_cur = -1;
-static long emu_progress = 0;
-static std::function<void()> emu_body;
+static thread_local EmuBlock* emu_block = nullptr;
+static thread_local std::vector<EmuFiber> emu_fibers;
+static thread_local ucontext_t emu_sched_ctx;
+static thread_local int emu_cur = -1;
+static thread_local long emu_progress = 0;
+static thread_local std::vector<unsigned char> emu_dyn_smem;   // `extern __shared__` of the running block
+static std::function<void()> emu_body;                        // one kernel at a time
+static inline unsigned char* emu_dynamic_smem() { return emu_dyn_smem.data(); }
 
 static inline void emu_yield() { swapcontext(&emu_fibers[emu_cur].ctx, &emu_sched_ctx); }
+// a thread polling memory another block writes (cooperative launches): let the other fibers and blocks run
+static inline void emu_poll_yield() { emu_yield(); }
 static inline void emu_open(EmuBarrier& b) { b.arrived = 0; b.gen++; emu_progress++; }
 static inline void emu_wait(EmuBarrier& b) {
   const unsigned int g = b.gen;
@@ -124,6 +129,16 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int o) {
   const int lane = threadIdx.x & 31;
   return emu_shfl(v, lane + o < 32 ? lane + o : lane);
 }
+static inline int __reduce_max_sync(unsigned, int v) {
+  EmuBlock& B = *emu_block;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  B.xch[(size_t)w * 32 + lane] = (uint64_t)(int64_t)v;
+  emu_wait(B.wbar[w]);
+  int m = v;
+  for (int l = 0; l < B.wbar[w].expected; l++) { const int o = (int)(int64_t)B.xch[(size_t)w * 32 + l]; m = o > m ? o : m; }
+  emu_wait(B.wbar[w]);
+  return m;
+}
 
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -161,48 +176,66 @@ static inline long long max(long long a, long long b) { return a > b ? a : b; }
 static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-// ---- launch: blocks one at a time (in `order`, or ascending), the threads of a block as round-robin fibers ----
-template <typename Body> static void emu_launch(unsigned int grid, unsigned int block, Body body, const std::vector<unsigned int>* order = nullptr) {
+// ---- launch ----
+// one block on the calling OS thread: its threads as round-robin fibers.  coop: other blocks run on other OS threads and
+// this block may be waiting for them, so a round without progress is not a deadlock (only a long silence is)
+static void emu_run_block(unsigned int b, unsigned int block, size_t smem_bytes, bool coop) {
   constexpr size_t STACK = 256 * 1024;
-  static std::vector<char> stacks;
+  static thread_local std::vector<char> stacks;
   if (stacks.size() < STACK * block) stacks.resize(STACK * block);
   if (emu_fibers.size() < block) emu_fibers.resize(block);
+  emu_dyn_smem.assign(smem_bytes + 16, 0xCD);     // garbage: a kernel must not rely on zeroed shared memory
+  blockIdx.x = b;
+  EmuBlock blk;
+  const int nw = (int)(block + 31) / 32;
+  blk.bar.expected = (int)block;
+  blk.wbar.resize(nw);
+  for (int w = 0; w < nw; w++) blk.wbar[w].expected = (int)block - 32 * w < 32 ? (int)block - 32 * w : 32;
+  blk.xch.assign((size_t)nw * 32, 0);
+  emu_block = &blk;
+  for (unsigned int t = 0; t < block; t++) {
+    EmuFiber& f = emu_fibers[t];
+    f.done = false;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stacks.data() + STACK * t;
+    f.ctx.uc_stack.ss_size = STACK;
+    f.ctx.uc_link = &emu_sched_ctx;
+    makecontext(&f.ctx, emu_trampoline, 0);
+  }
+  unsigned int remaining = block;
+  long idle_rounds = 0;
+  while (remaining) {
+    const long before = emu_progress;
+    for (unsigned int t = 0; t < block; t++) {
+      if (emu_fibers[t].done) continue;
+      emu_cur = (int)t;
+      threadIdx.x = t;
+      swapcontext(&emu_sched_ctx, &emu_fibers[t].ctx);
+      if (emu_fibers[t].done) remaining--;
+    }
+    if (remaining && emu_progress == before) {
+      if (coop && ++idle_rounds < 20000000L) { std::this_thread::yield(); continue; }
+      fprintf(stderr, "simt_emu: deadlock in block %u (%u threads waiting at barriers that cannot open)\n", b, remaining);
+      abort();
+    }
+    idle_rounds = 0;
+  }
+  emu_block = nullptr;
+}
+// ordinary launch: blocks one at a time, in `order` or ascending
+template <typename Body> static void emu_launch(unsigned int grid, unsigned int block, Body body, const std::vector<unsigned int>* order = nullptr,
+                                                size_t smem_bytes = 0) {
   gridDim.x = grid;
   blockDim.x = block;
   emu_body = body;
-  for (unsigned int bi = 0; bi < grid; bi++) {
-    blockIdx.x = order ? (*order)[bi] : bi;
-    EmuBlock blk;
-    const int nw = (int)(block + 31) / 32;
-    blk.bar.expected = (int)block;
-    blk.wbar.resize(nw);
-    for (int w = 0; w < nw; w++) blk.wbar[w].expected = (int)block - 32 * w < 32 ? (int)block - 32 * w : 32;
-    blk.xch.assign((size_t)nw * 32, 0);
-    emu_block = &blk;
-    for (unsigned int t = 0; t < block; t++) {
-      EmuFiber& f = emu_fibers[t];
-      f.done = false;
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = stacks.data() + STACK * t;
-      f.ctx.uc_stack.ss_size = STACK;
-      f.ctx.uc_link = &emu_sched_ctx;
-      makecontext(&f.ctx, emu_trampoline, 0);
-    }
-    unsigned int remaining = block;
-    while (remaining) {
-      const long before = emu_progress;
-      for (unsigned int t = 0; t < block; t++) {
-        if (emu_fibers[t].done) continue;
-        emu_cur = (int)t;
-        threadIdx.x = t;
-        swapcontext(&emu_sched_ctx, &emu_fibers[t].ctx);
-        if (emu_fibers[t].done) remaining--;
-      }
-      if (remaining && emu_progress == before) {
-        fprintf(stderr, "simt_emu: deadlock in block %u (%u threads waiting at barriers that cannot open)\n", blockIdx.x, remaining);
-        abort();
-      }
-    }
-    emu_block = nullptr;
-  }
+  for (unsigned int bi = 0; bi < grid; bi++) emu_run_block(order ? (*order)[bi] : bi, block, smem_bytes, false);
+}
+// cooperative launch: all blocks co-resident, one OS thread per block
+template <typename Body> static void emu_launch_cooperative(unsigned int grid, unsigned int block, size_t smem_bytes, Body body) {
+  gridDim.x = grid;
+  blockDim.x = block;
+  emu_body = body;
+  std::vector<std::thread> blocks;
+  for (unsigned int b = 0; b < grid; b++) blocks.emplace_back([=] { emu_run_block(b, block, smem_bytes, true); });
+  for (auto& th : blocks) th.join();
 }

@@ -23,7 +23,7 @@ AR, LG, RWD, ARCOS = 0, 1, 2, 4
 @pytest.fixture(scope="module")
 def host_stream(tmp_path_factory):
     exe = tmp_path_factory.mktemp("hs") / "host_stream"
-    subprocess.run(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", str(exe),
+    subprocess.run(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread", "-o", str(exe),
                     os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
 
     def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
