@@ -183,7 +183,7 @@ static __device__ __noinline__ void st_global(const StreamParams& P, int c, int 
           else if (r.m != NINF) scg = exp(r.m - M);
           run = st_bound(run, r.s, scg);
           const int o_next = (g == world - 1) ? n : sc.count_le(run / S);
-          if (o_next - o_prev + 4 > P.cap) overflow = 1;
+          if (o_next - o_prev > P.cap) overflow = 1;   // a row stores cap + 4 elements and the share starts at most 3 in: it fits
           if (g == rank) { sg.ngoff = o_prev; sg.nnloc = o_next - o_prev; }
           o_prev = o_next;
         }

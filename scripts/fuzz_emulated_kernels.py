@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Randomised CPU campaign: the streaming and persistent kernels' text on the SIMT emulation (tests/host_stream.cpp,
+tests/host_fast.cpp over tests/simt_emu.h) against the oracle's Philox-mode filter, over random sizes, geometries,
+resamplers, thresholds, models, seeds and (streaming) emulated shard counts / block orders.  f64 only: any difference
+above 1e-8 is a logic bug.  usage: python scripts/fuzz_emulated_kernels.py [--cases 200] [--seed 1] [--max-n 30000]"""
+import argparse
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from test_filter_gpu import THETA, sim_y  # noqa: E402
+
+CXX = ["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread"]
+
+
+def build(tmp, name):
+    exe = os.path.join(tmp, name)
+    subprocess.run(CXX + ["-o", exe, os.path.join(ROOT, "tests", name + ".cpp")], check=True)
+    return exe
+
+
+def call(exe, args, y, thetas):
+    th = np.zeros((len(thetas), 3))
+    for c, t in enumerate(thetas):
+        th[c, :len(t)] = t
+    r = subprocess.run([exe] + [str(a) for a in args], input=np.ascontiguousarray(y, dtype=np.float64).tobytes() + th.tobytes(),
+                       capture_output=True, timeout=900)
+    if r.returncode != 0:
+        return None, r.stderr.decode()[-500:]
+    lines, recs = r.stdout.decode().strip().splitlines(), []
+    for i in range(0, len(lines), 4):
+        h = lines[i].split()
+        recs.append({"rank": int(h[1]), "filter": int(h[3]), "loglike": float(h[5]), "n_resampled": int(h[7]), "status": int(h[9]),
+                     "early_exit": int(h[11]), "ess": np.array(lines[i + 1].split()[1:], float),
+                     "state_est": np.array(lines[i + 2].split()[1:], float)})
+    return recs, ""
+
+
+def differs(rec, ref, tol=1e-8):
+    if rec["status"] != 0 or rec["early_exit"] != ref["early_exit"] or rec["n_resampled"] != ref["n_resampled"]:
+        return "flags"
+    if ref["early_exit"]:
+        return ""
+    if abs(rec["loglike"] - ref["loglike"]) > tol * max(1.0, abs(ref["loglike"])):
+        return "loglike"
+    if not np.allclose(rec["ess"], ref["ess"], rtol=tol) or not np.allclose(rec["state_est"], ref["state_est"][:, 0], rtol=tol, atol=tol):
+        return "ess/state_est"
+    return ""
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=200)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--max-n", dest="max_n", type=int, default=30000)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    bad = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        hs, hf = build(tmp, "host_stream"), build(tmp, "host_fast")
+        for case in range(args.cases):
+            model = int(rng.choice([0, 1, 2, 4]))
+            base = np.array(THETA[0] if model == 4 else THETA[model])
+            if rng.random() < 0.25:
+                base = base * np.array([1.0, 1.0, rng.choice([0.01, 0.1, 3.0])])[:len(base)]   # sharp / flat likelihoods
+            N = int(rng.choice([rng.integers(1, 40), rng.integers(40, 3000), rng.integers(3000, args.max_n)]))
+            T = int(rng.integers(0, 9))
+            C = int(rng.choice([1, 1, 2, 3]))
+            rfn, ralg = int(rng.integers(0, 2)), int(rng.integers(0, 3))
+            thr = float(rng.choice([-1.0, -1.0, rng.uniform(0.1, 1.0) * N]))
+            seed, run_id, sb = int(rng.integers(0, 2**31)), int(rng.integers(0, 100)), int(rng.integers(0, 100))
+            y = sim_y(0 if model == 4 else model, T, rng) if T else np.zeros(0)
+            thetas = [list(base * (1 + 0.03 * c)) for c in range(C)]
+            refs = [oracle.particle_filter(model, 0, ralg, rfn, N, y, thetas[c], threshold=thr, seed=seed, run_id=run_id, stream=sb + c)
+                    for c in range(C)]
+            # streaming engine
+            threads = int(rng.choice([128, 256]))
+            world = int(rng.choice([1, 1, 2, 3, 4])) if C == 1 and N >= 64 else 1
+            bpc, order = int(rng.integers(1, 7)), int(rng.integers(0, 3))
+            sargs = [model, 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order]
+            recs, err = call(hs, sargs, y, thetas)
+            what = err or next((d for r in recs if (d := differs(r, refs[r["filter"]]))), "")
+            if what:
+                bad += 1
+                print("STREAM MISMATCH", what, sargs, thetas, flush=True)
+            # persistent kernel
+            variant = int(rng.integers(0, 2))
+            G = int(rng.integers(1, 6))
+            if (N + G - 1) // G > 7168:
+                G = (N + 7167) // 7168
+            fargs = [model, variant, G, int(rng.integers(1, C + 1)), N, T, C, rfn, ralg, thr, seed, run_id, sb]
+            recs, err = call(hf, fargs, y, thetas)
+            what = err or next((d for r in recs if (d := differs(r, refs[r["filter"]]))), "")
+            if what:
+                bad += 1
+                print("PERSISTENT MISMATCH", what, fargs, thetas, flush=True)
+            if (case + 1) % 20 == 0:
+                print(f"{case + 1} cases, {bad} mismatches", flush=True)
+    print(f"done: {args.cases} cases, {bad} mismatches")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

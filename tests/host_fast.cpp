@@ -55,7 +55,7 @@ static int run(char** argv) {
   std::vector<FastRec> rec((size_t)ngroups * 2 * G);
   memset((void*)rec.data(), 0, sizeof(FastRec) * rec.size());
   const size_t xbytes = (size_t)ngroups * G * nb_max * (sizeof(Real) == 4 ? 8 : 16);
-  std::vector<unsigned long long> xnew(xbytes / 8 + 2, 0ull);
+  std::vector<unsigned long long> xnew(xbytes / 8, 0ull);   // exactly what fast_launch() allocates (AddressSanitizer runs rely on it)
   P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
   emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<Model, Real, PPT, HEADS>(Pc); });

@@ -184,7 +184,7 @@ static void emu_run_block(unsigned int b, unsigned int block, size_t smem_bytes,
   static thread_local std::vector<char> stacks;
   if (stacks.size() < STACK * block) stacks.resize(STACK * block);
   if (emu_fibers.size() < block) emu_fibers.resize(block);
-  emu_dyn_smem.assign(smem_bytes + 16, 0xCD);     // garbage: a kernel must not rely on zeroed shared memory
+  emu_dyn_smem.assign(smem_bytes, 0xCD);          // exact size (AddressSanitizer sees overruns), garbage contents
   blockIdx.x = b;
   EmuBlock blk;
   const int nw = (int)(block + 31) / 32;

@@ -118,6 +118,37 @@ def test_capacity_overflow_is_reported_by_every_rank(host_stream):
     assert [r["status"] for r in recs] == [10, 10, 10, 10]               # BSSM_ERR_CAPACITY
 
 
+def test_capacity_factor_equal_to_the_rank_count_never_overflows(orc, host_stream):
+    # storage for N particles per rank: even when one rank inherits (nearly) every offspring the run completes
+    y, th = sim_y(AR, 5, np.random.default_rng(11)), [0.8, 1.0, 2e-4]
+    ref = orc.particle_filter(AR, 0, 1, 0, 20000, y, th, seed=13)
+    for rec in host_stream(AR, 20000, y, [th], threads=128, bpc=4, resample_algorithm=1, seed=13, run_id=0, stream_base=0, world=4,
+                           capacity_factor=4.0, block_order=2):
+        check(rec, ref)
+
+
+def test_kernels_stay_inside_their_buffers_under_address_sanitizer(tmp_path):
+    """Both harnesses allocate exactly what stream_launch() / fast_launch() allocate (particle rows, records, prefix arrays,
+    LL buffers, dynamic shared memory); AddressSanitizer then sees any access past them."""
+    y = sim_y(AR, 5, np.random.default_rng(11))
+    runs = {"host_stream": [([0.8, 1.0, 2e-4], [0, 64, 256, 50000, 5, 1, 4, 0, 1, -1.0, 13, 0, 0, 2, 2.0, 2]),
+                            ([0.8, 1.0, 0.5], [0, 64, 128, 5001, 5, 1, 3, 1, 2, -1.0, 13, 0, 0, 3, 3.0, 1]),
+                            ([0.8, 1.0, 0.5], [0, 32, 256, 9001, 5, 1, 2, 0, 2, -1.0, 13, 0, 0, 1, 1.5, 0])],
+            "host_fast": [([0.8, 1.0, 2e-4], [0, 0, 4, 1, 6000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 2e-4], [0, 1, 3, 1, 20000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 0.5], [0, 3, 2, 1, 9001, 5, 1, 0, 2, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 0.5], [0, 2, 5, 1, 4097, 5, 1, 1, 1, -1.0, 13, 0, 0])]}
+    for name, cases in runs.items():
+        exe = tmp_path / (name + "_asan")
+        subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread",
+                        "-o", str(exe), os.path.join(ROOT, "tests", name + ".cpp")], check=True)
+        for th, args in cases:
+            r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.array([th]).tobytes(), capture_output=True,
+                               timeout=900)
+            assert r.returncode == 0 and b"ERROR: AddressSanitizer" not in r.stderr, r.stderr.decode()[-3000:]
+            assert b"status 0" in r.stdout
+
+
 def test_f32_kernel_text_is_close_and_rank_independent(orc, host_stream):
     y = sim_y(AR, 5, np.random.default_rng(6000))
     ref = orc.particle_filter(AR, 0, 2, 0, 6000, y, THETA[AR], seed=1405, run_id=2, stream=3)
