@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """Randomised CPU campaign: the streaming and persistent kernels' text on the SIMT emulation (tests/host_stream.cpp,
 tests/host_fast.cpp over tests/simt_emu.h) against the oracle's Philox-mode filter, over random sizes, geometries,
-resamplers, thresholds, models, seeds and (streaming) emulated shard counts / block orders.  f64 only: any difference
-above 1e-8 is a logic bug.  usage: python scripts/fuzz_emulated_kernels.py [--cases 200] [--seed 1] [--max-n 30000]"""
+resamplers, thresholds, models, seeds and (streaming) emulated shard counts / block orders.  Parity precision (default):
+any difference above 1e-8 is a logic bug.  --f32: the throughput-precision instantiations; scratch memory starts as NaN
+bit patterns, so a slot that is never written poisons the sums -- the check is status 0, finite outputs and, from 2000
+particles up, closeness to the oracle at Monte-Carlo scale.
+usage: python scripts/fuzz_emulated_kernels.py [--cases 200] [--seed 1] [--max-n 30000] [--f32]"""
 import argparse
 import os
 import subprocess
@@ -43,6 +46,18 @@ def call(exe, args, y, thetas):
     return recs, ""
 
 
+def differs_f32(rec, ref, n):
+    if rec["status"] != 0:
+        return "status"
+    if ref["early_exit"] or rec["early_exit"]:
+        return "" if rec["early_exit"] == ref["early_exit"] else "early_exit"
+    if not (np.isfinite(rec["loglike"]) and np.isfinite(rec["ess"]).all() and np.isfinite(rec["state_est"]).all()):
+        return "non-finite"
+    if n >= 2000 and (abs(rec["loglike"] - ref["loglike"]) > 0.5 or np.abs(rec["state_est"] - ref["state_est"][:, 0]).max() > 0.5):
+        return "far from the oracle"
+    return ""
+
+
 def differs(rec, ref, tol=1e-8):
     if rec["status"] != 0 or rec["early_exit"] != ref["early_exit"] or rec["n_resampled"] != ref["n_resampled"]:
         return "flags"
@@ -60,6 +75,7 @@ def main():
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-n", dest="max_n", type=int, default=30000)
+    ap.add_argument("--f32", action="store_true")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
@@ -84,20 +100,21 @@ def main():
             threads = int(rng.choice([128, 256]))
             world = int(rng.choice([1, 1, 2, 3, 4])) if C == 1 and N >= 64 else 1
             bpc, order = int(rng.integers(1, 7)), int(rng.integers(0, 3))
-            sargs = [model, 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order]
+            sargs = [model, 32 if args.f32 else 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order]
             recs, err = call(hs, sargs, y, thetas)
-            what = err or next((d for r in recs if (d := differs(r, refs[r["filter"]]))), "")
+            cmp = (lambda r, ref: differs_f32(r, ref, N)) if args.f32 else differs
+            what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:
                 bad += 1
                 print("STREAM MISMATCH", what, sargs, thetas, flush=True)
             # persistent kernel
-            variant = int(rng.integers(0, 2))
+            variant = int(rng.integers(0, 2)) + (2 if args.f32 else 0)
             G = int(rng.integers(1, 6))
             if (N + G - 1) // G > 7168:
                 G = (N + 7167) // 7168
             fargs = [model, variant, G, int(rng.integers(1, C + 1)), N, T, C, rfn, ralg, thr, seed, run_id, sb]
             recs, err = call(hf, fargs, y, thetas)
-            what = err or next((d for r in recs if (d := differs(r, refs[r["filter"]]))), "")
+            what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:
                 bad += 1
                 print("PERSISTENT MISMATCH", what, fargs, thetas, flush=True)
