@@ -131,20 +131,21 @@ def test_kernels_stay_inside_their_buffers_under_address_sanitizer(tmp_path):
     """Both harnesses allocate exactly what stream_launch() / fast_launch() allocate (particle rows, records, prefix arrays,
     LL buffers, dynamic shared memory); AddressSanitizer then sees any access past them."""
     y = sim_y(AR, 5, np.random.default_rng(11))
-    runs = {"host_stream": [([0.8, 1.0, 2e-4], [0, 64, 256, 50000, 5, 1, 4, 0, 1, -1.0, 13, 0, 0, 2, 2.0, 2]),
+    runs = {"host_stream": [([0.8, 1.0, 2e-4], [0, 64, 256, 4099, 5, 1, 4, 0, 1, -1.0, 13, 0, 0, 2, 2.0, 2]),
                             ([0.8, 1.0, 0.5], [0, 64, 128, 5001, 5, 1, 3, 1, 2, -1.0, 13, 0, 0, 3, 3.0, 1]),
-                            ([0.8, 1.0, 0.5], [0, 32, 256, 9001, 5, 1, 2, 0, 2, -1.0, 13, 0, 0, 1, 1.5, 0])],
-            "host_fast": [([0.8, 1.0, 2e-4], [0, 0, 4, 1, 6000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
-                          ([0.8, 1.0, 2e-4], [0, 1, 3, 1, 20000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
-                          ([0.8, 1.0, 0.5], [0, 3, 2, 1, 9001, 5, 1, 0, 2, -1.0, 13, 0, 0]),
-                          ([0.8, 1.0, 0.5], [0, 2, 5, 1, 4097, 5, 1, 1, 1, -1.0, 13, 0, 0])]}
+                            ([0.8, 1.0, 0.5], [0, 32, 256, 3001, 5, 1, 2, 0, 2, -1.0, 13, 0, 0, 1, 1.5, 0])],
+            "host_fast": [([0.8, 1.0, 2e-4], [0, 0, 4, 1, 3000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 2e-4], [0, 1, 3, 1, 7000, 5, 1, 0, 1, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 0.5], [0, 3, 2, 1, 5001, 5, 1, 0, 2, -1.0, 13, 0, 0]),
+                          ([0.8, 1.0, 0.5], [0, 2, 5, 1, 2049, 5, 1, 1, 1, -1.0, 13, 0, 0])]}
+    builds = {name: subprocess.Popen(["g++", "-O1", "-fsanitize=address", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                                      "-pthread", "-o", str(tmp_path / (name + "_asan")), os.path.join(ROOT, "tests", name + ".cpp")])
+              for name in runs}                                    # both compilations at once
     for name, cases in runs.items():
-        exe = tmp_path / (name + "_asan")
-        subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread",
-                        "-o", str(exe), os.path.join(ROOT, "tests", name + ".cpp")], check=True)
+        assert builds[name].wait() == 0
         for th, args in cases:
-            r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.array([th]).tobytes(), capture_output=True,
-                               timeout=900)
+            r = subprocess.run([str(tmp_path / (name + "_asan"))] + [str(a) for a in args], input=y.tobytes() + np.array([th]).tobytes(),
+                               capture_output=True, timeout=900)
             assert r.returncode == 0 and b"ERROR: AddressSanitizer" not in r.stderr, r.stderr.decode()[-3000:]
             assert b"status 0" in r.stdout
 
