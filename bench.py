@@ -128,15 +128,29 @@ def run_reference(args, rank, world):
                 times.append(dt)
     total = sum(times)
     value = cores * N * T * args.steps / total
-    line = {"impl": "reference", "metric": "particle-timesteps/sec", "value": value, "unit": "particle-timesteps/s",
+    sample = (f"{cores} independent bootstrap filters (one per core), N=2^17, T=25, SISAR+stratified, "
+              "C oracle restating R/particle_filter_core.R + src/resampling.cpp with R's "
+              "Mersenne-Twister/inversion RNG; R itself is not installable in this image")
+    metric, unit, scaling, config = "particle-timesteps/sec", "particle-timesteps/s", "weak", workload_config(args)
+    if args.workload == "pmmh":
+        # one PMMH iteration = one filter of N x T particle-timesteps per chain (R/pmmh.R:445-457); proposal and accept
+        # are a few scalar operations beside it, so the port's iteration rate is its filter throughput over that work
+        per_iter = float(args.chains) * args.pmmh_N * args.T
+        value = value / per_iter
+        metric, unit, scaling = "pmmh-iterations/sec", "iter/s", "strong"
+        config = {"workload": f"pmmh nonlinear-AR {args.chains} chains x N={args.pmmh_N} x T={args.T}, chain-sharded, pilot skipped, "
+                              "final NCCL gather of draws", "chains": args.chains, "N": args.pmmh_N, "T": args.T, "engine": args.engine}
+        sample += f"; converted to iterations of {args.chains} chains x N={args.pmmh_N} x T={args.T} ({per_iter:.3g} particle-timesteps each)"
+    elif args.workload == "sharded":
+        scaling = "strong"
+        config = {"workload": f"ONE bootstrap filter nonlinear-AR N={args.shard_N} T={args.shard_T} SISAR stratified, particle-sharded over the ranks",
+                  "N": args.shard_N, "T": args.shard_T, "engine": "stream"}
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "particle-timesteps/s", "cores": cores, "kind": "port",
-                             "sample": f"{cores} independent bootstrap filters (one per core), N=2^17, T=25, SISAR+stratified, "
-                                       "C oracle restating R/particle_filter_core.R + src/resampling.cpp with R's "
-                                       "Mersenne-Twister/inversion RNG; R itself is not installable in this image"},
-            "e2e": {"value": value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
