@@ -94,15 +94,20 @@ def main():
             seed, run_id, sb = int(rng.integers(0, 2**31)), int(rng.integers(0, 100)), int(rng.integers(0, 100))
             y = sim_y(0 if model == 4 else model, T, rng) if T else np.zeros(0)
             thetas = [list(base * (1 + 0.03 * c)) for c in range(C)]
-            refs = [oracle.particle_filter(model, 0, ralg, rfn, N, y, thetas[c], threshold=thr, seed=seed, run_id=run_id, stream=sb + c)
+            ragged = C > 1 and thr < 0 and rng.random() < 0.5          # per-filter particle counts (FilterDev::n_per)
+            ns = [int(rng.integers(1, N + 1)) for _ in range(C)] if ragged else [N] * C
+            if ragged:
+                ns[int(rng.integers(0, C))] = N
+            tail = ns if ragged else []
+            refs = [oracle.particle_filter(model, 0, ralg, rfn, ns[c], y, thetas[c], threshold=thr, seed=seed, run_id=run_id, stream=sb + c)
                     for c in range(C)]
             # streaming engine
             threads = int(rng.choice([128, 256]))
             world = int(rng.choice([1, 1, 2, 3, 4])) if C == 1 and N >= 64 else 1
             bpc, order = int(rng.integers(1, 7)), int(rng.integers(0, 3))
-            sargs = [model, 32 if args.f32 else 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order]
+            sargs = [model, 32 if args.f32 else 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order] + tail
             recs, err = call(hs, sargs, y, thetas)
-            cmp = (lambda r, ref: differs_f32(r, ref, N)) if args.f32 else differs
+            cmp = (lambda r, ref: differs_f32(r, ref, ns[r["filter"]])) if args.f32 else differs
             what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:
                 bad += 1
@@ -112,7 +117,7 @@ def main():
             G = int(rng.integers(1, 6))
             if (N + G - 1) // G > 7168:
                 G = (N + 7167) // 7168
-            fargs = [model, variant, G, int(rng.integers(1, C + 1)), N, T, C, rfn, ralg, thr, seed, run_id, sb]
+            fargs = [model, variant, G, int(rng.integers(1, C + 1)), N, T, C, rfn, ralg, thr, seed, run_id, sb] + tail
             recs, err = call(hf, fargs, y, thetas)
             what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:

@@ -5,7 +5,8 @@
 // Prints loglike / n_resampled / status / early_exit / ess / state_est per filter; tests/test_fast_host.py compares
 // them with the oracle's Philox-mode filter.
 //
-// usage: host_fast model variant G ngroups N T C resample_fn ralg threshold seed run_id stream_base
+// usage: host_fast model variant G ngroups N T C resample_fn ralg threshold seed run_id stream_base [n_0 ... n_{C-1}]
+//   (optional trailing particle counts: a ragged batch, FilterDev::n_per; N is then the maximum)
 //                  < y (T doubles) theta (C x 3 doubles)
 //   variant: 0 = <double, 8, HEADS>, 1 = <double, 8, scatter loops>, 2 = <float, 8, HEADS>, 3 = <float, 16, scatter loops>
 #include "simt_emu.h"
@@ -15,13 +16,15 @@
 using namespace bssm;
 
 template <typename Model, typename Real, int PPT, bool HEADS>
-static int run(char** argv) {
+static int run(int argc, char** argv) {
   int a = 3;
   const int G = atoi(argv[a++]), ngroups_req = atoi(argv[a++]), N = atoi(argv[a++]), T = atoi(argv[a++]), C = atoi(argv[a++]);
   const int rfn = atoi(argv[a++]), ralg = atoi(argv[a++]);
   const double threshold = atof(argv[a++]);
   const unsigned long long seed = strtoull(argv[a++], nullptr, 10);
   const unsigned int run_id = (unsigned int)atoi(argv[a++]), stream_base = (unsigned int)atoi(argv[a++]);
+  std::vector<int> n_per;
+  if (argc >= a + C) for (int c = 0; c < C; c++) n_per.push_back(atoi(argv[a++]));
   std::vector<double> y(T), theta((size_t)C * 3);
   if (T && fread(y.data(), 8, T, stdin) != (size_t)T) return 2;
   if (fread(theta.data(), 8, theta.size(), stdin) != theta.size()) return 2;
@@ -47,6 +50,7 @@ static int run(char** argv) {
   f.C = C; f.N = N; f.T = T; f.dy = 1; f.d = 1;
   f.theta = theta.data(); f.theta_stride = 3; f.y = y.data();
   f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed;
+  f.n_per = n_per.empty() ? nullptr : n_per.data();
   f.M = M.data(); f.S = S.data(); f.loglike = loglike.data();
   f.alive = alive.data(); f.status = status.data(); f.early_exit = early.data(); f.n_resampled = nres.data();
   f.ess = ess.data(); f.state_est = se.data(); f.loglike_history = llh.data();
@@ -72,12 +76,12 @@ static int run(char** argv) {
   return 0;
 }
 
-template <typename Model> static int by_variant(char** argv) {
+template <typename Model> static int by_variant(int argc, char** argv) {
   switch (atoi(argv[2])) {
-    case 0: return run<Model, double, 8, true>(argv);
-    case 1: return run<Model, double, 8, false>(argv);
-    case 2: return run<Model, float, 8, true>(argv);
-    case 3: return run<Model, float, 16, false>(argv);
+    case 0: return run<Model, double, 8, true>(argc, argv);
+    case 1: return run<Model, double, 8, false>(argc, argv);
+    case 2: return run<Model, float, 8, true>(argc, argv);
+    case 3: return run<Model, float, 16, false>(argc, argv);
   }
   return 2;
 }
@@ -85,10 +89,10 @@ template <typename Model> static int by_variant(char** argv) {
 int main(int argc, char** argv) {
   if (argc < 14) { fprintf(stderr, "usage: see the header of tests/host_fast.cpp\n"); return 2; }
   switch (atoi(argv[1])) {
-    case 0: return by_variant<ModelArSin>(argv);
-    case 1: return by_variant<ModelLG>(argv);
-    case 2: return by_variant<ModelRwDrift>(argv);
-    case 4: return by_variant<ModelArCos>(argv);
+    case 0: return by_variant<ModelArSin>(argc, argv);
+    case 1: return by_variant<ModelLG>(argc, argv);
+    case 2: return by_variant<ModelRwDrift>(argc, argv);
+    case 4: return by_variant<ModelArCos>(argc, argv);
   }
   return 2;
 }

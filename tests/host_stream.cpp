@@ -6,7 +6,8 @@
 // state_est per filter; tests/test_stream_host.py compares them with the oracle's Philox-mode filter.
 //
 // usage: host_stream model precision threads N T C bpc resample_fn ralg threshold seed run_id stream_base world
-//                    capacity_factor block_order < y (T doubles) theta (C x 3 doubles)
+//                    capacity_factor block_order [n_0 ... n_{C-1}] < y (T doubles) theta (C x 3 doubles)
+//   the optional trailing particle counts make the batch ragged (FilterDev::n_per; N is then the stride / maximum)
 #include "simt_emu.h"
 
 #include "../bayesssm_b200/csrc/bssm_stream.cuh"
@@ -39,7 +40,8 @@ static int run(int argc, char** argv) {
   const int world = atoi(argv[a++]);
   const double capf = atof(argv[a++]);
   const int order_mode = atoi(argv[a++]);   // 0 ascending, 1 descending, 2 shuffled block order
-  (void)argc;
+  std::vector<int> n_per;
+  if (argc >= a + C) for (int c = 0; c < C; c++) n_per.push_back(atoi(argv[a++]));
   std::vector<double> y(T), theta((size_t)C * 3);
   if (T && fread(y.data(), 8, T, stdin) != (size_t)T) return 2;
   if (fread(theta.data(), 8, theta.size(), stdin) != theta.size()) return 2;
@@ -65,6 +67,7 @@ static int run(int argc, char** argv) {
     f.C = C; f.N = sharded ? cap : N; f.T = T; f.dy = 1; f.d = 1;
     f.theta = theta.data(); f.theta_stride = 3; f.y = y.data();
     f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed;
+    f.n_per = n_per.empty() ? nullptr : n_per.data();
     f.M = R.M.data(); f.S = R.S.data(); f.loglike = R.loglike.data();
     f.alive = R.alive.data(); f.status = R.status.data(); f.early_exit = R.early.data(); f.n_resampled = R.nres.data();
     f.ess = R.ess.data(); f.state_est = R.state_est.data(); f.loglike_history = R.llh.data();
@@ -72,7 +75,7 @@ static int run(int argc, char** argv) {
     P.resample_fn = rfn;
     P.sharded = sharded; P.rank = g; P.world = world; P.n_glob = sharded ? N : 0;
     P.cap = cap;
-    P.log_n = log((double)N);
+    P.log_n = n_per.empty() ? log((double)N) : nan("");
     P.nt = (cap + 4 + TS - 1) / TS;
     P.xstride = (size_t)P.nt * TS;
     P.bpc = std::max(1, std::min(bpc_req, P.nt));

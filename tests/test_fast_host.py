@@ -26,12 +26,12 @@ def host_fast(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_fast.cpp")], check=True)
 
     def run(model, variant, G, N, y, thetas, ngroups=1, resample_fn=0, resample_algorithm=2, threshold=-1.0, seed=1405,
-            run_id=2, stream_base=3):
+            run_id=2, stream_base=3, n_per=()):
         y = np.ascontiguousarray(y, dtype=np.float64)
         th = np.zeros((len(thetas), 3))
         for c, t in enumerate(thetas):
             th[c, :len(t)] = t
-        args = [model, variant, G, ngroups, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base]
+        args = [model, variant, G, ngroups, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base] + list(n_per)
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
@@ -72,6 +72,16 @@ def test_models_resample_algorithms_and_groups_walking_several_filters(orc, host
     recs = host_fast(model, variant, 3, 2000, y, thetas, ngroups=2, resample_algorithm=ralg, seed=9, run_id=0, stream_base=1)
     for c, rec in enumerate(recs):     # two groups share three filters: filter c keeps its own theta and Philox stream
         check(rec, orc.particle_filter(model, 0, ralg, 0, 2000, y, thetas[c], seed=9, stream=1 + c))
+
+
+def test_ragged_batch_particle_counts_per_filter(orc, host_fast):
+    # PMMH's tuned target_n differs from chain to chain (R/pmmh_tuning.R:54-57): FilterDev::n_per
+    y = sim_y(AR, 6, np.random.default_rng(3))
+    ns = [3000, 50, 1777]
+    thetas = [list(np.array(THETA[AR]) * (1 + 0.05 * c)) for c in range(3)]
+    recs = host_fast(AR, F64_HEADS, 3, 3000, y, thetas, ngroups=2, seed=5, run_id=1, stream_base=2, n_per=ns)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 2, 0, ns[c], y, thetas[c], seed=5, run_id=1, stream=2 + c))
 
 
 def test_threshold_early_exit_and_no_observations(orc, host_fast):

@@ -27,13 +27,13 @@ def host_stream(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
 
     def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
-            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0):
+            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=()):
         y = np.ascontiguousarray(y, dtype=np.float64)
         th = np.zeros((len(thetas), 3))
         for c, t in enumerate(thetas):
             th[c, :len(t)] = t
         args = [model, precision, threads, N, len(y), len(thetas), bpc, resample_fn, resample_algorithm, threshold, seed, run_id,
-                stream_base, world, capacity_factor, block_order]
+                stream_base, world, capacity_factor, block_order] + list(n_per)
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
@@ -75,6 +75,16 @@ def test_models_resample_algorithms_and_batches(orc, host_stream, model, ralg):
     assert [r["filter"] for r in recs] == [0, 1, 2]
     for c, rec in enumerate(recs):     # filter c: its own theta, Philox stream stream_base + c
         check(rec, orc.particle_filter(model, 0, ralg, 0, 2000, y, thetas[c], seed=9, stream=1 + c))
+
+
+def test_ragged_batch_particle_counts_per_filter(orc, host_stream):
+    # PMMH's tuned target_n differs from chain to chain (R/pmmh_tuning.R:54-57): FilterDev::n_per
+    y = sim_y(AR, 6, np.random.default_rng(3))
+    ns = [3000, 50, 1777]
+    thetas = [list(np.array(THETA[AR]) * (1 + 0.05 * c)) for c in range(3)]
+    recs = host_stream(AR, 3000, y, thetas, threads=128, bpc=3, seed=5, run_id=1, stream_base=2, block_order=2, n_per=ns)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 2, 0, ns[c], y, thetas[c], seed=5, run_id=1, stream=2 + c))
 
 
 def test_threshold_early_exit_and_no_observations(orc, host_stream):
