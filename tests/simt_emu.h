@@ -40,7 +40,8 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct emu_dim3 { unsigned int x = 1, y = 1, z = 1; };
-static thread_local emu_dim3 threadIdx, blockIdx;
+struct emu_idx3 { unsigned int x = 0, y = 0, z = 0; };
+static thread_local emu_idx3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;
 
 struct alignas(16) float4 { float x, y, z, w; };
@@ -129,6 +130,7 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int o) {
   const int lane = threadIdx.x & 31;
   return emu_shfl(v, lane + o < 32 ? lane + o : lane);
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_wait(emu_block->wbar[threadIdx.x >> 5]); }
 static inline int __reduce_max_sync(unsigned, int v) {
   EmuBlock& B = *emu_block;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,6 +231,15 @@ template <typename Body> static void emu_launch(unsigned int grid, unsigned int 
   blockDim.x = block;
   emu_body = body;
   for (unsigned int bi = 0; bi < grid; bi++) emu_run_block(order ? (*order)[bi] : bi, block, smem_bytes, false);
+}
+// ordinary launch of a two-dimensional grid (blockIdx.x fastest)
+template <typename Body> static void emu_launch2d(unsigned int gx, unsigned int gy, unsigned int block, Body body) {
+  gridDim.x = gx; gridDim.y = gy;
+  blockDim.x = block;
+  emu_body = body;
+  for (unsigned int by = 0; by < gy; by++)
+    for (unsigned int bx = 0; bx < gx; bx++) { blockIdx.y = by; emu_run_block(bx, block, 0, false); }
+  gridDim.y = 1; blockIdx.y = 0;
 }
 // cooperative launch: all blocks co-resident, one OS thread per block
 template <typename Body> static void emu_launch_cooperative(unsigned int grid, unsigned int block, size_t smem_bytes, Body body) {

@@ -1,0 +1,83 @@
+"""The general engine without a GPU: the kernel text of bayesssm_b200/csrc/bssm_filter.cuh (k_init, k_weight,
+k_finalize, k_search_gather, k_flip, k_post) and bssm_resample.cuh (k_tile_sums / k_tile_scan / k_chain / k_tile_exact,
+i.e. the bit-exact sequential cumsum of src/resampling.cpp:25 done in parallel) compiled by g++ over the SIMT emulation
+(tests/simt_emu.h) and driven as run_filter_steps() / resample_stage() / resample_cdf() in bssm_engine.cu drive it
+(tests/host_general.cpp).  Bootstrap, auxiliary (R/particle_filter_core.R:140-175) and resample-move (:226-234)
+filters, every built-in model, the three resamplers; compared with the oracle's Philox-mode filter at 1e-9."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_filter_gpu import THETA, sim_y
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AR, LG, RWD, SIR, ARCOS, RW2D = 0, 1, 2, 3, 4, 5
+NTHETA = {AR: 3, LG: 3, RWD: 2, SIR: 2, ARCOS: 3, RW2D: 1}
+BPF, APF, RMPF = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def host_general(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("hg") / "host_general"
+    subprocess.run(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "host_general.cpp")], check=True)
+
+    def run(model, algorithm, N, y, thetas, resample_fn=0, resample_algorithm=2, threshold=-1.0, seed=77, run_id=1, stream_base=5,
+            exact=1):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        args = [model, algorithm, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base, exact]
+        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.ascontiguousarray(thetas, dtype=np.float64).tobytes(),
+                           capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        lines, recs = r.stdout.decode().strip().splitlines(), []
+        for i in range(0, len(lines), 4):
+            h = lines[i].split()
+            recs.append({"filter": int(h[3]), "loglike": float(h[5]), "n_resampled": int(h[7]), "status": int(h[9]),
+                         "early_exit": int(h[11]), "ess": np.array(lines[i + 1].split()[1:], float),
+                         "state_est": np.array(lines[i + 2].split()[1:], float),
+                         "loglike_history": np.array(lines[i + 3].split()[1:], float)})
+        return recs
+    return run
+
+
+def check(rec, ref, tol=1e-9):
+    assert rec["status"] == 0 and rec["early_exit"] == ref["early_exit"]
+    assert rec["n_resampled"] == ref["n_resampled"]
+    assert abs(rec["loglike"] - ref["loglike"]) <= tol * abs(ref["loglike"])
+    np.testing.assert_allclose(rec["loglike_history"], ref["loglike_history"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(rec["ess"], ref["ess"], rtol=tol)
+    np.testing.assert_allclose(rec["state_est"], ref["state_est"].ravel(), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("algorithm", [BPF, APF, RMPF])
+@pytest.mark.parametrize("rfn", [0, 1, 2])
+def test_algorithms_and_resamplers_on_the_readme_model(orc, host_general, algorithm, rfn):
+    y = sim_y(AR, 5, np.random.default_rng(1))
+    ref = orc.particle_filter(AR, algorithm, 2, rfn, 2500, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    rec, = host_general(AR, algorithm, 2500, y, [THETA[AR]], resample_fn=rfn, seed=1405, run_id=2, stream_base=3)
+    check(rec, ref)
+
+
+@pytest.mark.parametrize("model,algorithm,N,C,ralg", [(SIR, BPF, 2000, 1, 2), (SIR, APF, 1500, 1, 2), (SIR, RMPF, 1500, 1, 1),
+                                                      (RW2D, BPF, 2500, 2, 2), (LG, APF, 1025, 2, 2), (RWD, RMPF, 700, 1, 0),
+                                                      (ARCOS, BPF, 1, 1, 2)])
+def test_every_builtin_model(orc, host_general, model, algorithm, N, C, ralg):
+    # integer-valued two-dimensional SIR states with constants, two-dimensional random walk, batches with their own theta
+    y = sim_y(model, 5, np.random.default_rng(model * 10 + algorithm))
+    nth = NTHETA[model]
+    thetas = [list(np.array(THETA[model][:nth]) * (1 + 0.05 * c)) + list(THETA[model][nth:]) for c in range(C)]
+    recs = host_general(model, algorithm, N, y, thetas, resample_algorithm=ralg)
+    for c, rec in enumerate(recs):
+        th = thetas[c] if model == SIR else thetas[c][:nth]
+        check(rec, orc.particle_filter(model, algorithm, ralg, 0, N, y, th, seed=77, run_id=1, stream=5 + c))
+
+
+def test_plain_parallel_scan_path(orc, host_general):
+    # exact_resampling = 0 (the throughput mode's cdf: ordinary fp64 scan): the same filter up to cdf rounding
+    y = sim_y(AR, 5, np.random.default_rng(4))
+    ref = orc.particle_filter(AR, BPF, 1, 0, 3000, y, THETA[AR], seed=77, run_id=1, stream=5)
+    rec, = host_general(AR, BPF, 3000, y, [THETA[AR]], resample_algorithm=1, exact=0)
+    assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
+    assert abs(rec["loglike"] - ref["loglike"]) < 1e-3 and np.abs(rec["state_est"] - ref["state_est"].ravel()).max() < 1e-2
