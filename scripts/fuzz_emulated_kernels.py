@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Randomised CPU campaign: the streaming and persistent kernels' text on the SIMT emulation (tests/host_stream.cpp,
-tests/host_fast.cpp over tests/simt_emu.h) against the oracle's Philox-mode filter, over random sizes, geometries,
+tests/host_fast.cpp, and in the parity precision tests/host_general.cpp, over tests/simt_emu.h) against the oracle's
+Philox-mode filter, over random sizes, geometries,
 resamplers, thresholds, models, seeds and (streaming) emulated shard counts / block orders.  Parity precision (default):
 any difference above 1e-8 is a logic bug.  --f32: the throughput-precision instantiations; scratch memory starts as NaN
 bit patterns, so a slot that is never written poisons the sums -- the check is status 0, finite outputs and, from 2000
@@ -80,7 +81,7 @@ def main():
     rng = np.random.default_rng(args.seed)
     bad = 0
     with tempfile.TemporaryDirectory() as tmp:
-        hs, hf = build(tmp, "host_stream"), build(tmp, "host_fast")
+        hs, hf, hg = build(tmp, "host_stream"), build(tmp, "host_fast"), build(tmp, "host_general")
         for case in range(args.cases):
             model = int(rng.choice([0, 1, 2, 4]))
             base = np.array(THETA[0] if model == 4 else THETA[model])
@@ -123,6 +124,36 @@ def main():
             if what:
                 bad += 1
                 print("PERSISTENT MISMATCH", what, fargs, thetas, flush=True)
+            # general engine (parity precision only): any algorithm, any built-in model, any resampler, smaller sizes
+            if not args.f32 and not ragged:
+                gmodel = int(rng.choice([0, 1, 2, 3, 4, 5]))
+                galg = int(rng.choice([0, 1, 2])) if gmodel != 5 else 0
+                grfn = int(rng.integers(0, 3))
+                gN = min(N, 4000)
+                nth = {0: 3, 1: 3, 2: 2, 3: 2, 4: 3, 5: 1}[gmodel]
+                gthetas = [list(np.array(THETA[gmodel][:nth]) * (1 + 0.03 * c)) + list(THETA[gmodel][nth:]) for c in range(C)]
+                gy = sim_y(gmodel, T, rng) if T else np.zeros(0)
+                gthr = thr if thr < 0 else min(thr, 0.9 * gN)
+                gargs = [gmodel, galg, gN, T, C, grfn, ralg, gthr, seed, run_id, sb, 1]
+                r = subprocess.run([hg] + [str(a) for a in gargs], input=np.ascontiguousarray(gy, dtype=np.float64).tobytes()
+                                   + np.ascontiguousarray(gthetas, dtype=np.float64).tobytes(), capture_output=True, timeout=900)
+                what = ""
+                if r.returncode != 0:
+                    what = r.stderr.decode()[-300:]
+                else:
+                    lines = r.stdout.decode().strip().splitlines()
+                    for i in range(0, len(lines), 4):
+                        h = lines[i].split()
+                        c = int(h[3])
+                        rec = {"status": int(h[9]), "early_exit": int(h[11]), "n_resampled": int(h[7]), "loglike": float(h[5]),
+                               "ess": np.array(lines[i + 1].split()[1:], float), "state_est": np.array(lines[i + 2].split()[1:], float)}
+                        ref = oracle.particle_filter(gmodel, galg, ralg, grfn, gN, gy, gthetas[c] if gmodel == 3 else gthetas[c][:nth],
+                                                     threshold=gthr, seed=seed, run_id=run_id, stream=sb + c)
+                        ref = dict(ref, state_est=ref["state_est"].reshape(-1, 1))
+                        what = what or differs(rec, ref)
+                if what:
+                    bad += 1
+                    print("GENERAL MISMATCH", what, gargs, gthetas, flush=True)
             if (case + 1) % 20 == 0:
                 print(f"{case + 1} cases, {bad} mismatches", flush=True)
     print(f"done: {args.cases} cases, {bad} mismatches")
