@@ -81,3 +81,14 @@ def test_plain_parallel_scan_path(orc, host_general):
     rec, = host_general(AR, BPF, 3000, y, [THETA[AR]], resample_algorithm=1, exact=0)
     assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
     assert abs(rec["loglike"] - ref["loglike"]) < 1e-3 and np.abs(rec["state_est"] - ref["state_est"].ravel()).max() < 1e-2
+
+
+def test_nan_observation_is_reported_as_in_the_oracle(orc, host_general):
+    # NaN weights: R's `if (all(lw < -1e8))` raises "missing value where TRUE/FALSE needed" (R/particle_filter_core.R:189);
+    # here status 3 (BSSM_ERR_NAN_WEIGHT), the log-likelihood staying at the last finite observation
+    y = sim_y(AR, 5, np.random.default_rng(1))
+    y[2] = np.nan
+    ref = orc.particle_filter(AR, 0, 2, 0, 3000, y, THETA[AR], seed=1)
+    assert ref["status"] == 3
+    for rec in host_general(AR, BPF, 3000, y, [THETA[AR]], seed=1, run_id=0, stream_base=0):
+        assert rec["status"] == 3 and rec["loglike"] == pytest.approx(ref["loglike"], rel=1e-12)

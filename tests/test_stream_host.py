@@ -168,3 +168,14 @@ def test_f32_kernel_text_is_close_and_rank_independent(orc, host_stream):
     assert abs(rec["loglike"] - ref["loglike"]) < 5e-3 and np.abs(rec["state_est"] - ref["state_est"][:, 0]).max() < 5e-3
     two = host_stream(AR, 6000, y, [THETA[AR]], precision=32, world=2, threads=128, block_order=1)
     assert two[0]["loglike"] == two[1]["loglike"] and abs(two[0]["loglike"] - ref["loglike"]) < 5e-2
+
+
+def test_nan_observation_is_reported_as_in_the_oracle(orc, host_stream):
+    # NaN weights: R's `if (all(lw < -1e8))` raises "missing value where TRUE/FALSE needed" (R/particle_filter_core.R:189);
+    # here status 3 (BSSM_ERR_NAN_WEIGHT), the log-likelihood staying at the last finite observation
+    y = sim_y(AR, 5, np.random.default_rng(1))
+    y[2] = np.nan
+    ref = orc.particle_filter(AR, 0, 2, 0, 3000, y, THETA[AR], seed=1)
+    assert ref["status"] == 3
+    for rec in host_stream(AR, 3000, y, [THETA[AR]], threads=128, seed=1, run_id=0, stream_base=0, world=3, capacity_factor=3.0, block_order=2):
+        assert rec["status"] == 3 and rec["loglike"] == pytest.approx(ref["loglike"], rel=1e-12)
