@@ -33,6 +33,11 @@ static int run(int argc, char** argv) {
   std::vector<double> M(C, 0), S(C, 0), loglike(C, 0), ess((size_t)C * (T + 1), 0), se((size_t)C * (T + 1), 0), llh((size_t)C * std::max(T, 1), 0);
   std::vector<int> alive(C, 1), status(C, 0), early(C, 0), nres(C, 0);
 
+  // optional observation times (gaps between them are extra transitions, R/particle_filter_core.R:70-71,124-136)
+  std::vector<int> obs_times;
+  if (const char* e = getenv("EMU_OBS_TIMES")) { for (const char* q = e; *q;) { obs_times.push_back((int)strtol(q, (char**)&q, 10)); if (*q == ',') q++; } }
+  if ((int)obs_times.size() != T) obs_times.clear();
+
   // geometry: fast_launch() of bssm_fast.cu
   int nb_max = (N + G - 1) / G;
   nb_max = (nb_max + PPT - 1) / PPT * PPT;
@@ -51,6 +56,7 @@ static int run(int argc, char** argv) {
   f.theta = theta.data(); f.theta_stride = 3; f.y = y.data();
   f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed;
   f.n_per = n_per.empty() ? nullptr : n_per.data();
+  f.obs_times = obs_times.empty() ? nullptr : obs_times.data();
   f.M = M.data(); f.S = S.data(); f.loglike = loglike.data();
   f.alive = alive.data(); f.status = status.data(); f.early_exit = early.data(); f.n_resampled = nres.data();
   f.ess = ess.data(); f.state_est = se.data(); f.loglike_history = llh.data();

@@ -86,10 +86,16 @@ static int run(char** argv) {
   std::vector<unsigned int> stream(C), runid(C, run_id);
   for (int c = 0; c < C; c++) stream[c] = stream_base + c;
 
+  // optional observation times (gaps between them are extra transitions, R/particle_filter_core.R:70-71,124-136)
+  std::vector<int> obs_times;
+  if (const char* e = getenv("EMU_OBS_TIMES")) { for (const char* q = e; *q;) { obs_times.push_back((int)strtol(q, (char**)&q, 10)); if (*q == ',') q++; } }
+  if ((int)obs_times.size() != T) obs_times.clear();
+
   // filter_setup() / filter_reset() of bssm_engine.cu
   FilterDev f;
   memset(&f, 0, sizeof(f));
   f.C = C; f.N = N; f.T = T; f.dy = 1; f.d = d; f.theta = theta.data(); f.theta_stride = ts; f.y = y.data();
+  f.obs_times = obs_times.empty() ? nullptr : obs_times.data();
   f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed; f.algorithm = algorithm; f.ralg = ralg; f.threshold = threshold;
   f.nblk = std::max(1, std::min(1024, (N + FT_THREADS - 1) / FT_THREADS));
   std::vector<Real> xa((size_t)C * d * N, NAN), xb((size_t)C * d * N, NAN), lw((size_t)C * N, NAN), lw_aux((size_t)C * N, NAN), auxg((size_t)C * N, NAN);

@@ -48,6 +48,10 @@ static int run(int argc, char** argv) {
   std::vector<unsigned int> stream(C), runid(C, run_id);
   for (int c = 0; c < C; c++) stream[c] = stream_base + c;
 
+  // optional observation times (gaps between them are extra transitions, R/particle_filter_core.R:70-71,124-136)
+  std::vector<int> obs_times;
+  if (const char* e = getenv("EMU_OBS_TIMES")) { for (const char* q = e; *q;) { obs_times.push_back((int)strtol(q, (char**)&q, 10)); if (*q == ',') q++; } }
+  if ((int)obs_times.size() != T) obs_times.clear();
   std::vector<Rank> ranks(world);
   const bool sharded = world > 1;
   for (int g = 0; g < world; g++) {
@@ -68,6 +72,7 @@ static int run(int argc, char** argv) {
     f.theta = theta.data(); f.theta_stride = 3; f.y = y.data();
     f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed;
     f.n_per = n_per.empty() ? nullptr : n_per.data();
+    f.obs_times = obs_times.empty() ? nullptr : obs_times.data();
     f.M = R.M.data(); f.S = R.S.data(); f.loglike = R.loglike.data();
     f.alive = R.alive.data(); f.status = R.status.data(); f.early_exit = R.early.data(); f.n_resampled = R.nres.data();
     f.ess = R.ess.data(); f.state_est = R.state_est.data(); f.loglike_history = R.llh.data();

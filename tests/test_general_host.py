@@ -25,11 +25,12 @@ def host_general(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_general.cpp")], check=True)
 
     def run(model, algorithm, N, y, thetas, resample_fn=0, resample_algorithm=2, threshold=-1.0, seed=77, run_id=1, stream_base=5,
-            exact=1):
+            exact=1, obs_times=None):
         y = np.ascontiguousarray(y, dtype=np.float64)
         args = [model, algorithm, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base, exact]
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.ascontiguousarray(thetas, dtype=np.float64).tobytes(),
-                           capture_output=True, timeout=600)
+                           capture_output=True, timeout=600,
+                           env=dict(os.environ, EMU_OBS_TIMES=",".join(str(int(t)) for t in obs_times)) if obs_times is not None else None)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
         for i in range(0, len(lines), 4):
@@ -92,3 +93,12 @@ def test_nan_observation_is_reported_as_in_the_oracle(orc, host_general):
     assert ref["status"] == 3
     for rec in host_general(AR, BPF, 3000, y, [THETA[AR]], seed=1, run_id=0, stream_base=0):
         assert rec["status"] == 3 and rec["loglike"] == pytest.approx(ref["loglike"], rel=1e-12)
+
+
+@pytest.mark.parametrize("algorithm", [BPF, APF, RMPF])
+def test_observation_times_with_gaps(orc, host_general, algorithm):
+    # R/particle_filter_core.R:70-71,124-136: the gap to the previous observation time is that many transitions
+    y, ot = sim_y(AR, 6, np.random.default_rng(6)), [1, 2, 4, 7, 8, 12]
+    ref = orc.particle_filter(AR, algorithm, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3)
+    rec, = host_general(AR, algorithm, 2048, y, [THETA[AR]], seed=3, run_id=0, stream_base=0, obs_times=ot)
+    check(rec, ref)

@@ -27,14 +27,15 @@ def host_stream(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
 
     def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
-            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=()):
+            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=(), obs_times=None):
         y = np.ascontiguousarray(y, dtype=np.float64)
         th = np.zeros((len(thetas), 3))
         for c, t in enumerate(thetas):
             th[c, :len(t)] = t
         args = [model, precision, threads, N, len(y), len(thetas), bpc, resample_fn, resample_algorithm, threshold, seed, run_id,
                 stream_base, world, capacity_factor, block_order] + list(n_per)
-        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600)
+        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600,
+                           env=dict(os.environ, EMU_OBS_TIMES=",".join(str(int(t)) for t in obs_times)) if obs_times is not None else None)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
         for i in range(0, len(lines), 4):
@@ -179,3 +180,11 @@ def test_nan_observation_is_reported_as_in_the_oracle(orc, host_stream):
     assert ref["status"] == 3
     for rec in host_stream(AR, 3000, y, [THETA[AR]], threads=128, seed=1, run_id=0, stream_base=0, world=3, capacity_factor=3.0, block_order=2):
         assert rec["status"] == 3 and rec["loglike"] == pytest.approx(ref["loglike"], rel=1e-12)
+
+
+def test_observation_times_with_gaps(orc, host_stream):
+    # R/particle_filter_core.R:70-71,124-136: the gap to the previous observation time is that many transitions
+    y, ot = sim_y(AR, 6, np.random.default_rng(6)), [1, 2, 4, 7, 8, 12]
+    ref = orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3)
+    for rec in host_stream(AR, 2048, y, [THETA[AR]], seed=3, run_id=0, stream_base=0, world=2, capacity_factor=2.0, block_order=1, obs_times=ot):
+        check(rec, ref)
