@@ -30,12 +30,12 @@ def build(tmp, name):
     return exe
 
 
-def call(exe, args, y, thetas):
+def call(exe, args, y, thetas, env=None):
     th = np.zeros((len(thetas), 3))
     for c, t in enumerate(thetas):
         th[c, :len(t)] = t
     r = subprocess.run([exe] + [str(a) for a in args], input=np.ascontiguousarray(y, dtype=np.float64).tobytes() + th.tobytes(),
-                       capture_output=True, timeout=900)
+                       capture_output=True, timeout=900, env=env)
     if r.returncode != 0:
         return None, r.stderr.decode()[-500:]
     lines, recs = r.stdout.decode().strip().splitlines(), []
@@ -95,19 +95,23 @@ def main():
             seed, run_id, sb = int(rng.integers(0, 2**31)), int(rng.integers(0, 100)), int(rng.integers(0, 100))
             y = sim_y(0 if model == 4 else model, T, rng) if T else np.zeros(0)
             thetas = [list(base * (1 + 0.03 * c)) for c in range(C)]
+            ot = None
+            if T and rng.random() < 0.3:                               # observation times with gaps (extra transitions)
+                ot = np.cumsum(rng.integers(1, 4, size=T)).tolist()
+            env = dict(os.environ, EMU_OBS_TIMES=",".join(map(str, ot))) if ot else None
             ragged = C > 1 and thr < 0 and rng.random() < 0.5          # per-filter particle counts (FilterDev::n_per)
             ns = [int(rng.integers(1, N + 1)) for _ in range(C)] if ragged else [N] * C
             if ragged:
                 ns[int(rng.integers(0, C))] = N
             tail = ns if ragged else []
-            refs = [oracle.particle_filter(model, 0, ralg, rfn, ns[c], y, thetas[c], threshold=thr, seed=seed, run_id=run_id, stream=sb + c)
+            refs = [oracle.particle_filter(model, 0, ralg, rfn, ns[c], y, thetas[c], threshold=thr, obs_times=ot, seed=seed, run_id=run_id, stream=sb + c)
                     for c in range(C)]
             # streaming engine
             threads = int(rng.choice([128, 256]))
             world = int(rng.choice([1, 1, 2, 3, 4])) if C == 1 and N >= 64 else 1
             bpc, order = int(rng.integers(1, 7)), int(rng.integers(0, 3))
             sargs = [model, 32 if args.f32 else 64, threads, N, T, C, bpc, rfn, ralg, thr, seed, run_id, sb, world, 4.0, order] + tail
-            recs, err = call(hs, sargs, y, thetas)
+            recs, err = call(hs, sargs, y, thetas, env)
             cmp = (lambda r, ref: differs_f32(r, ref, ns[r["filter"]])) if args.f32 else differs
             what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:
@@ -119,7 +123,7 @@ def main():
             if (N + G - 1) // G > 7168:
                 G = (N + 7167) // 7168
             fargs = [model, variant, G, int(rng.integers(1, C + 1)), N, T, C, rfn, ralg, thr, seed, run_id, sb] + tail
-            recs, err = call(hf, fargs, y, thetas)
+            recs, err = call(hf, fargs, y, thetas, env)
             what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
             if what:
                 bad += 1
@@ -136,7 +140,7 @@ def main():
                 gthr = thr if thr < 0 else min(thr, 0.9 * gN)
                 gargs = [gmodel, galg, gN, T, C, grfn, ralg, gthr, seed, run_id, sb, 1]
                 r = subprocess.run([hg] + [str(a) for a in gargs], input=np.ascontiguousarray(gy, dtype=np.float64).tobytes()
-                                   + np.ascontiguousarray(gthetas, dtype=np.float64).tobytes(), capture_output=True, timeout=900)
+                                   + np.ascontiguousarray(gthetas, dtype=np.float64).tobytes(), capture_output=True, timeout=900, env=env)
                 what = ""
                 if r.returncode != 0:
                     what = r.stderr.decode()[-300:]
@@ -148,7 +152,7 @@ def main():
                         rec = {"status": int(h[9]), "early_exit": int(h[11]), "n_resampled": int(h[7]), "loglike": float(h[5]),
                                "ess": np.array(lines[i + 1].split()[1:], float), "state_est": np.array(lines[i + 2].split()[1:], float)}
                         ref = oracle.particle_filter(gmodel, galg, ralg, grfn, gN, gy, gthetas[c] if gmodel == 3 else gthetas[c][:nth],
-                                                     threshold=gthr, seed=seed, run_id=run_id, stream=sb + c)
+                                                     threshold=gthr, obs_times=ot, seed=seed, run_id=run_id, stream=sb + c)
                         ref = dict(ref, state_est=ref["state_est"].reshape(-1, 1))
                         what = what or differs(rec, ref)
                 if what:
