@@ -1,27 +1,34 @@
 // bssm_fast.cuh -- persistent bootstrap-filter kernel: the whole T loop of
 // .particle_filter_core (R/particle_filter_core.R:123-246) for algorithm "BPF" in ONE launch.
 //
-// A filter is run by a GROUP of G co-resident CTAs (cooperative launch); CTA b owns the
-// contiguous slice [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps
-// (PPT particles per thread).  Per observation:
-//   P1  propagate (normals pre-generated while waiting at the previous sync point; one Philox call
-//       per 4 particles) + log-weight; block max; e = exp(lw - max_b); block sums of e, e^2, e*x
-//       and the block-local inclusive scan of e                              [registers + shuffles]
-//   B1  every CTA publishes (max_b, sums) as an epoch-stamped record in L2, generates the NEXT
-//       step's normals while the record travels, then polls the G records (release/acquire, no
-//       atomics); all CTAs derive, redundantly but bit-identically, the global max / sum / ESS /
-//       resampling decision and the cdf interval of every CTA                  [1 L2 round trip]
-//   P3  INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form -- the
-//       number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
-//       slots [F(c_{j-1}), F(c_j)).  No search.  The stratified uniforms of the CTA's output range
-//       are staged once in shared memory (one Philox call per 4 slots).
-//   P4  the chosen x are scattered into a shared-memory staging buffer and copied out to x_new
-//       with coalesced 16-byte stores
-//   B2  every CTA reloads its slice of x_new; each element carries its epoch tag (LL protocol:
-//       value and tag travel in one 8-byte word), so there is no fence, no flag and no second
-//       round trip -- the reader simply polls its own elements               [< 1 L2 round trip]
-// Records use the same self-validating words.  Only x_new (one write + one read per particle, L2
-// resident) and the tiny records leave the SM.
+// A filter is run by a GROUP of G co-resident CTAs (cooperative launch); CTA b owns the contiguous slice
+// [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps (PPT particles per thread).
+// A CTA is NW WORKER warps plus one SERVICE warp; the workers never meet at a block barrier of their own.
+// Per observation:
+//   P1  (workers) propagate (normals pre-generated during the previous wait; one Philox call per 4
+//       particles) + log-weight; WARP max; e = exp(lw - max_w); warp sums of e, e^2, e*x and the
+//       warp-local inclusive scan of e.  One 5-double record per warp goes to shared memory;
+//       the warp ARRIVES at named barrier A and goes on with work that does not depend on the exchange:
+//       the next observation's normals and the stratified uniforms of the slots it will probably
+//       serve (a window around its own slice; misses are repaired per warp, never wrong)
+//   B1  (service warp) waits on A, folds the warp records into the CTA record (max rescale, warp
+//       prefix), publishes it as epoch-stamped LL words in L2, polls the G records of the group, and
+//       derives -- bit-identically in every CTA -- the global max / sum / ESS / resampling decision, the
+//       cdf interval of the CTA and, per worker warp, the slot position of its first particle and
+//       its slots-per-unit-weight scale.  It arrives at named barrier B, where the workers wait
+//                                                                              [1 L2 round trip]
+//   P3  (workers) INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form --
+//       the number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
+//       slots [F(c_{j-1}), F(c_j)).  No search.  Warp boundaries are F of values both neighbours
+//       read from the same shared-memory (CTA boundaries: the same L2) words, so every slot is
+//       produced exactly once without any cross-warp prefix
+//   P4  WARP-PRIVATE expansion: every source marks the first of its slots in the warp's own
+//       head array, a running maximum over the slots tells every slot its source, the chosen x are
+//       staged per warp and leave the SM as coalesced 16-byte LL stores into x_new.  No block barrier
+//   B2  every thread polls its own elements of x_new: value and epoch tag travel in one 8-byte word
+//       (LL protocol), so there is no fence, no flag, no barrier; a warp whose particles have
+//       arrived starts the next observation at once                          [< 1 L2 round trip]
+// Only x_new (one write + one read per particle, L2 resident) and the tiny records leave the SM.
 // Same Philox keying and tie rule (first j with cdf[j] >= pos, clamp) as the general engine, so
 // results do not depend on G or the launch geometry beyond floating-point summation order.
 // In the throughput precision (Real = float) the within-thread part of the cdf and the slot
@@ -38,20 +45,46 @@ namespace bssm {
 
 constexpr int FAST_MAX_NB = 7168;    // particles per CTA
 constexpr int FAST_MAX_G = 256;      // CTAs per group
-constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
-constexpr int FAST_HEAVY = 64;       // offspring count above which a source is expanded cooperatively
-constexpr int FAST_HEAVY_CAP = 64;
-// output slots per thread of one expansion pass: 25 % beyond the slice, rounded up to whole 16-byte accesses
+constexpr int FAST_BAR_A = 1;        // named barriers: workers -> service, service -> workers
+constexpr int FAST_BAR_B = 2;
+// output slots per lane of one expansion pass: 25 % beyond the lane's sources, rounded up to whole 16-byte accesses
 __host__ __device__ constexpr int fast_spt(int ppt) { return (ppt * 5 / 4 + 3) & ~3; }
+// stride (elements) of a lane's particles in the warp's staging array: + 4 keeps the 16-byte accesses conflict-free
+__host__ __device__ constexpr int fast_xs(int ppt) { return ppt + 4; }
 
 // LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
 // 16-byte access.  A reader that sees the expected tag also sees the data: no fence, no separate
 // flag, no dependent second load.  The accesses are relaxed at GPU scope (all that an exchange between
-// CTAs of one GPU needs): +4 % over `volatile`, which is system scope (profiles/r1_ab_experiments.md).
-struct __align__(128) FastRec {   // published once per observation by each CTA: 5 doubles as (lo, tag, hi, tag)
-  uint4 w[5];                     // m, s, q, sx, pending sum of the previous step's resampled x
+// CTAs of one GPU needs).
+struct __align__(128) FastRec {   // published once per observation by each CTA
+  uint4 w[5];                     // f64: m, s, q, sx, pending as (lo, tag, hi, tag); f32: (m, tag, q, tag), s, (sx, tag, pending, tag)
   uint4 pad[3];
 };
+
+// launch geometry, shared by fast_launch() (bssm_fast.cu) and the CPU logic tests
+struct FastGeom {
+  int nb_max, nw, threads, ch, ucap, uw;
+  size_t smem;
+};
+template <typename Real, int PPT>
+inline FastGeom fast_geometry(int N, int G, int uw_req) {
+  FastGeom g;
+  g.nb_max = (N + G - 1) / G;
+  g.nb_max = (g.nb_max + PPT - 1) / PPT * PPT;
+  g.nw = (g.nb_max + 32 * PPT - 1) / (32 * PPT);
+  if (g.nw < 1) g.nw = 1;
+  g.threads = (g.nw + 1) * 32;
+  g.ch = 32 * fast_spt(PPT);
+  g.uw = uw_req >= 0 ? uw_req : (g.nb_max / 7 < 64 ? 64 : (g.nb_max / 7 > 2048 ? 2048 : g.nb_max / 7));
+  g.uw = (g.uw + 3) & ~3;
+  g.ucap = (g.nb_max + 2 * g.uw + 3) & ~3;
+  // parity precision with big slices: the per-warp staging areas fill the shared memory; no CTA-wide window of uniforms,
+  // every warp stages its own (the window is an optimisation only)
+  if (sizeof(Real) == 8 && g.nw > 14 && uw_req < 0) { g.uw = 0; g.ucap = 0; }
+  g.smem = (size_t)(160 + 34 + 32) * sizeof(double) + 16 + (size_t)((5 * G + 1) & ~1) * sizeof(double) + (size_t)2 * g.ucap * sizeof(unsigned int) +
+           (size_t)g.nw * ((size_t)32 * fast_xs(PPT) * sizeof(Real) + (size_t)g.ch * sizeof(unsigned int) + (size_t)g.ch * sizeof(Real));
+  return g;
+}
 
 struct FastParams {
   FilterDev f;
@@ -60,7 +93,7 @@ struct FastParams {
   FastRec* rec;     // [ngroups][2][G]
   void* xnew;       // [ngroups][G * nb_max] LL elements: uint2 (f32) / uint4 (f64)
   int nb_max;       // slice stride (multiple of PPT)
-  int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
+  int ucap, uw;     // staged window of stratified uniforms: slots [base - uw, base - uw + ucap) of the CTA with first particle `base`
   long long* timing;  // optional [gridDim][16] phase cycle counters (BSSM_FAST_TIMING=1, diagnostics)
 };
 
@@ -76,6 +109,10 @@ __device__ __forceinline__ uint4 ll_load_v4(const void* p) {
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+// named barriers (PTX bar.sync / bar.arrive with a thread count): the documented producer / consumer pairing --
+// memory accesses before the arrive are performed before the matching sync returns
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #else   // CPU logic test (tests/simt_emu.h): each 8-byte (value, tag) unit is one atomic access; a poll lets the others run
 inline void ll_store_v4(void* p, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
   __atomic_store_n((unsigned long long*)p, ((unsigned long long)b << 32) | a, __ATOMIC_RELEASE);
@@ -95,34 +132,52 @@ __device__ __forceinline__ void ll_put_double(uint4* p, double d, unsigned int t
 __device__ __forceinline__ double ll_get_double(const uint4& v) {
   return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
 }
-// publish a 5-double record / poll one until every word carries `tag`
-__device__ __forceinline__ void rec_publish(FastRec* r, double m, double s, double q, double sx, double sp, unsigned int tag) {
-  ll_put_double(&r->w[0], m, tag); ll_put_double(&r->w[1], s, tag); ll_put_double(&r->w[2], q, tag);
-  ll_put_double(&r->w[3], sx, tag); ll_put_double(&r->w[4], sp, tag);
-}
-__device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, double* out /*5*/) {
-  uint4 v[5];
-  bool ok;
-  do {
-    ok = true;
-#pragma unroll
-    for (int i = 0; i < 5; i++) { v[i] = ll_load_v4(&r->w[i]); ok = ok && v[i].y == tag && v[i].w == tag; }
-  } while (!ok);
-#pragma unroll
-  for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
-}
-#ifndef BSSM_EMU
-__device__ __forceinline__ void named_barrier(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-#endif
 
-template <typename Model, typename Real, int PPT, bool HEADS>
-__global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P) {
+// record codec.  NU 16-byte units per record: 5 doubles in the parity precision; in the throughput precision the sum of
+// the weights stays fp64 (it becomes the cdf), max / sum of squares / state sums travel as fp32
+template <bool F32> struct FastRecCodec {
+  static constexpr int NU = F32 ? 3 : 5;
+  // lane i < NU stores unit i (the five values are warp-uniform)
+  static __device__ __forceinline__ void publish(FastRec* r, int lane, double m, double s, double q, double sx, double sp, unsigned int tag) {
+    if (F32) {
+      if (lane == 0) ll_store_v4(&r->w[0], __float_as_uint((float)m), tag, __float_as_uint((float)q), tag);
+      else if (lane == 1) ll_put_double(&r->w[1], s, tag);
+      else if (lane == 2) ll_store_v4(&r->w[2], __float_as_uint((float)sx), tag, __float_as_uint((float)sp), tag);
+    } else {
+      const double v = lane == 0 ? m : (lane == 1 ? s : (lane == 2 ? q : (lane == 3 ? sx : sp)));
+      if (lane < 5) ll_put_double(&r->w[lane], v, tag);
+    }
+  }
+  static __device__ __forceinline__ void decode(const uint4* v, double* out /*5*/) {
+    if (F32) {
+      out[0] = (double)__uint_as_float(v[0].x); out[2] = (double)__uint_as_float(v[0].z);
+      out[1] = ll_get_double(v[1]);
+      out[3] = (double)__uint_as_float(v[2].x); out[4] = (double)__uint_as_float(v[2].z);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
+    }
+  }
+};
+
+template <typename Real> __device__ __forceinline__ Real fast_warp_sum(Real v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename Model, typename Real, int PPT, int NWMAX>
+__global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) {
   static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
                 "persistent kernel: 1-D models with one normal per transition");
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr bool F32 = sizeof(Real) == 4;
+  constexpr int SPT = fast_spt(PPT);                 // output slots per lane in one expansion pass
+  constexpr int CH = 32 * SPT;                       // ... per warp
+  constexpr int XS = fast_xs(PPT);                   // stride of a lane's particles in the warp's staging array
+  constexpr int VR = 16 / (int)sizeof(Real);         // Reals per 16-byte access
+  static_assert(SPT % 4 == 0 && 32 * XS <= 1024, "16-byte accesses to the head / staging arrays; 10-bit source index");
+  typedef FastRecCodec<F32> Codec;
 #ifndef BSSM_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #else
@@ -131,218 +186,108 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
   const FilterDev& f = P.f;
   const int G = P.G;
   const int group = blockIdx.x / G, b = blockIdx.x % G;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int NW = ((int)blockDim.x >> 5) - 1;         // worker warps; warp NW is the service warp
+  const int NBAR = (NW + 1) * 32;
   // shared memory carve-up
-  double* s_tab = (double*)smem_raw;                 // [5][G]: m, s -> inclusive cdf numerator A, q, sx, pending of every CTA
-  double* s_red = s_tab + ((5 * G + 1) & ~1);        // [5][32] per-warp partials (16-byte aligned)
-  Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
-  unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
-  unsigned int* s_head = s_u + P.cap;                // [cap] (HEADS only) expansion: (source index << 16 | index of its x in s_x) at the first slot of a source
-  Real* s_x = (Real*)(s_head + P.cap);               // [blockDim.x * PPT] this CTA's particles, [PPT/4][threads] x 16 B (conflict-free)
-  constexpr int SPT = fast_spt(PPT);                 // output slots per thread in the expansion: cap = blockDim.x * SPT
-  static_assert(SPT % 4 == 0, "16-byte accesses to the head / staging arrays");
-  __shared__ int s_wf[32];
-  __shared__ unsigned int s_wh[32];
-  __shared__ int s_heavy_n;
-  __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
-  __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
-  __shared__ double s_pending;                       // sum of the x chosen by this CTA in the last resampling
+  double* s_wrec = (double*)smem_raw;                // [5][32] one record per worker warp: m, s, q, sx, pending
+  double* s_T0 = s_wrec + 160;                       // [NW + 1] slot position of the first particle of every warp (and of the next CTA)
+  double* s_sl = s_T0 + 34;                          // [NW] output slots per unit of the warp's e
+  int* s_flag = (int*)(s_sl + 32);                   // dead | resample << 1
+  double* s_tab = (double*)(s_flag + 4);             // [5][G] (service warp) the group's records
+  unsigned int* s_u = (unsigned int*)(s_tab + ((5 * G + 1) & ~1));   // [2][ucap] staged stratified uniforms (raw words), by observation parity
+  unsigned char* s_warp = (unsigned char*)(s_u + 2 * P.ucap);
+  constexpr size_t WARP_BYTES = (size_t)32 * XS * sizeof(Real) + (size_t)CH * sizeof(unsigned int) + (size_t)CH * sizeof(Real);
+  Real* s_xs = (Real*)(s_warp + (size_t)(wid < NW ? wid : 0) * WARP_BYTES);   // [32][XS] this warp's particles
+  unsigned int* s_hd = (unsigned int*)(s_xs + 32 * XS);                         // [CH] expansion: epoch << 10 | index into s_xs, at the first slot of a source
+  Real* s_out = (Real*)(s_hd + CH);                                             // [CH] staging of the chosen x (also: the warp's own window of uniforms)
 
   FastRec* rec = P.rec + (size_t)group * 2 * G;
   typedef typename std::conditional<F32, uint2, uint4>::type XEl;   // LL element of x_new
   XEl* xnew = (XEl*)P.xnew + (size_t)group * G * P.nb_max;
-  unsigned int ep1 = 0, ep2 = 0;   // record / x_new epochs: identical sequences in every CTA of the group
-  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
-  // optional phase timing (diagnostics): compiled in only with -DBSSM_FAST_TIMING_BUILD, because the counters
-  // would otherwise hold ~26 registers for the whole kernel
+  const double INF = __longlong_as_double(0x7FF0000000000000LL), NINF = -INF;
 #ifdef BSSM_FAST_TIMING_BUILD
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
-#define FAST_TICK(ph) do { if (P.timing && tid == 0) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
+#define FAST_TICK(ph) do { if (P.timing && lane == 0 && (wid == 0 || wid == NW)) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
 #else
 #define FAST_TICK(ph) do { } while (0)
 #endif
-  const int R = (G + 31) >> 5;   // records per lane in P2
 
-  for (int c = group; c < f.C; c += P.ngroups) {
-    if (!f.alive[c]) continue;
-    const int n = filt_n(f, c);
-    int nb = (n + G - 1) / G;
-    nb = (nb + PPT - 1) / PPT * PPT;
-    const int base = b * nb;                                  // first global particle of this CTA
-    const int n_loc = max(0, min(n - base, nb));              // particles owned by this CTA
-    const int ibase = base + tid * PPT;                       // first global particle of this thread
-    const int n_own = max(0, min(PPT, min(n - ibase, nb - tid * PPT)));  // owned particles of this thread
-    Real par[Model::NPAR];
-    Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
-    const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
-    const int T1 = f.T + 1;
-    const int ralg = f.ralg;
-    double thr = f.threshold;
-    if (thr < 0) thr = (ralg == 0) ? __longlong_as_double(0x7FF0000000000000LL) : (ralg == 1 ? (double)n : (double)n / 2.0);
-    const double log_n = log((double)n);
-
-    // ---- init (R/particle_filter_core.R:76-116) ----
-    Real x[PPT];
-    double sum0 = 0.0;
+  if (wid == NW) {
+    // =========================== service warp ===========================
+    unsigned int ep1 = 0;          // record epoch: the same sequence in every CTA of the group
+    const int R = (G + 31) >> 5;   // records per lane
+    for (int c = group; c < f.C; c += P.ngroups) {
+      if (!f.alive[c]) continue;
+      const int n = filt_n(f, c);
+      int nb = (n + G - 1) / G;
+      nb = (nb + PPT - 1) / PPT * PPT;
+      const int base = b * nb;
+      const int T1 = f.T + 1;
+      const int ralg = f.ralg;
+      double thr = f.threshold;
+      if (thr < 0) thr = (ralg == 0) ? INF : (ralg == 1 ? (double)n : (double)n / 2.0);
+      const double log_n = log((double)n);
+      double loglike = 0.0;
+      int n_resampled = 0, pending_obs = -1;
+      // phase: 0 = t = 0 state estimate, 1 = observation `obs`, 2 = final flush.  Returns dead | resample << 1
+      auto exchange = [&](int phase, int obs) -> int {
+        FAST_TICK(6);
+        bar_sync_named(FAST_BAR_A, NBAR);
+        FAST_TICK(7);   // wait for the workers' records
+        // ---- the CTA's record: rescale the warp records to the CTA maximum, exclusive prefix over the warps ----
+        const bool act = lane < NW;
+        const double mw = act ? s_wrec[lane] : NINF;
+        const double mb = warp_max_d(mw);
+        double scw = 0.0;
+        if (!(mw == NINF || mb == NINF)) scw = F32 ? (double)__expf((float)(mw - mb)) : exp(mw - mb);
+        const double sbw = act ? s_wrec[32 + lane] * scw : 0.0;
+        const double inc_w = warp_incl_scan_d(sbw, lane);
+        const double wex = inc_w - sbw;
+        const double s_b = __shfl_sync(0xffffffffu, inc_w, 31);
+        const double q_b = warp_sum_d(act ? s_wrec[64 + lane] * scw * scw : 0.0);
+        const double x_b = warp_sum_d(act ? s_wrec[96 + lane] * scw : 0.0);
+        const double p_b = warp_sum_d(act ? s_wrec[128 + lane] : 0.0);
+        ep1++;
+        if (G > 1) {
+          Codec::publish(&rec[(ep1 & 1) * G + b], lane, mb, s_b, q_b, x_b, p_b, ep1);
+          // ---- poll the G records: every load of a round is in flight at once; whatever arrives is decoded into the
+          //      shared-memory table straight away (no registers held across the spin), the last round's values are the valid ones ----
+          constexpr int RB = F32 ? 5 : 3;
+          const FastRec* rb = rec + (ep1 & 1) * G;
+          for (int r0 = 0; r0 < R; r0 += RB) {
+            bool ok;
+            do {
+              ok = true;
 #pragma unroll
-    for (int h = 0; h < PPT / 4; h++) {
-      uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
-      Real zz[4];
-      Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
-      Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+              for (int r = 0; r < RB; r++) {
+                const int j = lane + 32 * (r0 + r);
+                if (r0 + r < R && j < G) {
+                  uint4 v[Codec::NU];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        Real xi[1]; Real zi[1] = {zz[k]};
-        Model::template init<Real>(xi, par, zi, nullptr);
-        x[4 * h + k] = (4 * h + k < n_own) ? xi[0] : (Real)0;   // padding lanes stay finite
-        sum0 += (double)x[4 * h + k];
-      }
-    }
-    int n_resampled = 0;
-    double loglike = 0.0;   // meaningful in thread 0 of CTA 0
-    if (tid == 0) { s_heavy_n = 0; s_pending = 0.0; }
-    if constexpr (HEADS) {
-#pragma unroll
-      for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;   // every thread keeps its own slots of the head array clear
-    }
-    int pending_obs = -1;   // observation whose resampled state estimate is still to be written
-    // t = 0 state estimate: block sum -> record; CTA 0 gathers
-    {
-      double v = warp_sum_d(sum0);
-      if (lane == 0) s_red[wid] = v;
-      __syncthreads();
-      if (wid == 0) {
-        double t = lane < nw ? s_red[lane] : 0.0;
-        t = warp_sum_d(t);
-        if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, t, 0.0, ep1 + 1);
-      }
-      ep1++;
-      // every CTA polls every record (not only CTA 0): a record buffer may only be reused once all CTAs
-      // have passed the poll of the epoch before, which is what orders the two-deep record buffers
-      {
-        double v0 = 0.0;
-        for (int j = tid; j < G; j += blockDim.x) {
-          double rv[5];
-          rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
-          v0 += rv[3];
+                  for (int i = 0; i < Codec::NU; i++) { v[i] = ll_load_v4(&rb[j].w[i]); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
+                  double o[5];
+                  Codec::decode(v, o);
+                  s_tab[j] = o[0]; s_tab[G + j] = o[1]; s_tab[2 * G + j] = o[2]; s_tab[3 * G + j] = o[3]; s_tab[4 * G + j] = o[4];
+                }
+              }
+            } while (!ok);
+          }
+        } else if (lane == 0) {
+          // a group of one: the CTA's record is the group's (rounded like a published one, so that G never changes a result by more than summation order)
+          if (F32) { s_tab[0] = (double)(float)mb; s_tab[1] = s_b; s_tab[2] = (double)(float)q_b; s_tab[3] = (double)(float)x_b; s_tab[4] = (double)(float)p_b; }
+          else { s_tab[0] = mb; s_tab[1] = s_b; s_tab[2] = q_b; s_tab[3] = x_b; s_tab[4] = p_b; }
         }
-        v0 = warp_sum_d(v0);
-        __syncthreads();
-        if (lane == 0) s_red[wid] = v0;
-        __syncthreads();
-        if (b == 0 && tid == 0) {
-          double t = 0.0;
-          for (int w = 0; w < nw; w++) t += s_red[w];
-          f.ess[(size_t)c * T1] = (double)n;
-          f.state_est[(size_t)c * T1] = t / (double)n;
-        }
-      }
-      __syncthreads();
-    }
-
-    // normals of the next transition, generated ahead of time (they do not depend on x)
-    Real zpre[PPT];
-    int zpre_t = -1;   // absolute time index (tnow - 1) the pre-generated normals belong to
-    auto gen_normals = [&](int tz) {
-#pragma unroll
-      for (int h = 0; h < PPT / 4; h++) {
-        uint4x qd = noise_quad(key, (unsigned int)tz, TAG_TRANS_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
-        Math<Real>::box_muller(qd.w[0], qd.w[1], zpre[4 * h + 0], zpre[4 * h + 1]);
-        Math<Real>::box_muller(qd.w[2], qd.w[3], zpre[4 * h + 2], zpre[4 * h + 3]);
-      }
-      zpre_t = tz;
-    };
-
-    double ynext[4] = {0, 0, 0, 0};
-    if (f.T > 0) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[k];
-    for (int obs = 0; obs < f.T; obs++) {
-      const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
-      const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
-      double yv[4] = {ynext[0], ynext[1], ynext[2], ynext[3]};
-      if (obs + 1 < f.T) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[(size_t)(obs + 1) * f.dy + k];   // prefetch
-
-      FAST_TICK(0);
-      // ---- P1: propagate + log-weight ----
-      for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
-        if (zpre_t != tnow - 1) gen_normals(tnow - 1);
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-          Real zi[1] = {zpre[k]};
-          Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
-        }
-      }
-      Real e[PPT];   // first the log-weights, then exp(lw - block max)
-      Real mloc = Math<Real>::ninf();
-#pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
-        if (k >= n_own) e[k] = Math<Real>::ninf();
-        mloc = e[k] > mloc ? e[k] : mloc;
-      }
-      // block max: per-warp partials, then every warp reduces the partials redundantly (one barrier)
-      {
-        Real v = mloc;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-        if (lane == 0) s_red[wid] = (double)v;
-      }
-      __syncthreads();
-      const double mb = warp_max_d(lane < nw ? s_red[lane] : NINF);
-      // e = exp(lw - mb); thread sums; block-local inclusive scan of e
-      double exu;            // block-local exclusive prefix of this thread (unnormalised)
-      {
-        Real fs = 0, fq = 0, fx = 0;
-        const Real mbr = (mb == NINF) ? (Real)0 : (Real)mb;   // exp(-inf - 0) = 0: no per-particle guard
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-          Real ek = Math<Real>::exp_(e[k] - mbr);
-          e[k] = ek;
-          fs += ek; fq += ek * ek; fx += ek * x[k];
-        }
-        const double run = (double)fs;
-        double inc = warp_incl_scan_d(run, lane);
-        double tq = warp_sum_d((double)fq), tx = warp_sum_d((double)fx);
-        __syncthreads();   // s_red partials of the max have been consumed by every warp
-        if (lane == 31) s_red[wid] = inc;            // warp totals of e
-        if (lane == 0) { s_red[32 + wid] = tq; s_red[64 + wid] = tx; }
-        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        exu = lane == 0 ? 0.0 : prev;                // exclusive within the warp
-        __syncthreads();
-        // every warp scans the warp totals redundantly
-        double wt = lane < nw ? s_red[lane] : 0.0;
-        double winc = warp_incl_scan_d(wt, lane);
-        exu += __shfl_sync(0xffffffffu, winc - wt, wid);   // + exclusive prefix of this warp
-        if (wid == 0) {
-          double a0 = __shfl_sync(0xffffffffu, winc, 31);
-          double a1 = warp_sum_d(lane < nw ? s_red[32 + lane] : 0.0), a2 = warp_sum_d(lane < nw ? s_red[64 + lane] : 0.0);
-          if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], mb, a0, a1, a2, s_pending, ep1 + 1);
-        }
-      }
-      ep1++;
-      FAST_TICK(1);   // P1 (propagate, weights, block reductions, publish)
-      // overlap the L2 round trip with the next observation's normals
-      if (obs + 1 < f.T) gen_normals(ot);
-      FAST_TICK(2);   // next-step normals
-      // ---- B1: poll the G records ----
-      for (int j = tid; j < G; j += blockDim.x) {
-        double rv[5];
-        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
-        s_tab[j] = rv[0]; s_tab[G + j] = rv[1]; s_tab[2 * G + j] = rv[2]; s_tab[3 * G + j] = rv[3]; s_tab[4 * G + j] = rv[4];
-      }
-      __syncthreads();
-      FAST_TICK(3);   // B1 poll + barrier
-      // ---- P2: global max / sums / this CTA's cdf interval.  EVERY warp evaluates the same expressions on the
-      //      same table (R consecutive records per lane, one warp scan), so the results are warp-uniform
-      //      registers, bit-identical in every warp of every CTA: no roles, no broadcast, no barrier ----
-      int dead = 0, resample = 0;
-      double lo_cdf = 0.0, hi_cdf = 0.0, wscale = 0.0;
-      {
+        __syncwarp();
+        FAST_TICK(8);   // CTA record + publish + poll
+        // ---- global max / sums / this CTA's cdf interval: R consecutive records per lane, one warp scan; the same
+        //      expressions on the same table in every CTA, so neighbouring CTAs agree on their common boundary bit for bit ----
         double M = NINF;
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
         M = warp_max_d(M);
         const int j0 = lane * R;
-        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0, my_lo = 0.0, my_hi = 0.0;
+        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0, my_lo = 0.0, my_hi = 0.0, my_g = 0.0;
         for (int r = 0; r < R; r++) {
           const int j = j0 + r;
           if (j < G) {
@@ -350,8 +295,8 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
             double sc = 0.0;
             if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
             loc_s += s_tab[G + j] * sc;
-            if (j == b - 1) my_lo = loc_s;            // thread-local inclusive values of records b-1 and b
-            if (j == b) my_hi = loc_s;
+            if (j == b - 1) my_lo = loc_s;            // lane-local inclusive values of records b-1 and b
+            if (j == b) { my_hi = loc_s; my_g = sc; }
             loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
           }
         }
@@ -361,338 +306,400 @@ __global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P)
         const double Q = warp_sum_d(loc_q), SX = warp_sum_d(loc_x), PEND = warp_sum_d(loc_p);
         const double A_hi = __shfl_sync(0xffffffffu, off + my_hi, b / R);
         const double A_lo = b == 0 ? 0.0 : __shfl_sync(0xffffffffu, off + my_lo, (b - 1) / R);
-        const bool bad = (S != S) || (SX != SX) || (M != M);
-        const bool empty = M < -1e8;
-        dead = (bad || empty) ? 1 : 0;
-        // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
-        resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
-        if (resample) {
-          const double invS = 1.0 / S;
-          lo_cdf = A_lo * invS;
-          hi_cdf = (b == G - 1) ? 2.0 : A_hi * invS;
-          double w = 0.0;
-          if (mb != NINF) w = F32 ? (double)__expf((float)(mb - M)) : exp(mb - M);
-          wscale = w * invS;
+        const double g_b = __shfl_sync(0xffffffffu, my_g, b / R);
+        int dead = 0, resample = 0;
+        bool bad = false, empty = false;
+        if (phase == 1) {
+          bad = (S != S) || (SX != SX) || (M != M);
+          empty = M < -1e8;
+          dead = (bad || empty) ? 1 : 0;
+          // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
+          resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
+          if (resample) {
+            // slot position of the first particle of every worker warp, and of the first particle after this CTA;
+            // a warp that starts at or beyond particle n sits at the end of the slots
+            const double nS = (double)n / S;
+            const long long lstart = (long long)lane * 32 * PPT < (long long)nb ? (long long)lane * 32 * PPT : (long long)nb;   // first particle of warp `lane` within the slice
+            double t0 = lstart >= nb ? A_hi * nS : (A_lo + wex * g_b) * nS;    // a warp beyond the slice starts where the next CTA does
+            if ((long long)base + lstart >= (long long)n) t0 = 2.0 * (double)n;
+            if (lane <= NW) s_T0[lane] = t0;
+            if (lane < NW) s_sl[lane] = scw * g_b * nS;
+          }
         }
-        if (b == 0 && tid == 0) {
+        if (lane == 0) s_flag[0] = dead | (resample << 1);
+        bar_arrive_named(FAST_BAR_B, NBAR);
+        FAST_TICK(9);   // merge
+        if (b == 0 && lane == 0) {
           // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
-          if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
-          if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
-            f.status[c] = 3;
-          } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
-            loglike = NINF;
-            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
-            f.early_exit[c] = 1;
+          if (phase == 0) {
+            f.ess[(size_t)c * T1] = (double)n;
+            f.state_est[(size_t)c * T1] = SX / (double)n;
           } else {
-            loglike += (M + log(S) - log_n);
-            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-            f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
-            if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+            if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+            if (phase == 1) {
+              if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+                f.status[c] = 3;
+              } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+                loglike = NINF;
+                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
+                f.early_exit[c] = 1;
+              } else {
+                loglike += (M + log(S) - log_n);
+                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+                f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+                if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+              }
+            } else {
+              f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
+            }
           }
         }
+        pending_obs = resample ? obs : -1;
+        n_resampled += resample;
+        return dead | (resample << 1);
+      };
+      exchange(0, -1);
+      for (int obs = 0; obs < f.T; obs++) {
+        if (exchange(1, obs) & 1) break;
       }
-      FAST_TICK(4);   // P2
-      pending_obs = -1;
-      if (dead) break;
-      if (!resample) continue;
-      n_resampled++;
-      pending_obs = obs;
+      exchange(2, -1);
+    }
+  } else {
+    // =========================== worker warps ===========================
+    const int wt = tid;            // worker thread index
+    const int NWT = NW * 32;
+    unsigned int ep2 = 0;          // x_new epoch: the same sequence in every CTA of the group
+    unsigned int hep = 0;          // head-array epoch of this warp (never reset: stale heads always compare low)
+    for (int i = lane; i < CH; i += 32) s_hd[i] = 0u;
+    __syncwarp();
+    for (int c = group; c < f.C; c += P.ngroups) {
+      if (!f.alive[c]) continue;
+      const int n = filt_n(f, c);
+      int nb = (n + G - 1) / G;
+      nb = (nb + PPT - 1) / PPT * PPT;
+      const int base = b * nb;                                  // first global particle of this CTA
+      const int ibase = base + wt * PPT;                        // first global particle of this thread
+      const int n_own = max(0, min(PPT, min(n - ibase, nb - wt * PPT)));  // owned particles of this thread
+      Real par[Model::NPAR];
+      Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+      const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+      const int ralg = f.ralg;
+      const int u_base = max(0, (base - P.uw) & ~3);            // first slot of the CTA's staged window of uniforms
 
-      // ---- P3: closed-form offspring ranges ----
-      SlotCounter sc;
-      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
-      sc.s_u = s_u; sc.u_cap = P.cap;
-      {
-        double t0 = lo_cdf * (double)n;
-        int i0 = t0 >= (double)n ? n : (int)t0;
-        sc.u_base = max(0, (i0 & ~3) - 4);
-      }
-      if (P.resample_fn == 1) {
-        uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
-        sc.w_sys = q0.w[0];
-      } else {
-        // stage the Philox words of the slots this CTA is expected to serve: one call per 4 slots
-        const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
-        for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += blockDim.x) {
-          uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-          *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
-        }
-        __syncthreads();
-      }
-      FAST_TICK(5);   // stage uniforms
-      const int o_lo = sc.count_le(lo_cdf);
-      const int o_hi = (b == G - 1) ? n : sc.count_le(hi_cdf);
-      // F of this thread's sources (monotone by a running max; clamped into [o_lo, o_hi])
-      int F[PPT];
-      {
-        int fmax = o_lo;
-        if (F32) {
-          // fp64 origin per thread, fp32 increments: t_k = T0 + (sum of e up to k) * wscale * n
-          const double T0 = (lo_cdf + exu * wscale) * (double)n;
-          const double T0c = T0 < (double)n ? T0 : (double)n;
-          const int I0 = (int)T0c;
-          const float f0 = (float)(T0c - (double)I0);
-          const float wsn = (float)(wscale * (double)n);
-          float accf = 0.f;
+      // ---- init (R/particle_filter_core.R:76-116) ----
+      Real x[PPT];
+      Real px = 0;   // sum of this thread's particles after the last resampling (state estimate, travels in the next record)
 #pragma unroll
-          for (int k = 0; k < PPT; k++) {
-            accf += (float)e[k];
-            const float tf = fmaf(accf, wsn, f0);
-            // floor and fraction without conversion instructions (1.5 * 2^23 trick)
-            const float r = (tf - 0.5f) + 12582912.0f;
-            const int ii = __float_as_int(r) - 0x4B400000;
-            const float frac = tf - (r - 12582912.0f);                    // in [0, 1]
-            const float g = frac + 1.0f;                                   // [1, 2]
-            const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;   // frac * 2^32, 23 bits
-            const int i = I0 + ii;
-            int v;
-            if (i >= n) v = n;
-            else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);   // (i + U_i) <= t  <=>  U_i <= frac
-            if (tid * PPT + k == n_loc - 1) v = o_hi;     // clamp: the last particle takes what is left
-            v = min(max(v, o_lo), o_hi);
-            if (k >= n_own) v = o_lo;
-            fmax = max(fmax, v);
-            F[k] = fmax;
-          }
-        } else {
-          double acc = exu;
+      for (int h = 0; h < PPT / 4; h++) {
+        uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
+        Real zz[4];
+        Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
+        Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
 #pragma unroll
-          for (int k = 0; k < PPT; k++) {
-            acc += (double)e[k];
-            int v = o_lo;
-            if (k < n_own) {
-              v = sc.count_le(lo_cdf + acc * wscale);
-              if (tid * PPT + k == n_loc - 1) v = o_hi;
-              v = min(max(v, o_lo), o_hi);
-            }
-            fmax = max(fmax, v);
-            F[k] = fmax;
-          }
+        for (int k = 0; k < 4; k++) {
+          Real xi[1]; Real zi[1] = {zz[k]};
+          Model::template init<Real>(xi, par, zi, nullptr);
+          x[4 * h + k] = (4 * h + k < n_own) ? xi[0] : (Real)0;   // padding lanes stay finite
+          px += x[4 * h + k];
         }
       }
-      // exclusive prefix-max of the per-thread last F over the block
-      int prevF;
+      // t = 0 state estimate: the sum of the initial particles travels in the record's sx
       {
-        int inc = F[PPT - 1];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
-        if (lane == 31) s_wf[wid] = inc;
-        prevF = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) prevF = o_lo;
-        __syncthreads();
-        int wv = lane < nw ? s_wf[lane] : o_lo;
-        int winc = wv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc = max(winc, t); }
-        int wprev = __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);
-        if (wid == 0) wprev = o_lo;
-        prevF = max(prevF, wprev);
-#pragma unroll
-        for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
+        const double v = warp_sum_d((double)px);
+        if (lane == 0) { s_wrec[wid] = 0.0; s_wrec[32 + wid] = 0.0; s_wrec[64 + wid] = 0.0; s_wrec[96 + wid] = v; s_wrec[128 + wid] = 0.0; }
+        bar_arrive_named(FAST_BAR_A, NBAR);
+        bar_sync_named(FAST_BAR_B, NBAR);
+        px = 0;
       }
-      FAST_TICK(6);   // offspring ranges + prefix max
-      // ---- P4: expansion, output-centric (chunks of `cap` slots).  Every source with offspring in the chunk marks the
-      //      first of its slots with (source index, index of its x in s_x); a running maximum over the slots -- source
-      //      indices grow with the slot -- tells every slot its source: O(1) per source and per slot, no loop over
-      //      the offspring of a source, no special case for heavy sources.  The chosen x are staged and leave the
-      //      SM as coalesced 16-byte stores ----
-      //      HEADS = false (big slices, 16 particles per thread): per-source scatter loops into the staging buffer --
-      //      measured 2 % faster there (the expansion pays two more barriers), 20 % slower on small slices ----
-      {
-        Real sumx = 0;
-        if constexpr (HEADS) {
-        const int o_base = o_lo & ~3;
-        const int nthr = blockDim.x;
-        // this CTA's particles into shared memory (the registers are reloaded from x_new below)
+
+      // normals of the next transition, generated ahead of time (they do not depend on x)
+      Real zpre[PPT];
+      int zpre_t = -1;   // absolute time index (tnow - 1) the pre-generated normals belong to
+      auto gen_normals = [&](int tz) {
 #pragma unroll
-        for (int h4 = 0; h4 < PPT / 4; h4++) {
-          if (F32) *(float4*)&s_x[(h4 * nthr + tid) * 4] = make_float4((float)x[4 * h4], (float)x[4 * h4 + 1], (float)x[4 * h4 + 2], (float)x[4 * h4 + 3]);
-          else { s_x[(h4 * nthr + tid) * 4] = x[4 * h4]; s_x[(h4 * nthr + tid) * 4 + 1] = x[4 * h4 + 1]; s_x[(h4 * nthr + tid) * 4 + 2] = x[4 * h4 + 2]; s_x[(h4 * nthr + tid) * 4 + 3] = x[4 * h4 + 3]; }
+        for (int h = 0; h < PPT / 4; h++) {
+          uint4x qd = noise_quad(key, (unsigned int)tz, TAG_TRANS_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
+          Math<Real>::box_muller(qd.w[0], qd.w[1], zpre[4 * h + 0], zpre[4 * h + 1]);
+          Math<Real>::box_muller(qd.w[2], qd.w[3], zpre[4 * h + 2], zpre[4 * h + 3]);
         }
-        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
-          const int c1 = min(o_hi, c0 + P.cap);
-          int lo_k = prevF;
+        zpre_t = tz;
+      };
+
+      double ynext[4] = {0, 0, 0, 0};
+      if (f.T > 0) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[k];
+      for (int obs = 0; obs < f.T; obs++) {
+        const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
+        const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
+        double yv[4] = {ynext[0], ynext[1], ynext[2], ynext[3]};
+        if (obs + 1 < f.T) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[(size_t)(obs + 1) * f.dy + k];   // prefetch
+
+        FAST_TICK(0);
+        // ---- P1: propagate + log-weight ----
+        for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
+          if (zpre_t != tnow - 1) gen_normals(tnow - 1);
 #pragma unroll
           for (int k = 0; k < PPT; k++) {
-            const int hi_k = F[k];
-            const int a = max(lo_k, c0);
-            if (min(hi_k, c1) > a) s_head[a - c0] = ((unsigned int)(tid * PPT + k) << 16) | (unsigned int)(((k >> 2) * nthr + tid) * 4 + (k & 3));
-            if (c0 == o_base && hi_k > lo_k) {
-              // count as a float without a conversion instruction (exact below 2^23)
-              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
-              sumx += (Real)cf * x[k];
-            }
-            lo_k = max(lo_k, hi_k);
+            Real zi[1] = {zpre[k]};
+            Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
           }
-          __syncthreads();
-          unsigned int hd[SPT];
+        }
+        Real e[PPT];   // first the log-weights, then exp(lw - warp max)
+        Real mloc = Math<Real>::ninf();
 #pragma unroll
-          for (int i = 0; i < SPT; i += 4) { const uint4 v4 = *(const uint4*)&s_head[tid * SPT + i]; hd[i] = v4.x; hd[i + 1] = v4.y; hd[i + 2] = v4.z; hd[i + 3] = v4.w; }
+        for (int k = 0; k < PPT; k++) {
+          e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
+          if (k >= n_own) e[k] = Math<Real>::ninf();
+          mloc = e[k] > mloc ? e[k] : mloc;
+        }
+        // warp max (a NaN log-weight is not an ordered maximum: it reaches the sums through exp below)
+        Real mw = mloc;
 #pragma unroll
-          for (int i = 0; i < SPT; i += 4) *(uint4*)&s_head[tid * SPT + i] = make_uint4(0u, 0u, 0u, 0u);   // clear for the next chunk / step
+        for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, mw, o); mw = t > mw ? t : mw; }
+        double exu;            // warp-local exclusive prefix of this thread (unnormalised, relative to the warp max)
+        {
+          Real fs = 0, fq = 0, fx = 0;
+          const Real mr = (mw == Math<Real>::ninf()) ? (Real)0 : mw;   // exp(-inf - 0) = 0: no per-particle guard
 #pragma unroll
-          for (int i = 1; i < SPT; i++) hd[i] = max(hd[i], hd[i - 1]);
-          unsigned int inc = hd[SPT - 1];
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
-          if (lane == 31) s_wh[wid] = inc;
-          unsigned int carry = __shfl_up_sync(0xffffffffu, inc, 1);
-          if (lane == 0) carry = 0u;
-          __syncthreads();
-          {
-            unsigned int wv = lane < nw ? s_wh[lane] : 0u;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, wv, o); if (lane >= o) wv = max(wv, t); }
-            const unsigned int wprev = __shfl_sync(0xffffffffu, wv, (wid + 31) & 31);
-            if (wid > 0) carry = max(carry, wprev);
+          for (int k = 0; k < PPT; k++) {
+            Real ek = Math<Real>::exp_(e[k] - mr);
+            e[k] = ek;
+            fs += ek; fq += ek * ek; fx += ek * x[k];
           }
-          Real val[SPT];
-#pragma unroll
-          for (int i = 0; i < SPT; i++) val[i] = s_x[max(hd[i], carry) & 0xFFFFu];
-#pragma unroll
-          for (int i = 0; i < SPT; i += 4) {
-            if (F32) *(float4*)&s_out[tid * SPT + i] = make_float4((float)val[i], (float)val[i + 1], (float)val[i + 2], (float)val[i + 3]);
-            else { s_out[tid * SPT + i] = val[i]; s_out[tid * SPT + i + 1] = val[i + 1]; s_out[tid * SPT + i + 2] = val[i + 2]; s_out[tid * SPT + i + 3] = val[i + 3]; }
-          }
-          __syncthreads();
-          // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
-          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
-          const unsigned int tag = ep2 + 1;
-          if (F32) {
-            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
-              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
-              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
-              else {
-                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
-                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
-              }
-            }
+          const double run = (double)fs;
+          const double inc = warp_incl_scan_d(run, lane);
+          exu = inc - run;
+          const double ws = __shfl_sync(0xffffffffu, inc, 31);
+          const Real tq = fast_warp_sum<Real>(fq), tx = fast_warp_sum<Real>(fx), tp = fast_warp_sum<Real>(px);
+          if (lane == 0) { s_wrec[wid] = (double)mw; s_wrec[32 + wid] = ws; s_wrec[64 + wid] = (double)tq; s_wrec[96 + wid] = (double)tx; s_wrec[128 + wid] = (double)tp; }
+        }
+        bar_arrive_named(FAST_BAR_A, NBAR);
+        FAST_TICK(1);   // P1 (propagate, weights, warp reductions)
+        // ---- work that does not depend on the exchange ----
+        if (obs + 1 < f.T) gen_normals(ot);
+        unsigned int w_sys = 0u;
+        unsigned int* const su = s_u + (obs & 1) * P.ucap;
+        if (ralg != 0) {
+          if (P.resample_fn == 1) {
+            uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
+            w_sys = q0.w[0];
           } else {
-            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
+            // stage the Philox words of the slots this CTA will probably serve: one call per 4 slots
+            const int q_end = min((n + 3) >> 2, (u_base + P.ucap) >> 2);
+            for (int qd = (u_base >> 2) + wt; qd < q_end; qd += NWT) {
+              uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+              *(uint4*)&su[4 * qd - u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+            }
           }
-          __syncthreads();
         }
-        } else {
-        const int o_base = o_lo & ~3;
-        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
-          const int c1 = min(o_hi, c0 + P.cap);
-          int lo_k = prevF;
-#pragma unroll
-          for (int k = 0; k < PPT; k++) {
-            const int hi_k = F[k];
-            const int a = max(lo_k, c0);
-            int cnt = min(hi_k, c1) - a;
-            if (c0 == o_base && hi_k > lo_k) {
-              // count as a float without a conversion instruction (exact below 2^23)
-              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
-              sumx += (Real)cf * x[k];
-            }
-            if (cnt > FAST_HEAVY) {
-              int slot = atomicAdd(&s_heavy_n, 1);
-              if (slot < FAST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = a + cnt; s_heavy_x[slot] = x[k]; cnt = 0; }
-            }
-            // warp-uniform trip count: no divergent loop bookkeeping
-            const int mx = __reduce_max_sync(0xffffffffu, cnt);
-            Real* dst = s_out + (a - c0);
-            for (int r = 0; r < mx; r++) if (r < cnt) dst[r] = x[k];
-            lo_k = max(lo_k, hi_k);
+        FAST_TICK(2);   // next-step normals + uniforms
+        bar_sync_named(FAST_BAR_B, NBAR);
+        FAST_TICK(3);   // wait for the exchange
+        const int fl = s_flag[0];
+        px = 0;
+        if (fl & 1) break;
+        if (!(fl & 2)) continue;
+
+        // ---- P3: closed-form offspring ranges ----
+        SlotCounter sc;
+        sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = w_sys;
+        sc.s_u = su; sc.u_base = u_base; sc.u_cap = P.ucap;
+        // output range of this warp: F at the warp's first particle and at the next warp's (both neighbours evaluate the same words)
+        int o_start, o_end;
+        {
+          const double tb = s_T0[wid + (lane & 1)];
+          const int o = sc.count_slots(tb);
+          o_start = __shfl_sync(0xffffffffu, o, 0);
+          o_end = __shfl_sync(0xffffffffu, o, 1);
+          if (o_end < o_start) o_end = o_start;   // cannot happen with a monotone table; keeps the ranges sane if it ever did
+        }
+        if (P.resample_fn != 1 && (o_start - 1 < u_base || o_end + 1 > u_base + P.ucap) && o_end > o_start) {
+          // the warp's slots fell outside the CTA's window: stage the warp's own window (what does not fit is recomputed per slot)
+          const int wb = max(0, (o_start - 1) & ~3);
+          unsigned int* const wu = (unsigned int*)s_out;
+          const int q_end = min((n + 3) >> 2, (wb + CH) >> 2);
+          for (int qd = (wb >> 2) + lane; qd < q_end; qd += 32) {
+            uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+            *(uint4*)&wu[4 * qd - wb] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
           }
-          __syncthreads();
-          const int nh = min(s_heavy_n, FAST_HEAVY_CAP);
-          for (int h = 0; h < nh; h++) {
-            const int a = s_heavy_lo[h], z = s_heavy_hi[h];
-            const Real xv = s_heavy_x[h];
-            for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
-          }
-          if (nh) __syncthreads();
-          // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
-          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
-          const unsigned int tag = ep2 + 1;
+          __syncwarp();
+          sc.s_u = wu; sc.u_base = wb; sc.u_cap = CH;
+        }
+        // F of this thread's sources (monotone by a running max; clamped into [o_start, o_end])
+        int F[PPT];
+        {
+          const double sl = s_sl[wid];
+          const double T0 = s_T0[wid] + exu * sl;      // slot position just before this thread's first particle
+          int fmax = o_start;
           if (F32) {
-            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
-              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
-              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
-              else {
-                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
-                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
-              }
-            }
-          } else {
-            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
-          }
-          if (tid == 0) s_heavy_n = 0;
-          __syncthreads();
-        }
-        }
-        // block sum of the chosen x: travels in the next record (state estimate after resampling)
-        double v = warp_sum_d((double)sumx);
-        if (lane == 0) s_red[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-          double t = lane < nw ? s_red[lane] : 0.0;
-          t = warp_sum_d(t);
-          if (lane == 0) s_pending = t;
-        }
-      }
-      ep2++;
-      FAST_TICK(7);   // scatter + copy-out + block sum
-      // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
-      if (n_own > 0) {
-        const XEl* src = xnew + ibase;
-        bool ok;
-        if (F32) {
-          do {
-            ok = true;
-#pragma unroll
-            for (int h = 0; h < PPT / 2; h++) {
-              const uint4 v = ll_load_v4(src + 2 * h);
-              ok = ok && (v.y == ep2 || 2 * h >= n_own) && (v.w == ep2 || 2 * h + 1 >= n_own);
-              x[2 * h] = (Real)__uint_as_float(v.x); x[2 * h + 1] = (Real)__uint_as_float(v.z);
-            }
-          } while (!ok);
-        } else {
-          do {
-            ok = true;
+            // fp64 origin per thread, fp32 increments: t_k = T0 + (sum of e up to k) * sl
+            const double T0c = T0 < (double)n ? T0 : (double)n;
+            const int I0 = (int)T0c;
+            const float f0 = (float)(T0c - (double)I0);
+            const float wsn = (float)sl;
+            float accf = 0.f;
 #pragma unroll
             for (int k = 0; k < PPT; k++) {
-              const uint4 v = ll_load_v4(src + k);
-              ok = ok && ((v.y == ep2 && v.w == ep2) || k >= n_own);
-              x[k] = (Real)ll_get_double(v);
+              accf += (float)e[k];
+              const float tf = fmaf(accf, wsn, f0);
+              // floor and fraction without conversion instructions (1.5 * 2^23 trick)
+              const float r = (tf - 0.5f) + 12582912.0f;
+              const int ii = __float_as_int(r) - 0x4B400000;
+              const float frac = tf - (r - 12582912.0f);                    // in [0, 1]
+              const float g = frac + 1.0f;                                   // [1, 2]
+              const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;   // frac * 2^32, 23 bits
+              const int i = I0 + ii;
+              int v;
+              if (i >= n) v = n;
+              else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);   // (i + U_i) <= t  <=>  U_i <= frac
+              if (ibase + k == n - 1 || (lane == 31 && k == PPT - 1)) v = o_end;   // the warp's last particle takes what is left
+              v = min(max(v, o_start), o_end);
+              if (k >= n_own) v = o_start;
+              fmax = max(fmax, v);
+              F[k] = fmax;
             }
-          } while (!ok);
-        }
-        if (n_own < PPT) {
+          } else {
+            double acc = 0.0;
 #pragma unroll
-          for (int k = 0; k < PPT; k++) if (k >= n_own) x[k] = (Real)0;   // x_new beyond n is never written
+            for (int k = 0; k < PPT; k++) {
+              acc += (double)e[k];
+              int v = o_start;
+              if (k < n_own) {
+                v = sc.count_slots(T0 + acc * sl);
+                if (ibase + k == n - 1 || (lane == 31 && k == PPT - 1)) v = o_end;
+                v = min(max(v, o_start), o_end);
+              }
+              fmax = max(fmax, v);
+              F[k] = fmax;
+            }
+          }
         }
+        // exclusive prefix-max of the per-lane last F over the warp
+        int prevF;
+        {
+          int inc = F[PPT - 1];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+          prevF = __shfl_up_sync(0xffffffffu, inc, 1);
+          if (lane == 0) prevF = o_start;
+#pragma unroll
+          for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
+        }
+        FAST_TICK(4);   // offspring ranges
+        // ---- P4: warp-private expansion, output-centric (passes of CH slots).  Every source with offspring in the pass marks
+        //      the first of its slots with (epoch, index of its x in s_xs); a running maximum over the slots -- source indices grow
+        //      with the slot, older epochs compare low -- tells every slot its source: O(1) per source and per slot, no loop over the
+        //      offspring of a source, no special case for heavy sources, nothing to clear ----
+        {
+          hep++;
+          const unsigned int hkey = hep << 10;
+#pragma unroll
+          for (int h4 = 0; h4 < PPT / VR; h4++) {
+            if (F32) *(float4*)&s_xs[lane * XS + 4 * h4] = make_float4((float)x[4 * h4], (float)x[4 * h4 + 1], (float)x[4 * h4 + 2], (float)x[4 * h4 + 3]);
+            else *(double2*)&s_xs[lane * XS + 2 * h4] = make_double2((double)x[2 * h4], (double)x[2 * h4 + 1]);
+          }
+          const unsigned int tag = ep2 + 1;
+          unsigned int pass_carry = 0u;
+          for (int c0 = o_start & ~3; c0 < o_end; c0 += CH) {
+            const int c1 = min(o_end, c0 + CH);
+            int lo_k = prevF;
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+              const int hi_k = F[k];
+              const int a = max(lo_k, c0);
+              if (min(hi_k, c1) > a) s_hd[a - c0] = hkey | (unsigned int)(lane * XS + k);
+              lo_k = hi_k;
+            }
+            __syncwarp();
+            unsigned int hd[SPT];
+#pragma unroll
+            for (int i = 0; i < SPT; i += 4) { const uint4 v4 = *(const uint4*)&s_hd[lane * SPT + i]; hd[i] = v4.x; hd[i + 1] = v4.y; hd[i + 2] = v4.z; hd[i + 3] = v4.w; }
+#pragma unroll
+            for (int i = 1; i < SPT; i++) hd[i] = max(hd[i], hd[i - 1]);
+            unsigned int inc = hd[SPT - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+            unsigned int carry = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) carry = 0u;
+            carry = max(carry, pass_carry);
+            pass_carry = max(pass_carry, __shfl_sync(0xffffffffu, inc, 31));
+            Real val[SPT];
+#pragma unroll
+            for (int i = 0; i < SPT; i++) val[i] = s_xs[max(hd[i], carry) & 1023u];
+#pragma unroll
+            for (int i = 0; i < SPT; i += VR) {
+              if (F32) *(float4*)&s_out[lane * SPT + i] = make_float4((float)val[i], (float)val[i + 1], (float)val[i + 2], (float)val[i + 3]);
+              else *(double2*)&s_out[lane * SPT + i] = make_double2((double)val[i], (double)val[i + 1]);
+            }
+            __syncwarp();
+            // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
+            const int first = max(c0, o_start), last = c1;   // slots [first, last) are valid in this pass
+            if (F32) {
+#pragma unroll
+              for (int it = 0; it < SPT / 2; it++) {
+                const int o = c0 + 2 * (it * 32 + lane);
+                const float2 v = *(const float2*)&s_out[o - c0];
+                if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v.x), tag, __float_as_uint(v.y), tag);
+                else {
+                  if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v.x), tag);
+                  if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v.y), tag);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < SPT; it++) {
+                const int o = c0 + it * 32 + lane;
+                if (o >= first && o < last) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        ep2++;
+        FAST_TICK(5);   // expansion + LL copy-out
+        // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
+        if (n_own > 0) {
+          const XEl* src = xnew + ibase;
+          bool ok;
+          if (F32) {
+            do {
+              ok = true;
+#pragma unroll
+              for (int h = 0; h < PPT / 2; h++) {
+                const uint4 v = ll_load_v4(src + 2 * h);
+                ok = ok && (v.y == ep2 || 2 * h >= n_own) && (v.w == ep2 || 2 * h + 1 >= n_own);
+                x[2 * h] = (Real)__uint_as_float(v.x); x[2 * h + 1] = (Real)__uint_as_float(v.z);
+              }
+            } while (!ok);
+          } else {
+            do {
+              ok = true;
+#pragma unroll
+              for (int k = 0; k < PPT; k++) {
+                const uint4 v = ll_load_v4(src + k);
+                ok = ok && ((v.y == ep2 && v.w == ep2) || k >= n_own);
+                x[k] = (Real)ll_get_double(v);
+              }
+            } while (!ok);
+          }
+          if (n_own < PPT) {
+#pragma unroll
+            for (int k = 0; k < PPT; k++) if (k >= n_own) x[k] = (Real)0;   // x_new beyond n is never written
+          }
+#pragma unroll
+          for (int k = 0; k < PPT; k++) px += x[k];   // state estimate after resampling: travels in the next record
+        }
+      }  // obs
+      // flush: the state estimate of a final resampling step still travels in the records
+      {
+        const double v = warp_sum_d((double)px);
+        if (lane == 0) { s_wrec[wid] = 0.0; s_wrec[32 + wid] = 0.0; s_wrec[64 + wid] = 0.0; s_wrec[96 + wid] = 0.0; s_wrec[128 + wid] = v; }
+        bar_arrive_named(FAST_BAR_A, NBAR);
+        bar_sync_named(FAST_BAR_B, NBAR);
       }
-      FAST_TICK(8);   // B2 poll (reload) -- no barrier here: warps whose elements arrived start the next step
-    }  // obs
-    // flush: the state estimate of a final resampling step still travels in the records
-    __syncthreads();
-    if (tid == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, 0.0, s_pending, ep1 + 1);
-    ep1++;
-    {
-      double v0 = 0.0;
-      for (int j = tid; j < G; j += blockDim.x) {   // all CTAs poll: see the note at the t = 0 exchange
-        double rv[5];
-        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
-        v0 += rv[4];
-      }
-      v0 = warp_sum_d(v0);
-      if (lane == 0) s_red[wid] = v0;
-      __syncthreads();
-      if (b == 0 && tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < nw; w++) t += s_red[w];
-        if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = t / (double)n;
-        f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
-      }
-    }
-    __syncthreads();
-  }    // filters
+    }    // filters
+  }
 #ifdef BSSM_FAST_TIMING_BUILD
-  if (P.timing && tid == 0) for (int i = 0; i < 12; i++) P.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
+  if (P.timing && lane == 0 && (wid == 0 || wid == NW)) for (int i = 0; i < 12; i++) if (tacc[i]) P.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
 #endif
 #undef FAST_TICK
 }

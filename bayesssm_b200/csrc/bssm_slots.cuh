@@ -40,13 +40,13 @@ struct SlotCounter {
     if (k < (unsigned int)u_cap) return s_u[k];
     return philox_word_slow(key, obs, i);
   }
-  __device__ __forceinline__ int count_le(double c) const {   // exact rule (fp64)
-    double t = c * (double)n;
+  __device__ __forceinline__ int count_slots(double t) const {   // exact rule (fp64), t = c * n: a position in units of slots
     if (!(t > 0.0)) return 0;
     if (t >= (double)n) return n;
     int i = (int)t;
     return i + (((double)i + word_to_unit_f64(word_of(i))) <= t ? 1 : 0);
   }
+  __device__ __forceinline__ int count_le(double c) const { return count_slots(c * (double)n); }
 };
 
 }  // namespace bssm

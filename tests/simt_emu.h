@@ -60,6 +60,7 @@ struct EmuBarrier { int expected = 0, arrived = 0; unsigned int gen = 0; };
 struct EmuFiber { ucontext_t ctx; bool done = false; };
 struct EmuBlock {
   EmuBarrier bar;
+  EmuBarrier nbar[16];            // named barriers (bar.sync / bar.arrive with an id and a thread count)
   std::vector<EmuBarrier> wbar;
   std::vector<uint64_t> xch;
   int orv = 0;
@@ -97,6 +98,13 @@ static void emu_trampoline() {
 }
 
 static inline void __syncthreads() { emu_wait(emu_block->bar); }
+// PTX named barriers: `nthreads` threads take part, some by waiting (sync), some by only announcing themselves (arrive)
+static inline void bar_sync_named(int id, int nthreads) { EmuBarrier& b = emu_block->nbar[id]; b.expected = nthreads; emu_wait(b); }
+static inline void bar_arrive_named(int id, int nthreads) {
+  EmuBarrier& b = emu_block->nbar[id];
+  b.expected = nthreads;
+  if (++b.arrived >= b.expected) emu_open(b);
+}
 static inline int __syncthreads_or(int pred) {
   if (pred) emu_block->orv = 1;
   emu_wait(emu_block->bar);
