@@ -18,6 +18,7 @@ static int fast_ppt_choice(int nb_max) {
   const char* e = getenv("BSSM_FAST_PPT");
   if (e && atoi(e) == 8) return 8;
   if (e && atoi(e) == 16) return 16;
+  if (e && atoi(e) == 12 && nb_max >= 2048) return 12;
   return nb_max >= 2048 ? 16 : 8;
 }
 
@@ -38,31 +39,47 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   if (ngroups > f.C) ngroups = f.C;
   FastParams P;
   P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = g.nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, (size_t)ngroups * 2 * G, &P.rec));
+  constexpr int CUS = FastRecLayout<sizeof(Real) == 4>::CUS;
+  const size_t rec_units = fast_rec_units(ngroups, G, CUS), aux_units = fast_aux_units(ngroups, G);
+  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, rec_units, &P.rec));
+  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 1, aux_units, &P.aux));
   // x_new holds LL elements (value + epoch tag): 8 bytes (f32) / 16 bytes (f64) per particle; tags start at 0
   const size_t xbytes = (size_t)ngroups * G * g.nb_max * (sizeof(Real) == 4 ? 8 : 16);
   BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, xbytes, &P.xnew));
-  BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(FastRec) * (size_t)ngroups * 2 * G, ctx->stream));
+  BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(uint4) * rec_units, ctx->stream));
+  BSSM_CK(cudaMemsetAsync(P.aux, 0, sizeof(uint4) * aux_units, ctx->stream));
   BSSM_CK(cudaMemsetAsync(P.xnew, 0, xbytes, ctx->stream));
   P.timing = nullptr;
   const bool timing = getenv("BSSM_FAST_TIMING") != nullptr;
   if (timing) {
-    BSSM_TRY(scratch(ctx, SL_FAST_BASE + 3, (size_t)ngroups * G * 16, &P.timing));
-    BSSM_CK(cudaMemsetAsync(P.timing, 0, sizeof(long long) * (size_t)ngroups * G * 16, ctx->stream));
+    BSSM_TRY(scratch(ctx, SL_FAST_BASE + 3, (size_t)ngroups * G * 640, &P.timing));
+    BSSM_CK(cudaMemsetAsync(P.timing, 0, sizeof(long long) * (size_t)ngroups * G * 640, ctx->stream));
   }
   void* args[] = {&P};
   BSSM_CK(cudaLaunchCooperativeKernel((void*)kern, dim3(ngroups * G), dim3(g.threads), args, g.smem, ctx->stream));
   BSSM_LAUNCH(ctx, "k_fast_bpf");
-  if (timing) {   // diagnostics only (build with -DBSSM_FAST_TIMING_BUILD): per-phase cycles of worker warp 0 and of the service warp, averaged over the CTAs
-    std::vector<long long> h((size_t)ngroups * G * 16);
+  if (timing) {   // diagnostics only (build with -DBSSM_FAST_TIMING_BUILD): per-phase cycles of every warp, averaged over the CTAs
+    std::vector<long long> h((size_t)ngroups * G * 640);
     BSSM_CK(cudaMemcpyAsync(h.data(), P.timing, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
     BSSM_CK(cudaStreamSynchronize(ctx->stream));
-    const char* names[10] = {"W loop head / B2 tail", "W P1 propagate/weights/reduce", "W normals + uniforms", "W wait for the exchange", "W offspring ranges",
-                             "W expansion + copy-out", "S bookkeeping", "S wait for the workers", "S record + publish + poll", "S merge"};
-    double avg[10];
-    for (int i = 0; i < 10; i++) { double a = 0; for (int c = 0; c < ngroups * G; c++) a += (double)h[(size_t)c * 16 + i]; avg[i] = a / (ngroups * G); }
-    fprintf(stderr, "[bssm fast timing] G=%d groups=%d threads=%d T=%d: cycles per observation (mean over CTAs)\n", G, ngroups, g.threads, f.T);
-    for (int i = 0; i < 10; i++) fprintf(stderr, "  %-32s %9.0f\n", names[i], avg[i] / (f.T > 0 ? f.T : 1));
+    const int ncta = ngroups * G, T = f.T > 0 ? f.T : 1;
+    fprintf(stderr, "[bssm fast timing] G=%d groups=%d threads=%d T=%d: cycles per observation, mean over CTAs\n"
+                    "  worker warps: reload | P1 | wait A | normals+uniforms | wait B | offspring ranges | expansion     service: bookkeeping | wait A | record+publish | poll | merge\n", G, ngroups, g.threads, f.T);
+    for (int w = 0; w <= g.nw && w < 16; w++) {
+      fprintf(stderr, "  warp %2d%s", w, w == g.nw ? " (service)" : "          ");
+      for (int i = 0; i < 7; i++) { double a = 0; for (int c = 0; c < ncta; c++) a += (double)h[((size_t)c * 16 + w) * 8 + i]; fprintf(stderr, " %8.0f", a / ncta / T); }
+      fprintf(stderr, "\n");
+    }
+    if (const char* tf = getenv("BSSM_FAST_TRACE")) {   // absolute times, observations 500 .. 531
+      FILE* fp = fopen(tf, "w");
+      if (fp) {
+        for (int c = 0; c < ncta; c++) for (int o = 0; o < 32; o++) {
+          const long long* q = &h[(size_t)ncta * 128 + ((size_t)c * 32 + o) * 12];
+          fprintf(fp, "%d %d %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", c, o, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9]);
+        }
+        fclose(fp);
+      }
+    }
   }
   return BSSM_OK;
 }
@@ -87,6 +104,7 @@ static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   const int nb = (f.N + G - 1) / G;
   if (L.precision == BSSM_F64) return fast_launch<Model, double, 8, 28>(ctx, f, L, G);
   if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, 14>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 12) return fast_launch<Model, float, 12, 19>(ctx, f, L, G);
   return nb <= 2048 ? fast_launch<Model, float, 8, 8>(ctx, f, L, G) : fast_launch<Model, float, 8, 28>(ctx, f, L, G);
 }
 

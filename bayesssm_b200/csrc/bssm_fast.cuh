@@ -50,16 +50,23 @@ constexpr int FAST_BAR_B = 2;
 // output slots per lane of one expansion pass: 25 % beyond the lane's sources, rounded up to whole 16-byte accesses
 __host__ __device__ constexpr int fast_spt(int ppt) { return (ppt * 5 / 4 + 3) & ~3; }
 // stride (elements) of a lane's particles in the warp's staging array: + 4 keeps the 16-byte accesses conflict-free
-__host__ __device__ constexpr int fast_xs(int ppt) { return ppt + 4; }
+__host__ __device__ constexpr int fast_xs(int ppt) { return ppt % 8 == 4 ? ppt : ppt + 4; }
 
 // LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
 // 16-byte access.  A reader that sees the expected tag also sees the data: no fence, no separate
 // flag, no dependent second load.  The accesses are relaxed at GPU scope (all that an exchange between
 // CTAs of one GPU needs).
-struct __align__(128) FastRec {   // published once per observation by each CTA
-  uint4 w[5];                     // f64: m, s, q, sx, pending as (lo, tag, hi, tag); f32: (m, tag, q, tag), s, (sx, tag, pending, tag)
-  uint4 pad[3];
+// The group exchange: one record per CTA and observation, polled by every CTA of the group.  A record holds what the
+// resampling decision and the cdf need (max, sum, sum of squares of the CTA's weights) in CU 16-byte units; the state
+// sums -- outputs only CTA 0 writes -- travel in a second array that CTA 0 reads after it has released its workers.
+// (scripts/probes/exchange_probe.cu: one store -> remote load hop through the B200's L2 costs about 1060 cycles, an
+// all-to-all of 148 CTAs about 4200; a private inbox per reader, G x G stores, was slower: 6350.)
+template <bool F32> struct FastRecLayout {
+  static constexpr int CU = F32 ? 2 : 3;      // units per record: f32 (s), (m, q); f64 m, s, q
+  static constexpr int CUS = F32 ? 2 : 4;     // stride in units
 };
+__host__ __device__ inline size_t fast_rec_units(int ngroups, int G, int cus) { return (size_t)ngroups * 2 * G * cus; }
+__host__ __device__ inline size_t fast_aux_units(int ngroups, int G) { return (size_t)ngroups * 2 * G * 2; }
 
 // launch geometry, shared by fast_launch() (bssm_fast.cu) and the CPU logic tests
 struct FastGeom {
@@ -90,7 +97,8 @@ struct FastParams {
   FilterDev f;
   int G, ngroups;
   int resample_fn;
-  FastRec* rec;     // [ngroups][2][G]
+  uint4* rec;       // [ngroups][2][G][CUS] LL units: the CTAs' records
+  uint4* aux;       // [ngroups][2][G][2] LL units: the state sums, read by CTA 0
   void* xnew;       // [ngroups][G * nb_max] LL elements: uint2 (f32) / uint4 (f64)
   int nb_max;       // slice stride (multiple of PPT)
   int ucap, uw;     // staged window of stratified uniforms: slots [base - uw, base - uw + ucap) of the CTA with first particle `base`
@@ -133,33 +141,6 @@ __device__ __forceinline__ double ll_get_double(const uint4& v) {
   return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
 }
 
-// record codec.  NU 16-byte units per record: 5 doubles in the parity precision; in the throughput precision the sum of
-// the weights stays fp64 (it becomes the cdf), max / sum of squares / state sums travel as fp32
-template <bool F32> struct FastRecCodec {
-  static constexpr int NU = F32 ? 3 : 5;
-  // lane i < NU stores unit i (the five values are warp-uniform)
-  static __device__ __forceinline__ void publish(FastRec* r, int lane, double m, double s, double q, double sx, double sp, unsigned int tag) {
-    if (F32) {
-      if (lane == 0) ll_store_v4(&r->w[0], __float_as_uint((float)m), tag, __float_as_uint((float)q), tag);
-      else if (lane == 1) ll_put_double(&r->w[1], s, tag);
-      else if (lane == 2) ll_store_v4(&r->w[2], __float_as_uint((float)sx), tag, __float_as_uint((float)sp), tag);
-    } else {
-      const double v = lane == 0 ? m : (lane == 1 ? s : (lane == 2 ? q : (lane == 3 ? sx : sp)));
-      if (lane < 5) ll_put_double(&r->w[lane], v, tag);
-    }
-  }
-  static __device__ __forceinline__ void decode(const uint4* v, double* out /*5*/) {
-    if (F32) {
-      out[0] = (double)__uint_as_float(v[0].x); out[2] = (double)__uint_as_float(v[0].z);
-      out[1] = ll_get_double(v[1]);
-      out[3] = (double)__uint_as_float(v[2].x); out[4] = (double)__uint_as_float(v[2].z);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
-    }
-  }
-};
-
 template <typename Real> __device__ __forceinline__ Real fast_warp_sum(Real v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -176,8 +157,8 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
   constexpr int CH = 32 * SPT;                       // ... per warp
   constexpr int XS = fast_xs(PPT);                   // stride of a lane's particles in the warp's staging array
   constexpr int VR = 16 / (int)sizeof(Real);         // Reals per 16-byte access
-  static_assert(SPT % 4 == 0 && 32 * XS <= 1024, "16-byte accesses to the head / staging arrays; 10-bit source index");
-  typedef FastRecCodec<F32> Codec;
+  static_assert(SPT % 4 == 0 && XS % 8 == 4 && 32 * XS <= 1024, "16-byte accesses to the head / staging arrays; 10-bit source index");
+  typedef FastRecLayout<F32> RL;
 #ifndef BSSM_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #else
@@ -202,16 +183,21 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
   unsigned int* s_hd = (unsigned int*)(s_xs + 32 * XS);                         // [CH] expansion: epoch << 10 | index into s_xs, at the first slot of a source
   Real* s_out = (Real*)(s_hd + CH);                                             // [CH] staging of the chosen x (also: the warp's own window of uniforms)
 
-  FastRec* rec = P.rec + (size_t)group * 2 * G;
+  uint4* const rec = P.rec + (size_t)group * 2 * G * RL::CUS;
+  uint4* const aux = P.aux + (size_t)group * 2 * G * 2;
   typedef typename std::conditional<F32, uint2, uint4>::type XEl;   // LL element of x_new
   XEl* xnew = (XEl*)P.xnew + (size_t)group * G * P.nb_max;
   const double INF = __longlong_as_double(0x7FF0000000000000LL), NINF = -INF;
 #ifdef BSSM_FAST_TIMING_BUILD
-  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
-#define FAST_TICK(ph) do { if (P.timing && lane == 0 && (wid == 0 || wid == NW)) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
+#define FAST_TICK(ph) do { if (P.timing && lane == 0) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
+  // absolute times (ns, %globaltimer) in observations [500, 532): the service warp's exchange and worker warp 5's phases
+#define FAST_TRACE(slot, obs_) do { if (P.timing && lane == 0 && (wid == NW || wid == (NW > 5 ? 5 : 0)) && (obs_) >= 500 && (obs_) < 532) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); \
+    P.timing[(size_t)gridDim.x * 128 + ((size_t)blockIdx.x * 32 + ((obs_) - 500)) * 12 + (slot)] = (long long)g_; } } while (0)
 #else
 #define FAST_TICK(ph) do { } while (0)
+#define FAST_TRACE(slot, obs_) do { } while (0)
 #endif
 
   if (wid == NW) {
@@ -233,84 +219,118 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
       int n_resampled = 0, pending_obs = -1;
       // phase: 0 = t = 0 state estimate, 1 = observation `obs`, 2 = final flush.  Returns dead | resample << 1
       auto exchange = [&](int phase, int obs) -> int {
-        FAST_TICK(6);
+        FAST_TICK(0);
         bar_sync_named(FAST_BAR_A, NBAR);
-        FAST_TICK(7);   // wait for the workers' records
-        // ---- the CTA's record: rescale the warp records to the CTA maximum, exclusive prefix over the warps ----
         const bool act = lane < NW;
-        const double mw = act ? s_wrec[lane] : NINF;
-        const double mb = warp_max_d(mw);
+        const double mw = act ? *(volatile double*)&s_wrec[lane] : NINF;
+        FAST_TICK(1);   // wait for the workers' records
+        FAST_TRACE(0, obs);
+        // ---- the CTA's record: rescale the warp records to the CTA maximum, exclusive prefix over the warps.  First what the
+        //      decision needs (max, sum, sum of squares); the state sums follow after the publication ----
+        double mb;
+        if (F32) {   // the warp maxima are floats: one 32-bit shuffle per step
+          float t = (float)mw;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, t, o); t = u > t ? u : t; }
+          mb = (double)t;
+        } else mb = warp_max_d(mw);
         double scw = 0.0;
         if (!(mw == NINF || mb == NINF)) scw = F32 ? (double)__expf((float)(mw - mb)) : exp(mw - mb);
         const double sbw = act ? s_wrec[32 + lane] * scw : 0.0;
+        const double qbw = act ? s_wrec[64 + lane] * scw * scw : 0.0;
         const double inc_w = warp_incl_scan_d(sbw, lane);
+        const double q_b = F32 ? (double)fast_warp_sum<float>((float)qbw) : warp_sum_d(qbw);
         const double wex = inc_w - sbw;
         const double s_b = __shfl_sync(0xffffffffu, inc_w, 31);
-        const double q_b = warp_sum_d(act ? s_wrec[64 + lane] * scw * scw : 0.0);
+        ep1++;
+        const int par = (int)(ep1 & 1u);
+        if (G > 1) {
+          uint4* dst = rec + (size_t)(par * G + b) * RL::CUS;
+          if (F32) {
+            if (lane == 0) ll_put_double(dst, s_b, ep1);
+            else if (lane == 1) ll_store_v4(dst + 1, __float_as_uint((float)mb), ep1, __float_as_uint((float)q_b), ep1);
+          } else if (lane < 3) ll_put_double(dst + lane, lane == 0 ? mb : (lane == 1 ? s_b : q_b), ep1);
+        }
+        FAST_TICK(2);   // CTA record + publish
+        FAST_TRACE(1, obs);
+        // the state sums: to CTA 0, which reads them after it has released its workers
         const double x_b = warp_sum_d(act ? s_wrec[96 + lane] * scw : 0.0);
         const double p_b = warp_sum_d(act ? s_wrec[128 + lane] : 0.0);
-        ep1++;
         if (G > 1) {
-          Codec::publish(&rec[(ep1 & 1) * G + b], lane, mb, s_b, q_b, x_b, p_b, ep1);
-          // ---- poll the G records: every load of a round is in flight at once; whatever arrives is decoded into the
-          //      shared-memory table straight away (no registers held across the spin), the last round's values are the valid ones ----
-          constexpr int RB = F32 ? 5 : 3;
-          const FastRec* rb = rec + (ep1 & 1) * G;
-          for (int r0 = 0; r0 < R; r0 += RB) {
+          uint4* dst = aux + (size_t)(par * G + b) * 2;
+          if (F32) { if (lane == 0) ll_store_v4(dst, __float_as_uint((float)x_b), ep1, __float_as_uint((float)p_b), ep1); }
+          else if (lane < 2) ll_put_double(dst + lane, lane == 0 ? x_b : p_b, ep1);
+          // ---- poll the G records: every load of a round is in flight at once ----
+          const uint4* src = rec + (size_t)par * G * RL::CUS;
+          const int nunits = G * RL::CUS;
+          constexpr int UB = 10;   // units per lane and round
+          for (int u0 = 0; u0 < nunits; u0 += 32 * UB) {
+            uint4 v[UB];
             bool ok;
             do {
               ok = true;
 #pragma unroll
-              for (int r = 0; r < RB; r++) {
-                const int j = lane + 32 * (r0 + r);
-                if (r0 + r < R && j < G) {
-                  uint4 v[Codec::NU];
-#pragma unroll
-                  for (int i = 0; i < Codec::NU; i++) { v[i] = ll_load_v4(&rb[j].w[i]); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
-                  double o[5];
-                  Codec::decode(v, o);
-                  s_tab[j] = o[0]; s_tab[G + j] = o[1]; s_tab[2 * G + j] = o[2]; s_tab[3 * G + j] = o[3]; s_tab[4 * G + j] = o[4];
-                }
+              for (int i = 0; i < UB; i++) {
+                const int u = u0 + 32 * i + lane;
+                if (u < nunits && (u % RL::CUS) < RL::CU) { v[i] = ll_load_v4(src + u); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
               }
             } while (!ok);
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+              const int u = u0 + 32 * i + lane;
+              if (u < nunits) {
+                const int j = u / RL::CUS, h = u % RL::CUS;
+                if (F32) {
+                  if (h == 0) s_tab[G + j] = ll_get_double(v[i]);
+                  else { s_tab[j] = (double)__uint_as_float(v[i].x); s_tab[2 * G + j] = (double)__uint_as_float(v[i].z); }
+                } else if (h < 3) s_tab[h * G + j] = ll_get_double(v[i]);
+              }
+            }
           }
         } else if (lane == 0) {
           // a group of one: the CTA's record is the group's (rounded like a published one, so that G never changes a result by more than summation order)
-          if (F32) { s_tab[0] = (double)(float)mb; s_tab[1] = s_b; s_tab[2] = (double)(float)q_b; s_tab[3] = (double)(float)x_b; s_tab[4] = (double)(float)p_b; }
-          else { s_tab[0] = mb; s_tab[1] = s_b; s_tab[2] = q_b; s_tab[3] = x_b; s_tab[4] = p_b; }
+          if (F32) { s_tab[0] = (double)(float)mb; s_tab[1] = s_b; s_tab[2] = (double)(float)q_b; }
+          else { s_tab[0] = mb; s_tab[1] = s_b; s_tab[2] = q_b; }
         }
         __syncwarp();
-        FAST_TICK(8);   // CTA record + publish + poll
+        FAST_TICK(3);   // poll
+        FAST_TRACE(2, obs);
         // ---- global max / sums / this CTA's cdf interval: R consecutive records per lane, one warp scan; the same
         //      expressions on the same table in every CTA, so neighbouring CTAs agree on their common boundary bit for bit ----
         double M = NINF;
         for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
-        M = warp_max_d(M);
+        if (F32) {
+          float t = (float)M;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, t, o); t = u > t ? u : t; }
+          M = (double)t;
+        } else M = warp_max_d(M);
         const int j0 = lane * R;
-        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0, my_lo = 0.0, my_hi = 0.0, my_g = 0.0;
+        double loc_s = 0.0, loc_q = 0.0, my_lo = 0.0, my_hi = 0.0, my_g = 0.0;
         for (int r = 0; r < R; r++) {
           const int j = j0 + r;
           if (j < G) {
             const double mj = s_tab[j];
             double sc = 0.0;
             if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
+            s_tab[3 * G + j] = sc;                    // kept for the state sums
             loc_s += s_tab[G + j] * sc;
             if (j == b - 1) my_lo = loc_s;            // lane-local inclusive values of records b-1 and b
             if (j == b) { my_hi = loc_s; my_g = sc; }
-            loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
+            loc_q += s_tab[2 * G + j] * sc * sc;
           }
         }
         const double inc = warp_incl_scan_d(loc_s, lane);
+        const double Q = warp_sum_d(loc_q);
         const double off = inc - loc_s;               // everything before this lane's first record
         const double S = __shfl_sync(0xffffffffu, inc, 31);
-        const double Q = warp_sum_d(loc_q), SX = warp_sum_d(loc_x), PEND = warp_sum_d(loc_p);
         const double A_hi = __shfl_sync(0xffffffffu, off + my_hi, b / R);
         const double A_lo = b == 0 ? 0.0 : __shfl_sync(0xffffffffu, off + my_lo, (b - 1) / R);
         const double g_b = __shfl_sync(0xffffffffu, my_g, b / R);
         int dead = 0, resample = 0;
         bool bad = false, empty = false;
         if (phase == 1) {
-          bad = (S != S) || (SX != SX) || (M != M);
+          bad = (S != S) || (M != M);
           empty = M < -1e8;
           dead = (bad || empty) ? 1 : 0;
           // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
@@ -328,29 +348,52 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
         }
         if (lane == 0) s_flag[0] = dead | (resample << 1);
         bar_arrive_named(FAST_BAR_B, NBAR);
-        FAST_TICK(9);   // merge
-        if (b == 0 && lane == 0) {
-          // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
-          if (phase == 0) {
-            f.ess[(size_t)c * T1] = (double)n;
-            f.state_est[(size_t)c * T1] = SX / (double)n;
+        FAST_TICK(4);   // merge
+        FAST_TRACE(3, obs);
+        if (b == 0) {
+          // the outputs of this observation, off everybody's critical path: the state sums of the group (CTA 0 only)
+          double SX, PEND;
+          if (G > 1) {
+            double lx = 0.0, lp = 0.0;
+            const uint4* src = aux + (size_t)par * G * 2;
+            for (int j = lane; j < G; j += 32) {
+              uint4 v0, v1 = make_uint4(0u, 0u, 0u, 0u);
+              bool ok;
+              do {
+                v0 = ll_load_v4(src + 2 * j);
+                ok = v0.y == ep1 && v0.w == ep1;
+                if (!F32) { v1 = ll_load_v4(src + 2 * j + 1); ok = ok && v1.y == ep1 && v1.w == ep1; }
+              } while (!ok);
+              const double sxj = F32 ? (double)__uint_as_float(v0.x) : ll_get_double(v0);
+              const double pj = F32 ? (double)__uint_as_float(v0.z) : ll_get_double(v1);
+              lx += sxj * s_tab[3 * G + j]; lp += pj;
+            }
+            SX = warp_sum_d(lx); PEND = warp_sum_d(lp);
           } else {
-            if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
-            if (phase == 1) {
-              if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
-                f.status[c] = 3;
-              } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
-                loglike = NINF;
-                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
-                f.early_exit[c] = 1;
-              } else {
-                loglike += (M + log(S) - log_n);
-                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-                f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
-                if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-              }
+            SX = F32 ? (double)(float)x_b : x_b; PEND = F32 ? (double)(float)p_b : p_b;
+          }
+          if (lane == 0) {
+            if (phase == 0) {
+              f.ess[(size_t)c * T1] = (double)n;
+              f.state_est[(size_t)c * T1] = SX / (double)n;
             } else {
-              f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
+              if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+              if (phase == 1) {
+                if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+                  f.status[c] = 3;
+                } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+                  loglike = NINF;
+                  if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
+                  f.early_exit[c] = 1;
+                } else {
+                  loglike += (M + log(S) - log_n);
+                  if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+                  f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+                  if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+                }
+              } else {
+                f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
+              }
             }
           }
         }
@@ -407,7 +450,7 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
       {
         const double v = warp_sum_d((double)px);
         if (lane == 0) { s_wrec[wid] = 0.0; s_wrec[32 + wid] = 0.0; s_wrec[64 + wid] = 0.0; s_wrec[96 + wid] = v; s_wrec[128 + wid] = 0.0; }
-        bar_arrive_named(FAST_BAR_A, NBAR);
+        bar_sync_named(FAST_BAR_A, NBAR);
         bar_sync_named(FAST_BAR_B, NBAR);
         px = 0;
       }
@@ -433,7 +476,8 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
         double yv[4] = {ynext[0], ynext[1], ynext[2], ynext[3]};
         if (obs + 1 < f.T) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[(size_t)(obs + 1) * f.dy + k];   // prefetch
 
-        FAST_TICK(0);
+        FAST_TICK(0);   // reload of x_new (resample steps)
+        FAST_TRACE(8, obs);
         // ---- P1: propagate + log-weight ----
         for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
           if (zpre_t != tnow - 1) gen_normals(tnow - 1);
@@ -472,8 +516,13 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
           const Real tq = fast_warp_sum<Real>(fq), tx = fast_warp_sum<Real>(fx), tp = fast_warp_sum<Real>(px);
           if (lane == 0) { s_wrec[wid] = (double)mw; s_wrec[32 + wid] = ws; s_wrec[64 + wid] = (double)tq; s_wrec[96 + wid] = (double)tx; s_wrec[128 + wid] = (double)tp; }
         }
-        bar_arrive_named(FAST_BAR_A, NBAR);
         FAST_TICK(1);   // P1 (propagate, weights, warp reductions)
+        FAST_TRACE(9, obs);
+        // all records are in: the service warp runs the exchange, the workers the part of the resampling and of the next
+        // observation that does not depend on it.  A full barrier rather than an arrive: the next normals of a fast warp must
+        // not take issue slots from a slower warp's weights, which are on the critical path
+        bar_sync_named(FAST_BAR_A, NBAR);
+        FAST_TICK(2);   // wait for the other workers
         // ---- work that does not depend on the exchange ----
         if (obs + 1 < f.T) gen_normals(ot);
         unsigned int w_sys = 0u;
@@ -491,10 +540,11 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
             }
           }
         }
-        FAST_TICK(2);   // next-step normals + uniforms
+        FAST_TICK(3);   // next-step normals + uniforms
         bar_sync_named(FAST_BAR_B, NBAR);
-        FAST_TICK(3);   // wait for the exchange
-        const int fl = s_flag[0];
+        const int fl = *(volatile int*)&s_flag[0];
+        FAST_TICK(4);   // wait for the exchange
+        FAST_TRACE(4, obs);
         px = 0;
         if (fl & 1) break;
         if (!(fl & 2)) continue;
@@ -584,7 +634,8 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
 #pragma unroll
           for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
         }
-        FAST_TICK(4);   // offspring ranges
+        FAST_TICK(5);   // offspring ranges
+        FAST_TRACE(6, obs);
         // ---- P4: warp-private expansion, output-centric (passes of CH slots).  Every source with offspring in the pass marks
         //      the first of its slots with (epoch, index of its x in s_xs); a running maximum over the slots -- source indices grow
         //      with the slot, older epochs compare low -- tells every slot its source: O(1) per source and per slot, no loop over the
@@ -655,7 +706,8 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
           }
         }
         ep2++;
-        FAST_TICK(5);   // expansion + LL copy-out
+        FAST_TICK(6);   // expansion + LL copy-out
+        FAST_TRACE(7, obs);
         // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
         if (n_own > 0) {
           const XEl* src = xnew + ibase;
@@ -693,15 +745,16 @@ __global__ void __launch_bounds__((NWMAX + 1) * 32, 1) k_fast_bpf(FastParams P) 
       {
         const double v = warp_sum_d((double)px);
         if (lane == 0) { s_wrec[wid] = 0.0; s_wrec[32 + wid] = 0.0; s_wrec[64 + wid] = 0.0; s_wrec[96 + wid] = 0.0; s_wrec[128 + wid] = v; }
-        bar_arrive_named(FAST_BAR_A, NBAR);
+        bar_sync_named(FAST_BAR_A, NBAR);
         bar_sync_named(FAST_BAR_B, NBAR);
       }
     }    // filters
   }
 #ifdef BSSM_FAST_TIMING_BUILD
-  if (P.timing && lane == 0 && (wid == 0 || wid == NW)) for (int i = 0; i < 12; i++) if (tacc[i]) P.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
+  if (P.timing && lane == 0 && wid < 16) for (int i = 0; i < 8; i++) P.timing[((size_t)blockIdx.x * 16 + wid) * 8 + i] = tacc[i];
 #endif
 #undef FAST_TICK
+#undef FAST_TRACE
 }
 
 }  // namespace bssm

@@ -58,11 +58,10 @@ static int run(int argc, char** argv) {
   f.ess = ess.data(); f.state_est = se.data(); f.loglike_history = llh.data();
   f.algorithm = 0; f.ralg = ralg; f.threshold = threshold;
   P.G = G; P.ngroups = ngroups; P.resample_fn = rfn; P.nb_max = nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<FastRec> rec((size_t)ngroups * 2 * G);
-  memset((void*)rec.data(), 0, sizeof(FastRec) * rec.size());
+  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<sizeof(Real) == 4>::CUS), uint4{0, 0, 0, 0}), aux(fast_aux_units(ngroups, G), uint4{0, 0, 0, 0});
   const size_t xbytes = (size_t)ngroups * G * nb_max * (sizeof(Real) == 4 ? 8 : 16);
   std::vector<unsigned long long> xnew(xbytes / 8, 0ull);   // exactly what fast_launch() allocates (AddressSanitizer runs rely on it)
-  P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
+  P.rec = rec.data(); P.aux = aux.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
   emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<Model, Real, PPT, NWMAX>(Pc); });
   for (int c = 0; c < C; c++) {
@@ -83,6 +82,7 @@ template <typename Model> static int by_variant(int argc, char** argv) {
     case 0: case 1: return run<Model, double, 8, 28>(argc, argv);
     case 2: return run<Model, float, 8, 8>(argc, argv);
     case 3: return run<Model, float, 16, 14>(argc, argv);
+    case 4: return run<Model, float, 12, 19>(argc, argv);
   }
   return 2;
 }

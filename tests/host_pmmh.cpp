@@ -44,10 +44,9 @@ static void run_filters(const FilterDev& f, int resample_fn, const int* active, 
   FastParams P;
   memset(&P, 0, sizeof(P));
   P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = resample_fn; P.nb_max = nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<FastRec> rec((size_t)ngroups * 2 * G);
-  memset((void*)rec.data(), 0, sizeof(FastRec) * rec.size());
+  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<false>::CUS), uint4{0, 0, 0, 0}), aux(fast_aux_units(ngroups, G), uint4{0, 0, 0, 0});
   std::vector<unsigned long long> xnew((size_t)ngroups * G * nb_max * 2, 0ull);
-  P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
+  P.rec = rec.data(); P.aux = aux.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
   emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<ModelArSin, double, 8, 28>(Pc); });
 }
