@@ -38,47 +38,35 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   int ngroups = (int)(resident / G);
   if (ngroups > f.C) ngroups = f.C;
   FastParams P;
-  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = g.nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  constexpr int CUS = FastRecLayout<sizeof(Real) == 4>::CUS;
-  const size_t rec_units = fast_rec_units(ngroups, G, CUS), aux_units = fast_aux_units(ngroups, G);
+  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = L.resample_fn; P.nb_max = g.nb_max; P.xstride = g.xstride; P.ucap = g.ucap; P.uw = g.uw;
+  const size_t rec_units = fast_rec_units(ngroups, G, FastRecLayout<sizeof(Real) == 4>::NUS);
   BSSM_TRY(scratch(ctx, SL_FAST_BASE + 0, rec_units, &P.rec));
-  BSSM_TRY(scratch(ctx, SL_FAST_BASE + 1, aux_units, &P.aux));
   // x_new holds LL elements (value + epoch tag): 8 bytes (f32) / 16 bytes (f64) per particle; tags start at 0
-  const size_t xbytes = (size_t)ngroups * G * g.nb_max * (sizeof(Real) == 4 ? 8 : 16);
+  const size_t xbytes = (size_t)ngroups * g.xstride * (sizeof(Real) == 4 ? 8 : 16);
   BSSM_TRY(scratch_get(ctx, SL_FAST_BASE + 2, xbytes, &P.xnew));
   BSSM_CK(cudaMemsetAsync(P.rec, 0, sizeof(uint4) * rec_units, ctx->stream));
-  BSSM_CK(cudaMemsetAsync(P.aux, 0, sizeof(uint4) * aux_units, ctx->stream));
   BSSM_CK(cudaMemsetAsync(P.xnew, 0, xbytes, ctx->stream));
   P.timing = nullptr;
   const bool timing = getenv("BSSM_FAST_TIMING") != nullptr;
   if (timing) {
-    BSSM_TRY(scratch(ctx, SL_FAST_BASE + 3, (size_t)ngroups * G * 640, &P.timing));
-    BSSM_CK(cudaMemsetAsync(P.timing, 0, sizeof(long long) * (size_t)ngroups * G * 640, ctx->stream));
+    BSSM_TRY(scratch(ctx, SL_FAST_BASE + 3, (size_t)ngroups * G * 192, &P.timing));
+    BSSM_CK(cudaMemsetAsync(P.timing, 0, sizeof(long long) * (size_t)ngroups * G * 192, ctx->stream));
   }
   void* args[] = {&P};
   BSSM_CK(cudaLaunchCooperativeKernel((void*)kern, dim3(ngroups * G), dim3(g.threads), args, g.smem, ctx->stream));
   BSSM_LAUNCH(ctx, "k_fast_bpf");
   if (timing) {   // diagnostics only (build with -DBSSM_FAST_TIMING_BUILD): per-phase cycles of every warp, averaged over the CTAs
-    std::vector<long long> h((size_t)ngroups * G * 640);
+    std::vector<long long> h((size_t)ngroups * G * 192);
     BSSM_CK(cudaMemcpyAsync(h.data(), P.timing, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
     BSSM_CK(cudaStreamSynchronize(ctx->stream));
     const int ncta = ngroups * G, T = f.T > 0 ? f.T : 1;
     fprintf(stderr, "[bssm fast timing] G=%d groups=%d threads=%d T=%d: cycles per observation, mean over CTAs\n"
-                    "  worker warps: reload | P1 | wait A | normals+uniforms | wait B | offspring ranges | expansion     service: bookkeeping | wait A | record+publish | poll | merge\n", G, ngroups, g.threads, f.T);
-    for (int w = 0; w <= g.nw && w < 16; w++) {
-      fprintf(stderr, "  warp %2d%s", w, w == g.nw ? " (service)" : "          ");
-      for (int i = 0; i < 7; i++) { double a = 0; for (int c = 0; c < ncta; c++) a += (double)h[((size_t)c * 16 + w) * 8 + i]; fprintf(stderr, " %8.0f", a / ncta / T); }
+                    "  0 reload | 11 P1a | 8 barriers(max,totals) | 1 P1b | 9 scan+publish | 2 overlap | 3 poll | 10 barrier(records) | 4 merge | 5 uniforms | 6 ranges | 7 expansion\n", G, ngroups, g.threads, f.T);
+    for (int w = 0; w < g.nw && w < 16; w++) {
+      fprintf(stderr, "  warp %2d", w);
+      const int order[12] = {0, 11, 8, 1, 9, 2, 3, 10, 4, 5, 6, 7};
+      for (int k = 0; k < 12; k++) { const int i = order[k]; double a = 0; for (int c = 0; c < ncta; c++) a += (double)h[((size_t)c * 16 + w) * 12 + i]; fprintf(stderr, " %7.0f", a / ncta / T); }
       fprintf(stderr, "\n");
-    }
-    if (const char* tf = getenv("BSSM_FAST_TRACE")) {   // absolute times, observations 500 .. 531
-      FILE* fp = fopen(tf, "w");
-      if (fp) {
-        for (int c = 0; c < ncta; c++) for (int o = 0; o < 32; o++) {
-          const long long* q = &h[(size_t)ncta * 128 + ((size_t)c * 32 + o) * 12];
-          fprintf(fp, "%d %d %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", c, o, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9]);
-        }
-        fclose(fp);
-      }
     }
   }
   return BSSM_OK;
@@ -103,8 +91,8 @@ static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   if (G < 1) G = 1;
   const int nb = (f.N + G - 1) / G;
   if (L.precision == BSSM_F64) return fast_launch<Model, double, 8, 28>(ctx, f, L, G);
-  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, 14>(ctx, f, L, G);
-  if (fast_ppt_choice(nb) == 12) return fast_launch<Model, float, 12, 19>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, 16>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 12) return fast_launch<Model, float, 12, 20>(ctx, f, L, G);
   return nb <= 2048 ? fast_launch<Model, float, 8, 8>(ctx, f, L, G) : fast_launch<Model, float, 8, 28>(ctx, f, L, G);
 }
 

@@ -8,7 +8,7 @@
 // usage: host_fast model variant G ngroups N T C resample_fn ralg threshold seed run_id stream_base [n_0 ... n_{C-1}]
 //   (optional trailing particle counts: a ragged batch, FilterDev::n_per; N is then the maximum)
 //                  < y (T doubles) theta (C x 3 doubles)
-//   variant: 0, 1 = <double, 8, 28 worker warps>, 2 = <float, 8, 8>, 3 = <float, 16, 14>   (EMU_UW: slack of the staged window of uniforms)
+//   variant: 0, 1 = <double, 8, 28 worker warps>, 2 = <float, 8, 8>, 3 = <float, 16, 16>, 4 = <float, 12, 20>   (EMU_UW: slack of the staged window of uniforms)
 #include "simt_emu.h"
 
 #include "../bayesssm_b200/csrc/bssm_fast.cuh"
@@ -57,11 +57,11 @@ static int run(int argc, char** argv) {
   f.alive = alive.data(); f.status = status.data(); f.early_exit = early.data(); f.n_resampled = nres.data();
   f.ess = ess.data(); f.state_est = se.data(); f.loglike_history = llh.data();
   f.algorithm = 0; f.ralg = ralg; f.threshold = threshold;
-  P.G = G; P.ngroups = ngroups; P.resample_fn = rfn; P.nb_max = nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<sizeof(Real) == 4>::CUS), uint4{0, 0, 0, 0}), aux(fast_aux_units(ngroups, G), uint4{0, 0, 0, 0});
-  const size_t xbytes = (size_t)ngroups * G * nb_max * (sizeof(Real) == 4 ? 8 : 16);
+  P.G = G; P.ngroups = ngroups; P.resample_fn = rfn; P.nb_max = nb_max; P.xstride = g.xstride; P.ucap = g.ucap; P.uw = g.uw;
+  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<sizeof(Real) == 4>::NUS), uint4{0, 0, 0, 0});
+  const size_t xbytes = (size_t)ngroups * g.xstride * (sizeof(Real) == 4 ? 8 : 16);
   std::vector<unsigned long long> xnew(xbytes / 8, 0ull);   // exactly what fast_launch() allocates (AddressSanitizer runs rely on it)
-  P.rec = rec.data(); P.aux = aux.data(); P.xnew = xnew.data(); P.timing = nullptr;
+  P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
   emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<Model, Real, PPT, NWMAX>(Pc); });
   for (int c = 0; c < C; c++) {
@@ -81,8 +81,8 @@ template <typename Model> static int by_variant(int argc, char** argv) {
   switch (atoi(argv[2])) {
     case 0: case 1: return run<Model, double, 8, 28>(argc, argv);
     case 2: return run<Model, float, 8, 8>(argc, argv);
-    case 3: return run<Model, float, 16, 14>(argc, argv);
-    case 4: return run<Model, float, 12, 19>(argc, argv);
+    case 3: return run<Model, float, 16, 16>(argc, argv);
+    case 4: return run<Model, float, 12, 20>(argc, argv);
   }
   return 2;
 }

@@ -43,10 +43,10 @@ static void run_filters(const FilterDev& f, int resample_fn, const int* active, 
   const int ngroups = (int)std::min<size_t>(C, 4);
   FastParams P;
   memset(&P, 0, sizeof(P));
-  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = resample_fn; P.nb_max = nb_max; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<false>::CUS), uint4{0, 0, 0, 0}), aux(fast_aux_units(ngroups, G), uint4{0, 0, 0, 0});
-  std::vector<unsigned long long> xnew((size_t)ngroups * G * nb_max * 2, 0ull);
-  P.rec = rec.data(); P.aux = aux.data(); P.xnew = xnew.data(); P.timing = nullptr;
+  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = resample_fn; P.nb_max = nb_max; P.xstride = g.xstride; P.ucap = g.ucap; P.uw = g.uw;
+  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<false>::NUS), uint4{0, 0, 0, 0});
+  std::vector<unsigned long long> xnew((size_t)ngroups * g.xstride * 2, 0ull);
+  P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
   emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<ModelArSin, double, 8, 28>(Pc); });
 }
