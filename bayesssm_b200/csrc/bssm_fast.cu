@@ -91,8 +91,8 @@ static int fast_model(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L) {
   if (G < 1) G = 1;
   const int nb = (f.N + G - 1) / G;
   if (L.precision == BSSM_F64) return fast_launch<Model, double, 8, 28>(ctx, f, L, G);
-  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, 16>(ctx, f, L, G);
-  if (fast_ppt_choice(nb) == 12) return fast_launch<Model, float, 12, 20>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 16) return fast_launch<Model, float, 16, 14>(ctx, f, L, G);
+  if (fast_ppt_choice(nb) == 12) return fast_launch<Model, float, 12, 19>(ctx, f, L, G);
   return nb <= 2048 ? fast_launch<Model, float, 8, 8>(ctx, f, L, G) : fast_launch<Model, float, 8, 28>(ctx, f, L, G);
 }
 

@@ -5,13 +5,18 @@
 // [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps (PPT particles per thread).
 // Per observation:
 //   P1  propagate (normals pre-generated while the previous record travelled; one Philox call per 4
-//       particles) + log-weight; block max; e = exp(lw - max_b); block sums of e, e^2, e*x and the
-//       block-local inclusive scan of e                       [registers + shuffles, 2 block barriers]
+//       particles) + log-weight; e = exp(lw - ref) against a reference every CTA knows WITHOUT
+//       communication -- the model's upper bound of the log-likelihood -- so the weights of all CTAs
+//       are on one scale from the start: block sums of e, e^2, e*x, block max of lw and the block-local
+//       inclusive scan of e                                   [registers + shuffles, 1 block barrier]
 //   B1  every CTA publishes (max_b, sums) as an epoch-stamped LL record in L2, generates the NEXT
-//       step's normals while the record travels, then polls the G records (no atomics, no fences);
-//       every warp of every CTA derives, redundantly but bit-identically, the global max / sum / ESS /
-//       resampling decision, the cdf interval of its CTA and the slot positions where its own
-//       particles begin and end                                  [1 L2 all-to-all, 1 block barrier]
+//       step's normals while the record travels, then polls the G records (no atomics, no fences): the
+//       polling warps scan the records of 32 CTAs each, and after one block barrier every warp adds up at
+//       most 8 group totals to get -- bit-identically in every warp of every CTA -- the global sum / ESS /
+//       resampling decision, the cdf interval of its CTA and the slot positions where its own particles
+//       begin and end.  (If the best particle lies more than e^-60 below the bound -- an outlying
+//       observation -- the step is redone against the true maximum, which the records carry.)
+//                                                                [1 L2 all-to-all, 1 block barrier]
 //   P3  INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form -- the
 //       number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
 //       slots [F(c_{j-1}), F(c_j)).  No search.  Warp boundaries are F of values both neighbouring
@@ -66,24 +71,24 @@ struct FastGeom {
   size_t smem;
 };
 template <typename Real, int PPT>
-inline FastGeom fast_geometry(int N, int G, int uw_req) {
+inline FastGeom fast_geometry(int N, int G, int uw_req /* < 0: default */) {
   FastGeom g;
   g.nb_max = (N + G - 1) / G;
   g.nb_max = (g.nb_max + PPT - 1) / PPT * PPT;
   g.nw = (g.nb_max + 32 * PPT - 1) / (32 * PPT);
   if (g.nw < 1) g.nw = 1;
-  // a multiple of 4 warps when the CTA has several: the warps share the slice evenly (each a contiguous run of at most 32 * PPT
-  // particles), so the four warp schedulers of the SM carry the same load
-  if (g.nw > 2) g.nw = (g.nw + 3) & ~3;
   g.threads = g.nw * 32;
   g.ch = 32 * fast_spt(PPT);
   // uw_req < 0: no CTA-wide window of stratified uniforms staged ahead of the exchange -- every warp stages exactly its own output
   // range after it; >= 0: a window around the CTA's slice with that slack (misses are repaired per warp)
+  // default for big slices: a window with 1536 slots of slack on either side (measured on the B200 at N = 2^20: 72.6 G particle-
+  // timesteps/s without a window, 80.1 / 81.4 / 82.8 / 71.4 with 512 / 1012 / 1536 / 2048)
+  if (uw_req < 0 && g.nb_max >= 4096 && sizeof(Real) == 4) uw_req = 1536;
   g.uw = uw_req >= 0 ? (uw_req + 3) & ~3 : 0;
   g.ucap = uw_req >= 0 ? (g.nb_max + 2 * g.uw + 3) & ~3 : 0;
   g.xstride = G * g.nb_max + 32 * PPT;   // a partly filled lane reads whole 16-byte pairs beyond its particles
   if (sizeof(Real) == 8 && g.nw > 14) { g.uw = 0; g.ucap = 0; }
-  g.smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + (size_t)(34 + 4 * 32) * sizeof(double) + (size_t)2 * g.ucap * sizeof(unsigned int) +
+  g.smem = (size_t)(((G + 1) & ~1) + 40 + 32 + 4 * 32) * sizeof(double) + (size_t)2 * g.ucap * sizeof(unsigned int) +
            (size_t)g.nw * ((size_t)32 * fast_xs(PPT) * sizeof(Real) + (size_t)g.ch * sizeof(unsigned int) + (size_t)g.ch * sizeof(Real));
   return g;
 }
@@ -168,9 +173,10 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
   const int NW = (int)blockDim.x >> 5;
   const int NT = (int)blockDim.x;
   // shared memory carve-up
-  double* s_tab = (double*)smem_raw;                 // [5][G] the group's records: m, s, q, sx, pending
-  double* s_max = s_tab + ((5 * G + 1) & ~1);        // [32] per-warp maxima of the log-weights, [32] the block's
-  double* s_tot = s_max + 34;                        // [4][32] per-warp sums of e, e^2, e*x and of the resampled x
+  double* s_pre = (double*)smem_raw;                 // [G] the group's records: inclusive sums of the CTAs' weight totals within groups of 32 records
+  double* s_grp = s_pre + ((G + 1) & ~1);            // [5][8] per group of 32 records: max, total, sum of squares, state sum, pending state sum
+  double* s_max = s_grp + 40;                        // [32] per-warp maxima of the log-weights
+  double* s_tot = s_max + 32;                        // [4][32] per-warp sums of e, e^2, e*x and of the resampled x
   unsigned int* s_u = (unsigned int*)(s_tot + 4 * 32);   // [2][ucap] (optional) stratified uniforms staged ahead of the exchange, by observation parity
   unsigned char* s_warp = (unsigned char*)(s_u + 2 * P.ucap);
   constexpr size_t WARP_BYTES = (size_t)32 * XS * sizeof(Real) + (size_t)CH * sizeof(unsigned int) + (size_t)CH * sizeof(Real);
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
     int nb = (n + G - 1) / G;
     nb = (nb + PPT - 1) / PPT * PPT;
     const int base = b * nb;                                  // first global particle of this CTA
-    const int ws = NW > 2 ? ((nb + NW - 1) / NW + 3) & ~3 : 32 * PPT;   // particles per warp: the slice shared evenly, whole Philox quads
+    const int ws = 32 * PPT;                                  // particles per warp
     const int wbase = min(wid * ws, nb);                      // first particle of this warp within the slice
     const int wcnt = max(0, min(min(ws, nb - wbase), n - (base + wbase)));   // particles of this warp
     const int ibase = base + wid * ws + lane * PPT;           // first global particle of this thread
@@ -224,14 +230,15 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
     double loglike = 0.0;                            // meaningful in thread 0 of CTA 0
     int n_resampled = 0, pending_obs = -1;
 
-    // ---- one exchange.  phase 0: t = 0 state estimate, 1: observation `obs`, 2: final flush.  In: this warp's max (phase 1),
-    //      the thread's sums.  Returns dead | resample << 1; leaves t_start / t_end / t_sl / w_start ----
-    auto exchange = [&](int phase, int obs, Real mw, double inc_e /* warp-inclusive scan of the thread sums of e */, Real fq, Real fx, Real fp,
-                        auto&& overlap) -> int {
+    double g_M = 0.0;                                // global max of the log-weights of the last exchange
+    // ---- one exchange.  phase 0: t = 0 state estimate, 1: observation `obs`, 2: final flush.  In: this warp's max of the log-weights
+    //      (phase 1), the warp-inclusive scan of the thread sums of e = exp(lw - ref), the thread's other sums.  Returns dead |
+    //      resample << 1, or 4: the weights underflow against `ref`, redo against g_M; leaves t_start / t_end / t_sl / w_start ----
+    auto exchange = [&](int phase, int obs, Real mw, double inc_e, Real fq, Real fx, Real fp, Real ref, auto&& overlap) -> int {
       // block totals: per-warp sums -> shared memory -> every warp scans them redundantly (bit-identical in all warps)
       const Real tq = fast_warp_sum<Real>(fq), tx = fast_warp_sum<Real>(fx), tp = fast_warp_sum<Real>(fp);
       if (lane == 31) s_tot[wid] = inc_e;
-      if (lane == 0) { s_tot[32 + wid] = (double)tq; s_tot[64 + wid] = (double)tx; s_tot[96 + wid] = (double)tp; }
+      if (lane == 0) { s_tot[32 + wid] = (double)tq; s_tot[64 + wid] = (double)tx; s_tot[96 + wid] = (double)tp; s_max[wid] = (double)mw; }
       FAST_TICK(1);   // P1 (propagate, weights, warp reductions)
       __syncthreads();
       const double wt = lane < NW ? *(volatile double*)&s_tot[lane] : 0.0;
@@ -241,85 +248,88 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
       w_start = wid == 0 ? 0.0 : __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);     // ... before this warp: the previous warp's w_end, bit for bit
       ep1++;
       const int par = (int)(ep1 & 1u);
+      const int npg = (G + 31) >> 5;                  // groups of 32 records
       if (wid == 0) {
         // the CTA's record, by warp 0
         const double s_b = __shfl_sync(0xffffffffu, winc, 31);
-        const double q_b = warp_sum_d(lane < NW ? s_tot[32 + lane] : 0.0), x_b = warp_sum_d(lane < NW ? s_tot[64 + lane] : 0.0),
-                     p_b = warp_sum_d(lane < NW ? s_tot[96 + lane] : 0.0);
-        const double mb = phase == 1 ? s_max[32] : 0.0;   // the block max (every warp found the same value)
+        const Real q_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[32 + lane] : (Real)0), x_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[64 + lane] : (Real)0),
+                   p_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[96 + lane] : (Real)0);
+        const Real m_r = fast_warp_max<Real>(lane < NW ? (Real)s_max[lane] : Math<Real>::ninf());
         if (G > 1) {
           uint4* dst = rec + (size_t)(par * G + b) * RL::NUS;
           if (F32) {
             if (lane == 0) ll_put_double(dst, s_b, ep1);
-            else if (lane == 1) ll_store_v4(dst + 1, __float_as_uint((float)mb), ep1, __float_as_uint((float)q_b), ep1);
-            else if (lane == 2) ll_store_v4(dst + 2, __float_as_uint((float)x_b), ep1, __float_as_uint((float)p_b), ep1);
-          } else if (lane < 5) ll_put_double(dst + lane, lane == 0 ? mb : (lane == 1 ? s_b : (lane == 2 ? q_b : (lane == 3 ? x_b : p_b))), ep1);
+            else if (lane == 1) ll_store_v4(dst + 1, __float_as_uint((float)m_r), ep1, __float_as_uint((float)q_r), ep1);
+            else if (lane == 2) ll_store_v4(dst + 2, __float_as_uint((float)x_r), ep1, __float_as_uint((float)p_r), ep1);
+          } else if (lane < 5) ll_put_double(dst + lane, lane == 0 ? (double)m_r : (lane == 1 ? s_b : (lane == 2 ? (double)q_r : (lane == 3 ? (double)x_r : (double)p_r))), ep1);
         } else if (lane == 0) {
-          // a group of one: the CTA's record is the group's (rounded like a published one, so that G never changes a result by more than summation order)
-          s_tab[0] = F32 ? (double)(float)mb : mb; s_tab[1] = s_b;
-          s_tab[2] = F32 ? (double)(float)q_b : q_b; s_tab[3] = F32 ? (double)(float)x_b : x_b; s_tab[4] = F32 ? (double)(float)p_b : p_b;
+          // a group of one: the CTA's record is the group's
+          s_pre[0] = s_b;
+          s_grp[0] = (double)m_r; s_grp[8] = s_b; s_grp[16] = (double)q_r; s_grp[24] = (double)x_r; s_grp[32] = (double)p_r;
         }
       }
       FAST_TICK(9);   // block scan, publish
       overlap();      // work that does not depend on the exchange, while the record travels
       FAST_TICK(2);
-      // ---- poll the G records (thread j: record j, all its units in flight at once) ----
+      // ---- poll the G records, 32 per warp and round: lane l holds record 32 g + l (all its units in flight at once); the warp
+      //      leaves the inclusive sums of the weight totals within the group and the group's totals ----
       if (G > 1) {
         const uint4* src = rec + (size_t)par * G * RL::NUS;
-        for (int j = tid; j < G; j += NT) {
+        for (int g = wid; g < npg; g += NW) {
+          const int j = 32 * g + lane;
+          const bool valid = j < G;
+          const uint4* rj = src + (size_t)(valid ? j : G - 1) * RL::NUS;
           uint4 v[RL::NU];
           bool ok;
           do {
             ok = true;
 #pragma unroll
-            for (int i = 0; i < RL::NU; i++) { v[i] = ll_load_v4(src + (size_t)j * RL::NUS + i); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
+            for (int i = 0; i < RL::NU; i++) { v[i] = ll_load_v4(rj + i); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
           } while (!ok);
+          double sj; Real mj, qj, xj, pj;
           if (F32) {
-            s_tab[G + j] = ll_get_double(v[0]);
-            s_tab[j] = (double)__uint_as_float(v[1].x); s_tab[2 * G + j] = (double)__uint_as_float(v[1].z);
-            s_tab[3 * G + j] = (double)__uint_as_float(v[2].x); s_tab[4 * G + j] = (double)__uint_as_float(v[2].z);
+            sj = ll_get_double(v[0]);
+            mj = (Real)__uint_as_float(v[1].x); qj = (Real)__uint_as_float(v[1].z);
+            xj = (Real)__uint_as_float(v[2 % RL::NU].x); pj = (Real)__uint_as_float(v[2 % RL::NU].z);
           } else {
-#pragma unroll
-            for (int i = 0; i < 5; i++) s_tab[i * G + j] = ll_get_double(v[i % RL::NU]);
+            mj = (Real)ll_get_double(v[0]); sj = ll_get_double(v[1]); qj = (Real)ll_get_double(v[2]);
+            xj = (Real)ll_get_double(v[3 % RL::NU]); pj = (Real)ll_get_double(v[4 % RL::NU]);
           }
+          if (!valid) { sj = 0.0; mj = Math<Real>::ninf(); qj = (Real)0; xj = (Real)0; pj = (Real)0; }
+          const double inc = warp_incl_scan_d(sj, lane);
+          const Real gm = fast_warp_max<Real>(mj);
+          // sums in the summation order of the records (a fixed tree): identical in every CTA
+          const double gq = warp_sum_d((double)qj), gx = warp_sum_d((double)xj), gp = warp_sum_d((double)pj);
+          if (valid) s_pre[j] = inc;
+          if (lane == 31) s_grp[8 + g] = inc;
+          if (lane == 0) { s_grp[g] = (double)gm; s_grp[16 + g] = gq; s_grp[24 + g] = gx; s_grp[32 + g] = gp; }
         }
       }
       FAST_TICK(3);   // poll
       __syncthreads();
-      const double m0_ = *(volatile double*)&s_tab[0];
+      const double m0_ = *(volatile double*)&s_grp[0];
       FAST_TICK(10);  // barrier (records)
-      // ---- global max / sums / this CTA's cdf interval.  EVERY warp evaluates the same expressions on the same table (R consecutive
-      //      records per lane, one warp scan), so the results are warp-uniform registers, bit-identical in every warp of every
-      //      CTA: no roles, no broadcast, no barrier.  Only what the decision and the cdf need; the state sums follow below ----
-      double M = m0_;
-      for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
-      M = F32 ? (double)fast_warp_max<float>((float)M) : warp_max_d(M);
-      const int j0 = lane * R;
-      double loc_s = 0.0, loc_q = 0.0, my_lo = 0.0, my_hi = 0.0, my_g = 0.0;
-      for (int r = 0; r < R; r++) {
-        const int j = j0 + r;
-        if (j < G) {
-          const double mj = s_tab[j];
-          double sc = 0.0;
-          if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
-          loc_s += s_tab[G + j] * sc;
-          if (j == b - 1) my_lo = loc_s;            // lane-local inclusive values of records b-1 and b
-          if (j == b) { my_hi = loc_s; my_g = sc; }
-          loc_q += s_tab[2 * G + j] * sc * sc;
+      // ---- global sums / this CTA's cdf interval: every thread adds up the (at most 8) group totals in the same order, so the
+      //      results are bit-identical in every warp of every CTA: no roles, no broadcast, no further barrier ----
+      double M = m0_, S = 0.0, Q = 0.0, A_lo = 0.0, A_hi = 0.0;
+      {
+        const int gl = (b - 1) >> 5, gh = b >> 5;   // groups of records b - 1 and b
+        for (int g = 0; g < npg; g++) {
+          if (b > 0 && g == gl) A_lo = S + s_pre[b - 1];
+          if (g == gh) A_hi = S + s_pre[b];
+          const double mg = s_grp[g];
+          M = mg > M ? mg : M;
+          S += s_grp[8 + g]; Q += s_grp[16 + g];
         }
       }
-      const double inc = warp_incl_scan_d(loc_s, lane);
-      const double Q = warp_sum_d(loc_q);
-      const double off = inc - loc_s;               // everything before this lane's first record
-      const double S = __shfl_sync(0xffffffffu, inc, 31);
-      const double A_hi = __shfl_sync(0xffffffffu, off + my_hi, b / R);
-      const double A_lo = b == 0 ? 0.0 : __shfl_sync(0xffffffffu, off + my_lo, (b - 1) / R);
-      const double g_b = __shfl_sync(0xffffffffu, my_g, b / R);
+      g_M = M;
       int dead = 0, resample = 0;
       bool bad = false, empty = false;
       if (phase == 1) {
         bad = (S != S) || (M != M);
         empty = M < -1e8;
+        // the weights are exp(lw - ref): if even the best one is tiny the sums have lost their precision (or are 0): redo against M
+        if (!bad && !empty && M - (double)ref < (F32 ? -60.0 : -600.0)) return 4;
         dead = (bad || empty) ? 1 : 0;
         // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
         resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
@@ -327,49 +337,38 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
           // slot positions where this warp's particles begin and end.  The end is the next warp's (next CTA's) beginning,
           // formed by the same expression from the same values; a warp that starts at or beyond particle n sits at the end of the slots
           const double nS = (double)n / S;
-          t_sl = g_b * nS;
-          t_start = lstart >= nb ? A_hi * nS : (A_lo + w_start * g_b) * nS;
-          t_end = lnext >= nb ? A_hi * nS : (A_lo + w_end * g_b) * nS;
+          t_sl = nS;
+          t_start = lstart >= nb ? A_hi * nS : (A_lo + w_start) * nS;
+          t_end = lnext >= nb ? A_hi * nS : (A_lo + w_end) * nS;
           if ((long long)base + lstart >= (long long)n) t_start = 2.0 * (double)n;
           if ((long long)base + lnext >= (long long)n) t_end = 2.0 * (double)n;
         }
       }
       FAST_TICK(4);   // merge
-      if (b == 0 && wid == 0) {
-        // running log-likelihood and the outputs of this observation: one warp, off everybody's critical path
-        double loc_x = 0.0, loc_p = 0.0;
-        for (int r = 0; r < R; r++) {
-          const int j = j0 + r;
-          if (j < G) {
-            const double mj = s_tab[j];
-            double sc = 0.0;
-            if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
-            loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
-          }
-        }
-        const double SX = warp_sum_d(loc_x), PEND = warp_sum_d(loc_p);
-        if (lane == 0) {
-          if (phase == 0) {
-            f.ess[(size_t)c * T1] = (double)n;
-            f.state_est[(size_t)c * T1] = SX / (double)n;
-          } else {
-            if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
-            if (phase == 1) {
-              if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
-                f.status[c] = 3;
-              } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
-                loglike = NINF;
-                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
-                f.early_exit[c] = 1;
-              } else {
-                loglike += (M + log(S) - log_n);
-                if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-                f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
-                if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-              }
+      if (b == 0 && tid == 0) {
+        // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
+        double SX = 0.0, PEND = 0.0;
+        for (int g = 0; g < npg; g++) { SX += s_grp[24 + g]; PEND += s_grp[32 + g]; }
+        if (phase == 0) {
+          f.ess[(size_t)c * T1] = (double)n;
+          f.state_est[(size_t)c * T1] = SX / (double)n;
+        } else {
+          if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+          if (phase == 1) {
+            if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+              f.status[c] = 3;
+            } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+              loglike = NINF;
+              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
+              f.early_exit[c] = 1;
             } else {
-              f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
+              loglike += ((double)ref + log(S) - log_n);
+              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+              f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+              if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
             }
+          } else {
+            f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
           }
         }
       }
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
       }
     }
     // t = 0 state estimate: the sum of the initial particles travels in the record's sx
-    exchange(0, -1, (Real)0, 0.0, (Real)0, px, (Real)0, [] {});
+    exchange(0, -1, (Real)0, 0.0, (Real)0, px, (Real)0, (Real)0, [] {});
     px = 0;
 
     // normals of the next transition, generated ahead of time (they do not depend on x)
@@ -430,7 +429,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
           Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
         }
       }
-      Real e[PPT];   // first the log-weights, then exp(lw - block max)
+      Real e[PPT];   // first the log-weights, then exp(lw - ref)
       Real mloc = Math<Real>::ninf();
 #pragma unroll
       for (int k = 0; k < PPT; k++) {
@@ -438,34 +437,31 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
         if (k >= n_own) e[k] = Math<Real>::ninf();
         mloc = e[k] > mloc ? e[k] : mloc;
       }
-      // block max: per-warp partials, then every warp reduces the partials redundantly (one barrier).  A NaN log-weight is not
-      // an ordered maximum: it reaches the sums through exp below
+      // a NaN log-weight is not an ordered maximum: it reaches the sums through exp below
       const Real mw = fast_warp_max<Real>(mloc);
-      if (lane == 0) s_max[wid] = (double)mw;
-      FAST_TICK(11);  // P1 up to the block max
-      __syncthreads();
-      const Real mbr0 = fast_warp_max<Real>(lane < NW ? (Real)*(volatile double*)&s_max[lane] : Math<Real>::ninf());
-      FAST_TICK(8);   // barrier (block max)
-      if (tid == 0) s_max[32] = (double)mbr0;   // for the record (the warps agree bit for bit)
-      double exu;            // warp-local exclusive prefix of this thread (unnormalised, relative to the block max)
+      FAST_TICK(11);  // P1 up to the weights
+      double exu;            // warp-local exclusive prefix of this thread (unnormalised, relative to the reference)
       double inc_e;
-      Real fq = 0, fx = 0;
-      {
+      Real fq, fx;
+      // e = exp(lw - ref); thread sums; warp-local inclusive scan of the thread sums
+      auto weigh = [&](Real ref) {
         Real fs = 0;
-        const Real mr = (mbr0 == Math<Real>::ninf()) ? (Real)0 : mbr0;   // exp(-inf - 0) = 0: no per-particle guard
+        fq = 0; fx = 0;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
-          Real ek = Math<Real>::exp_(e[k] - mr);
+          Real ek = Math<Real>::exp_(e[k] - ref);
           e[k] = ek;
           fs += ek; fq += ek * ek; fx += ek * x[k];
         }
         const double run = (double)fs;
         inc_e = warp_incl_scan_d(run, lane);
         exu = inc_e - run;
-      }
+      };
+      Real ref = Model::template loglik_bound<Real>(par);
+      weigh(ref);
       unsigned int w_sys = 0u;
       unsigned int* const su = s_u + (obs & 1) * P.ucap;
-      const int fl = exchange(1, obs, mw, inc_e, fq, fx, px, [&] {
+      int fl = exchange(1, obs, mw, inc_e, fq, fx, px, ref, [&] {
         if (obs + 1 < f.T) gen_normals(ot);
         if (ralg != 0 && (P.ucap > 0 || P.resample_fn == 1)) {
           if (P.resample_fn == 1) {
@@ -481,6 +477,17 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
           }
         }
       });
+      if (fl == 4) {
+        // an outlying observation: every weight is tiny against the bound.  Once more, against the true maximum
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+          e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
+          if (k >= n_own) e[k] = Math<Real>::ninf();
+        }
+        ref = (Real)g_M;
+        weigh(ref);
+        fl = exchange(1, obs, mw, inc_e, fq, fx, px, ref, [] {});
+      }
       px = 0;
       if (fl & 1) break;
       if (!(fl & 2)) continue;
@@ -677,7 +684,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
       }
     }  // obs
     // flush: the state estimate of a final resampling step still travels in the records
-    exchange(2, -1, (Real)0, 0.0, (Real)0, (Real)0, px, [] {});
+    exchange(2, -1, (Real)0, 0.0, (Real)0, (Real)0, px, (Real)0, [] {});
     __syncthreads();
   }    // filters
 #ifdef BSSM_FAST_TIMING_BUILD

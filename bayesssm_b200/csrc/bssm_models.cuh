@@ -29,6 +29,8 @@ struct ModelArSin {
     par[0] = (R)th[0]; par[1] = (R)th[1]; par[2] = (R)th[2]; par[3] = (R)log(th[2]);
   }
   template <typename R> static BSSM_DEV void init(R* x, const R*, const R* z, const double*) { x[0] = z[0]; }
+  // an upper bound of loglik over all states and observations (the persistent kernel's reference for exp(lw - bound))
+  template <typename R> static BSSM_DEV R loglik_bound(const R* par) { return -((R)0.918938533204672741780329736406 + par[3]); }
   template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R* z, const double*) {
     x[0] = par[0] * x[0] + Math<R>::sin_(x[0]) + par[1] * z[0];
   }
@@ -69,6 +71,7 @@ struct ModelLG {
     par[0] = (R)th[0]; par[1] = (R)th[1]; par[2] = (R)th[2]; par[3] = (R)log(th[2]);
   }
   template <typename R> static BSSM_DEV void init(R* x, const R*, const R* z, const double*) { x[0] = z[0]; }
+  template <typename R> static BSSM_DEV R loglik_bound(const R* par) { return -((R)0.918938533204672741780329736406 + par[3]); }
   template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R* z, const double*) {
     x[0] = par[0] * x[0] + par[1] * z[0];
   }
@@ -94,6 +97,7 @@ struct ModelRwDrift {
     par[0] = (R)th[0]; par[1] = (R)th[1]; par[2] = (R)log(th[1]);
   }
   template <typename R> static BSSM_DEV void init(R* x, const R*, const R* z, const double*) { x[0] = z[0]; }
+  template <typename R> static BSSM_DEV R loglik_bound(const R* par) { return -((R)0.918938533204672741780329736406 + par[2]); }
   template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R* z, const double*) {
     x[0] = x[0] + (par[0] + z[0]);
   }

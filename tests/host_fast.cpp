@@ -8,7 +8,7 @@
 // usage: host_fast model variant G ngroups N T C resample_fn ralg threshold seed run_id stream_base [n_0 ... n_{C-1}]
 //   (optional trailing particle counts: a ragged batch, FilterDev::n_per; N is then the maximum)
 //                  < y (T doubles) theta (C x 3 doubles)
-//   variant: 0, 1 = <double, 8, 28 worker warps>, 2 = <float, 8, 8>, 3 = <float, 16, 16>, 4 = <float, 12, 20>   (EMU_UW: slack of the staged window of uniforms)
+//   variant: 0, 1 = <double, 8, 28 worker warps>, 2 = <float, 8, 8>, 3 = <float, 16, 14>, 4 = <float, 12, 19>   (EMU_UW: slack of the staged window of uniforms)
 #include "simt_emu.h"
 
 #include "../bayesssm_b200/csrc/bssm_fast.cuh"
@@ -81,8 +81,8 @@ template <typename Model> static int by_variant(int argc, char** argv) {
   switch (atoi(argv[2])) {
     case 0: case 1: return run<Model, double, 8, 28>(argc, argv);
     case 2: return run<Model, float, 8, 8>(argc, argv);
-    case 3: return run<Model, float, 16, 16>(argc, argv);
-    case 4: return run<Model, float, 12, 20>(argc, argv);
+    case 3: return run<Model, float, 16, 14>(argc, argv);
+    case 4: return run<Model, float, 12, 19>(argc, argv);
   }
   return 2;
 }

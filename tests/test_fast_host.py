@@ -142,3 +142,24 @@ def test_observation_times_with_gaps(orc, host_fast):
     ref = orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3)
     rec, = host_fast(AR, F64_HEADS, 3, 2048, y, [THETA[AR]], seed=3, run_id=0, stream_base=0, obs_times=ot)
     check(rec, ref)
+
+
+def test_outlying_observations_redo_the_step_against_the_true_maximum(orc, host_fast):
+    # the kernel weighs against the model's upper bound of the log-likelihood; when even the best particle is far below it (here
+    # 40 - 60 standard deviations) the sums underflow and the step is redone against the true maximum the records carry
+    y = np.array([0.1, 30.0, 0.2, -25.0, 0.3, 0.1])
+    ref = orc.particle_filter(AR, 0, 2, 0, 3000, y, THETA[AR], seed=7)
+    rec, = host_fast(AR, F64_HEADS, 3, 3000, y, [THETA[AR]], seed=7, run_id=0, stream_base=0)
+    check(rec, ref)
+    rec, = host_fast(AR, F32_LOOPS, 2, 9000, y, [THETA[AR]], seed=7, run_id=0, stream_base=0)
+    ref = orc.particle_filter(AR, 0, 2, 0, 9000, y, THETA[AR], seed=7)
+    assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
+    np.testing.assert_allclose(rec["loglike_history"], ref["loglike_history"], rtol=2e-4)
+
+
+def test_more_than_32_ctas_in_a_group(orc, host_fast):
+    # the records are scanned in groups of 32 CTAs; 40 CTAs make two groups
+    y = sim_y(AR, 5, np.random.default_rng(40))
+    ref = orc.particle_filter(AR, 0, 2, 0, 2560, y, THETA[AR], seed=4)
+    rec, = host_fast(AR, F64_HEADS, 40, 2560, y, [THETA[AR]], seed=4, run_id=0, stream_base=0)
+    check(rec, ref)
