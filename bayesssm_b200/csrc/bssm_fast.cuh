@@ -1,41 +1,31 @@
 // bssm_fast.cuh -- persistent bootstrap-filter kernel: the whole T loop of
 // .particle_filter_core (R/particle_filter_core.R:123-246) for algorithm "BPF" in ONE launch.
 //
-// A filter is run by a GROUP of G co-resident CTAs (cooperative launch); CTA b owns the contiguous slice
-// [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps (PPT particles per thread).
-// Per observation:
-//   P1  propagate (normals pre-generated while the previous record travelled; one Philox call per 4
-//       particles) + log-weight; e = exp(lw - ref) against a reference every CTA knows WITHOUT
-//       communication -- the model's upper bound of the log-likelihood -- so the weights of all CTAs
-//       are on one scale from the start: block sums of e, e^2, e*x, block max of lw and the block-local
-//       inclusive scan of e                                   [registers + shuffles, 1 block barrier]
-//   B1  every CTA publishes (max_b, sums) as an epoch-stamped LL record in L2, generates the NEXT
-//       step's normals while the record travels, then polls the G records (no atomics, no fences): the
-//       polling warps scan the records of 32 CTAs each, and after one block barrier every warp adds up at
-//       most 8 group totals to get -- bit-identically in every warp of every CTA -- the global sum / ESS /
-//       resampling decision, the cdf interval of its CTA and the slot positions where its own particles
-//       begin and end.  (If the best particle lies more than e^-60 below the bound -- an outlying
-//       observation -- the step is redone against the true maximum, which the records carry.)
-//                                                                [1 L2 all-to-all, 1 block barrier]
+// A filter is run by a GROUP of G co-resident CTAs (cooperative launch); CTA b owns the
+// contiguous slice [b*nb, (b+1)*nb) of the particles and keeps it in REGISTERS for all T steps
+// (PPT particles per thread).  Per observation:
+//   P1  propagate (normals pre-generated while waiting at the previous sync point; one Philox call
+//       per 4 particles) + log-weight; block max; e = exp(lw - max_b); block sums of e, e^2, e*x
+//       and the block-local inclusive scan of e                              [registers + shuffles]
+//   B1  every CTA publishes (max_b, sums) as an epoch-stamped record in L2, generates the NEXT
+//       step's normals while the record travels, then polls the G records (release/acquire, no
+//       atomics); all CTAs derive, redundantly but bit-identically, the global max / sum / ESS /
+//       resampling decision and the cdf interval of every CTA                  [1 L2 round trip]
 //   P3  INPUT-centric resampling: source j knows its cdf value c_j, hence -- in closed form -- the
 //       number F(c_j) of output slots whose position (i + U_i)/N is <= c_j; it owns the output
-//       slots [F(c_{j-1}), F(c_j)).  No search.  Warp boundaries are F of values both neighbouring
-//       warps (CTAs) compute with the same expression from the same shared-memory (L2) words, so
-//       every slot is produced exactly once without any cross-warp prefix or barrier.  Each warp
-//       stages the stratified uniforms of exactly its own output range (one Philox call per 4 slots)
-//   P4  WARP-PRIVATE expansion: every source marks the first of its slots in the warp's own
-//       head array, a running maximum over the slots tells every slot its source, the chosen x are
-//       staged per warp and leave the SM as coalesced 16-byte LL stores into x_new.  No block barrier
-//   B2  every thread polls its own elements of x_new: value and epoch tag travel in one 8-byte word
-//       (LL protocol), so there is no fence, no flag, no barrier; a warp whose particles have
-//       arrived starts the next observation at once                          [1 L2 hop]
-// Only x_new (one write + one read per particle, L2 resident) and the tiny records leave the SM.
+//       slots [F(c_{j-1}), F(c_j)).  No search.  The stratified uniforms of the CTA's output range
+//       are staged once in shared memory (one Philox call per 4 slots).
+//   P4  the chosen x are scattered into a shared-memory staging buffer and copied out to x_new
+//       with coalesced 16-byte stores
+//   B2  every CTA reloads its slice of x_new; each element carries its epoch tag (LL protocol:
+//       value and tag travel in one 8-byte word), so there is no fence, no flag and no second
+//       round trip -- the reader simply polls its own elements               [< 1 L2 round trip]
+// Records use the same self-validating words.  Only x_new (one write + one read per particle, L2
+// resident) and the tiny records leave the SM.
 // Same Philox keying and tie rule (first j with cdf[j] >= pos, clamp) as the general engine, so
 // results do not depend on G or the launch geometry beyond floating-point summation order.
 // In the throughput precision (Real = float) the within-thread part of the cdf and the slot
 // arithmetic run in fp32 relative to an fp64 per-thread origin.
-// What the B200 charges for the exchanges (scripts/probes/exchange_probe.cu): one store -> remote poll hop
-// through L2 about 1060 cycles, the all-to-all of 148 CTAs about 4200 per round.
 #pragma once
 #include "bssm_common.cuh"
 #include "bssm_filter.cuh"
@@ -48,60 +38,29 @@ namespace bssm {
 
 constexpr int FAST_MAX_NB = 7168;    // particles per CTA
 constexpr int FAST_MAX_G = 256;      // CTAs per group
-// output slots per lane of one expansion pass: 25 % beyond the lane's sources, rounded up to whole 16-byte accesses
+constexpr int FAST_SLACK = 1024;     // staging capacity beyond the slice size
+constexpr int FAST_HEAVY = 64;       // offspring count above which a source is expanded cooperatively
+constexpr int FAST_HEAVY_CAP = 64;
+// output slots per thread of one expansion pass: 25 % beyond the slice, rounded up to whole 16-byte accesses
 __host__ __device__ constexpr int fast_spt(int ppt) { return (ppt * 5 / 4 + 3) & ~3; }
-// stride (elements) of a lane's particles in the warp's staging array: + 4 keeps the 16-byte accesses conflict-free
-__host__ __device__ constexpr int fast_xs(int ppt) { return ppt % 8 == 4 ? ppt : ppt + 4; }
 
 // LL ("low latency") words: 32 data bits + 32-bit epoch tag in one 8-byte unit, two units per
 // 16-byte access.  A reader that sees the expected tag also sees the data: no fence, no separate
 // flag, no dependent second load.  The accesses are relaxed at GPU scope (all that an exchange between
-// CTAs of one GPU needs).
-// The group exchange: one record per CTA and observation, polled by every CTA of the group: NU 16-byte units.
-// f32: (sum), (max, sum of squares), (state sum, pending state sum); f64: five doubles
-template <bool F32> struct FastRecLayout {
-  static constexpr int NU = F32 ? 3 : 5;
-  static constexpr int NUS = F32 ? 4 : 8;     // stride in units (64 / 128 bytes)
+// CTAs of one GPU needs): +4 % over `volatile`, which is system scope (profiles/r1_ab_experiments.md).
+struct __align__(128) FastRec {   // published once per observation by each CTA: 5 doubles as (lo, tag, hi, tag)
+  uint4 w[5];                     // m, s, q, sx, pending sum of the previous step's resampled x
+  uint4 pad[3];
 };
-__host__ __device__ inline size_t fast_rec_units(int ngroups, int G, int nus) { return (size_t)ngroups * 2 * G * nus; }
-
-// launch geometry, shared by fast_launch() (bssm_fast.cu) and the CPU logic tests
-struct FastGeom {
-  int nb_max, nw, threads, ch, ucap, uw, xstride;
-  size_t smem;
-};
-template <typename Real, int PPT>
-inline FastGeom fast_geometry(int N, int G, int uw_req /* < 0: default */) {
-  FastGeom g;
-  g.nb_max = (N + G - 1) / G;
-  g.nb_max = (g.nb_max + PPT - 1) / PPT * PPT;
-  g.nw = (g.nb_max + 32 * PPT - 1) / (32 * PPT);
-  if (g.nw < 1) g.nw = 1;
-  g.threads = g.nw * 32;
-  g.ch = 32 * fast_spt(PPT);
-  // uw_req < 0: no CTA-wide window of stratified uniforms staged ahead of the exchange -- every warp stages exactly its own output
-  // range after it; >= 0: a window around the CTA's slice with that slack (misses are repaired per warp)
-  // default for big slices: a window with 1536 slots of slack on either side (measured on the B200 at N = 2^20: 72.6 G particle-
-  // timesteps/s without a window, 80.1 / 81.4 / 82.8 / 71.4 with 512 / 1012 / 1536 / 2048)
-  if (uw_req < 0 && g.nb_max >= 4096 && sizeof(Real) == 4) uw_req = 1536;
-  g.uw = uw_req >= 0 ? (uw_req + 3) & ~3 : 0;
-  g.ucap = uw_req >= 0 ? (g.nb_max + 2 * g.uw + 3) & ~3 : 0;
-  g.xstride = G * g.nb_max + 32 * PPT;   // a partly filled lane reads whole 16-byte pairs beyond its particles
-  if (sizeof(Real) == 8 && g.nw > 14) { g.uw = 0; g.ucap = 0; }
-  g.smem = (size_t)(((G + 1) & ~1) + 40 + 32 + 4 * 32) * sizeof(double) + (size_t)2 * g.ucap * sizeof(unsigned int) +
-           (size_t)g.nw * ((size_t)32 * fast_xs(PPT) * sizeof(Real) + (size_t)g.ch * sizeof(unsigned int) + (size_t)g.ch * sizeof(Real));
-  return g;
-}
 
 struct FastParams {
   FilterDev f;
   int G, ngroups;
   int resample_fn;
-  uint4* rec;       // [ngroups][2][G][NUS] LL units: the CTAs' records
-  void* xnew;       // [ngroups][xstride] LL elements: uint2 (f32) / uint4 (f64)
-  int nb_max;       // largest slice (multiple of PPT)
-  int xstride;
-  int ucap, uw;     // staged window of stratified uniforms: slots [base - uw, base - uw + ucap) of the CTA with first particle `base`
+  FastRec* rec;     // [ngroups][2][G]
+  void* xnew;       // [ngroups][G * nb_max] LL elements: uint2 (f32) / uint4 (f64)
+  int nb_max;       // slice stride (multiple of PPT)
+  int cap;          // staging capacity (outputs) = nb_max + FAST_SLACK
   long long* timing;  // optional [gridDim][16] phase cycle counters (BSSM_FAST_TIMING=1, diagnostics)
 };
 
@@ -136,31 +95,34 @@ __device__ __forceinline__ void ll_put_double(uint4* p, double d, unsigned int t
 __device__ __forceinline__ double ll_get_double(const uint4& v) {
   return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
 }
-
-template <typename Real> __device__ __forceinline__ Real fast_warp_sum(Real v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// publish a 5-double record / poll one until every word carries `tag`
+__device__ __forceinline__ void rec_publish(FastRec* r, double m, double s, double q, double sx, double sp, unsigned int tag) {
+  ll_put_double(&r->w[0], m, tag); ll_put_double(&r->w[1], s, tag); ll_put_double(&r->w[2], q, tag);
+  ll_put_double(&r->w[3], sx, tag); ll_put_double(&r->w[4], sp, tag);
 }
-
-template <typename Real> __device__ __forceinline__ Real fast_warp_max(Real v) {
+__device__ __forceinline__ void rec_poll(const FastRec* r, unsigned int tag, double* out /*5*/) {
+  uint4 v[5];
+  bool ok;
+  do {
+    ok = true;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) { const Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-  return v;
+    for (int i = 0; i < 5; i++) { v[i] = ll_load_v4(&r->w[i]); ok = ok && v[i].y == tag && v[i].w == tag; }
+  } while (!ok);
+#pragma unroll
+  for (int i = 0; i < 5; i++) out[i] = ll_get_double(v[i]);
 }
+#ifndef BSSM_EMU
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#endif
 
-template <typename Model, typename Real, int PPT, int NWMAX>
-__global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
+template <typename Model, typename Real, int PPT, bool HEADS>
+__global__ void __launch_bounds__(FAST_MAX_NB / PPT, 1) k_fast_bpf(FastParams P) {
   static_assert(Model::D == 1 && Model::NZ_TRANS == 1 && Model::NU_TRANS == 0 && Model::NZ_INIT == 1 && Model::NU_INIT == 0,
                 "persistent kernel: 1-D models with one normal per transition");
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr bool F32 = sizeof(Real) == 4;
-  constexpr int SPT = fast_spt(PPT);                 // output slots per lane in one expansion pass
-  constexpr int CH = 32 * SPT;                       // ... per warp
-  constexpr int XS = fast_xs(PPT);                   // stride of a lane's particles in the warp's staging array
-  constexpr int VR = 16 / (int)sizeof(Real);         // Reals per 16-byte access
-  static_assert(SPT % 4 == 0 && XS % 8 == 4 && 32 * XS <= 1024, "16-byte accesses to the head / staging arrays; 10-bit source index");
-  typedef FastRecLayout<F32> RL;
 #ifndef BSSM_EMU
   extern __shared__ __align__(16) unsigned char smem_raw[];
 #else
@@ -169,37 +131,38 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
   const FilterDev& f = P.f;
   const int G = P.G;
   const int group = blockIdx.x / G, b = blockIdx.x % G;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int NW = (int)blockDim.x >> 5;
-  const int NT = (int)blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   // shared memory carve-up
-  double* s_pre = (double*)smem_raw;                 // [G] the group's records: inclusive sums of the CTAs' weight totals within groups of 32 records
-  double* s_grp = s_pre + ((G + 1) & ~1);            // [5][8] per group of 32 records: max, total, sum of squares, state sum, pending state sum
-  double* s_max = s_grp + 40;                        // [32] per-warp maxima of the log-weights
-  double* s_tot = s_max + 32;                        // [4][32] per-warp sums of e, e^2, e*x and of the resampled x
-  unsigned int* s_u = (unsigned int*)(s_tot + 4 * 32);   // [2][ucap] (optional) stratified uniforms staged ahead of the exchange, by observation parity
-  unsigned char* s_warp = (unsigned char*)(s_u + 2 * P.ucap);
-  constexpr size_t WARP_BYTES = (size_t)32 * XS * sizeof(Real) + (size_t)CH * sizeof(unsigned int) + (size_t)CH * sizeof(Real);
-  Real* s_xs = (Real*)(s_warp + (size_t)wid * WARP_BYTES);     // [32][XS] this warp's particles
-  unsigned int* s_hd = (unsigned int*)(s_xs + 32 * XS);         // [CH] expansion: epoch << 10 | index into s_xs, at the first slot of a source
-  Real* s_out = (Real*)(s_hd + CH);                             // [CH] staging of the chosen x (before that: the warp's window of uniforms)
+  double* s_tab = (double*)smem_raw;                 // [5][G]: m, s -> inclusive cdf numerator A, q, sx, pending of every CTA
+  double* s_red = s_tab + ((5 * G + 1) & ~1);        // [5][32] per-warp partials (16-byte aligned)
+  Real* s_out = (Real*)(s_red + 5 * 32);             // [cap] staging of the chosen x
+  unsigned int* s_u = (unsigned int*)(s_out + P.cap);  // [cap] staged stratified uniforms (raw words)
+  unsigned int* s_head = s_u + P.cap;                // [cap] (HEADS only) expansion: (source index << 16 | index of its x in s_x) at the first slot of a source
+  Real* s_x = (Real*)(s_head + P.cap);               // [blockDim.x * PPT] this CTA's particles, [PPT/4][threads] x 16 B (conflict-free)
+  constexpr int SPT = fast_spt(PPT);                 // output slots per thread in the expansion: cap = blockDim.x * SPT
+  static_assert(SPT % 4 == 0, "16-byte accesses to the head / staging arrays");
+  __shared__ int s_wf[32];
+  __shared__ unsigned int s_wh[32];
+  __shared__ int s_heavy_n;
+  __shared__ int s_heavy_lo[FAST_HEAVY_CAP], s_heavy_hi[FAST_HEAVY_CAP];
+  __shared__ Real s_heavy_x[FAST_HEAVY_CAP];
+  __shared__ double s_pending;                       // sum of the x chosen by this CTA in the last resampling
 
-  uint4* const rec = P.rec + (size_t)group * 2 * G * RL::NUS;
+  FastRec* rec = P.rec + (size_t)group * 2 * G;
   typedef typename std::conditional<F32, uint2, uint4>::type XEl;   // LL element of x_new
-  XEl* xnew = (XEl*)P.xnew + (size_t)group * P.xstride;
-  const double INF = __longlong_as_double(0x7FF0000000000000LL), NINF = -INF;
+  XEl* xnew = (XEl*)P.xnew + (size_t)group * G * P.nb_max;
+  unsigned int ep1 = 0, ep2 = 0;   // record / x_new epochs: identical sequences in every CTA of the group
+  const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
+  // optional phase timing (diagnostics): compiled in only with -DBSSM_FAST_TIMING_BUILD, because the counters
+  // would otherwise hold ~26 registers for the whole kernel
 #ifdef BSSM_FAST_TIMING_BUILD
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
-#define FAST_TICK(ph) do { if (P.timing && lane == 0) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
+#define FAST_TICK(ph) do { if (P.timing && tid == 0) { long long t_ = clock64(); tacc[ph] += t_ - tprev; tprev = t_; } } while (0)
 #else
 #define FAST_TICK(ph) do { } while (0)
 #endif
-  unsigned int ep1 = 0, ep2 = 0;   // record / x_new epochs: identical sequences in every CTA of the group
-  unsigned int hep = 0;            // head-array epoch of this warp (never reset: stale heads always compare low)
-  const int R = (G + 31) >> 5;     // records per lane in the merge
-  for (int i = lane; i < CH; i += 32) s_hd[i] = 0u;
-  __syncwarp();
+  const int R = (G + 31) >> 5;   // records per lane in P2
 
   for (int c = group; c < f.C; c += P.ngroups) {
     if (!f.alive[c]) continue;
@@ -207,179 +170,21 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
     int nb = (n + G - 1) / G;
     nb = (nb + PPT - 1) / PPT * PPT;
     const int base = b * nb;                                  // first global particle of this CTA
-    const int ws = 32 * PPT;                                  // particles per warp
-    const int wbase = min(wid * ws, nb);                      // first particle of this warp within the slice
-    const int wcnt = max(0, min(min(ws, nb - wbase), n - (base + wbase)));   // particles of this warp
-    const int ibase = base + wid * ws + lane * PPT;           // first global particle of this thread
-    const int n_own = max(0, min(PPT, wcnt - lane * PPT));    // owned particles of this thread
+    const int n_loc = max(0, min(n - base, nb));              // particles owned by this CTA
+    const int ibase = base + tid * PPT;                       // first global particle of this thread
+    const int n_own = max(0, min(PPT, min(n - ibase, nb - tid * PPT)));  // owned particles of this thread
     Real par[Model::NPAR];
     Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
     const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
     const int T1 = f.T + 1;
     const int ralg = f.ralg;
     double thr = f.threshold;
-    if (thr < 0) thr = (ralg == 0) ? INF : (ralg == 1 ? (double)n : (double)n / 2.0);
+    if (thr < 0) thr = (ralg == 0) ? __longlong_as_double(0x7FF0000000000000LL) : (ralg == 1 ? (double)n : (double)n / 2.0);
     const double log_n = log((double)n);
-    const int u_base = max(0, (base - P.uw) & ~3);            // first slot of the CTA's (optional) staged window of uniforms
-    // first particle of this warp / of the next one within the slice (clamped to the slice)
-    const int lstart = wbase, lnext = min((wid + 1) * ws, nb);
-
-    // what the merge of an exchange leaves in (warp-uniform) registers
-    double t_start = 0.0, t_end = 0.0, t_sl = 0.0;   // slot positions where this warp's particles begin / end; slots per unit of e
-    double w_start = 0.0;                            // block-local sum of e before this warp
-    double loglike = 0.0;                            // meaningful in thread 0 of CTA 0
-    int n_resampled = 0, pending_obs = -1;
-
-    double g_M = 0.0;                                // global max of the log-weights of the last exchange
-    // ---- one exchange.  phase 0: t = 0 state estimate, 1: observation `obs`, 2: final flush.  In: this warp's max of the log-weights
-    //      (phase 1), the warp-inclusive scan of the thread sums of e = exp(lw - ref), the thread's other sums.  Returns dead |
-    //      resample << 1, or 4: the weights underflow against `ref`, redo against g_M; leaves t_start / t_end / t_sl / w_start ----
-    auto exchange = [&](int phase, int obs, Real mw, double inc_e, Real fq, Real fx, Real fp, Real ref, auto&& overlap) -> int {
-      // block totals: per-warp sums -> shared memory -> every warp scans them redundantly (bit-identical in all warps)
-      const Real tq = fast_warp_sum<Real>(fq), tx = fast_warp_sum<Real>(fx), tp = fast_warp_sum<Real>(fp);
-      if (lane == 31) s_tot[wid] = inc_e;
-      if (lane == 0) { s_tot[32 + wid] = (double)tq; s_tot[64 + wid] = (double)tx; s_tot[96 + wid] = (double)tp; s_max[wid] = (double)mw; }
-      FAST_TICK(1);   // P1 (propagate, weights, warp reductions)
-      __syncthreads();
-      const double wt = lane < NW ? *(volatile double*)&s_tot[lane] : 0.0;
-      FAST_TICK(8);   // barrier (block totals)
-      const double winc = warp_incl_scan_d(wt, lane);
-      const double w_end = __shfl_sync(0xffffffffu, winc, wid);                       // block-local sum of e up to and including this warp
-      w_start = wid == 0 ? 0.0 : __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);     // ... before this warp: the previous warp's w_end, bit for bit
-      ep1++;
-      const int par = (int)(ep1 & 1u);
-      const int npg = (G + 31) >> 5;                  // groups of 32 records
-      if (wid == 0) {
-        // the CTA's record, by warp 0
-        const double s_b = __shfl_sync(0xffffffffu, winc, 31);
-        const Real q_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[32 + lane] : (Real)0), x_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[64 + lane] : (Real)0),
-                   p_r = fast_warp_sum<Real>(lane < NW ? (Real)s_tot[96 + lane] : (Real)0);
-        const Real m_r = fast_warp_max<Real>(lane < NW ? (Real)s_max[lane] : Math<Real>::ninf());
-        if (G > 1) {
-          uint4* dst = rec + (size_t)(par * G + b) * RL::NUS;
-          if (F32) {
-            if (lane == 0) ll_put_double(dst, s_b, ep1);
-            else if (lane == 1) ll_store_v4(dst + 1, __float_as_uint((float)m_r), ep1, __float_as_uint((float)q_r), ep1);
-            else if (lane == 2) ll_store_v4(dst + 2, __float_as_uint((float)x_r), ep1, __float_as_uint((float)p_r), ep1);
-          } else if (lane < 5) ll_put_double(dst + lane, lane == 0 ? (double)m_r : (lane == 1 ? s_b : (lane == 2 ? (double)q_r : (lane == 3 ? (double)x_r : (double)p_r))), ep1);
-        } else if (lane == 0) {
-          // a group of one: the CTA's record is the group's
-          s_pre[0] = s_b;
-          s_grp[0] = (double)m_r; s_grp[8] = s_b; s_grp[16] = (double)q_r; s_grp[24] = (double)x_r; s_grp[32] = (double)p_r;
-        }
-      }
-      FAST_TICK(9);   // block scan, publish
-      overlap();      // work that does not depend on the exchange, while the record travels
-      FAST_TICK(2);
-      // ---- poll the G records, 32 per warp and round: lane l holds record 32 g + l (all its units in flight at once); the warp
-      //      leaves the inclusive sums of the weight totals within the group and the group's totals ----
-      if (G > 1) {
-        const uint4* src = rec + (size_t)par * G * RL::NUS;
-        for (int g = wid; g < npg; g += NW) {
-          const int j = 32 * g + lane;
-          const bool valid = j < G;
-          const uint4* rj = src + (size_t)(valid ? j : G - 1) * RL::NUS;
-          uint4 v[RL::NU];
-          bool ok;
-          do {
-            ok = true;
-#pragma unroll
-            for (int i = 0; i < RL::NU; i++) { v[i] = ll_load_v4(rj + i); ok = ok && v[i].y == ep1 && v[i].w == ep1; }
-          } while (!ok);
-          double sj; Real mj, qj, xj, pj;
-          if (F32) {
-            sj = ll_get_double(v[0]);
-            mj = (Real)__uint_as_float(v[1].x); qj = (Real)__uint_as_float(v[1].z);
-            xj = (Real)__uint_as_float(v[2 % RL::NU].x); pj = (Real)__uint_as_float(v[2 % RL::NU].z);
-          } else {
-            mj = (Real)ll_get_double(v[0]); sj = ll_get_double(v[1]); qj = (Real)ll_get_double(v[2]);
-            xj = (Real)ll_get_double(v[3 % RL::NU]); pj = (Real)ll_get_double(v[4 % RL::NU]);
-          }
-          if (!valid) { sj = 0.0; mj = Math<Real>::ninf(); qj = (Real)0; xj = (Real)0; pj = (Real)0; }
-          const double inc = warp_incl_scan_d(sj, lane);
-          const Real gm = fast_warp_max<Real>(mj);
-          // sums in the summation order of the records (a fixed tree): identical in every CTA
-          const double gq = warp_sum_d((double)qj), gx = warp_sum_d((double)xj), gp = warp_sum_d((double)pj);
-          if (valid) s_pre[j] = inc;
-          if (lane == 31) s_grp[8 + g] = inc;
-          if (lane == 0) { s_grp[g] = (double)gm; s_grp[16 + g] = gq; s_grp[24 + g] = gx; s_grp[32 + g] = gp; }
-        }
-      }
-      FAST_TICK(3);   // poll
-      __syncthreads();
-      const double m0_ = *(volatile double*)&s_grp[0];
-      FAST_TICK(10);  // barrier (records)
-      // ---- global sums / this CTA's cdf interval: every thread adds up the (at most 8) group totals in the same order, so the
-      //      results are bit-identical in every warp of every CTA: no roles, no broadcast, no further barrier ----
-      double M = m0_, S = 0.0, Q = 0.0, A_lo = 0.0, A_hi = 0.0;
-      {
-        const int gl = (b - 1) >> 5, gh = b >> 5;   // groups of records b - 1 and b
-        for (int g = 0; g < npg; g++) {
-          if (b > 0 && g == gl) A_lo = S + s_pre[b - 1];
-          if (g == gh) A_hi = S + s_pre[b];
-          const double mg = s_grp[g];
-          M = mg > M ? mg : M;
-          S += s_grp[8 + g]; Q += s_grp[16 + g];
-        }
-      }
-      g_M = M;
-      int dead = 0, resample = 0;
-      bool bad = false, empty = false;
-      if (phase == 1) {
-        bad = (S != S) || (M != M);
-        empty = M < -1e8;
-        // the weights are exp(lw - ref): if even the best one is tiny the sums have lost their precision (or are 0): redo against M
-        if (!bad && !empty && M - (double)ref < (F32 ? -60.0 : -600.0)) return 4;
-        dead = (bad || empty) ? 1 : 0;
-        // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
-        resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
-        if (resample) {
-          // slot positions where this warp's particles begin and end.  The end is the next warp's (next CTA's) beginning,
-          // formed by the same expression from the same values; a warp that starts at or beyond particle n sits at the end of the slots
-          const double nS = (double)n / S;
-          t_sl = nS;
-          t_start = lstart >= nb ? A_hi * nS : (A_lo + w_start) * nS;
-          t_end = lnext >= nb ? A_hi * nS : (A_lo + w_end) * nS;
-          if ((long long)base + lstart >= (long long)n) t_start = 2.0 * (double)n;
-          if ((long long)base + lnext >= (long long)n) t_end = 2.0 * (double)n;
-        }
-      }
-      FAST_TICK(4);   // merge
-      if (b == 0 && tid == 0) {
-        // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
-        double SX = 0.0, PEND = 0.0;
-        for (int g = 0; g < npg; g++) { SX += s_grp[24 + g]; PEND += s_grp[32 + g]; }
-        if (phase == 0) {
-          f.ess[(size_t)c * T1] = (double)n;
-          f.state_est[(size_t)c * T1] = SX / (double)n;
-        } else {
-          if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
-          if (phase == 1) {
-            if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
-              f.status[c] = 3;
-            } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
-              loglike = NINF;
-              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
-              f.early_exit[c] = 1;
-            } else {
-              loglike += ((double)ref + log(S) - log_n);
-              if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
-              f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
-              if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
-            }
-          } else {
-            f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
-          }
-        }
-      }
-      pending_obs = resample ? obs : -1;
-      n_resampled += resample;
-      return dead | (resample << 1);
-    };
 
     // ---- init (R/particle_filter_core.R:76-116) ----
     Real x[PPT];
-    Real px = 0;   // sum of this thread's particles after the last resampling (state estimate, travels in the next record)
+    double sum0 = 0.0;
 #pragma unroll
     for (int h = 0; h < PPT / 4; h++) {
       uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)(ibase + 4 * h) >> 2);
@@ -391,12 +196,50 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
         Real xi[1]; Real zi[1] = {zz[k]};
         Model::template init<Real>(xi, par, zi, nullptr);
         x[4 * h + k] = (4 * h + k < n_own) ? xi[0] : (Real)0;   // padding lanes stay finite
-        px += x[4 * h + k];
+        sum0 += (double)x[4 * h + k];
       }
     }
-    // t = 0 state estimate: the sum of the initial particles travels in the record's sx
-    exchange(0, -1, (Real)0, 0.0, (Real)0, px, (Real)0, (Real)0, [] {});
-    px = 0;
+    int n_resampled = 0;
+    double loglike = 0.0;   // meaningful in thread 0 of CTA 0
+    if (tid == 0) { s_heavy_n = 0; s_pending = 0.0; }
+    if constexpr (HEADS) {
+#pragma unroll
+      for (int i = 0; i < SPT; i++) s_head[tid * SPT + i] = 0u;   // every thread keeps its own slots of the head array clear
+    }
+    int pending_obs = -1;   // observation whose resampled state estimate is still to be written
+    // t = 0 state estimate: block sum -> record; CTA 0 gathers
+    {
+      double v = warp_sum_d(sum0);
+      if (lane == 0) s_red[wid] = v;
+      __syncthreads();
+      if (wid == 0) {
+        double t = lane < nw ? s_red[lane] : 0.0;
+        t = warp_sum_d(t);
+        if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, t, 0.0, ep1 + 1);
+      }
+      ep1++;
+      // every CTA polls every record (not only CTA 0): a record buffer may only be reused once all CTAs
+      // have passed the poll of the epoch before, which is what orders the two-deep record buffers
+      {
+        double v0 = 0.0;
+        for (int j = tid; j < G; j += blockDim.x) {
+          double rv[5];
+          rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+          v0 += rv[3];
+        }
+        v0 = warp_sum_d(v0);
+        __syncthreads();
+        if (lane == 0) s_red[wid] = v0;
+        __syncthreads();
+        if (b == 0 && tid == 0) {
+          double t = 0.0;
+          for (int w = 0; w < nw; w++) t += s_red[w];
+          f.ess[(size_t)c * T1] = (double)n;
+          f.state_est[(size_t)c * T1] = t / (double)n;
+        }
+      }
+      __syncthreads();
+    }
 
     // normals of the next transition, generated ahead of time (they do not depend on x)
     Real zpre[PPT];
@@ -419,7 +262,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
       double yv[4] = {ynext[0], ynext[1], ynext[2], ynext[3]};
       if (obs + 1 < f.T) for (int k = 0; k < f.dy && k < 4; k++) ynext[k] = f.y[(size_t)(obs + 1) * f.dy + k];   // prefetch
 
-      FAST_TICK(0);   // reload of x_new (resample steps)
+      FAST_TICK(0);
       // ---- P1: propagate + log-weight ----
       for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
         if (zpre_t != tnow - 1) gen_normals(tnow - 1);
@@ -429,7 +272,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
           Model::template transition<Real>(&x[k], par, tnow, zi, nullptr);
         }
       }
-      Real e[PPT];   // first the log-weights, then exp(lw - ref)
+      Real e[PPT];   // first the log-weights, then exp(lw - block max)
       Real mloc = Math<Real>::ninf();
 #pragma unroll
       for (int k = 0; k < PPT; k++) {
@@ -437,99 +280,159 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
         if (k >= n_own) e[k] = Math<Real>::ninf();
         mloc = e[k] > mloc ? e[k] : mloc;
       }
-      // a NaN log-weight is not an ordered maximum: it reaches the sums through exp below
-      const Real mw = fast_warp_max<Real>(mloc);
-      FAST_TICK(11);  // P1 up to the weights
-      double exu;            // warp-local exclusive prefix of this thread (unnormalised, relative to the reference)
-      double inc_e;
-      Real fq, fx;
-      // e = exp(lw - ref); thread sums; warp-local inclusive scan of the thread sums
-      auto weigh = [&](Real ref) {
-        Real fs = 0;
-        fq = 0; fx = 0;
+      // block max: per-warp partials, then every warp reduces the partials redundantly (one barrier)
+      {
+        Real v = mloc;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { Real t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+        if (lane == 0) s_red[wid] = (double)v;
+      }
+      __syncthreads();
+      const double mb = warp_max_d(lane < nw ? s_red[lane] : NINF);
+      // e = exp(lw - mb); thread sums; block-local inclusive scan of e
+      double exu;            // block-local exclusive prefix of this thread (unnormalised)
+      {
+        Real fs = 0, fq = 0, fx = 0;
+        const Real mbr = (mb == NINF) ? (Real)0 : (Real)mb;   // exp(-inf - 0) = 0: no per-particle guard
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
-          Real ek = Math<Real>::exp_(e[k] - ref);
+          Real ek = Math<Real>::exp_(e[k] - mbr);
           e[k] = ek;
           fs += ek; fq += ek * ek; fx += ek * x[k];
         }
         const double run = (double)fs;
-        inc_e = warp_incl_scan_d(run, lane);
-        exu = inc_e - run;
-      };
-      Real ref = Model::template loglik_bound<Real>(par);
-      weigh(ref);
-      unsigned int w_sys = 0u;
-      unsigned int* const su = s_u + (obs & 1) * P.ucap;
-      int fl = exchange(1, obs, mw, inc_e, fq, fx, px, ref, [&] {
-        if (obs + 1 < f.T) gen_normals(ot);
-        if (ralg != 0 && (P.ucap > 0 || P.resample_fn == 1)) {
-          if (P.resample_fn == 1) {
-            uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
-            w_sys = q0.w[0];
-          } else {
-            // stage the Philox words of the slots this CTA will probably serve: one call per 4 slots
-            const int q_end = min((n + 3) >> 2, (u_base + P.ucap) >> 2);
-            for (int qd = (u_base >> 2) + tid; qd < q_end; qd += NT) {
-              uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-              *(uint4*)&su[4 * qd - u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
-            }
+        double inc = warp_incl_scan_d(run, lane);
+        double tq = warp_sum_d((double)fq), tx = warp_sum_d((double)fx);
+        __syncthreads();   // s_red partials of the max have been consumed by every warp
+        if (lane == 31) s_red[wid] = inc;            // warp totals of e
+        if (lane == 0) { s_red[32 + wid] = tq; s_red[64 + wid] = tx; }
+        double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        exu = lane == 0 ? 0.0 : prev;                // exclusive within the warp
+        __syncthreads();
+        // every warp scans the warp totals redundantly
+        double wt = lane < nw ? s_red[lane] : 0.0;
+        double winc = warp_incl_scan_d(wt, lane);
+        exu += __shfl_sync(0xffffffffu, winc - wt, wid);   // + exclusive prefix of this warp
+        if (wid == 0) {
+          double a0 = __shfl_sync(0xffffffffu, winc, 31);
+          double a1 = warp_sum_d(lane < nw ? s_red[32 + lane] : 0.0), a2 = warp_sum_d(lane < nw ? s_red[64 + lane] : 0.0);
+          if (lane == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], mb, a0, a1, a2, s_pending, ep1 + 1);
+        }
+      }
+      ep1++;
+      FAST_TICK(1);   // P1 (propagate, weights, block reductions, publish)
+      // overlap the L2 round trip with the next observation's normals
+      if (obs + 1 < f.T) gen_normals(ot);
+      FAST_TICK(2);   // next-step normals
+      // ---- B1: poll the G records ----
+      for (int j = tid; j < G; j += blockDim.x) {
+        double rv[5];
+        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+        s_tab[j] = rv[0]; s_tab[G + j] = rv[1]; s_tab[2 * G + j] = rv[2]; s_tab[3 * G + j] = rv[3]; s_tab[4 * G + j] = rv[4];
+      }
+      __syncthreads();
+      FAST_TICK(3);   // B1 poll + barrier
+      // ---- P2: global max / sums / this CTA's cdf interval.  EVERY warp evaluates the same expressions on the
+      //      same table (R consecutive records per lane, one warp scan), so the results are warp-uniform
+      //      registers, bit-identical in every warp of every CTA: no roles, no broadcast, no barrier ----
+      int dead = 0, resample = 0;
+      double lo_cdf = 0.0, hi_cdf = 0.0, wscale = 0.0;
+      {
+        double M = NINF;
+        for (int j = lane; j < G; j += 32) M = s_tab[j] > M ? s_tab[j] : M;
+        M = warp_max_d(M);
+        const int j0 = lane * R;
+        double loc_s = 0.0, loc_q = 0.0, loc_x = 0.0, loc_p = 0.0, my_lo = 0.0, my_hi = 0.0;
+        for (int r = 0; r < R; r++) {
+          const int j = j0 + r;
+          if (j < G) {
+            const double mj = s_tab[j];
+            double sc = 0.0;
+            if (!(mj == NINF || M == NINF)) sc = F32 ? (double)__expf((float)(mj - M)) : exp(mj - M);
+            loc_s += s_tab[G + j] * sc;
+            if (j == b - 1) my_lo = loc_s;            // thread-local inclusive values of records b-1 and b
+            if (j == b) my_hi = loc_s;
+            loc_q += s_tab[2 * G + j] * sc * sc; loc_x += s_tab[3 * G + j] * sc; loc_p += s_tab[4 * G + j];
           }
         }
-      });
-      if (fl == 4) {
-        // an outlying observation: every weight is tiny against the bound.  Once more, against the true maximum
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-          e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
-          if (k >= n_own) e[k] = Math<Real>::ninf();
+        const double inc = warp_incl_scan_d(loc_s, lane);
+        const double off = inc - loc_s;               // everything before this lane's first record
+        const double S = __shfl_sync(0xffffffffu, inc, 31);
+        const double Q = warp_sum_d(loc_q), SX = warp_sum_d(loc_x), PEND = warp_sum_d(loc_p);
+        const double A_hi = __shfl_sync(0xffffffffu, off + my_hi, b / R);
+        const double A_lo = b == 0 ? 0.0 : __shfl_sync(0xffffffffu, off + my_lo, (b - 1) / R);
+        const bool bad = (S != S) || (SX != SX) || (M != M);
+        const bool empty = M < -1e8;
+        dead = (bad || empty) ? 1 : 0;
+        // ess < thr  <=>  S^2 < thr * Q  (no division on the critical path)
+        resample = dead ? 0 : ((ralg == 0) ? 0 : (ralg == 1 ? 1 : (S * S < thr * Q)));
+        if (resample) {
+          const double invS = 1.0 / S;
+          lo_cdf = A_lo * invS;
+          hi_cdf = (b == G - 1) ? 2.0 : A_hi * invS;
+          double w = 0.0;
+          if (mb != NINF) w = F32 ? (double)__expf((float)(mb - M)) : exp(mb - M);
+          wscale = w * invS;
         }
-        ref = (Real)g_M;
-        weigh(ref);
-        fl = exchange(1, obs, mw, inc_e, fq, fx, px, ref, [] {});
+        if (b == 0 && tid == 0) {
+          // running log-likelihood and the outputs of this observation: one thread, off everybody's critical path
+          if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = PEND / (double)n;
+          if (bad) {                       // NaN weight somewhere: R's `if (NA)` error
+            f.status[c] = 3;
+          } else if (empty) {              // all(lw < -1e8): R/particle_filter_core.R:189-202
+            loglike = NINF;
+            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = NINF;
+            f.early_exit[c] = 1;
+          } else {
+            loglike += (M + log(S) - log_n);
+            if (f.loglike_history) f.loglike_history[(size_t)c * f.T + obs] = loglike;
+            f.ess[(size_t)c * T1 + obs + 1] = resample ? (double)n : (S * S) / Q;
+            if (!resample) f.state_est[(size_t)c * T1 + obs + 1] = SX / S;
+          }
+        }
       }
-      px = 0;
-      if (fl & 1) break;
-      if (!(fl & 2)) continue;
+      FAST_TICK(4);   // P2
+      pending_obs = -1;
+      if (dead) break;
+      if (!resample) continue;
+      n_resampled++;
+      pending_obs = obs;
 
       // ---- P3: closed-form offspring ranges ----
       SlotCounter sc;
-      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = w_sys;
-      sc.s_u = su; sc.u_base = u_base; sc.u_cap = P.ucap;
-      // output range of this warp: F at the warp's first particle and at the next warp's (both neighbours evaluate the same values)
-      int o_start, o_end;
+      sc.key = key; sc.obs = (unsigned int)obs; sc.fn = P.resample_fn; sc.n = n; sc.w_sys = 0u;
+      sc.s_u = s_u; sc.u_cap = P.cap;
       {
-        const int o = sc.count_slots((lane & 1) ? t_end : t_start);
-        o_start = __shfl_sync(0xffffffffu, o, 0);
-        o_end = __shfl_sync(0xffffffffu, o, 1);
-        if (o_end < o_start) o_end = o_start;   // cannot happen with monotone sums; keeps the ranges sane if it ever did
+        double t0 = lo_cdf * (double)n;
+        int i0 = t0 >= (double)n ? n : (int)t0;
+        sc.u_base = max(0, (i0 & ~3) - 4);
       }
-      if (P.resample_fn != 1 && (o_start - 1 < u_base || o_end + 1 > u_base + P.ucap) && o_end > o_start) {
-        // stage the Philox words of exactly this warp's output range (lookups at floor(t) reach one slot below): one call per
-        // 4 slots; what does not fit the window (more than CH offspring in the warp) is recomputed per lookup
-        const int wb = max(0, (o_start - 1) & ~3);
-        unsigned int* const wu = (unsigned int*)s_out;
-        const int q_end = min(min((n + 3) >> 2, (o_end + 4) >> 2), (wb + CH) >> 2);
-        for (int qd = (wb >> 2) + lane; qd < q_end; qd += 32) {
+      if (P.resample_fn == 1) {
+        uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
+        sc.w_sys = q0.w[0];
+      } else {
+        // stage the Philox words of the slots this CTA is expected to serve: one call per 4 slots
+        const int q_end = min((n + 3) >> 2, (sc.u_base + P.cap) >> 2);
+        for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += blockDim.x) {
           uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-          *(uint4*)&wu[4 * qd - wb] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+          *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
         }
-        __syncwarp();
-        sc.s_u = wu; sc.u_base = wb; sc.u_cap = min(CH, 4 * q_end - wb);
+        __syncthreads();
       }
-      FAST_TICK(5);   // uniforms of the warp's output range
-      // F of this thread's sources (monotone by a running max; clamped into [o_start, o_end])
+      FAST_TICK(5);   // stage uniforms
+      const int o_lo = sc.count_le(lo_cdf);
+      const int o_hi = (b == G - 1) ? n : sc.count_le(hi_cdf);
+      // F of this thread's sources (monotone by a running max; clamped into [o_lo, o_hi])
       int F[PPT];
       {
-        const double sl = t_sl;
-        const double T0 = t_start + exu * sl;      // slot position just before this thread's first particle
-        int fmax = o_start;
+        int fmax = o_lo;
         if (F32) {
-          // fp64 origin per thread, fp32 increments: t_k = T0 + (sum of e up to k) * sl
+          // fp64 origin per thread, fp32 increments: t_k = T0 + (sum of e up to k) * wscale * n
+          const double T0 = (lo_cdf + exu * wscale) * (double)n;
           const double T0c = T0 < (double)n ? T0 : (double)n;
           const int I0 = (int)T0c;
           const float f0 = (float)(T0c - (double)I0);
-          const float wsn = (float)sl;
+          const float wsn = (float)(wscale * (double)n);
           float accf = 0.f;
 #pragma unroll
           for (int k = 0; k < PPT; k++) {
@@ -545,111 +448,194 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
             int v;
             if (i >= n) v = n;
             else v = i + ((sc.word_of(i) < fbits || g >= 2.0f) ? 1 : 0);   // (i + U_i) <= t  <=>  U_i <= frac
-            if (lane * PPT + k == wcnt - 1) v = o_end;   // the warp's last particle takes what is left
-            v = min(max(v, o_start), o_end);
-            if (k >= n_own) v = o_start;
+            if (tid * PPT + k == n_loc - 1) v = o_hi;     // clamp: the last particle takes what is left
+            v = min(max(v, o_lo), o_hi);
+            if (k >= n_own) v = o_lo;
             fmax = max(fmax, v);
             F[k] = fmax;
           }
         } else {
-          double acc = 0.0;
+          double acc = exu;
 #pragma unroll
           for (int k = 0; k < PPT; k++) {
             acc += (double)e[k];
-            int v = o_start;
+            int v = o_lo;
             if (k < n_own) {
-              v = sc.count_slots(T0 + acc * sl);
-              if (lane * PPT + k == wcnt - 1) v = o_end;
-              v = min(max(v, o_start), o_end);
+              v = sc.count_le(lo_cdf + acc * wscale);
+              if (tid * PPT + k == n_loc - 1) v = o_hi;
+              v = min(max(v, o_lo), o_hi);
             }
             fmax = max(fmax, v);
             F[k] = fmax;
           }
         }
       }
-      // exclusive prefix-max of the per-lane last F over the warp
+      // exclusive prefix-max of the per-thread last F over the block
       int prevF;
       {
         int inc = F[PPT - 1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+        if (lane == 31) s_wf[wid] = inc;
         prevF = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) prevF = o_start;
+        if (lane == 0) prevF = o_lo;
+        __syncthreads();
+        int wv = lane < nw ? s_wf[lane] : o_lo;
+        int winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc = max(winc, t); }
+        int wprev = __shfl_sync(0xffffffffu, winc, (wid + 31) & 31);
+        if (wid == 0) wprev = o_lo;
+        prevF = max(prevF, wprev);
 #pragma unroll
         for (int k = 0; k < PPT; k++) F[k] = max(F[k], prevF);
       }
-      FAST_TICK(6);   // offspring ranges
-      // ---- P4: warp-private expansion, output-centric (passes of CH slots).  Every source with offspring in the pass marks
-      //      the first of its slots with (epoch, index of its x in s_xs); a running maximum over the slots -- source indices grow
-      //      with the slot, older epochs compare low -- tells every slot its source: O(1) per source and per slot, no loop over the
-      //      offspring of a source, no special case for heavy sources, nothing to clear ----
+      FAST_TICK(6);   // offspring ranges + prefix max
+      // ---- P4: expansion, output-centric (chunks of `cap` slots).  Every source with offspring in the chunk marks the
+      //      first of its slots with (source index, index of its x in s_x); a running maximum over the slots -- source
+      //      indices grow with the slot -- tells every slot its source: O(1) per source and per slot, no loop over
+      //      the offspring of a source, no special case for heavy sources.  The chosen x are staged and leave the
+      //      SM as coalesced 16-byte stores ----
+      //      HEADS = false (big slices, 16 particles per thread): per-source scatter loops into the staging buffer --
+      //      measured 2 % faster there (the expansion pays two more barriers), 20 % slower on small slices ----
       {
-        hep++;
-        const unsigned int hkey = hep << 10;
+        Real sumx = 0;
+        if constexpr (HEADS) {
+        const int o_base = o_lo & ~3;
+        const int nthr = blockDim.x;
+        // this CTA's particles into shared memory (the registers are reloaded from x_new below)
 #pragma unroll
-        for (int h4 = 0; h4 < PPT / VR; h4++) {
-          if (F32) *(float4*)&s_xs[lane * XS + 4 * h4] = make_float4((float)x[4 * h4], (float)x[4 * h4 + 1], (float)x[4 * h4 + 2], (float)x[4 * h4 + 3]);
-          else *(double2*)&s_xs[lane * XS + 2 * h4] = make_double2((double)x[2 * h4], (double)x[2 * h4 + 1]);
+        for (int h4 = 0; h4 < PPT / 4; h4++) {
+          if (F32) *(float4*)&s_x[(h4 * nthr + tid) * 4] = make_float4((float)x[4 * h4], (float)x[4 * h4 + 1], (float)x[4 * h4 + 2], (float)x[4 * h4 + 3]);
+          else { s_x[(h4 * nthr + tid) * 4] = x[4 * h4]; s_x[(h4 * nthr + tid) * 4 + 1] = x[4 * h4 + 1]; s_x[(h4 * nthr + tid) * 4 + 2] = x[4 * h4 + 2]; s_x[(h4 * nthr + tid) * 4 + 3] = x[4 * h4 + 3]; }
         }
-        const unsigned int tag = ep2 + 1;
-        unsigned int pass_carry = 0u;
-        for (int c0 = o_start & ~3; c0 < o_end; c0 += CH) {
-          const int c1 = min(o_end, c0 + CH);
+        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
+          const int c1 = min(o_hi, c0 + P.cap);
           int lo_k = prevF;
 #pragma unroll
           for (int k = 0; k < PPT; k++) {
             const int hi_k = F[k];
             const int a = max(lo_k, c0);
-            if (min(hi_k, c1) > a) s_hd[a - c0] = hkey | (unsigned int)(lane * XS + k);
-            lo_k = hi_k;
+            if (min(hi_k, c1) > a) s_head[a - c0] = ((unsigned int)(tid * PPT + k) << 16) | (unsigned int)(((k >> 2) * nthr + tid) * 4 + (k & 3));
+            if (c0 == o_base && hi_k > lo_k) {
+              // count as a float without a conversion instruction (exact below 2^23)
+              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
+              sumx += (Real)cf * x[k];
+            }
+            lo_k = max(lo_k, hi_k);
           }
-          __syncwarp();
+          __syncthreads();
           unsigned int hd[SPT];
 #pragma unroll
-          for (int i = 0; i < SPT; i += 4) { const uint4 v4 = *(const uint4*)&s_hd[lane * SPT + i]; hd[i] = v4.x; hd[i + 1] = v4.y; hd[i + 2] = v4.z; hd[i + 3] = v4.w; }
+          for (int i = 0; i < SPT; i += 4) { const uint4 v4 = *(const uint4*)&s_head[tid * SPT + i]; hd[i] = v4.x; hd[i + 1] = v4.y; hd[i + 2] = v4.z; hd[i + 3] = v4.w; }
+#pragma unroll
+          for (int i = 0; i < SPT; i += 4) *(uint4*)&s_head[tid * SPT + i] = make_uint4(0u, 0u, 0u, 0u);   // clear for the next chunk / step
 #pragma unroll
           for (int i = 1; i < SPT; i++) hd[i] = max(hd[i], hd[i - 1]);
           unsigned int inc = hd[SPT - 1];
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+          if (lane == 31) s_wh[wid] = inc;
           unsigned int carry = __shfl_up_sync(0xffffffffu, inc, 1);
           if (lane == 0) carry = 0u;
-          carry = max(carry, pass_carry);
-          pass_carry = max(pass_carry, __shfl_sync(0xffffffffu, inc, 31));
+          __syncthreads();
+          {
+            unsigned int wv = lane < nw ? s_wh[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, wv, o); if (lane >= o) wv = max(wv, t); }
+            const unsigned int wprev = __shfl_sync(0xffffffffu, wv, (wid + 31) & 31);
+            if (wid > 0) carry = max(carry, wprev);
+          }
           Real val[SPT];
 #pragma unroll
-          for (int i = 0; i < SPT; i++) val[i] = s_xs[max(hd[i], carry) & 1023u];
+          for (int i = 0; i < SPT; i++) val[i] = s_x[max(hd[i], carry) & 0xFFFFu];
 #pragma unroll
-          for (int i = 0; i < SPT; i += VR) {
-            if (F32) *(float4*)&s_out[lane * SPT + i] = make_float4((float)val[i], (float)val[i + 1], (float)val[i + 2], (float)val[i + 3]);
-            else *(double2*)&s_out[lane * SPT + i] = make_double2((double)val[i], (double)val[i + 1]);
+          for (int i = 0; i < SPT; i += 4) {
+            if (F32) *(float4*)&s_out[tid * SPT + i] = make_float4((float)val[i], (float)val[i + 1], (float)val[i + 2], (float)val[i + 3]);
+            else { s_out[tid * SPT + i] = val[i]; s_out[tid * SPT + i + 1] = val[i + 1]; s_out[tid * SPT + i + 2] = val[i + 2]; s_out[tid * SPT + i + 3] = val[i + 3]; }
           }
-          __syncwarp();
+          __syncthreads();
           // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
-          const int first = max(c0, o_start), last = c1;   // slots [first, last) are valid in this pass
+          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
+          const unsigned int tag = ep2 + 1;
           if (F32) {
-#pragma unroll
-            for (int it = 0; it < SPT / 2; it++) {
-              const int o = c0 + 2 * (it * 32 + lane);
-              const float2 v = *(const float2*)&s_out[o - c0];
-              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v.x), tag, __float_as_uint(v.y), tag);
+            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
+              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
+              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
               else {
-                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v.x), tag);
-                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v.y), tag);
+                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
+                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
               }
             }
           } else {
-#pragma unroll
-            for (int it = 0; it < SPT; it++) {
-              const int o = c0 + it * 32 + lane;
-              if (o >= first && o < last) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
-            }
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
           }
-          __syncwarp();
+          __syncthreads();
+        }
+        } else {
+        const int o_base = o_lo & ~3;
+        for (int c0 = o_base; c0 < o_hi; c0 += P.cap) {
+          const int c1 = min(o_hi, c0 + P.cap);
+          int lo_k = prevF;
+#pragma unroll
+          for (int k = 0; k < PPT; k++) {
+            const int hi_k = F[k];
+            const int a = max(lo_k, c0);
+            int cnt = min(hi_k, c1) - a;
+            if (c0 == o_base && hi_k > lo_k) {
+              // count as a float without a conversion instruction (exact below 2^23)
+              const float cf = __int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f;
+              sumx += (Real)cf * x[k];
+            }
+            if (cnt > FAST_HEAVY) {
+              int slot = atomicAdd(&s_heavy_n, 1);
+              if (slot < FAST_HEAVY_CAP) { s_heavy_lo[slot] = a; s_heavy_hi[slot] = a + cnt; s_heavy_x[slot] = x[k]; cnt = 0; }
+            }
+            // warp-uniform trip count: no divergent loop bookkeeping
+            const int mx = __reduce_max_sync(0xffffffffu, cnt);
+            Real* dst = s_out + (a - c0);
+            for (int r = 0; r < mx; r++) if (r < cnt) dst[r] = x[k];
+            lo_k = max(lo_k, hi_k);
+          }
+          __syncthreads();
+          const int nh = min(s_heavy_n, FAST_HEAVY_CAP);
+          for (int h = 0; h < nh; h++) {
+            const int a = s_heavy_lo[h], z = s_heavy_hi[h];
+            const Real xv = s_heavy_x[h];
+            for (int o = a + tid; o < z; o += blockDim.x) s_out[o - c0] = xv;
+          }
+          if (nh) __syncthreads();
+          // copy out as LL elements (value + epoch tag): 16-byte stores, 8-byte at the ragged ends
+          const int first = max(c0, o_lo), last = c1;   // slots [first, last) are valid in this chunk
+          const unsigned int tag = ep2 + 1;
+          if (F32) {
+            for (int o = c0 + 2 * tid; o < last; o += 2 * blockDim.x) {
+              const float v0 = (float)s_out[o - c0], v1 = (float)s_out[o + 1 - c0];
+              if (o >= first && o + 1 < last) ll_store_v4(&xnew[o], __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+              else {
+                if (o >= first && o < last) ll_store_v2(&xnew[o], __float_as_uint(v0), tag);
+                if (o + 1 >= first && o + 1 < last) ll_store_v2(&xnew[o + 1], __float_as_uint(v1), tag);
+              }
+            }
+          } else {
+            for (int o = max(first, c0) + tid; o < last; o += blockDim.x) ll_put_double((uint4*)&xnew[o], (double)s_out[o - c0], tag);
+          }
+          if (tid == 0) s_heavy_n = 0;
+          __syncthreads();
+        }
+        }
+        // block sum of the chosen x: travels in the next record (state estimate after resampling)
+        double v = warp_sum_d((double)sumx);
+        if (lane == 0) s_red[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+          double t = lane < nw ? s_red[lane] : 0.0;
+          t = warp_sum_d(t);
+          if (lane == 0) s_pending = t;
         }
       }
       ep2++;
-      FAST_TICK(7);   // expansion + LL copy-out
+      FAST_TICK(7);   // scatter + copy-out + block sum
       // ---- B2: poll this thread's own elements of x_new until they carry this step's tag ----
       if (n_own > 0) {
         const XEl* src = xnew + ibase;
@@ -679,16 +665,34 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) k_fast_bpf(FastParams P) {
 #pragma unroll
           for (int k = 0; k < PPT; k++) if (k >= n_own) x[k] = (Real)0;   // x_new beyond n is never written
         }
-#pragma unroll
-        for (int k = 0; k < PPT; k++) px += x[k];   // state estimate after resampling: travels in the next record
       }
+      FAST_TICK(8);   // B2 poll (reload) -- no barrier here: warps whose elements arrived start the next step
     }  // obs
     // flush: the state estimate of a final resampling step still travels in the records
-    exchange(2, -1, (Real)0, 0.0, (Real)0, (Real)0, px, (Real)0, [] {});
+    __syncthreads();
+    if (tid == 0) rec_publish(&rec[((ep1 + 1) & 1) * G + b], 0.0, 0.0, 0.0, 0.0, s_pending, ep1 + 1);
+    ep1++;
+    {
+      double v0 = 0.0;
+      for (int j = tid; j < G; j += blockDim.x) {   // all CTAs poll: see the note at the t = 0 exchange
+        double rv[5];
+        rec_poll(&rec[(ep1 & 1) * G + j], ep1, rv);
+        v0 += rv[4];
+      }
+      v0 = warp_sum_d(v0);
+      if (lane == 0) s_red[wid] = v0;
+      __syncthreads();
+      if (b == 0 && tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nw; w++) t += s_red[w];
+        if (pending_obs >= 0) f.state_est[(size_t)c * T1 + pending_obs + 1] = t / (double)n;
+        f.loglike[c] = loglike; f.n_resampled[c] = n_resampled;
+      }
+    }
     __syncthreads();
   }    // filters
 #ifdef BSSM_FAST_TIMING_BUILD
-  if (P.timing && lane == 0 && wid < 16) for (int i = 0; i < 12; i++) P.timing[((size_t)blockIdx.x * 16 + wid) * 12 + i] = tacc[i];
+  if (P.timing && tid == 0) for (int i = 0; i < 12; i++) P.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
 #endif
 #undef FAST_TICK
 }

@@ -8,14 +8,14 @@
 // usage: host_fast model variant G ngroups N T C resample_fn ralg threshold seed run_id stream_base [n_0 ... n_{C-1}]
 //   (optional trailing particle counts: a ragged batch, FilterDev::n_per; N is then the maximum)
 //                  < y (T doubles) theta (C x 3 doubles)
-//   variant: 0, 1 = <double, 8, 28 worker warps>, 2 = <float, 8, 8>, 3 = <float, 16, 14>, 4 = <float, 12, 19>   (EMU_UW: slack of the staged window of uniforms)
+//   variant: 0 = <double, 8, HEADS>, 1 = <double, 8, scatter loops>, 2 = <float, 8, HEADS>, 3 = <float, 16, scatter loops>
 #include "simt_emu.h"
 
 #include "../bayesssm_b200/csrc/bssm_fast.cuh"
 
 using namespace bssm;
 
-template <typename Model, typename Real, int PPT, int NWMAX>
+template <typename Model, typename Real, int PPT, bool HEADS>
 static int run(int argc, char** argv) {
   int a = 3;
   const int G = atoi(argv[a++]), ngroups_req = atoi(argv[a++]), N = atoi(argv[a++]), T = atoi(argv[a++]), C = atoi(argv[a++]);
@@ -39,10 +39,14 @@ static int run(int argc, char** argv) {
   if ((int)obs_times.size() != T) obs_times.clear();
 
   // geometry: fast_launch() of bssm_fast.cu
-  const FastGeom g = fast_geometry<Real, PPT>(N, G, getenv("EMU_UW") ? atoi(getenv("EMU_UW")) : -1);
-  if (g.nb_max > FAST_MAX_NB || g.nw > NWMAX) { fprintf(stderr, "slice too large\n"); return 2; }
-  const int nb_max = g.nb_max, threads = g.threads;
-  const size_t smem = g.smem;
+  int nb_max = (N + G - 1) / G;
+  nb_max = (nb_max + PPT - 1) / PPT * PPT;
+  if (nb_max > FAST_MAX_NB) { fprintf(stderr, "slice too large\n"); return 2; }
+  int threads = (nb_max / PPT + 31) / 32 * 32;
+  if (threads < 32) threads = 32;
+  const int cap = HEADS ? threads * fast_spt(PPT) : (nb_max + FAST_SLACK + 31) / 32 * 32;
+  size_t smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(Real) + (size_t)cap * sizeof(unsigned int);
+  if (HEADS) smem += (size_t)cap * sizeof(unsigned int) + (size_t)threads * PPT * sizeof(Real);
   const int ngroups = std::max(1, std::min(ngroups_req, C));
 
   FastParams P;
@@ -57,13 +61,14 @@ static int run(int argc, char** argv) {
   f.alive = alive.data(); f.status = status.data(); f.early_exit = early.data(); f.n_resampled = nres.data();
   f.ess = ess.data(); f.state_est = se.data(); f.loglike_history = llh.data();
   f.algorithm = 0; f.ralg = ralg; f.threshold = threshold;
-  P.G = G; P.ngroups = ngroups; P.resample_fn = rfn; P.nb_max = nb_max; P.xstride = g.xstride; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<sizeof(Real) == 4>::NUS), uint4{0, 0, 0, 0});
-  const size_t xbytes = (size_t)ngroups * g.xstride * (sizeof(Real) == 4 ? 8 : 16);
+  P.G = G; P.ngroups = ngroups; P.resample_fn = rfn; P.nb_max = nb_max; P.cap = cap;
+  std::vector<FastRec> rec((size_t)ngroups * 2 * G);
+  memset((void*)rec.data(), 0, sizeof(FastRec) * rec.size());
+  const size_t xbytes = (size_t)ngroups * G * nb_max * (sizeof(Real) == 4 ? 8 : 16);
   std::vector<unsigned long long> xnew(xbytes / 8, 0ull);   // exactly what fast_launch() allocates (AddressSanitizer runs rely on it)
   P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
-  emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<Model, Real, PPT, NWMAX>(Pc); });
+  emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<Model, Real, PPT, HEADS>(Pc); });
   for (int c = 0; c < C; c++) {
     printf("rank 0 filter %d loglike %.17g n_resampled %d status %d early_exit %d\n", c, loglike[c], nres[c], status[c], early[c]);
     printf("ess");
@@ -79,10 +84,10 @@ static int run(int argc, char** argv) {
 
 template <typename Model> static int by_variant(int argc, char** argv) {
   switch (atoi(argv[2])) {
-    case 0: case 1: return run<Model, double, 8, 28>(argc, argv);
-    case 2: return run<Model, float, 8, 8>(argc, argv);
-    case 3: return run<Model, float, 16, 14>(argc, argv);
-    case 4: return run<Model, float, 12, 19>(argc, argv);
+    case 0: return run<Model, double, 8, true>(argc, argv);
+    case 1: return run<Model, double, 8, false>(argc, argv);
+    case 2: return run<Model, float, 8, true>(argc, argv);
+    case 3: return run<Model, float, 16, false>(argc, argv);
   }
   return 2;
 }

@@ -37,18 +37,23 @@ static void run_filters(const FilterDev& f, int resample_fn, const int* active, 
   std::fill(f.ess, f.ess + C * (T + 1), 0.0);
   std::fill(f.state_est, f.state_est + C * (T + 1), 0.0);
   std::fill(f.loglike_history, f.loglike_history + C * T, 0.0);
-  const FastGeom g = fast_geometry<double, PPT>(f.N, G, -1);
-  const int nb_max = g.nb_max, threads = g.threads;
-  const size_t smem = g.smem;
+  int nb_max = (f.N + G - 1) / G;
+  nb_max = (nb_max + PPT - 1) / PPT * PPT;
+  int threads = (nb_max / PPT + 31) / 32 * 32;
+  if (threads < 32) threads = 32;
+  const int cap = threads * fast_spt(PPT);
+  const size_t smem = (size_t)((5 * G + 1) & ~1) * sizeof(double) + 5 * 32 * sizeof(double) + (size_t)cap * sizeof(double) +
+                      (size_t)cap * sizeof(unsigned int) + (size_t)cap * sizeof(unsigned int) + (size_t)threads * PPT * sizeof(double);
   const int ngroups = (int)std::min<size_t>(C, 4);
   FastParams P;
   memset(&P, 0, sizeof(P));
-  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = resample_fn; P.nb_max = nb_max; P.xstride = g.xstride; P.ucap = g.ucap; P.uw = g.uw;
-  std::vector<uint4> rec(fast_rec_units(ngroups, G, FastRecLayout<false>::NUS), uint4{0, 0, 0, 0});
-  std::vector<unsigned long long> xnew((size_t)ngroups * g.xstride * 2, 0ull);
+  P.f = f; P.G = G; P.ngroups = ngroups; P.resample_fn = resample_fn; P.nb_max = nb_max; P.cap = cap;
+  std::vector<FastRec> rec((size_t)ngroups * 2 * G);
+  memset((void*)rec.data(), 0, sizeof(FastRec) * rec.size());
+  std::vector<unsigned long long> xnew((size_t)ngroups * G * nb_max * 2, 0ull);
   P.rec = rec.data(); P.xnew = xnew.data(); P.timing = nullptr;
   const FastParams Pc = P;
-  emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<ModelArSin, double, 8, 28>(Pc); });
+  emu_launch_cooperative((unsigned int)(ngroups * G), (unsigned int)threads, smem, [&] { k_fast_bpf<ModelArSin, double, 8, true>(Pc); });
 }
 
 int main(int argc, char** argv) {

@@ -145,8 +145,8 @@ def test_observation_times_with_gaps(orc, host_fast):
 
 
 def test_outlying_observations_redo_the_step_against_the_true_maximum(orc, host_fast):
-    # the kernel weighs against the model's upper bound of the log-likelihood; when even the best particle is far below it (here
-    # 40 - 60 standard deviations) the sums underflow and the step is redone against the true maximum the records carry
+    # observations 40 - 60 standard deviations away from every particle: log-weights around -1000 to -2000, far from the early-exit
+    # threshold (-1e8) but deep in exp's underflow range unless the maximum is taken out first
     y = np.array([0.1, 30.0, 0.2, -25.0, 0.3, 0.1])
     ref = orc.particle_filter(AR, 0, 2, 0, 3000, y, THETA[AR], seed=7)
     rec, = host_fast(AR, F64_HEADS, 3, 3000, y, [THETA[AR]], seed=7, run_id=0, stream_base=0)
@@ -163,3 +163,4 @@ def test_more_than_32_ctas_in_a_group(orc, host_fast):
     ref = orc.particle_filter(AR, 0, 2, 0, 2560, y, THETA[AR], seed=4)
     rec, = host_fast(AR, F64_HEADS, 40, 2560, y, [THETA[AR]], seed=4, run_id=0, stream_base=0)
     check(rec, ref)
+
