@@ -88,6 +88,7 @@ class PmmhResult(C.Structure):
         ("n_accept", c_int32_p), ("status", c_int32_p),
         ("pilot_ms", C.c_float), ("main_ms", C.c_float),
         ("latent_state_chain", c_double_p),
+        ("main_resampled_fraction", C.c_double),
     ]
 
 

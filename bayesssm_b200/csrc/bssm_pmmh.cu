@@ -69,6 +69,9 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   BSSM_TRY(scratch(ctx, slot++, (size_t)C * p, &d_init));
   int* d_moved;
   BSSM_TRY(scratch(ctx, slot++, (size_t)C, &d_moved));
+  unsigned long long* d_nres;
+  BSSM_TRY(scratch(ctx, slot++, (size_t)2, &d_nres));
+  BSSM_CK(cudaMemsetAsync(d_nres, 0, sizeof(unsigned long long) * 2, st));
   // latent state estimates (R/pmmh.R: return_latent_state_est): current + per-iteration copies, only when asked for
   const bool latent = cfg->return_latent_state_est != 0 && res->latent_state_chain != nullptr;
   const int se_len = (T + 1) * d;
@@ -170,7 +173,7 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : BSSM_SISAR;
   L.resample_fn = BSSM_STRATIFIED;
   BSSM_TRY(filter_setup(ctx, f, L, need_aux, false, &cdf));
-  P.f_loglike = f.loglike; P.f_status = f.status;
+  P.f_loglike = f.loglike; P.f_status = f.status; P.f_nres = f.n_resampled; P.nres_acc = d_nres;
   BSSM_CK(cudaEventRecord(ctx->ev0, st));
   k_pm_start<<<gb, 128, 0, st>>>(P, B.mean, PH_MAIN, cfg->skip_pilot ? 1 : 0, cfg->skip_pilot ? 1 : 0);
   BSSM_LAUNCH(ctx, "k_pm_start");
@@ -204,11 +207,14 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
   DL(res->n_accept, B.n_accept, (size_t)C, int);
   if (latent) DL(res->latent_state_chain, d_se_chain, (size_t)C * m * se_len, double);
   DL(res->status, B.status, (size_t)C, int);
+  unsigned long long h_nres[2] = {0, 0};
+  BSSM_CK(cudaMemcpyAsync(h_nres, d_nres, sizeof(h_nres), cudaMemcpyDeviceToHost, st));
 #undef DL
   BSSM_CK(cudaStreamSynchronize(st));
   BSSM_CK(cudaEventElapsedTime(&main_ms, ctx->ev0, ctx->ev1));
   res->pilot_ms = pilot_ms;
   res->main_ms = main_ms;
+  res->main_resampled_fraction = (h_nres[1] && T) ? (double)h_nres[0] / ((double)h_nres[1] * T) : 0.0;
   return BSSM_OK;
 }
 

@@ -35,6 +35,8 @@ struct PmmhDev {
   unsigned int *stream, *run_id;  // [C] filter Philox ids
   // filter outputs
   const double* f_loglike; const int* f_status;
+  const int* f_nres;         // [C] resampling steps of the last filter run
+  unsigned long long* nres_acc;  // [2]: resampling steps / filter runs of the main phase, summed over the chains (for the roofline)
 };
 
 // R densities as in SURVEY.md Appendix F
@@ -168,6 +170,7 @@ __global__ void k_pm_accept(PmmhDev P, int phase, int it, double* chain, double*
   for (int j = 0; j < p; j++) cur[j] = P.cur[(size_t)c * p + j];
   P.moved[c] = 0;
   if (P.alive[c] && P.valid[c]) {
+    if (phase == PH_MAIN && P.nres_acc) { atomicAdd(&P.nres_acc[0], (unsigned long long)P.f_nres[c]); atomicAdd(&P.nres_acc[1], 1ull); }
     if (P.f_status[c]) { P.alive[c] = 0; P.status[c] = P.f_status[c]; }
     else {
       double prop[PMAX];

@@ -145,6 +145,7 @@ def run_chains(ctx, model, algorithm, y, init_theta, prior_specs, transforms, tu
     nat.check(ctx.lib.bssm_pmmh_run(ctx.handle, C.byref(cfg), y.ctypes.data_as(nat.c_double_p),
                                     init_theta.ctypes.data_as(nat.c_double_p), C.byref(res)))
     out["pilot_ms"], out["main_ms"] = res.pilot_ms, res.main_ms
+    out["main_resampled_fraction"] = res.main_resampled_fraction
     return out
 
 

@@ -7,9 +7,17 @@
 A "step" is one full pass of the hot path over one batch: one bootstrap filter of the README
 nonlinear-AR model, T=1000 observations, N=2^20 particles, SISAR (threshold 0.5 N) + stratified
 resampling -- BASELINE.json configs[1].  With N GPUs every rank runs its own independent filter
-(independent units, no data-path collective; weak scaling); `--workload pmmh` instead times
-chain-sharded PMMH iterations (configs[4]) with the final NCCL gather of draws.
-Prints ONE JSON line on rank 0.
+(independent units, no data-path collective; weak scaling): that is `value`.
+
+The same line carries three more blocks, measured in the same run (skip them with --no-extras):
+  "pmmh"     BASELINE configs[4]: 1024 chains x N=65536 x T=1000, the chains SHARDED over the N ranks by global id, one
+             final NCCL gather of the draws (strong scaling): iterations/s, particle-timesteps/s, roofline fraction
+             from the run's own resampling count
+  "sharded"  ONE filter of 2^28 particles, its particles sharded over the N ranks (one 64-byte ncclAllGather per
+             observation; strong scaling), with an inline parity check: a small f64 filter run sharded and on one
+             GPU must agree to 1e-9
+  "f64"      configs[1] in the reference's own precision (fp64 throughout) on the persistent kernel
+`--workload pmmh|sharded` times one of them alone as the line's `value`.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -132,15 +140,20 @@ def run_reference(args, rank, world):
               "C oracle restating R/particle_filter_core.R + src/resampling.cpp with R's "
               "Mersenne-Twister/inversion RNG; R itself is not installable in this image")
     metric, unit, scaling, config = "particle-timesteps/sec", "particle-timesteps/s", "weak", workload_config(args)
+    # what this arm actually runs: a bounded sample of that workload's algorithm, one filter per host core
+    config["workload"] = ("bootstrap_filter nonlinear-AR (README model) SISAR threshold=0.5N %s resampling, CPU port: %d independent filters "
+                          "(one per host core) of N=%d T=%d per step -- a bounded sample of the GPU arm's N=%d T=%d" % (args.resample_fn, cores, N, T, args.N, args.T))
+    config["N"], config["T"], config["filters"], config["gpu_arm"] = N, T, cores, {"N": args.N, "T": args.T}
+    config["precision"], config["engine"], config["l2"] = "f64", "oracle port (C)", "n/a (host)"
     if args.workload == "pmmh":
         # one PMMH iteration = one filter of N x T particle-timesteps per chain (R/pmmh.R:445-457); proposal and accept
         # are a few scalar operations beside it, so the port's iteration rate is its filter throughput over that work
-        per_iter = float(args.chains) * args.pmmh_N * args.T
+        per_iter = float(args.chains) * args.pmmh_N * args.pmmh_T
         value = value / per_iter
         metric, unit, scaling = "pmmh-iterations/sec", "iter/s", "strong"
-        config = {"workload": f"pmmh nonlinear-AR {args.chains} chains x N={args.pmmh_N} x T={args.T}, chain-sharded, pilot skipped, "
-                              "final NCCL gather of draws", "chains": args.chains, "N": args.pmmh_N, "T": args.T, "engine": args.engine}
-        sample += f"; converted to iterations of {args.chains} chains x N={args.pmmh_N} x T={args.T} ({per_iter:.3g} particle-timesteps each)"
+        config = {"workload": f"pmmh nonlinear-AR {args.chains} chains x N={args.pmmh_N} x T={args.pmmh_T}, chain-sharded, pilot skipped, "
+                              "final NCCL gather of draws", "chains": args.chains, "N": args.pmmh_N, "T": args.pmmh_T, "engine": args.engine}
+        sample += f"; converted to iterations of {args.chains} chains x N={args.pmmh_N} x T={args.pmmh_T} ({per_iter:.3g} particle-timesteps each)"
     elif args.workload == "sharded":
         scaling = "strong"
         config = {"workload": f"ONE bootstrap filter nonlinear-AR N={args.shard_N} T={args.shard_T} SISAR stratified, particle-sharded over the ranks",
@@ -161,7 +174,7 @@ def workload_config(args):
             "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)"}
 
 
-def run_pmmh_workload(args, ctx, rank, local_rank, world):
+def run_pmmh_workload(args, ctx, rank, local_rank, world, steps=None, warmup=None):
     """BASELINE configs[4]: PMMH on the nonlinear AR model, `--chains` chains x N = 65536 x T = 1000, chains split
     across the ranks by global id (strong scaling), pilot skipped (fixed proposal factor and particle count), one
     final NCCL gather of the draws.  A step is one PMMH iteration of ALL chains."""
@@ -172,7 +185,9 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world):
     from bayesssm_b200 import models, priors
     from bayesssm_b200 import _native as nat
     from bayesssm_b200.pmmh import default_tune_control, run_chains
-    T, N, Ctot = args.T, args.pmmh_N, args.chains
+    T, N, Ctot = args.pmmh_T, args.pmmh_N, args.chains
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     y = simulate_y(T)
     base, count = D.shard_chains(Ctot, rank, world)
     m = models.nonlinear_ar()
@@ -193,45 +208,50 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world):
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    run(max(args.warmup, 1), 1)
+    run(max(warmup, 1), 1)
     barrier()
     l0 = ctx.launch_count()
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
-        out = run(args.steps, 2)
-        main_ms = out["main_ms"] * args.steps / (args.steps + 1)   # the first filter of the phase is not an iteration
+        out = run(steps, 2)
+        main_ms = out["main_ms"] * steps / (steps + 1)   # the first filter of the phase is not an iteration
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = ctx.launch_count() - l0
     gathered = D.gather_chain_arrays({"theta_chain": out["theta_chain"], "n_accept": out["n_accept"]}, Ctot, rank, world,
                                      device=torch.device("cuda", local_rank) if world > 1 else None)
+    r_frac = float(out["main_resampled_fraction"])
     if world > 1:
         t = torch.tensor([main_ms, wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         main_ms, wall_ms = float(t[0]), float(t[1])
-    iters_per_s = args.steps / (main_ms * 1e-3)
+        t = torch.tensor([r_frac], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r_frac = float(t[0]) / world
+    iters_per_s = steps / (main_ms * 1e-3)
     pts = Ctot * N * T * iters_per_s
     peak, peak_src = measured_peak_gbs()
-    line = {"metric": "pmmh-iterations/sec", "value": iters_per_s, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": main_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+    bpp = 12.0 + 28.0 * r_frac     # 12 B every step + 28 B on the steps that resampled (f32 state / weights, f64 cdf)
+    return {"metric": "pmmh-iterations/sec", "value": iters_per_s, "unit": "iter/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": main_ms / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"pmmh nonlinear-AR {Ctot} chains x N={N} x T={T}, chain-sharded, pilot skipped, final NCCL gather of draws",
                        "chains": Ctot, "N": N, "T": T, "engine": args.engine, "l2": "working set 2 x 256 MiB of particles per GPU at 1024 chains: larger than L2"},
             "particle_timesteps_per_s": pts,
-            "e2e": {"value": (args.steps + 1) / (wall_ms * 1e-3), "unit": "iter/s",   # the call runs steps + 1 filter passes: draw 1 is the filter at the start value (R/pmmh.R:402-423)
-                    "h2d_bytes_per_step": int(8 * T / args.steps),
-                    "d2h_bytes_per_step": int(out["theta_chain"].nbytes / args.steps)},
+            "e2e": {"value": (steps + 1) / (wall_ms * 1e-3), "unit": "iter/s",   # the call runs steps + 1 filter passes: draw 1 is the filter at the start value (R/pmmh.R:402-423)
+                    "h2d_bytes_per_step": int(8 * T / steps),
+                    "d2h_bytes_per_step": int(out["theta_chain"].nbytes / steps)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "achieved": pts * 30.0 / 1e9, "peak": peak * world, "unit": "GB/s",
-                         "frac": pts * 30.0 / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": pts * bpp / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": pts * bpp / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
                          "kernel": "batched filter kernels of one iteration (AUTO: streaming engine k_st_step + k_st_resample at this size)",
-                         "algorithmic_bytes_per_particle_timestep": 30.0, "note": "12 B + 28 B x resampled fraction (0.63 on this model)"},
-            "acceptance_rate": float(gathered["n_accept"].mean() / max(args.steps, 1)),
+                         "algorithmic_bytes_per_particle_timestep": bpp, "resampled_fraction": r_frac,
+                         "note": "12 B + 28 B x the share of filter steps that resampled in THIS run (bssm_pmmh_result.main_resampled_fraction)"},
+            "acceptance_rate": float(gathered["n_accept"].mean() / max(steps, 1)),
             "draws_gathered_shape": list(gathered["theta_chain"].shape)}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
 
-def run_sharded_workload(args, ctx, rank, local_rank, world):
+
+def run_sharded_workload(args, ctx, rank, local_rank, world, steps=None, warmup=None, parity=False):
     """One bootstrap filter of `--shard-N` particles (default 2^28) sharded over the ranks (third row):
     per observation ONE ncclAllGather of a 64-byte record; no particle crosses NVLink.  Strong scaling: the
     filter is fixed, the ranks split its particles.  A step is one whole filter of `--shard-T` observations."""
@@ -240,6 +260,8 @@ def run_sharded_workload(args, ctx, rank, local_rank, world):
 
     from bayesssm_b200 import models, sharding as S
     N, T = args.shard_N, args.shard_T
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     y = simulate_y(T)
     grp = S.ShardGroup(ctx, rank=rank, world=world, device=torch.device("cuda", local_rank) if world > 1 else None)
     m = models.nonlinear_ar()
@@ -256,13 +278,13 @@ def run_sharded_workload(args, ctx, rank, local_rank, world):
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         run(i)
     barrier()
     l0 = ctx.launch_count()
     ms, e2e = [], []
     with ClockSampler(local_rank) as clocks:
-        for i in range(args.steps):
+        for i in range(steps):
             barrier()
             t1 = time.perf_counter()
             r = run(100 + i)
@@ -275,27 +297,49 @@ def run_sharded_workload(args, ctx, rank, local_rank, world):
         t = torch.tensor([tot, tot_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot, tot_e2e = float(t[0]), float(t[1])
-    value = N * T * args.steps / (tot * 1e-3)
+    value = N * T * steps / (tot * 1e-3)
     peak, peak_src = measured_peak_gbs()
     nbytes = algorithmic_bytes(N, T, r["n_resampled"])
-    achieved = nbytes / (tot / args.steps * 1e-3) / 1e9
+    achieved = nbytes / (tot / steps * 1e-3) / 1e9
     line = {"metric": "particle-timesteps/sec", "value": value, "unit": "particle-timesteps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": tot / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"ONE bootstrap filter nonlinear-AR N={N} T={T} SISAR threshold=0.5N {args.resample_fn}, particles "
                                    f"sharded over {world} GPU(s), one ncclAllGather of a 64-byte record per observation",
                        "N": N, "T": T, "engine": "stream (sharded)", "capacity_factor": args.capacity_factor,
                        "l2": "working set (8 B/particle x 2 buffers per rank) far larger than L2"},
-            "e2e": {"value": N * T * args.steps / (tot_e2e * 1e-3), "unit": "particle-timesteps/s",
+            "e2e": {"value": N * T * steps / (tot_e2e * 1e-3), "unit": "particle-timesteps/s",
                     "h2d_bytes_per_step": 8 * T + 24, "d2h_bytes_per_step": 8 * (3 * T + 3) + 12},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src, "kernel": "k_st_step + k_st_resample (all launches of one filter)",
                          "algorithmic_bytes_per_launch": nbytes, "resampled_steps": int(r["n_resampled"]), "T": T},
             "loglike": r["loglike"], "n_local_final": r["n_local_final"]}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    if parity:
+        # inline parity check: a small filter in the parity precision, sharded over these ranks, against the SAME filter on one
+        # GPU (this rank's streaming engine).  Philox streams are keyed by the global particle index, so the two differ only in
+        # the summation order of the normaliser: 1e-9 relative
+        from bayesssm_b200 import _native as nat
+        from bayesssm_b200 import bootstrap_filter
+        Np, Tp = 100003, 20
+        yp = simulate_y(Tp, seed=7)
+        rs = S.sharded_bootstrap_filter(yp, Np, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp, resample_algorithm="SISAR",
+                                        resample_fn=args.resample_fn, threshold=0.5 * Np, precision="f64", seed=11,
+                                        capacity_factor=max(args.capacity_factor, 2.0), phi=THETA[0], sigma_x=THETA[1], sigma_y=THETA[2])
+        r1 = bootstrap_filter(yp, Np, m.init_fn, m.transition_fn, m.log_likelihood_fn, resample_algorithm="SISAR",
+                              resample_fn=args.resample_fn, threshold=0.5 * Np, return_particles=False, precision="f64", seed=11,
+                              ctx=ctx, engine=nat.ENGINE_STREAM, phi=THETA[0], sigma_x=THETA[1], sigma_y=THETA[2])
+        rel = abs(rs["loglike"] - r1["loglike"]) / abs(r1["loglike"])
+        ok = bool(rel <= 1e-9 and rs["n_resampled"] == r1["n_resampled"])
+        if world > 1:
+            t = torch.tensor([0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ok = bool(t.item() == 0.0)
+        line["parity_ok"] = ok
+        line["parity"] = {"N": Np, "T": Tp, "precision": "f64", "loglike_sharded": rs["loglike"], "loglike_one_gpu": r1["loglike"],
+                          "rel_diff": rel, "tolerance": 1e-9, "n_resampled": [int(rs["n_resampled"]), int(r1["n_resampled"])]}
     grp.close()
+    return line
 
 
 def main():
@@ -318,6 +362,8 @@ def main():
     ap.add_argument("--capacity-factor", dest="capacity_factor", type=float, default=1.5)
     ap.add_argument("--chains", type=int, default=1024)
     ap.add_argument("--pmmh-N", dest="pmmh_N", type=int, default=65536)
+    ap.add_argument("--pmmh-T", dest="pmmh_T", type=int, default=1000)
+    ap.add_argument("--no-extras", action="store_true", help="default workload only: skip the pmmh / sharded / f64 blocks of the line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -342,7 +388,10 @@ def main():
     ctx = nat.Context(local_rank)
     lib = ctx.lib
     if args.workload in ("pmmh", "sharded"):
-        (run_pmmh_workload if args.workload == "pmmh" else run_sharded_workload)(args, ctx, rank, local_rank, world)
+        line = (run_pmmh_workload(args, ctx, rank, local_rank, world) if args.workload == "pmmh"
+                else run_sharded_workload(args, ctx, rank, local_rank, world, parity=True))
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
@@ -460,6 +509,52 @@ def main():
         line["cpu_baseline"] = {"value": Ns * Ts / secs, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
                                 "sample": f"same model/config, N=2^20, first {Ts} of the {T} observations, 1 thread (the R "
                                           "interpreter is single-threaded), C oracle with R's RNG cost model"}
+    if not args.no_extras:
+        # the north star's other numbers, in the same run and on the same line (the driver records this line for every N)
+        def keep(d, keys):
+            return {k: d[k] for k in keys if k in d}
+        px = run_pmmh_workload(args, ctx, rank, local_rank, world, steps=max(3, min(args.steps, 5)), warmup=1)
+        line["pmmh"] = keep(px, ["metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config",
+                                 "particle_timesteps_per_s", "e2e", "gpu_launches", "roofline", "acceptance_rate", "draws_gathered_shape"])
+        sx = run_sharded_workload(args, ctx, rank, local_rank, world, steps=max(2, min(args.steps, 4)), warmup=1, parity=True)
+        line["sharded"] = keep(sx, ["metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config", "e2e",
+                                    "gpu_launches", "roofline", "loglike", "n_local_final", "parity_ok", "parity"])
+        # configs[1] in the reference's precision: fp64 state, weights, cdf -- 64 B per resampled particle-timestep, 24 B otherwise
+        cfg.precision, cfg.engine = nat.F64, nat.ENGINE_PERSISTENT
+        d_ll64 = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+        def f64_step(i):
+            cfg.run_id = i
+            ms = C.c_float()
+            nat.check(lib.bssm_filter_run_device(ctx.handle, C.byref(cfg), d_y.data_ptr(), d_theta.data_ptr(), d_ll64.data_ptr(), C.byref(ms)))
+            return ms.value
+        f64_step(0)
+        barrier()
+        n64 = max(2, min(args.steps, 3))
+        ms64 = []
+        for i in range(n64):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            ms64.append(f64_step(10 + i))
+        barrier()
+        tot64 = float(sum(ms64))
+        if world > 1:
+            t = torch.tensor([tot64], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot64 = float(t.item())
+        r64 = bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn, resample_algorithm="SISAR", resample_fn=args.resample_fn,
+                               threshold=0.5 * N, return_particles=False, precision="f64", seed=1405, ctx=ctx, engine=nat.ENGINE_PERSISTENT,
+                               phi=THETA[0], sigma_x=THETA[1], sigma_y=THETA[2])
+        b64 = algorithmic_bytes(N, T, r64["n_resampled"], sx=8, sw=8)
+        a64 = b64 / (tot64 / n64 * 1e-3) / 1e9
+        line["f64"] = {"metric": "particle-timesteps/sec", "value": world * N * T * n64 / (tot64 * 1e-3), "unit": "particle-timesteps/s",
+                       "n_gpus": world, "steps": n64, "ms_per_step": tot64 / n64, "scaling": "weak", "dtype": "f64",
+                       "config": {"workload": "the default workload in the reference's precision (fp64 state, weights, cdf, libm sin / exp / log), "
+                                              "persistent kernel k_fast_bpf<double>", "T": T, "N": N, "engine": "persistent"},
+                       "roofline": {"bound": "hbm", "achieved": a64, "peak": peak, "unit": "GB/s", "frac": a64 / peak,
+                                    "algorithmic_bytes_per_launch": b64, "resampled_steps": int(r64["n_resampled"]),
+                                    "note": "24 B per particle-timestep + 40 B on resampled steps (all-fp64 model of SURVEY 8d)"},
+                       "loglike": r64["loglike"], "loglike_f32": r0["loglike"]}
     if world > 1:
         dist.barrier()
     if rank == 0:

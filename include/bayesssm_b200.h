@@ -251,6 +251,8 @@ typedef struct {
   int32_t *status;             /* [chains] */
   float pilot_ms, main_ms;     /* device time of the two phases */
   double *latent_state_chain;  /* [chains][m][T+1][d] state_est of the filter run behind every draw (R/pmmh.R:420,494-499), or NULL */
+  double main_resampled_fraction; /* out: share of the main phase's filter steps that resampled (accepted or not): the measured
+                                     r of the roofline's 12 + 28 r bytes per particle-timestep */
 } bssm_pmmh_result;
 
 /* init_theta: [num_chains][p] (pilot_init_params) */
