@@ -546,7 +546,7 @@ static int filter_validate(const bssm_filter_config* cfg) {
   if (cfg->algorithm < 0 || cfg->algorithm > 2 || cfg->resample_algorithm < 0 || cfg->resample_algorithm > 2 ||
       cfg->resample_fn < 0 || cfg->resample_fn > 2) { set_error("unknown algorithm / resample_algorithm / resample_fn"); return BSSM_ERR_BAD_ARG; }
   if (cfg->obs_times) {
-    int prev = 0;
+    int prev = 1;   // R/particle_filter_core.R:69: checkmate::assert_integerish(obs_times, lower = 1, sorted = TRUE)
     for (int i = 0; i < cfg->num_obs; i++) {
       if (cfg->obs_times[i] < prev) { set_error("obs_times must be non-decreasing positive integers"); return BSSM_ERR_BAD_ARG; }
       prev = cfg->obs_times[i];

@@ -135,13 +135,16 @@ int bssm_pmmh_run(bssm_ctx* ctx, const bssm_pmmh_config* cfg, const double* y, c
     }
     k_pm_pilot_stats<<<gb, 128, 0, st>>>(P, B.pilot_chain, pm, B.mean, B.cov);
     BSSM_LAUNCH(ctx, "k_pm_pilot_stats");
-    // ---- .pilot_run: reps replicate filters per chain at the pilot mean, wrapper defaults SISAR + stratified ----
+    // ---- .pilot_run: reps replicate filters per chain at the pilot mean.  They run with tune_control's pilot_resample_algorithm /
+    //      pilot_resample_fn like the pilot chain: pmmh() hands both to .run_pilot_chain (R/pmmh.R:366-367), which has no such
+    //      formals, so they travel in its `...` into do.call(.pilot_run, ...) (R/pmmh_tuning.R:292-305) and on to pf_wrapper
+    //      (R/pmmh_tuning.R:34-50).  Only the MAIN chain runs on the wrapper's defaults (quirk A10) ----
     {
       FilterDev fr = f;
       fr.C = C * reps; fr.theta = B.theta_rep; fr.stream = B.ids_rep; fr.run_id = B.ids_rep + (size_t)C * reps;
-      fr.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : BSSM_SISAR;
+      fr.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->pilot_resample_algorithm;
       FilterLaunch Lr = L;
-      Lr.resample_fn = BSSM_STRATIFIED;
+      Lr.resample_fn = cfg->pilot_resample_fn;
       BSSM_TRY(filter_setup(ctx, fr, Lr, need_aux, false, &cdf));
       k_pm_reps_setup<<<(C * reps + 127) / 128, 128, 0, st>>>(P, B.mean, reps, B.theta_rep, B.ids_rep, B.ids_rep + (size_t)C * reps, B.active_rep);
       BSSM_LAUNCH(ctx, "k_pm_reps_setup");

@@ -46,10 +46,10 @@ def pmmh_sharded(run_local, num_chains: int, rank: int, world: int, device=None,
                  keys=("theta_chain", "loglike_chain", "n_accept", "target_n", "status")):
     """run_local(chain_id_base, count) -> dict of per-chain arrays for this rank's shard (e.g. a closure over
     bayesssm_b200.pmmh.run_chains).  Returns the gathered dict on every rank."""
-    base, count = shard_chains(num_chains, rank, world)
-    local = run_local(base, count) if count > 0 else None
-    if local is None:
+    if num_chains < world:     # checked on EVERY rank before any work: a rank left without chains must not leave the others in the gather
         raise ValueError("more ranks than chains")
+    base, count = shard_chains(num_chains, rank, world)
+    local = run_local(base, count)
     return gather_chain_arrays({k: local[k] for k in keys if k in local}, num_chains, rank, world, device)
 
 

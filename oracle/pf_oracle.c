@@ -753,11 +753,13 @@ int orc_pmmh_chain(const orc_pmmh_config *c, const double *y, const double *init
              (res->pilot_theta_chain[(size_t)it * p + b] - res->pilot_theta_mean[b]);
       res->pilot_theta_cov[a * p + b] = s / (double)(nn - 1);
     }
-  /* .pilot_run R/pmmh_tuning.R:29-64 (wrapper defaults: SISAR + stratified, quirk A10) */
+  /* .pilot_run R/pmmh_tuning.R:29-64.  resample_algorithm / resample_fn are tune_control's pilot settings here too: pmmh() passes
+   * them to .run_pilot_chain (R/pmmh.R:366-367), whose `...` is spliced into do.call(.pilot_run, ...) (R/pmmh_tuning.R:292-305);
+   * .pilot_run forwards resample_fn and its own `...` to pf_wrapper (:34-50).  run_filter() applies RMPF's SISR override. */
   {
     double mean_ll = 0.0;
     for (int r = 0; r < c->pilot_reps; r++) {
-      st = run_filter(c, y, res->pilot_theta_mean, c->pilot_n, ORC_SISAR, ORC_STRATIFIED,
+      st = run_filter(c, y, res->pilot_theta_mean, c->pilot_n, c->pilot_resample_algorithm, c->pilot_resample_fn,
                       ((uint32_t)PH_PILOT_RUN << 28) | (uint32_t)r, chain_id, &res->pilot_loglikes[r]);
       if (st) return st;
       mean_ll += res->pilot_loglikes[r];

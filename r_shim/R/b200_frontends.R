@@ -65,6 +65,7 @@ b200_prior_halfnormal <- function(sigma = 1) c(4, sigma, 0)
   checkmate::assert_count(num_particles, positive = TRUE)
   checkmate::assert_numeric(y, any.missing = FALSE)
   if (is.vector(y)) y <- matrix(y, ncol = 1)
+  storage.mode(y) <- "double"   # integer observations (rpois ...) are numeric to the reference; the shim reads REAL()
   if (!is.null(obs_times)) checkmate::assert_integerish(obs_times, len = nrow(y), lower = 1, sorted = TRUE)
   theta <- .b200_theta(model, list(...))
   cfg <- list(model = model$id, algorithm = match(algorithm, c("BPF", "APF", "RMPF")) - 1L,
@@ -133,6 +134,7 @@ pmmh <- function(pf_wrapper, y, m, init_fn, transition_fn, log_likelihood_fn, lo
   init <- t(vapply(pilot_init_params, function(p) as.numeric(unlist(p[model$params])), numeric(length(model$params))))
   if (length(model$params) == 1) init <- matrix(init, ncol = 1)
   if (is.vector(y)) y <- matrix(y, ncol = 1)
+  storage.mode(y) <- "double"   # integer observations (rpois ...) are numeric to the reference; the shim reads REAL()
   if (is.null(seed)) seed <- sample.int(.Machine$integer.max, 1)
   cfg <- list(model = model$id, algorithm = algorithm, prior_kind = as.integer(priors[, 1]), prior_a = priors[, 2],
               prior_b = priors[, 3],
@@ -217,6 +219,7 @@ b200_sharded_bootstrap_filter <- function(y, num_particles, init_fn, transition_
   model <- .b200_resolve(init_fn, transition_fn, log_likelihood_fn)
   resample_algorithm <- match.arg(resample_algorithm); resample_fn <- match.arg(resample_fn)
   if (is.vector(y)) y <- matrix(y, ncol = 1)
+  storage.mode(y) <- "double"   # integer observations (rpois ...) are numeric to the reference; the shim reads REAL()
   cfg <- list(model = model$id, resample_algorithm = match(resample_algorithm, c("SIS", "SISR", "SISAR")) - 1L,
               resample_fn = match(resample_fn, c("stratified", "systematic")) - 1L,
               threshold = if (is.null(threshold)) -1 else threshold, num_particles = as.integer(num_particles),

@@ -107,14 +107,14 @@ int main(int argc, char** argv) {
     launch(gb, [&] { k_pm_accept(Pc, PH_PILOT, it, pilot_chain.data(), pilot_ll.data(), pm); });
   }
   { const PmmhDev Pc = P; launch(gb, [&] { k_pm_pilot_stats(Pc, pilot_chain.data(), pm, mean.data(), cov.data()); }); }
-  // ---- .pilot_run (R/pmmh_tuning.R:29-64): reps replicate filters per chain at the pilot mean, SISAR + stratified ----
+  // ---- .pilot_run (R/pmmh_tuning.R:29-64): reps replicate filters per chain at the pilot mean, with the pilot's resampler settings ----
   {
     FilterDev fr = f;
-    fr.C = C * reps; fr.theta = theta_rep.data(); fr.stream = ids_rep.data(); fr.run_id = ids_rep.data() + (size_t)C * reps; fr.ralg = 2;
+    fr.C = C * reps; fr.theta = theta_rep.data(); fr.stream = ids_rep.data(); fr.run_id = ids_rep.data() + (size_t)C * reps; fr.ralg = pilot_ralg;
     fsr.attach(fr);
     const PmmhDev Pc = P;
     launch((unsigned int)(C * reps + 127) / 128, [&] { k_pm_reps_setup(Pc, mean.data(), reps, theta_rep.data(), ids_rep.data(), ids_rep.data() + (size_t)C * reps, active_rep.data()); });
-    run_filters(fr, 0, active_rep.data(), G);
+    run_filters(fr, pilot_rfn, active_rep.data(), G);
     launch(gb, [&] { k_pm_tune(Pc, fr.loglike, fr.status, reps, pilot_n, fixed_n, mean.data(), cov.data(), rep_ll.data(), target_n.data(), chol.data()); });
   }
   // ---- main chain (R/pmmh.R:395-500); SISAR + stratified whatever the caller asked for (quirk A10) ----

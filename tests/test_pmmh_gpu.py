@@ -20,12 +20,15 @@ def readme_data(T, rng):
     return np.array(ys)
 
 
-@pytest.mark.parametrize("transform", [[0, 0, 0], [2, 1, 1]])
-def test_chains_match_oracle(orc, engine, transform):
+# the last case: tune_control's pilot_resample_algorithm = "SISR", pilot_resample_fn = "systematic" -- they steer the pilot chain AND
+# the .pilot_run replicates behind target_n (R/pmmh.R:366-367 -> `...` of .run_pilot_chain -> do.call(.pilot_run), R/pmmh_tuning.R:292-305)
+@pytest.mark.parametrize("transform,pilot", [([0, 0, 0], (2, 0)), ([2, 1, 1], (2, 0)), ([2, 1, 1], (1, 1))])
+def test_chains_match_oracle(orc, engine, transform, pilot):
     rng = np.random.default_rng(1405)
     y = readme_data(12, rng)
     inits = np.array([[0.8, 1.0, 0.5], [0.5, 0.7, 1.2], [0.3, 1.5, 0.8]])
-    kw = dict(transform=transform, pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=30, pilot_reps=6, m=40, seed=99)
+    kw = dict(transform=transform, pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=30, pilot_reps=6, m=40, seed=99,
+              pilot_resample_algorithm=pilot[0], pilot_resample_fn=pilot[1])
     got = eh.pmmh_run(engine, 0, 0, y, inits, chain_id_base=4, return_latent_state_est=True, **PRIOR, **kw)
     assert (got["status"] == 0).all()
     for c in range(3):

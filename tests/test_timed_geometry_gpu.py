@@ -1,0 +1,78 @@
+"""Gates on the instantiations bench.py times, AT the geometry it times them (N = 2^20 x T = 1000 on the persistent kernel,
+1024 x 65536 x T = 1000 on the streaming engine, throughput precision f32).  The north star's third check -- agreement with
+the exact Kalman log-likelihood within 3 Monte-Carlo standard errors on the linear-Gaussian model -- and f32 against the
+parity precision on the README model, both over the full 1000 observations: every resampling step adds fp32 cdf increments,
+slot arithmetic and SFU approximations, and only a run of the full length shows whether they drift.
+(SISR on the linear-Gaussian model: with SISAR the reference drops the weights on steps that do not resample -- SURVEY App. A1 --
+which biases the estimate it is compared with; the timed SISAR configuration is gated against its own f64 run instead.)"""
+import numpy as np
+import pytest
+
+import engine_helpers as eh
+from bayesssm_b200 import _native as nat
+from test_filter_gpu import THETA, sim_y
+
+pytestmark = pytest.mark.gpu
+AR, LG = 0, 1
+
+
+def logmeanexp(v):
+    v = np.asarray(v, float)
+    return np.log(np.mean(np.exp(v - v.max()))) + v.max()
+
+
+def test_persistent_f32_lg_n2pow20_t1000_against_kalman(orc, engine):
+    y = sim_y(LG, 1000, np.random.default_rng(2020))
+    exact = orc.kalman_loglik(y, *THETA[LG])
+    got = eh.filter_run(engine, LG, 0, 1, 0, 1 << 20, y, THETA[LG], seed=77, num_filters=16, precision=nat.F32,
+                        engine=nat.ENGINE_PERSISTENT)
+    assert (got["status"] == 0).all() and (got["n_resampled"] == 1000).all()
+    lls = got["loglike"]
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    # tolerance: 3 Monte-Carlo standard errors of the 16 replicates (north star), + 2e-3 absolute for fp32 log / exp over 1000 steps
+    assert abs(logmeanexp(lls) - exact) < 3 * se + 2e-3, (logmeanexp(lls), exact, se)
+
+
+def test_persistent_f32_against_its_f64_run_at_the_timed_configuration(engine):
+    # bench.py's default workload itself: README model, N = 2^20, T = 1000, SISAR 0.5 N, stratified
+    y = sim_y(AR, 1000, np.random.default_rng(1405))
+    N = 1 << 20
+    f32 = [eh.filter_run(engine, AR, 0, 2, 0, N, y, THETA[AR], threshold=0.5 * N, seed=5, run_id=r, precision=nat.F32,
+                         engine=nat.ENGINE_PERSISTENT) for r in range(4)]
+    f64 = eh.filter_run(engine, AR, 0, 2, 0, N, y, THETA[AR], threshold=0.5 * N, seed=5, run_id=0, precision=nat.F64,
+                        engine=nat.ENGINE_PERSISTENT)
+    l32 = np.array([r["loglike"][0] for r in f32])
+    assert all(r["status"][0] == 0 for r in f32) and f64["status"][0] == 0
+    # the f32 runs are independent Monte-Carlo replicates (different run ids); the f64 run is one more draw of the same estimator
+    # if -- and only if -- fp32 adds no bias: within 4 standard deviations of a single run (+ 5e-3 absolute)
+    sd = max(l32.std(ddof=1), 1e-3)
+    assert abs(f64["loglike"][0] - l32.mean()) < 4 * sd * np.sqrt(1 + 1 / len(l32)) + 5e-3, (f64["loglike"][0], l32)
+    # the resampling schedule (ESS below N / 2) is a property of the data, hardly of the precision
+    n64 = int(f64["n_resampled"][0])
+    assert all(abs(int(r["n_resampled"][0]) - n64) <= 5 for r in f32)
+    # state estimates: Monte-Carlo agreement (the largest gaps sit at low-ESS observations; 0.024 observed)
+    np.testing.assert_allclose(f32[0]["state_est"][0], f64["state_est"][0], atol=0.06)
+
+
+def test_streaming_f32_lg_1024_x_65536_t1000_against_kalman(orc, engine):
+    # one PMMH iteration's worth of filters at BASELINE configs[4]: 1024 filters x 65536 particles x 1000 observations
+    y = sim_y(LG, 1000, np.random.default_rng(4040))
+    exact = orc.kalman_loglik(y, *THETA[LG])
+    got = eh.filter_run(engine, LG, 0, 1, 0, 65536, y, THETA[LG], seed=99, num_filters=1024, precision=nat.F32, engine=nat.ENGINE_STREAM)
+    assert (got["status"] == 0).all()
+    lls = got["loglike"]
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(logmeanexp(lls) - exact) < 3 * se + 2e-3, (logmeanexp(lls), exact, se)
+    assert len(np.unique(lls)) == 1024
+
+
+def test_streaming_f32_against_f64_at_the_pmmh_geometry(engine):
+    # README model, SISAR + stratified as pmmh()'s main chain runs it; 128 of the 1024 filters in the parity precision
+    y = sim_y(AR, 1000, np.random.default_rng(1405))
+    a = eh.filter_run(engine, AR, 0, 2, 0, 65536, y, THETA[AR], seed=3, num_filters=1024, precision=nat.F32, engine=nat.ENGINE_STREAM)
+    b = eh.filter_run(engine, AR, 0, 2, 0, 65536, y, THETA[AR], seed=3, num_filters=128, precision=nat.F64, engine=nat.ENGINE_STREAM)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    la, lb = a["loglike"], b["loglike"]
+    se = np.sqrt(la.var(ddof=1) / len(la) + lb.var(ddof=1) / len(lb))
+    assert abs(la.mean() - lb.mean()) < 4 * se + 5e-3, (la.mean(), lb.mean(), se)
+    assert abs(np.median(a["n_resampled"]) - np.median(b["n_resampled"])) <= 5
