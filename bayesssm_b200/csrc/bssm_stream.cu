@@ -23,9 +23,22 @@ bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L) 
 
 // kernels are launched through handles, so that built-in models (function addresses) and NVRTC-compiled user
 // models (cudaKernel_t of the compiled library) share one orchestration
-static int st_launch(bssm_ctx* ctx, void* kern, dim3 grid, int threads, StreamParams& P, int* obs, const char* what) {
+// pdl: programmatic dependent launch -- the kernel may become resident while its predecessor in the stream drains (both kernels
+// call griddepcontrol.launch_dependents / .wait, bssm_stream.cuh); BSSM_ST_PDL=0 turns it off
+static int st_launch(bssm_ctx* ctx, void* kern, dim3 grid, int threads, StreamParams& P, int* obs, const char* what, bool pdl) {
   void* args[] = {&P, obs};
-  BSSM_CK(cudaLaunchKernel(kern, grid, dim3(threads), args, 0, ctx->stream));
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BSSM_CK(cudaLaunchKernelExC(&cfg, kern, args));
+  } else {
+    BSSM_CK(cudaLaunchKernel(kern, grid, dim3(threads), args, 0, ctx->stream));
+  }
   BSSM_LAUNCH(ctx, what);
   return BSSM_OK;
 }
@@ -103,15 +116,19 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_LAUNCH(ctx, "k_st_init");
   }
   const bool may_resample = f.ralg != BSSM_SIS;
+  // one GPU: the two kernels of an observation chain by programmatic dependent launch (the sharded filter has an NCCL call
+  // and a merge kernel between them: ordinary launches there)
+  const char* pdl_env = getenv("BSSM_ST_PDL");
+  const bool pdl = !sh && !(pdl_env && atoi(pdl_env) == 0);
   for (int obs = 0; obs < L.T; obs++) {
-    BSSM_TRY(st_launch(ctx, K.step, grid, ST_THREADS, P, &obs, "k_st_step"));
+    BSSM_TRY(st_launch(ctx, K.step, grid, ST_THREADS, P, &obs, "k_st_step", pdl && obs > 0));
     if (sh) {
       BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
       k_st_merge<<<(C + 127) / 128, 128, 0, st>>>(P, obs);
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample"));
+      BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample", pdl));
     }
   }
   if (P.dbg) {

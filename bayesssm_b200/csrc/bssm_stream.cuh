@@ -384,6 +384,19 @@ template <typename Real> __device__ __forceinline__ Real st_warp_max(Real v) {
   return v;
 }
 
+// Programmatic dependent launch (sm_90+): k_st_step and k_st_resample of a one-GPU filter are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  A kernel lets its successor's blocks become resident as soon as
+// its own blocks make room (launch_dependents, first thing), and reads nothing the predecessor wrote before
+// griddepcontrol.wait -- which returns when the predecessor grid has completed and its writes are visible.  What sits above
+// the wait (parameter set-up, Philox key, the observation) depends only on data that was final two launches earlier.
+#if !defined(BSSM_EMU)
+__device__ __forceinline__ void st_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void st_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+inline void st_pdl_launch_dependents() {}
+inline void st_pdl_wait() {}
+#endif
+
 // ---- K_A: propagate + log-weight + tile / block partials; the last block of a filter merges ----
 // Block (c, j) walks the contiguous tiles [j * tpb, (j + 1) * tpb) of filter c; the next tile's particles
 // are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
@@ -400,6 +413,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   __shared__ double s_red[4 * ST_NW];
   const FilterDev& f = P.f;
   const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  st_pdl_launch_dependents();
+  // independent of the previous launch: parameters, Philox key, the observation
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
+  const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
+  double yv[4] = {0, 0, 0, 0};
+  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
+  st_pdl_wait();
   const long long t_start = P.dbg ? clock64() : 0;
   if (!f.alive[c]) return;
   const StLayout L = st_layout_in<TS>(P, c, obs);
@@ -410,13 +433,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParam
   const Real* xin = (const Real*)(rprev ? P.x0 : P.x1) + (size_t)c * P.xstride + tid * PPT;
   Real* xout = (Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
   st_prefetch<Real, PPT, ST_THREADS>(s_pf[0], xin + (size_t)t0 * TS);
-  Real par[Model::NPAR];
-  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
-  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
-  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
-  const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
-  double yv[4] = {0, 0, 0, 0};
-  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   // this thread's record: running max and sums (relative to it) over its particles of all the block's tiles
   // (a NaN log-weight never raises the max and turns exp(NaN - ref) into NaN: it poisons the sum by itself --
   // R's `if (NA)` error, reported as BSSM_ERR_NAN_WEIGHT)
@@ -556,6 +572,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   __shared__ unsigned int s_wh[ST_NW];
   const FilterDev& f = P.f;
   const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  st_pdl_launch_dependents();
+  // independent of the previous launch: parameters, Philox key, the observation
+  const int n = P.n_glob ? P.n_glob : filt_n(f, c);
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
+  double yv[4] = {0, 0, 0, 0};
+  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
+  st_pdl_wait();
   if (!f.alive[c]) return;
   const int pc = obs & 1;
   if (!P.res[pc * f.C + c]) return;
@@ -566,13 +592,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   const int t0 = j * L.tpb, t1 = min(ntc, t0 + L.tpb);
   const Real* xin = (const Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
   st_prefetch<Real, PPT, ST_THREADS>(s_pf[0], xin + (size_t)t0 * TS);
-  const int n = P.n_glob ? P.n_glob : filt_n(f, c);
-  Real par[Model::NPAR];
-  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
-  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
-  const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
-  double yv[4] = {0, 0, 0, 0};
-  for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   const double M = f.M[c], S = f.S[c];
   const double wscale = 1.0 / S;
   const double* pref = P.pref + (size_t)c * (P.bpc + 1);
