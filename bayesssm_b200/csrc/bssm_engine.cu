@@ -152,6 +152,35 @@ static int launch_post(bssm_ctx* ctx, const ModelKernels& K, dim3 grid, FilterDe
   return BSSM_OK;
 }
 
+// one history row (particles and weights of all filters at time `row`): computed into ring slot row % 2 on the compute stream
+// once the copy of row - 2 has left that slot, then copied to the caller's [C][T+1][..] buffers on the copy stream (2-D copies:
+// one line per filter).  The destination is pinned for the duration of the call when the driver allows it (bssm_filter_run).
+template <typename Real>
+static int hist_row_out(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, dim3 grid, int row) {
+  cudaStream_t st = ctx->stream;
+  const int slot = row % f.hist_rows;
+  if (!ctx->copy_stream) {
+    BSSM_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { BSSM_CK(cudaEventCreateWithFlags(&ctx->ev_row[i], cudaEventDisableTiming)); BSSM_CK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming)); }
+  }
+  if (row >= f.hist_rows) BSSM_CK(cudaStreamWaitEvent(st, ctx->ev_free[slot], 0));
+  k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, row);
+  BSSM_LAUNCH(ctx, "k_history");
+  BSSM_CK(cudaEventRecord(ctx->ev_row[slot], st));
+  BSSM_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_row[slot], 0));
+  const size_t T1 = (size_t)f.T + 1, N = (size_t)f.N, d = (size_t)f.d, C = (size_t)f.C;
+  if (L.h_particles_history)
+    BSSM_CK(cudaMemcpy2DAsync(L.h_particles_history + (size_t)row * d * N, T1 * d * N * sizeof(double),
+                              f.particles_history + (size_t)slot * d * N, (size_t)f.hist_rows * d * N * sizeof(double),
+                              d * N * sizeof(double), C, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (L.h_weights_history)
+    BSSM_CK(cudaMemcpy2DAsync(L.h_weights_history + (size_t)row * N, T1 * N * sizeof(double),
+                              f.weights_history + (size_t)slot * N, (size_t)f.hist_rows * N * sizeof(double),
+                              N * sizeof(double), C, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  BSSM_CK(cudaEventRecord(ctx->ev_free[slot], ctx->copy_stream));
+  return BSSM_OK;
+}
+
 template <typename Real>
 static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf, const ModelKernels& K) {
   dim3 grid(f.C, f.nblk);
@@ -161,7 +190,7 @@ static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, 
   BSSM_TRY(launch_init(ctx, K, grid, f));
   k_finalize<<<f.C, 128, 0, st>>>(f, 0, 0);
   BSSM_LAUNCH(ctx, "k_finalize");
-  if (L.hist) { k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, 0); BSSM_LAUNCH(ctx, "k_history"); }
+  if (L.hist) BSSM_TRY(hist_row_out<Real>(ctx, f, L, grid, 0));
   const bool may_resample = (f.algorithm == BSSM_RMPF) || (f.ralg != BSSM_SIS);
   for (int obs = 0; obs < L.T; obs++) {
     if (f.algorithm == BSSM_APF) {
@@ -181,7 +210,7 @@ static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, 
       k_finalize<<<f.C, 128, 0, st>>>(f, obs, 3);
       BSSM_LAUNCH(ctx, "k_finalize");
     }
-    if (L.hist) { k_history<Real><<<grid, FT_THREADS, 0, st>>>(f, obs + 1); BSSM_LAUNCH(ctx, "k_history"); }
+    if (L.hist) BSSM_TRY(hist_row_out<Real>(ctx, f, L, grid, obs + 1));
   }
   return BSSM_OK;
 }
@@ -318,9 +347,12 @@ int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_a
   BSSM_TRY(scratch(ctx, SL_F_SEST, C * (T + 1) * d, &f.state_est));
   BSSM_TRY(scratch(ctx, SL_F_LLH, C * (T ? T : 1), &f.loglike_history));
   if (L.hist) {
-    BSSM_TRY(scratch(ctx, SL_F_PH, C * (T + 1) * d * N, &f.particles_history));
-    BSSM_TRY(scratch(ctx, SL_F_WH, C * (T + 1) * N, &f.weights_history));
-  } else { f.particles_history = nullptr; f.weights_history = nullptr; }
+    // histories (R/particle_filter_core.R:100-116,242-264) never exist on the device as a whole -- (T + 1) N 16 bytes is 16.8 GB at
+    // N = 2^20, T = 1000: a ring of two rows, each copied to the caller's buffers on a second stream while the next is computed
+    f.hist_rows = 2;
+    BSSM_TRY(scratch(ctx, SL_F_PH, C * f.hist_rows * d * N, &f.particles_history));
+    BSSM_TRY(scratch(ctx, SL_F_WH, C * f.hist_rows * N, &f.weights_history));
+  } else { f.particles_history = nullptr; f.weights_history = nullptr; f.hist_rows = 1; }
   if (want_anc) {
     BSSM_TRY(scratch(ctx, SL_F_ANC, C * (T ? T : 1) * N, &f.anc_history));
     BSSM_CK(cudaMemsetAsync(f.anc_history, 0, C * T * N * sizeof(int), ctx->stream));
@@ -385,6 +417,7 @@ void bssm_destroy(bssm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < SL_COUNT; i++) if (ctx->scratch[i].p) cudaFree(ctx->scratch[i].p);
   cudaEventDestroy(ctx->ev0);
+  if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_row[i]); cudaEventDestroy(ctx->ev_free[i]); } }
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -573,6 +606,16 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
   L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
   L.hist = cfg->return_particles; L.T = T; L.engine = cfg->engine;
+  bool pinned_ph = false, pinned_wh = false;
+  if (cfg->return_particles) {
+    // rows stream to the caller's buffers while the filter runs: pin them for the call (a pageable destination still works, the
+    // copies then stage through the driver's own pinned buffer and the copy stream runs behind)
+    L.h_particles_history = res->particles_history; L.h_weights_history = res->weights_history;
+    const size_t T1h = (size_t)T + 1;
+    if (res->particles_history) { pinned_ph = cudaHostRegister(res->particles_history, (size_t)C * T1h * d * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess; }
+    if (res->weights_history) { pinned_wh = cudaHostRegister(res->weights_history, (size_t)C * T1h * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess; }
+    cudaGetLastError();   // a refused registration is not an error of the call
+  }
   const bool need_aux = cfg->algorithm == BSSM_APF;
   const bool want_anc = res->ancestors_history != nullptr || res->ancestors_aux_history != nullptr;
   double* cdf;
@@ -630,10 +673,6 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   DL(res->loglike_history, f.loglike_history, (size_t)C * T, double);
   DL(res->ess, f.ess, (size_t)C * T1, double);
   DL(res->state_est, f.state_est, (size_t)C * T1 * d, double);
-  if (cfg->return_particles) {
-    DL(res->particles_history, f.particles_history, (size_t)C * T1 * d * N, double);
-    DL(res->weights_history, f.weights_history, (size_t)C * T1 * N, double);
-  }
   DL(res->status, f.status, (size_t)C, int);
   DL(res->early_exit, f.early_exit, (size_t)C, int);
   DL(res->n_resampled, f.n_resampled, (size_t)C, int);
@@ -642,7 +681,11 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
     if (need_aux) DL(res->ancestors_aux_history, f.anc_aux_history, (size_t)C * T * N, int);
   }
 #undef DL
-  BSSM_CK(cudaStreamSynchronize(st));
+  cudaError_t e_sync = cudaStreamSynchronize(st);
+  if (e_sync == cudaSuccess && cfg->return_particles && ctx->copy_stream) e_sync = cudaStreamSynchronize(ctx->copy_stream);
+  if (pinned_ph) cudaHostUnregister(res->particles_history);
+  if (pinned_wh) cudaHostUnregister(res->weights_history);
+  BSSM_CK(e_sync);
   BSSM_CK(cudaEventElapsedTime(&res->kernel_ms, ctx->ev0, ctx->ev1));
   return BSSM_OK;
 }

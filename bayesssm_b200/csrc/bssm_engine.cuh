@@ -72,6 +72,8 @@ struct bssm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;            // history rows travel on it (bssm_engine.cu: hist_row_out)
+  cudaEvent_t ev_row[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaDeviceProp prop;
   int64_t launches = 0;
   bssm::Scratch scratch[bssm::SL_COUNT];
@@ -115,6 +117,8 @@ struct RsArgs {
 // ---- batched filter runs (bssm_engine.cu), reused by the PMMH driver -----------------------------
 struct FilterLaunch {
   int model, precision, resample_fn, exact, hist, T, engine;
+  // return_particles: the caller's host buffers [C][T+1][d][N] / [C][T+1][N]; rows stream there while the filter runs
+  double *h_particles_history = nullptr, *h_weights_history = nullptr;
 };
 int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst);
 int resolve_engine(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L, bool injected, bool want_anc);

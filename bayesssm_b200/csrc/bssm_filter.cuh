@@ -43,8 +43,9 @@ struct FilterDev {
   double *ess;                 // [C][T+1]
   double *state_est;           // [C][T+1][d]
   double *loglike_history;     // [C][T] or nullptr
-  double *particles_history;   // [C][T+1][d][N] or nullptr
-  double *weights_history;     // [C][T+1][N] or nullptr
+  double *particles_history;   // [C][hist_rows][d][N] or nullptr
+  double *weights_history;     // [C][hist_rows][N] or nullptr
+  int hist_rows;               // rows the device history buffers hold: a ring of 2 (row r lives in slot r % 2 until it has been copied out)
   int *anc_history;            // [C][T][N] 1-based (tests) or nullptr
   int *anc_aux_history;        // [C][T][N] or nullptr
   int algorithm, ralg;
@@ -357,18 +358,28 @@ __global__ void __launch_bounds__(FT_THREADS) k_post(FilterDev f, int obs) {
 template <typename Real>
 __global__ void __launch_bounds__(FT_THREADS) k_history(FilterDev f, int row /* 0..T */) {
   int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
-  if (!f.alive[c]) return;
   int n = filt_n(f, c);
+  const size_t slot = (size_t)c * f.hist_rows + row % f.hist_rows;
+  if (!f.alive[c]) {
+    // a filter that has stopped (early exit, R/particle_filter_core.R:189-202: the remaining rows stay zero): the ring slot is
+    // copied out whatever happens, so it must not keep the row of two observations ago
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < f.N; i += gridDim.y * blockDim.x) {
+      if (f.particles_history) for (int k = 0; k < f.d; k++) f.particles_history[(slot * f.d + k) * f.N + i] = 0.0;
+      if (f.weights_history) f.weights_history[slot * f.N + i] = 0.0;
+    }
+    return;
+  }
   const Real* x = x_cur<Real>(f, c);
   const Real* lw = (const Real*)f.lw + (size_t)c * f.N;
   bool uniform = (row == 0) || f.resample[c];
   double M = f.M[c], S = f.S[c];
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < f.N; i += gridDim.y * blockDim.x) {
+    const bool on = i < n;   // ragged batches: the tail of a row beyond this filter's particles is zero
     if (f.particles_history)
       for (int k = 0; k < f.d; k++)
-        f.particles_history[(((size_t)c * (f.T + 1) + row) * f.d + k) * f.N + i] = (double)x[(size_t)k * f.N + i];
+        f.particles_history[(slot * f.d + k) * f.N + i] = on ? (double)x[(size_t)k * f.N + i] : 0.0;
     if (f.weights_history)
-      f.weights_history[((size_t)c * (f.T + 1) + row) * f.N + i] = uniform ? 1.0 / (double)n : exp((double)lw[i] - M) / S;
+      f.weights_history[slot * f.N + i] = !on ? 0.0 : (uniform ? 1.0 / (double)n : exp((double)lw[i] - M) / S);
   }
 }
 

@@ -140,3 +140,25 @@ def test_more_than_65535_filters_in_one_batch(engine):
                         engine=nat.ENGINE_GENERAL)
     assert (got["status"] == 0).all() and np.isfinite(got["loglike"]).all()
     assert len(np.unique(got["loglike"])) > 69000
+
+
+def test_histories_stream_through_a_two_row_ring(orc, engine):
+    # return_particles: the device holds two history rows at a time; rows travel to the caller's buffers on a copy stream while
+    # the filter runs (R/particle_filter_core.R:100-116,242-264).  A batch of three filters over 40 observations -- the ring
+    # wraps 20 times -- one of which stops early (its remaining rows stay zero, :189-202)
+    rng = np.random.default_rng(12)
+    T, N = 40, 3000
+    y = sim_y(AR, T, rng)
+    thetas = np.array([THETA[AR], [0.7, 1.1, 0.6], THETA[AR]])
+    got = eh.filter_run(engine, AR, 0, 2, 0, N, y, thetas, seed=8, precision=nat.F64, return_particles=True)
+    for c in range(3):
+        ref = orc.particle_filter(AR, 0, 2, 0, N, y, thetas[c], seed=8, stream=c, return_particles=True)
+        np.testing.assert_allclose(got["particles_history"][c], ref["particles_history"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(got["weights_history"][c], ref["weights_history"], rtol=1e-9, atol=1e-15)
+    y2 = y.copy()
+    y2[25] = 1e6                                  # every log-weight below -1e8 at observation 25 with sigma_y = 1e-3
+    th = [0.8, 1.0, 1e-3]
+    got = eh.filter_run(engine, AR, 0, 1, 0, 512, y2, th, seed=8, precision=nat.F64, return_particles=True)
+    assert got["early_exit"][0] == 1
+    ph, wh = got["particles_history"][0], got["weights_history"][0]
+    assert np.abs(ph[:26]).max() > 0 and not ph[26:].any() and not wh[26:].any()
