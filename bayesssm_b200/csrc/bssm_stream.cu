@@ -12,7 +12,6 @@ namespace bssm {
 
 bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L) {
   if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history) return false;
-  if (L.resample_fn == BSSM_MULTINOMIAL) return false;
   if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC user model: its shape decides (bssm_nvrtc.cu)
     const UserModelInfo* u = user_model(ctx, L.model);
     return u && u->stream_ok;
@@ -101,6 +100,15 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 8, (size_t)C, &P.rec_local));
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, (size_t)C * sh->world, &P.rec_all));
   }
+  const bool mn = L.resample_fn == BSSM_MULTINOMIAL;
+  if (mn) {
+    if (sh) { set_error("streaming engine: multinomial resampling is not available for the particle-sharded filter"); return BSSM_ERR_UNSUPPORTED; }
+    // sorted uniforms from exponential spacings (bssm_stream.cuh): positions of the output slots + the scan of the spacings
+    P.mn_nt = (cap + 1 + MN_TILE - 1) / MN_TILE + 1;
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.xstride, &P.mn_pos));
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 8, (size_t)C * P.mn_nt, &P.mn_tsum));
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, (size_t)C, &P.mn_total));
+  }
   P.dbg = nullptr;
   if (getenv("BSSM_ST_TIMING")) {
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 11, (size_t)8, &P.dbg));
@@ -128,7 +136,16 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample", pdl));
+      if (mn) {   // the positions of this observation's output slots (the kernels return at once for filters that do not resample)
+        const dim3 gmn((unsigned int)C, (unsigned int)P.mn_nt);
+        k_st_mn_sums<<<gmn, MN_THREADS, 0, st>>>(P, obs);
+        BSSM_LAUNCH(ctx, "k_st_mn_sums");
+        k_st_mn_scan<<<C, MN_THREADS, 0, st>>>(P, obs);
+        BSSM_LAUNCH(ctx, "k_st_mn_scan");
+        k_st_mn_positions<<<gmn, MN_THREADS, 0, st>>>(P, obs);
+        BSSM_LAUNCH(ctx, "k_st_mn_positions");
+      }
+      BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample", pdl && !mn));
     }
   }
   if (P.dbg) {

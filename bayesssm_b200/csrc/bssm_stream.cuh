@@ -75,6 +75,11 @@ struct StreamParams {
   int bpc;                 // blocks per filter (k_st_init, k_st_step and k_st_resample share the block -> tile ranges)
   double log_n;            // log(particle count) when every filter has the same count (else NaN: computed on the device)
   long long* dbg;          // optional [8] clock64 stamps of the merging block (BSSM_ST_TIMING, diagnostics)
+  // multinomial resampling (resample_fn == 2): sorted uniforms from exponential spacings
+  double* mn_pos;          // [C][xstride] positions of the output slots: U_(0) < U_(1) < ... (order statistics of n uniforms)
+  double* mn_tsum;         // [C][mn_nt] sums of the spacings of 1024 slots; after the scan: their exclusive prefix
+  double* mn_total;        // [C] sum of all n + 1 spacings
+  int mn_nt;               // 1024-slot tiles of spacings per filter row
 };
 
 // explicitly rounded a + p * g: the same boundary value in every tile / rank that evaluates it
@@ -549,6 +554,123 @@ static __global__ void k_st_merge(StreamParams P, int obs) {
 }
 
 // ---- K_B: resampling (scan + closed-form offspring ranges + staged scatter) ----
+// ---- multinomial resampling (src/resampling.cpp:5-13) on the streaming engine ------------------------------------------
+// n iid uniforms, sorted, are the normalised partial sums of n + 1 iid Exp(1) spacings: U_(i) = (E_0 + .. + E_i) / (E_0 + .. + E_n),
+// E_k = -log(U_k), U_k the Philox word of slot k.  The positions arrive in increasing order, so the input-centric expansion of
+// k_st_resample serves them like the stratified ones: source j owns the slots [F(c_{j-1}), F(c_j)), F(c) = #{ i : U_(i) <= c } --
+// a count found in the staged positions instead of in closed form.  Same law as Rcpp::sample's draws (offspring counts
+// ~ Multinomial(n, p)); the ancestors come out sorted (oracle: orc_resample_multinomial_sorted).
+// Three small kernels per resampling step: tile sums of the spacings, their scan, the positions.  Fixed reduction trees: the
+// positions do not depend on the launch geometry.
+constexpr int MN_THREADS = 256, MN_TILE = 1024;
+__device__ __forceinline__ void st_mn_spacings(const NoiseKey& key, unsigned int obs, int i0, int n, double* e /*4*/) {
+  const uint4x q = noise_quad(key, obs, TAG_RESAMP_U, 0u, (unsigned int)i0 >> 2);
+#pragma unroll
+  for (int k = 0; k < 4; k++) e[k] = (i0 + k <= n) ? -log(word_to_unit_f64(q.w[k])) : 0.0;   // slots 0 .. n: n + 1 spacings
+}
+// block-wide sum in a fixed order (warp trees, then the warps one after the other); valid in every thread
+__device__ __forceinline__ double st_mn_block_sum(double v, double* s_w /*[MN_THREADS / 32]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) s_w[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < MN_THREADS / 32; w++) t += s_w[w];
+  return t;
+}
+static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_sums(StreamParams P, int obs) {
+  __shared__ double s_w[MN_THREADS / 32];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x, tile = blockIdx.y;
+  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  const int n = filt_n(f, c);
+  if ((long long)tile * MN_TILE > n) return;
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  double e[4];
+  st_mn_spacings(key, (unsigned int)obs, tile * MN_TILE + 4 * threadIdx.x, n, e);
+  const double t = st_mn_block_sum((e[0] + e[1]) + (e[2] + e[3]), s_w);
+  if (threadIdx.x == 0) P.mn_tsum[(size_t)c * P.mn_nt + tile] = t;
+}
+// exclusive prefix of a filter's tile sums (in place) and their total: one block per filter, 256 tiles per round
+static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_scan(StreamParams P, int obs) {
+  __shared__ double s_w[MN_THREADS / 32];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  const int n = filt_n(f, c);
+  const int ntile = n / MN_TILE + 1;          // tiles that hold one of the slots 0 .. n
+  double* ts = P.mn_tsum + (size_t)c * P.mn_nt;
+  double carry = 0.0;
+  for (int b0 = 0; b0 < ntile; b0 += MN_THREADS) {
+    const int t = b0 + tid;
+    const double v = t < ntile ? ts[t] : 0.0;
+    const double inc = warp_incl_scan_d(v, lane);
+    __syncthreads();
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    double woff = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < MN_THREADS / 32; w++) { if (w == wid) woff = tot; tot += s_w[w]; }
+    if (t < ntile) ts[t] = carry + (woff + (inc - v));
+    carry += tot;
+  }
+  if (tid == 0) P.mn_total[c] = carry;
+}
+static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_positions(StreamParams P, int obs) {
+  __shared__ double s_w[MN_THREADS / 32];
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  const int n = filt_n(f, c);
+  if ((long long)tile * MN_TILE >= n) return;
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int i0 = tile * MN_TILE + 4 * tid;
+  double e[4];
+  st_mn_spacings(key, (unsigned int)obs, i0, n, e);
+  const double run = (e[0] + e[1]) + (e[2] + e[3]);       // the association k_st_mn_sums used
+  const double inc = warp_incl_scan_d(run, lane);
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  double woff = 0.0;
+#pragma unroll
+  for (int w = 0; w < MN_THREADS / 32; w++) if (w < wid) woff += s_w[w];
+  double cum = P.mn_tsum[(size_t)c * P.mn_nt + tile] + (woff + (inc - run));
+  const double total = P.mn_total[c];
+  double* pos = P.mn_pos + (size_t)c * P.xstride;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    cum += e[k];
+    if (i0 + k < n) pos[i0 + k] = cum / total;
+  }
+}
+// #{ i < n : pos[i] <= c }, by one warp: a window around c n (the order statistics stay within a few sqrt(n) slots of the
+// diagonal), widened until it brackets the answer, then narrowed 32 ways per round
+__device__ __forceinline__ int st_mn_count(const double* __restrict__ pos, int n, double c, int lane) {
+  if (!(c > 0.0)) return 0;
+  if (c >= 1.0) return n;
+  const int g = (int)(c * (double)n);
+  int w = (int)(4.0 * sqrt((double)n)) + 64;
+  int lo, hi;
+  for (;;) {
+    lo = max(0, g - w); hi = min(n, g + w);
+    const bool ok_lo = lo == 0 || pos[lo - 1] <= c, ok_hi = hi == n || pos[hi] > c;   // answer in [lo, hi]
+    if (ok_lo && ok_hi) break;
+    w *= 4;
+  }
+  while (hi - lo > 32) {
+    const int stp = (hi - lo + 31) / 32;
+    const int idx = lo + (lane + 1) * stp - 1;
+    const bool le = idx < hi && pos[idx] <= c;
+    const int k = __popc(__ballot_sync(0xffffffffu, le));
+    lo += k * stp;
+    hi = min(hi, lo + stp);
+  }
+  const bool le = lo + lane < hi && pos[lo + lane] <= c;
+  return lo + __popc(__ballot_sync(0xffffffffu, le));
+}
+
 // Same block -> tile ranges and prefetch as k_st_step.  A block's cdf interval comes from the block prefix
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
 // running sums of the tile totals it computes itself (clamped into the block's interval).
@@ -562,9 +684,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
   static_assert(CAP % ST_THREADS == 0 && SPT % 2 == 0, "staging capacity: whole, even number of slots per thread");
   // one buffer, two lives: the staged stratified uniforms (raw Philox words) of the tile while the offspring
   // ranges are computed, then the staged outputs of a chunk
-  __shared__ __align__(16) unsigned char s_uo[CAP * (sizeof(Real) > 4 ? sizeof(Real) : 4)];
+  __shared__ __align__(16) unsigned char s_uo[CAP * 8];    // (multinomial: the staged positions, doubles)
   unsigned int* const s_u = (unsigned int*)s_uo;
+  double* const s_p = (double*)s_uo;
   Real* const s_out = (Real*)s_uo;
+  __shared__ int s_mn[2];
   __shared__ __align__(16) unsigned int s_head[CAP];       // expansion: (source index << 16 | address of its x) at the first slot of a source
   __shared__ uint4 s_pf[2][2 * ST_THREADS];
   __shared__ double s_red[ST_NW], s_bs[ST_NW];
@@ -667,23 +791,71 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamP
     const int i0 = t0 >= (double)n ? n : (int)t0;
     sc.u_base = max(0, (i0 & ~3) - 4);
   }
-  if (P.resample_fn == 1) {
-    uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
-    sc.w_sys = q0.w[0];
-  } else {
-    const int q_end = min((n + 3) >> 2, (sc.u_base + CAP) >> 2);
-    for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += ST_THREADS) {
-      uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
-      *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+  const bool MN = P.resample_fn == 2;
+  const double* const mpos = P.mn_pos + (size_t)c * P.xstride;   // multinomial: the sorted positions of the output slots
+  int o_lo, o_hi, mn_cnt = 0;
+  if (MN) {
+    // output range of the tile: counts of positions below its cdf interval's ends (warp 0; the neighbouring tile / block
+    // counts against the same value), then the positions of that range into shared memory
+    if (wid == 0) {
+      const int a = st_mn_count(mpos, n, lo_cdf, lane);
+      const int z = tail ? n : st_mn_count(mpos, n, hi_cdf, lane);
+      if (lane == 0) { s_mn[0] = a; s_mn[1] = z; }
     }
+    __syncthreads();
+    o_lo = s_mn[0]; o_hi = max(s_mn[1], o_lo);
+    mn_cnt = min(o_hi - o_lo, CAP);
+    for (int i = tid; i < mn_cnt; i += ST_THREADS) s_p[i] = mpos[o_lo + i];
+    __syncthreads();
+  } else {
+    if (P.resample_fn == 1) {
+      uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
+      sc.w_sys = q0.w[0];
+    } else {
+      const int q_end = min((n + 3) >> 2, (sc.u_base + CAP) >> 2);
+      for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += ST_THREADS) {
+        uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+        *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
+      }
+    }
+    __syncthreads();
+    o_lo = sc.count_le(lo_cdf);
+    o_hi = tail ? n : sc.count_le(hi_cdf);
   }
-  __syncthreads();
-  const int o_lo = sc.count_le(lo_cdf);
-  const int o_hi = tail ? n : sc.count_le(hi_cdf);
   int F[PPT];
   {
     int fmax = o_lo;
-    if (F32) {
+    if (MN) {
+      // F(c) = o_lo + #{ staged positions <= c }: a binary search for the thread's first particle, a short walk for the next ones
+      // (the positions grow with k); beyond the staged window (more than CAP offspring in the tile) a search in global memory
+      double acc = exu;
+      int j = 0;
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        acc += (double)e[k];
+        int v = o_lo;
+        if (k >= k_lo && k < k_hi) {
+          const double ck = lo_cdf + acc * wscale;
+          if (k == k_lo) {
+            int lo = 0, hi = mn_cnt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_p[mid] <= ck) lo = mid + 1; else hi = mid; }
+            j = lo;
+          } else {
+            while (j < mn_cnt && s_p[j] <= ck) j++;
+          }
+          v = o_lo + j;
+          if (j == mn_cnt && o_hi - o_lo > mn_cnt) {
+            int lo = o_lo + mn_cnt, hi = o_hi;
+            while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (mpos[mid] <= ck) lo = mid + 1; else hi = mid; }
+            v = lo;
+          }
+          if (tid * PPT + k == last_s) v = o_hi;
+          v = min(max(v, o_lo), o_hi);
+        }
+        fmax = max(fmax, v);
+        F[k] = fmax;
+      }
+    } else if (F32) {
       const double T0 = (lo_cdf + exu * wscale) * (double)n;
       const double T0c = T0 < (double)n ? T0 : (double)n;
       const int I0 = (int)T0c;

@@ -109,6 +109,28 @@ int orc_resample_multinomial_invcdf(int n, const double *w, const double *u, int
   return st;
 }
 
+/* Multinomial resampling by SORTED uniforms: the order statistics of n iid uniforms are the normalised partial sums of n + 1
+ * iid Exp(1) spacings, U_(i) = (E_0 + ... + E_i) / (E_0 + ... + E_n), E_k = -log(u[k]) -- so the n draws arrive in increasing
+ * order and the two-pointer search of src/resampling.cpp:32-37 serves them like the stratified positions.  Same law as
+ * src/resampling.cpp:5-13 (offspring counts ~ Multinomial(n, p)); the ancestors come out sorted, where Rcpp::sample returns
+ * them in draw order -- for a particle filter only the multiset matters.  This is what the streaming engine's multinomial
+ * path is checked against (u: n + 1 uniforms). */
+int orc_resample_multinomial_sorted(int n, const double *w, const double *u, int32_t *idx1) {
+  double *cdf = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  double *pos = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  int st = orc_resample_cdf(n, w, cdf, NULL);
+  if (st == ORC_OK) {
+    double total = 0.0;
+    for (int i = 0; i <= n; i++) total += -log(u[i]);
+    double run = 0.0;
+    for (int i = 0; i < n; i++) { run += -log(u[i]); pos[i] = run / total; }
+    search_positions(n, cdf, pos, idx1);
+  }
+  free(cdf);
+  free(pos);
+  return st;
+}
+
 /* src/resampling.cpp:5-13 -> Rcpp::sample(n, n, true, prob).  Rcpp (unpinned,
  * DESCRIPTION:28) is absent from the reference tree; its published algorithm
  * (Rcpp/sugar/functions/sample.h, mirroring R's src/main/random.c) is:
@@ -439,10 +461,14 @@ static int do_resample(const fctx *f, const double *weights, int obs_i, int aux,
     double u = get_u(f, buf, 1, tag, (uint32_t)obs_i, obs_i, 0, 0);
     st = orc_resample_systematic(N, weights, u, anc1);
   } else {
-    double *u = (double *)malloc(sizeof(double) * (size_t)N);
-    for (int i = 0; i < N; i++) u[i] = get_u(f, buf, 1, tag, (uint32_t)obs_i, obs_i, 0, i);
+    /* ORC_MULTINOMIAL_SORTED consumes one uniform more (n + 1 spacings): Philox mode only (the injected buffers hold N per step) */
+    const int sorted = f->cfg->resample_fn == ORC_MULTINOMIAL_SORTED;
+    if (sorted && buf) return ORC_ERR_BAD_ARG;
+    const int nu = sorted ? N + 1 : N;
+    double *u = (double *)malloc(sizeof(double) * (size_t)nu);
+    for (int i = 0; i < nu; i++) u[i] = get_u(f, buf, 1, tag, (uint32_t)obs_i, obs_i, 0, i);
     st = (f->cfg->resample_fn == ORC_STRATIFIED) ? orc_resample_stratified(N, weights, u, anc1)
-                                                 : orc_resample_multinomial_invcdf(N, weights, u, anc1);
+         : (sorted ? orc_resample_multinomial_sorted(N, weights, u, anc1) : orc_resample_multinomial_invcdf(N, weights, u, anc1));
     free(u);
   }
   return st;

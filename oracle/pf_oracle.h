@@ -33,7 +33,7 @@ extern "C" {
 /* enums shared (by value) with include/bayesssm_b200.h */
 enum { ORC_BPF = 0, ORC_APF = 1, ORC_RMPF = 2 };
 enum { ORC_SIS = 0, ORC_SISR = 1, ORC_SISAR = 2 };
-enum { ORC_STRATIFIED = 0, ORC_SYSTEMATIC = 1, ORC_MULTINOMIAL = 2 };
+enum { ORC_STRATIFIED = 0, ORC_SYSTEMATIC = 1, ORC_MULTINOMIAL = 2, ORC_MULTINOMIAL_SORTED = 3 /* filters only: sorted uniforms, see orc_resample_multinomial_sorted */ };
 enum {
   ORC_MODEL_AR_SIN = 0,  /* README.md:137-146 */
   ORC_MODEL_LG = 1,      /* tests/testthat/test-pmmh_tuning.R:163-173 (generalised sigmas) */
@@ -48,7 +48,9 @@ enum { ORC_TR_IDENTITY = 0, ORC_TR_LOG = 1, ORC_TR_LOGIT = 2 };
 /* ---- resamplers: src/resampling.cpp:5-66 (uniforms injected) ---- */
 int orc_resample_stratified(int n, const double *w, const double *u, int32_t *idx1);
 int orc_resample_systematic(int n, const double *w, double u, int32_t *idx1);
-/* natural-order inverse-CDF multinomial (what the CUDA path is bit-exact against) */
+/* multinomial by sorted uniforms from n + 1 exponential spacings (what the streaming engine runs); u: n + 1 uniforms */
+int orc_resample_multinomial_sorted(int n, const double *w, const double *u, int32_t *idx1);
+/* natural-order inverse-CDF multinomial (what the general kernels are bit-exact against) */
 int orc_resample_multinomial_invcdf(int n, const double *w, const double *u, int32_t *idx1);
 /* Rcpp::sample(n, n, TRUE, p) restated (Walker alias / sorted inverse CDF), distributional pin only */
 int orc_resample_multinomial_rcpp(int n, const double *w, const double *u, int32_t *idx1);

@@ -20,7 +20,7 @@ using namespace bssm;
 struct Rank {
   StreamParams P;
   std::vector<unsigned char> x0, x1;
-  std::vector<double> pref, bsum, blk, M, S, loglike, ess, state_est, llh;
+  std::vector<double> pref, bsum, blk, M, S, loglike, ess, state_est, llh, mn_pos, mn_tsum, mn_total;
   std::vector<unsigned int> counter;
   std::vector<int> res, alive, status, early, nres;
   std::vector<StSeg> seg;
@@ -95,6 +95,11 @@ static int run(int argc, char** argv) {
     R.rec_local.resize(C); R.rec_all.resize((size_t)C * world);
     P.rec_local = R.rec_local.data(); P.rec_all = R.rec_all.data();
     P.dbg = nullptr;
+    if (rfn == 2) {   // multinomial: positions of the output slots + the scan of the spacings (stream_launch, bssm_stream.cu)
+      P.mn_nt = (cap + 1 + MN_TILE - 1) / MN_TILE + 1;
+      R.mn_pos.assign((size_t)C * P.xstride, -1.0); R.mn_tsum.assign((size_t)C * P.mn_nt, -1.0); R.mn_total.assign(C, -1.0);
+      P.mn_pos = R.mn_pos.data(); P.mn_tsum = R.mn_tsum.data(); P.mn_total = R.mn_total.data();
+    }
   }
   std::mt19937 shuf(12345);
   auto block_order = [&](unsigned int grid) {
@@ -129,6 +134,11 @@ static int run(int argc, char** argv) {
       for (int g = 0; g < world; g++) {
         const StreamParams P = ranks[g].P;
         const auto o = block_order((unsigned int)P.bpc * C);
+        if (rfn == 2) {
+          emu_launch2d((unsigned int)C, (unsigned int)P.mn_nt, MN_THREADS, [&] { k_st_mn_sums(P, obs); });
+          emu_launch((unsigned int)C, MN_THREADS, [&] { k_st_mn_scan(P, obs); });
+          emu_launch2d((unsigned int)C, (unsigned int)P.mn_nt, MN_THREADS, [&] { k_st_mn_positions(P, obs); });
+        }
         emu_launch((unsigned int)P.bpc * C, THREADS, [&] { k_st_resample<Model, Real, PPT, THREADS>(P, obs); }, &o);
       }
     }

@@ -139,6 +139,17 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int o) {
   return emu_shfl(v, lane + o < 32 ? lane + o : lane);
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_wait(emu_block->wbar[threadIdx.x >> 5]); }
+static inline unsigned int __ballot_sync(unsigned, int pred) {
+  EmuBlock& B = *emu_block;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  B.xch[(size_t)w * 32 + lane] = pred ? 1u : 0u;
+  emu_wait(B.wbar[w]);
+  unsigned int m = 0;
+  for (int l = 0; l < B.wbar[w].expected; l++) if (B.xch[(size_t)w * 32 + l]) m |= 1u << l;
+  emu_wait(B.wbar[w]);
+  return m;
+}
+static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
 static inline int __reduce_max_sync(unsigned, int v) {
   EmuBlock& B = *emu_block;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;

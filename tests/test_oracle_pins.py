@@ -177,3 +177,38 @@ def test_pmmh_latent_state_chain_travels_with_the_draws(orc):
         assert ref["loglike"] == r["loglike_chain"][i]
         moved += 1
     assert moved == r["n_accept"] + 1 and stayed > 0
+
+
+def test_multinomial_by_sorted_uniforms_has_the_multinomial_law(orc):
+    # orc_resample_multinomial_sorted (what the streaming engine's multinomial path is checked against): same offspring
+    # proportions as the reference's test asks of resample_multinomial_cpp (tests/testthat/test-resampling.R:29-47), sorted
+    # ancestors, degenerate weights (:190-202), and the reference's error strings through the shared cdf (:2-28)
+    import ctypes as C
+    L = orc.lib()
+    L.orc_resample_multinomial_sorted.restype = C.c_int
+    rng = np.random.default_rng(1405)
+    w = np.array([0.1, 0.5, 0.1, 0.15, 0.15])
+    counts = np.zeros(5)
+    for _ in range(10000):
+        u = np.ascontiguousarray(rng.random(6))
+        idx = np.zeros(5, dtype=np.int32)
+        assert L.orc_resample_multinomial_sorted(5, w.ctypes.data_as(C.POINTER(C.c_double)), u.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 idx.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        assert (np.diff(idx) >= 0).all() and idx.min() >= 1 and idx.max() <= 5
+        counts += np.bincount(idx - 1, minlength=5)
+    assert np.abs(counts / counts.sum() - w).max() < 0.05 / 4
+    # variance of one offspring count: n p (1 - p) (a stratified scheme would have far less)
+    n, reps, p = 200, 4000, 0.3
+    w2 = np.r_[p, np.full(n - 1, (1 - p) / (n - 1))]
+    c0 = np.empty(reps)
+    for r in range(reps):
+        u = np.ascontiguousarray(rng.random(n + 1))
+        idx = np.zeros(n, dtype=np.int32)
+        L.orc_resample_multinomial_sorted(n, w2.ctypes.data_as(C.POINTER(C.c_double)), u.ctypes.data_as(C.POINTER(C.c_double)), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+        c0[r] = (idx == 1).sum()
+    assert abs(c0.mean() - n * p) < 0.5 and abs(c0.var() / (n * p * (1 - p)) - 1) < 0.1
+    w3 = np.array([0.0, 0.0, 1.0, 0.0, 0.0])
+    idx = np.zeros(5, dtype=np.int32)
+    u = np.ascontiguousarray(rng.random(6))
+    L.orc_resample_multinomial_sorted(5, w3.ctypes.data_as(C.POINTER(C.c_double)), u.ctypes.data_as(C.POINTER(C.c_double)), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert (idx == 3).all()

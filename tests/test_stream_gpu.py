@@ -194,3 +194,30 @@ def test_big_single_filters_f32_against_kalman(orc, engine):
     se = lls.std(ddof=1) / np.sqrt(len(lls))
     assert abs(lls.mean() - exact) < 3 * se + 5e-3, (lls, exact)
     assert lls.std(ddof=1) < 0.05
+
+
+# multinomial resampling on the streaming engine (sorted uniforms from exponential spacings; oracle resample_fn = 3)
+@pytest.mark.parametrize("N,T,ralg", [(1000, 20, 2), (4097, 12, 1), (70001, 10, 2), (1 << 17, 6, 1)])
+def test_multinomial_f64_matches_oracle(orc, engine, N, T, ralg):
+    y = sim_y(AR, T, np.random.default_rng(N))
+    ref = orc.particle_filter(AR, 0, ralg, 3, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    got = eh.filter_run(engine, AR, 0, ralg, 2, N, y, THETA[AR], seed=1405, run_id=2, stream_base=3,
+                        precision=nat.F64, engine=nat.ENGINE_STREAM)
+    assert got["status"][0] == 0 and got["n_resampled"][0] == ref["n_resampled"]
+    assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"])      # north-star tolerance
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-6)
+    np.testing.assert_allclose(got["state_est"][0][:, 0], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+
+
+def test_multinomial_f32_batched_against_kalman_and_auto_engine(orc, engine):
+    y = sim_y(LG, 200, np.random.default_rng(7))
+    exact = orc.kalman_loglik(y, 0.8, 1.0, 1.0)
+    got = eh.filter_run(engine, LG, 0, 1, 2, 1 << 14, y, THETA[LG], seed=11, num_filters=64, precision=nat.F32, engine=nat.ENGINE_AUTO)
+    assert (got["status"] == 0).all()
+    lls = got["loglike"]
+    est = np.log(np.mean(np.exp(lls - lls.max()))) + lls.max()
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(est - exact) < 3 * se + 0.01, (est, exact, se)
+    # AUTO took the streaming engine: the same numbers when it is asked for by name
+    again = eh.filter_run(engine, LG, 0, 1, 2, 1 << 14, y, THETA[LG], seed=11, num_filters=64, precision=nat.F32, engine=nat.ENGINE_STREAM)
+    np.testing.assert_array_equal(again["loglike"], lls)

@@ -188,3 +188,27 @@ def test_observation_times_with_gaps(orc, host_stream):
     ref = orc.particle_filter(AR, 0, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3)
     for rec in host_stream(AR, 2048, y, [THETA[AR]], seed=3, run_id=0, stream_base=0, world=2, capacity_factor=2.0, block_order=1, obs_times=ot):
         check(rec, ref)
+
+
+# multinomial resampling on the streaming engine: sorted uniforms from exponential spacings (k_st_mn_sums / _scan / _positions),
+# offspring ranges counted in the staged positions.  Oracle: orc_resample_multinomial_sorted inside the Philox-mode filter
+# (resample_fn = 3).  Sizes around the tile edges, several blocks per filter, a batch, degenerate weights (several chunks)
+@pytest.mark.parametrize("N,T,threads,bpc,ralg", [(1, 4, 128, 1, 1), (37, 6, 128, 1, 1), (1024, 6, 256, 1, 2), (1025, 6, 128, 2, 1),
+                                                  (5000, 8, 128, 3, 2), (20011, 5, 256, 4, 1)])
+def test_multinomial_by_sorted_uniforms_matches_the_oracle(orc, host_stream, N, T, threads, bpc, ralg):
+    y = sim_y(AR, T, np.random.default_rng(N))
+    ref = orc.particle_filter(AR, 0, ralg, 3, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    rec, = host_stream(AR, N, y, [THETA[AR]], threads=threads, bpc=bpc, resample_fn=2, resample_algorithm=ralg)
+    check(rec, ref)
+
+
+def test_multinomial_batch_degenerate_weights_and_f32(orc, host_stream):
+    y = sim_y(AR, 5, np.random.default_rng(8))
+    thetas = [THETA[AR], [0.8, 1.0, 2e-3], [0.6, 1.2, 0.7]]      # the second filter: a few particles take everything
+    recs = host_stream(AR, 6000, y, thetas, threads=128, bpc=2, resample_fn=2, resample_algorithm=1, seed=4, run_id=0, stream_base=0)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 1, 3, 6000, y, thetas[c], seed=4, stream=c))
+    rec, = host_stream(AR, 20000, y, [THETA[AR]], precision=32, threads=128, bpc=3, resample_fn=2, resample_algorithm=2)
+    ref = orc.particle_filter(AR, 0, 2, 3, 20000, y, THETA[AR], seed=1405, run_id=2, stream=3)
+    assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
+    assert abs(rec["loglike"] - ref["loglike"]) < 2e-2 and np.abs(rec["state_est"] - ref["state_est"][:, 0]).max() < 2e-2
