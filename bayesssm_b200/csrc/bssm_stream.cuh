@@ -407,7 +407,7 @@ inline void st_pdl_wait() {}
 // are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
 // the parameter set-up and the fence + ticket once, not once per tile.
 template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(StreamParams P, int obs) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(const __grid_constant__ StreamParams P, int obs) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   // serves 1-D models with one normal per init / transition and no uniforms; checked on the host (stream_supported),
   // because NVRTC instantiates these kernels for every user model whatever its shape
@@ -675,7 +675,7 @@ __device__ __forceinline__ int st_mn_count(const double* __restrict__ pos, int n
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
 // running sums of the tile totals it computes itself (clamped into the block's interval).
 template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(StreamParams P, int obs) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const __grid_constant__ StreamParams P, int obs) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;

@@ -32,16 +32,16 @@ prog = '#include "bssm_filter.cuh"\n#include "bssm_stream.cuh"\nnamespace bssm {
 namespace bssm {
 template __global__ void k_st_init<UserModel, float, 8, 256>(StreamParams);
 template __global__ void k_st_init<UserModel, double, 4, 256>(StreamParams);
-template __global__ void k_st_step<UserModel, float, 8, 256>(StreamParams, int);
-template __global__ void k_st_step<UserModel, double, 4, 256>(StreamParams, int);
-template __global__ void k_st_resample<UserModel, float, 8, 256>(StreamParams, int);
-template __global__ void k_st_resample<UserModel, double, 4, 256>(StreamParams, int);
+template __global__ void k_st_step<UserModel, float, 8, 256>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_step<UserModel, double, 4, 256>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_resample<UserModel, float, 8, 256>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_resample<UserModel, double, 4, 256>(const __grid_constant__ StreamParams, int);
 template __global__ void k_st_init<UserModel, float, 8, 128>(StreamParams);
 template __global__ void k_st_init<UserModel, double, 4, 128>(StreamParams);
-template __global__ void k_st_step<UserModel, float, 8, 128>(StreamParams, int);
-template __global__ void k_st_step<UserModel, double, 4, 128>(StreamParams, int);
-template __global__ void k_st_resample<UserModel, float, 8, 128>(StreamParams, int);
-template __global__ void k_st_resample<UserModel, double, 4, 128>(StreamParams, int);
+template __global__ void k_st_step<UserModel, float, 8, 128>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_step<UserModel, double, 4, 128>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_resample<UserModel, float, 8, 128>(const __grid_constant__ StreamParams, int);
+template __global__ void k_st_resample<UserModel, double, 4, 128>(const __grid_constant__ StreamParams, int);
 template __global__ void k_init<UserModel, float>(FilterDev);
 template __global__ void k_init<UserModel, double>(FilterDev);
 template __global__ void k_weight<UserModel, float>(FilterDev, int, int, int);

@@ -35,6 +35,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
+#define __grid_constant__
 #define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
