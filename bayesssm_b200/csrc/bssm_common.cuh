@@ -75,25 +75,35 @@ template <> struct Math<double> {
   static BSSM_DEV double sin_(double x) { return sin(x); }
   static BSSM_DEV double cos_(double x) { return cos(x); }
   static BSSM_DEV double div_(double a, double b) { return a / b; }
+  static BSSM_DEV double max_(double a, double b) { return b > a ? b : a; }
   static BSSM_DEV double ninf() { return -__longlong_as_double(0x7FF0000000000000LL); }
 };
 template <> struct Math<float> {
   // Throughput precision.  Uniforms come from the top 23 bits of a Philox word by bit assembly
   // (no int->float conversion on the XU pipe), logarithm / square root / sine / cosine / exp on the SFU.
-  static BSSM_DEV float unit(uint32_t w) { return (__uint_as_float(0x3F800000u | (w >> 9)) - 1.0f) + 5.9604645e-8f; }  // (0, 1)
+  // (k + 0.5) * 2^-23 for the 23-bit k = w >> 9: one exact subtraction (1 + k 2^-23) - (1 - 2^-24)
+  static BSSM_DEV float unit(uint32_t w) { return __uint_as_float(0x3F800000u | (w >> 9)) - 0.99999994f; }  // (0, 1)
+  // SFU instructions in their flush-to-zero form: the default forms wrap every MUFU in a denormal test and two predicated
+  // multiplies (issue slots, taken or not); no quantity here is a denormal that matters (weights below 2^-126 of the maximum)
 #ifndef BSSM_EMU
   static BSSM_DEV float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static BSSM_DEV float ex2_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static BSSM_DEV float lg2_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static BSSM_DEV float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else   // CPU logic test (tests/simt_emu.h)
   static BSSM_DEV float sqrt_approx(float x) { return sqrtf(x); }
+  static BSSM_DEV float ex2_(float x) { return exp2f(x); }
+  static BSSM_DEV float lg2_(float x) { return log2f(x); }
+  static BSSM_DEV float rcp_(float x) { return 1.0f / x; }
 #endif
   static BSSM_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     float u1 = unit(a), u2 = unit(b);
-    float r = sqrt_approx(-2.0f * __logf(u1));
+    float r = sqrt_approx(-1.3862943611198906f * lg2_(u1));   // sqrt(-2 ln u1)
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);  // argument in (0, 2pi): the SFU path is accurate to ~1e-6 here
     n0 = r * c; n1 = r * s;
   }
-  static BSSM_DEV float exp_(float x) { return __expf(x); }
+  static BSSM_DEV float exp_(float x) { return ex2_(x * 1.4426950408889634f); }
   static BSSM_DEV float log_(float x) { return logf(x); }
   // reduce to [-pi, pi] with a two-term 2*pi (round-to-nearest by the 1.5*2^23 trick), then the SFU (abs. error < 1e-6)
   static BSSM_DEV float reduce_2pi(float x) {
@@ -103,7 +113,8 @@ template <> struct Math<float> {
   }
   static BSSM_DEV float sin_(float x) { return __sinf(reduce_2pi(x)); }
   static BSSM_DEV float cos_(float x) { return __cosf(reduce_2pi(x)); }
-  static BSSM_DEV float div_(float a, float b) { return __fdividef(a, b); }
+  static BSSM_DEV float div_(float a, float b) { return a * rcp_(b); }
+  static BSSM_DEV float max_(float a, float b) { return fmaxf(a, b); }   // a NaN operand never wins, like (b > a ? b : a) for a finite a
   static BSSM_DEV float ninf() { return -__int_as_float(0x7F800000); }
 };
 
@@ -111,6 +122,11 @@ template <> struct Math<float> {
 template <typename Real> BSSM_DEV Real dnorm_log(Real x, Real mu, Real sigma, Real log_sigma) {
   Real z = Math<Real>::div_(x - mu, sigma);
   return -((Real)0.918938533204672741780329736406 + (Real)0.5 * z * z + log_sigma);
+}
+// throughput precision: the same value as two operations on the reciprocal (hoisted out of particle loops by the compiler)
+template <> BSSM_DEV float dnorm_log<float>(float x, float mu, float sigma, float log_sigma) {
+  const float z = (x - mu) * Math<float>::rcp_(sigma);
+  return fmaf(z, -0.5f * z, -(0.918938533204672741780329736406f + log_sigma));
 }
 template <typename Real> BSSM_DEV Real dpois_log(Real y, Real lambda) {
   if (lambda == (Real)0) return (y == (Real)0) ? (Real)0 : Math<Real>::ninf();

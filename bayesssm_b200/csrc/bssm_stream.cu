@@ -50,6 +50,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   StreamParams P;
   memset(&P, 0, sizeof(P));
   P.f = f; P.resample_fn = L.resample_fn;
+  st_fill_round_keys(P);
   const int C = f.C;
   long long goff0 = 0; int nloc0 = f.N; int cap = f.N;
   if (sh) {

@@ -55,6 +55,13 @@ struct StSeg {
 
 struct StRec { double m, s, q, sx, pend, nan, pad0, pad1; };   // per-rank record (sharded runs)
 
+// resident threads per SM the two hot kernels are compiled for (register budget = 65536 / this)
+#ifndef BSSM_ST_OCC_STEP
+#define BSSM_ST_OCC_STEP 1024
+#endif
+#ifndef BSSM_ST_OCC_RES
+#define BSSM_ST_OCC_RES 1024
+#endif
 struct StreamParams {
   FilterDev f;
   int resample_fn;
@@ -80,7 +87,32 @@ struct StreamParams {
   double* mn_tsum;         // [C][mn_nt] sums of the spacings of 1024 slots; after the scan: their exclusive prefix
   double* mn_total;        // [C] sum of all n + 1 spacings
   int mn_nt;               // 1024-slot tiles of spacings per filter row
+  // Philox round keys of the launch-wide key word (seed_lo + r * 0x9E3779B9): operands straight from the constant bank
+  unsigned int rk0[10];
 };
+#ifndef __CUDACC_RTC__
+inline void st_fill_round_keys(StreamParams& P) {
+  for (int r = 0; r < 10; r++) P.rk0[r] = (unsigned int)P.f.seed + (unsigned int)r * 0x9E3779B9u;
+}
+#endif
+// Philox4x32-10 with the first key word's round keys given (same function as philox4x32_10)
+__device__ __forceinline__ uint4x philox4x32_10_rk(const unsigned int (&rk0)[10], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    const uint32_t n0 = hi1 ^ c1 ^ rk0[r], n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k1 += 0xBB67AE85u;
+  }
+  uint4x o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
 
 // explicitly rounded a + p * g: the same boundary value in every tile / rank that evaluates it
 __device__ __forceinline__ double st_bound(double a, double p, double g) { return __dadd_rn(a, __dmul_rn(p, g)); }
@@ -407,7 +439,7 @@ inline void st_pdl_wait() {}
 // are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
 // the parameter set-up and the fence + ticket once, not once per tile.
 template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(const __grid_constant__ StreamParams P, int obs) {
+__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_STEP / THREADS) k_st_step(const __grid_constant__ StreamParams P, int obs) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   // serves 1-D models with one normal per init / transition and no uniforms; checked on the host (stream_supported),
   // because NVRTC instantiates these kernels for every user model whatever its shape
@@ -481,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_step(const __gri
       for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) e[k] = Math<Real>::ninf();
     }
 #pragma unroll
-    for (int k = 0; k < PPT; k++) mloc = e[k] > mloc ? e[k] : mloc;
+    for (int k = 0; k < PPT; k++) mloc = Math<Real>::max_(mloc, e[k]);
     // Thread-local online accumulation: e relative to this THREAD's running max (rescaled on the rare tiles that
     // raise it).  No shuffle, no barrier, no store of partials in this loop: the sums meet once, at the block's end.
     if (mloc > mT) {
@@ -675,7 +707,7 @@ __device__ __forceinline__ int st_mn_count(const double* __restrict__ pos, int n
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
 // running sums of the tile totals it computes itself (clamped into the block's interval).
 template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const __grid_constant__ StreamParams P, int obs) {
+__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_resample(const __grid_constant__ StreamParams P, int obs) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;
@@ -689,7 +721,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
   double* const s_p = (double*)s_uo;
   Real* const s_out = (Real*)s_uo;
   __shared__ int s_mn[2];
-  __shared__ __align__(16) unsigned int s_head[CAP];       // expansion: (source index << 16 | address of its x) at the first slot of a source
+  __shared__ __align__(16) unsigned int s_head[CAP + ST_THREADS];   // expansion: (source index << 16 | address of its x) at the first slot of a source (+ a spare word per thread)
   __shared__ uint4 s_pf[2][2 * ST_THREADS];
   __shared__ double s_red[ST_NW], s_bs[ST_NW];
   __shared__ int s_wf[ST_NW];
@@ -812,9 +844,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
       uint4x q0 = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, 0u);
       sc.w_sys = q0.w[0];
     } else {
-      const int q_end = min((n + 3) >> 2, (sc.u_base + CAP) >> 2);
+      // the window ends with the quad after the slot the tile's upper cdf edge falls into (an fp32 position may round one slot
+      // past the edge; what it finds there is clamped to o_hi), not with the buffer: a Philox call per four slots is the
+      // largest single item of this kernel
+      const double th = hi_cdf * (double)n;
+      const int i_hi = th >= (double)n ? n : (int)th;
+      const int q_end = min(min((n + 3) >> 2, (sc.u_base + CAP) >> 2), (i_hi >> 2) + 2);
+      sc.u_cap = max(0, min(CAP, 4 * q_end - sc.u_base));
       for (int qd = (sc.u_base >> 2) + tid; qd < q_end; qd += ST_THREADS) {
-        uint4x uq = noise_quad(key, (unsigned int)obs, TAG_RESAMP_U, 0u, (unsigned int)qd);
+        uint4x uq = philox4x32_10_rk(P.rk0, (unsigned int)qd, (unsigned int)obs, key.stream, TAG_RESAMP_U, key.k1);
         *(uint4*)&s_u[4 * qd - sc.u_base] = make_uint4(uq.w[0], uq.w[1], uq.w[2], uq.w[3]);
       }
     }
@@ -866,7 +904,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
       // the staged window of uniforms, below n and within the range of the fp32 floor trick, all of them are.
       const float tf_last = fmaf((float)fs, wsn, f0);
       const int rel0 = I0 - sc.u_base;
-      const bool fast = P.resample_fn != 1 && tf_last < 4194304.0f && rel0 >= 0 && rel0 + (int)tf_last + 1 < CAP &&
+      const bool fast = P.resample_fn != 1 && tf_last < 4194304.0f && rel0 >= 0 && rel0 + (int)tf_last + 1 < sc.u_cap &&
                         I0 + (int)tf_last + 1 < n;
       if (fast) {
         const unsigned int* su = s_u + rel0;
@@ -876,14 +914,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
           const float tf = fmaf(accf, wsn, f0);
           const float r = (tf - 0.5f) + 12582912.0f;                       // floor and fraction without conversion instructions
           const int ii = __float_as_int(r) - 0x4B400000;
-          const float frac = tf - (r - 12582912.0f);
-          const float g = frac + 1.0f;
-          const unsigned int fbits = ((unsigned int)__float_as_int(g) & 0x7FFFFFu) << 9;
-          int v = I0 + ii + ((su[ii] < fbits || g >= 2.0f) ? 1 : 0);       // (i + U_i) <= t  <=>  U_i <= frac
-          v = min(max(v, o_lo), o_hi);
-          fmax = max(fmax, v);
-          F[k] = fmax;
+          const float g = (tf - (r - 12582912.0f)) + 1.0f;                  // 1 + fraction, in [1, 2]
+          // (i + U_i) <= t  <=>  U_i <= frac, on the 23 leading bits of the word: 1.U_i < 1 + frac as floats (g = 2: always)
+          const float u1 = __uint_as_float(0x3F800000u | (su[ii] >> 9));
+          // the positions grow with k (accf sums non-negative terms), so v does: no running maximum; the lower clamp is
+          // the max with prevF below
+          F[k] = min(I0 + ii + (u1 < g ? 1 : 0), o_hi);
         }
+        fmax = F[PPT - 1];
       } else {
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
@@ -933,7 +971,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
   }
   int prevF;
   {
-    int inc = F[PPT - 1];
+    int inc = max(F[PPT - 1], o_lo);   // (the fast path above leaves the lower clamp to this scan)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
     if (lane == 31) s_wf[wid] = inc;
@@ -967,9 +1005,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_st_resample(const _
 #pragma unroll
       for (int k = 0; k < PPT; k++) {
         const int hi_k = F[k];           // F is non-decreasing and starts at prevF
+        // branch-free: a source without offspring writes its mark into the thread's own spare word behind the head array
+        unsigned int* const hp = (hi_k > lo_k) ? &s_head[lo_k - o_base] : &s_head[CAP + tid];
+        *hp = key0 + (((unsigned int)k << 16) | (unsigned int)((k / EPH) * ST_THREADS * EPH + (k % EPH)));
         if (hi_k > lo_k) {
-          s_head[lo_k - o_base] = key0 + (((unsigned int)k << 16) | (unsigned int)((k / EPH) * ST_THREADS * EPH + (k % EPH)));
-          if constexpr (F32) sumx += (__int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f) * x[k];   // count as a float, exact below 2^23
+          if constexpr (F32) sumx = fmaf(__int_as_float(0x4B000000 | (hi_k - lo_k)) - 8388608.0f, x[k], sumx);   // count as a float, exact below 2^23
           else sumx += (Real)(hi_k - lo_k) * x[k];
         }
         lo_k = hi_k;

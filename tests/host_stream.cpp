@@ -78,6 +78,7 @@ static int run(int argc, char** argv) {
     f.ess = R.ess.data(); f.state_est = R.state_est.data(); f.loglike_history = R.llh.data();
     f.algorithm = 0; f.ralg = ralg; f.threshold = threshold;
     P.resample_fn = rfn;
+    st_fill_round_keys(P);
     P.sharded = sharded; P.rank = g; P.world = world; P.n_glob = sharded ? N : 0;
     P.cap = cap;
     P.log_n = n_per.empty() ? log((double)N) : nan("");
