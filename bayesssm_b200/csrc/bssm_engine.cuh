@@ -44,7 +44,7 @@ enum ScratchSlot {
   SL_FAST_BASE,
   SL_FAST_LAST = SL_FAST_BASE + 7,
   SL_ST_BASE,   /* streaming engine */
-  SL_ST_LAST = SL_ST_BASE + 11,
+  SL_ST_LAST = SL_ST_BASE + 13,
   SL_DG_BASE,   /* MCMC diagnostics (bssm_diag.cu) */
   SL_DG_LAST = SL_DG_BASE + 5,
   SL_COUNT
@@ -56,7 +56,7 @@ struct Scratch { void* p = nullptr; size_t cap = 0; };
 // NVRTC user model: cudaKernel_t from the compiled library)
 struct ModelKernels { void *init = nullptr, *weight = nullptr, *post = nullptr; bool has_aux = false, has_move = false; };
 // handles of the streaming engine's kernels (bssm_stream.cuh): k_st_init, k_st_step, k_st_resample, k_st_flush
-struct StreamKernels { void *init = nullptr, *step = nullptr, *resample = nullptr, *flush = nullptr; };
+struct StreamKernels { void *init = nullptr, *step = nullptr, *resample = nullptr, *flush = nullptr, *chain = nullptr; };   // chain: the chain-persistent kernel (built-in models)
 constexpr int BSSM_USER_MODEL_BASE = 1000;
 struct UserModelInfo {
   void* library = nullptr;   // cudaLibrary_t

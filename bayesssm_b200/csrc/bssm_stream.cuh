@@ -89,6 +89,9 @@ struct StreamParams {
   int mn_nt;               // 1024-slot tiles of spacings per filter row
   // Philox round keys of the launch-wide key word (seed_lo + r * 0x9E3779B9): operands straight from the constant bank
   unsigned int rk0[10];
+  // chain-persistent kernel (k_st_chain): per-filter barrier words between the blocks of a filter
+  unsigned int* epoch;     // [C] observations whose bookkeeping the merging block has published
+  unsigned int* bar2;      // [C] arrivals after resampling steps (monotonic)
 };
 #ifndef __CUDACC_RTC__
 inline void st_fill_round_keys(StreamParams& P) {
@@ -261,12 +264,12 @@ static __device__ __forceinline__ void st_local_merge(const StreamParams& P, int
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double NINF = -__longlong_as_double(0x7FF0000000000000LL);
   const size_t row = (size_t)c * P.bpc;
-  const double* __restrict__ pm = P.blk_m + row;
-  const double* __restrict__ ps = P.blk_s + row;
-  const double* __restrict__ pq = P.blk_q + row;
-  const double* __restrict__ px = P.blk_x + row;
-  const double* __restrict__ bsum = P.bsum + row;
-  double* __restrict__ pref = P.pref + (size_t)c * (P.bpc + 1);
+  const double* pm = P.blk_m + row;
+  const double* ps = P.blk_s + row;
+  const double* pq = P.blk_q + row;
+  const double* px = P.blk_x + row;
+  const double* bsum = P.bsum + row;
+  double* pref = P.pref + (size_t)c * (P.bpc + 1);
   const int seg = ((nb + ST_NW - 1) / ST_NW + 31) & ~31;      // records per warp, multiple of 32
   const int j0 = min(nb, wid * seg), j1 = min(nb, j0 + seg);
   if (P.dbg && tid == 0) P.dbg[4] = clock64();
@@ -329,6 +332,7 @@ static __global__ void k_st_setup(StreamParams P, long long goff0, int nloc0) {
   P.seg[1 * P.f.C + c] = sg; P.seg[c] = sg;
   P.res[1 * P.f.C + c] = 1; P.res[c] = 0;
   P.counter[c] = 0u;
+  if (P.epoch) { P.epoch[c] = 0u; P.bar2[c] = 0u; }
 }
 
 // ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, block sums for the t = 0 state estimate ----
@@ -434,36 +438,87 @@ inline void st_pdl_launch_dependents() {}
 inline void st_pdl_wait() {}
 #endif
 
+// ---- barriers between the blocks of ONE filter (chain-persistent kernel k_st_chain; the blocks are co-resident) ----
+#ifndef BSSM_EMU
+__device__ __forceinline__ unsigned int st_ld_acquire(const unsigned int* p) {
+  unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#else
+inline unsigned int st_ld_acquire(const unsigned int* p) { emu_poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_st_release(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#endif
+// publish: everything the block wrote (any thread) before the call is visible to a block that has seen the value
+__device__ __forceinline__ void st_chain_publish(unsigned int* p, unsigned int v) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); st_st_release(p, v); }
+}
+// wait until the word reaches v; afterwards every thread of the block reads what the publisher wrote (the fence drops
+// this SM's stale L1 lines: the descriptors live at the same addresses every other observation)
+__device__ __forceinline__ void st_chain_wait(const unsigned int* p, unsigned int v) {
+  if (threadIdx.x == 0) { while ((int)(st_ld_acquire(p) - v) < 0) {} }
+  __syncthreads();
+  __threadfence();
+}
+// arrive + wait on a monotonic counter (target = arrivals of all rounds so far)
+__device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); atomicAdd(p, 1u); while ((int)(st_ld_acquire(p) - target) < 0) {} }
+  __syncthreads();
+  __threadfence();
+}
+
+// shared memory of the two per-observation bodies (the chain-persistent kernel overlays them)
+template <typename Real, int THREADS> struct StStepSmem {
+  uint4 pf[2][2 * THREADS];
+  Real w[4][THREADS / 32];        // per-warp records at the end of the block
+  double red[4 * (THREADS / 32)];
+};
+template <typename Real, int PPT, int THREADS> struct StResSmem {
+  static constexpr int CAP = THREADS * ((PPT * 5 / 4 + 1) & ~1);   // staging capacity: a quarter beyond the tile (more offspring take further chunks)
+  // one buffer, two lives: the staged stratified uniforms (raw Philox words) of the tile while the offspring
+  // ranges are computed, then the staged outputs of a chunk (multinomial: the staged positions, doubles)
+  __align__(16) unsigned char uo[CAP * 8];
+  __align__(16) unsigned int head[CAP + THREADS];   // expansion: (source index << 16 | address of its x) at the first slot of a source (+ a spare word per thread)
+  uint4 pf[2][2 * THREADS];
+  double red[THREADS / 32], bs[THREADS / 32];
+  int wf[THREADS / 32];
+  unsigned int wh[THREADS / 32];
+  int mn[2];
+};
+enum { ST_GO = 0, ST_LEAVE = 1 };   // body results: carry on / this block has nothing more to do for the filter (dead filter, no tiles)
+
 // ---- K_A: propagate + log-weight + tile / block partials; the last block of a filter merges ----
 // Block (c, j) walks the contiguous tiles [j * tpb, (j + 1) * tpb) of filter c; the next tile's particles
 // are in flight (cp.async) while the current tile is computed, and the block pays the descriptor loads,
 // the parameter set-up and the fence + ticket once, not once per tile.
-template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_STEP / THREADS) k_st_step(const __grid_constant__ StreamParams P, int obs) {
+// PERSIST: called once per observation by the chain-persistent kernel -- the blocks of a filter meet at the end of the body
+// (the merging block publishes the observation's bookkeeping, the others wait for it) instead of at a kernel boundary.
+template <typename Model, typename Real, int PPT, int THREADS, bool PERSIST>
+__device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int c, int j, const Real* par, const NoiseKey& key,
+                                            StStepSmem<Real, THREADS>& sm) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   // serves 1-D models with one normal per init / transition and no uniforms; checked on the host (stream_supported),
   // because NVRTC instantiates these kernels for every user model whatever its shape
   static_assert(PPT % 4 == 0, "one Philox call serves 4 particles");
   constexpr int TS = ST_THREADS * PPT;
-  __shared__ uint4 s_pf[2][2 * ST_THREADS];
-  __shared__ Real s_w[4][ST_NW];        // per-warp records at the end of the block
-  __shared__ double s_red[4 * ST_NW];
+  uint4 (&s_pf)[2][2 * ST_THREADS] = sm.pf;
+  Real (&s_w)[4][ST_NW] = sm.w;
+  double* const s_red = sm.red;
   const FilterDev& f = P.f;
-  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  st_pdl_launch_dependents();
-  // independent of the previous launch: parameters, Philox key, the observation
-  Real par[Model::NPAR];
-  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
-  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // independent of the previous launch: the observation
   const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
   const int prev_t = obs == 0 ? 0 : (f.obs_times ? f.obs_times[obs - 1] : obs);
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
-  st_pdl_wait();
-  const long long t_start = P.dbg ? clock64() : 0;
-  if (!f.alive[c]) return;
+  if constexpr (!PERSIST) st_pdl_wait();
+  const long long t_start = (!PERSIST && P.dbg) ? clock64() : 0;
+  if (!f.alive[c]) return ST_LEAVE;
   const StLayout L = st_layout_in<TS>(P, c, obs);
-  if (j >= L.nb) return;
+  if (j >= L.nb) return ST_LEAVE;
   const int pp = (obs + 1) & 1;
   const int rprev = P.res[pp * f.C + c];
   const int t0 = j * L.tpb, t1 = min(L.ntc, t0 + L.tpb);
@@ -559,9 +614,12 @@ __global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_STEP / THREADS) k_st_step
     const unsigned int ticket = atomicAdd(&P.counter[c], 1u);
     mine = (ticket == (unsigned int)(L.nb - 1));
   }
-  if (!__syncthreads_or(mine)) return;
+  if (!__syncthreads_or(mine)) {
+    if constexpr (PERSIST) st_chain_wait(&P.epoch[c], (unsigned int)(obs + 1));
+    return ST_GO;
+  }
   __threadfence();
-  const long long t_tick = P.dbg ? clock64() : 0;
+  const long long t_tick = (!PERSIST && P.dbg) ? clock64() : 0;
   // records of the pending state sum: the blocks of the layout the previous resampling (or the init) ran on
   int nb_pending = 0;
   if (rprev) {
@@ -570,11 +628,25 @@ __global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_STEP / THREADS) k_st_step
   }
   StRec r;
   st_local_merge<Real, ST_THREADS>(P, c, L.nb, nb_pending, s_red, r);
-  const long long t_merge = P.dbg ? clock64() : 0;
+  const long long t_merge = (!PERSIST && P.dbg) ? clock64() : 0;
   if (tid == 0) P.counter[c] = 0u;
   if (P.sharded) { if (tid == 0) P.rec_local[c] = r; }
   else if (lane == 0 && wid < 3) st_global(P, c, obs, &r, 0, 1, 0, L.goff, L.nloc, 1 << wid);   // three roles on three warps
-  if (P.dbg && tid == 0) { P.dbg[0] = t_tick - t_start; P.dbg[1] = t_merge - t_tick; P.dbg[2] = clock64() - t_merge; P.dbg[7] = t_merge - P.dbg[7]; P.dbg[6] = P.dbg[6] - P.dbg[5]; P.dbg[5] = P.dbg[5] - P.dbg[4]; P.dbg[4] = P.dbg[4] - t_tick; }
+  if constexpr (PERSIST) st_chain_publish(&P.epoch[c], (unsigned int)(obs + 1));
+  else if (P.dbg && tid == 0) { P.dbg[0] = t_tick - t_start; P.dbg[1] = t_merge - t_tick; P.dbg[2] = clock64() - t_merge; P.dbg[7] = t_merge - P.dbg[7]; P.dbg[6] = P.dbg[6] - P.dbg[5]; P.dbg[5] = P.dbg[5] - P.dbg[4]; P.dbg[4] = P.dbg[4] - t_tick; }
+  return ST_GO;
+}
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_STEP / THREADS) k_st_step(const __grid_constant__ StreamParams P, int obs) {
+  __shared__ StStepSmem<Real, THREADS> sm;
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc;
+  st_pdl_launch_dependents();
+  // independent of the previous launch: parameters, Philox key
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  st_step_body<Model, Real, PPT, THREADS, false>(P, obs, c, j, par, key, sm);
 }
 
 // sharded runs: global bookkeeping from the gathered records (one thread per filter)
@@ -706,44 +778,45 @@ __device__ __forceinline__ int st_mn_count(const double* __restrict__ pos, int n
 // Same block -> tile ranges and prefetch as k_st_step.  A block's cdf interval comes from the block prefix
 // array (bit-identical in the neighbouring blocks); the tile boundaries inside it are this block's own
 // running sums of the tile totals it computes itself (clamped into the block's interval).
-template <typename Model, typename Real, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_resample(const __grid_constant__ StreamParams P, int obs) {
+// PERSIST: see st_step_body; the caller meets the other blocks of the filter after the body (the next observation reads
+// slots its neighbours wrote).  Result: ST_LEAVE for a dead filter / a block without tiles, else ST_GO; *resampled tells
+// whether the filter resampled at this observation (the same answer in every block of the filter).
+template <typename Model, typename Real, int PPT, int THREADS, bool PERSIST>
+__device__ __forceinline__ int st_resample_body(const StreamParams& P, int obs, int c, int j, const Real* par, const NoiseKey& key,
+                                                StResSmem<Real, PPT, THREADS>& sm, int* resampled, int* nb_out) {
   constexpr int ST_THREADS = THREADS, ST_NW = THREADS / 32;
   constexpr bool F32 = sizeof(Real) == 4;
   constexpr int TS = ST_THREADS * PPT;
-  constexpr int CAP = ST_THREADS * ((PPT * 5 / 4 + 1) & ~1);   // staging capacity: a quarter beyond the tile (more offspring take further chunks)
+  constexpr int CAP = StResSmem<Real, PPT, THREADS>::CAP;
   constexpr int SPT = CAP / ST_THREADS;      // output slots per thread in the expansion
   static_assert(CAP % ST_THREADS == 0 && SPT % 2 == 0, "staging capacity: whole, even number of slots per thread");
-  // one buffer, two lives: the staged stratified uniforms (raw Philox words) of the tile while the offspring
-  // ranges are computed, then the staged outputs of a chunk
-  __shared__ __align__(16) unsigned char s_uo[CAP * 8];    // (multinomial: the staged positions, doubles)
+  unsigned char* const s_uo = sm.uo;
   unsigned int* const s_u = (unsigned int*)s_uo;
   double* const s_p = (double*)s_uo;
   Real* const s_out = (Real*)s_uo;
-  __shared__ int s_mn[2];
-  __shared__ __align__(16) unsigned int s_head[CAP + ST_THREADS];   // expansion: (source index << 16 | address of its x) at the first slot of a source (+ a spare word per thread)
-  __shared__ uint4 s_pf[2][2 * ST_THREADS];
-  __shared__ double s_red[ST_NW], s_bs[ST_NW];
-  __shared__ int s_wf[ST_NW];
-  __shared__ unsigned int s_wh[ST_NW];
+  int* const s_mn = sm.mn;
+  unsigned int* const s_head = sm.head;
+  uint4 (&s_pf)[2][2 * ST_THREADS] = sm.pf;
+  double* const s_red = sm.red; double* const s_bs = sm.bs;
+  int* const s_wf = sm.wf;
+  unsigned int* const s_wh = sm.wh;
   const FilterDev& f = P.f;
-  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  st_pdl_launch_dependents();
-  // independent of the previous launch: parameters, Philox key, the observation
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // independent of the previous launch: the observation
   const int n = P.n_glob ? P.n_glob : filt_n(f, c);
-  Real par[Model::NPAR];
-  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
-  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
   const int ot = f.obs_times ? f.obs_times[obs] : obs + 1;
   double yv[4] = {0, 0, 0, 0};
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
-  st_pdl_wait();
-  if (!f.alive[c]) return;
+  if constexpr (!PERSIST) st_pdl_wait();
+  *resampled = 0;
+  if (!f.alive[c]) return ST_LEAVE;
   const int pc = obs & 1;
-  if (!P.res[pc * f.C + c]) return;
+  if (!P.res[pc * f.C + c]) return ST_GO;
+  *resampled = 1;
   const StSeg sg = P.seg[pc * f.C + c];
   const StLayout L = st_make_layout<TS>(sg.goff, sg.nloc, P.bpc);
-  if (j >= L.nb) return;
+  *nb_out = L.nb;
+  if (j >= L.nb) return ST_LEAVE;
   const int lead = L.lead, ntc = L.ntc;
   const int t0 = j * L.tpb, t1 = min(ntc, t0 + L.tpb);
   const Real* xin = (const Real*)P.x1 + (size_t)c * P.xstride + tid * PPT;
@@ -1083,6 +1156,50 @@ __global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_resam
     }
   }
   if (tid == 0) P.bsum[(size_t)c * P.bpc + j] = bacc;
+  return ST_GO;
+}
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_resample(const __grid_constant__ StreamParams P, int obs) {
+  __shared__ StResSmem<Real, PPT, THREADS> sm;
+  const FilterDev& f = P.f;
+  const int c = blockIdx.x / P.bpc, j = blockIdx.x % P.bpc;
+  st_pdl_launch_dependents();
+  // independent of the previous launch: parameters, Philox key
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  int resampled, nb;
+  st_resample_body<Model, Real, PPT, THREADS, false>(P, obs, c, j, par, key, sm, &resampled, &nb);
+}
+
+// ---- chain-persistent kernel: every observation of a batch of filters in ONE cooperative launch ----
+// Block (c, j) keeps its tile range of filter c for the whole run and alternates the two bodies above.  The blocks of a filter
+// meet twice per observation -- after the merge of the block records (the merging block publishes the bookkeeping) and after
+// a resampling (the next step reads slots the neighbouring blocks wrote) -- through two words per filter; filters never wait
+// for each other, so the blocks an SM holds drift apart and fill each other's waits.  Launched cooperatively (the blocks of
+// a filter spin on each other: all of them must be resident); serves batches, where two launches per observation leave the
+// chip a quarter idle (ramp, drain, every block in the same phase).
+template <typename Model, typename Real, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_chain(const __grid_constant__ StreamParams P, int c_base, int T) {
+  union Smem { StStepSmem<Real, THREADS> a; StResSmem<Real, PPT, THREADS> b; };
+  __shared__ Smem sm;
+  const FilterDev& f = P.f;
+  const int c = c_base + blockIdx.x / P.bpc, j = blockIdx.x % P.bpc;
+  Real par[Model::NPAR];
+  Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
+  const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
+  unsigned int arrivals = 0u;
+  for (int obs = 0; obs < T; obs++) {
+    if (st_step_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.a) == ST_LEAVE) return;
+    __syncthreads();                       // the two bodies overlay their shared memory
+    int resampled = 0, nb = 1;
+    if (st_resample_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.b, &resampled, &nb) == ST_LEAVE) return;
+    if (resampled) {
+      arrivals += (unsigned int)nb;
+      if (nb > 1) st_chain_arrive_wait(&P.bar2[c], arrivals);
+      else __syncthreads();
+    }
+  }
 }
 
 // ---- flush: the state estimate of a final resampling (or of the initial particles when T = 0) ----

@@ -21,7 +21,7 @@ struct Rank {
   StreamParams P;
   std::vector<unsigned char> x0, x1;
   std::vector<double> pref, bsum, blk, M, S, loglike, ess, state_est, llh, mn_pos, mn_tsum, mn_total;
-  std::vector<unsigned int> counter;
+  std::vector<unsigned int> counter, epoch, bar2;
   std::vector<int> res, alive, status, early, nres;
   std::vector<StSeg> seg;
   std::vector<StRec> rec_local, rec_all;
@@ -93,6 +93,7 @@ static int run(int argc, char** argv) {
     P.blk_m = R.blk.data(); P.blk_s = P.blk_m + (size_t)C * P.bpc; P.blk_q = P.blk_s + (size_t)C * P.bpc; P.blk_x = P.blk_q + (size_t)C * P.bpc;
     R.counter.assign(C, 77u); R.res.assign((size_t)2 * C, -1); R.seg.resize((size_t)2 * C);
     P.counter = R.counter.data(); P.res = R.res.data(); P.seg = R.seg.data();
+    if (getenv("EMU_CHAIN")) { R.epoch.assign(C, 99u); R.bar2.assign(C, 98u); P.epoch = R.epoch.data(); P.bar2 = R.bar2.data(); }   // stream_launch(): only for k_st_chain
     R.rec_local.resize(C); R.rec_all.resize((size_t)C * world);
     P.rec_local = R.rec_local.data(); P.rec_all = R.rec_all.data();
     P.dbg = nullptr;
@@ -121,7 +122,18 @@ static int run(int argc, char** argv) {
     const auto o = block_order(grid);
     emu_launch(grid, THREADS, [&] { k_st_init<Model, Real, PPT, THREADS>(P); }, &o);
   }
-  for (int obs = 0; obs < T; obs++) {
+  // chain-persistent kernel (stream_launch(): batches on one GPU): cooperative launches over groups of filters, every
+  // observation inside; EMU_CHAIN = filters per launch
+  const int chain_group = getenv("EMU_CHAIN") ? std::max(1, atoi(getenv("EMU_CHAIN"))) : 0;
+  if (chain_group && T > 0) {
+    if (sharded || rfn == 2) { fprintf(stderr, "EMU_CHAIN: one rank, stratified / systematic only\n"); return 2; }
+    const StreamParams P = ranks[0].P;
+    for (int c0 = 0; c0 < C; c0 += chain_group) {
+      const int cb = std::min(chain_group, C - c0);
+      emu_launch_cooperative((unsigned int)(cb * P.bpc), THREADS, 0, [&] { k_st_chain<Model, Real, PPT, THREADS>(P, c0, T); });
+    }
+  }
+  for (int obs = 0; obs < T && !chain_group; obs++) {
     for (int g = 0; g < world; g++) {
       const StreamParams P = ranks[g].P;
       const auto o = block_order((unsigned int)P.bpc * C);

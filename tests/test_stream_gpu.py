@@ -221,3 +221,38 @@ def test_multinomial_f32_batched_against_kalman_and_auto_engine(orc, engine):
     # AUTO took the streaming engine: the same numbers when it is asked for by name
     again = eh.filter_run(engine, LG, 0, 1, 2, 1 << 14, y, THETA[LG], seed=11, num_filters=64, precision=nat.F32, engine=nat.ENGINE_STREAM)
     np.testing.assert_array_equal(again["loglike"], lls)
+
+
+# ---- batches: the chain-persistent kernel (k_st_chain, one cooperative launch per group of filters) ----
+@pytest.mark.parametrize("C,N,T,prec", [(24, 70001, 12, nat.F64), (1500, 3000, 10, nat.F32), (128, 65536, 40, nat.F32), (17, 1, 5, nat.F64)])
+def test_chain_persistent_kernel_equals_the_launch_per_body_form(engine, monkeypatch, C, N, T, prec):
+    # same bodies, same block -> tile ranges when the blocks per filter agree: bit-identical results, several launch groups
+    # (1500 filters > resident block slots), ragged tiles, SISAR decisions taken per filter
+    y = sim_y(AR, T, np.random.default_rng(C))
+    out = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("BSSM_ST_CHAIN", chain)
+        monkeypatch.setenv("BSSM_ST_BPC", "3" if N > 3000 else "1")
+        out[chain] = eh.filter_run(engine, AR, 0, 2, 0, N, y, THETA[AR], seed=77, num_filters=C, precision=prec, engine=ST)
+    a, b = out["1"], out["0"]
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    np.testing.assert_array_equal(a["loglike"], b["loglike"])
+    np.testing.assert_array_equal(a["n_resampled"], b["n_resampled"])
+    np.testing.assert_array_equal(a["ess"], b["ess"])
+    np.testing.assert_array_equal(a["state_est"], b["state_est"])
+    assert len(np.unique(a["loglike"])) == C
+
+
+def test_chain_persistent_kernel_against_oracle_with_dead_filters_and_gaps(orc, engine, monkeypatch):
+    monkeypatch.setenv("BSSM_ST_CHAIN", "1")
+    y = sim_y(AR, 9, np.random.default_rng(2))
+    times = [1, 2, 4, 5, 6, 9, 10, 11, 12]
+    got = eh.filter_run(engine, AR, 0, 2, 1, 5000, y, THETA[AR], seed=13, num_filters=40, precision=nat.F64, engine=ST, obs_times=times)
+    for c in (0, 7, 39):
+        ref = orc.particle_filter(AR, 0, 2, 1, 5000, y, THETA[AR], seed=13, stream=c, obs_times=times)
+        assert abs(got["loglike"][c] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"]) and got["n_resampled"][c] == ref["n_resampled"]
+        np.testing.assert_allclose(got["ess"][c], ref["ess"], rtol=1e-6)
+    # all weights below -1e8 at the second observation: every filter stops there (R/particle_filter_core.R:189-202)
+    y2, th = np.array([0.1, 1e6, 0.2]), [0.8, 1.0, 1e-3]
+    got = eh.filter_run(engine, AR, 0, 2, 0, 4096, y2, th, seed=3, num_filters=20, precision=nat.F64, engine=ST)
+    assert (got["early_exit"] == 1).all() and (got["loglike"] == -np.inf).all() and (got["status"] == 0).all()

@@ -27,15 +27,19 @@ def host_stream(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
 
     def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
-            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=(), obs_times=None):
+            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=(), obs_times=None, chain=0):
         y = np.ascontiguousarray(y, dtype=np.float64)
         th = np.zeros((len(thetas), 3))
         for c, t in enumerate(thetas):
             th[c, :len(t)] = t
         args = [model, precision, threads, N, len(y), len(thetas), bpc, resample_fn, resample_algorithm, threshold, seed, run_id,
                 stream_base, world, capacity_factor, block_order] + list(n_per)
-        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600,
-                           env=dict(os.environ, EMU_OBS_TIMES=",".join(str(int(t)) for t in obs_times)) if obs_times is not None else None)
+        env = dict(os.environ)
+        if obs_times is not None:
+            env["EMU_OBS_TIMES"] = ",".join(str(int(t)) for t in obs_times)
+        if chain:      # the chain-persistent kernel k_st_chain: cooperative launches over groups of `chain` filters
+            env["EMU_CHAIN"] = str(chain)
+        r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
         for i in range(0, len(lines), 4):
@@ -212,3 +216,42 @@ def test_multinomial_batch_degenerate_weights_and_f32(orc, host_stream):
     ref = orc.particle_filter(AR, 0, 2, 3, 20000, y, THETA[AR], seed=1405, run_id=2, stream=3)
     assert rec["status"] == 0 and rec["n_resampled"] == ref["n_resampled"]
     assert abs(rec["loglike"] - ref["loglike"]) < 2e-2 and np.abs(rec["state_est"] - ref["state_est"][:, 0]).max() < 2e-2
+
+
+# ---- the chain-persistent kernel (k_st_chain): all observations in one cooperative launch per group of filters ----
+@pytest.mark.parametrize("N,T,threads,bpc,rfn,ralg,group", [(3000, 8, 128, 3, 0, 2, 2), (1025, 6, 256, 1, 1, 1, 5), (7000, 7, 128, 5, 0, 2, 1),
+                                                            (2048, 6, 256, 2, 0, 0, 3)])
+def test_chain_persistent_kernel_matches_oracle(orc, host_stream, N, T, threads, bpc, rfn, ralg, group):
+    y = sim_y(AR, T, np.random.default_rng(N + 1))
+    thetas = [list(np.array(THETA[AR]) * (1 + 0.04 * c)) for c in range(3)]
+    recs = host_stream(AR, N, y, thetas, threads=threads, bpc=bpc, resample_fn=rfn, resample_algorithm=ralg, seed=21, run_id=1,
+                       stream_base=4, chain=group)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, ralg, rfn, N, y, thetas[c], seed=21, run_id=1, stream=4 + c))
+
+
+def test_chain_persistent_kernel_ragged_counts_gaps_early_exit_and_f32(orc, host_stream):
+    y = sim_y(AR, 6, np.random.default_rng(3))
+    ns = [3000, 50, 1777]
+    thetas = [list(np.array(THETA[AR]) * (1 + 0.05 * c)) for c in range(3)]
+    recs = host_stream(AR, 3000, y, thetas, threads=128, bpc=3, seed=5, run_id=1, stream_base=2, n_per=ns, chain=3)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 2, 0, ns[c], y, thetas[c], seed=5, run_id=1, stream=2 + c))
+    # observation times with gaps
+    times = [1, 2, 5, 6, 9, 10]
+    recs = host_stream(AR, 2500, y, thetas[:2], threads=128, bpc=2, seed=8, run_id=0, stream_base=0, obs_times=times, chain=2)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 2, 0, 2500, y, thetas[c], seed=8, stream=c, obs_times=times))
+    # one filter of the batch dies (all weights below -1e8), the other carries on
+    y2 = np.array([0.1, 1e6, 0.2])
+    th_dead, th_ok = [0.8, 1.0, 1e-3], [0.8, 1.0, 1e7]
+    recs = host_stream(AR, 1500, y2, [th_dead, th_ok], threads=128, bpc=2, seed=3, run_id=0, stream_base=0, chain=2)
+    ref = [orc.particle_filter(AR, 0, 2, 0, 1500, y2, th, seed=3, stream=c) for c, th in enumerate([th_dead, th_ok])]
+    assert ref[0]["early_exit"] == 1 and recs[0]["early_exit"] == 1 and recs[0]["loglike"] == -np.inf
+    check(recs[1], ref[1])
+    # throughput precision: the same kernel text in f32 agrees with the launch-per-body form bit for bit
+    a = host_stream(AR, 5000, y, thetas, precision=32, threads=128, bpc=4, seed=5, run_id=1, stream_base=2)
+    b = host_stream(AR, 5000, y, thetas, precision=32, threads=128, bpc=4, seed=5, run_id=1, stream_base=2, chain=3)
+    for ra, rb in zip(a, b):
+        assert ra["loglike"] == rb["loglike"] and ra["n_resampled"] == rb["n_resampled"]
+        np.testing.assert_array_equal(ra["state_est"], rb["state_est"])
