@@ -140,7 +140,12 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, (size_t)C, &P.mn_total));
   }
   P.dbg = nullptr;
-  if (getenv("BSSM_ST_TIMING") && !chain) {
+#ifdef BSSM_ST_CHAIN_TIMING
+  const bool dbg_ok = true;
+#else
+  const bool dbg_ok = !chain;
+#endif
+  if (getenv("BSSM_ST_TIMING") && dbg_ok) {
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 11, (size_t)8, &P.dbg));
     BSSM_CK(cudaMemsetAsync(P.dbg, 0, 8 * sizeof(long long), st));
   }
@@ -187,7 +192,14 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
       BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample", pdl && !mn));
     }
   }
-  if (P.dbg) {
+  if (P.dbg && chain) {
+    long long h[8];
+    BSSM_CK(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BSSM_CK(cudaStreamSynchronize(st));
+    const double nbk = h[3] > 0 ? (double)h[3] : 1.0;
+    fprintf(stderr, "[bssm chain timing] per block, cycles: step body %.0f (of which waiting for the merge %.0f), resample body %.0f, wait after resampling %.0f; %lld blocks, bpc=%d\n",
+            h[0] / nbk, h[4] / nbk, h[1] / nbk, h[2] / nbk, h[3], P.bpc);
+  } else if (P.dbg) {
     long long h[8];
     BSSM_CK(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     BSSM_CK(cudaStreamSynchronize(st));

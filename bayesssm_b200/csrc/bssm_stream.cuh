@@ -333,6 +333,9 @@ static __global__ void k_st_setup(StreamParams P, long long goff0, int nloc0) {
   P.res[1 * P.f.C + c] = 1; P.res[c] = 0;
   P.counter[c] = 0u;
   if (P.epoch) { P.epoch[c] = 0u; P.bar2[c] = 0u; }
+#ifdef BSSM_ST_CHAIN_TIMING
+  if (c == 0) g_st_chain_wait = 0ull;
+#endif
 }
 
 // ---- init (R/particle_filter_core.R:76-116): x0 <- init_fn, block sums for the t = 0 state estimate ----
@@ -438,6 +441,9 @@ inline void st_pdl_launch_dependents() {}
 inline void st_pdl_wait() {}
 #endif
 
+#ifdef BSSM_ST_CHAIN_TIMING
+__device__ unsigned long long g_st_chain_wait;   // diagnostics build: cycles spent waiting for the merging block
+#endif
 // ---- barriers between the blocks of ONE filter (chain-persistent kernel k_st_chain; the blocks are co-resident) ----
 #ifndef BSSM_EMU
 __device__ __forceinline__ unsigned int st_ld_acquire(const unsigned int* p) {
@@ -615,7 +621,15 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
     mine = (ticket == (unsigned int)(L.nb - 1));
   }
   if (!__syncthreads_or(mine)) {
-    if constexpr (PERSIST) st_chain_wait(&P.epoch[c], (unsigned int)(obs + 1));
+    if constexpr (PERSIST) {
+#ifdef BSSM_ST_CHAIN_TIMING
+      const long long tw_ = clock64();
+#endif
+      st_chain_wait(&P.epoch[c], (unsigned int)(obs + 1));
+#ifdef BSSM_ST_CHAIN_TIMING
+      if (P.dbg && tid == 0) atomicAdd(&g_st_chain_wait, (unsigned long long)(clock64() - tw_));
+#endif
+    }
     return ST_GO;
   }
   __threadfence();
@@ -1189,17 +1203,33 @@ __global__ void __launch_bounds__(THREADS, BSSM_ST_OCC_RES / THREADS) k_st_chain
   Model::template prepare<Real>(f.theta + (size_t)c * f.theta_stride, par);
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
   unsigned int arrivals = 0u;
+#ifdef BSSM_ST_CHAIN_TIMING   // diagnostics build: where a block's cycles go (thread 0; step body incl. its wait, resample body, second wait)
+  long long tc[3] = {0, 0, 0};
+#define ST_TC(i, ...) { const long long t0_ = clock64(); __VA_ARGS__; tc[i] += clock64() - t0_; }
+#else
+#define ST_TC(i, ...) { __VA_ARGS__; }
+#endif
   for (int obs = 0; obs < T; obs++) {
-    if (st_step_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.a) == ST_LEAVE) return;
+    int leave = 0;
+    ST_TC(0, leave = st_step_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.a) == ST_LEAVE);
+    if (leave) return;
     __syncthreads();                       // the two bodies overlay their shared memory
     int resampled = 0, nb = 1;
-    if (st_resample_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.b, &resampled, &nb) == ST_LEAVE) return;
+    ST_TC(1, leave = st_resample_body<Model, Real, PPT, THREADS, true>(P, obs, c, j, par, key, sm.b, &resampled, &nb) == ST_LEAVE);
+    if (leave) return;
     if (resampled) {
       arrivals += (unsigned int)nb;
-      if (nb > 1) st_chain_arrive_wait(&P.bar2[c], arrivals);
-      else __syncthreads();
+      ST_TC(2, if (nb > 1) st_chain_arrive_wait(&P.bar2[c], arrivals); else __syncthreads());
     }
   }
+#ifdef BSSM_ST_CHAIN_TIMING
+  if (P.dbg && threadIdx.x == 0) {
+    for (int i = 0; i < 3; i++) atomicAdd((unsigned long long*)&P.dbg[i], (unsigned long long)tc[i]);
+    atomicAdd((unsigned long long*)&P.dbg[3], 1ull);
+    P.dbg[4] = (long long)atomicAdd(&g_st_chain_wait, 0ull);   // the last block to finish leaves the total
+  }
+#endif
+#undef ST_TC
 }
 
 // ---- flush: the state estimate of a final resampling (or of the initial particles when T = 0) ----

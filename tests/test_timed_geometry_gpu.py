@@ -76,3 +76,16 @@ def test_streaming_f32_against_f64_at_the_pmmh_geometry(engine):
     se = np.sqrt(la.var(ddof=1) / len(la) + lb.var(ddof=1) / len(lb))
     assert abs(la.mean() - lb.mean()) < 4 * se + 5e-3, (la.mean(), lb.mean(), se)
     assert abs(np.median(a["n_resampled"]) - np.median(b["n_resampled"])) <= 5
+
+
+def test_chain_persistent_kernel_f32_lg_128_x_65536_t1000_against_kalman(orc, engine):
+    # what one of eight GPUs runs per PMMH iteration at BASELINE configs[4] (1024 chains over 8 ranks): 128 filters x 65536 x 1000
+    # on the chain-persistent kernel (one cooperative launch, 2000 barriers between the blocks of each filter)
+    y = sim_y(LG, 1000, np.random.default_rng(4141))
+    exact = orc.kalman_loglik(y, *THETA[LG])
+    got = eh.filter_run(engine, LG, 0, 1, 0, 65536, y, THETA[LG], seed=101, num_filters=128, precision=nat.F32, engine=nat.ENGINE_STREAM)
+    assert (got["status"] == 0).all() and (got["n_resampled"] == 1000).all()
+    lls = got["loglike"]
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(logmeanexp(lls) - exact) < 3 * se + 2e-3, (logmeanexp(lls), exact, se)
+    assert len(np.unique(lls)) == 128
