@@ -1,9 +1,9 @@
 // bssm_stream.cuh -- streaming bootstrap-filter engine: particles resident in HBM, TWO kernels per
-// observation.  Serves what does not fit the persistent kernel's registers (bssm_fast.cuh): single
+// observation (or, for batches, one cooperative kernel for all of them).  Serves what does not fit the persistent kernel's registers (bssm_fast.cuh): single
 // filters beyond ~10^6 particles, large batches [chains x particles], and the particle-sharded
 // multi-GPU filter (bssm_shard.cu), where one small record exchange sits between the two kernels.
 // Replaces the per-observation loop of .particle_filter_core (R/particle_filter_core.R:123-246)
-// for algorithm "BPF" and the resamplers of src/resampling.cpp:16-66 (stratified / systematic).
+// for algorithm "BPF" and the resamplers of src/resampling.cpp:5-66 (multinomial / stratified / systematic).
 //
 //   k_st_step      read x, propagate (one Philox call per 4 particles), log-weight, write x.  A block
 //                  walks a contiguous range of tiles; every thread keeps an online (max, sum e,
@@ -18,6 +18,11 @@
 //                  output slots [F(c_prev), F(c)), F(c) = #{ i : (i + U_i)/n <= c } -- no search,
 //                  no cdf array in memory; chosen states are staged in shared memory and leave
 //                  the SM as coalesced vector stores.                            [8 B / particle]
+//   k_st_chain     batches: every observation of a group of filters in ONE cooperative launch; a block keeps its
+//                  tile range of a filter and alternates the two bodies above (st_step_body, st_resample_body), the
+//                  blocks of a filter meet through two words per filter and observation.
+//   k_st_mn_*      multinomial resampling (src/resampling.cpp:5-13): the n uniforms drawn already sorted (partial sums
+//                  of exponential spacings), served by k_st_resample like the stratified positions.
 // Log-weights and the cdf never touch HBM (the weight is recomputed from x and y: a few flops
 // against 8 bytes), so the traffic is 16 B per resampled particle-timestep against the 40 B of the
 // algorithmic model.
