@@ -606,14 +606,25 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
   L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
   L.hist = cfg->return_particles; L.T = T; L.engine = cfg->engine;
-  bool pinned_ph = false, pinned_wh = false;
+  // the caller's history buffers stay pinned for exactly this call, whichever way it ends (an error return included: the guard
+  // drains both streams first, so no copy is in flight into memory it un-pins)
+  struct HostPins {
+    bssm_ctx* ctx; void* p[2] = {nullptr, nullptr};
+    ~HostPins() {
+      if (!p[0] && !p[1]) return;
+      cudaStreamSynchronize(ctx->stream);
+      if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+      for (void* q : p) if (q) cudaHostUnregister(q);
+      cudaGetLastError();
+    }
+  } pins{ctx};
   if (cfg->return_particles) {
     // rows stream to the caller's buffers while the filter runs: pin them for the call (a pageable destination still works, the
     // copies then stage through the driver's own pinned buffer and the copy stream runs behind)
     L.h_particles_history = res->particles_history; L.h_weights_history = res->weights_history;
     const size_t T1h = (size_t)T + 1;
-    if (res->particles_history) { pinned_ph = cudaHostRegister(res->particles_history, (size_t)C * T1h * d * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess; }
-    if (res->weights_history) { pinned_wh = cudaHostRegister(res->weights_history, (size_t)C * T1h * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess; }
+    if (res->particles_history && cudaHostRegister(res->particles_history, (size_t)C * T1h * d * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) pins.p[0] = res->particles_history;
+    if (res->weights_history && cudaHostRegister(res->weights_history, (size_t)C * T1h * N * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) pins.p[1] = res->weights_history;
     cudaGetLastError();   // a refused registration is not an error of the call
   }
   const bool need_aux = cfg->algorithm == BSSM_APF;
@@ -683,8 +694,6 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
 #undef DL
   cudaError_t e_sync = cudaStreamSynchronize(st);
   if (e_sync == cudaSuccess && cfg->return_particles && ctx->copy_stream) e_sync = cudaStreamSynchronize(ctx->copy_stream);
-  if (pinned_ph) cudaHostUnregister(res->particles_history);
-  if (pinned_wh) cudaHostUnregister(res->weights_history);
   BSSM_CK(e_sync);
   BSSM_CK(cudaEventElapsedTime(&res->kernel_ms, ctx->ev0, ctx->ev1));
   return BSSM_OK;

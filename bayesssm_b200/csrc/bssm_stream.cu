@@ -168,7 +168,13 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     for (int c0 = 0; c0 < C; c0 += per) {
       int cb = C - c0 < per ? C - c0 : per, T = L.T;
       void* args[] = {&P, &c0, &T};
-      BSSM_CK(cudaLaunchCooperativeKernel(K.chain, dim3((unsigned int)((size_t)cb * P.bpc)), dim3(ST_THREADS), args, 0, st));
+      const cudaError_t ce = cudaLaunchCooperativeKernel(K.chain, dim3((unsigned int)((size_t)cb * P.bpc)), dim3(ST_THREADS), args, 0, st);
+      if (ce == cudaErrorCooperativeLaunchTooLarge && c0 == 0) {   // fewer resident blocks than the occupancy query promised (a shared
+        cudaGetLastError();                                         // GPU): nothing has run yet -- the launch-per-body form serves any bpc
+        chain = false;
+        break;
+      }
+      BSSM_CK(ce);
       BSSM_LAUNCH(ctx, "k_st_chain");
     }
   }

@@ -117,6 +117,24 @@ def main():
             if what:
                 bad += 1
                 print("STREAM MISMATCH", what, sargs, thetas, flush=True)
+            # the same configuration on the chain-persistent kernel (cooperative launches over groups of filters, concurrent blocks)
+            if world == 1 and T > 0:
+                cenv = dict(env or os.environ, EMU_CHAIN=str(int(rng.integers(1, C + 1))))
+                recs, err = call(hs, sargs, y, thetas, cenv)
+                what = err or next((d for r in recs if (d := cmp(r, refs[r["filter"]]))), "")
+                if what:
+                    bad += 1
+                    print("CHAIN KERNEL MISMATCH", what, sargs, cenv["EMU_CHAIN"], thetas, flush=True)
+            # multinomial by sorted uniforms on the streaming engine (oracle: resample_fn 3 restates the same variant)
+            if world == 1 and ralg != 0 and rng.random() < 0.5:
+                mrefs = [oracle.particle_filter(model, 0, ralg, 3, ns[c], y, thetas[c], threshold=thr, obs_times=ot, seed=seed, run_id=run_id, stream=sb + c)
+                         for c in range(C)]
+                margs = list(sargs); margs[7] = 2
+                recs, err = call(hs, margs, y, thetas, env)
+                what = err or next((d for r in recs if (d := cmp(r, mrefs[r["filter"]]))), "")
+                if what:
+                    bad += 1
+                    print("MULTINOMIAL MISMATCH", what, margs, thetas, flush=True)
             # persistent kernel
             variant = int(rng.integers(0, 2)) + (2 if args.f32 else 0)
             G = int(rng.integers(1, 6))
