@@ -81,12 +81,17 @@ __device__ __forceinline__ void acc_init(Acc& a) {
   a.m = -__longlong_as_double(0x7FF0000000000000LL); a.s = 0; a.q = 0; a.nan = 0;
   a.sx[0] = a.sx[1] = a.sx[2] = a.sx[3] = 0;
 }
+// F32: the rescaling factors by the SFU exp of the throughput precision (the per-particle terms were formed that way too); the
+// fp64 exp costs ~5x the rest of a merge, and a block reduction merges ten times per thread
+template <bool F32 = false>
 __device__ __forceinline__ void acc_merge(Acc& a, const Acc& b, int d) {
   a.nan |= b.nan;
   if (b.s == 0.0 && b.q == 0.0 && !(b.m > a.m) && b.sx[0] == 0.0 && b.sx[1] == 0.0 && b.sx[2] == 0.0 && b.sx[3] == 0.0) return;
   double m = a.m > b.m ? a.m : b.m;
   if (m == -__longlong_as_double(0x7FF0000000000000LL)) { a.m = m; return; }
-  double ea = (a.m == m) ? 1.0 : exp(a.m - m), eb = (b.m == m) ? 1.0 : exp(b.m - m);
+  double ea, eb;
+  if constexpr (F32) { ea = (a.m == m) ? 1.0 : (double)Math<float>::exp_((float)(a.m - m)); eb = (b.m == m) ? 1.0 : (double)Math<float>::exp_((float)(b.m - m)); }
+  else { ea = (a.m == m) ? 1.0 : exp(a.m - m); eb = (b.m == m) ? 1.0 : exp(b.m - m); }
   a.s = a.s * ea + b.s * eb;
   a.q = a.q * (ea * ea) + b.q * (eb * eb);
   for (int k = 0; k < d; k++) a.sx[k] = a.sx[k] * ea + b.sx[k] * eb;
@@ -117,16 +122,17 @@ __device__ __forceinline__ Acc acc_shfl_down(const Acc& a, int o) {
   return b;
 }
 // deterministic block reduction (fixed tree); result valid in thread 0
+template <bool F32 = false>
 __device__ __forceinline__ void acc_block_reduce(Acc& a, int d, Acc* sm /* >= 32 */) {
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  for (int o = 16; o; o >>= 1) { Acc b = acc_shfl_down(a, o); if (lane + o < 32) acc_merge(a, b, d); }
+  for (int o = 16; o; o >>= 1) { Acc b = acc_shfl_down(a, o); if (lane + o < 32) acc_merge<F32>(a, b, d); }
   __syncthreads();
   if (lane == 0) sm[wid] = a;
   __syncthreads();
   if (wid == 0) {
     Acc t;
     if (lane < nw) t = sm[lane]; else acc_init(t);
-    for (int o = 16; o; o >>= 1) { Acc b = acc_shfl_down(t, o); if (lane + o < 32) acc_merge(t, b, d); }
+    for (int o = 16; o; o >>= 1) { Acc b = acc_shfl_down(t, o); if (lane + o < 32) acc_merge<F32>(t, b, d); }
     a = t;
   }
 }
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_init(FilterDev f) {
     for (int k = 0; k < Model::D; k++) { x[(size_t)k * f.N + i] = xi[k]; a.sx[k] += (double)xi[k]; }
     a.s += 1.0;
   }
-  acc_block_reduce(a, Model::D, sm);
+  acc_block_reduce<sizeof(Real) == 4>(a, Model::D, sm);
   if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_init(FilterDev f) {
 //        2 = log_likelihood - gathered aux (:169-175)
 enum { WF_GAP = 1, WF_SECOND = 2 };
 template <typename Model, typename Real>
-__global__ void __launch_bounds__(FT_THREADS) k_weight(FilterDev f, int obs, int flags, int wkind) {
+__global__ void __launch_bounds__(FT_THREADS, 3) k_weight(FilterDev f, int obs, int flags, int wkind) {
   __shared__ Acc sm[32];
   int c = blockIdx.x;   // filter in grid.x (no 65535 limit), block within the filter in grid.y
   if (!f.alive[c]) return;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_weight(FilterDev f, int obs, int
     lw[i] = l;
     acc_add<Real>(a, l, xi, Model::D);
   }
-  acc_block_reduce(a, Model::D, sm);
+  acc_block_reduce<sizeof(Real) == 4>(a, Model::D, sm);
   if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_post(FilterDev f, int obs) {
     }
     for (int k = 0; k < Model::D; k++) a.sx[k] += (double)xi[k];
   }
-  acc_block_reduce(a, Model::D, sm);
+  acc_block_reduce<sizeof(Real) == 4>(a, Model::D, sm);
   if (threadIdx.x == 0) acc_store(a, f.part + ((size_t)c * f.nblk + blockIdx.y) * PART_W);
 }
 

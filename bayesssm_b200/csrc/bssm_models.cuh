@@ -128,6 +128,14 @@ struct ModelSirCB {
     x[0] = par[2] - par[3]; x[1] = par[3];
   }
   template <typename R> static BSSM_DEV void transition(R* x, const R* par, int, const R*, const double* u) {
+    if constexpr (sizeof(R) == 4) {    // throughput precision: fp32 inversion on log(1 - p) = -rate (counts up to 2^24 are exact in fp32)
+      const float S = x[0], I = x[1];
+      if (I == 0.f) return;
+      const float ni = binom_inversion_f32(S, -par[0] * I * Math<float>::rcp_(par[2]), (float)u[0]);
+      const float nr = binom_inversion_f32(I, -par[1], (float)u[1]);
+      x[0] = S - ni; x[1] = I + ni - nr;
+      return;
+    }
     double S = (double)x[0], I = (double)x[1];
     if (I == 0.0) return;
     double p_inf = 1.0 - exp(-(double)par[0] * I / (double)par[2]);
@@ -140,6 +148,11 @@ struct ModelSirCB {
     return dpois_log<R>((R)y[0], x[1]);
   }
   template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
+    if constexpr (sizeof(R) == 4) {
+      const float S = x[0], I = x[1];
+      const float p_inf = 1.0f - Math<float>::exp_(-par[0] * I * Math<float>::rcp_(par[2])), p_rec = 1.0f - Math<float>::exp_(-par[1]);
+      return dpois_log<float>((float)y[0], I + S * p_inf - I * p_rec);
+    }
     double S = (double)x[0], I = (double)x[1];
     double p_inf = 1.0 - exp(-(double)par[0] * I / (double)par[2]), p_rec = 1.0 - exp(-(double)par[1]);
     return dpois_log<R>((R)y[0], (R)(I + S * p_inf - I * p_rec));

@@ -1,7 +1,9 @@
 """Configuration C4 (chain-binomial SIR, N = 2^18, general kernels): one APF / RMPF / BPF run each, for launch lists."""
 import sys, time
 import numpy as np
-sys.path.insert(0, "tests")
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import engine_helpers as eh
 from bayesssm_b200 import _native as nat
 
