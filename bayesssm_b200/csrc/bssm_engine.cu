@@ -188,26 +188,26 @@ static int run_filter_steps(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, 
   if (f.algorithm == BSSM_APF && !K.has_aux) { set_error("model has no aux_log_likelihood_fn"); return BSSM_ERR_UNSUPPORTED; }
   if (f.algorithm == BSSM_RMPF && !K.has_move) { set_error("model has no move_fn"); return BSSM_ERR_UNSUPPORTED; }
   BSSM_TRY(launch_init(ctx, K, grid, f));
-  k_finalize<<<f.C, 128, 0, st>>>(f, 0, 0);
+  k_finalize<sizeof(Real) == 4><<<f.C, 128, 0, st>>>(f, 0, 0);
   BSSM_LAUNCH(ctx, "k_finalize");
   if (L.hist) BSSM_TRY(hist_row_out<Real>(ctx, f, L, grid, 0));
   const bool may_resample = (f.algorithm == BSSM_RMPF) || (f.ralg != BSSM_SIS);
   for (int obs = 0; obs < L.T; obs++) {
     if (f.algorithm == BSSM_APF) {
       BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_GAP, 1));
-      k_finalize<<<f.C, 128, 0, st>>>(f, obs, 2);
+      k_finalize<sizeof(Real) == 4><<<f.C, 128, 0, st>>>(f, obs, 2);
       BSSM_LAUNCH(ctx, "k_finalize");
       BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 1, cdf));
       BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_SECOND, 2));
     } else {
       BSSM_TRY(launch_weight(ctx, K, grid, f, obs, WF_GAP, 0));
     }
-    k_finalize<<<f.C, 128, 0, st>>>(f, obs, 1);
+    k_finalize<sizeof(Real) == 4><<<f.C, 128, 0, st>>>(f, obs, 1);
     BSSM_LAUNCH(ctx, "k_finalize");
     if (may_resample) {
       BSSM_TRY(resample_stage<Real>(ctx, f, L, obs, 0, cdf));
       BSSM_TRY(launch_post(ctx, K, grid, f, obs));
-      k_finalize<<<f.C, 128, 0, st>>>(f, obs, 3);
+      k_finalize<sizeof(Real) == 4><<<f.C, 128, 0, st>>>(f, obs, 3);
       BSSM_LAUNCH(ctx, "k_finalize");
     }
     if (L.hist) BSSM_TRY(hist_row_out<Real>(ctx, f, L, grid, obs + 1));

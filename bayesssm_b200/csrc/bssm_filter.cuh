@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_weight(FilterDev f, int obs, 
 // ---- K3: per-filter finalise -------------------------------------------------------------------
 // kind 0: t = 0 bookkeeping (:106-116); 1: main weights (:189-224); 2: APF first stage (:152-155);
 // 3: after resampling (:222-223,237-241)
+// F32: the throughput precision merges the block records with the SFU exp (acc_merge)
+template <bool F32>
 static __global__ void __launch_bounds__(128) k_finalize(FilterDev f, int obs, int kind) {
   __shared__ Acc sm[32];
   int c = blockIdx.x;
@@ -246,9 +248,9 @@ static __global__ void __launch_bounds__(128) k_finalize(FilterDev f, int obs, i
   if (kind == 0 || kind == 3) a.m = 0.0;
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     Acc t; acc_load(t, f.part + ((size_t)c * f.nblk + b) * PART_W);
-    acc_merge(a, t, f.d);
+    acc_merge<F32>(a, t, f.d);
   }
-  acc_block_reduce(a, f.d, sm);
+  acc_block_reduce<F32>(a, f.d, sm);
   if (threadIdx.x) return;
   const int T1 = f.T + 1;
   if (kind == 0) {

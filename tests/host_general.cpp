@@ -112,7 +112,7 @@ static int run(char** argv) {
   // run_filter_steps() of bssm_engine.cu
   if ((algorithm == BSSM_APF && !Model::HAS_AUX) || (algorithm == BSSM_RMPF && !Model::HAS_MOVE)) return 3;
   const FilterDev fc = f;
-  auto finalize = [&](int obs, int kind) { emu_launch(C, 128, [&] { k_finalize(fc, obs, kind); }); };
+  auto finalize = [&](int obs, int kind) { emu_launch(C, 128, [&] { k_finalize<sizeof(Real) == 4>(fc, obs, kind); }); };
   auto weight = [&](int obs, int flags, int wkind) { emu_launch2d(C, f.nblk, FT_THREADS, [&] { k_weight<Model, Real>(fc, obs, flags, wkind); }); };
   emu_launch2d(C, f.nblk, FT_THREADS, [&] { k_init<Model, Real>(fc); });
   finalize(0, 0);
