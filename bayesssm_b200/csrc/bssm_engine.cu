@@ -417,6 +417,7 @@ void bssm_destroy(bssm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < SL_COUNT; i++) if (ctx->scratch[i].p) cudaFree(ctx->scratch[i].p);
   cudaEventDestroy(ctx->ev0);
+  if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_mn_start); for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_mn_ready[i]); cudaEventDestroy(ctx->ev_mn_free[i]); } }
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_row[i]); cudaEventDestroy(ctx->ev_free[i]); } }
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

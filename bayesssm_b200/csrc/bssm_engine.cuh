@@ -74,6 +74,8 @@ struct bssm_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;            // history rows travel on it (bssm_engine.cu: hist_row_out)
   cudaEvent_t ev_row[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaStream_t aux_stream = nullptr;             // streaming engine, multinomial: the positions of the next observation are laid out here
+  cudaEvent_t ev_mn_ready[2] = {nullptr, nullptr}, ev_mn_free[2] = {nullptr, nullptr}, ev_mn_start = nullptr;
   cudaDeviceProp prop;
   int64_t launches = 0;
   bssm::Scratch scratch[bssm::SL_COUNT];

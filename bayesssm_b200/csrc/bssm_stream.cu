@@ -135,9 +135,23 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     if (sh) { set_error("streaming engine: multinomial resampling is not available for the particle-sharded filter"); return BSSM_ERR_UNSUPPORTED; }
     // sorted uniforms from exponential spacings (bssm_stream.cuh): positions of the output slots + the scan of the spacings
     P.mn_nt = (cap + 1 + MN_TILE - 1) / MN_TILE + 1;
-    BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, (size_t)C * P.xstride, &P.mn_pos));
-    BSSM_TRY(scratch(ctx, SL_ST_BASE + 8, (size_t)C * P.mn_nt, &P.mn_tsum));
-    BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, (size_t)C, &P.mn_total));
+    // The positions of an observation's output slots depend on nothing but its index: they are laid out on a second stream
+    // while the main stream still propagates (double-buffered by the observation's parity, for every observation, since its
+    // resampling decision is not known yet) -- at N = 2^20 the three launches were half of an observation's time.
+    // Only where launches, not bytes, are what an observation costs (C2: 22.1 -> 29.8 G particle-timesteps/s; at N = 2^24 the
+    // positions of the 37 % of observations that do not resample are wasted bandwidth: 47.2 -> 42.9, profiles/r2_ab_multinomial.txt).
+    // BSSM_ST_MN_AHEAD=0 / 1: in line on the main stream and only for the filters that resample / ahead.
+    const char* e = getenv("BSSM_ST_MN_AHEAD");
+    P.mn_ahead = e ? (atoi(e) != 0) : ((long long)C * cap <= (1LL << 22));
+    const size_t rows = P.mn_ahead ? (size_t)2 * C : (size_t)C;
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 2, rows * P.xstride, &P.mn_pos));
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 8, rows * P.mn_nt, &P.mn_tsum));
+    BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, rows, &P.mn_total));
+    if (P.mn_ahead && !ctx->aux_stream) {
+      BSSM_CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+      BSSM_CK(cudaEventCreateWithFlags(&ctx->ev_mn_start, cudaEventDisableTiming));
+      for (int i = 0; i < 2; i++) { BSSM_CK(cudaEventCreateWithFlags(&ctx->ev_mn_ready[i], cudaEventDisableTiming)); BSSM_CK(cudaEventCreateWithFlags(&ctx->ev_mn_free[i], cudaEventDisableTiming)); }
+    }
   }
   P.dbg = nullptr;
 #ifdef BSSM_ST_CHAIN_TIMING
@@ -178,6 +192,24 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
       BSSM_LAUNCH(ctx, "k_st_chain");
     }
   }
+  auto mn_positions = [&](cudaStream_t s, int obs) -> int {
+    const dim3 gmn((unsigned int)C, (unsigned int)P.mn_nt);
+    k_st_mn_sums<<<gmn, MN_THREADS, 0, s>>>(P, obs);
+    BSSM_LAUNCH(ctx, "k_st_mn_sums");
+    k_st_mn_scan<<<C, MN_THREADS, 0, s>>>(P, obs);
+    BSSM_LAUNCH(ctx, "k_st_mn_scan");
+    k_st_mn_positions<<<gmn, MN_THREADS, 0, s>>>(P, obs);
+    BSSM_LAUNCH(ctx, "k_st_mn_positions");
+    return BSSM_OK;
+  };
+  if (mn && P.mn_ahead && may_resample && L.T > 0) {
+    // the second stream starts behind everything already queued on the main one (an earlier filter's resampling may still read
+    // the position buffers), with the positions of observation 0
+    BSSM_CK(cudaEventRecord(ctx->ev_mn_start, st));
+    BSSM_CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_mn_start, 0));
+    BSSM_TRY(mn_positions(ctx->aux_stream, 0));
+    BSSM_CK(cudaEventRecord(ctx->ev_mn_ready[0], ctx->aux_stream));
+  }
   for (int obs = 0; obs < L.T && !chain; obs++) {
     BSSM_TRY(st_launch(ctx, K.step, grid, ST_THREADS, P, &obs, "k_st_step", pdl && obs > 0));
     if (sh) {
@@ -186,16 +218,20 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
       BSSM_LAUNCH(ctx, "k_st_merge");
     }
     if (may_resample) {
-      if (mn) {   // the positions of this observation's output slots (the kernels return at once for filters that do not resample)
-        const dim3 gmn((unsigned int)C, (unsigned int)P.mn_nt);
-        k_st_mn_sums<<<gmn, MN_THREADS, 0, st>>>(P, obs);
-        BSSM_LAUNCH(ctx, "k_st_mn_sums");
-        k_st_mn_scan<<<C, MN_THREADS, 0, st>>>(P, obs);
-        BSSM_LAUNCH(ctx, "k_st_mn_scan");
-        k_st_mn_positions<<<gmn, MN_THREADS, 0, st>>>(P, obs);
-        BSSM_LAUNCH(ctx, "k_st_mn_positions");
+      if (mn && !P.mn_ahead) {   // the positions of this observation's output slots (the kernels return at once for filters that do not resample)
+        BSSM_TRY(mn_positions(st, obs));
+      } else if (mn) {
+        // observation obs + 1's positions go out now (their buffer is free once the resampling of obs - 1 has run); this
+        // observation's were laid out an observation ago
+        if (obs + 1 < L.T) {
+          if (obs >= 1) BSSM_CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_mn_free[(obs + 1) & 1], 0));
+          BSSM_TRY(mn_positions(ctx->aux_stream, obs + 1));
+          BSSM_CK(cudaEventRecord(ctx->ev_mn_ready[(obs + 1) & 1], ctx->aux_stream));
+        }
+        BSSM_CK(cudaStreamWaitEvent(st, ctx->ev_mn_ready[obs & 1], 0));
       }
       BSSM_TRY(st_launch(ctx, K.resample, grid, ST_THREADS, P, &obs, "k_st_resample", pdl && !mn));
+      if (mn && P.mn_ahead) BSSM_CK(cudaEventRecord(ctx->ev_mn_free[obs & 1], st));
     }
   }
   if (P.dbg && chain) {

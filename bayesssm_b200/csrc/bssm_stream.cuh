@@ -92,6 +92,8 @@ struct StreamParams {
   double* mn_tsum;         // [C][mn_nt] sums of the spacings of 1024 slots; after the scan: their exclusive prefix
   double* mn_total;        // [C] sum of all n + 1 spacings
   int mn_nt;               // 1024-slot tiles of spacings per filter row
+  int mn_ahead;            // 1: the three arrays above are doubled by the observation's parity and laid out for EVERY observation, ahead of
+                           // its resampling decision, on a second stream (one GPU); 0: in line, only where a filter resamples
   // Philox round keys of the launch-wide key word (seed_lo + r * 0x9E3779B9): operands straight from the constant bank
   unsigned int rk0[10];
   // chain-persistent kernel (k_st_chain): per-filter barrier words between the blocks of a filter
@@ -703,28 +705,30 @@ __device__ __forceinline__ double st_mn_block_sum(double v, double* s_w /*[MN_TH
   for (int w = 0; w < MN_THREADS / 32; w++) t += s_w[w];
   return t;
 }
+// first row of the observation's copy of the multinomial arrays ([2][C] rows when they are laid out ahead, by parity)
+__device__ __forceinline__ int st_mn_row(const StreamParams& P, int obs) { return P.mn_ahead ? (obs & 1) * P.f.C : 0; }
 static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_sums(StreamParams P, int obs) {
   __shared__ double s_w[MN_THREADS / 32];
   const FilterDev& f = P.f;
   const int c = blockIdx.x, tile = blockIdx.y;
-  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  if (!P.mn_ahead && (!f.alive[c] || !P.res[(obs & 1) * f.C + c])) return;
   const int n = filt_n(f, c);
   if ((long long)tile * MN_TILE > n) return;
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
   double e[4];
   st_mn_spacings(key, (unsigned int)obs, tile * MN_TILE + 4 * threadIdx.x, n, e);
   const double t = st_mn_block_sum((e[0] + e[1]) + (e[2] + e[3]), s_w);
-  if (threadIdx.x == 0) P.mn_tsum[(size_t)c * P.mn_nt + tile] = t;
+  if (threadIdx.x == 0) P.mn_tsum[((size_t)st_mn_row(P, obs) + c) * P.mn_nt + tile] = t;
 }
 // exclusive prefix of a filter's tile sums (in place) and their total: one block per filter, 256 tiles per round
 static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_scan(StreamParams P, int obs) {
   __shared__ double s_w[MN_THREADS / 32];
   const FilterDev& f = P.f;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  if (!P.mn_ahead && (!f.alive[c] || !P.res[(obs & 1) * f.C + c])) return;
   const int n = filt_n(f, c);
   const int ntile = n / MN_TILE + 1;          // tiles that hold one of the slots 0 .. n
-  double* ts = P.mn_tsum + (size_t)c * P.mn_nt;
+  double* ts = P.mn_tsum + ((size_t)st_mn_row(P, obs) + c) * P.mn_nt;
   double carry = 0.0;
   for (int b0 = 0; b0 < ntile; b0 += MN_THREADS) {
     const int t = b0 + tid;
@@ -739,13 +743,13 @@ static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_scan(StreamParams P
     if (t < ntile) ts[t] = carry + (woff + (inc - v));
     carry += tot;
   }
-  if (tid == 0) P.mn_total[c] = carry;
+  if (tid == 0) P.mn_total[st_mn_row(P, obs) + c] = carry;
 }
 static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_positions(StreamParams P, int obs) {
   __shared__ double s_w[MN_THREADS / 32];
   const FilterDev& f = P.f;
   const int c = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (!f.alive[c] || !P.res[(obs & 1) * f.C + c]) return;
+  if (!P.mn_ahead && (!f.alive[c] || !P.res[(obs & 1) * f.C + c])) return;
   const int n = filt_n(f, c);
   if ((long long)tile * MN_TILE >= n) return;
   const NoiseKey key = make_key(f.seed, f.run_id[c], f.stream[c]);
@@ -759,9 +763,9 @@ static __global__ void __launch_bounds__(MN_THREADS) k_st_mn_positions(StreamPar
   double woff = 0.0;
 #pragma unroll
   for (int w = 0; w < MN_THREADS / 32; w++) if (w < wid) woff += s_w[w];
-  double cum = P.mn_tsum[(size_t)c * P.mn_nt + tile] + (woff + (inc - run));
-  const double total = P.mn_total[c];
-  double* pos = P.mn_pos + (size_t)c * P.xstride;
+  double cum = P.mn_tsum[((size_t)st_mn_row(P, obs) + c) * P.mn_nt + tile] + (woff + (inc - run));
+  const double total = P.mn_total[st_mn_row(P, obs) + c];
+  double* pos = P.mn_pos + ((size_t)st_mn_row(P, obs) + c) * P.xstride;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     cum += e[k];
@@ -916,7 +920,7 @@ __device__ __forceinline__ int st_resample_body(const StreamParams& P, int obs, 
     sc.u_base = max(0, (i0 & ~3) - 4);
   }
   const bool MN = P.resample_fn == 2;
-  const double* const mpos = P.mn_pos + (size_t)c * P.xstride;   // multinomial: the sorted positions of the output slots
+  const double* const mpos = P.mn_pos + ((size_t)(P.mn_ahead ? (obs & 1) * f.C : 0) + c) * P.xstride;   // multinomial: the sorted positions of the output slots
   int o_lo, o_hi, mn_cnt = 0;
   if (MN) {
     // output range of the tile: counts of positions below its cdf interval's ends (warp 0; the neighbouring tile / block

@@ -99,7 +99,9 @@ static int run(int argc, char** argv) {
     P.dbg = nullptr;
     if (rfn == 2) {   // multinomial: positions of the output slots + the scan of the spacings (stream_launch, bssm_stream.cu)
       P.mn_nt = (cap + 1 + MN_TILE - 1) / MN_TILE + 1;
-      R.mn_pos.assign((size_t)C * P.xstride, -1.0); R.mn_tsum.assign((size_t)C * P.mn_nt, -1.0); R.mn_total.assign(C, -1.0);
+      P.mn_ahead = getenv("EMU_MN_AHEAD") ? 1 : 0;      // one GPU: the arrays doubled by parity, laid out for every observation
+      const size_t rows = P.mn_ahead ? (size_t)2 * C : (size_t)C;
+      R.mn_pos.assign(rows * P.xstride, -1.0); R.mn_tsum.assign(rows * P.mn_nt, -1.0); R.mn_total.assign(rows, -1.0);
       P.mn_pos = R.mn_pos.data(); P.mn_tsum = R.mn_tsum.data(); P.mn_total = R.mn_total.data();
     }
   }

@@ -27,7 +27,7 @@ def host_stream(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_stream.cpp")], check=True)
 
     def run(model, N, y, thetas, precision=64, threads=256, bpc=2, resample_fn=0, resample_algorithm=2, threshold=-1.0,
-            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=(), obs_times=None, chain=0):
+            seed=1405, run_id=2, stream_base=3, world=1, capacity_factor=1.5, block_order=0, n_per=(), obs_times=None, chain=0, mn_ahead=False):
         y = np.ascontiguousarray(y, dtype=np.float64)
         th = np.zeros((len(thetas), 3))
         for c, t in enumerate(thetas):
@@ -37,6 +37,8 @@ def host_stream(tmp_path_factory):
         env = dict(os.environ)
         if obs_times is not None:
             env["EMU_OBS_TIMES"] = ",".join(str(int(t)) for t in obs_times)
+        if mn_ahead:   # multinomial: position arrays doubled by the observation's parity and laid out for every observation
+            env["EMU_MN_AHEAD"] = "1"
         if chain:      # the chain-persistent kernel k_st_chain: cooperative launches over groups of `chain` filters
             env["EMU_CHAIN"] = str(chain)
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + th.tobytes(), capture_output=True, timeout=600, env=env)
@@ -203,6 +205,9 @@ def test_multinomial_by_sorted_uniforms_matches_the_oracle(orc, host_stream, N, 
     y = sim_y(AR, T, np.random.default_rng(N))
     ref = orc.particle_filter(AR, 0, ralg, 3, N, y, THETA[AR], seed=1405, run_id=2, stream=3)
     rec, = host_stream(AR, N, y, [THETA[AR]], threads=threads, bpc=bpc, resample_fn=2, resample_algorithm=ralg)
+    check(rec, ref)
+    # the layout of the one-GPU launcher: positions of every observation, buffers doubled by the observation's parity
+    rec, = host_stream(AR, N, y, [THETA[AR]], threads=threads, bpc=bpc, resample_fn=2, resample_algorithm=ralg, mn_ahead=True)
     check(rec, ref)
 
 
