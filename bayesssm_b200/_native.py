@@ -20,7 +20,7 @@ SIS, SISR, SISAR = 0, 1, 2
 STRATIFIED, SYSTEMATIC, MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
 ENGINE_AUTO, ENGINE_GENERAL, ENGINE_PERSISTENT, ENGINE_STREAM = 0, 1, 2, 3
-MODEL_AR_SIN, MODEL_LG, MODEL_RW_DRIFT, MODEL_SIR_CB, MODEL_AR_COS, MODEL_RW2D = range(6)
+MODEL_AR_SIN, MODEL_LG, MODEL_RW_DRIFT, MODEL_SIR_CB, MODEL_AR_COS, MODEL_RW2D, MODEL_SIR_GILLESPIE = range(7)
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_EXP, PRIOR_UNIF, PRIOR_HALFNORMAL = range(5)
 TR_IDENTITY, TR_LOG, TR_LOGIT = range(3)
 

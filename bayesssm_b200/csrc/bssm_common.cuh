@@ -20,6 +20,7 @@ namespace bssm {
 enum : uint32_t {
   TAG_INIT_Z = 1, TAG_TRANS_Z = 2, TAG_TRANS2_Z = 3, TAG_RESAMP_U = 4, TAG_RESAMP_AUX_U = 5,
   TAG_MOVE_Z = 6, TAG_MOVE_U = 7, TAG_TRANS_U = 8, TAG_TRANS2_U = 9, TAG_INIT_U = 10,
+  TAG_TRANS_DYN = 11, TAG_TRANS2_DYN = 12,   // uniforms on demand (DynU): a transition that draws a data-dependent number of them
   TAG_THETA_Z = 16, TAG_THETA_U = 17
 };
 constexpr uint32_t T_INIT = 0xFFFFFFFFu;
@@ -57,6 +58,21 @@ BSSM_HD uint4x noise_quad(const NoiseKey& k, uint32_t t, uint32_t tag, uint32_t 
   return philox4x32_10(quad, t, k.stream, tag | (slot << 8), k.k0, k.k1);
 }
 BSSM_HD double word_to_unit_f64(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+// Uniforms on demand for ONE particle's transition (models with DYN_U, e.g. an exact Gillespie step): uniform k is word k & 3 of
+// Philox(counter = (particle, t, stream, tag | (k >> 2) << 8)) -- the particle index itself in the first counter word, a tag of its own.
+// Philox mode only (injected noise buffers have a fixed number of slots).
+struct DynU {
+  NoiseKey key; uint32_t t, tag, particle; uint4x q; int have;
+  BSSM_HD DynU(const NoiseKey& k, uint32_t t_, uint32_t tag_, uint32_t particle_) : key(k), t(t_), tag(tag_), particle(particle_), have(-1) { q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0u; }
+  BSSM_HD double operator()(int k) {
+    const int call = k >> 2;
+    if (call != have) { q = philox4x32_10(particle, t, key.stream, tag | ((uint32_t)call << 8), key.k0, key.k1); have = call; }
+    return word_to_unit_f64(q.w[k & 3]);
+  }
+};
+// does a model draw its transition uniforms on demand?  (built-in and NVRTC user models alike: the member is optional)
+template <typename M, typename = void> struct ModelDynU { static constexpr bool value = false; };
+template <typename M> struct ModelDynU<M, decltype((void)M::DYN_U)> { static constexpr bool value = M::DYN_U; };
 BSSM_HD float word_to_unit_f32(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 // ---- math wrappers templated on the state precision ----

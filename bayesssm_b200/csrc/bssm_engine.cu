@@ -236,6 +236,7 @@ int model_dims(bssm_ctx* ctx, int model, int* d, int* ntheta, int* nconst) {
     case BSSM_MODEL_SIR_CB: MD(ModelSirCB)
     case BSSM_MODEL_AR_COS: MD(ModelArCos)
     case BSSM_MODEL_RW2D: MD(ModelRw2D)
+    case BSSM_MODEL_SIR_GILLESPIE: MD(ModelSirGillespie)
   }
 #undef MD
   set_error("unknown model id %d", model);
@@ -295,6 +296,7 @@ int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* c
     case BSSM_MODEL_SIR_CB: return run_filter_model<ModelSirCB>(ctx, f, L, cdf);
     case BSSM_MODEL_AR_COS: return run_filter_model<ModelArCos>(ctx, f, L, cdf);
     case BSSM_MODEL_RW2D: return run_filter_model<ModelRw2D>(ctx, f, L, cdf);
+    case BSSM_MODEL_SIR_GILLESPIE: return run_filter_model<ModelSirGillespie>(ctx, f, L, cdf);
   }
   set_error("unknown model id %d", L.model);
   return BSSM_ERR_BAD_ARG;
@@ -579,6 +581,10 @@ static int filter_validate(const bssm_filter_config* cfg) {
   if (cfg->num_filters < 1) { set_error("num_filters must be >= 1"); return BSSM_ERR_BAD_ARG; }
   if (cfg->algorithm < 0 || cfg->algorithm > 2 || cfg->resample_algorithm < 0 || cfg->resample_algorithm > 2 ||
       cfg->resample_fn < 0 || cfg->resample_fn > 2) { set_error("unknown algorithm / resample_algorithm / resample_fn"); return BSSM_ERR_BAD_ARG; }
+  if (cfg->model == BSSM_MODEL_SIR_GILLESPIE && cfg->noise) {
+    set_error("model %d draws a data-dependent number of uniforms per transition: injected noise buffers are not supported", cfg->model);
+    return BSSM_ERR_UNSUPPORTED;
+  }
   if (cfg->obs_times) {
     int prev = 1;   // R/particle_filter_core.R:69: checkmate::assert_integerish(obs_times, lower = 1, sorted = TRUE)
     for (int i = 0; i < cfg->num_obs; i++) {
@@ -759,6 +765,7 @@ int bssm_model_noise_dims(bssm_ctx* ctx, int model, int* nz_init, int* nu_init, 
     case BSSM_MODEL_SIR_CB: ND(ModelSirCB)
     case BSSM_MODEL_AR_COS: ND(ModelArCos)
     case BSSM_MODEL_RW2D: ND(ModelRw2D)
+    case BSSM_MODEL_SIR_GILLESPIE: ND(ModelSirGillespie)
   }
 #undef ND
   set_error("unknown model id %d", model);

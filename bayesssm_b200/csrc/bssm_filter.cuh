@@ -208,15 +208,25 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_weight(FilterDev f, int obs, 
     double u[Model::NU_TRANS > 0 ? Model::NU_TRANS : 1];
     if (flags & WF_GAP) {
       for (int tnow = prev_t + 1; tnow <= ot; tnow++) {
+        if constexpr (ModelDynU<Model>::value) {      // uniforms on demand (Philox mode only: checked on the host)
+          DynU du(key, (unsigned int)(tnow - 1), TAG_TRANS_DYN, (unsigned int)i);
+          Model::template transition_dyn<Real>(xi, par, tnow, du);
+          continue;
+        }
         for (int s = 0; s < Model::NZ_TRANS; s++) z[s] = noise_normal<Real>(f, key, f.noise.z_trans, Model::NZ_TRANS, TAG_TRANS_Z, (unsigned int)(tnow - 1), tnow - 1, s, i);
         for (int s = 0; s < Model::NU_TRANS; s++) u[s] = noise_uniform(f, key, f.noise.u_trans, Model::NU_TRANS, TAG_TRANS_U, (unsigned int)(tnow - 1), tnow - 1, s, i);
         Model::template transition<Real>(xi, par, tnow, z, u);
       }
     }
     if (flags & WF_SECOND) {
-      for (int s = 0; s < Model::NZ_TRANS; s++) z[s] = noise_normal<Real>(f, key, f.noise.z_trans2, Model::NZ_TRANS, TAG_TRANS2_Z, (unsigned int)obs, obs, s, i);
-      for (int s = 0; s < Model::NU_TRANS; s++) u[s] = noise_uniform(f, key, f.noise.u_trans2, Model::NU_TRANS, TAG_TRANS2_U, (unsigned int)obs, obs, s, i);
-      Model::template transition<Real>(xi, par, ot, z, u);
+      if constexpr (ModelDynU<Model>::value) {
+        DynU du(key, (unsigned int)obs, TAG_TRANS2_DYN, (unsigned int)i);
+        Model::template transition_dyn<Real>(xi, par, ot, du);
+      } else {
+        for (int s = 0; s < Model::NZ_TRANS; s++) z[s] = noise_normal<Real>(f, key, f.noise.z_trans2, Model::NZ_TRANS, TAG_TRANS2_Z, (unsigned int)obs, obs, s, i);
+        for (int s = 0; s < Model::NU_TRANS; s++) u[s] = noise_uniform(f, key, f.noise.u_trans2, Model::NU_TRANS, TAG_TRANS2_U, (unsigned int)obs, obs, s, i);
+        Model::template transition<Real>(xi, par, ot, z, u);
+      }
     }
     if (flags) for (int k = 0; k < Model::D; k++) x[(size_t)k * f.N + i] = xi[k];
     Real l;

@@ -165,6 +165,32 @@ struct ModelSirCB {
   }
 };
 
+// Stochastic SIR with the EXACT (Gillespie) daily step of the reference's vignette
+// (vignettes/articles/stochastic-sir-model.Rmd:152-176: epidemic_step): competing exponential clocks for infection
+// (rate lambda s i / pop) and removal (rate gamma i) until the day is over; two uniforms per event, drawn on demand (DynU).
+// Initial state, observation model, auxiliary predictor and move as the chain-binomial model above.
+struct ModelSirGillespie : ModelSirCB {
+  static constexpr int NU_TRANS = 0;
+  static constexpr bool DYN_U = true;
+  template <typename R> static BSSM_DEV void transition_dyn(R* x, const R* par, int, DynU& du) {
+    // always fp64: the event times of a day sum to ~1 and the comparison t + dt > 1 ends the loop; the work is the
+    // data-dependent event count (tens to hundreds of events per particle and day), not the arithmetic
+    double s = (double)x[0], i = (double)x[1], t = 0.0;
+    const double lam = (double)par[0] / (double)par[2], gam = (double)par[1];
+    const int max_events = 2 * (int)par[2] + 8;          // s + 2 i <= 2 pop events can happen at all
+    for (int e = 0; e < max_events && i > 0.0; e++) {
+      const double rate_inf = lam * s * i, rate_rem = gam * i, rate = rate_inf + rate_rem;
+      if (!(rate > 0.0)) break;
+      const double dt = -log(du(2 * e)) / rate;           // rexp(1, rate)
+      if (t + dt > 1.0) break;
+      t += dt;
+      if (du(2 * e + 1) < rate_inf / rate) { s -= 1.0; i += 1.0; } else { i -= 1.0; }
+    }
+    x[0] = (R)s; x[1] = (R)i;
+  }
+  template <typename R> static BSSM_DEV void transition(R*, const R*, int, const R*, const double*) {}   // (never called: DYN_U)
+};
+
 // tests/testthat/test-bootstrap_filter.R:211-217, test-pmmh.R:622-628: 2-D random walk, flat likelihood
 struct ModelRw2D {
   static constexpr int D = 2, NTHETA = 1, NCONST = 0, NZ_INIT = 2, NU_INIT = 0, NZ_TRANS = 2, NU_TRANS = 0,

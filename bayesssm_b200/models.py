@@ -72,13 +72,20 @@ def sir_chain_binomial():
     return DeviceModel("sir_chain_binomial", nat.MODEL_SIR_CB, ("lambda", "gamma"), ("pop", "I0"), dim=2)
 
 
+def sir_gillespie():
+    """The same SIR model with the exact (Gillespie) daily step of the reference's vignette
+    (vignettes/articles/stochastic-sir-model.Rmd:152-176, `epidemic_step`): a data-dependent number of uniforms per
+    transition, drawn on demand from the particle's Philox stream."""
+    return DeviceModel("sir_gillespie", nat.MODEL_SIR_GILLESPIE, ("lambda", "gamma"), ("pop", "I0"), dim=2)
+
+
 def random_walk_2d():
     """tests/testthat/test-bootstrap_filter.R:211-217: 2-D random walk, flat likelihood."""
     return DeviceModel("random_walk_2d", nat.MODEL_RW2D, ("phi",), dim=2, has_aux=False, has_move=False)
 
 
 BUILTIN = {m().name: m for m in (nonlinear_ar, nonlinear_ar_cos_obs, linear_gaussian, random_walk_drift,
-                                 sir_chain_binomial, random_walk_2d)}
+                                 sir_chain_binomial, sir_gillespie, random_walk_2d)}
 
 
 def resolve_model(*fns) -> DeviceModel:

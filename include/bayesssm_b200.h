@@ -49,6 +49,8 @@ enum {
   BSSM_MODEL_LG = 1,       /* tests/testthat/test-pmmh_tuning.R:163   theta = (phi, sigma_x, sigma_y) */
   BSSM_MODEL_RW_DRIFT = 2, /* tests/testthat/test-auxiliary_filter.R  theta = (mu, sigma)             */
   BSSM_MODEL_SIR_CB = 3,   /* chain-binomial SIR, Poisson obs         theta = (lambda, gamma), consts = (pop, I0) */
+  BSSM_MODEL_SIR_GILLESPIE = 6, /* the same model with the exact (Gillespie) daily step of vignettes/articles/stochastic-sir-model.Rmd:152-176;
+                               Philox noise only (a data-dependent number of uniforms per transition) */
   BSSM_MODEL_AR_COS = 4,   /* R/pmmh.R:157-159                         theta = (phi, sigma_x, sigma_y) */
   BSSM_MODEL_RW2D = 5,     /* tests/testthat/test-bootstrap_filter.R:211  theta = (phi)               */
   BSSM_MODEL_BUILTIN_COUNT = 6

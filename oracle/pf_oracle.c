@@ -258,6 +258,7 @@ double orc_noise_normal(uint64_t seed, uint32_t run_id, uint32_t stream, uint32_
 enum {
   TAG_INIT_Z = 1, TAG_TRANS_Z = 2, TAG_TRANS2_Z = 3, TAG_RESAMP_U = 4, TAG_RESAMP_AUX_U = 5,
   TAG_MOVE_Z = 6, TAG_MOVE_U = 7, TAG_TRANS_U = 8, TAG_TRANS2_U = 9, TAG_INIT_U = 10,
+  TAG_TRANS_DYN = 11, TAG_TRANS2_DYN = 12,
   TAG_THETA_Z = 16, TAG_THETA_U = 17
 };
 #define T_INIT 0xFFFFFFFFu
@@ -306,6 +307,8 @@ static int get_dims(int model, model_dims *m) {
       m->d = 1; m->ntheta = 2; m->nz_init = 1; m->nz_trans = 1; m->nz_move = 1; m->nu_move = 1; return 0;
     case ORC_MODEL_SIR_CB:
       m->d = 2; m->ntheta = 2; m->nconst = 2; m->nu_trans = 2; m->nu_move = 2; return 0;
+    case ORC_MODEL_SIR_GILLESPIE: /* uniforms on demand (dyn_u), none by slot */
+      m->d = 2; m->ntheta = 2; m->nconst = 2; m->nu_move = 2; return 0;
     case ORC_MODEL_RW2D:
       m->d = 2; m->ntheta = 1; m->nz_init = 2; m->nz_trans = 2; return 0;
   }
@@ -326,16 +329,39 @@ static void model_init(int model, double *x, const double *th, const double *z, 
   switch (model) {
     case ORC_MODEL_AR_SIN: case ORC_MODEL_LG: case ORC_MODEL_AR_COS: case ORC_MODEL_RW_DRIFT:
       x[0] = 0.0 + 1.0 * z[0]; break; /* rnorm(N, 0, 1): README.md:137-139 */
-    case ORC_MODEL_SIR_CB:
+    case ORC_MODEL_SIR_CB: case ORC_MODEL_SIR_GILLESPIE:
       x[0] = th[2] - th[3]; x[1] = th[3]; break; /* stochastic-sir-model.Rmd:285-292 */
     case ORC_MODEL_RW2D:
       x[0] = z[0]; x[1] = z[1]; break; /* test-bootstrap_filter.R:211 */
   }
 }
+/* uniforms on demand for one particle's transition (engine: DynU, bssm_common.cuh): uniform k is word k & 3 of
+   Philox(ctr = (particle, t, stream, tag | (k >> 2) << 8)) */
+typedef struct { uint64_t seed; uint32_t run_id, stream, t, tag, particle; } dyn_u;
+static double dyn_uniform(const dyn_u *du, int k) {
+  uint32_t ctr[4] = {du->particle, du->t, du->stream, du->tag | ((uint32_t)(k >> 2) << 8)};
+  uint32_t key[2] = {(uint32_t)du->seed, (uint32_t)(du->seed >> 32) ^ du->run_id}, w[4];
+  orc_philox4x32_10(ctr, key, w);
+  return word_to_unit(w[k & 3]);
+}
 static void model_transition(int model, double *x, const double *th, int t, const double *z,
-                             const double *u) {
+                             const double *u, const dyn_u *du) {
   (void)t;
   switch (model) {
+    case ORC_MODEL_SIR_GILLESPIE: { /* stochastic-sir-model.Rmd:152-176: epidemic_step(state, lambda, gamma, n_total) */
+      double s = x[0], i = x[1], tt = 0.0;
+      const double lam = th[0] / th[2], gam = th[1];
+      const int max_events = 2 * (int)th[2] + 8;
+      for (int e = 0; e < max_events && i > 0.0; e++) {
+        const double rate_inf = lam * s * i, rate_rem = gam * i, rate = rate_inf + rate_rem;
+        if (!(rate > 0.0)) break;
+        const double dt = -log(dyn_uniform(du, 2 * e)) / rate; /* rexp(1, rate_total) */
+        if (tt + dt > 1.0) break;
+        tt += dt;
+        if (dyn_uniform(du, 2 * e + 1) < rate_inf / rate) { s -= 1.0; i += 1.0; } else { i -= 1.0; }
+      }
+      x[0] = s; x[1] = i; break;
+    }
     case ORC_MODEL_AR_SIN: case ORC_MODEL_AR_COS: /* README.md:140-143 */
       x[0] = th[0] * x[0] + sin(x[0]) + (0.0 + th[1] * z[0]); break;
     case ORC_MODEL_LG: /* test-pmmh_tuning.R:166-168 */
@@ -361,7 +387,7 @@ static double model_loglik(int model, const double *y, const double *x, const do
     case ORC_MODEL_AR_SIN: case ORC_MODEL_LG: return r_dnorm_log(y[0], x[0], th[2]); /* README.md:144-146 */
     case ORC_MODEL_AR_COS: return r_dnorm_log(y[0], cos(x[0]), th[2]); /* R/pmmh.R:157-159 */
     case ORC_MODEL_RW_DRIFT: return r_dnorm_log(y[0], x[0], th[1]);
-    case ORC_MODEL_SIR_CB: return r_dpois_log(y[0], x[1]); /* stochastic-sir-model.Rmd:306-309 */
+    case ORC_MODEL_SIR_CB: case ORC_MODEL_SIR_GILLESPIE: return r_dpois_log(y[0], x[1]); /* stochastic-sir-model.Rmd:306-309 */
     case ORC_MODEL_RW2D: return 1.0; /* test-bootstrap_filter.R:215 */
   }
   return NAN;
@@ -369,7 +395,7 @@ static double model_loglik(int model, const double *y, const double *x, const do
 static double model_aux_loglik(int model, const double *y, const double *x, const double *th, int t) {
   switch (model) {
     case ORC_MODEL_RW_DRIFT: return r_dnorm_log(y[0], x[0] + th[0], th[1]); /* test-auxiliary_filter.R:24-27 */
-    case ORC_MODEL_SIR_CB: {
+    case ORC_MODEL_SIR_CB: case ORC_MODEL_SIR_GILLESPIE: {
       double S = x[0], I = x[1], pop = th[2];
       double p_inf = 1.0 - exp(-th[0] * I / pop), p_rec = 1.0 - exp(-th[1]);
       return r_dpois_log(y[0], I + S * p_inf - I * p_rec);
@@ -385,7 +411,7 @@ static double model_aux_loglik(int model, const double *y, const double *x, cons
 static void model_move(int model, double *x, const double *y, const double *th, int t, const double *z,
                        const double *u) {
   switch (model) {
-    case ORC_MODEL_SIR_CB: {
+    case ORC_MODEL_SIR_CB: case ORC_MODEL_SIR_GILLESPIE: {
       double prop[2] = {x[0], x[1] + (u[0] < 0.5 ? -1.0 : 1.0)};
       if (prop[1] < 0 || prop[1] > th[2] - x[0]) return;
       double lc = model_loglik(model, y, x, th, t), lp = model_loglik(model, y, prop, th, t);
@@ -445,7 +471,9 @@ static void do_transition(const fctx *f, double *px, const double *th, int tnow,
       for (int s = 0; s < f->md.nu_trans; s++)
         u[s] = get_u(f, nb ? nb->u_trans2 : NULL, f->md.nu_trans, TAG_TRANS2_U, (uint32_t)obs_i, obs_i, s, i);
     }
-    model_transition(f->cfg->model, x, th, tnow, z, u);
+    dyn_u du = {f->cfg->seed, f->cfg->run_id, f->cfg->stream, second ? (uint32_t)obs_i : (uint32_t)(tnow - 1),
+                second ? TAG_TRANS2_DYN : TAG_TRANS_DYN, (uint32_t)i};
+    model_transition(f->cfg->model, x, th, tnow, z, u, &du);
     for (int k = 0; k < d; k++) px[(size_t)k * N + i] = x[k];
   }
 }
@@ -489,6 +517,7 @@ int orc_particle_filter(const orc_filter_config *cfg, const double *y, const dou
   if (N <= 0 || T < 0 || dy <= 0) return ORC_ERR_BAD_ARG;
   f.N = N;
   const orc_noise_buffers *nb = cfg->noise;
+  if (nb && cfg->model == ORC_MODEL_SIR_GILLESPIE) return ORC_ERR_BAD_ARG; /* uniforms on demand: Philox noise only */
   /* R/resample_move_filter.R:228-230: RMPF forces SISR */
   int ralg = (cfg->algorithm == ORC_RMPF) ? ORC_SISR : cfg->resample_algorithm;
   /* R/particle_filter_core.R:44-50 */
@@ -994,7 +1023,7 @@ double orc_bench_bootstrap_filter(int model, int N, int T, const double *y, cons
   for (int i = 0; i < N; i++) { z = orc_rrng_norm(&rng); model_init(model, &px[i], theta, &z, NULL); }
   double loglike = 0.0; int nres = 0;
   for (int t = 0; t < T; t++) {
-    for (int i = 0; i < N; i++) { z = orc_rrng_norm(&rng); model_transition(model, &px[i], theta, t + 1, &z, NULL); }
+    for (int i = 0; i < N; i++) { z = orc_rrng_norm(&rng); model_transition(model, &px[i], theta, t + 1, &z, NULL, NULL); }
     for (int i = 0; i < N; i++) lw[i] = model_loglik(model, &y[t], &px[i], theta, t + 1);
     double mx = -INFINITY;
     for (int i = 0; i < N; i++) if (lw[i] > mx) mx = lw[i];

@@ -40,7 +40,8 @@ enum {
   ORC_MODEL_RW_DRIFT = 2,/* tests/testthat/test-auxiliary_filter.R:17-27, test-resample_move_filter.R:17-35 */
   ORC_MODEL_SIR_CB = 3,  /* chain-binomial SIR; obs as stochastic-sir-model.Rmd:306-309 */
   ORC_MODEL_AR_COS = 4,  /* R/pmmh.R:157-159 */
-  ORC_MODEL_RW2D = 5     /* tests/testthat/test-bootstrap_filter.R:211-217 */
+  ORC_MODEL_RW2D = 5,    /* tests/testthat/test-bootstrap_filter.R:211-217 */
+  ORC_MODEL_SIR_GILLESPIE = 6 /* the SIR model with the exact daily step of stochastic-sir-model.Rmd:152-176 (epidemic_step); Philox noise only */
 };
 enum { ORC_PRIOR_FLAT = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_EXP = 2, ORC_PRIOR_UNIF = 3, ORC_PRIOR_HALFNORMAL = 4 };
 enum { ORC_TR_IDENTITY = 0, ORC_TR_LOG = 1, ORC_TR_LOGIT = 2 };

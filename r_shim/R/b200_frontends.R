@@ -7,11 +7,13 @@
 # is tested through the Python mirror of these functions (bayesssm_b200/filters.py, pmmh.py, sharding.py).
 
 .b200_models <- c(nonlinear_ar = 0L, linear_gaussian = 1L, random_walk_drift = 2L,
-                  sir_chain_binomial = 3L, nonlinear_ar_cos_obs = 4L, random_walk_2d = 5L)
+                  sir_chain_binomial = 3L, nonlinear_ar_cos_obs = 4L, random_walk_2d = 5L,
+                  sir_gillespie = 6L)
 .b200_params <- list(nonlinear_ar = c("phi", "sigma_x", "sigma_y"), linear_gaussian = c("phi", "sigma_x", "sigma_y"),
                      random_walk_drift = c("mu", "sigma"), sir_chain_binomial = c("lambda", "gamma"),
-                     nonlinear_ar_cos_obs = c("phi", "sigma_x", "sigma_y"), random_walk_2d = c("phi"))
-.b200_consts <- list(sir_chain_binomial = c("pop", "I0"))
+                     nonlinear_ar_cos_obs = c("phi", "sigma_x", "sigma_y"), random_walk_2d = c("phi"),
+                     sir_gillespie = c("lambda", "gamma"))
+.b200_consts <- list(sir_chain_binomial = c("pop", "I0"), sir_gillespie = c("pop", "I0"))
 
 .b200_slots <- function(desc) {
   slot <- function(s) structure(list(model = desc, slot = s), class = "b200_device_fn")

@@ -155,6 +155,7 @@ int main(int argc, char** argv) {
     case BSSM_MODEL_SIR_CB: return run<ModelSirCB>(argv);
     case BSSM_MODEL_AR_COS: return run<ModelArCos>(argv);
     case BSSM_MODEL_RW2D: return run<ModelRw2D>(argv);
+    case BSSM_MODEL_SIR_GILLESPIE: return run<ModelSirGillespie>(argv);
   }
   return 2;
 }

@@ -189,3 +189,41 @@ def test_replicate_filters_sharded_is_placement_independent(engine):
     part = _particle_filter_core(y, 2000, mdl, "BPF", "SISR", "stratified", None, False, None,
                                  dict(phi=0.8, sigma_x=1.0, sigma_y=1.0), "f64", 9, engine, num_filters=count, stream_base=base)
     np.testing.assert_array_equal(part["loglike"], full["loglike"][base:base + count])
+
+
+def test_exact_gillespie_sir_through_the_public_api():
+    # vignettes/articles/stochastic-sir-model.Rmd:128-176, 285-309: data from the exact jump process (numpy restatement of
+    # simulate_epidemic), filtered with the same model on the device; pmmh() runs on it as on any built-in model
+    rng = np.random.default_rng(2025)
+    s, i, latent = 430, 70, []
+    for _ in range(10):
+        t = 0.0
+        while i > 0:
+            ri, rr = 0.5 / 500 * s * i, 0.2 * i
+            dt = rng.exponential(1.0 / (ri + rr))
+            if t + dt > 1.0:
+                break
+            t += dt
+            if rng.random() < ri / (ri + rr):
+                s, i = s - 1, i + 1
+            else:
+                i -= 1
+        latent.append(i)
+    latent = np.array(latent, dtype=float)
+    y = rng.poisson(latent).astype(float)
+    m = b.models.sir_gillespie()
+    kw = dict(seed=7, pop=500.0, I0=70.0, return_particles=False)
+    r = b.bootstrap_filter(y, 2000, m.init_fn, m.transition_fn, m.log_likelihood_fn, **{"lambda": 0.5, "gamma": 0.2}, **kw)
+    assert r["state_est"].shape == (11, 2)
+    assert np.sqrt(np.mean((r["state_est"][1:, 1] - latent) ** 2)) < 12.0          # Poisson noise of ~ sqrt(150) per observation
+    assert np.all(r["state_est"][:, 0] + r["state_est"][:, 1] <= 500.0 + 1e-9)
+    # a far-off infection rate explains the data much worse
+    r_bad = b.bootstrap_filter(y, 2000, m.init_fn, m.transition_fn, m.log_likelihood_fn, **{"lambda": 1.5, "gamma": 0.2}, **kw)
+    assert r["loglike"] > r_bad["loglike"] + 10
+    out = b.pmmh(b.bootstrap_filter, y, m=150, init_fn=m.init_fn, transition_fn=m.transition_fn, log_likelihood_fn=m.log_likelihood_fn,
+                 log_priors={"lambda": b.priors.half_normal(1.0), "gamma": b.priors.half_normal(2.0)},
+                 pilot_init_params=[{"lambda": 0.6, "gamma": 0.3}, {"lambda": 0.4, "gamma": 0.15}], burn_in=50, num_chains=2,
+                 param_transform={"lambda": "log", "gamma": "log"}, seed=1405, pop=500.0, I0=70.0,
+                 tune_control=b.default_tune_control(pilot_m=50, pilot_n=100, pilot_reps=4), verbose=False)
+    tc = out["theta_chain"]
+    assert 0.2 < tc["lambda"].mean() < 1.0 and 0.05 < tc["gamma"].mean() < 0.6

@@ -162,3 +162,36 @@ def test_histories_stream_through_a_two_row_ring(orc, engine):
     assert got["early_exit"][0] == 1
     ph, wh = got["particles_history"][0], got["weights_history"][0]
     assert np.abs(ph[:26]).max() > 0 and not ph[26:].any() and not wh[26:].any()
+
+
+# ---- stochastic SIR with the exact (Gillespie) daily step: uniforms drawn on demand from the particle's Philox stream ----
+GIL = 6
+THETA_GIL = [0.5, 0.2, 500.0, 70.0]
+
+
+@pytest.mark.parametrize("algorithm,ralg", [(0, 2), (0, 1), (1, 2), (2, 2)])
+def test_gillespie_sir_matches_oracle_philox(orc, engine, algorithm, ralg):
+    # vignettes/articles/stochastic-sir-model.Rmd:152-176 (epidemic_step) on both sides, the same Philox words: the event
+    # sequences are identical, so the parity is that of the other Philox-mode tests
+    y = np.array([82, 95, 118, 130, 151, 160, 158, 149], dtype=float)
+    for stream in (0, 3):
+        ref = orc.particle_filter(GIL, algorithm, ralg, 0, 1500, y, THETA_GIL, seed=11, run_id=1, stream=stream, return_particles=True)
+        got = eh.filter_run(engine, GIL, algorithm, ralg, 0, 1500, y, THETA_GIL, seed=11, run_id=1, stream_base=stream,
+                            precision=nat.F64, return_particles=True)
+        assert ref["status"] == 0 and got["status"][0] == 0
+        assert got["n_resampled"][0] == ref["n_resampled"]
+        assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-9 * abs(ref["loglike"])
+        np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-9)
+        np.testing.assert_allclose(got["state_est"][0], ref["state_est"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_array_equal(got["particles_history"][0], ref["particles_history"])    # integer states: exactly
+    # throughput precision: the same integer trajectories (the step itself is always fp64), weights in fp32
+    got32 = eh.filter_run(engine, GIL, 0, 2, 0, 1500, y, THETA_GIL, seed=11, run_id=1, stream_base=3, precision=nat.F32)
+    ref = orc.particle_filter(GIL, 0, 2, 0, 1500, y, THETA_GIL, seed=11, run_id=1, stream=3)
+    assert abs(got32["loglike"][0] - ref["loglike"]) < 0.05
+
+
+def test_gillespie_sir_rejects_injected_noise(orc, engine):
+    y = np.array([80.0, 90.0])
+    noise = orc.make_noise(SIR, 64, 2, 2, np.random.default_rng(0))
+    with pytest.raises(Exception):
+        eh.filter_run(engine, GIL, 0, 2, 0, 64, y, THETA_GIL, noise=noise)

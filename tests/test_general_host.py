@@ -13,8 +13,8 @@ import pytest
 from test_filter_gpu import THETA, sim_y
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-AR, LG, RWD, SIR, ARCOS, RW2D = 0, 1, 2, 3, 4, 5
-NTHETA = {AR: 3, LG: 3, RWD: 2, SIR: 2, ARCOS: 3, RW2D: 1}
+AR, LG, RWD, SIR, ARCOS, RW2D, GIL = 0, 1, 2, 3, 4, 5, 6
+NTHETA = {AR: 3, LG: 3, RWD: 2, SIR: 2, ARCOS: 3, RW2D: 1, GIL: 2}
 BPF, APF, RMPF = 0, 1, 2
 
 
@@ -63,15 +63,17 @@ def test_algorithms_and_resamplers_on_the_readme_model(orc, host_general, algori
 
 @pytest.mark.parametrize("model,algorithm,N,C,ralg", [(SIR, BPF, 2000, 1, 2), (SIR, APF, 1500, 1, 2), (SIR, RMPF, 1500, 1, 1),
                                                       (RW2D, BPF, 2500, 2, 2), (LG, APF, 1025, 2, 2), (RWD, RMPF, 700, 1, 0),
-                                                      (ARCOS, BPF, 1, 1, 2)])
+                                                      (ARCOS, BPF, 1, 1, 2), (GIL, BPF, 600, 2, 2), (GIL, APF, 500, 1, 2), (GIL, RMPF, 500, 1, 1)])
 def test_every_builtin_model(orc, host_general, model, algorithm, N, C, ralg):
     # integer-valued two-dimensional SIR states with constants, two-dimensional random walk, batches with their own theta
-    y = sim_y(model, 5, np.random.default_rng(model * 10 + algorithm))
+    # GIL: the same SIR model with the exact (Gillespie) daily step, uniforms drawn on demand (DynU)
+    base = THETA[SIR] if model == GIL else THETA[model]
+    y = sim_y(SIR if model == GIL else model, 5, np.random.default_rng(model * 10 + algorithm))
     nth = NTHETA[model]
-    thetas = [list(np.array(THETA[model][:nth]) * (1 + 0.05 * c)) + list(THETA[model][nth:]) for c in range(C)]
+    thetas = [list(np.array(base[:nth]) * (1 + 0.05 * c)) + list(base[nth:]) for c in range(C)]
     recs = host_general(model, algorithm, N, y, thetas, resample_algorithm=ralg)
     for c, rec in enumerate(recs):
-        th = thetas[c] if model == SIR else thetas[c][:nth]
+        th = thetas[c] if model in (SIR, GIL) else thetas[c][:nth]
         check(rec, orc.particle_filter(model, algorithm, ralg, 0, N, y, th, seed=77, run_id=1, stream=5 + c))
 
 

@@ -212,3 +212,36 @@ def test_multinomial_by_sorted_uniforms_has_the_multinomial_law(orc):
     u = np.ascontiguousarray(rng.random(6))
     L.orc_resample_multinomial_sorted(5, w3.ctypes.data_as(C.POINTER(C.c_double)), u.ctypes.data_as(C.POINTER(C.c_double)), idx.ctypes.data_as(C.POINTER(C.c_int32)))
     assert (idx == 3).all()
+
+
+def test_gillespie_sir_step_has_the_law_of_the_reference_simulation(orc):
+    """vignettes/articles/stochastic-sir-model.Rmd:152-176 (epidemic_step): one day of the exact SIR jump process from
+    (s, i) = (430, 70), lambda = 0.5, gamma = 0.2, N = 500 -- the oracle's particles after one SIS step against an
+    independent numpy simulation of the same process (means within 4 standard errors, spreads within 10 %)."""
+    n = 20000
+    out = orc.particle_filter(6, 0, 0, 0, n, np.array([75.0]), [0.5, 0.2, 500.0, 70.0], seed=5, return_particles=True)
+    assert out["status"] == 0
+    s1, i1 = out["particles_history"][1]
+    assert np.all(s1 == np.round(s1)) and np.all(i1 == np.round(i1)) and np.all(s1 <= 430) and np.all(s1 + i1 <= 500) and np.all(i1 >= 0)
+    rng = np.random.default_rng(1)
+    sim = np.zeros((n, 2))
+    for k in range(n):
+        s, i, t = 430, 70, 0.0
+        while i > 0:
+            ri, rr = 0.5 / 500 * s * i, 0.2 * i
+            dt = rng.exponential(1.0 / (ri + rr))
+            if t + dt > 1.0:
+                break
+            t += dt
+            if rng.random() < ri / (ri + rr):
+                s, i = s - 1, i + 1
+            else:
+                i -= 1
+        sim[k] = s, i
+    for got, ref in ((s1, sim[:, 0]), (i1, sim[:, 1])):
+        se = np.sqrt(got.var() / n + ref.var() / n)
+        assert abs(got.mean() - ref.mean()) < 4 * se, (got.mean(), ref.mean(), se)
+        assert abs(got.std() / ref.std() - 1) < 0.1
+    # injected noise buffers cannot serve a data-dependent number of uniforms
+    noise = orc.make_noise(3, 16, 1, 1, np.random.default_rng(0))
+    assert orc.particle_filter(6, 0, 2, 0, 16, np.array([75.0]), [0.5, 0.2, 500.0, 70.0], noise=noise)["status"] != 0
