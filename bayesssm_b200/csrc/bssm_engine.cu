@@ -63,15 +63,28 @@ int resample_cdf(bssm_ctx* ctx, const Src& src, MakeNorm make_norm, const RsArgs
   if (a.total) total = a.total; else BSSM_TRY(scratch(ctx, SL_RS_TOTAL, (size_t)a.nseg, &total));
   dim3 grid(a.nseg, ntiles);
   cudaStream_t st = ctx->stream;
+  // large inputs: the tile totals are scanned once per pass (k_tile_prefix) instead of summed again by every tile;
+  // BSSM_RS_PREFIX_TILES moves the threshold (tests)
+  int prefix_from = RS_PREFIX_TILES;
+  if (const char* e = getenv("BSSM_RS_PREFIX_TILES")) prefix_from = atoi(e);
+  double* pref = nullptr;
+  if (ntiles > prefix_from) BSSM_TRY(scratch(ctx, SL_RS_PREF, (size_t)a.nseg * ntiles, &pref));
+  auto tile_prefix = [&]() -> int {
+    if (!pref) return BSSM_OK;
+    k_tile_prefix<<<a.nseg, 256, 0, st>>>(part, a.n, a.n_per, ntiles, pref, a.enable);
+    BSSM_LAUNCH(ctx, "k_tile_prefix");
+    return BSSM_OK;
+  };
   k_tile_sums<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.status, a.validate, a.enable);
   BSSM_LAUNCH(ctx, "k_tile_sums");
+  BSSM_TRY(tile_prefix());
   if (!a.exact) {
-    k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.cdf, a.cdf_stride, rec, 0, a.enable);
+    k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, a.cdf, a.cdf_stride, rec, 0, a.enable, pref);
     BSSM_LAUNCH(ctx, "k_tile_scan");
     return BSSM_OK;
   }
   // pass 1: exact sequential total of the raw weights (src/resampling.cpp:20,47)
-  k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable);
+  k_tile_scan<Src><<<grid, RS_THREADS, 0, st>>>(src, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable, pref);
   BSSM_LAUNCH(ctx, "k_tile_scan");
   k_chain<Src><<<a.nseg, 32, 0, st>>>(src, a.n, a.n_per, ntiles, rec, cstart, used, total, nullptr, 0, nullptr, a.enable);
   BSSM_LAUNCH(ctx, "k_chain");
@@ -84,7 +97,8 @@ int resample_cdf(bssm_ctx* ctx, const Src& src, MakeNorm make_norm, const RsArgs
   typedef decltype(srcn) SrcN;
   k_tile_sums<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, part, nullptr, 0, a.enable);
   BSSM_LAUNCH(ctx, "k_tile_sums");
-  k_tile_scan<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable);
+  BSSM_TRY(tile_prefix());
+  k_tile_scan<SrcN><<<grid, RS_THREADS, 0, st>>>(srcn, a.n, a.n_per, ntiles, part, nullptr, 0, rec, 1, a.enable, pref);
   BSSM_LAUNCH(ctx, "k_tile_scan");
   k_chain<SrcN><<<a.nseg, 32, 0, st>>>(srcn, a.n, a.n_per, ntiles, rec, cstart, used, part /* pass-2 total (~1) is not needed; must not overwrite `total` */,
                                        a.cdf, a.cdf_stride, a.n_serial, a.enable);

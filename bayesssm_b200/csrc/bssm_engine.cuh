@@ -33,7 +33,7 @@ void set_error(const char* fmt, ...);
 
 // growable device scratch buffers owned by the context
 enum ScratchSlot {
-  SL_RS_PART = 0, SL_RS_REC, SL_RS_CSTART, SL_RS_USED, SL_RS_TOTAL, SL_RS_NSERIAL, SL_RS_STATUS,
+  SL_RS_PART = 0, SL_RS_REC, SL_RS_CSTART, SL_RS_USED, SL_RS_TOTAL, SL_RS_NSERIAL, SL_RS_STATUS, SL_RS_PREF,
   SL_API_W, SL_API_U, SL_API_IDX, SL_API_CDF,
   SL_F_XA, SL_F_XB, SL_F_LW, SL_F_LWAUX, SL_F_AUXG, SL_F_PART, SL_F_CDF, SL_F_SCAL_D, SL_F_SCAL_I,
   SL_F_ESS, SL_F_SEST, SL_F_LLH, SL_F_PH, SL_F_WH, SL_F_ANC, SL_F_ANCA, SL_F_THETA, SL_F_Y, SL_F_OBS,

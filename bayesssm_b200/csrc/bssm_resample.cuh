@@ -110,6 +110,33 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_sums(Src src, int n, const 
   if (validate && bad) atomicMax(&status[seg], bad);
 }
 
+// ---- exclusive prefix of a segment's tile totals (large inputs) --------------------------------
+// Below RS_PREFIX_TILES tiles k_tile_scan sums the preceding totals itself (<= 8 loads per thread, no launch); beyond, that
+// sum would be O(tiles^2) loads per scan, so one block per segment scans the totals once (256 per round, fixed order).
+constexpr int RS_PREFIX_TILES = 2048;
+static __global__ void __launch_bounds__(256) k_tile_prefix(const double* __restrict__ part, int n, const int* __restrict__ n_per_seg,
+                                                            int ntiles, double* __restrict__ pref, const int* __restrict__ enable) {
+  __shared__ double wsum[8];
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (!seg_on(enable, seg)) return;
+  const int nn = n_per_seg ? n_per_seg[seg] : n;
+  const int nt = (nn + RS_TILE - 1) / RS_TILE;
+  double carry = 0.0;
+  for (int b0 = 0; b0 < nt; b0 += 256) {
+    const int t = b0 + tid;
+    const double v = t < nt ? part[(size_t)seg * ntiles + t] : 0.0;
+    const double inc = warp_incl_scan(v, lane);
+    __syncthreads();
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    double woff = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { if (w == wid) woff = tot; tot += wsum[w]; }
+    if (t < nt) pref[(size_t)seg * ntiles + t] = carry + (woff + (inc - v));
+    carry += tot;
+  }
+}
+
 // ---- K4b: approximate inclusive scan per tile, binade classification, tile maps ---------------
 // mode 0 (fast): write the approximate cdf to `cdf`.  mode 1 (exact): write TileRec only.
 template <typename Src>
@@ -117,7 +144,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_scan(Src src, int n, const 
                                                          int ntiles, const double* __restrict__ part,
                                                          double* __restrict__ cdf, size_t cdf_stride,
                                                          TileRec* __restrict__ rec, int exact,
-                                                         const int* __restrict__ enable) {
+                                                         const int* __restrict__ enable, const double* __restrict__ pref) {
   __shared__ double sm[34];
   __shared__ double wsum[RS_THREADS / 32];
   __shared__ int s_irreg;
@@ -127,11 +154,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_scan(Src src, int n, const 
   int nn = n_per_seg ? n_per_seg[seg] : n;
   if (tile * RS_TILE >= nn) return;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // exclusive tile prefix: fixed-order sum of the preceding partials
-  double pre = 0.0;
-  for (int t = threadIdx.x; t < tile; t += RS_THREADS) pre += part[(size_t)seg * ntiles + t];
+  // exclusive tile prefix: fixed-order sum of the preceding partials, or (large inputs) the scanned totals of k_tile_prefix
   if (threadIdx.x == 0) s_irreg = 0;
-  double prefix = block_sum_bcast(pre, sm);
+  double prefix;
+  if (pref) { prefix = pref[(size_t)seg * ntiles + tile]; __syncthreads(); }
+  else {
+    double pre = 0.0;
+    for (int t = threadIdx.x; t < tile; t += RS_THREADS) pre += part[(size_t)seg * ntiles + t];
+    prefix = block_sum_bcast(pre, sm);
+  }
   int base = tile * RS_TILE + threadIdx.x * RS_IPT;
   double v[RS_IPT], loc[RS_IPT];
   double run = 0.0;

@@ -34,18 +34,25 @@ static void resample_cdf(const Src& src, MakeNorm make_norm, const RsArgs& a) {
   std::vector<TileRec> rec((size_t)a.nseg * ntiles);
   std::vector<int> used((size_t)a.nseg * ntiles);
   double* total = a.total ? a.total : total_own.data();
+  // large inputs scan the tile totals once per pass (k_tile_prefix); EMU_RS_PREFIX_TILES moves the threshold, as BSSM_RS_PREFIX_TILES does
+  const int prefix_from = getenv("EMU_RS_PREFIX_TILES") ? atoi(getenv("EMU_RS_PREFIX_TILES")) : RS_PREFIX_TILES;
+  std::vector<double> pref_v(ntiles > prefix_from ? (size_t)a.nseg * ntiles : 0, -7.0);
+  double* const pref = pref_v.empty() ? nullptr : pref_v.data();
+  auto tile_prefix = [&] { if (pref) emu_launch(a.nseg, 256, [&] { k_tile_prefix(part.data(), a.n, a.n_per, ntiles, pref, a.enable); }); };
   emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_sums<Src>(src, a.n, a.n_per, ntiles, part.data(), a.status, a.validate, a.enable); });
+  tile_prefix();
   if (!a.exact) {
-    emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<Src>(src, a.n, a.n_per, ntiles, part.data(), a.cdf, a.cdf_stride, rec.data(), 0, a.enable); });
+    emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<Src>(src, a.n, a.n_per, ntiles, part.data(), a.cdf, a.cdf_stride, rec.data(), 0, a.enable, pref); });
     return;
   }
-  emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<Src>(src, a.n, a.n_per, ntiles, part.data(), nullptr, 0, rec.data(), 1, a.enable); });
+  emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<Src>(src, a.n, a.n_per, ntiles, part.data(), nullptr, 0, rec.data(), 1, a.enable, pref); });
   emu_launch(a.nseg, 32, [&] { k_chain<Src>(src, a.n, a.n_per, ntiles, rec.data(), cstart.data(), used.data(), total, nullptr, 0, nullptr, a.enable); });
   if (a.status) emu_launch((a.nseg + 127) / 128, 128, [&] { k_zero_sum_check(total, a.nseg, a.status, a.enable); });
   auto srcn = make_norm(total);
   typedef decltype(srcn) SrcN;
   emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_sums<SrcN>(srcn, a.n, a.n_per, ntiles, part.data(), nullptr, 0, a.enable); });
-  emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<SrcN>(srcn, a.n, a.n_per, ntiles, part.data(), nullptr, 0, rec.data(), 1, a.enable); });
+  tile_prefix();
+  emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_scan<SrcN>(srcn, a.n, a.n_per, ntiles, part.data(), nullptr, 0, rec.data(), 1, a.enable, pref); });
   emu_launch(a.nseg, 32, [&] { k_chain<SrcN>(srcn, a.n, a.n_per, ntiles, rec.data(), cstart.data(), used.data(), part.data(), a.cdf, a.cdf_stride, a.n_serial, a.enable); });
   emu_launch2d(a.nseg, ntiles, RS_THREADS, [&] { k_tile_exact<SrcN>(srcn, a.n, a.n_per, ntiles, cstart.data(), used.data(), a.cdf, a.cdf_stride, a.enable); });
 }

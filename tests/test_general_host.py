@@ -25,12 +25,16 @@ def host_general(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_general.cpp")], check=True)
 
     def run(model, algorithm, N, y, thetas, resample_fn=0, resample_algorithm=2, threshold=-1.0, seed=77, run_id=1, stream_base=5,
-            exact=1, obs_times=None):
+            exact=1, obs_times=None, prefix_tiles=None):
         y = np.ascontiguousarray(y, dtype=np.float64)
         args = [model, algorithm, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base, exact]
+        env = dict(os.environ)
+        if obs_times is not None:
+            env["EMU_OBS_TIMES"] = ",".join(str(int(t)) for t in obs_times)
+        if prefix_tiles is not None:       # tile totals scanned by k_tile_prefix from this many tiles on (large-input path of the cdf pipeline)
+            env["EMU_RS_PREFIX_TILES"] = str(prefix_tiles)
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.ascontiguousarray(thetas, dtype=np.float64).tobytes(),
-                           capture_output=True, timeout=600,
-                           env=dict(os.environ, EMU_OBS_TIMES=",".join(str(int(t)) for t in obs_times)) if obs_times is not None else None)
+                           capture_output=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         lines, recs = r.stdout.decode().strip().splitlines(), []
         for i in range(0, len(lines), 4):
@@ -104,3 +108,14 @@ def test_observation_times_with_gaps(orc, host_general, algorithm):
     ref = orc.particle_filter(AR, algorithm, 2, 0, 2048, y, THETA[AR], obs_times=ot, seed=3)
     rec, = host_general(AR, algorithm, 2048, y, [THETA[AR]], seed=3, run_id=0, stream_base=0, obs_times=ot)
     check(rec, ref)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+def test_large_input_path_of_the_cdf_pipeline_scans_the_tile_totals_once(orc, host_general, exact):
+    # beyond RS_PREFIX_TILES tiles k_tile_scan reads the scanned totals of k_tile_prefix instead of summing the preceding
+    # totals itself: forced here from the second tile on; exact mode reproduces the sequential cumsum whatever the prefix path
+    y = sim_y(AR, 5, np.random.default_rng(8))
+    thetas = [THETA[AR], list(np.array(THETA[AR]) * 1.05)]
+    recs = host_general(AR, BPF, 7000, y, thetas, resample_algorithm=1, exact=exact, prefix_tiles=1)
+    for c, rec in enumerate(recs):
+        check(rec, orc.particle_filter(AR, 0, 1, 0, 7000, y, thetas[c], seed=77, run_id=1, stream=5 + c), tol=1e-9 if exact else 1e-6)

@@ -96,3 +96,21 @@ def test_proportions(engine):
         for _ in range(2000):
             counts += np.bincount(eh.resample(engine, fn, w, rng.random(5)) - 1, minlength=5)
         np.testing.assert_allclose(counts / 10000, w, atol=0.03)
+
+
+@pytest.mark.parametrize("kind", ["pf", "tail"])
+def test_large_inputs_scan_the_tile_totals_once(engine, orc, kind, monkeypatch):
+    # more than RS_PREFIX_TILES (2048) tiles: k_tile_prefix scans the tile totals once per pass instead of every tile summing its
+    # predecessors (O(tiles^2) loads); the exact pipeline still reproduces the sequential cumsum bit for bit.  Also forced at small n.
+    rng = np.random.default_rng(5)
+    for n, force in ((1 << 22, None), (100003, "0"), (4097, "1")):
+        if force is None:
+            monkeypatch.delenv("BSSM_RS_PREFIX_TILES", raising=False)
+        else:
+            monkeypatch.setenv("BSSM_RS_PREFIX_TILES", force)
+        w = _weights(kind, n, rng)
+        ref_cdf, ref_tot = orc.cdf(w)
+        got_cdf, got_tot, _ = eh.cdf(engine, w)
+        assert got_tot == ref_tot and np.array_equal(got_cdf.view(np.int64), ref_cdf.view(np.int64)), (kind, n)
+        u = rng.random(n)
+        assert np.array_equal(eh.resample(engine, "stratified", w, u), orc.resample("stratified", w, u))
