@@ -286,6 +286,22 @@ int resolve_engine(bssm_ctx* ctx, const FilterDev& f_in, const FilterLaunch& L, 
   return BSSM_ENGINE_GENERAL;
 }
 
+// particle / weight / cdf arrays of the general kernels (f.nblk set)
+static int general_arrays(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_aux, double** cdf_out) {
+  const size_t C = f.C, N = f.N, d = f.d;
+  const size_t rs = L.precision == BSSM_F64 ? 8 : 4;
+  BSSM_TRY(scratch_get(ctx, SL_F_XA, C * d * N * rs, &f.xa));
+  BSSM_TRY(scratch_get(ctx, SL_F_XB, C * d * N * rs, &f.xb));
+  BSSM_TRY(scratch_get(ctx, SL_F_LW, C * N * rs, &f.lw));
+  if (need_aux) {
+    BSSM_TRY(scratch_get(ctx, SL_F_LWAUX, C * N * rs, &f.lw_aux));
+    BSSM_TRY(scratch_get(ctx, SL_F_AUXG, C * N * rs, &f.auxg));
+  }
+  BSSM_TRY(scratch(ctx, SL_F_PART, C * f.nblk * PART_W, &f.part));
+  BSSM_TRY(scratch(ctx, SL_F_CDF, C * N, cdf_out));
+  return BSSM_OK;
+}
+
 // enqueue one batched filter run on ctx->stream (no synchronisation)
 int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* cdf) {
   const int eng = resolve_engine(ctx, f, L, f.noise.injected != 0, f.anc_history != nullptr);
@@ -294,8 +310,15 @@ int filter_enqueue(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, double* c
               L.engine == BSSM_ENGINE_PERSISTENT ? "BSSM_ENGINE_PERSISTENT" : "BSSM_ENGINE_STREAM");
     return BSSM_ERR_UNSUPPORTED;
   }
-  if (eng == BSSM_ENGINE_PERSISTENT) return fast_filter_enqueue(ctx, f, L);
-  if (eng == BSSM_ENGINE_STREAM) return stream_filter_enqueue(ctx, f, L, nullptr);
+  if (eng == BSSM_ENGINE_PERSISTENT || eng == BSSM_ENGINE_STREAM) {
+    const int st = eng == BSSM_ENGINE_PERSISTENT ? fast_filter_enqueue(ctx, f, L) : stream_filter_enqueue(ctx, f, L, nullptr);
+    // A fast engine may still turn a configuration down when it sizes its launch (fewer resident blocks than the choice assumed:
+    // a shared GPU, a part with fewer SMs) -- before anything has been launched.  Picked by AUTO, the general kernels then serve
+    // the run; named by the caller, the refusal is the answer.
+    if (st != BSSM_ERR_UNSUPPORTED || L.engine != BSSM_ENGINE_AUTO) return st;
+    if (f.nblk < 1) { f.nblk = (int)(((size_t)f.N + FT_THREADS - 1) / FT_THREADS); if (f.nblk > 1024) f.nblk = 1024; }
+    BSSM_TRY(general_arrays(ctx, f, L, false, &cdf));
+  }
   if (!f.xa) { set_error("internal: general engine selected but its particle arrays were not set up"); return BSSM_ERR_BAD_ARG; }
   if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC-compiled user model (bssm_nvrtc.cu)
     const UserModelInfo* u = user_model(ctx, L.model);
@@ -343,17 +366,7 @@ int filter_setup(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, bool need_a
   const int eng = resolve_engine(ctx, f, L, injected, want_anc);
   const bool general = eng == BSSM_ENGINE_GENERAL || eng < 0;
   f.xa = f.xb = f.lw = f.lw_aux = f.auxg = nullptr; f.part = nullptr; *cdf_out = nullptr;
-  if (general) {
-    BSSM_TRY(scratch_get(ctx, SL_F_XA, C * d * N * rs, &f.xa));
-    BSSM_TRY(scratch_get(ctx, SL_F_XB, C * d * N * rs, &f.xb));
-    BSSM_TRY(scratch_get(ctx, SL_F_LW, C * N * rs, &f.lw));
-    if (need_aux) {
-      BSSM_TRY(scratch_get(ctx, SL_F_LWAUX, C * N * rs, &f.lw_aux));
-      BSSM_TRY(scratch_get(ctx, SL_F_AUXG, C * N * rs, &f.auxg));
-    }
-    BSSM_TRY(scratch(ctx, SL_F_PART, C * f.nblk * PART_W, &f.part));
-    BSSM_TRY(scratch(ctx, SL_F_CDF, C * N, cdf_out));
-  }
+  if (general) BSSM_TRY(general_arrays(ctx, f, L, need_aux, cdf_out));
   double* sd; int* si;
   BSSM_TRY(scratch(ctx, SL_F_SCAL_D, C * 4, &sd));
   BSSM_TRY(scratch(ctx, SL_F_SCAL_I, C * 6, &si));

@@ -40,6 +40,7 @@ static int fast_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, int G
   BSSM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   long long resident = (long long)per_sm * nsm;
   if (resident < G) { set_error("persistent kernel: group of %d CTAs does not fit (%lld resident)", G, resident); return BSSM_ERR_UNSUPPORTED; }
+  if (getenv("BSSM_TEST_FAST_LAUNCH_UNSUPPORTED")) { set_error("persistent kernel: launch refused (BSSM_TEST_FAST_LAUNCH_UNSUPPORTED: test hook of the AUTO fallback)"); return BSSM_ERR_UNSUPPORTED; }
   int ngroups = (int)(resident / G);
   if (ngroups > f.C) ngroups = f.C;
   FastParams P;

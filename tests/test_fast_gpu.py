@@ -132,3 +132,16 @@ def test_many_filters_per_group_and_several_groups_per_sm(orc, engine):
     big = eh.filter_run(engine, AR, 0, 1, 1, 30000, y, THETA[AR], seed=32, num_filters=40, precision=nat.F32,
                         engine=nat.ENGINE_PERSISTENT)
     assert (big["status"] == 0).all() and np.isfinite(big["loglike"]).all() and (big["n_resampled"] == 8).all()
+
+
+def test_auto_falls_back_to_the_general_kernels_when_a_fast_launch_is_refused(engine, monkeypatch):
+    # the persistent kernel sizes its cooperative launch at launch time and may refuse (fewer resident CTAs than the choice
+    # assumed); AUTO then runs the general kernels, a request by name stays an error
+    y = sim_y(AR, 12, np.random.default_rng(9))
+    ref = eh.filter_run(engine, AR, 0, 2, 0, 50000, y, THETA[AR], seed=3, precision=nat.F32, engine=nat.ENGINE_GENERAL)
+    monkeypatch.setenv("BSSM_TEST_FAST_LAUNCH_UNSUPPORTED", "1")
+    got = eh.filter_run(engine, AR, 0, 2, 0, 50000, y, THETA[AR], seed=3, precision=nat.F32, engine=nat.ENGINE_AUTO)
+    assert got["status"][0] == 0 and got["loglike"][0] == ref["loglike"][0]
+    np.testing.assert_array_equal(got["state_est"], ref["state_est"])
+    with pytest.raises(Exception, match="refused"):
+        eh.filter_run(engine, AR, 0, 2, 0, 50000, y, THETA[AR], seed=3, precision=nat.F32, engine=nat.ENGINE_PERSISTENT)
