@@ -75,6 +75,25 @@ template <typename M, typename = void> struct ModelDynU { static constexpr bool 
 template <typename M> struct ModelDynU<M, decltype((void)M::DYN_U)> { static constexpr bool value = M::DYN_U; };
 BSSM_HD float word_to_unit_f32(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// ---- packed fp32 pairs (sm_100a: add / mul / fma .f32x2 issue as ONE instruction for two lanes -- FADD2 / FMUL2 / FFMA2) ----
+// Used where the streaming engine's tile loops do the same fp32 operation on neighbouring particles and are bound by issue
+// slots.  Each lane is the IEEE operation of the scalar instruction.
+#ifndef BSSM_EMU
+struct F2 { unsigned long long v; };
+BSSM_DEV F2 f2_make(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+BSSM_DEV void f2_get(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+BSSM_DEV F2 f2_add(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+BSSM_DEV F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+BSSM_DEV F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#else   // CPU logic test (tests/simt_emu.h)
+struct F2 { float lo, hi; };
+inline F2 f2_make(float lo, float hi) { F2 r; r.lo = lo; r.hi = hi; return r; }
+inline void f2_get(F2 a, float& lo, float& hi) { lo = a.lo; hi = a.hi; }
+inline F2 f2_add(F2 a, F2 b) { return f2_make(a.lo + b.lo, a.hi + b.hi); }
+inline F2 f2_mul(F2 a, F2 b) { return f2_make(a.lo * b.lo, a.hi * b.hi); }
+inline F2 f2_fma(F2 a, F2 b, F2 c) { return f2_make(fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)); }
+#endif
+
 // ---- math wrappers templated on the state precision ----
 template <typename Real> struct Math;
 template <> struct Math<double> {
@@ -86,6 +105,7 @@ template <> struct Math<double> {
     sincos(2.0 * 3.14159265358979323846 * u2, &s, &c);
     n0 = r * c; n1 = r * s;
   }
+  static BSSM_DEV void box_muller4(const uint32_t* w, double* z) { box_muller(w[0], w[1], z[0], z[1]); box_muller(w[2], w[3], z[2], z[3]); }
   static BSSM_DEV double exp_(double x) { return exp(x); }
   static BSSM_DEV double log_(double x) { return log(x); }
   static BSSM_DEV double sin_(double x) { return sin(x); }
@@ -118,6 +138,22 @@ template <> struct Math<float> {
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);  // argument in (0, 2pi): the SFU path is accurate to ~1e-6 here
     n0 = r * c; n1 = r * s;
+  }
+  // the four normals of a Philox quad (words 0, 1 -> pair 0; words 2, 3 -> pair 1), the two Box-Muller transforms side by side:
+  // the same values as two box_muller() calls, the fp32 arithmetic between the SFU calls as packed pairs
+  static BSSM_DEV void box_muller4(const uint32_t* w, float* z) {
+    const F2 c = f2_make(-0.99999994f, -0.99999994f);
+    float u1a, u1b, a0, a1;
+    f2_get(f2_add(f2_make(__uint_as_float(0x3F800000u | (w[0] >> 9)), __uint_as_float(0x3F800000u | (w[2] >> 9))), c), u1a, u1b);
+    f2_get(f2_mul(f2_add(f2_make(__uint_as_float(0x3F800000u | (w[1] >> 9)), __uint_as_float(0x3F800000u | (w[3] >> 9))), c),
+                  f2_make(6.283185307179586f, 6.283185307179586f)), a0, a1);
+    float l0, l1;
+    f2_get(f2_mul(f2_make(lg2_(u1a), lg2_(u1b)), f2_make(-1.3862943611198906f, -1.3862943611198906f)), l0, l1);
+    const float r0 = sqrt_approx(l0), r1 = sqrt_approx(l1);
+    float s0, c0, s1, c1;
+    __sincosf(a0, &s0, &c0); __sincosf(a1, &s1, &c1);
+    f2_get(f2_mul(f2_make(r0, r0), f2_make(c0, s0)), z[0], z[1]);
+    f2_get(f2_mul(f2_make(r1, r1), f2_make(c1, s1)), z[2], z[3]);
   }
   static BSSM_DEV float exp_(float x) { return ex2_(x * 1.4426950408889634f); }
   static BSSM_DEV float log_(float x) { return logf(x); }

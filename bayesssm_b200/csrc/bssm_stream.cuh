@@ -368,8 +368,7 @@ __global__ void __launch_bounds__(THREADS) k_st_init(StreamParams P) {
     for (int h = 0; h < PPT / 4; h++) {
       uint4x qd = noise_quad(key, T_INIT, TAG_INIT_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
       Real zz[4];
-      Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
-      Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+      Math<Real>::box_muller4(qd.w, zz);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         Real xi[1]; Real zi[1] = {zz[k]};
@@ -542,6 +541,7 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
   // (a NaN log-weight never raises the max and turns exp(NaN - ref) into NaN: it poisons the sum by itself --
   // R's `if (NA)` error, reported as BSSM_ERR_NAN_WEIGHT)
   Real mT = Math<Real>::ninf(), sT = 0, qT = 0, xT = 0;
+  F2 s2 = f2_make(0.f, 0.f), q2 = s2, x2 = s2;     // throughput precision: the three sums as packed pairs (even / odd particles)
 
   for (int tile = t0; tile < t1; tile++) {
     const int pb = (tile - t0) & 1;
@@ -562,8 +562,7 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
       for (int h = 0; h < PPT / 4; h++) {
         uint4x qd = noise_quad(key, (unsigned int)(tnow - 1), TAG_TRANS_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
         Real zz[4];
-        Math<Real>::box_muller(qd.w[0], qd.w[1], zz[0], zz[1]);
-        Math<Real>::box_muller(qd.w[2], qd.w[3], zz[2], zz[3]);
+        Math<Real>::box_muller4(qd.w, zz);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           Real zi[1] = {zz[k]};
@@ -586,16 +585,36 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
     // raise it).  No shuffle, no barrier, no store of partials in this loop: the sums meet once, at the block's end.
     if (mloc > mT) {
       const Real r = (mT == Math<Real>::ninf()) ? (Real)0 : Math<Real>::exp_(mT - mloc);
-      sT *= r; qT *= r * r; xT *= r; mT = mloc;
+      if constexpr (sizeof(Real) == 4) {
+        const F2 r2 = f2_make((float)r, (float)r);
+        s2 = f2_mul(s2, r2); q2 = f2_mul(q2, f2_mul(r2, r2)); x2 = f2_mul(x2, r2);
+      } else { sT *= r; qT *= r * r; xT *= r; }
+      mT = mloc;
     }
     {
       const Real mref = (mT == Math<Real>::ninf()) ? (Real)0 : mT;
+      if constexpr (sizeof(Real) == 4) {
+        // two particles per instruction: exponent arguments and the three sums as packed fp32 pairs (lane sums meet after the loop)
+        const F2 nm2 = f2_make(-mref, -mref), l2e = f2_make(1.4426950408889634f, 1.4426950408889634f);
 #pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        const Real ek = Math<Real>::exp_(e[k] - mref);
-        sT += ek; qT += ek * ek; xT += ek * x[k];
+        for (int k = 0; k < PPT; k += 2) {
+          float a0, a1;
+          f2_get(f2_mul(f2_add(f2_make(e[k], e[k + 1]), nm2), l2e), a0, a1);
+          const F2 ek2 = f2_make(Math<float>::ex2_(a0), Math<float>::ex2_(a1));
+          s2 = f2_add(s2, ek2); q2 = f2_fma(ek2, ek2, q2); x2 = f2_fma(ek2, f2_make(x[k], x[k + 1]), x2);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+          const Real ek = Math<Real>::exp_(e[k] - mref);
+          sT += ek; qT += ek * ek; xT += ek * x[k];
+        }
       }
     }
+  }
+  if constexpr (sizeof(Real) == 4) {
+    float a, b;
+    f2_get(s2, a, b); sT = a + b; f2_get(q2, a, b); qT = a + b; f2_get(x2, a, b); xT = a + b;
   }
   // block record: thread records -> warp records (shuffles) -> block record (fixed order)
   {
@@ -872,10 +891,21 @@ __device__ __forceinline__ int st_resample_body(const StreamParams& P, int obs, 
   Real fs = 0;
   {
     const Real Mr = (Real)M;
+    if constexpr (F32) {        // exponent arguments two particles per instruction (packed fp32 pairs)
+      const F2 nm2 = f2_make(-Mr, -Mr), l2e = f2_make(1.4426950408889634f, 1.4426950408889634f);
 #pragma unroll
-    for (int k = 0; k < PPT; k++) {
-      const Real lw = Model::template loglik<Real>(yv, &x[k], par, ot);
-      e[k] = Math<Real>::exp_(lw - Mr);
+      for (int k = 0; k < PPT; k += 2) {
+        const float lw0 = Model::template loglik<Real>(yv, &x[k], par, ot), lw1 = Model::template loglik<Real>(yv, &x[k + 1], par, ot);
+        float a0, a1;
+        f2_get(f2_mul(f2_add(f2_make(lw0, lw1), nm2), l2e), a0, a1);
+        e[k] = Math<float>::ex2_(a0); e[k + 1] = Math<float>::ex2_(a1);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const Real lw = Model::template loglik<Real>(yv, &x[k], par, ot);
+        e[k] = Math<Real>::exp_(lw - Mr);
+      }
     }
     if (ragged) {
 #pragma unroll
@@ -1004,18 +1034,25 @@ __device__ __forceinline__ int st_resample_body(const StreamParams& P, int obs, 
                         I0 + (int)tf_last + 1 < n;
       if (fast) {
         const unsigned int* su = s_u + rel0;
+        // two particles per instruction (packed fp32 pairs) wherever the arithmetic is the same on both
+        const F2 wsn2 = f2_make(wsn, wsn), f02 = f2_make(f0, f0), mh2 = f2_make(-0.5f, -0.5f), mg2 = f2_make(12582912.0f, 12582912.0f),
+                 nmg2 = f2_make(-12582912.0f, -12582912.0f), one2 = f2_make(1.0f, 1.0f), m12 = f2_make(-1.0f, -1.0f);
 #pragma unroll
-        for (int k = 0; k < PPT; k++) {
-          accf += (float)e[k];
-          const float tf = fmaf(accf, wsn, f0);
-          const float r = (tf - 0.5f) + 12582912.0f;                       // floor and fraction without conversion instructions
-          const int ii = __float_as_int(r) - 0x4B400000;
-          const float g = (tf - (r - 12582912.0f)) + 1.0f;                  // 1 + fraction, in [1, 2]
+        for (int k = 0; k < PPT; k += 2) {
+          const float acc0 = accf + (float)e[k];
+          accf = acc0 + (float)e[k + 1];
+          const F2 tf = f2_fma(f2_make(acc0, accf), wsn2, f02);
+          const F2 r = f2_add(f2_add(tf, mh2), mg2);                         // floor and fraction without conversion instructions
+          const F2 g = f2_add(f2_fma(f2_add(r, nmg2), m12, tf), one2);         // 1 + fraction, in [1, 2]
+          float r0, r1, g0, g1;
+          f2_get(r, r0, r1); f2_get(g, g0, g1);
+          const int ii0 = __float_as_int(r0) - 0x4B400000, ii1 = __float_as_int(r1) - 0x4B400000;
           // (i + U_i) <= t  <=>  U_i <= frac, on the 23 leading bits of the word: 1.U_i < 1 + frac as floats (g = 2: always)
-          const float u1 = __uint_as_float(0x3F800000u | (su[ii] >> 9));
+          const float u0 = __uint_as_float(0x3F800000u | (su[ii0] >> 9)), u1 = __uint_as_float(0x3F800000u | (su[ii1] >> 9));
           // the positions grow with k (accf sums non-negative terms), so v does: no running maximum; the lower clamp is
           // the max with prevF below
-          F[k] = min(I0 + ii + (u1 < g ? 1 : 0), o_hi);
+          F[k] = min(I0 + ii0 + (u0 < g0 ? 1 : 0), o_hi);
+          F[k + 1] = min(I0 + ii1 + (u1 < g1 ? 1 : 0), o_hi);
         }
         fmax = F[PPT - 1];
       } else {
