@@ -165,6 +165,13 @@ template <> struct Math<float> {
   }
   static BSSM_DEV float sin_(float x) { return __sinf(reduce_2pi(x)); }
   static BSSM_DEV float cos_(float x) { return __cosf(reduce_2pi(x)); }
+  // the same on a packed pair: the reduction's four fp32 operations once for two particles, the SFU call per lane
+  static BSSM_DEV F2 reduce_2pi2(F2 x) {
+    const F2 k = f2_add(f2_fma(x, f2_make(0.15915494309189535f, 0.15915494309189535f), f2_make(12582912.0f, 12582912.0f)), f2_make(-12582912.0f, -12582912.0f));
+    return f2_fma(k, f2_make(1.7484556e-7f, 1.7484556e-7f), f2_fma(k, f2_make(-6.2831854820251465f, -6.2831854820251465f), x));
+  }
+  static BSSM_DEV F2 sin2_(F2 x) { float a, b; f2_get(reduce_2pi2(x), a, b); return f2_make(__sinf(a), __sinf(b)); }
+  static BSSM_DEV F2 cos2_(F2 x) { float a, b; f2_get(reduce_2pi2(x), a, b); return f2_make(__cosf(a), __cosf(b)); }
   static BSSM_DEV float div_(float a, float b) { return a * rcp_(b); }
   static BSSM_DEV float max_(float a, float b) { return fmaxf(a, b); }   // a NaN operand never wins, like (b > a ? b : a) for a finite a
   static BSSM_DEV float ninf() { return -__int_as_float(0x7F800000); }
@@ -180,6 +187,15 @@ template <> BSSM_DEV float dnorm_log<float>(float x, float mu, float sigma, floa
   const float z = (x - mu) * Math<float>::rcp_(sigma);
   return fmaf(z, -0.5f * z, -(0.918938533204672741780329736406f + log_sigma));
 }
+// dnorm_log<float> on a packed pair (the same operations per lane)
+BSSM_DEV F2 dnorm_log2(float x, F2 mu, float sigma, float log_sigma) {
+  const F2 z = f2_mul(f2_fma(mu, f2_make(-1.0f, -1.0f), f2_make(x, x)), f2_make(Math<float>::rcp_(sigma), Math<float>::rcp_(sigma)));
+  const float c = -(0.918938533204672741780329736406f + log_sigma);
+  return f2_fma(z, f2_mul(z, f2_make(-0.5f, -0.5f)), f2_make(c, c));
+}
+// does a model offer its transition / log-likelihood on packed pairs (throughput precision of the streaming engine)?
+template <typename M, typename = void> struct ModelPacked { static constexpr bool value = false; };
+template <typename M> struct ModelPacked<M, decltype((void)M::PACKED)> { static constexpr bool value = M::PACKED; };
 template <typename Real> BSSM_DEV Real dpois_log(Real y, Real lambda) {
   if (lambda == (Real)0) return (y == (Real)0) ? (Real)0 : Math<Real>::ninf();
   return y * Math<Real>::log_(lambda) - lambda - (Real)lgamma((double)y + 1.0);

@@ -40,6 +40,12 @@ struct ModelArSin {
   template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
     return dnorm_log<R>((R)y[0], par[0] * x[0] + Math<R>::sin_(x[0]), par[2], par[3]);
   }
+  // two particles per instruction (throughput precision, streaming engine): transition<float> / loglik<float> lane by lane
+  static constexpr bool PACKED = true;
+  static BSSM_DEV F2 transition2(F2 x, const float* par, int, F2 z) {
+    return f2_fma(f2_make(par[1], par[1]), z, f2_fma(f2_make(par[0], par[0]), x, Math<float>::sin2_(x)));
+  }
+  static BSSM_DEV F2 loglik2(const double* y, F2 x, const float* par, int) { return dnorm_log2((float)y[0], x, par[2], par[3]); }
   template <typename R> static BSSM_DEV void move(R* x, const double* y, const R* par, int t, const R* z, const double* u) {
     R prop = x[0] + (R)0.1 * z[0];  // tests/testthat/test-resample_move_filter.R:24-35
     R lc = loglik<R>(y, x, par, t), lp = loglik<R>(y, &prop, par, t);
@@ -55,6 +61,7 @@ struct ModelArCos : ModelArSin {
   template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
     return dnorm_log<R>((R)y[0], Math<R>::cos_(par[0] * x[0] + Math<R>::sin_(x[0])), par[2], par[3]);
   }
+  static BSSM_DEV F2 loglik2(const double* y, F2 x, const float* par, int) { return dnorm_log2((float)y[0], Math<float>::cos2_(x), par[2], par[3]); }
   template <typename R> static BSSM_DEV void move(R* x, const double* y, const R* par, int t, const R* z, const double* u) {
     R prop = x[0] + (R)0.1 * z[0];
     R lc = loglik<R>(y, x, par, t), lp = loglik<R>(y, &prop, par, t);
@@ -81,6 +88,9 @@ struct ModelLG {
   template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
     return dnorm_log<R>((R)y[0], par[0] * x[0], par[2], par[3]);
   }
+  static constexpr bool PACKED = true;
+  static BSSM_DEV F2 transition2(F2 x, const float* par, int, F2 z) { return f2_fma(f2_make(par[1], par[1]), z, f2_mul(f2_make(par[0], par[0]), x)); }
+  static BSSM_DEV F2 loglik2(const double* y, F2 x, const float* par, int) { return dnorm_log2((float)y[0], x, par[2], par[3]); }
   template <typename R> static BSSM_DEV void move(R* x, const double* y, const R* par, int t, const R* z, const double* u) {
     R prop = x[0] + (R)0.1 * z[0];
     R lc = loglik<R>(y, x, par, t), lp = loglik<R>(y, &prop, par, t);
@@ -107,6 +117,9 @@ struct ModelRwDrift {
   template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int) {
     return dnorm_log<R>((R)y[0], x[0] + par[0], par[1], par[2]);
   }
+  static constexpr bool PACKED = true;
+  static BSSM_DEV F2 transition2(F2 x, const float* par, int, F2 z) { return f2_add(x, f2_add(f2_make(par[0], par[0]), z)); }
+  static BSSM_DEV F2 loglik2(const double* y, F2 x, const float* par, int) { return dnorm_log2((float)y[0], x, par[1], par[2]); }
   template <typename R> static BSSM_DEV void move(R* x, const double* y, const R* par, int t, const R* z, const double* u) {
     R prop = x[0] + (R)0.1 * z[0];
     R lc = loglik<R>(y, x, par, t), lp = loglik<R>(y, &prop, par, t);

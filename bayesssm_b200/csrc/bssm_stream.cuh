@@ -563,10 +563,16 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
         uint4x qd = noise_quad(key, (unsigned int)(tnow - 1), TAG_TRANS_Z, 0u, (unsigned int)((g0 + 4 * h) >> 2));
         Real zz[4];
         Math<Real>::box_muller4(qd.w, zz);
+        if constexpr (sizeof(Real) == 4 && ModelPacked<Model>::value) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          Real zi[1] = {zz[k]};
-          Model::template transition<Real>(&x[4 * h + k], par, tnow, zi, nullptr);
+          for (int k = 0; k < 4; k += 2)
+            f2_get(Model::transition2(f2_make(x[4 * h + k], x[4 * h + k + 1]), par, tnow, f2_make(zz[k], zz[k + 1])), x[4 * h + k], x[4 * h + k + 1]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            Real zi[1] = {zz[k]};
+            Model::template transition<Real>(&x[4 * h + k], par, tnow, zi, nullptr);
+          }
         }
       }
     }
@@ -574,7 +580,10 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
     Real e[PPT];
     Real mloc = Math<Real>::ninf();
 #pragma unroll
-    for (int k = 0; k < PPT; k++) e[k] = Model::template loglik<Real>(yv, &x[k], par, ot);
+    for (int k = 0; k < PPT; k += 2) {
+      if constexpr (sizeof(Real) == 4 && ModelPacked<Model>::value) f2_get(Model::loglik2(yv, f2_make(x[k], x[k + 1]), par, ot), e[k], e[k + 1]);
+      else { e[k] = Model::template loglik<Real>(yv, &x[k], par, ot); e[k + 1] = Model::template loglik<Real>(yv, &x[k + 1], par, ot); }
+    }
     if (ragged) {
 #pragma unroll
       for (int k = 0; k < PPT; k++) if (k < k_lo || k >= k_hi) e[k] = Math<Real>::ninf();
@@ -895,9 +904,11 @@ __device__ __forceinline__ int st_resample_body(const StreamParams& P, int obs, 
       const F2 nm2 = f2_make(-Mr, -Mr), l2e = f2_make(1.4426950408889634f, 1.4426950408889634f);
 #pragma unroll
       for (int k = 0; k < PPT; k += 2) {
-        const float lw0 = Model::template loglik<Real>(yv, &x[k], par, ot), lw1 = Model::template loglik<Real>(yv, &x[k + 1], par, ot);
+        F2 lw2;
+        if constexpr (ModelPacked<Model>::value) lw2 = Model::loglik2(yv, f2_make(x[k], x[k + 1]), par, ot);
+        else lw2 = f2_make(Model::template loglik<Real>(yv, &x[k], par, ot), Model::template loglik<Real>(yv, &x[k + 1], par, ot));
         float a0, a1;
-        f2_get(f2_mul(f2_add(f2_make(lw0, lw1), nm2), l2e), a0, a1);
+        f2_get(f2_mul(f2_add(lw2, nm2), l2e), a0, a1);
         e[k] = Math<float>::ex2_(a0); e[k + 1] = Math<float>::ex2_(a1);
       }
     } else {
