@@ -95,7 +95,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   // the two bodies and keep the launch-per-body form, as do NVRTC user models.
   // Measured (PMMH geometry, 65 536 particles per filter): +8 % at 256 filters, +6 % at 128, -8 % at 1024 -- a big batch keeps the
   // chip busy across kernel boundaries anyway, and the cooperative form gives up the block slots its groups cannot fill: it
-  // takes batches of up to a third of the resident block slots.
+  // takes batches of up to a quarter of the resident block slots (384 and 512 filters: level with the launch-per-body form).
   bool chain = K.chain != nullptr && !sh && !mn && L.T > 0 && ctx->prop.cooperativeLaunch;
   int chain_slots = 0;
   if (chain) {
@@ -106,7 +106,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   if (chain) {
     const char* e = getenv("BSSM_ST_CHAIN");
-    chain = e ? atoi(e) != 0 : (C >= 16 && 3 * C <= chain_slots);
+    chain = e ? atoi(e) != 0 : (C >= 16 && 4 * C <= chain_slots);
   }
   if (chain) {
     // blocks per filter: the resident slots split over the filters of a group (all blocks of a group are co-resident)
