@@ -628,6 +628,10 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   BSSM_CK(cudaSetDevice(ctx->device));
   int d, nth, nc;
   BSSM_TRY(model_dims(ctx, cfg->model, &d, &nth, &nc));
+  if (cfg->noise && cfg->model >= BSSM_USER_MODEL_BASE) {
+    const UserModelInfo* um = user_model(ctx, cfg->model);
+    if (um && um->dims[12]) { set_error("user model %d draws its transition uniforms on demand (DYN_U): injected noise buffers are not supported", cfg->model); return BSSM_ERR_UNSUPPORTED; }
+  }
   const int C = cfg->num_filters, N = cfg->num_particles, T = cfg->num_obs;
   FilterDev f;
   memset(&f, 0, sizeof(f));

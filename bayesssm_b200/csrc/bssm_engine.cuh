@@ -63,7 +63,7 @@ struct UserModelInfo {
   ModelKernels k32, k64;
   StreamKernels s32[2], s64[2];   // streaming engine, [0] 256 / [1] 128 threads per block (valid when stream_ok)
   bool stream_ok = false;    // 1-D state, one normal per init / transition, no uniforms
-  int dims[12];              // D, NTHETA, NCONST, NZ_INIT, NU_INIT, NZ_TRANS, NU_TRANS, NZ_MOVE, NU_MOVE, HAS_AUX, HAS_MOVE, NPAR
+  int dims[13];              // D, NTHETA, NCONST, NZ_INIT, NU_INIT, NZ_TRANS, NU_TRANS, NZ_MOVE, NU_MOVE, HAS_AUX, HAS_MOVE, NPAR, DYN_U
 };
 
 }  // namespace bssm

@@ -15,6 +15,11 @@
 //   init(x, par, z, u); transition(x, par, t, z, u); loglik(y, x, par, t);
 //   aux_loglik(y, x, par, t); move(x, y, par, t, z, u)
 // z are N(0,1) draws in R; u are uniforms in (0,1), always double.
+// Optional members:
+//   DYN_U = true + transition_dyn(x, par, t, DynU& du)   the transition draws a data-dependent number of uniforms: du(k) is its k-th
+//                           (Philox mode only; bssm_common.cuh).  transition() is then never called.
+//   PACKED = true + transition2(F2 x, par, t, F2 z), loglik2(y, F2 x, par, t)   1-D models: the same operations on a packed pair of
+//                           fp32 particles (FADD2 / FMUL2 / FFMA2), used by the streaming engine in the throughput precision.
 #pragma once
 #include "bssm_common.cuh"
 

@@ -145,3 +145,52 @@ def test_snippets_run_on_the_streaming_engine(orc, engine):
     # APF / injected noise / 2-D models stay on the general kernels; asking for the streaming engine there is an error
     with pytest.raises(nat.EngineError):
         eh.filter_run(engine, sv.value, 1, 2, 0, 1000, ysv, thv, seed=8, precision=nat.F32, engine=ST)
+
+
+# a user model that draws its transition uniforms on demand (DYN_U): the exact-Gillespie SIR step of the reference's vignette
+# (vignettes/articles/stochastic-sir-model.Rmd:152-176) restated as a snippet -- must reproduce the built-in model 6 bit for bit
+GILLESPIE_SNIPPET = r'''
+struct UserModel {
+  static constexpr int D = 2, NTHETA = 2, NCONST = 2, NZ_INIT = 0, NU_INIT = 0, NZ_TRANS = 0, NU_TRANS = 0,
+                       NZ_MOVE = 0, NU_MOVE = 0, NPAR = 4;
+  static constexpr bool HAS_AUX = false, HAS_MOVE = false, DYN_U = true;
+  template <typename R> static BSSM_DEV void prepare(const double* th, R* par) { for (int k = 0; k < 4; k++) par[k] = (R)th[k]; }
+  template <typename R> static BSSM_DEV void init(R* x, const R* par, const R*, const double*) { x[0] = par[2] - par[3]; x[1] = par[3]; }
+  template <typename R> static BSSM_DEV void transition(R*, const R*, int, const R*, const double*) {}
+  template <typename R> static BSSM_DEV void transition_dyn(R* x, const R* par, int, DynU& du) {
+    double s = (double)x[0], i = (double)x[1], t = 0.0;
+    const double lam = (double)par[0] / (double)par[2], gam = (double)par[1];
+    const int max_events = 2 * (int)par[2] + 8;
+    for (int e = 0; e < max_events && i > 0.0; e++) {
+      const double rate_inf = lam * s * i, rate_rem = gam * i, rate = rate_inf + rate_rem;
+      if (!(rate > 0.0)) break;
+      const double dt = -log(du(2 * e)) / rate;
+      if (t + dt > 1.0) break;
+      t += dt;
+      if (du(2 * e + 1) < rate_inf / rate) { s -= 1.0; i += 1.0; } else { i -= 1.0; }
+    }
+    x[0] = (R)s; x[1] = (R)i;
+  }
+  template <typename R> static BSSM_DEV R loglik(const double* y, const R* x, const R*, int) { return dpois_log<R>((R)y[0], x[1]); }
+  template <typename R> static BSSM_DEV R aux_loglik(const double* y, const R* x, const R* par, int t) { return loglik<R>(y, x, par, t); }
+  template <typename R> static BSSM_DEV void move(R*, const double*, const R*, int, const R*, const double*) {}
+};
+'''
+
+
+def test_user_model_with_uniforms_on_demand(orc, engine):
+    mid = C.c_int()
+    nat.check(engine.lib.bssm_model_compile(engine.handle, GILLESPIE_SNIPPET.encode(), C.byref(mid)))
+    y = np.array([82, 95, 118, 130, 151, 160], dtype=float)
+    th = [0.5, 0.2, 500.0, 70.0]
+    for prec in (nat.F64, nat.F32):
+        a = eh.filter_run(engine, mid.value, 0, 2, 0, 3000, y, th, seed=5, run_id=2, stream_base=1, precision=prec, num_filters=2)
+        b_ = eh.filter_run(engine, 6, 0, 2, 0, 3000, y, th, seed=5, run_id=2, stream_base=1, precision=prec, num_filters=2)
+        np.testing.assert_array_equal(a["loglike"], b_["loglike"])
+        np.testing.assert_array_equal(a["state_est"], b_["state_est"])
+    ref = orc.particle_filter(6, 0, 2, 0, 3000, y, th, seed=5, run_id=2, stream=2)
+    assert abs(a["loglike"][1] - ref["loglike"]) < 0.05       # (f32 weights; the trajectories are the oracle's)
+    # injected noise buffers cannot serve it
+    noise = orc.make_noise(3, 64, 2, 2, np.random.default_rng(0))
+    with pytest.raises(Exception, match="on demand"):
+        eh.filter_run(engine, mid.value, 0, 2, 0, 64, y[:2], th, noise=noise)
