@@ -48,7 +48,7 @@ class FilterConfig(C.Structure):
         ("num_filters", C.c_int), ("precision", C.c_int),
         ("seed", C.c_uint64), ("run_id", C.c_uint32), ("stream_base", C.c_uint32),
         ("noise", C.POINTER(NoiseBuffers)),
-        ("return_particles", C.c_int), ("exact_resampling", C.c_int), ("engine", C.c_int),
+        ("return_particles", C.c_int), ("exact_resampling", C.c_int), ("engine", C.c_int), ("carry_weights", C.c_int),
     ]
 
 

@@ -640,6 +640,8 @@ int bssm_filter_run(bssm_ctx* ctx, const bssm_filter_config* cfg, const double* 
   f.algorithm = cfg->algorithm;
   f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->resample_algorithm;
   f.threshold = cfg->threshold;
+  f.carry = cfg->carry_weights ? 1 : 0;
+  if (f.carry && cfg->algorithm == BSSM_APF) { set_error("carry_weights: not defined for the auxiliary filter's two-stage weights"); return BSSM_ERR_UNSUPPORTED; }
   FilterLaunch L;
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
   L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;
@@ -754,6 +756,8 @@ int bssm_filter_run_device(bssm_ctx* ctx, const bssm_filter_config* cfg, const d
   f.algorithm = cfg->algorithm;
   f.ralg = cfg->algorithm == BSSM_RMPF ? BSSM_SISR : cfg->resample_algorithm;
   f.threshold = cfg->threshold;
+  f.carry = cfg->carry_weights ? 1 : 0;
+  if (f.carry && cfg->algorithm == BSSM_APF) { set_error("carry_weights: not defined for the auxiliary filter's two-stage weights"); return BSSM_ERR_UNSUPPORTED; }
   FilterLaunch L;
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn;
   L.exact = cfg->exact_resampling < 0 ? (cfg->precision == BSSM_F64) : cfg->exact_resampling;

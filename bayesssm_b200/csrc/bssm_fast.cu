@@ -7,7 +7,7 @@
 namespace bssm {
 
 bool fast_supported(const FilterDev& f, const FilterLaunch& L) {
-  if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history) return false;
+  if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history || f.carry) return false;
   if (L.resample_fn == BSSM_MULTINOMIAL) return false;
   if (!(L.model == BSSM_MODEL_AR_SIN || L.model == BSSM_MODEL_LG || L.model == BSSM_MODEL_AR_COS || L.model == BSSM_MODEL_RW_DRIFT)) return false;
   if ((long long)f.N > (long long)FAST_MAX_G * FAST_MAX_NB) return false;

@@ -50,6 +50,8 @@ struct FilterDev {
   int *anc_aux_history;        // [C][T][N] or nullptr
   int algorithm, ralg;
   double threshold;            // < 0: reference default
+  int carry;                   // 1: carried-weights mode (a stated DEVIATION from the reference, which drops the weights on steps that do
+                               // not resample -- SURVEY App. A1): w_t ~ w_{t-1} g_t there; general kernels, BPF / RMPF
 };
 
 __device__ __forceinline__ int filt_n(const FilterDev& f, int c) { return f.n_per ? f.n_per[c] : f.N; }
@@ -201,6 +203,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_weight(FilterDev f, int obs, 
   double yv[4];
   for (int k = 0; k < f.dy && k < 4; k++) yv[k] = f.y[(size_t)obs * f.dy + k];
   Acc a; acc_init(a);
+  const bool carried = f.carry && wkind == 0 && obs > 0 && !f.resample[c];   // (f.resample[c]: still the previous observation's decision)
+  const double m_prev = carried ? f.M[c] : 0.0, s_prev = carried ? f.S[c] : 1.0;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     Real xi[Model::D];
     for (int k = 0; k < Model::D; k++) xi[k] = x[(size_t)k * f.N + i];
@@ -234,6 +238,9 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_weight(FilterDev f, int obs, 
     else {
       l = Model::template loglik<Real>(yv, xi, par, ot);
       if (wkind == 2) l = l - auxg[i];
+      // carried weights: + log(n W_{t-1,i}), W the previous observation's normalised weight, when it did not resample (after a
+      // resampling, and at the first observation, every W is 1 / n)
+      if (carried) l = l + (Real)log((double)n * (exp((double)lw[i] - m_prev) / s_prev));
     }
     lw[i] = l;
     acc_add<Real>(a, l, xi, Model::D);

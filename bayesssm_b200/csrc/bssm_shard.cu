@@ -158,6 +158,7 @@ int bssm_filter_run_sharded(bssm_ctx* ctx, const bssm_filter_config* cfg, const 
   memset(&f, 0, sizeof(f));
   f.C = C; f.N = sh.cap; f.T = T; f.dy = cfg->dy; f.d = d; f.n_per = nullptr;
   f.theta_stride = nth + nc; f.seed = cfg->seed;
+  if (cfg->carry_weights) { set_error("particle-sharded filter: carry_weights is served by the general kernels only"); return BSSM_ERR_UNSUPPORTED; }
   f.algorithm = cfg->algorithm; f.ralg = cfg->resample_algorithm; f.threshold = cfg->threshold;
   FilterLaunch L;
   L.model = cfg->model; L.precision = cfg->precision; L.resample_fn = cfg->resample_fn; L.exact = 0; L.hist = 0; L.T = T;

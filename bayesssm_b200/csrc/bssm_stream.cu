@@ -11,7 +11,7 @@
 namespace bssm {
 
 bool stream_supported(bssm_ctx* ctx, const FilterDev& f, const FilterLaunch& L) {
-  if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history) return false;
+  if (f.algorithm != BSSM_BPF || L.hist || f.noise.injected || f.anc_history || f.carry) return false;
   if (L.model >= BSSM_USER_MODEL_BASE) {   // NVRTC user model: its shape decides (bssm_nvrtc.cu)
     const UserModelInfo* u = user_model(ctx, L.model);
     return u && u->stream_ok;

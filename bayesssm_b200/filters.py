@@ -42,7 +42,7 @@ def _theta_vector(model, params):
 
 def _particle_filter_core(y, num_particles, model, algorithm, resample_algorithm, resample_fn, threshold,
                           return_particles, obs_times, params, precision, seed, ctx, num_filters=1,
-                          exact_resampling=-1, engine=nat.ENGINE_AUTO, run_id=0, stream_base=0):
+                          exact_resampling=-1, engine=nat.ENGINE_AUTO, run_id=0, stream_base=0, carry_weights=False):
     # validation as R/particle_filter_core.R:33-73
     if not (isinstance(num_particles, (int, np.integer)) and num_particles > 0):
         raise ValueError("Assertion on 'num_particles' failed: Must be a positive count")
@@ -82,6 +82,7 @@ def _particle_filter_core(y, num_particles, model, algorithm, resample_algorithm
     cfg.return_particles = int(bool(return_particles))
     cfg.exact_resampling = exact_resampling
     cfg.engine = engine
+    cfg.carry_weights = int(bool(carry_weights))
     N = int(num_particles)
     out = {"loglike": np.zeros(num_filters), "loglike_history": np.zeros((num_filters, T)),
            "ess": np.zeros((num_filters, T + 1)), "state_est": np.zeros((num_filters, T + 1, d)),
@@ -125,13 +126,16 @@ def _as_result(out, c, algorithm, resample_algorithm, return_particles, d):
 def bootstrap_filter(y, num_particles, init_fn, transition_fn, log_likelihood_fn, obs_times=None,
                      resample_algorithm=("SISAR", "SISR", "SIS"), resample_fn=("stratified", "systematic", "multinomial"),
                      threshold=None, return_particles=True, *, precision="f64", seed=None, ctx=None,
-                     engine=nat.ENGINE_AUTO, **params):
-    """Bootstrap particle filter (R/bootstrap_filter.R:129-171).  Model parameters travel by name in **params."""
+                     engine=nat.ENGINE_AUTO, carry_weights=False, **params):
+    """Bootstrap particle filter (R/bootstrap_filter.R:129-171).  Model parameters travel by name in **params.
+
+    `carry_weights=True` (not in the reference, a stated deviation) carries the weights over steps that do not resample --
+    standard SMC, where the reference's weights are the current likelihoods only; general kernels."""
     resample_algorithm = _match_arg(resample_algorithm, ("SISAR", "SISR", "SIS"), "resample_algorithm")
     resample_fn = _match_arg(resample_fn, ("stratified", "systematic", "multinomial"), "resample_fn")
     model = resolve_model(init_fn, transition_fn, log_likelihood_fn)
     out = _particle_filter_core(y, num_particles, model, "BPF", resample_algorithm, resample_fn, threshold,
-                                return_particles, obs_times, params, precision, seed, ctx, engine=engine)
+                                return_particles, obs_times, params, precision, seed, ctx, engine=engine, carry_weights=carry_weights)
     return _as_result(out, 0, "BPF", resample_algorithm, return_particles, model.dim)
 
 

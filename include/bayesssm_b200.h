@@ -140,6 +140,9 @@ typedef struct {
   int exact_resampling;   /* 1: cdf bit-exact vs the sequential reference cumsum; 0: plain parallel fp64 scan;
                              -1 => auto (1 for BSSM_F64, 0 for BSSM_F32) */
   int engine;             /* BSSM_ENGINE_AUTO / GENERAL / PERSISTENT / STREAM */
+  int carry_weights;      /* 0: the reference's rule (weights of a step are its likelihoods only, R/particle_filter_core.R:204-209, SURVEY
+                             App. A1); 1: DEVIATION, standard SMC: weights carried over steps that do not resample (BPF / RMPF, general
+                             kernels) */
 } bssm_filter_config;
 
 typedef struct {

@@ -518,6 +518,8 @@ int orc_particle_filter(const orc_filter_config *cfg, const double *y, const dou
   f.N = N;
   const orc_noise_buffers *nb = cfg->noise;
   if (nb && cfg->model == ORC_MODEL_SIR_GILLESPIE) return ORC_ERR_BAD_ARG; /* uniforms on demand: Philox noise only */
+  if (cfg->carry_weights && cfg->algorithm == ORC_APF) return ORC_ERR_BAD_ARG;
+  int resampled_prev = 1;
   /* R/resample_move_filter.R:228-230: RMPF forces SISR */
   int ralg = (cfg->algorithm == ORC_RMPF) ? ORC_SISR : cfg->resample_algorithm;
   /* R/particle_filter_core.R:44-50 */
@@ -598,6 +600,8 @@ int orc_particle_filter(const orc_filter_config *cfg, const double *y, const dou
       for (int j = 0; j < N; j++) { /* :177-183 */
         for (int k = 0; k < d; k++) x[k] = px[(size_t)k * N + j];
         lw[j] = model_loglik(cfg->model, yi, x, theta, prev_t);
+        /* carried-weights mode (not the reference): + log(N w_{t-1}); w is 1/N at the first observation and after a resampling */
+        if (cfg->carry_weights && i > 0 && !resampled_prev) lw[j] = lw[j] + log((double)N * w[j]);
       }
     }
     for (int j = 0; j < N; j++) if (isnan(lw[j])) { status = ORC_ERR_NAN_WEIGHT; goto done; }
@@ -625,6 +629,7 @@ int orc_particle_filter(const orc_filter_config *cfg, const double *y, const dou
     res->ess[i + 1] = ess;
     /* :214-224 */
     int should = (ralg == ORC_SIS) ? 0 : (ralg == ORC_SISR ? 1 : (ess < threshold));
+    resampled_prev = (cfg->algorithm == ORC_RMPF || should);
     if (cfg->algorithm == ORC_RMPF || should) {
       status = do_resample(&f, w, i, 0, anc);
       if (status) goto done;

@@ -95,6 +95,8 @@ typedef struct {
   uint64_t seed;
   uint32_t run_id;
   uint32_t stream;
+  int carry_weights; /* 0: the reference (R/particle_filter_core.R:204-209: a step's weights are its likelihoods only);
+                        1: DEVIATION, weights carried over steps that do not resample (BPF / RMPF) */
 } orc_filter_config;
 
 typedef struct {

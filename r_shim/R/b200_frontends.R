@@ -63,7 +63,8 @@ b200_prior_halfnormal <- function(sigma = 1) c(4, sigma, 0)
 }
 
 .b200_filter <- function(algorithm, y, num_particles, model, obs_times, resample_algorithm, resample_fn,
-                         threshold, return_particles, ..., precision = "f64", engine = "auto") {
+                         threshold, return_particles, ..., precision = "f64", engine = "auto", carry_weights = FALSE) {
+  # carry_weights = TRUE (an extension, not the reference's rule): weights carried over steps that do not resample
   checkmate::assert_count(num_particles, positive = TRUE)
   checkmate::assert_numeric(y, any.missing = FALSE)
   if (is.vector(y)) y <- matrix(y, ncol = 1)
@@ -77,6 +78,7 @@ b200_prior_halfnormal <- function(sigma = 1) c(4, sigma, 0)
               precision = match(precision, c("f32", "f64")) - 1L,
               engine = match(engine, c("auto", "general", "persistent", "stream")) - 1L,
               seed = sample.int(.Machine$integer.max, 1), return_particles = as.integer(return_particles),
+              carry_weights = as.integer(isTRUE(carry_weights)),
               obs_times = if (is.null(obs_times)) NULL else as.integer(obs_times))
   r <- .Call("_bayesSSM_b200_filter", cfg, y, theta)
   out <- list(state_est = r$state_est, ess = r$ess, loglike = r$loglike, loglike_history = r$loglike_history,

@@ -78,6 +78,7 @@ SEXP _bayesSSM_b200_filter(SEXP cfg_, SEXP y_, SEXP theta_) {
   cfg.algorithm = opt_int(cfg_, "algorithm", BSSM_BPF);
   cfg.resample_algorithm = opt_int(cfg_, "resample_algorithm", BSSM_SISAR);
   cfg.resample_fn = opt_int(cfg_, "resample_fn", BSSM_STRATIFIED);
+  cfg.carry_weights = opt_int(cfg_, "carry_weights", 0);   /* extension: standard SMC weights (not the reference's rule) */
   cfg.threshold = opt_real(cfg_, "threshold", -1.0);
   cfg.num_particles = opt_int(cfg_, "num_particles", 0);
   cfg.num_obs = Rf_isMatrix(y_) ? Rf_nrows(y_) : (int)XLENGTH(y_);

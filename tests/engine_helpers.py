@@ -46,7 +46,7 @@ def cdf(ctx, w):
 
 def filter_run(ctx, model, algorithm, resample_algorithm, resample_fn, N, y, theta, threshold=-1.0, obs_times=None,
                noise=None, seed=0, run_id=0, stream_base=0, precision=nat.F64, return_particles=False,
-               want_ancestors=False, exact=-1, engine=nat.ENGINE_AUTO, num_filters=None):
+               want_ancestors=False, exact=-1, engine=nat.ENGINE_AUTO, num_filters=None, carry_weights=False):
     y = _d(y)
     if y.ndim == 1:
         y = y[:, None]
@@ -79,6 +79,7 @@ def filter_run(ctx, model, algorithm, resample_algorithm, resample_fn, N, y, the
     cfg.return_particles = int(return_particles)
     cfg.exact_resampling = exact
     cfg.engine = engine
+    cfg.carry_weights = int(carry_weights)
     out = {"loglike": np.zeros(Cn), "loglike_history": np.zeros((Cn, T)), "ess": np.zeros((Cn, T + 1)),
            "state_est": np.zeros((Cn, T + 1, d)), "status": np.zeros(Cn, dtype=np.int32),
            "early_exit": np.zeros(Cn, dtype=np.int32), "n_resampled": np.zeros(Cn, dtype=np.int32)}

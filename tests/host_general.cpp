@@ -102,6 +102,7 @@ static int run(char** argv) {
   FilterDev f;
   memset(&f, 0, sizeof(f));
   f.C = C; f.N = N; f.T = T; f.dy = 1; f.d = d; f.theta = theta.data(); f.theta_stride = ts; f.y = y.data();
+  f.carry = getenv("EMU_CARRY") ? 1 : 0;        // carried-weights mode (bssm_filter_config::carry_weights)
   f.obs_times = obs_times.empty() ? nullptr : obs_times.data();
   f.stream = stream.data(); f.run_id = runid.data(); f.seed = seed; f.algorithm = algorithm; f.ralg = ralg; f.threshold = threshold;
   f.nblk = std::max(1, std::min(1024, (N + FT_THREADS - 1) / FT_THREADS));

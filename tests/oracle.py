@@ -35,7 +35,7 @@ class FilterConfig(C.Structure):
     _fields_ = [("model", C.c_int), ("algorithm", C.c_int), ("resample_algorithm", C.c_int), ("resample_fn", C.c_int),
                 ("threshold", C.c_double), ("num_particles", C.c_int), ("num_obs", C.c_int), ("dy", C.c_int),
                 ("obs_times", ip), ("return_particles", C.c_int), ("noise", C.POINTER(NoiseBuffers)),
-                ("seed", C.c_uint64), ("run_id", C.c_uint32), ("stream", C.c_uint32)]
+                ("seed", C.c_uint64), ("run_id", C.c_uint32), ("stream", C.c_uint32), ("carry_weights", C.c_int)]
 
 
 class FilterResult(C.Structure):
@@ -170,7 +170,7 @@ def make_noise(model: int, N: int, T: int, n_time: int, rng: np.random.Generator
 
 
 def particle_filter(model, algorithm, resample_algorithm, resample_fn, N, y, theta, threshold=-1.0, obs_times=None,
-                    noise=None, seed=0, run_id=0, stream=0, return_particles=False, want_ancestors=False):
+                    noise=None, seed=0, run_id=0, stream=0, return_particles=False, want_ancestors=False, carry_weights=False):
     y = _d(y)
     if y.ndim == 1:
         y = y[:, None]
@@ -194,6 +194,7 @@ def particle_filter(model, algorithm, resample_algorithm, resample_fn, N, y, the
             setattr(nbs, k, _p(v))
         cfg.noise = C.pointer(nbs)
     cfg.seed, cfg.run_id, cfg.stream = seed, run_id, stream
+    cfg.carry_weights = int(carry_weights)
     res = FilterResult()
     out = {"state_est": np.zeros((T + 1, d)), "ess": np.zeros(T + 1), "loglike_history": np.zeros(T)}
     res.state_est, res.ess, res.loglike_history = _p(out["state_est"]), _p(out["ess"]), _p(out["loglike_history"])

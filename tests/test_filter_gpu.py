@@ -195,3 +195,36 @@ def test_gillespie_sir_rejects_injected_noise(orc, engine):
     noise = orc.make_noise(SIR, 64, 2, 2, np.random.default_rng(0))
     with pytest.raises(Exception):
         eh.filter_run(engine, GIL, 0, 2, 0, 64, y, THETA_GIL, noise=noise)
+
+
+# ---- carried-weights mode (bssm_filter_config::carry_weights): a stated deviation from the reference's weight rule ----
+@pytest.mark.parametrize("model,algorithm,ralg", [(LG, 0, 0), (AR, 0, 2), (SIR, 0, 2), (RWD, 2, 1)])
+def test_carried_weights_match_the_oracle(orc, engine, model, algorithm, ralg):
+    rng = np.random.default_rng(50 + model)
+    T, N = 9, 1200
+    y = sim_y(model, T, rng)
+    noise = orc.make_noise(model, N, T, T, rng)
+    ref = orc.particle_filter(model, algorithm, ralg, 0, N, y, THETA[model], noise=noise, return_particles=True, carry_weights=True)
+    got = eh.filter_run(engine, model, algorithm, ralg, 0, N, y, THETA[model], noise=noise, precision=nat.F64, return_particles=True,
+                        carry_weights=True)
+    assert ref["status"] == 0 and got["status"][0] == 0 and got["n_resampled"][0] == ref["n_resampled"]
+    assert abs(got["loglike"][0] - ref["loglike"]) <= 1e-9 * max(1.0, abs(ref["loglike"]))
+    np.testing.assert_allclose(got["ess"][0], ref["ess"], rtol=1e-8)
+    np.testing.assert_allclose(got["state_est"][0], ref["state_est"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(got["weights_history"][0], ref["weights_history"], rtol=1e-8, atol=1e-300)
+    if ralg != 1 and algorithm == 0:
+        plain = eh.filter_run(engine, model, algorithm, ralg, 0, N, y, THETA[model], noise=noise, precision=nat.F64)
+        assert plain["loglike"][0] != got["loglike"][0]
+
+
+def test_carried_weights_are_refused_where_they_are_not_served(engine):
+    y = sim_y(AR, 5, np.random.default_rng(1))
+    with pytest.raises(Exception, match="carry_weights"):
+        eh.filter_run(engine, AR, 1, 2, 0, 500, y, THETA[AR], carry_weights=True)                      # auxiliary filter
+    for eng in (nat.ENGINE_PERSISTENT, nat.ENGINE_STREAM):
+        with pytest.raises(Exception):
+            eh.filter_run(engine, AR, 0, 2, 0, 5000, y, THETA[AR], precision=nat.F32, engine=eng, carry_weights=True)
+    # AUTO in the throughput precision: served by the general kernels
+    a = eh.filter_run(engine, AR, 0, 2, 0, 50000, y, THETA[AR], seed=4, precision=nat.F32, carry_weights=True)
+    b = eh.filter_run(engine, AR, 0, 2, 0, 50000, y, THETA[AR], seed=4, precision=nat.F32, carry_weights=True, engine=nat.ENGINE_GENERAL)
+    assert a["status"][0] == 0 and a["loglike"][0] == b["loglike"][0]

@@ -25,12 +25,14 @@ def host_general(tmp_path_factory):
                     os.path.join(ROOT, "tests", "host_general.cpp")], check=True)
 
     def run(model, algorithm, N, y, thetas, resample_fn=0, resample_algorithm=2, threshold=-1.0, seed=77, run_id=1, stream_base=5,
-            exact=1, obs_times=None, prefix_tiles=None):
+            exact=1, obs_times=None, prefix_tiles=None, carry=False):
         y = np.ascontiguousarray(y, dtype=np.float64)
         args = [model, algorithm, N, len(y), len(thetas), resample_fn, resample_algorithm, threshold, seed, run_id, stream_base, exact]
         env = dict(os.environ)
         if obs_times is not None:
             env["EMU_OBS_TIMES"] = ",".join(str(int(t)) for t in obs_times)
+        if carry:
+            env["EMU_CARRY"] = "1"
         if prefix_tiles is not None:       # tile totals scanned by k_tile_prefix from this many tiles on (large-input path of the cdf pipeline)
             env["EMU_RS_PREFIX_TILES"] = str(prefix_tiles)
         r = subprocess.run([str(exe)] + [str(a) for a in args], input=y.tobytes() + np.ascontiguousarray(thetas, dtype=np.float64).tobytes(),
@@ -119,3 +121,15 @@ def test_large_input_path_of_the_cdf_pipeline_scans_the_tile_totals_once(orc, ho
     recs = host_general(AR, BPF, 7000, y, thetas, resample_algorithm=1, exact=exact, prefix_tiles=1)
     for c, rec in enumerate(recs):
         check(rec, orc.particle_filter(AR, 0, 1, 0, 7000, y, thetas[c], seed=77, run_id=1, stream=5 + c), tol=1e-9 if exact else 1e-6)
+
+
+@pytest.mark.parametrize("algorithm,ralg", [(BPF, 0), (BPF, 2), (RMPF, 1)])
+def test_carried_weights_mode(orc, host_general, algorithm, ralg):
+    # the deviation mode: weights carried over steps that do not resample (SIS: all of them; SISAR: some; RMPF: none)
+    y = sim_y(LG, 7, np.random.default_rng(31))
+    rec, = host_general(LG, algorithm, 3000, y, [THETA[LG]], resample_algorithm=ralg, carry=True)
+    ref = orc.particle_filter(LG, algorithm, ralg, 0, 3000, y, THETA[LG], seed=77, run_id=1, stream=5, carry_weights=True)
+    check(rec, ref)
+    if ralg == 0:      # and it is a different estimator from the reference's rule
+        plain = orc.particle_filter(LG, algorithm, ralg, 0, 3000, y, THETA[LG], seed=77, run_id=1, stream=5)
+        assert abs(plain["loglike"] - ref["loglike"]) > 1e-3

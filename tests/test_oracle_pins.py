@@ -245,3 +245,26 @@ def test_gillespie_sir_step_has_the_law_of_the_reference_simulation(orc):
     # injected noise buffers cannot serve a data-dependent number of uniforms
     noise = orc.make_noise(3, 16, 1, 1, np.random.default_rng(0))
     assert orc.particle_filter(6, 0, 2, 0, 16, np.array([75.0]), [0.5, 0.2, 500.0, 70.0], noise=noise)["status"] != 0
+
+
+def test_carried_weights_mode_is_standard_importance_sampling(orc):
+    """The optional deviation that fixes SURVEY App. A1: with SIS (never resampling) and the weights carried from step to
+    step, prod_t sum_i W_{t-1,i} g_t(x_i) is plain importance sampling of the likelihood -- it agrees with the exact Kalman
+    value, while the reference's rule (each step's weights are its likelihoods only) gives the product of the marginal means."""
+    rng = np.random.default_rng(3)
+    x, ys = rng.standard_normal(), []
+    for _ in range(6):
+        x = 0.8 * x + rng.standard_normal()
+        ys.append(x + rng.standard_normal())
+    y, th = np.array(ys), [0.8, 1.0, 1.0]
+    exact = orc.kalman_loglik(y, *th)
+    carried = orc.particle_filter(1, 0, 0, 0, 400000, y, th, seed=1, carry_weights=True)
+    plain = orc.particle_filter(1, 0, 0, 0, 400000, y, th, seed=1)
+    assert abs(carried["loglike"] - exact) < 0.05 and abs(plain["loglike"] - exact) > 0.3
+    assert carried["ess"][-1] < plain["ess"][-1]       # the carried weights degenerate, as they must
+    # under SISR every step resamples: the two rules coincide
+    a = orc.particle_filter(1, 0, 1, 0, 5000, y, th, seed=2, carry_weights=True)
+    b = orc.particle_filter(1, 0, 1, 0, 5000, y, th, seed=2)
+    assert a["loglike"] == b["loglike"]
+    # not defined for the auxiliary filter's two-stage weights
+    assert orc.particle_filter(1, 1, 2, 0, 100, y, th, seed=2, carry_weights=True)["status"] != 0
