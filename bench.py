@@ -442,7 +442,13 @@ def main():
         barrier()
     launches = ctx.launch_count() - launches0
     total_ms = float(sum(step_ms))
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        # every rank's own time as well (each runs its own filter, no data-path collective): the spread between the GPUs of a box
+        # is what the max over ranks -- the line's ms_per_step -- loses against one GPU
+        g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([total_ms / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [float(v.item()) for v in g]
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
@@ -495,6 +501,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "particle-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
+        "per_rank_ms": per_rank_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": "persistent filter kernel" if launches / max(args.steps, 1) <= 4 else
