@@ -256,3 +256,28 @@ def test_chain_persistent_kernel_against_oracle_with_dead_filters_and_gaps(orc, 
     y2, th = np.array([0.1, 1e6, 0.2]), [0.8, 1.0, 1e-3]
     got = eh.filter_run(engine, AR, 0, 2, 0, 4096, y2, th, seed=3, num_filters=20, precision=nat.F64, engine=ST)
     assert (got["early_exit"] == 1).all() and (got["loglike"] == -np.inf).all() and (got["status"] == 0).all()
+
+
+def test_pmmh_with_ragged_tuned_particle_counts_on_the_chain_kernel(orc, engine, monkeypatch):
+    # 20 chains: the batched filters of the pilot chain, of .pilot_run's replicates (chains x reps filters) and of the main chain
+    # -- where every chain has its own tuned particle count (FilterDev::n_per, R/pmmh_tuning.R:54-57) -- all run on k_st_chain;
+    # the draws equal those of the launch-per-body form bit for bit, and two of the chains equal the oracle's
+    from test_pmmh_gpu import PRIOR, readme_data
+    rng = np.random.default_rng(77)
+    y = readme_data(10, rng)
+    inits = np.array([[0.8, 1.0, 0.5]] * 20) * (1 + 0.005 * np.arange(20))[:, None]
+    kw = dict(transform=[2, 1, 1], pilot_proposal_sd=[0.1, 0.15, 0.2], pilot_n=64, pilot_m=20, pilot_reps=4, m=25, seed=5)
+    out = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("BSSM_ST_CHAIN", chain)
+        out[chain] = eh.pmmh_run(engine, 0, 0, y, inits, chain_id_base=2, engine=ST, **PRIOR, **kw)
+        assert (out[chain]["status"] == 0).all()
+    a, b = out["1"], out["0"]
+    assert len(set(a["target_n"].tolist())) > 1                      # ragged particle counts in the main phase
+    np.testing.assert_array_equal(a["target_n"], b["target_n"])
+    np.testing.assert_array_equal(a["theta_chain"], b["theta_chain"])
+    np.testing.assert_array_equal(a["loglike_chain"], b["loglike_chain"])
+    for c in (0, 19):
+        ref = orc.pmmh_chain(0, 0, y, inits[c], chain_id=2 + c, **PRIOR, **kw)
+        assert a["target_n"][c] == ref["target_n"]
+        np.testing.assert_allclose(a["theta_chain"][c], ref["theta_chain"], rtol=1e-6, atol=1e-9)
