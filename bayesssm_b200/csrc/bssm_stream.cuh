@@ -451,6 +451,10 @@ inline void st_pdl_wait() {}
 __device__ unsigned long long g_st_chain_wait;   // diagnostics build: cycles spent waiting for the merging block
 #endif
 // ---- barriers between the blocks of ONE filter (chain-persistent kernel k_st_chain; the blocks are co-resident) ----
+// One fence per side and no more: the publisher's release (store or reduction) is the only MEMBAR, the waiter's acquire load brings
+// the L1 invalidation with it (LDG.STRONG.GPU + CCTL.IVALL) -- it is thread 0's, but the L1 is the SM's, and the other threads of
+// the block read nothing between that load and the block barrier that follows it.  (A __threadfence() by every thread on both
+// sides, the first version, was a MEMBAR.SC per warp and barrier: profiles/r2_ab_chain_on_off.txt.)
 #ifndef BSSM_EMU
 __device__ __forceinline__ unsigned int st_ld_acquire(const unsigned int* p) {
   unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -458,28 +462,30 @@ __device__ __forceinline__ unsigned int st_ld_acquire(const unsigned int* p) {
 __device__ __forceinline__ void st_st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_red_release(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 #else
 inline unsigned int st_ld_acquire(const unsigned int* p) { emu_poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_st_release(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void st_red_release(unsigned int* p, unsigned int v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 #endif
 // publish: everything the block wrote (any thread) before the call is visible to a block that has seen the value
 __device__ __forceinline__ void st_chain_publish(unsigned int* p, unsigned int v) {
   __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); st_st_release(p, v); }
+  if (threadIdx.x == 0) st_st_release(p, v);
 }
-// wait until the word reaches v; afterwards every thread of the block reads what the publisher wrote (the fence drops
-// this SM's stale L1 lines: the descriptors live at the same addresses every other observation)
+// wait until the word reaches v; afterwards every thread of the block reads what the publisher wrote (the descriptors live at the
+// same addresses every other observation: the acquire load drops this SM's stale L1 lines)
 __device__ __forceinline__ void st_chain_wait(const unsigned int* p, unsigned int v) {
   if (threadIdx.x == 0) { while ((int)(st_ld_acquire(p) - v) < 0) {} }
   __syncthreads();
-  __threadfence();
 }
 // arrive + wait on a monotonic counter (target = arrivals of all rounds so far)
 __device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned int target) {
   __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); atomicAdd(p, 1u); while ((int)(st_ld_acquire(p) - target) < 0) {} }
+  if (threadIdx.x == 0) { st_red_release(p, 1u); while ((int)(st_ld_acquire(p) - target) < 0) {} }
   __syncthreads();
-  __threadfence();
 }
 
 // shared memory of the two per-observation bodies (the chain-persistent kernel overlays them)
