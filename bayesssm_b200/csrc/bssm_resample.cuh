@@ -258,7 +258,6 @@ __global__ void __launch_bounds__(32) k_chain(Src src, int n, const int* __restr
                                               double* __restrict__ cdf, size_t cdf_stride,
                                               long long* __restrict__ n_serial, const int* __restrict__ enable) {
   __shared__ TileRec srec[32];
-  __shared__ double sval[32];
   __shared__ double s_cstart[32];
   __shared__ int s_use[32];
   __shared__ double s_c;
@@ -293,21 +292,30 @@ __global__ void __launch_bounds__(32) k_chain(Src src, int n, const int* __restr
       if (use < 0) {  // walk the tile in reference order
         int lo = (t0 + j) * RS_TILE, hi = min(nn, lo + RS_TILE);
         serial += hi - lo;
+        // The reference's order, one addition after the other -- but in EVERY lane at once: each lane receives the 32 values by
+        // shuffle and runs the same chain in registers (8 cycles per addition: the fp64 latency), keeping the partial sum that
+        // belongs to its own element.  At N = 2^18 the ~9 tiles in which the running sum changes binade are most of an
+        // exact-mode filter's time (k_chain ~200 us, 4 per APF observation): a single warp hides no latency, so a round costs the
+        // full dependent latency of its source (global load, fp64 exp, two divisions: ~1000 cycles) on top of the additions.
+        // Finer irregular regions than a tile, or helper warps that evaluate the source ahead, would be the next step.
+        double cc = __shfl_sync(0xffffffffu, c, 0);
+        double vnext = lo + lane < hi ? src(seg, lo + lane) : 0.0;
         for (int i0 = lo; i0 < hi; i0 += 32) {
-          int i = i0 + lane;
-          if (i < hi) sval[lane] = src(seg, i);
-          __syncwarp();
-          if (lane == 0) {
-            int m = min(32, hi - i0);
-            for (int k = 0; k < m; k++) {
-              c = (i0 + k == 0) ? sval[k] : c + sval[k];  // c[0] = p[0] (src/resampling.cpp:25)
-              sval[k] = c;
+          const int i = i0 + lane, m = min(32, hi - i0);
+          const double v = vnext;
+          vnext = i + 32 < hi ? src(seg, i + 32) : 0.0;     // the next round's value (load, exp, divisions) under this round's additions
+          double mine = 0.0;
+#pragma unroll
+          for (int k = 0; k < 32; k++) {
+            const double vk = __shfl_sync(0xffffffffu, v, k);
+            if (k < m) {
+              cc = (i0 + k == 0) ? vk : cc + vk;  // c[0] = p[0] (src/resampling.cpp:25)
+              if (k == lane) mine = cc;
             }
           }
-          __syncwarp();
-          if (cdf && i < hi) cdf[(size_t)seg * cdf_stride + i] = sval[lane];
-          __syncwarp();
+          if (cdf && i < hi) cdf[(size_t)seg * cdf_stride + i] = mine;
         }
+        c = cc;
       }
     }
     __syncwarp();
