@@ -295,9 +295,10 @@ __global__ void __launch_bounds__(32) k_chain(Src src, int n, const int* __restr
         // The reference's order, one addition after the other -- but in EVERY lane at once: each lane receives the 32 values by
         // shuffle and runs the same chain in registers (8 cycles per addition: the fp64 latency), keeping the partial sum that
         // belongs to its own element.  At N = 2^18 the ~9 tiles in which the running sum changes binade are most of an
-        // exact-mode filter's time (k_chain ~200 us, 4 per APF observation): a single warp hides no latency, so a round costs the
-        // full dependent latency of its source (global load, fp64 exp, two divisions: ~1000 cycles) on top of the additions.
-        // Finer irregular regions than a tile, or helper warps that evaluate the source ahead, would be the next step.
+        // exact-mode filter's time (k_chain ~200 us, 4 per APF observation).  Measured: a whole block evaluating the tile's values
+        // at once cut the instructions 4x and the time not at all -- what remains is the one-thread map chain over the 256 tiles
+        // (~100 dependent instructions each) and these additions; the next step is to compose the maps of a batch of regular
+        // tiles in the same binade by a warp scan (they are associative) and keep this walk for the batches that fail the check.
         double cc = __shfl_sync(0xffffffffu, c, 0);
         double vnext = lo + lane < hi ? src(seg, lo + lane) : 0.0;
         for (int i0 = lo; i0 < hi; i0 += 32) {
