@@ -150,6 +150,11 @@ static inline unsigned int __ballot_sync(unsigned, int pred) {
   emu_wait(B.wbar[w]);
   return m;
 }
+static inline int __all_sync(unsigned m, int pred) {
+  const unsigned int b = __ballot_sync(m, pred);
+  const int n = emu_block->wbar[threadIdx.x >> 5].expected;
+  return b == (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+}
 static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
 static inline int __reduce_max_sync(unsigned, int v) {
   EmuBlock& B = *emu_block;
