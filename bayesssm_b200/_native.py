@@ -121,6 +121,10 @@ SYMBOLS = {
     "bssm_shard_unique_id": (C.c_int, [C.c_char_p, _vp]),
     "bssm_shard_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, _vp]),
     "bssm_shard_finalize": (C.c_int, [_vp]),
+    "bssm_shard_peer_export": (C.c_int, [_vp, _vp]),
+    "bssm_shard_peer_attach": (C.c_int, [_vp, _vp]),
+    "bssm_shard_peer_detach": (C.c_int, [_vp]),
+    "bssm_shard_peer_active": (C.c_int, [_vp]),
     "bssm_shard_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), c_int_p]),
     "bssm_filter_run_sharded": (C.c_int, [_vp, C.POINTER(FilterConfig), c_double_p, c_double_p, C.c_double,
                                           C.POINTER(FilterResult), c_int_p]),

@@ -83,6 +83,11 @@ struct bssm_ctx {
   std::vector<bssm::UserModelInfo> user_models;
   void* nccl_comm = nullptr;   // ncclComm_t of the shard group (bssm_shard.cu)
   int shard_rank = 0, shard_world = 1;
+  // peer-memory exchange of the sharded filter (bssm_shard_peer_export / _attach): every rank's inbox, mapped here with CUDA IPC
+  void* peer_inbox = nullptr;              // this rank's own allocation
+  void* peer_ptr[16] = {nullptr};          // [world] rank g's inbox as this process sees it (peer_ptr[shard_rank] == peer_inbox)
+  int peer_on = 0;
+  unsigned long long peer_seq = 1;         // next unused sequence number (advances identically on every rank: the calls are collective)
 };
 
 namespace bssm {

@@ -13,6 +13,12 @@
 // Philox streams are keyed by the GLOBAL particle index, so the result is the single-GPU result up to
 // the floating-point summation order of the normaliser (tests/test_shard_gpu.py).
 //
+// The exchange has two forms.  Default after bssm_shard_init: ncclAllGather + a one-thread merge kernel between the two kernels
+// of an observation.  After bssm_shard_peer_export / _attach (every rank maps every rank's 2 x world x 128-byte inbox with CUDA
+// IPC): the merging block of k_st_step stores the record into every peer's inbox over NVLink, polls its own inbox and does the
+// global bookkeeping itself -- compute and collective are one kernel, the host enqueues the same two launches per observation
+// as on one GPU (programmatic dependent launch included).  Both forms sum the same records in the same order: identical results.
+//
 // NCCL is loaded at run time (dlopen), so the library has no link-time dependency on it; the unique
 // id travels through whatever the host already has (torch.distributed in the Python mirror, a file
 // or MPI under R).
@@ -112,8 +118,79 @@ int bssm_shard_init(bssm_ctx* ctx, const char* nccl_lib_path, int rank, int worl
   return BSSM_OK;
 }
 
+// ---- peer-memory exchange (CUDA IPC over NVLink): the per-observation all-gather fused into k_st_step's tail ----
+static void peer_release(bssm_ctx* ctx) {
+  for (int g = 0; g < 16; g++) {
+    if (ctx->peer_ptr[g] && ctx->peer_ptr[g] != ctx->peer_inbox) cudaIpcCloseMemHandle(ctx->peer_ptr[g]);
+    ctx->peer_ptr[g] = nullptr;
+  }
+  if (ctx->peer_inbox) { cudaFree(ctx->peer_inbox); ctx->peer_inbox = nullptr; }
+  ctx->peer_on = 0; ctx->peer_seq = 1;
+  cudaGetLastError();
+}
+
+int bssm_shard_peer_export(bssm_ctx* ctx, void* handle_out_64) {
+  if (!ctx || !handle_out_64) { set_error("bssm_shard_peer_export: null argument"); return BSSM_ERR_BAD_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (ctx->shard_world < 2 || ctx->shard_world > BSSM_PEER_MAX_WORLD) { set_error("bssm_shard_peer_export: needs a shard group of 2 .. %d ranks (bssm_shard_init)", BSSM_PEER_MAX_WORLD); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  BSSM_CK(cudaStreamSynchronize(ctx->stream));
+  peer_release(ctx);
+  const size_t bytes = (size_t)2 * ctx->shard_world * sizeof(StPeerSlot);
+  BSSM_CK(cudaMalloc(&ctx->peer_inbox, bytes));
+  BSSM_CK(cudaMemset(ctx->peer_inbox, 0, bytes));
+  BSSM_CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, ctx->peer_inbox);
+  if (e != cudaSuccess) {
+    set_error("bssm_shard_peer_export: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    peer_release(ctx);
+    return BSSM_ERR_CUDA;
+  }
+  memcpy(handle_out_64, &h, sizeof(h));
+  return BSSM_OK;
+}
+
+int bssm_shard_peer_attach(bssm_ctx* ctx, const void* handles_world_x_64) {
+  if (!ctx || !handles_world_x_64) { set_error("bssm_shard_peer_attach: null argument"); return BSSM_ERR_BAD_ARG; }
+  if (!ctx->peer_inbox) { set_error("bssm_shard_peer_attach: call bssm_shard_peer_export first"); return BSSM_ERR_BAD_ARG; }
+  BSSM_CK(cudaSetDevice(ctx->device));
+  const char* hs = (const char*)handles_world_x_64;
+  for (int g = 0; g < ctx->shard_world; g++) {
+    if (g == ctx->shard_rank) { ctx->peer_ptr[g] = ctx->peer_inbox; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + (size_t)g * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("bssm_shard_peer_attach: cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+      cudaGetLastError();
+      for (int k = 0; k < g; k++) {
+        if (ctx->peer_ptr[k] && ctx->peer_ptr[k] != ctx->peer_inbox) cudaIpcCloseMemHandle(ctx->peer_ptr[k]);
+        ctx->peer_ptr[k] = nullptr;
+      }
+      return BSSM_ERR_CUDA;
+    }
+    ctx->peer_ptr[g] = p;
+  }
+  ctx->peer_seq = 1;
+  ctx->peer_on = 1;
+  return BSSM_OK;
+}
+
+int bssm_shard_peer_detach(bssm_ctx* ctx) {
+  if (!ctx) return BSSM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  peer_release(ctx);
+  return BSSM_OK;
+}
+
+int bssm_shard_peer_active(const bssm_ctx* ctx) { return ctx ? ctx->peer_on : 0; }
+
 int bssm_shard_finalize(bssm_ctx* ctx) {
   if (!ctx) return BSSM_OK;
+  if (ctx->peer_inbox) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); peer_release(ctx); }
   if (ctx->nccl_comm) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);

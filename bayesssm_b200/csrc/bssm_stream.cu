@@ -127,9 +127,18 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 5, (size_t)C, &P.counter));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 6, (size_t)2 * C, &P.res));
   BSSM_TRY(scratch(ctx, SL_ST_BASE + 7, (size_t)2 * C, &P.seg));
+  bool peer = false;
   if (sh) {
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 8, (size_t)C, &P.rec_local));
     BSSM_TRY(scratch(ctx, SL_ST_BASE + 9, (size_t)C * sh->world, &P.rec_all));
+    // the ranks' records travel through peer memory from k_st_step's tail when the group attached its inboxes
+    // (bssm_shard_peer_attach); otherwise ncclAllGather + k_st_merge between the two kernels of an observation
+    peer = ctx->peer_on && sh->world > 1 && sh->world <= BSSM_PEER_MAX_WORLD && C == 1;
+    if (peer) {
+      for (int g = 0; g < sh->world; g++) P.peer[g] = (StPeerSlot*)ctx->peer_ptr[g];
+      P.peer_seq0 = ctx->peer_seq;
+      ctx->peer_seq += (unsigned long long)L.T + 2;
+    }
   }
   if (mn) {
     if (sh) { set_error("streaming engine: multinomial resampling is not available for the particle-sharded filter"); return BSSM_ERR_UNSUPPORTED; }
@@ -173,10 +182,11 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     BSSM_LAUNCH(ctx, "k_st_init");
   }
   const bool may_resample = f.ralg != BSSM_SIS;
-  // one GPU: the two kernels of an observation chain by programmatic dependent launch (the sharded filter has an NCCL call
-  // and a merge kernel between them: ordinary launches there)
+  // the two kernels of an observation chain by programmatic dependent launch -- on one GPU, and for the sharded filter when its
+  // records travel through peer memory from k_st_step's tail (with the NCCL exchange there is an all-gather and a merge kernel
+  // between them: ordinary launches)
   const char* pdl_env = getenv("BSSM_ST_PDL");
-  const bool pdl = !sh && !(pdl_env && atoi(pdl_env) == 0);
+  const bool pdl = (!sh || peer) && !(pdl_env && atoi(pdl_env) == 0);
   if (chain) {
     const int per = chain_slots / P.bpc;     // filters per cooperative launch
     for (int c0 = 0; c0 < C; c0 += per) {
@@ -212,7 +222,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   for (int obs = 0; obs < L.T && !chain; obs++) {
     BSSM_TRY(st_launch(ctx, K.step, grid, ST_THREADS, P, &obs, "k_st_step", pdl && obs > 0));
-    if (sh) {
+    if (sh && !peer) {
       BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
       k_st_merge<<<(C + 127) / 128, 128, 0, st>>>(P, obs);
       BSSM_LAUNCH(ctx, "k_st_merge");
@@ -250,7 +260,7 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
   }
   k_st_flush<TS><<<C, 256, 0, st>>>(P, L.T);
   BSSM_LAUNCH(ctx, "k_st_flush");
-  if (sh) {
+  if (sh && !peer) {
     BSSM_TRY(shard_allgather(ctx, sh, P.rec_local, P.rec_all, (size_t)C * sizeof(StRec)));
     k_st_flush_merge<<<(C + 127) / 128, 128, 0, st>>>(P, L.T);
     BSSM_LAUNCH(ctx, "k_st_flush_merge");

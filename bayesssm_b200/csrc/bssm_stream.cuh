@@ -59,6 +59,11 @@ struct StSeg {
 };
 
 struct StRec { double m, s, q, sx, pend, nan, pad0, pad1; };   // per-rank record (sharded runs)
+// sharded runs, peer-memory exchange: one slot per (parity of the exchange, sending rank) in every rank's inbox.  The sender
+// stores its record into the slot of EVERY rank's inbox over NVLink and releases the slot's sequence word; the receiver polls
+// only its own memory.
+struct StPeerSlot { StRec rec; unsigned long long seq; unsigned long long pad[7]; };
+#define BSSM_PEER_MAX_WORLD 16
 
 // resident threads per SM the two hot kernels are compiled for (register budget = 65536 / this)
 #ifndef BSSM_ST_OCC_STEP
@@ -83,6 +88,8 @@ struct StreamParams {
   int sharded, rank, world;
   StRec* rec_local;        // [C] this rank's record
   StRec* rec_all;          // [world][C] gathered records
+  StPeerSlot* peer[BSSM_PEER_MAX_WORLD];   // sharded, peer-memory exchange: rank g's inbox [2][world] (peer[rank] is this rank's own); else null
+  unsigned long long peer_seq0;            // sequence number of observation 0's exchange (> 0; 0: the exchange is ncclAllGather + k_st_merge)
   int cap;                 // storage capacity (particles) of a row
   int bpc;                 // blocks per filter (k_st_init, k_st_step and k_st_resample share the block -> tile ranges)
   double log_n;            // log(particle count) when every filter has the same count (else NaN: computed on the device)
@@ -488,6 +495,54 @@ __device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned i
   __syncthreads();
 }
 
+// ---- particle-sharded filter: the all-gather of the ranks' records, fused into the kernel that produces them ----------------
+// One thread (the merging block's thread 0) stores the rank's 48 bytes into its slot of every rank's inbox -- peer memory mapped
+// with CUDA IPC, the stores travel over NVLink / NVSwitch -- fences system-wide, releases the slots' sequence words, and then polls
+// the `world` sequence words of its OWN inbox (local HBM / L2) before copying the records to rec_all.  Slots alternate with the
+// parity of the sequence number: a rank can only reach exchange k + 2 after every rank has published exchange k + 1, i.e. after
+// every rank's kernel of exchange k has finished reading.  No kernel of another GPU has to be resident for this one to finish (a
+// peer's record arrives when that peer's own step kernel reaches its tail), so there is no co-scheduling requirement.  A peer that
+// never arrives is a failed job: after BSSM_PEER_TIMEOUT_NS the filter is marked BSSM_ERR_NCCL and dead instead of hanging the GPU.
+#ifndef BSSM_PEER_TIMEOUT_NS
+#define BSSM_PEER_TIMEOUT_NS 8000000000ull
+#endif
+#ifndef BSSM_EMU
+__device__ __forceinline__ unsigned long long st_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long st_globaltimer() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+static __device__ __noinline__ bool st_peer_allgather(const StreamParams& P, int c, const StRec& r, unsigned long long seq) {
+  const int par = (int)(seq & 1ull), W = P.world;
+  for (int g = 0; g < W; g++) {
+    volatile double* d = (volatile double*)&P.peer[g][(size_t)par * W + P.rank].rec;
+    d[0] = r.m; d[1] = r.s; d[2] = r.q; d[3] = r.sx; d[4] = r.pend; d[5] = r.nan;
+  }
+  __threadfence_system();
+  for (int g = 0; g < W; g++) st_st_release_sys(&P.peer[g][(size_t)par * W + P.rank].seq, seq);
+  const unsigned long long t0 = st_globaltimer();
+  for (int g = 0; g < W; g++) {
+    const StPeerSlot* src = &P.peer[P.rank][(size_t)par * W + g];
+    while (st_ld_acquire_sys(&src->seq) < seq) {
+      if (st_globaltimer() - t0 > BSSM_PEER_TIMEOUT_NS) return false;
+    }
+    const volatile double* q = (const volatile double*)&src->rec;
+    StRec o; o.m = q[0]; o.s = q[1]; o.q = q[2]; o.sx = q[3]; o.pend = q[4]; o.nan = q[5]; o.pad0 = o.pad1 = 0.0;
+    P.rec_all[(size_t)g * P.f.C + c] = o;
+  }
+  return true;
+}
+#else
+inline bool st_peer_allgather(const StreamParams&, int, const StRec&, unsigned long long) { return false; }   // emulated ranks run one after the other
+#endif
+static __device__ __forceinline__ void st_peer_failed(const StreamParams& P, int c) {
+  P.f.status[c] = 11 /*BSSM_ERR_NCCL: the exchange between the ranks failed*/; P.f.alive[c] = 0;
+}
+
 // shared memory of the two per-observation bodies (the chain-persistent kernel overlays them)
 template <typename Real, int THREADS> struct StStepSmem {
   uint4 pf[2][2 * THREADS];
@@ -685,7 +740,20 @@ __device__ __forceinline__ int st_step_body(const StreamParams& P, int obs, int 
   st_local_merge<Real, ST_THREADS>(P, c, L.nb, nb_pending, s_red, r);
   const long long t_merge = (!PERSIST && P.dbg) ? clock64() : 0;
   if (tid == 0) P.counter[c] = 0u;
-  if (P.sharded) { if (tid == 0) P.rec_local[c] = r; }
+  if (P.sharded) {
+    if (tid == 0) {
+      bool fused = false;
+      if constexpr (!PERSIST) {   // (the chain-persistent kernel never runs sharded: its text stays free of this branch)
+        if (P.peer_seq0) {   // the exchange and the global bookkeeping in this kernel's tail (k_st_merge's work)
+          fused = true;
+          if (st_peer_allgather(P, c, r, P.peer_seq0 + (unsigned long long)obs))
+            st_global(P, c, obs, P.rec_all + c, f.C, P.world, P.rank, L.goff, L.nloc, ST_ALL_ROLES);
+          else st_peer_failed(P, c);
+        }
+      }
+      if (!fused) P.rec_local[c] = r;
+    }
+  }
   else if (lane == 0 && wid < 3) st_global(P, c, obs, &r, 0, 1, 0, L.goff, L.nloc, 1 << wid);   // three roles on three warps
   if constexpr (PERSIST) st_chain_publish(&P.epoch[c], (unsigned int)(obs + 1));
   else if (P.dbg && tid == 0) { P.dbg[0] = t_tick - t_start; P.dbg[1] = t_merge - t_tick; P.dbg[2] = clock64() - t_merge; P.dbg[7] = t_merge - P.dbg[7]; P.dbg[6] = P.dbg[6] - P.dbg[5]; P.dbg[5] = P.dbg[5] - P.dbg[4]; P.dbg[4] = P.dbg[4] - t_tick; }
@@ -1317,7 +1385,18 @@ static __global__ void __launch_bounds__(256) k_st_flush(StreamParams P, int obs
     double t = 0.0;
     for (int w = 0; w < ST_NW; w++) t += s_red[w];
     const int n = P.n_glob ? P.n_glob : filt_n(f, c);
-    if (P.sharded) { StRec r; r.m = 0; r.s = 0; r.q = 0; r.sx = 0; r.pend = t; r.nan = rprev ? 1.0 : 0.0; r.pad0 = r.pad1 = 0; P.rec_local[c] = r; }
+    if (P.sharded) {
+      StRec r; r.m = 0; r.s = 0; r.q = 0; r.sx = 0; r.pend = t; r.nan = rprev ? 1.0 : 0.0; r.pad0 = r.pad1 = 0;
+      if (P.peer_seq0) {   // k_st_flush_merge's work, after the same fused exchange as in k_st_step
+        if (!st_peer_allgather(P, c, r, P.peer_seq0 + (unsigned long long)obs)) st_peer_failed(P, c);
+        else if (rprev) {
+          double tt = 0.0;
+          for (int g = 0; g < P.world; g++) tt += P.rec_all[(size_t)g * f.C + c].pend;
+          if (obs == 0) f.ess[(size_t)c * (f.T + 1)] = (double)P.n_glob;
+          f.state_est[(size_t)c * (f.T + 1) + obs] = tt / (double)P.n_glob;
+        }
+      } else P.rec_local[c] = r;
+    }
     else if (rprev) {
       if (obs == 0) f.ess[(size_t)c * (f.T + 1)] = (double)n;
       f.state_est[(size_t)c * (f.T + 1) + obs] = t / (double)n;

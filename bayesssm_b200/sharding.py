@@ -2,7 +2,9 @@
 of one box, one process per GPU (third row; C ABI: bssm_shard_* / bssm_filter_run_sharded).
 
 Per observation the ranks exchange one 64-byte record (local max log-weight, sum e, sum e^2, sum e*x,
-pending state sum) with ncclAllGather; every rank derives the same global normaliser / ESS / decision and
+pending state sum) -- through peer memory from inside the propagate / weight kernel when the ranks could
+map each other's inboxes with CUDA IPC (`ShardGroup.exchange == "peer"`, the default on one box), else with
+ncclAllGather between the kernels; every rank derives the same global normaliser / ESS / decision and
 its own cdf offset (exclusive prefix of the per-rank weight totals), and resamples the offspring of its
 own particles -- the output slots [F(A_g / S), F(A_{g+1} / S)).  No particle crosses NVLink.
 
@@ -48,7 +50,8 @@ def partition(n: int, world: int, rank: int):
 class ShardGroup:
     """The engine's NCCL communicator over the ranks of torch.distributed's default group."""
 
-    def __init__(self, ctx: nat.Context, rank: int | None = None, world: int | None = None, device=None):
+    def __init__(self, ctx: nat.Context, rank: int | None = None, world: int | None = None, device=None,
+                 exchange: str | None = None):
         import torch
         import torch.distributed as dist
         self.ctx = ctx
@@ -70,9 +73,58 @@ class ShardGroup:
             raw = bytes(t.cpu().tolist())
             uid = (C.c_ubyte * 128).from_buffer_copy(raw)
         nat.check(ctx.lib.bssm_shard_init(ctx.handle, cpath, self.rank, self.world, uid))
+        self.exchange = "nccl" if self.world > 1 else "none"
+        self.exchange_note = ""
+        if exchange is None:
+            exchange = os.environ.get("BSSM_SHARD_EXCHANGE", "peer")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        if self.world > 1 and exchange == "peer":
+            self._attach_peers(device)
+
+    def _attach_peers(self, device):
+        """The per-observation exchange through peer memory (CUDA IPC over NVLink, fused into the filter kernel) instead
+        of ncclAllGather.  All ranks attach or none does: the outcome of every stage is agreed with an all_reduce(MIN)."""
+        import torch
+        import torch.distributed as dist
+        lib, h = self.ctx.lib, self.ctx.handle
+
+        def agreed(ok: bool) -> bool:
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+            if device is not None:
+                t = t.to(device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(int(t.cpu()[0]))
+
+        mine = (C.c_ubyte * 64)()
+        st = lib.bssm_shard_peer_export(h, mine)
+        note = "" if st == nat.OK else nat.last_error()
+        if not agreed(st == nat.OK):
+            lib.bssm_shard_peer_detach(h)
+            self.exchange_note = "peer export failed on a rank: " + (note or "another rank")
+            return
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t)
+        raw = b"".join(bytes(q.cpu().tolist()) for q in parts)
+        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(raw)
+        st = lib.bssm_shard_peer_attach(h, buf)
+        note = "" if st == nat.OK else nat.last_error()
+        if not agreed(st == nat.OK):
+            lib.bssm_shard_peer_detach(h)
+            self.exchange_note = "peer attach failed on a rank: " + (note or "another rank")
+            return
+        self.exchange = "peer"
 
     def close(self):
         if self.ctx is not None and self.ctx.handle:
+            if self.exchange == "peer":
+                import torch.distributed as dist
+                self.ctx.lib.bssm_shard_peer_detach(self.ctx.handle)   # waits for this rank's stream
+                if dist.is_initialized():
+                    dist.barrier()                                        # nobody frees an inbox a peer still has mapped
             self.ctx.lib.bssm_shard_finalize(self.ctx.handle)
         self.ctx = None
 

@@ -13,8 +13,8 @@ The same line carries three more blocks, measured in the same run (skip them wit
   "pmmh"     BASELINE configs[4]: 1024 chains x N=65536 x T=1000, the chains SHARDED over the N ranks by global id, one
              final NCCL gather of the draws (strong scaling): iterations/s, particle-timesteps/s, roofline fraction
              from the run's own resampling count
-  "sharded"  ONE filter of 2^28 particles, its particles sharded over the N ranks (one 64-byte ncclAllGather per
-             observation; strong scaling), with an inline parity check: a small f64 filter run sharded and on one
+  "sharded"  ONE filter of 2^28 particles, its particles sharded over the N ranks (one all-gather of a 64-byte record per
+             observation, fused into the filter kernel through peer memory -- BSSM_SHARD_EXCHANGE=nccl: ncclAllGather; strong scaling), with an inline parity check: a small f64 filter run sharded and on one
              GPU must agree to 1e-9
   "f64"      configs[1] in the reference's own precision (fp64 throughout) on the persistent kernel
 `--workload pmmh|sharded` times one of them alone as the line's `value`.  Prints ONE JSON line on rank 0.
@@ -253,7 +253,7 @@ def run_pmmh_workload(args, ctx, rank, local_rank, world, steps=None, warmup=Non
 
 def run_sharded_workload(args, ctx, rank, local_rank, world, steps=None, warmup=None, parity=False):
     """One bootstrap filter of `--shard-N` particles (default 2^28) sharded over the ranks (third row):
-    per observation ONE ncclAllGather of a 64-byte record; no particle crosses NVLink.  Strong scaling: the
+    per observation ONE all-gather of a 64-byte record (config.exchange says how); no particle crosses NVLink.  Strong scaling: the
     filter is fixed, the ranks split its particles.  A step is one whole filter of `--shard-T` observations."""
     import torch
     import torch.distributed as dist
@@ -265,6 +265,9 @@ def run_sharded_workload(args, ctx, rank, local_rank, world, steps=None, warmup=
     y = simulate_y(T)
     grp = S.ShardGroup(ctx, rank=rank, world=world, device=torch.device("cuda", local_rank) if world > 1 else None)
     m = models.nonlinear_ar()
+    exch_text = {"peer": "fused into the filter kernel: stores into every rank's inbox through CUDA-IPC peer memory over NVLink",
+                 "nccl": "ncclAllGather + merge kernel between the filter's two kernels" + (f" [{grp.exchange_note}]" if grp.exchange_note else ""),
+                 "none": "one rank: no exchange"}[grp.exchange]
 
     def run(seed):
         return S.sharded_bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp,
@@ -305,8 +308,8 @@ def run_sharded_workload(args, ctx, rank, local_rank, world, steps=None, warmup=
             "steps": steps, "warmup": warmup, "ms_per_step": tot / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"ONE bootstrap filter nonlinear-AR N={N} T={T} SISAR threshold=0.5N {args.resample_fn}, particles "
-                                   f"sharded over {world} GPU(s), one ncclAllGather of a 64-byte record per observation",
-                       "N": N, "T": T, "engine": "stream (sharded)", "capacity_factor": args.capacity_factor,
+                                   f"sharded over {world} GPU(s), one all-gather of a 64-byte record per observation ({exch_text})",
+                       "N": N, "T": T, "engine": "stream (sharded)", "exchange": grp.exchange, "capacity_factor": args.capacity_factor,
                        "l2": "working set (8 B/particle x 2 buffers per rank) far larger than L2"},
             "e2e": {"value": N * T * steps / (tot_e2e * 1e-3), "unit": "particle-timesteps/s",
                     "h2d_bytes_per_step": 8 * T + 24, "d2h_bytes_per_step": 8 * (3 * T + 3) + 12},

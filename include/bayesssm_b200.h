@@ -196,6 +196,16 @@ int bssm_filter_run_device(bssm_ctx *ctx, const bssm_filter_config *cfg, const d
 int bssm_shard_unique_id(const char *nccl_lib_path, void *id_out_128);
 int bssm_shard_init(bssm_ctx *ctx, const char *nccl_lib_path, int rank, int world, const void *id_128);
 int bssm_shard_finalize(bssm_ctx *ctx);
+/* Optional, after bssm_shard_init on every rank: move the per-observation exchange from ncclAllGather into the filter
+ * kernel itself.  Each rank exports a 64-byte CUDA IPC handle of its inbox, the host gathers the `world` handles in rank
+ * order (the same channel that carried the unique id) and every rank attaches them; from then on the merging block of
+ * the propagate / weight kernel stores its record into every rank's inbox over NVLink and polls its own.  Results are
+ * identical to the NCCL form (same records, same summation order).  Collective: all ranks attach, or none does.
+ * bssm_shard_peer_active: 1 while attached.  A peer that never arrives shows as status BSSM_ERR_NCCL after a timeout. */
+int bssm_shard_peer_export(bssm_ctx *ctx, void *handle_out_64);
+int bssm_shard_peer_attach(bssm_ctx *ctx, const void *handles_world_x_64);
+int bssm_shard_peer_detach(bssm_ctx *ctx);
+int bssm_shard_peer_active(const bssm_ctx *ctx);
 /* initial block partition (boundaries at multiples of 4): rank's slice [goff, goff + nloc) */
 int bssm_shard_partition(int n, int world, int rank, int64_t *goff_out, int *nloc_out);
 int bssm_filter_run_sharded(bssm_ctx *ctx, const bssm_filter_config *cfg, const double *y, const double *theta,

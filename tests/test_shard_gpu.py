@@ -1,6 +1,7 @@
 """Particle-sharded single filter on the GPU (bssm_filter_run_sharded).  world = 1 runs in the one-GPU suite and
 exercises the sharded code path (records, merge kernel, layout descriptors) against the oracle; the two-rank
-test needs two GPUs (gpurun --gpus 2) and compares the sharded result with the one-GPU result and the oracle."""
+test needs two GPUs (gpurun --gpus 2) and compares the sharded result with the one-GPU result and the oracle, once
+with the exchange fused into the filter kernel through peer memory and once with ncclAllGather (bit-identical)."""
 import os
 import subprocess
 import sys
@@ -44,59 +45,66 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ctx = nat.Context(lr)
-grp = S.ShardGroup(ctx, device=torch.device("cuda", lr))
-m = models.nonlinear_ar()
-rng = np.random.default_rng(5)
-out = {}
-for name, N, T, rfn, prec in (("small_f64", 6000, 15, "stratified", "f64"), ("sys_f64", 100003, 10, "systematic", "f64"),
-                              ("big_f32", 1 << 22, 12, "stratified", "f32")):
-    y = sim_y(0, T, rng)
-    got = S.sharded_bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp, resample_fn=rfn,
-                                     precision=prec, seed=31, stream=2, phi=0.8, sigma_x=1.0, sigma_y=0.5)
-    counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([got["n_local_final"]], dtype=torch.int64, device="cuda"))
-    assert sum(int(c) for c in counts) == N, (name, [int(c) for c in counts])
-    # every rank holds the same outputs
-    ll = torch.tensor([got["loglike"]], dtype=torch.float64, device="cuda")
-    lls = [torch.zeros_like(ll) for _ in range(world)]
-    dist.all_gather(lls, ll)
-    assert all(float(l) == got["loglike"] for l in lls), name
-    one = eh.filter_run(ctx, 0, 0, 2, 0 if rfn == "stratified" else 1, N, y, THETA[0], seed=31, stream_base=2,
-                        precision=nat.F64 if prec == "f64" else nat.F32, engine=nat.ENGINE_STREAM)
-    if prec == "f64":
-        ref = oracle.particle_filter(0, 0, 2, 0 if rfn == "stratified" else 1, N, y, THETA[0], seed=31, stream=2)
-        assert got["n_resampled"] == ref["n_resampled"] == int(one["n_resampled"][0]), name
-        assert abs(got["loglike"] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"]), name
-        assert abs(got["loglike"] - one["loglike"][0]) <= 1e-9 * abs(ref["loglike"]), name
-        np.testing.assert_allclose(got["ess"], ref["ess"], rtol=1e-6)
-        np.testing.assert_allclose(got["state_est"], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
-    else:
-        assert abs(got["loglike"] - one["loglike"][0]) < 0.05, (name, got["loglike"], one["loglike"][0])
-        np.testing.assert_allclose(got["state_est"], one["state_est"][0][:, 0], atol=0.02)
-    out[name] = got["loglike"]
-# Kalman gate on the sharded path: linear-Gaussian model, SISR, throughput precision, a few seeds
-lg = models.linear_gaussian()
-rng2 = np.random.default_rng(21)
-ylg = sim_y(1, 60, rng2)
-exact = oracle.kalman_loglik(ylg, 0.8, 1.0, 1.0)
-lls = np.array([S.sharded_bootstrap_filter(ylg, 1 << 21, lg.init_fn, lg.transition_fn, lg.log_likelihood_fn, grp,
-                                           resample_algorithm="SISR", precision="f32", seed=200 + s, phi=0.8, sigma_x=1.0,
-                                           sigma_y=1.0)["loglike"] for s in range(5)])
-se = lls.std(ddof=1) / np.sqrt(len(lls))
-assert abs(lls.mean() - exact) < 3 * se + 5e-3, (lls, exact)
-out["kalman_diff"] = float(lls.mean() - exact)
-# capacity overflow is reported, not a crash: a very sharp likelihood piles the offspring on one rank
-y = np.array([0.3, 0.1]); 
-try:
-    S.sharded_bootstrap_filter(y, 1 << 16, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp, resample_algorithm="SISR",
-                               precision="f64", seed=3, capacity_factor=1.0, phi=0.8, sigma_x=1.0, sigma_y=1e-3)
-    overflow = False
-except nat.EngineError as e:
-    overflow = e.status == nat.ERR_CAPACITY
-flags = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-dist.all_gather(flags, torch.tensor([int(overflow)], dtype=torch.int64, device="cuda"))
-assert len({int(f) for f in flags}) == 1, "ranks disagree on the capacity overflow"
-grp.close(); ctx.close()
+results = {}
+for exch in ("peer", "nccl"):   # the fused peer-memory exchange, then ncclAllGather + k_st_merge: same records, same order, same bits
+    grp = S.ShardGroup(ctx, device=torch.device("cuda", lr), exchange=exch)
+    assert grp.exchange == exch, (grp.exchange, grp.exchange_note)
+    assert bool(ctx.lib.bssm_shard_peer_active(ctx.handle)) == (exch == "peer")
+    m = models.nonlinear_ar()
+    rng = np.random.default_rng(5)
+    out = {}
+    for name, N, T, rfn, prec in (("small_f64", 6000, 15, "stratified", "f64"), ("sys_f64", 100003, 10, "systematic", "f64"),
+                                  ("big_f32", 1 << 22, 12, "stratified", "f32")):
+        y = sim_y(0, T, rng)
+        got = S.sharded_bootstrap_filter(y, N, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp, resample_fn=rfn,
+                                         precision=prec, seed=31, stream=2, phi=0.8, sigma_x=1.0, sigma_y=0.5)
+        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([got["n_local_final"]], dtype=torch.int64, device="cuda"))
+        assert sum(int(c) for c in counts) == N, (name, [int(c) for c in counts])
+        # every rank holds the same outputs
+        ll = torch.tensor([got["loglike"]], dtype=torch.float64, device="cuda")
+        lls = [torch.zeros_like(ll) for _ in range(world)]
+        dist.all_gather(lls, ll)
+        assert all(float(l) == got["loglike"] for l in lls), name
+        one = eh.filter_run(ctx, 0, 0, 2, 0 if rfn == "stratified" else 1, N, y, THETA[0], seed=31, stream_base=2,
+                            precision=nat.F64 if prec == "f64" else nat.F32, engine=nat.ENGINE_STREAM)
+        if prec == "f64":
+            ref = oracle.particle_filter(0, 0, 2, 0 if rfn == "stratified" else 1, N, y, THETA[0], seed=31, stream=2)
+            assert got["n_resampled"] == ref["n_resampled"] == int(one["n_resampled"][0]), name
+            assert abs(got["loglike"] - ref["loglike"]) <= 1e-6 * abs(ref["loglike"]), name
+            assert abs(got["loglike"] - one["loglike"][0]) <= 1e-9 * abs(ref["loglike"]), name
+            np.testing.assert_allclose(got["ess"], ref["ess"], rtol=1e-6)
+            np.testing.assert_allclose(got["state_est"], ref["state_est"][:, 0], rtol=1e-6, atol=1e-6)
+        else:
+            assert abs(got["loglike"] - one["loglike"][0]) < 0.05, (name, got["loglike"], one["loglike"][0])
+            np.testing.assert_allclose(got["state_est"], one["state_est"][0][:, 0], atol=0.02)
+        out[name] = got["loglike"]
+    # Kalman gate on the sharded path: linear-Gaussian model, SISR, throughput precision, a few seeds
+    lg = models.linear_gaussian()
+    rng2 = np.random.default_rng(21)
+    ylg = sim_y(1, 60, rng2)
+    exact = oracle.kalman_loglik(ylg, 0.8, 1.0, 1.0)
+    lls = np.array([S.sharded_bootstrap_filter(ylg, 1 << 21, lg.init_fn, lg.transition_fn, lg.log_likelihood_fn, grp,
+                                               resample_algorithm="SISR", precision="f32", seed=200 + s, phi=0.8, sigma_x=1.0,
+                                               sigma_y=1.0)["loglike"] for s in range(5)])
+    se = lls.std(ddof=1) / np.sqrt(len(lls))
+    assert abs(lls.mean() - exact) < 3 * se + 5e-3, (lls, exact)
+    out["kalman_diff"] = float(lls.mean() - exact)
+    # capacity overflow is reported, not a crash: a very sharp likelihood piles the offspring on one rank
+    y = np.array([0.3, 0.1]); 
+    try:
+        S.sharded_bootstrap_filter(y, 1 << 16, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp, resample_algorithm="SISR",
+                                   precision="f64", seed=3, capacity_factor=1.0, phi=0.8, sigma_x=1.0, sigma_y=1e-3)
+        overflow = False
+    except nat.EngineError as e:
+        overflow = e.status == nat.ERR_CAPACITY
+    flags = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([int(overflow)], dtype=torch.int64, device="cuda"))
+    assert len({int(f) for f in flags}) == 1, "ranks disagree on the capacity overflow"
+    results[exch] = dict(out, overflow=overflow)
+    grp.close()
+assert results["peer"] == results["nccl"], results
+ctx.close()
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank, json.dumps(out), "overflow", overflow)
 '''
