@@ -497,7 +497,7 @@ __device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned i
 
 // ---- particle-sharded filter: the all-gather of the ranks' records, fused into the kernel that produces them ----------------
 // One thread (the merging block's thread 0) stores the rank's 48 bytes into its slot of every rank's inbox -- peer memory mapped
-// with CUDA IPC, the stores travel over NVLink / NVSwitch -- fences system-wide, releases the slots' sequence words, and then polls
+// with CUDA IPC, the stores travel over NVLink / NVSwitch -- fences system-wide once, stores the slots' sequence words, and then polls
 // the `world` sequence words of its OWN inbox (local HBM / L2) before copying the records to rec_all.  Slots alternate with the
 // parity of the sequence number: a rank can only reach exchange k + 2 after every rank has published exchange k + 1, i.e. after
 // every rank's kernel of exchange k has finished reading.  No kernel of another GPU has to be resident for this one to finish (a
@@ -510,8 +510,8 @@ __device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned i
 __device__ __forceinline__ unsigned long long st_ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void st_st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long st_globaltimer() {
   unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
@@ -522,8 +522,8 @@ static __device__ __noinline__ bool st_peer_allgather(const StreamParams& P, int
     volatile double* d = (volatile double*)&P.peer[g][(size_t)par * W + P.rank].rec;
     d[0] = r.m; d[1] = r.s; d[2] = r.q; d[3] = r.sx; d[4] = r.pend; d[5] = r.nan;
   }
-  __threadfence_system();
-  for (int g = 0; g < W; g++) st_st_release_sys(&P.peer[g][(size_t)par * W + P.rank].seq, seq);
+  __threadfence_system();   // ONE system-scope fence between the records and the sequence words (a release store per peer would be `world` fences in a row)
+  for (int g = 0; g < W; g++) st_st_relaxed_sys(&P.peer[g][(size_t)par * W + P.rank].seq, seq);
   const unsigned long long t0 = st_globaltimer();
   for (int g = 0; g < W; g++) {
     const StPeerSlot* src = &P.peer[P.rank][(size_t)par * W + g];

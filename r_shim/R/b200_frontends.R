@@ -216,6 +216,10 @@ rhat <- function(chains) .b200_diag(chains, "rhat")
 # every rank: b200_shard_init(rank, world, id); then the collective b200_sharded_bootstrap_filter(...)
 b200_shard_unique_id <- function() .Call("_bayesSSM_b200_shard_unique_id")
 b200_shard_init <- function(rank, world, id = NULL) invisible(.Call("_bayesSSM_b200_shard_init", as.integer(rank), as.integer(world), id))
+# optional, after b200_shard_init on every rank: h <- b200_shard_peer_export(); gather the raw(64) of all ranks in rank order
+# (Rmpi::mpi.allgather, files); b200_shard_peer_attach(do.call(c, handles)) -- the exchange then runs inside the filter kernel
+b200_shard_peer_export <- function() .Call("_bayesSSM_b200_shard_peer_export")
+b200_shard_peer_attach <- function(handles) invisible(.Call("_bayesSSM_b200_shard_peer_attach", handles))
 b200_sharded_bootstrap_filter <- function(y, num_particles, init_fn, transition_fn, log_likelihood_fn,
                                           resample_algorithm = c("SISAR", "SISR", "SIS"),
                                           resample_fn = c("stratified", "systematic"), threshold = NULL,

@@ -237,6 +237,21 @@ SEXP _bayesSSM_b200_shard_init(SEXP rank_, SEXP world_, SEXP id_) {
   if (bssm_shard_init(g_ctx, NULL, rank, world, world > 1 ? RAW(id_) : NULL) != BSSM_OK) Rf_error("%s", bssm_last_error());
   return R_NilValue;
 }
+/* optional: the per-observation exchange through peer memory instead of ncclAllGather (include/bayesssm_b200.h, bssm_shard_peer_*).
+ * .Call("_bayesSSM_b200_shard_peer_export")           every rank, after shard_init: raw(64), to be gathered in rank order
+ * .Call("_bayesSSM_b200_shard_peer_attach", handles)  every rank: raw(64 * world), the handles of ranks 0 .. world - 1 */
+SEXP _bayesSSM_b200_shard_peer_export(void) {
+  SEXP h = PROTECT(Rf_allocVector(RAWSXP, 64));
+  int st = bssm_shard_peer_export(ctx_get(), RAW(h));
+  UNPROTECT(1);
+  if (st != BSSM_OK) Rf_error("%s", bssm_last_error());
+  return h;
+}
+SEXP _bayesSSM_b200_shard_peer_attach(SEXP handles_) {
+  if (TYPEOF(handles_) != RAWSXP || XLENGTH(handles_) % 64 != 0) Rf_error("handles must be the concatenated raw(64) of every rank, in rank order");
+  if (bssm_shard_peer_attach(ctx_get(), RAW(handles_)) != BSSM_OK) Rf_error("%s", bssm_last_error());
+  return R_NilValue;
+}
 SEXP _bayesSSM_b200_shard_filter(SEXP cfg_, SEXP y_, SEXP theta_) {
   bssm_ctx *ctx = ctx_get();
   bssm_filter_config cfg;
@@ -335,6 +350,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bayesSSM_b200_shard_unique_id", (DL_FUNC)&_bayesSSM_b200_shard_unique_id, 0},
     {"_bayesSSM_b200_shard_init", (DL_FUNC)&_bayesSSM_b200_shard_init, 3},
     {"_bayesSSM_b200_shard_filter", (DL_FUNC)&_bayesSSM_b200_shard_filter, 3},
+    {"_bayesSSM_b200_shard_peer_export", (DL_FUNC)&_bayesSSM_b200_shard_peer_export, 0},
+    {"_bayesSSM_b200_shard_peer_attach", (DL_FUNC)&_bayesSSM_b200_shard_peer_attach, 1},
     {NULL, NULL, 0}};
 
 void R_init_bayesSSM(DllInfo *dll) { /* replaces src/RcppExports.cpp:57-60 */
