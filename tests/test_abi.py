@@ -36,6 +36,19 @@ def test_no_cpu_fallback_without_device():
     assert e.value.status == _native.ERR_NO_DEVICE
 
 
+def test_peer_exchange_entry_points_refuse_bad_arguments_without_a_gpu():
+    """bssm_shard_peer_* (the sharded filter's exchange through peer memory): argument errors are reported, not crashes."""
+    import ctypes as C
+    from bayesssm_b200 import _native
+    lib = _native.load_library()
+    buf = (C.c_ubyte * 64)()
+    assert lib.bssm_shard_peer_export(None, buf) == _native.ERR_BAD_ARG
+    assert "peer_export" in _native.last_error()
+    assert lib.bssm_shard_peer_attach(None, buf) == _native.ERR_BAD_ARG
+    assert lib.bssm_shard_peer_active(None) == 0
+    assert lib.bssm_shard_peer_detach(None) == _native.OK
+
+
 def test_host_side_transforms_match_oracle(orc):
     from bayesssm_b200 import _native
     lib = _native.load_library()
