@@ -136,6 +136,9 @@ static int stream_launch(bssm_ctx* ctx, FilterDev& f, const FilterLaunch& L, con
     peer = ctx->peer_on && sh->world > 1 && sh->world <= BSSM_PEER_MAX_WORLD && C == 1;
     if (peer) {
       for (int g = 0; g < sh->world; g++) P.peer[g] = (StPeerSlot*)ctx->peer_ptr[g];
+      const char* to_env = getenv("BSSM_PEER_TIMEOUT_MS");
+      const long long to_ms = to_env ? atoll(to_env) : 0;
+      P.peer_timeout_ns = (unsigned long long)(to_ms > 0 ? to_ms : 30000) * 1000000ull;
       P.peer_seq0 = ctx->peer_seq;
       ctx->peer_seq += (unsigned long long)L.T + 2;
     }

@@ -89,6 +89,7 @@ struct StreamParams {
   StRec* rec_local;        // [C] this rank's record
   StRec* rec_all;          // [world][C] gathered records
   StPeerSlot* peer[BSSM_PEER_MAX_WORLD];   // sharded, peer-memory exchange: rank g's inbox [2][world] (peer[rank] is this rank's own); else null
+  unsigned long long peer_timeout_ns;      // a peer's record that has not arrived after this long fails the filter (BSSM_ERR_NCCL) instead of hanging the GPU
   unsigned long long peer_seq0;            // sequence number of observation 0's exchange (> 0; 0: the exchange is ncclAllGather + k_st_merge)
   int cap;                 // storage capacity (particles) of a row
   int bpc;                 // blocks per filter (k_st_init, k_st_step and k_st_resample share the block -> tile ranges)
@@ -502,10 +503,7 @@ __device__ __forceinline__ void st_chain_arrive_wait(unsigned int* p, unsigned i
 // parity of the sequence number: a rank can only reach exchange k + 2 after every rank has published exchange k + 1, i.e. after
 // every rank's kernel of exchange k has finished reading.  No kernel of another GPU has to be resident for this one to finish (a
 // peer's record arrives when that peer's own step kernel reaches its tail), so there is no co-scheduling requirement.  A peer that
-// never arrives is a failed job: after BSSM_PEER_TIMEOUT_NS the filter is marked BSSM_ERR_NCCL and dead instead of hanging the GPU.
-#ifndef BSSM_PEER_TIMEOUT_NS
-#define BSSM_PEER_TIMEOUT_NS 8000000000ull
-#endif
+// never arrives is a failed job: after P.peer_timeout_ns (30 s; $BSSM_PEER_TIMEOUT_MS) the filter is marked BSSM_ERR_NCCL and dead instead of hanging the GPU.
 #ifndef BSSM_EMU
 __device__ __forceinline__ unsigned long long st_ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
@@ -528,7 +526,7 @@ static __device__ __noinline__ bool st_peer_allgather(const StreamParams& P, int
   for (int g = 0; g < W; g++) {
     const StPeerSlot* src = &P.peer[P.rank][(size_t)par * W + g];
     while (st_ld_acquire_sys(&src->seq) < seq) {
-      if (st_globaltimer() - t0 > BSSM_PEER_TIMEOUT_NS) return false;
+      if (st_globaltimer() - t0 > P.peer_timeout_ns) return false;
     }
     const volatile double* q = (const volatile double*)&src->rec;
     StRec o; o.m = q[0]; o.s = q[1]; o.q = q[2]; o.sx = q[3]; o.pend = q[4]; o.nan = q[5]; o.pad0 = o.pad1 = 0.0;

@@ -170,6 +170,8 @@ def sharded_bootstrap_filter(y, num_particles, init_fn, transition_fn, log_likel
                                               C.byref(n_local)))
     if out["status"][0] == nat.ERR_CAPACITY:
         raise nat.EngineError(nat.ERR_CAPACITY, "a rank's share of the offspring outgrew its storage; raise capacity_factor")
+    if out["status"][0] == nat.ERR_NCCL:
+        raise nat.EngineError(nat.ERR_NCCL, "a rank's record never arrived (peer-memory exchange timed out): the group is out of step, re-create it")
     if out["status"][0] == nat.ERR_NAN_WEIGHT:
         raise ValueError("missing value where TRUE/FALSE needed")
     se = out["state_est"][0]

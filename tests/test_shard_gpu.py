@@ -104,6 +104,27 @@ for exch in ("peer", "nccl"):   # the fused peer-memory exchange, then ncclAllGa
     results[exch] = dict(out, overflow=overflow)
     grp.close()
 assert results["peer"] == results["nccl"], results
+# a peer that never arrives is an error after the timeout, not a hung GPU: rank 1 stays out of one collective call
+os.environ["BSSM_PEER_TIMEOUT_MS"] = "400"
+grp = S.ShardGroup(ctx, device=torch.device("cuda", lr), exchange="peer")
+timed_out = True
+if rank == 0:
+    try:
+        S.sharded_bootstrap_filter(sim_y(0, 6, np.random.default_rng(1)), 6000, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp,
+                                   precision="f64", seed=1, phi=0.8, sigma_x=1.0, sigma_y=0.5)
+        timed_out = False
+    except nat.EngineError as e:
+        timed_out = e.status == nat.ERR_NCCL
+assert timed_out
+dist.barrier()
+grp.close()
+del os.environ["BSSM_PEER_TIMEOUT_MS"]
+# ... and a fresh group works again
+grp = S.ShardGroup(ctx, device=torch.device("cuda", lr), exchange="peer")
+again = S.sharded_bootstrap_filter(sim_y(0, 15, np.random.default_rng(5)), 6000, m.init_fn, m.transition_fn, m.log_likelihood_fn, grp,
+                                   precision="f64", seed=31, stream=2, phi=0.8, sigma_x=1.0, sigma_y=0.5)
+assert again["loglike"] == results["peer"]["small_f64"], (again["loglike"], results["peer"]["small_f64"])
+grp.close()
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank, json.dumps(out), "overflow", overflow)
