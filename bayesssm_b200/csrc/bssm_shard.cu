@@ -119,8 +119,9 @@ int bssm_shard_init(bssm_ctx* ctx, const char* nccl_lib_path, int rank, int worl
 }
 
 // ---- peer-memory exchange (CUDA IPC over NVLink): the per-observation all-gather fused into k_st_step's tail ----
+static_assert(BSSM_PEER_MAX_WORLD == sizeof(((bssm_ctx*)nullptr)->peer_ptr) / sizeof(void*), "bssm_ctx::peer_ptr holds one pointer per rank of the largest group");
 static void peer_release(bssm_ctx* ctx) {
-  for (int g = 0; g < 16; g++) {
+  for (int g = 0; g < BSSM_PEER_MAX_WORLD; g++) {
     if (ctx->peer_ptr[g] && ctx->peer_ptr[g] != ctx->peer_inbox) cudaIpcCloseMemHandle(ctx->peer_ptr[g]);
     ctx->peer_ptr[g] = nullptr;
   }
